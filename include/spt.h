@@ -1,0 +1,256 @@
+/* spt.h — C ABI of the B200 spectral path-tracing core (libspt.so).
+ *
+ * This is the drop-in boundary for ONE hot path of scienstanford/pbrt-v2-spectral:
+ *   Renderer::Render (src/core/renderer.h:35-46) as implemented by
+ *   SamplerRenderer::Render / SamplerRendererTask::Run (src/renderers/samplerrenderer.cpp:188-222, :60-164),
+ *   i.e. LDSampler -> PerspectiveCamera::GenerateRayDifferential -> BVHAccel::Intersect/IntersectP ->
+ *   PathIntegrator::Li (+UniformSampleOneLight/EstimateDirect, BSDF::Sample_f/f/Pdf) ->
+ *   SpectralImageFilm::AddSample.
+ * The reference's parser, pbrtApi, Shape/Material/Light/Camera classes and BVH *build* stay on
+ * the CPU; the host side (pbrt_v2_spectral_b200/host/lowering.cpp, compiled against the
+ * reference's own headers) lowers the built Scene into the flat buffers described here and calls
+ * this ABI. The same ABI is bound from Python with ctypes (pbrt_v2_spectral_b200/capi.py).
+ *
+ * Conventions: plain C, caller-owned HOST buffers unless a name ends in _dev, opaque handles,
+ * int status returns (0 = ok, negative = error; text via spt_last_error()), thread-compatible
+ * (not thread-safe) per handle. There is NO CPU fallback: every entry point that computes needs a
+ * CUDA device and fails with SPT_ERR_CUDA otherwise.
+ *
+ * Spectra: SPT_NBANDS floats per spectrum, the reference's SampledSpectrum
+ * (src/core/spectrum.h:41-43, 269-450: 32 bands 395-715 nm as shipped; 30 is a build option).
+ */
+#ifndef SPT_H
+#define SPT_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef SPT_NBANDS
+#define SPT_NBANDS 32
+#endif
+
+#define SPT_OK            0
+#define SPT_ERR_ARG      -1
+#define SPT_ERR_CUDA     -2
+#define SPT_ERR_UNSUPP   -3
+#define SPT_ERR_IO       -4
+
+/* ---- primitive table: one row per slot of BVHAccel::primitives (src/accelerators/bvh.h:58-63),
+ *      i.e. in BVH leaf order (src/accelerators/bvh.cpp:177-182). ---- */
+enum { SPT_PRIM_TRIANGLE = 0, SPT_PRIM_SPHERE = 1, SPT_PRIM_DISK = 2 };
+/* prim_flags bits */
+enum {
+    SPT_PF_FLIP_NORMAL = 1,   /* Shape::ReverseOrientation ^ TransformSwapsHandedness (src/core/diffgeom.cpp:44-46) */
+    SPT_PF_HAS_N       = 2,   /* TriangleMesh::n != NULL  (src/shapes/trianglemesh.cpp:285-289) */
+    SPT_PF_HAS_UV      = 4,   /* TriangleMesh::uvs != NULL (src/shapes/trianglemesh.h:78-92) */
+    SPT_PF_REVERSE     = 8,   /* Shape::ReverseOrientation alone (src/shapes/sphere.cpp:231,250) */
+    SPT_PF_HAS_S       = 16   /* TriangleMesh::s != NULL */
+};
+
+/* Quadric record (sphere: src/shapes/sphere.cpp:31-41; disk: src/shapes/disk.cpp:31-39). */
+typedef struct SptQuadric {
+    int32_t kind;        /* SPT_PRIM_SPHERE / SPT_PRIM_DISK */
+    int32_t xform;       /* row of xforms[] holding ObjectToWorld and its inverse */
+    float radius;        /* sphere radius | disk radius */
+    float zmin, zmax;    /* sphere clipping | disk: zmin = height, zmax = innerRadius */
+    float thetaMin, thetaMax;
+    float phiMax;
+} SptQuadric;
+
+/* ObjectToWorld and WorldToObject as the reference holds them: Transform::m and ::mInv, row-major
+ * (src/core/transform.h:184-241). */
+typedef struct SptXform { float m[16]; float minv[16]; } SptXform;
+
+/* Material table row = the BSDF a reference material builds when all its textures are constant
+ * (de-duplicated by value).
+ *   MATTE   spec0 = Kd.Clamp(), p0 = sigma clamped to [0,90]        (src/materials/matte.cpp:34-60)
+ *   PLASTIC spec0 = Kd.Clamp(), spec1 = Ks.Clamp(), p0 = roughness  (src/materials/plastic.cpp:34-61)
+ *   METAL   spec0 = eta, spec1 = k, p0 = roughness                  (src/materials/metal.cpp:44-68)
+ *   MIRROR  spec0 = Kr.Clamp()                                      (src/materials/mirror.cpp)
+ *   GLASS   spec0 = Kr.Clamp(), spec1 = Kt.Clamp(), p0 = index      (src/materials/glass.cpp)
+ */
+enum { SPT_MAT_MATTE = 0, SPT_MAT_PLASTIC = 1, SPT_MAT_METAL = 2, SPT_MAT_MIRROR = 3, SPT_MAT_GLASS = 4 };
+typedef struct SptMaterial {
+    int32_t type;
+    float p0, p1, p2;
+    float spec0[SPT_NBANDS];
+    float spec1[SPT_NBANDS];
+} SptMaterial;
+
+/* Light table row.
+ *   AREA     spectrum = Lemit; shapes [shape_first, shape_first+shape_count) of light_shapes[]
+ *            (src/lights/diffuse.cpp:61-78, src/core/light.cpp:106-172)
+ *   POINT    spectrum = Intensity; pos = LightToWorld(0,0,0)         (src/lights/point.cpp:34-49)
+ *   INFINITE spectrum unused (already folded into the texels); env map + Distribution2D tables
+ *            in the scene desc; xform = LightToWorld                 (src/lights/infinite.cpp:60-226)
+ */
+enum { SPT_LIGHT_AREA = 0, SPT_LIGHT_POINT = 1, SPT_LIGHT_INFINITE = 2 };
+typedef struct SptLight {
+    int32_t type;
+    int32_t shape_first, shape_count;
+    int32_t xform;
+    float pos[3];
+    float sum_area;                 /* ShapeSet::sumArea as the reference accumulated it */
+    float spectrum[SPT_NBANDS];
+} SptLight;
+
+/* One entry of a ShapeSet (src/core/light.cpp:106-128): a refined, intersectable shape. */
+typedef struct SptLightShape {
+    int32_t kind;        /* SPT_PRIM_* */
+    int32_t flags;       /* SPT_PF_* */
+    int32_t data;        /* triangle: index into tri_vidx/3 ; quadric: row of quadrics[] */
+    float area;          /* Shape::Area() as the reference computed it */
+} SptLightShape;
+
+/* Tables of SampledSpectrum statics the path needs (src/core/spectrum.h:297-351,417-422;
+ * src/core/spectrum.cpp:136-176). Order of rgb_illum: White,Cyan,Magenta,Yellow,Red,Green,Blue. */
+typedef struct SptSpectralTables {
+    float cie_y[SPT_NBANDS];
+    float yint;
+    float rgb_illum[7][SPT_NBANDS];
+} SptSpectralTables;
+
+typedef struct SptSceneDesc {
+    int32_t nbands;                 /* must equal SPT_NBANDS of the library */
+    /* BVHAccel::nodes, reference layout (src/accelerators/bvh.cpp:105-115), n_nodes * 32 bytes */
+    uint32_t n_nodes;
+    const void *bvh_nodes;
+    /* per BVH slot */
+    uint32_t n_prims;
+    const uint8_t  *prim_kind;      /* SPT_PRIM_* */
+    const uint8_t  *prim_flags;     /* SPT_PF_* */
+    const uint32_t *prim_id;        /* Primitive::primitiveId (src/core/primitive.cpp:32,155-169) */
+    const uint32_t *prim_data;      /* triangle: triangle number ; quadric: row of quadrics[] */
+    const int32_t  *prim_material;  /* row of materials[] */
+    const int32_t  *prim_light;     /* row of lights[] or -1 (GeometricPrimitive::areaLight) */
+    const int32_t  *prim_xform;     /* row of xforms[] (Shape::ObjectToWorld) */
+    /* triangle geometry: world-space P (src/shapes/trianglemesh.cpp:61-63), object-space N,S */
+    uint32_t n_tris;
+    const int32_t *tri_vidx;        /* 3 per triangle, into the vertex arrays below */
+    uint32_t n_verts;
+    const float *P;                 /* 3 per vertex */
+    const float *N;                 /* 3 per vertex (zeros where the mesh has none) */
+    const float *UV;                /* 2 per vertex (unused where the mesh has none) */
+    uint32_t n_quadrics;   const SptQuadric *quadrics;
+    uint32_t n_xforms;     const SptXform *xforms;
+    uint32_t n_materials;  const SptMaterial *materials;
+    uint32_t n_lights;     const SptLight *lights;
+    uint32_t n_light_shapes; const SptLightShape *light_shapes;
+    SptSpectralTables tables;
+    /* infinite light (at most one): MIPMap level 0 texels RGB (src/core/mipmap.h), and the
+     * Distribution2D built by the reference (src/lights/infinite.cpp:80-96): func rows [h][w],
+     * cdf rows [h][w+1], per-row integrals [h], marginal func [h], marginal cdf [h+1]. */
+    int32_t env_w, env_h;
+    const float *env_rgb;
+    const float *env_func, *env_cdf, *env_func_int;
+    const float *env_marg_func, *env_marg_cdf;
+    float env_marg_int;
+} SptSceneDesc;
+
+/* PerspectiveCamera (src/cameras/perspective.cpp:33-106, src/core/camera.cpp:84-103). */
+typedef struct SptCameraDesc {
+    float raster_to_camera[16];     /* ProjectiveCamera::RasterToCamera.m, row-major */
+    float camera_to_world[16];      /* CameraToWorld.startTransform->m (static scenes) */
+    float lens_radius, focal_distance;
+    float shutter_open, shutter_close;
+} SptCameraDesc;
+
+/* SpectralImageFilm (src/film/spectralImage.cpp:40-75,176-194). */
+typedef struct SptFilmDesc {
+    int32_t x_resolution, y_resolution;
+    int32_t x_pixel_start, y_pixel_start, x_pixel_count, y_pixel_count;
+    float filter_xwidth, filter_ywidth, filter_inv_xwidth, filter_inv_ywidth;
+    float filter_table[256];        /* 16x16, row = y (src/film/spectralImage.cpp:55-66) */
+} SptFilmDesc;
+
+/* What SamplerRenderer + LDSampler + PathIntegrator are configured with. */
+typedef struct SptRenderParams {
+    int32_t spp;                    /* LDSampler::nPixelSamples (power of two) */
+    int32_t max_depth;              /* PathIntegrator::maxDepth (src/integrators/path.cpp:118-121) */
+    int32_t x_start, x_end, y_start, y_end;   /* sample extent (Film::GetSampleExtent) */
+    uint64_t seed;
+    int32_t tile_rank, tile_nranks; /* image tile set of this GPU: tiles t with t % nranks == rank */
+    int32_t tile_size;              /* tile edge in pixels (0 = default 32) */
+    int32_t wave_pixels;            /* pixels per wavefront (0 = default) */
+    int32_t skip_border;            /* 1: skip the sample-extent border column/row whose samples the
+                                       box filter rejects */
+} SptRenderParams;
+
+typedef struct SptStats {
+    uint64_t camera_samples;        /* samples traced */
+    uint64_t closest_rays, any_rays;
+    uint64_t node_visits, prim_tests;     /* only when counters are enabled */
+    uint64_t kernel_launches;
+    double   render_ms;             /* CUDA-event time of the last spt_render */
+    double   trace_ms;              /* CUDA-event time of the last spt_trace_* kernel */
+} SptStats;
+
+typedef struct SptScene SptScene;
+typedef struct SptFilm  SptFilm;
+
+int         spt_nbands(void);
+const char *spt_last_error(void);
+int         spt_device_count(void);
+int         spt_set_device(int ordinal);
+
+/* Scene: uploads every table to HBM (replaces nothing in the reference; it is the hand-off). */
+SptScene *spt_scene_create(const SptSceneDesc *desc);
+void      spt_scene_destroy(SptScene *scene);
+int       spt_scene_enable_counters(SptScene *scene, int on);
+int       spt_get_stats(SptScene *scene, SptStats *out);
+
+/* K1: PerspectiveCamera::GenerateRayDifferential (src/cameras/perspective.cpp:73-106).
+ * samples: n x 5 floats {imageX, imageY, lensU, lensV, time}; out_rays: n x 8 {o, d, mint, maxt}. */
+int spt_camera_rays(const SptCameraDesc *cam, const float *samples, uint64_t n, float *out_rays);
+
+/* K2: BVHAccel::Intersect (src/accelerators/bvh.cpp:380-432). rays: n x 8 {o,d,mint,maxt}.
+ * out_slot: BVH slot or 0xffffffff on miss; out_prim_id: Primitive::primitiveId or 0; out_t: ray.maxt
+ * after the call. Any output pointer may be NULL. */
+int spt_trace_closest(SptScene *scene, const float *rays, uint64_t n,
+                      uint32_t *out_slot, uint32_t *out_prim_id, float *out_t);
+/* K3: BVHAccel::IntersectP (src/accelerators/bvh.cpp:435-481). out_hit: 0/1 per ray. */
+int spt_trace_any(SptScene *scene, const float *rays, uint64_t n, uint8_t *out_hit);
+/* Same kernels on buffers already resident in HBM (device pointers), for the timed kernel-only runs. */
+int spt_trace_closest_dev(SptScene *scene, const float *rays_dev, uint64_t n,
+                          uint32_t *out_slot_dev, float *out_t_dev);
+int spt_trace_any_dev(SptScene *scene, const float *rays_dev, uint64_t n, uint8_t *out_hit_dev);
+
+/* SamplerRenderer::Li + PathIntegrator::Li for caller-supplied sample vectors
+ * (src/renderers/samplerrenderer.cpp:225-247, src/integrators/path.cpp:44-115).
+ * samples: n x 37 floats in the reference's Sample memory order {imageX,imageY,lensU,lensV,time,
+ * oneD[0..13], twoD[0..8][2]} (src/core/sampler.cpp:88-117, src/integrators/path.cpp:33-41);
+ * rng: n x n_rng floats consumed in order where the reference draws from RNG (bounces >= 3 and
+ * Russian roulette, src/integrators/path.cpp:82,97; src/core/integrator.cpp:84-99).
+ * out_L: n x SPT_NBANDS radiance BEFORE the NaN/negative/inf guards of
+ * src/renderers/samplerrenderer.cpp:119-133. */
+int spt_shade_samples(SptScene *scene, const SptCameraDesc *cam, int32_t max_depth,
+                      const float *samples, const float *rng, int32_t n_rng, uint64_t n, float *out_L);
+
+/* Film: SpectralImageFilm pixels {c[SPT_NBANDS], weightSum} (src/film/spectralImage.h:74-84). */
+SptFilm *spt_film_create(const SptFilmDesc *desc);
+/* Same, accumulating into caller-provided device memory of
+ * y_pixel_count * x_pixel_count * (SPT_NBANDS+1) floats (e.g. an NCCL buffer). */
+SptFilm *spt_film_create_external(const SptFilmDesc *desc, float *pixels_dev);
+void     spt_film_destroy(SptFilm *film);
+int      spt_film_clear(SptFilm *film);
+/* K7 on caller-supplied samples: SpectralImageFilm::AddSample (src/film/spectralImage.cpp:77-152)
+ * preceded by the radiance guards of src/renderers/samplerrenderer.cpp:119-133.
+ * image_xy: n x 2 {imageX, imageY}; L: n x SPT_NBANDS. */
+int      spt_film_add_samples(SptFilm *film, const SptSpectralTables *tables,
+                              const float *image_xy, const float *L, uint64_t n);
+/* c: [y][x][SPT_NBANDS] un-normalised sums, weight: [y][x]. Either may be NULL. */
+int      spt_film_download(SptFilm *film, float *c, float *weight);
+float   *spt_film_device_ptr(SptFilm *film);   /* [y][x][SPT_NBANDS+1], band SPT_NBANDS = weightSum */
+/* SpectralImageFilm::WriteImage's .dat (src/film/spectralImage.cpp:267-378): two text lines then
+ * [band][x][y] float64. */
+int      spt_film_write_dat(SptFilm *film, const char *path);
+
+/* The whole job: SamplerRenderer::Render without the final WriteImage
+ * (src/renderers/samplerrenderer.cpp:188-222). Accumulates into film. */
+int spt_render(SptScene *scene, const SptCameraDesc *cam, SptFilm *film, const SptRenderParams *params);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPT_H */

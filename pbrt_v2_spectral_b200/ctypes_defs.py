@@ -1,0 +1,68 @@
+"""ctypes mirrors of the plain-C structs in include/spt.h (kept field-for-field in the same order)."""
+import ctypes as C
+
+NBANDS = 32
+
+
+class SptSpectralTables(C.Structure):
+    _fields_ = [("cie_y", C.c_float * NBANDS), ("yint", C.c_float), ("rgb_illum", (C.c_float * NBANDS) * 7)]
+
+
+class SptSceneDesc(C.Structure):
+    _fields_ = [
+        ("nbands", C.c_int32),
+        ("n_nodes", C.c_uint32), ("bvh_nodes", C.c_void_p),
+        ("n_prims", C.c_uint32),
+        ("prim_kind", C.c_void_p), ("prim_flags", C.c_void_p), ("prim_id", C.c_void_p),
+        ("prim_data", C.c_void_p), ("prim_material", C.c_void_p), ("prim_light", C.c_void_p),
+        ("prim_xform", C.c_void_p),
+        ("n_tris", C.c_uint32), ("tri_vidx", C.c_void_p),
+        ("n_verts", C.c_uint32), ("P", C.c_void_p), ("N", C.c_void_p), ("UV", C.c_void_p),
+        ("n_quadrics", C.c_uint32), ("quadrics", C.c_void_p),
+        ("n_xforms", C.c_uint32), ("xforms", C.c_void_p),
+        ("n_materials", C.c_uint32), ("materials", C.c_void_p),
+        ("n_lights", C.c_uint32), ("lights", C.c_void_p),
+        ("n_light_shapes", C.c_uint32), ("light_shapes", C.c_void_p),
+        ("tables", SptSpectralTables),
+        ("env_w", C.c_int32), ("env_h", C.c_int32),
+        ("env_rgb", C.c_void_p), ("env_func", C.c_void_p), ("env_cdf", C.c_void_p),
+        ("env_func_int", C.c_void_p), ("env_marg_func", C.c_void_p), ("env_marg_cdf", C.c_void_p),
+        ("env_marg_int", C.c_float),
+    ]
+
+
+class SptCameraDesc(C.Structure):
+    _fields_ = [("raster_to_camera", C.c_float * 16), ("camera_to_world", C.c_float * 16),
+                ("lens_radius", C.c_float), ("focal_distance", C.c_float),
+                ("shutter_open", C.c_float), ("shutter_close", C.c_float)]
+
+
+class SptFilmDesc(C.Structure):
+    _fields_ = [("x_resolution", C.c_int32), ("y_resolution", C.c_int32),
+                ("x_pixel_start", C.c_int32), ("y_pixel_start", C.c_int32),
+                ("x_pixel_count", C.c_int32), ("y_pixel_count", C.c_int32),
+                ("filter_xwidth", C.c_float), ("filter_ywidth", C.c_float),
+                ("filter_inv_xwidth", C.c_float), ("filter_inv_ywidth", C.c_float),
+                ("filter_table", C.c_float * 256)]
+
+
+class SptRenderParams(C.Structure):
+    _fields_ = [("spp", C.c_int32), ("max_depth", C.c_int32),
+                ("x_start", C.c_int32), ("x_end", C.c_int32), ("y_start", C.c_int32), ("y_end", C.c_int32),
+                ("seed", C.c_uint64),
+                ("tile_rank", C.c_int32), ("tile_nranks", C.c_int32), ("tile_size", C.c_int32),
+                ("wave_pixels", C.c_int32), ("skip_border", C.c_int32)]
+
+
+class SptStats(C.Structure):
+    _fields_ = [("camera_samples", C.c_uint64), ("closest_rays", C.c_uint64), ("any_rays", C.c_uint64),
+                ("node_visits", C.c_uint64), ("prim_tests", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("render_ms", C.c_double), ("trace_ms", C.c_double)]
+
+
+# row sizes of the table structs (bytes), for sanity checks against the container file
+SIZEOF_QUADRIC = 32
+SIZEOF_XFORM = 128
+SIZEOF_MATERIAL = 16 + 2 * 4 * NBANDS
+SIZEOF_LIGHT = 32 + 4 * NBANDS
+SIZEOF_LIGHT_SHAPE = 16

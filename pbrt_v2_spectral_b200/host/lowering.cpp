@@ -1,0 +1,482 @@
+// lowering.cpp — Scene -> flat SoA buffers (include/spt.h). Host side of the drop-in boundary.
+//
+// The reference keeps everything the GPU needs in private members (BVHAccel::nodes/primitives
+// src/accelerators/bvh.h:58-63, GeometricPrimitive::shape/material/areaLight
+// src/core/primitive.h:80-83, Triangle::mesh/v src/shapes/trianglemesh.h:99-101, ...). A
+// maintainer would add `friend struct GpuSceneLowering;` lines; to stay zero-patch this TU is
+// instead compiled with private/protected opened up AFTER all standard headers are included
+// (option ii).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <set>
+#include <sstream>
+#include <string>
+#include <typeinfo>
+#include <vector>
+#include <list>
+#include <pthread.h>
+#include <stdint.h>
+
+#define private public
+#define protected public
+#include "pbrt.h"
+#include "scene.h"
+#include "primitive.h"
+#include "shape.h"
+#include "light.h"
+#include "camera.h"
+#include "film.h"
+#include "filter.h"
+#include "sampler.h"
+#include "integrator.h"
+#include "texture.h"
+#include "mipmap.h"
+#include "montecarlo.h"
+#include "spectrum.h"
+#include "accelerators/bvh.h"
+#include "shapes/trianglemesh.h"
+#include "shapes/sphere.h"
+#include "shapes/disk.h"
+#include "materials/matte.h"
+#include "materials/plastic.h"
+#include "materials/metal.h"
+#include "lights/diffuse.h"
+#include "lights/point.h"
+#include "lights/infinite.h"
+#include "cameras/perspective.h"
+#include "film/spectralImage.h"
+#include "samplers/lowdiscrepancy.h"
+#include "integrators/path.h"
+#include "textures/constant.h"
+#undef private
+#undef protected
+
+#include "lowering.h"
+
+// Same bytes as the reference's file-local LinearBVHNode (src/accelerators/bvh.cpp:105-115).
+struct LoweringBVHNode {
+    float bounds[6];
+    uint32_t offset;        // primitivesOffset (leaf) | secondChildOffset (interior)
+    uint8_t nPrimitives;
+    uint8_t axis;
+    uint8_t pad[2];
+};
+
+LoweredScene::LoweredScene() : env_w(0), env_h(0), env_marg_int(0.f) {
+    memset(&tables, 0, sizeof(tables));
+    memset(&camera, 0, sizeof(camera));
+    memset(&film, 0, sizeof(film));
+    memset(&params, 0, sizeof(params));
+}
+
+template <typename T> static const T *ptr_or_null(const std::vector<T> &v) {
+    return v.empty() ? NULL : &v[0];
+}
+
+SptSceneDesc LoweredScene::Desc() const {
+    SptSceneDesc d;
+    memset(&d, 0, sizeof(d));
+    d.nbands = SPT_NBANDS;
+    d.n_nodes = (uint32_t)(bvh_nodes.size() / 32);
+    d.bvh_nodes = ptr_or_null(bvh_nodes);
+    d.n_prims = (uint32_t)prim_kind.size();
+    d.prim_kind = ptr_or_null(prim_kind);
+    d.prim_flags = ptr_or_null(prim_flags);
+    d.prim_id = ptr_or_null(prim_id);
+    d.prim_data = ptr_or_null(prim_data);
+    d.prim_material = ptr_or_null(prim_material);
+    d.prim_light = ptr_or_null(prim_light);
+    d.prim_xform = ptr_or_null(prim_xform);
+    d.n_tris = (uint32_t)(tri_vidx.size() / 3);
+    d.tri_vidx = ptr_or_null(tri_vidx);
+    d.n_verts = (uint32_t)(P.size() / 3);
+    d.P = ptr_or_null(P);
+    d.N = ptr_or_null(N);
+    d.UV = ptr_or_null(UV);
+    d.n_quadrics = (uint32_t)quadrics.size();
+    d.quadrics = ptr_or_null(quadrics);
+    d.n_xforms = (uint32_t)xforms.size();
+    d.xforms = ptr_or_null(xforms);
+    d.n_materials = (uint32_t)materials.size();
+    d.materials = ptr_or_null(materials);
+    d.n_lights = (uint32_t)lights.size();
+    d.lights = ptr_or_null(lights);
+    d.n_light_shapes = (uint32_t)light_shapes.size();
+    d.light_shapes = ptr_or_null(light_shapes);
+    d.tables = tables;
+    d.env_w = env_w;
+    d.env_h = env_h;
+    d.env_rgb = ptr_or_null(env_rgb);
+    d.env_func = ptr_or_null(env_func);
+    d.env_cdf = ptr_or_null(env_cdf);
+    d.env_func_int = ptr_or_null(env_func_int);
+    d.env_marg_func = ptr_or_null(env_marg_func);
+    d.env_marg_cdf = ptr_or_null(env_marg_cdf);
+    d.env_marg_int = env_marg_int;
+    return d;
+}
+
+bool LoweredScene::Save(const std::string &path, std::string *err) const {
+    SptContainerWriter w;
+    if (!w.begin(path)) { if (err) *err = "cannot open " + path; return false; }
+    int32_t nb = SPT_NBANDS;
+    w.put("nbands", 1, &nb, 4, 1);
+    w.put("bvh_nodes", 0, ptr_or_null(bvh_nodes), bvh_nodes.size(), bvh_nodes.size() / 32, 32);
+    w.vec("prim_kind", 0, prim_kind);
+    w.vec("prim_flags", 0, prim_flags);
+    w.vec("prim_id", 2, prim_id);
+    w.vec("prim_data", 2, prim_data);
+    w.vec("prim_material", 1, prim_material);
+    w.vec("prim_light", 1, prim_light);
+    w.vec("prim_xform", 1, prim_xform);
+    w.vec("tri_vidx", 1, tri_vidx, 3);
+    w.vec("P", 3, P, 3);
+    w.vec("N", 3, N, 3);
+    w.vec("UV", 3, UV, 2);
+    w.pod("quadrics", quadrics);
+    w.pod("xforms", xforms);
+    w.pod("materials", materials);
+    w.pod("lights", lights);
+    w.pod("light_shapes", light_shapes);
+    w.put("tables", 0, &tables, sizeof(tables), 1, sizeof(tables));
+    int32_t envdims[2] = { env_w, env_h };
+    w.put("env_dims", 1, envdims, 8, 2);
+    w.vec("env_rgb", 3, env_rgb);
+    w.vec("env_func", 3, env_func);
+    w.vec("env_cdf", 3, env_cdf);
+    w.vec("env_func_int", 3, env_func_int);
+    w.vec("env_marg_func", 3, env_marg_func);
+    w.vec("env_marg_cdf", 3, env_marg_cdf);
+    w.put("env_marg_int", 3, &env_marg_int, 4, 1);
+    w.put("camera", 0, &camera, sizeof(camera), 1, sizeof(camera));
+    w.put("film", 0, &film, sizeof(film), 1, sizeof(film));
+    w.put("params", 0, &params, sizeof(params), 1, sizeof(params));
+    w.put("film_filename", 0, film_filename.data(), film_filename.size(), film_filename.size());
+    w.end();
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct Lowerer {
+    LoweredScene *out;
+    std::string err;
+    std::map<const Transform *, int> xformIdx;
+    std::map<const TriangleMesh *, std::pair<uint32_t, uint32_t> > meshBase;  // vertex base, tri base
+    std::map<const Shape *, int> quadricIdx;
+    std::map<const Light *, int> lightIdx;
+
+    bool fail(const std::string &why) { err = why; return false; }
+
+    int AddXform(const Transform *o2w) {
+        std::map<const Transform *, int>::iterator it = xformIdx.find(o2w);
+        if (it != xformIdx.end()) return it->second;
+        SptXform x;
+        memcpy(x.m, o2w->m.m, 64);
+        memcpy(x.minv, o2w->mInv.m, 64);
+        out->xforms.push_back(x);
+        int idx = (int)out->xforms.size() - 1;
+        xformIdx[o2w] = idx;
+        return idx;
+    }
+
+    std::pair<uint32_t, uint32_t> AddMesh(const TriangleMesh *mesh) {
+        std::map<const TriangleMesh *, std::pair<uint32_t, uint32_t> >::iterator it = meshBase.find(mesh);
+        if (it != meshBase.end()) return it->second;
+        uint32_t vbase = (uint32_t)(out->P.size() / 3);
+        uint32_t tbase = (uint32_t)(out->tri_vidx.size() / 3);
+        for (int i = 0; i < mesh->nverts; ++i) {
+            out->P.push_back(mesh->p[i].x); out->P.push_back(mesh->p[i].y); out->P.push_back(mesh->p[i].z);
+            if (mesh->n) {
+                out->N.push_back(mesh->n[i].x); out->N.push_back(mesh->n[i].y); out->N.push_back(mesh->n[i].z);
+            } else { out->N.push_back(0.f); out->N.push_back(0.f); out->N.push_back(0.f); }
+            if (mesh->uvs) { out->UV.push_back(mesh->uvs[2*i]); out->UV.push_back(mesh->uvs[2*i+1]); }
+            else { out->UV.push_back(0.f); out->UV.push_back(0.f); }
+        }
+        for (int i = 0; i < 3 * mesh->ntris; ++i)
+            out->tri_vidx.push_back((int32_t)(mesh->vertexIndex[i] + vbase));
+        std::pair<uint32_t, uint32_t> r(vbase, tbase);
+        meshBase[mesh] = r;
+        return r;
+    }
+
+    static uint8_t ShapeFlags(const Shape *s) {
+        uint8_t f = 0;
+        if (s->ReverseOrientation ^ s->TransformSwapsHandedness) f |= SPT_PF_FLIP_NORMAL;
+        if (s->ReverseOrientation) f |= SPT_PF_REVERSE;
+        return f;
+    }
+
+    // kind/flags/data of one intersectable shape; registers meshes, quadrics, transforms
+    bool AddShape(const Shape *shape, uint8_t *kind, uint8_t *flags, uint32_t *data, int32_t *xform) {
+        *flags = ShapeFlags(shape);
+        *xform = AddXform(shape->ObjectToWorld);
+        if (const Triangle *tri = dynamic_cast<const Triangle *>(shape)) {
+            const TriangleMesh *mesh = tri->mesh.GetPtr();
+            if (mesh->alphaTexture.GetPtr())
+                return fail("triangle mesh with an alpha texture is not supported");
+            if (mesh->s) return fail("triangle mesh with explicit tangents S is not supported");
+            std::pair<uint32_t, uint32_t> base = AddMesh(mesh);
+            if (mesh->n) *flags |= SPT_PF_HAS_N;
+            if (mesh->uvs) *flags |= SPT_PF_HAS_UV;
+            *kind = SPT_PRIM_TRIANGLE;
+            *data = base.second + (uint32_t)((tri->v - mesh->vertexIndex) / 3);
+            return true;
+        }
+        std::map<const Shape *, int>::iterator it = quadricIdx.find(shape);
+        if (const Sphere *sp = dynamic_cast<const Sphere *>(shape)) {
+            *kind = SPT_PRIM_SPHERE;
+            if (it == quadricIdx.end()) {
+                SptQuadric q;
+                memset(&q, 0, sizeof(q));
+                q.kind = SPT_PRIM_SPHERE; q.xform = *xform; q.radius = sp->radius;
+                q.zmin = sp->zmin; q.zmax = sp->zmax; q.thetaMin = sp->thetaMin;
+                q.thetaMax = sp->thetaMax; q.phiMax = sp->phiMax;
+                out->quadrics.push_back(q);
+                quadricIdx[shape] = (int)out->quadrics.size() - 1;
+            }
+            *data = (uint32_t)quadricIdx[shape];
+            return true;
+        }
+        if (const Disk *dk = dynamic_cast<const Disk *>(shape)) {
+            *kind = SPT_PRIM_DISK;
+            if (it == quadricIdx.end()) {
+                SptQuadric q;
+                memset(&q, 0, sizeof(q));
+                q.kind = SPT_PRIM_DISK; q.xform = *xform; q.radius = dk->radius;
+                q.zmin = dk->height; q.zmax = dk->innerRadius; q.phiMax = dk->phiMax;
+                out->quadrics.push_back(q);
+                quadricIdx[shape] = (int)out->quadrics.size() - 1;
+            }
+            *data = (uint32_t)quadricIdx[shape];
+            return true;
+        }
+        return fail(std::string("unsupported shape type ") + typeid(*shape).name());
+    }
+
+    template <typename T> bool ConstTex(const Reference<Texture<T> > &tex, T *value, const char *what) {
+        const ConstantTexture<T> *c = dynamic_cast<const ConstantTexture<T> *>(tex.GetPtr());
+        if (!c) return fail(std::string("non-constant texture for ") + what);
+        *value = c->value;
+        return true;
+    }
+
+    // materials whose bump/normal maps are the constant-0 defaults only
+    bool CheckFlat(const Reference<Texture<float> > &bump, const Reference<Texture<Spectrum> > &normal) {
+        float b; Spectrum n;
+        if (!ConstTex(bump, &b, "bumpmap") || !ConstTex(normal, &n, "normalmap")) return false;
+        if (b != 0.f) return fail("non-zero constant bump map");
+        if (!n.IsBlack()) return fail("normal map present");
+        return true;
+    }
+
+    static void CopySpectrum(const Spectrum &s, float *dst) {
+        for (int i = 0; i < nSpectralSamples; ++i) dst[i] = s.c[i];
+    }
+
+    bool AddMaterial(const Material *m, int32_t *idx) {
+        SptMaterial row;
+        memset(&row, 0, sizeof(row));
+        if (const MatteMaterial *mm = dynamic_cast<const MatteMaterial *>(m)) {
+            Spectrum kd; float sig;
+            if (!CheckFlat(mm->bumpMap, mm->normalMap) || !ConstTex(mm->Kd, &kd, "Kd") ||
+                !ConstTex(mm->sigma, &sig, "sigma")) return false;
+            row.type = SPT_MAT_MATTE;
+            CopySpectrum(kd.Clamp(), row.spec0);
+            row.p0 = Clamp(sig, 0.f, 90.f);
+        } else if (const PlasticMaterial *pm = dynamic_cast<const PlasticMaterial *>(m)) {
+            Spectrum kd, ks; float rough;
+            if (!CheckFlat(pm->bumpMap, pm->normalMap) || !ConstTex(pm->Kd, &kd, "Kd") ||
+                !ConstTex(pm->Ks, &ks, "Ks") || !ConstTex(pm->roughness, &rough, "roughness")) return false;
+            row.type = SPT_MAT_PLASTIC;
+            CopySpectrum(kd.Clamp(), row.spec0);
+            CopySpectrum(ks.Clamp(), row.spec1);
+            row.p0 = rough;
+        } else if (const MetalMaterial *me = dynamic_cast<const MetalMaterial *>(m)) {
+            Spectrum eta, k; float rough;
+            if (!CheckFlat(me->bumpMap, me->normalMap) || !ConstTex(me->eta, &eta, "eta") ||
+                !ConstTex(me->k, &k, "k") || !ConstTex(me->roughness, &rough, "roughness")) return false;
+            row.type = SPT_MAT_METAL;
+            CopySpectrum(eta, row.spec0);
+            CopySpectrum(k, row.spec1);
+            row.p0 = rough;
+        } else {
+            return fail(std::string("unsupported material type ") + typeid(*m).name());
+        }
+        for (size_t i = 0; i < out->materials.size(); ++i)
+            if (!memcmp(&out->materials[i], &row, sizeof(row))) { *idx = (int32_t)i; return true; }
+        out->materials.push_back(row);
+        *idx = (int32_t)out->materials.size() - 1;
+        return true;
+    }
+
+    bool AddLights(const Scene *scene) {
+        for (size_t li = 0; li < scene->lights.size(); ++li) {
+            const Light *l = scene->lights[li];
+            SptLight row;
+            memset(&row, 0, sizeof(row));
+            row.xform = -1;
+            if (const DiffuseAreaLight *al = dynamic_cast<const DiffuseAreaLight *>(l)) {
+                row.type = SPT_LIGHT_AREA;
+                CopySpectrum(al->Lemit, row.spectrum);
+                const ShapeSet *ss = al->shapeSet;
+                row.shape_first = (int32_t)out->light_shapes.size();
+                row.shape_count = (int32_t)ss->shapes.size();
+                row.sum_area = ss->sumArea;
+                for (size_t i = 0; i < ss->shapes.size(); ++i) {
+                    SptLightShape s;
+                    uint8_t kind, flags; uint32_t data; int32_t xf;
+                    if (!AddShape(ss->shapes[i].GetPtr(), &kind, &flags, &data, &xf)) return false;
+                    s.kind = kind; s.flags = flags; s.data = (int32_t)data; s.area = ss->areas[i];
+                    out->light_shapes.push_back(s);
+                }
+            } else if (const PointLight *pl = dynamic_cast<const PointLight *>(l)) {
+                row.type = SPT_LIGHT_POINT;
+                CopySpectrum(pl->Intensity, row.spectrum);
+                row.pos[0] = pl->lightPos.x; row.pos[1] = pl->lightPos.y; row.pos[2] = pl->lightPos.z;
+            } else if (const InfiniteAreaLight *il = dynamic_cast<const InfiniteAreaLight *>(l)) {
+                if (out->env_w) return fail("more than one infinite area light");
+                row.type = SPT_LIGHT_INFINITE;
+                row.xform = AddXform(&il->LightToWorld);
+                const MIPMap<RGBSpectrum> *mm = il->radianceMap;
+                if (mm->wrapMode != TEXTURE_REPEAT) return fail("env map wrap mode");
+                const BlockedArray<RGBSpectrum> *lvl0 = mm->pyramid[0];
+                out->env_w = lvl0->uSize(); out->env_h = lvl0->vSize();
+                out->env_rgb.resize((size_t)3 * out->env_w * out->env_h);
+                for (int v = 0; v < out->env_h; ++v)
+                    for (int u = 0; u < out->env_w; ++u) {
+                        float rgb[3];
+                        (*lvl0)(u, v).ToRGB(rgb);
+                        memcpy(&out->env_rgb[3 * ((size_t)v * out->env_w + u)], rgb, 12);
+                    }
+                const Distribution2D *d2 = il->distribution;
+                int nv = (int)d2->pConditionalV.size();
+                int nu = d2->pConditionalV[0]->count;
+                // the distribution is built over the ORIGINAL image size, which the MIPMap may
+                // have resampled to powers of two; the GPU tables carry their own dims
+                if (nu != out->env_w || nv != out->env_h)
+                    return fail("environment map resolution is not a power of two");
+                for (int v = 0; v < nv; ++v) {
+                    const Distribution1D *d1 = d2->pConditionalV[v];
+                    out->env_func.insert(out->env_func.end(), d1->func, d1->func + nu);
+                    out->env_cdf.insert(out->env_cdf.end(), d1->cdf, d1->cdf + nu + 1);
+                    out->env_func_int.push_back(d1->funcInt);
+                }
+                const Distribution1D *dm = d2->pMarginal;
+                out->env_marg_func.assign(dm->func, dm->func + nv);
+                out->env_marg_cdf.assign(dm->cdf, dm->cdf + nv + 1);
+                out->env_marg_int = dm->funcInt;
+            } else {
+                return fail(std::string("unsupported light type ") + typeid(*l).name());
+            }
+            lightIdx[l] = (int)out->lights.size();
+            out->lights.push_back(row);
+        }
+        return true;
+    }
+
+    bool Run(const Scene *scene, const Camera *camera, const Sampler *sampler,
+             const SurfaceIntegrator *surf) {
+        if (scene->volumeRegion) return fail("participating media are not supported");
+        const BVHAccel *bvh = dynamic_cast<const BVHAccel *>(scene->aggregate);
+        if (!bvh) return fail("aggregate is not a BVHAccel");
+        if (!bvh->nodes) return fail("empty BVH");
+        // node count: the depth-first layout makes the tree the range [0, size(root))
+        const LoweringBVHNode *nodes = (const LoweringBVHNode *)bvh->nodes;
+        uint32_t nNodes = 0;
+        {
+            std::vector<uint32_t> todo(1, 0u);
+            while (!todo.empty()) {
+                uint32_t n = todo.back(); todo.pop_back();
+                nNodes = std::max(nNodes, n + 1);
+                if (nodes[n].nPrimitives == 0) { todo.push_back(n + 1); todo.push_back(nodes[n].offset); }
+            }
+        }
+        out->bvh_nodes.assign((const uint8_t *)nodes, (const uint8_t *)nodes + (size_t)nNodes * 32);
+
+        if (!AddLights(scene)) return false;
+
+        size_t np = bvh->primitives.size();
+        for (size_t i = 0; i < np; ++i) {
+            const GeometricPrimitive *gp = dynamic_cast<const GeometricPrimitive *>(bvh->primitives[i].GetPtr());
+            if (!gp) return fail("non-geometric primitive (object instance / animated transform) in the BVH");
+            uint8_t kind, flags; uint32_t data; int32_t xf, mat;
+            if (!AddShape(gp->shape.GetPtr(), &kind, &flags, &data, &xf)) return false;
+            if (!AddMaterial(gp->material.GetPtr(), &mat)) return false;
+            int32_t light = -1;
+            if (gp->areaLight) {
+                std::map<const Light *, int>::iterator it = lightIdx.find(gp->areaLight);
+                if (it == lightIdx.end()) return fail("area light of a primitive is not in scene->lights");
+                light = it->second;
+            }
+            out->prim_kind.push_back(kind); out->prim_flags.push_back(flags);
+            out->prim_id.push_back(gp->primitiveId); out->prim_data.push_back(data);
+            out->prim_material.push_back(mat); out->prim_light.push_back(light);
+            out->prim_xform.push_back(xf);
+        }
+
+        // spectral tables (SampledSpectrum statics, src/core/spectrum.h:297-351)
+        for (int i = 0; i < nSpectralSamples; ++i) out->tables.cie_y[i] = SampledSpectrum::Y.c[i];
+        out->tables.yint = SampledSpectrum::yint;
+        const SampledSpectrum *ill[7] = {
+            &SampledSpectrum::rgbIllum2SpectWhite, &SampledSpectrum::rgbIllum2SpectCyan,
+            &SampledSpectrum::rgbIllum2SpectMagenta, &SampledSpectrum::rgbIllum2SpectYellow,
+            &SampledSpectrum::rgbIllum2SpectRed, &SampledSpectrum::rgbIllum2SpectGreen,
+            &SampledSpectrum::rgbIllum2SpectBlue };
+        for (int k = 0; k < 7; ++k)
+            for (int i = 0; i < nSpectralSamples; ++i) out->tables.rgb_illum[k][i] = ill[k]->c[i];
+
+        // camera
+        const PerspectiveCamera *pc = dynamic_cast<const PerspectiveCamera *>(camera);
+        if (!pc) return fail("camera is not a PerspectiveCamera");
+        if (pc->CameraToWorld.actuallyAnimated) return fail("animated camera");
+        memcpy(out->camera.raster_to_camera, pc->RasterToCamera.m.m, 64);
+        memcpy(out->camera.camera_to_world, pc->CameraToWorld.startTransform->m.m, 64);
+        out->camera.lens_radius = pc->lensRadius;
+        out->camera.focal_distance = pc->focalDistance;
+        out->camera.shutter_open = pc->shutterOpen;
+        out->camera.shutter_close = pc->shutterClose;
+
+        // film
+        const SpectralImageFilm *film = dynamic_cast<const SpectralImageFilm *>(camera->film);
+        if (!film) return fail("film is not a SpectralImageFilm");
+        out->film.x_resolution = film->xResolution; out->film.y_resolution = film->yResolution;
+        out->film.x_pixel_start = film->xPixelStart; out->film.y_pixel_start = film->yPixelStart;
+        out->film.x_pixel_count = film->xPixelCount; out->film.y_pixel_count = film->yPixelCount;
+        out->film.filter_xwidth = film->filter->xWidth; out->film.filter_ywidth = film->filter->yWidth;
+        out->film.filter_inv_xwidth = film->filter->invXWidth;
+        out->film.filter_inv_ywidth = film->filter->invYWidth;
+        memcpy(out->film.filter_table, film->filterTable, 256 * sizeof(float));
+        out->film_filename = film->imageOutputName;
+
+        // sampler + integrator
+        const LDSampler *ld = dynamic_cast<const LDSampler *>(sampler);
+        if (!ld) return fail("sampler is not the low-discrepancy sampler");
+        const PathIntegrator *pi = dynamic_cast<const PathIntegrator *>(surf);
+        if (!pi) return fail("surface integrator is not the path integrator");
+        out->params.spp = ld->nPixelSamples;
+        out->params.max_depth = pi->maxDepth;
+        out->params.x_start = ld->xPixelStart; out->params.x_end = ld->xPixelEnd;
+        out->params.y_start = ld->yPixelStart; out->params.y_end = ld->yPixelEnd;
+        out->params.seed = 0;
+        out->params.tile_rank = 0; out->params.tile_nranks = 1;
+        return true;
+    }
+};
+
+}  // namespace
+
+bool LowerScene(const Scene *scene, const Camera *camera, const Sampler *sampler,
+                const SurfaceIntegrator *surf, LoweredScene *out, std::string *err) {
+    Lowerer L;
+    L.out = out;
+    bool ok = L.Run(scene, camera, sampler, surf);
+    if (!ok && err) *err = L.err;
+    return ok;
+}
