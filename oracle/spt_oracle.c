@@ -3,6 +3,7 @@
  * build with -O2 -ffp-contract=off, never -ffast-math / -march=native — SURVEY.md F8).
  * Every function cites the reference lines it follows (paths relative to /root/reference/src).
  * The product path must never link or load this file. */
+#include <alloca.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>

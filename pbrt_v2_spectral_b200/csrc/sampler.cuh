@@ -1,0 +1,108 @@
+// sampler.cuh — K1's sample generator.
+//
+// The reference's LDSampler (src/samplers/lowdiscrepancy.cpp:59-71 -> LDPixelSample,
+// src/core/montecarlo.cpp:192-244, src/core/montecarlo.h:262-315) gives every dimension of every
+// pixel a randomly scrambled (0,2)-sequence visited in a random order, both drawn from ONE
+// sequential MT19937 stream per image tile — inherently serial. Here the sequence is the same
+// (VanDerCorput / Sobol2, bit-exact integer code) but scramble and visiting order come from
+// counter-based hashes of (seed, pixel, dimension), so any sample of any pixel can be produced
+// independently by any thread on any GPU: statistically equivalent, not stream-identical
+// (SURVEY.md 7 "hard parts" 3). Draws the reference takes from the RNG itself (bounces >= 3,
+// Russian roulette) are hashes of (seed, pixel, sample, counter).
+#pragma once
+#include "spt_device.cuh"
+
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ uint32_t hash4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    uint32_t h = mix32(a + 0x9e3779b9U);
+    h = mix32(h ^ (b + 0x85ebca6bU));
+    h = mix32(h ^ (c + 0xc2b2ae35U));
+    h = mix32(h ^ (d + 0x27d4eb2fU));
+    return h;
+}
+// random permutation of [0,n), n a power of two (invertible mixing restricted to log2 n bits)
+__device__ __forceinline__ uint32_t permute_pow2(uint32_t i, uint32_t n, uint32_t key) {
+    uint32_t mask = n - 1;
+    if (!mask) return 0;
+    i ^= key; i *= 0xe170893dU; i ^= key >> 16;
+    i ^= (i & mask) >> 4; i ^= key >> 8; i *= 0x0929eb3fU; i ^= key >> 23;
+    i ^= (i & mask) >> 1; i *= 1 | key >> 27; i *= 0x6935fa69U;
+    i ^= (i & mask) >> 11; i *= 0x74dcb303U; i ^= (i & mask) >> 2; i *= 0x9e501cc3U;
+    i ^= (i & mask) >> 2; i *= 0xc860a3dfU; i &= mask; i ^= i >> 5;
+    return (i + key) & mask;
+}
+__device__ __forceinline__ float van_der_corput(uint32_t n, uint32_t scramble) {   // montecarlo.h:270-279
+    n = __brev(n);
+    n ^= scramble;
+    return stdminf(((n >> 8) & 0xffffff) / (float)(1 << 24), ONE_MINUS_EPS);
+}
+__device__ __forceinline__ float sobol2(uint32_t n, uint32_t scramble) {           // montecarlo.h:282-286
+    for (uint32_t v = 1u << 31; n != 0; n >>= 1, v ^= v >> 1)
+        if (n & 0x1) scramble ^= v;
+    return stdminf(((scramble >> 8) & 0xffffff) / (float)(1 << 24), ONE_MINUS_EPS);
+}
+__device__ __forceinline__ float ld1(uint32_t seed, uint32_t pix, uint32_t dim, uint32_t s, uint32_t spp) {
+    uint32_t idx = permute_pow2(s, spp, hash4(seed, pix, dim, 0u));
+    return van_der_corput(idx, hash4(seed, pix, dim, 1u));
+}
+__device__ __forceinline__ void ld2(uint32_t seed, uint32_t pix, uint32_t dim, uint32_t s, uint32_t spp, float *out) {
+    uint32_t idx = permute_pow2(s, spp, hash4(seed, pix, dim, 0u));
+    out[0] = van_der_corput(idx, hash4(seed, pix, dim, 1u));
+    out[1] = sobol2(idx, hash4(seed, pix, dim, 2u));
+}
+__device__ __forceinline__ float rng_float(uint32_t seed, uint32_t pix, uint32_t s, uint32_t k) {
+    return (hash4(seed, pix, 0x10000u + s, k) & 0xffffff) / (float)(1 << 24);   // RNG::RandomFloat, rng.cpp:51-57
+}
+
+// Where a path's sample values come from: generated (production) or caller-supplied arrays in the
+// reference's Sample memory order (spt_shade_samples).
+struct SampleSource {
+    const float *smp;       // n x 37, or NULL
+    const float *rng;       // n x n_rng, or NULL
+    int n_rng;
+    uint32_t seed, spp;
+};
+
+// The ten values bounce `b` consumes: {lightNum, lightPos0, lightPos1, lightComp, bsdfDir0,
+// bsdfDir1, bsdfComp, pathDir0, pathDir1, pathComp} (src/integrators/path.cpp:33-41,63-83;
+// src/core/integrator.cpp:84-99), and the Russian-roulette draw (path.cpp:97).
+__device__ inline void bounce_dims(const SampleSource &src, uint64_t idx, uint32_t pix, uint32_t s, int b,
+                                   bool haveLights, float u[10], float *rr) {
+    if (b < 3) {
+        if (src.smp) {
+            const float *oneD = src.smp + 37 * idx + 5 + 4 * b;
+            const float *twoD = src.smp + 37 * idx + 19 + 6 * b;
+            u[0] = oneD[1]; u[1] = twoD[0]; u[2] = twoD[1]; u[3] = oneD[0];
+            u[4] = twoD[2]; u[5] = twoD[3]; u[6] = oneD[2];
+            u[7] = twoD[4]; u[8] = twoD[5]; u[9] = oneD[3];
+        } else {
+            float t[2];
+            u[3] = ld1(src.seed, pix, 3 + 4 * b + 0, s, src.spp);
+            u[0] = ld1(src.seed, pix, 3 + 4 * b + 1, s, src.spp);
+            u[6] = ld1(src.seed, pix, 3 + 4 * b + 2, s, src.spp);
+            u[9] = ld1(src.seed, pix, 3 + 4 * b + 3, s, src.spp);
+            ld2(src.seed, pix, 17 + 3 * b + 0, s, src.spp, t); u[1] = t[0]; u[2] = t[1];
+            ld2(src.seed, pix, 17 + 3 * b + 1, s, src.spp, t); u[4] = t[0]; u[5] = t[1];
+            ld2(src.seed, pix, 17 + 3 * b + 2, s, src.spp, t); u[7] = t[0]; u[8] = t[1];
+        }
+        *rr = 0.f;
+        return;
+    }
+    // bounces >= 3: sequential RNG draws; a path that reaches bounce b has consumed a fixed count
+    int perBounce = (haveLights ? 7 : 0) + 3;
+    int k = (b - 3) * perBounce + (b > 4 ? b - 4 : 0);
+    float v[11];
+    for (int j = 0; j < perBounce + 1; ++j) {
+        int kk = k + j;
+        if (src.rng) v[j] = kk < src.n_rng ? src.rng[(size_t)src.n_rng * idx + kk] : 0.5f;
+        else v[j] = rng_float(src.seed, pix, s, (uint32_t)kk);
+    }
+    int j = 0;
+    if (haveLights) { for (; j < 7; ++j) u[j] = v[j]; }
+    else { for (int q = 0; q < 7; ++q) u[q] = 0.f; }
+    u[7] = v[j]; u[8] = v[j + 1]; u[9] = v[j + 2];
+    *rr = v[j + 3];
+}

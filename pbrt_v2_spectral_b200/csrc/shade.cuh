@@ -1,0 +1,524 @@
+// shade.cuh — device code for K4-K6: shading frame, BSDF terms, light sampling, MIS.
+//
+// The reference evaluates every BSDF/light quantity as a 32-float SampledSpectrum
+// (src/core/spectrum.h:93-266). Here a direction's BSDF value is kept as a handful of SCALAR
+// terms (DirTerms) — everything that does not depend on wavelength — and the per-band value is
+// rebuilt inside the one band loop of the accumulate kernel from the material row
+// (f_band()), in the reference's own operation order. A path therefore stages ~200 bytes
+// between kernels instead of 3 x 128-byte spectra.
+#pragma once
+#include "traverse.cuh"
+
+// ---- Monte Carlo helpers (src/core/montecarlo.cpp / montecarlo.h) ------------------------------
+__device__ inline void concentric_sample_disk(float u1, float u2, float *dx, float *dy) {   // montecarlo.cpp:298-340
+    float r, theta;
+    float sx = 2 * u1 - 1;
+    float sy = 2 * u2 - 1;
+    if (sx == 0.0f && sy == 0.0f) { *dx = 0.0f; *dy = 0.0f; return; }
+    if (sx >= -sy) {
+        if (sx > sy) {
+            r = sx;
+            if (sy > 0.0f) theta = sy / r;
+            else theta = 8.0f + sy / r;
+        } else { r = sy; theta = 2.0f - sx / r; }
+    } else {
+        if (sx <= sy) { r = -sx; theta = 4.0f - sy / r; }
+        else { r = -sy; theta = 6.0f + sx / r; }
+    }
+    theta *= PI_F / 4.f;
+    *dx = r * cosf(theta);
+    *dy = r * sinf(theta);
+}
+__device__ inline v3 cosine_sample_hemisphere(float u1, float u2) {                        // montecarlo.h:120-125
+    v3 ret;
+    concentric_sample_disk(u1, u2, &ret.x, &ret.y);
+    ret.z = sqrtf(stdmaxf(0.f, 1.f - ret.x * ret.x - ret.y * ret.y));
+    return ret;
+}
+__device__ inline v3 uniform_sample_sphere(float u1, float u2) {                           // montecarlo.cpp:270-277
+    float z = 1.f - 2.f * u1;
+    float r = sqrtf(stdmaxf(0.f, 1.f - z * z));
+    float phi = 2.f * PI_F * u2;
+    return V(r * cosf(phi), r * sinf(phi), z);
+}
+__device__ inline v3 uniform_sample_cone(float u1, float u2, float costhetamax, v3 x, v3 y, v3 z) {   // :405-412
+    float costheta = lerpf(u1, costhetamax, 1.f);
+    float sintheta = sqrtf(1.f - costheta * costheta);
+    float phi = u2 * 2.f * PI_F;
+    return vadd(vadd(vmul(x, cosf(phi) * sintheta), vmul(y, sinf(phi) * sintheta)), vmul(z, costheta));
+}
+__device__ __forceinline__ float uniform_cone_pdf(float c) { return 1.f / (2.f * PI_F * (1.f - c)); }
+__device__ __forceinline__ float power_heuristic(float fPdf, float gPdf) {                 // montecarlo.h:254-257
+    float f = 1 * fPdf, g = 1 * gPdf;
+    return (f * f) / (f * f + g * g);
+}
+
+// ---- K1: PerspectiveCamera::GenerateRayDifferential (src/cameras/perspective.cpp:73-106) --------
+__device__ inline void camera_ray(const SptCameraDesc &cam, float imageX, float imageY, float lu, float lv, Ray *ray) {
+    v3 Pcamera = xf_point(cam.raster_to_camera, V(imageX, imageY, 0.f));
+    ray->o = V(0, 0, 0);
+    ray->d = normalize(Pcamera);
+    ray->mint = 0.f;
+    ray->maxt = SPT_INF;
+    if (cam.lens_radius > 0.f) {
+        float lensU, lensV;
+        concentric_sample_disk(lu, lv, &lensU, &lensV);
+        lensU *= cam.lens_radius;
+        lensV *= cam.lens_radius;
+        float ft = cam.focal_distance / ray->d.z;
+        v3 Pfocus = ray_at(*ray, ft);
+        ray->o = V(lensU, lensV, 0.f);
+        ray->d = normalize(vsub(Pfocus, ray->o));
+    }
+    ray->o = xf_point(cam.camera_to_world, ray->o);
+    ray->d = xf_vector(cam.camera_to_world, ray->d);
+}
+
+// ---- BSDF -------------------------------------------------------------------------------------
+enum { BX_LAMBERT = 0, BX_ORENNAYAR = 1, BX_MF_DIEL = 2, BX_MF_COND = 3 };
+struct Bsdf {
+    v3 nn, sn, tn, ng;
+    int mtype;            // SPT_MAT_*
+    bool orenNayar;
+    float exponent, A, B;
+};
+// Wavelength-independent factors of BSDF::f(wo,wi) for one direction.
+//   Oren-Nayar: a0 = A + B*maxcos*sinalpha*tanbeta
+//   Microfacet: a0 = D, a1 = G, a2 = F (dielectric) or |cos theta_h| (conductor), a3 = 4 cosI cosO
+struct DirTerms { float a0, a1, a2, a3; bool reflect, mf; };
+
+__device__ __forceinline__ v3 w2l(const Bsdf &b, v3 v) { return V(dot(v, b.sn), dot(v, b.tn), dot(v, b.nn)); }
+__device__ __forceinline__ v3 l2w(const Bsdf &b, v3 v) {
+    return V(b.sn.x * v.x + b.tn.x * v.y + b.nn.x * v.z, b.sn.y * v.x + b.tn.y * v.y + b.nn.y * v.z,
+             b.sn.z * v.x + b.tn.z * v.y + b.nn.z * v.z);
+}
+__device__ __forceinline__ float abs_cos_theta(v3 w) { return fabsf(w.z); }
+__device__ __forceinline__ bool same_hemisphere(v3 w, v3 wp) { return w.z * wp.z > 0.f; }
+__device__ __forceinline__ float sin_theta(v3 w) { return sqrtf(stdmaxf(0.f, 1.f - w.z * w.z)); }
+__device__ __forceinline__ float cos_phi(v3 w) { float s = sin_theta(w); if (s == 0.f) return 1.f; return clampf(w.x / s, -1.f, 1.f); }
+__device__ __forceinline__ float sin_phi(v3 w) { float s = sin_theta(w); if (s == 0.f) return 0.f; return clampf(w.y / s, -1.f, 1.f); }
+__device__ __forceinline__ float blinn_exponent(float e) { if (e > 10000.f || isnan(e)) e = 10000.f; return e; }
+
+// Triangle::GetShadingGeometry (trianglemesh.cpp:285-360) + Material::Bump with the constant-0
+// displacement every reference material carries (material.cpp:39-82) + BSDF frame
+// (reflection.cpp:593-601) + the BxDF set of matte/plastic/metal (materials/*.cpp).
+__device__ inline void make_bsdf(const DevScene &sc, uint32_t slot, const Hit &dg, Bsdf *b) {
+    int flags = sc.prim_flags[slot];
+    v3 s_dpdu = dg.dpdu, s_dpdv = dg.dpdv;
+    if (sc.prim_kind[slot] == SPT_PRIM_TRIANGLE && (flags & SPT_PF_HAS_N)) {
+        const int32_t *vi = sc.tri_vidx + 3 * (size_t)sc.prim_data[slot];
+        float uv[3][2];
+        tri_uvs(sc, flags, vi, uv);
+        float A00 = uv[1][0] - uv[0][0], A01 = uv[2][0] - uv[0][0];
+        float A10 = uv[1][1] - uv[0][1], A11 = uv[2][1] - uv[0][1];
+        float C0 = dg.u - uv[0][0], C1 = dg.v - uv[0][1];
+        float bb0, bb1, bb2;
+        float det = A00 * A11 - A01 * A10;                          // SolveLinearSystem2x2, transform.cpp:31-41
+        bool ok = true;
+        if (fabsf(det) < 1e-10f) ok = false;
+        else {
+            bb1 = (A11 * C0 - A01 * C1) / det;
+            bb2 = (A00 * C1 - A10 * C0) / det;
+            if (isnan(bb1) || isnan(bb2)) ok = false;
+        }
+        if (!ok) bb0 = bb1 = bb2 = 1.f / 3.f;
+        else bb0 = 1.f - bb1 - bb2;
+        const SptXform &xf = sc.xforms[sc.prim_xform[slot]];
+        const float *n0 = sc.N + 3 * (size_t)vi[0], *n1 = sc.N + 3 * (size_t)vi[1], *n2 = sc.N + 3 * (size_t)vi[2];
+        v3 nsum = vadd(vadd(vmul(V(n0[0], n0[1], n0[2]), bb0), vmul(V(n1[0], n1[1], n1[2]), bb1)),
+                       vmul(V(n2[0], n2[1], n2[2]), bb2));
+        v3 ns = normalize(xf_normal(xf.minv, nsum));
+        v3 ss = normalize(dg.dpdu);
+        v3 ts = cross(ss, ns);
+        if (len2(ts) > 0.f) { ts = normalize(ts); ss = cross(ts, ns); }
+        else coordinate_system(ns, &ss, &ts);
+        s_dpdu = ss; s_dpdv = ts;
+    }
+    v3 nn = normalize(cross(s_dpdu, s_dpdv));
+    if (flags & SPT_PF_FLIP_NORMAL) nn = vmul(nn, -1.f);
+    if (dot(nn, dg.nn) < 0.f) nn = vneg(nn);                        // Faceforward to the geometric normal
+    b->nn = nn;
+    b->ng = dg.nn;
+    b->sn = normalize(s_dpdu);
+    b->tn = cross(b->nn, b->sn);
+    const SptMaterial &m = sc.materials[sc.prim_material[slot]];
+    b->mtype = m.type;
+    b->orenNayar = false; b->exponent = 0.f; b->A = b->B = 0.f;
+    if (m.type == SPT_MAT_MATTE) {
+        if (m.p0 != 0.f) {                                           // OrenNayar ctor, reflection.h:363-370
+            b->orenNayar = true;
+            float sigma = (PI_F / 180.f) * m.p0;
+            float sigma2 = sigma * sigma;
+            b->A = 1.f - (sigma2 / (2.f * (sigma2 + 0.33f)));
+            b->B = 0.45f * sigma2 / (sigma2 + 0.09f);
+        }
+    } else {
+        b->exponent = blinn_exponent(1.f / m.p0);
+    }
+}
+__device__ __forceinline__ int bsdf_ncomp(const Bsdf &b) { return b.mtype == SPT_MAT_PLASTIC ? 2 : 1; }
+
+__device__ inline float fresnel_dielectric(float cosi, float eta_i, float eta_t) {          // reflection.cpp:107-127,52-60
+    cosi = clampf(cosi, -1.f, 1.f);
+    bool entering = cosi > 0.f;
+    float ei = eta_i, et = eta_t;
+    if (!entering) { float tmp = ei; ei = et; et = tmp; }
+    float sint = ei / et * sqrtf(stdmaxf(0.f, 1.f - cosi * cosi));
+    if (sint >= 1.f) return 1.f;
+    float cost = sqrtf(stdmaxf(0.f, 1.f - sint * sint));
+    float ac = fabsf(cosi);
+    float Rparl = ((et * ac) - (ei * cost)) / ((et * ac) + (ei * cost));
+    float Rperp = ((ei * ac) - (et * cost)) / ((ei * ac) + (et * cost));
+    return (Rparl * Rparl + Rperp * Rperp) / 2.f;
+}
+__device__ __forceinline__ float fr_cond(float cosi, float eta, float k) {                   // reflection.cpp:63-71
+    float tmp = (eta * eta + k * k) * cosi * cosi;
+    float Rparl2 = (tmp - (2.f * eta * cosi) + 1) / (tmp + (2.f * eta * cosi) + 1);
+    float tmp_f = eta * eta + k * k;
+    float Rperp2 = (tmp_f - (2.f * eta * cosi) + cosi * cosi) / (tmp_f + (2.f * eta * cosi) + cosi * cosi);
+    return (Rparl2 + Rperp2) / 2.f;
+}
+
+// scalar part of BSDF::f (reflection.cpp:604-618, with Lambertian :165-167, OrenNayar :170-193,
+// Microfacet :203-214, G reflection.h:395-402, Blinn::D reflection.h:419-422)
+__device__ inline void bsdf_terms(const Bsdf &b, v3 woW, v3 wiW, v3 wo, v3 wi, DirTerms *t) {
+    t->a0 = t->a1 = t->a2 = t->a3 = 0.f;
+    t->mf = false;
+    t->reflect = dot(wiW, b.ng) * dot(woW, b.ng) > 0;
+    if (!t->reflect) return;
+    if (b.mtype == SPT_MAT_MATTE) {
+        if (b.orenNayar) {
+            float sinthetai = sin_theta(wi), sinthetao = sin_theta(wo);
+            float maxcos = 0.f;
+            if ((double)sinthetai > 1e-4 && (double)sinthetao > 1e-4) {
+                float sinphii = sin_phi(wi), cosphii = cos_phi(wi);
+                float sinphio = sin_phi(wo), cosphio = cos_phi(wo);
+                float dcos = cosphii * cosphio + sinphii * sinphio;
+                maxcos = stdmaxf(0.f, dcos);
+            }
+            float sinalpha, tanbeta;
+            if (abs_cos_theta(wi) > abs_cos_theta(wo)) { sinalpha = sinthetao; tanbeta = sinthetai / abs_cos_theta(wi); }
+            else { sinalpha = sinthetai; tanbeta = sinthetao / abs_cos_theta(wo); }
+            t->a0 = (b.A + b.B * maxcos * sinalpha * tanbeta);
+        }
+        return;
+    }
+    float cosThetaO = abs_cos_theta(wo), cosThetaI = abs_cos_theta(wi);
+    if (cosThetaI == 0.f || cosThetaO == 0.f) return;
+    v3 wh = vadd(wi, wo);
+    if (wh.x == 0.f && wh.y == 0.f && wh.z == 0.f) return;
+    wh = normalize(wh);
+    float cosThetaH = dot(wi, wh);
+    t->a0 = (b.exponent + 2) * INV_TWOPI_F * powf(abs_cos_theta(wh), b.exponent);
+    float NdotWh = abs_cos_theta(wh), NdotWo = abs_cos_theta(wo), NdotWi = abs_cos_theta(wi);
+    float WOdotWh = absdot(wo, wh);
+    t->a1 = stdminf(1.f, stdminf((2.f * NdotWh * NdotWo / WOdotWh), (2.f * NdotWh * NdotWi / WOdotWh)));
+    t->a2 = (b.mtype == SPT_MAT_PLASTIC) ? fresnel_dielectric(cosThetaH, 1.5f, 1.f) : fabsf(cosThetaH);
+    t->a3 = (4.f * cosThetaI * cosThetaO);
+    t->mf = true;
+}
+// f for band c from the staged terms, in the reference's operation order
+__device__ __forceinline__ float f_band(const SptMaterial &m, bool orenNayar, const DirTerms &t, int c) {
+    if (!t.reflect) return 0.f;
+    float f = 0.f;
+    if (m.type == SPT_MAT_MATTE) {
+        if (orenNayar) f += m.spec0[c] * INV_PI_F * t.a0;
+        else f += m.spec0[c] * INV_PI_F;
+    } else if (m.type == SPT_MAT_PLASTIC) {
+        f += m.spec0[c] * INV_PI_F;
+        if (t.mf) f += m.spec1[c] * t.a0 * t.a1 * t.a2 / t.a3;
+    } else {
+        if (t.mf) f += 1.f * t.a0 * t.a1 * fr_cond(t.a2, m.spec0[c], m.spec1[c]) / t.a3;
+    }
+    return f;
+}
+// Pdf of component i (BxDF::Pdf reflection.cpp:312-315, Microfacet::Pdf :331-335, Blinn::Pdf :356-366)
+__device__ inline float bxdf_pdf(const Bsdf &b, int i, v3 wo, v3 wi) {
+    bool mf = (b.mtype == SPT_MAT_METAL) || (b.mtype == SPT_MAT_PLASTIC && i == 1);
+    if (!mf) return same_hemisphere(wo, wi) ? abs_cos_theta(wi) * INV_PI_F : 0.f;
+    if (!same_hemisphere(wo, wi)) return 0.f;
+    v3 wh = normalize(vadd(wo, wi));
+    float costheta = abs_cos_theta(wh);
+    float blinn_pdf = ((b.exponent + 1.f) * powf(costheta, b.exponent)) / (2.f * PI_F * 4.f * dot(wo, wh));
+    if (dot(wo, wh) <= 0.f) blinn_pdf = 0.f;
+    return blinn_pdf;
+}
+__device__ inline float bsdf_pdf(const Bsdf &b, v3 wo, v3 wi) {                              // reflection.cpp:575-590
+    int n = bsdf_ncomp(b);
+    float pdf = 0.f;
+    for (int i = 0; i < n; ++i) pdf += bxdf_pdf(b, i, wo, wi);
+    return pdf / n;
+}
+// BSDF::Sample_f (reflection.cpp:514-572): direction + pdf + scalar terms. pdf == 0: no sample.
+__device__ inline void bsdf_sample(const Bsdf &b, v3 woW, v3 wo, float uComp, float u1, float u2,
+                                   v3 *wiW, float *pdf, DirTerms *t) {
+    int matching = bsdf_ncomp(b);
+    int which = (int)floorf(uComp * matching);
+    if (matching - 1 < which) which = matching - 1;
+    bool mf = (b.mtype == SPT_MAT_METAL) || (b.mtype == SPT_MAT_PLASTIC && which == 1);
+    v3 wi;
+    *pdf = 0.f;
+    t->a0 = t->a1 = t->a2 = t->a3 = 0.f; t->mf = false; t->reflect = false;
+    if (!mf) {                                                       // BxDF::Sample_f, reflection.cpp:303-310
+        wi = cosine_sample_hemisphere(u1, u2);
+        if (wo.z < 0.f) wi.z *= -1.f;
+        *pdf = bxdf_pdf(b, which, wo, wi);
+    } else {                                                         // Blinn::Sample_f, reflection.cpp:338-354
+        float costheta = powf(u1, 1.f / (b.exponent + 1));
+        float sintheta = sqrtf(stdmaxf(0.f, 1.f - costheta * costheta));
+        float phi = u2 * 2.f * PI_F;
+        v3 wh = V(sintheta * cosf(phi), sintheta * sinf(phi), costheta);
+        if (!same_hemisphere(wo, wh)) wh = vneg(wh);
+        wi = vadd(vneg(wo), vmul(wh, 2.f * dot(wo, wh)));
+        float blinn_pdf = ((b.exponent + 1.f) * powf(costheta, b.exponent)) / (2.f * PI_F * 4.f * dot(wo, wh));
+        if (dot(wo, wh) <= 0.f) blinn_pdf = 0.f;
+        *pdf = blinn_pdf;
+    }
+    if (*pdf == 0.f) return;
+    *wiW = l2w(b, wi);
+    if (matching > 1) {
+        for (int i = 0; i < matching; ++i)
+            if (i != which) *pdf += bxdf_pdf(b, i, wo, wi);
+        *pdf /= matching;
+    }
+    bsdf_terms(b, woW, *wiW, wo, wi, t);
+}
+
+// ---- spectral tables ----------------------------------------------------------------------------
+// SampledSpectrum::FromRGB(rgb, SPECTRUM_ILLUMINANT) (src/core/spectrum.cpp:136-176) is linear in
+// three basis spectra chosen by the ordering of r,g,b: keep the three coefficients, rebuild per band.
+struct IllumCoefs { float k0, k1, k2; int b1, b2; };
+__device__ inline IllumCoefs illum_coefs(const float rgb[3]) {
+    enum { W = 0, Cy = 1, Mg = 2, Ye = 3, Rd = 4, Gr = 5, Bl = 6 };
+    IllumCoefs k;
+    if (rgb[0] <= rgb[1] && rgb[0] <= rgb[2]) {
+        k.k0 = rgb[0];
+        if (rgb[1] <= rgb[2]) { k.k1 = rgb[1] - rgb[0]; k.b1 = Cy; k.k2 = rgb[2] - rgb[1]; k.b2 = Bl; }
+        else { k.k1 = rgb[2] - rgb[0]; k.b1 = Cy; k.k2 = rgb[1] - rgb[2]; k.b2 = Gr; }
+    } else if (rgb[1] <= rgb[0] && rgb[1] <= rgb[2]) {
+        k.k0 = rgb[1];
+        if (rgb[0] <= rgb[2]) { k.k1 = rgb[0] - rgb[1]; k.b1 = Mg; k.k2 = rgb[2] - rgb[0]; k.b2 = Bl; }
+        else { k.k1 = rgb[2] - rgb[1]; k.b1 = Mg; k.k2 = rgb[0] - rgb[2]; k.b2 = Rd; }
+    } else {
+        k.k0 = rgb[2];
+        if (rgb[0] <= rgb[1]) { k.k1 = rgb[0] - rgb[2]; k.b1 = Ye; k.k2 = rgb[1] - rgb[0]; k.b2 = Gr; }
+        else { k.k1 = rgb[1] - rgb[2]; k.b1 = Ye; k.k2 = rgb[0] - rgb[1]; k.b2 = Rd; }
+    }
+    return k;
+}
+__device__ __forceinline__ float illum_band(const SptSpectralTables &t, const IllumCoefs &k, int c) {
+    float r = 0.f;
+    r += t.rgb_illum[0][c] * k.k0;
+    r += t.rgb_illum[k.b1][c] * k.k1;
+    r += t.rgb_illum[k.b2][c] * k.k2;
+    r *= .86445f;
+    return clampf(r, 0.f, SPT_INF);
+}
+__device__ __forceinline__ int imod(int a, int b) { int n = (int)(a / b); a -= n * b; if (a < 0) a += b; return a; }
+// MIPMap::Lookup(s,t) -> triangle(0,s,t), repeat wrap (src/core/mipmap.h:198-221,233-274)
+__device__ inline void env_lookup(const DevScene &sc, float s, float t, float rgb[3]) {
+    int w = sc.env_w, h = sc.env_h;
+    s = s * w - 0.5f;
+    t = t * h - 0.5f;
+    int s0 = (int)floorf(s), t0 = (int)floorf(t);
+    float ds = s - s0, dt = t - t0;
+    const float *a = sc.env_rgb + 3 * ((size_t)imod(t0, h) * w + imod(s0, w));
+    const float *b = sc.env_rgb + 3 * ((size_t)imod(t0 + 1, h) * w + imod(s0, w));
+    const float *c = sc.env_rgb + 3 * ((size_t)imod(t0, h) * w + imod(s0 + 1, w));
+    const float *d = sc.env_rgb + 3 * ((size_t)imod(t0 + 1, h) * w + imod(s0 + 1, w));
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+        rgb[k] = a[k] * ((1.f - ds) * (1.f - dt)) + b[k] * ((1.f - ds) * dt) + c[k] * (ds * (1.f - dt)) + d[k] * (ds * dt);
+}
+__device__ __forceinline__ float spherical_theta(v3 v) { return acosf(clampf(v.z, -1.f, 1.f)); }
+__device__ __forceinline__ float spherical_phi(v3 v) { float p = atan2f(v.y, v.x); return (p < 0.f) ? p + 2.f * PI_F : p; }
+// InfiniteAreaLight::Le (src/lights/infinite.cpp:109-114) as RGB; spectrum via illum_coefs/illum_band
+__device__ inline void infinite_le_rgb(const DevScene &sc, const SptLight &l, v3 d, float rgb[3]) {
+    const SptXform &xf = sc.xforms[l.xform];
+    v3 wh = normalize(xf_vector(xf.minv, d));
+    float s = spherical_phi(wh) * INV_TWOPI_F;
+    float t = spherical_theta(wh) * INV_PI_F;
+    env_lookup(sc, s, t, rgb);
+}
+// std::upper_bound(cdf, cdf+count+1, u) - cdf - 1, clamped at 0 (montecarlo.h:70-99)
+__device__ inline int cdf_find(const float *cdf, int count, float u) {
+    int lo = 0, hi = count + 1;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (cdf[mid] <= u) lo = mid + 1; else hi = mid; }
+    int offset = lo - 1;
+    return offset < 0 ? 0 : offset;
+}
+__device__ inline float dist1d_sample_continuous(const float *func, const float *cdf, float funcInt, int count,
+                                                 float u, float *pdf, int *off) {
+    int offset = cdf_find(cdf, count, u);
+    if (off) *off = offset;
+    float du = (u - cdf[offset]) / (cdf[offset + 1] - cdf[offset]);
+    *pdf = func[offset] / funcInt;
+    return (offset + du) / count;
+}
+__device__ inline float env_pdf_uv(const DevScene &sc, float u, float v) {                     // montecarlo.h:146-154
+    int nu = sc.env_w, nv = sc.env_h;
+    int iu = clampi((int)(u * nu), 0, nu - 1);
+    int iv = clampi((int)(v * nv), 0, nv - 1);
+    if (sc.env_func_int[iv] * sc.env_marg_int == 0.f) return 0.f;
+    return (sc.env_func[(size_t)iv * nu + iu] * sc.env_marg_func[iv]) / (sc.env_func_int[iv] * sc.env_marg_int);
+}
+
+// ---- area-light shapes (ShapeSet, src/core/light.cpp:106-172) ----------------------------------
+__device__ inline v3 tri_vertex(const DevScene &sc, int idx) { const float *p = sc.P + 3 * (size_t)idx; return V(p[0], p[1], p[2]); }
+// Shape::Sample(u1,u2,Ns): trianglemesh.cpp:436-448, disk.cpp:140-149, sphere.cpp:220-225
+__device__ inline v3 shape_sample_area(const DevScene &sc, const SptLightShape &s, float u1, float u2, v3 *ns) {
+    if (s.kind == SPT_PRIM_TRIANGLE) {
+        float su1 = sqrtf(u1);                                        // UniformSampleTriangle, montecarlo.cpp:342-347
+        float b1 = 1.f - su1, b2 = u2 * su1;
+        const int32_t *vi = sc.tri_vidx + 3 * (size_t)s.data;
+        v3 p1 = tri_vertex(sc, vi[0]), p2 = tri_vertex(sc, vi[1]), p3 = tri_vertex(sc, vi[2]);
+        v3 p = vadd(vadd(vmul(p1, b1), vmul(p2, b2)), vmul(p3, (1.f - b1 - b2)));
+        *ns = normalize(cross(vsub(p2, p1), vsub(p3, p1)));
+        if (s.flags & SPT_PF_REVERSE) *ns = vmul(*ns, -1.f);
+        return p;
+    }
+    const SptQuadric &q = sc.quadrics[s.data];
+    const SptXform &xf = sc.xforms[q.xform];
+    if (s.kind == SPT_PRIM_DISK) {
+        v3 p;
+        concentric_sample_disk(u1, u2, &p.x, &p.y);
+        p.x *= q.radius; p.y *= q.radius; p.z = q.zmin;
+        *ns = normalize(xf_normal(xf.minv, V(0, 0, 1)));
+        if (s.flags & SPT_PF_REVERSE) *ns = vmul(*ns, -1.f);
+        return xf_point(xf.m, p);
+    }
+    v3 p = vadd(V(0, 0, 0), vmul(uniform_sample_sphere(u1, u2), q.radius));
+    *ns = normalize(xf_normal(xf.minv, p));
+    if (s.flags & SPT_PF_REVERSE) *ns = vmul(*ns, -1.f);
+    return xf_point(xf.m, p);
+}
+// Shape::Sample(p,u1,u2,Ns): Sphere sphere.cpp:228-252, others = area sampling
+__device__ inline v3 shape_sample_from(const DevScene &sc, const SptLightShape &s, v3 p, float u1, float u2, v3 *ns) {
+    if (s.kind != SPT_PRIM_SPHERE) return shape_sample_area(sc, s, u1, u2, ns);
+    const SptQuadric &q = sc.quadrics[s.data];
+    const SptXform &xf = sc.xforms[q.xform];
+    v3 Pcenter = xf_point(xf.m, V(0, 0, 0));
+    v3 wc = normalize(vsub(Pcenter, p));
+    v3 wcX, wcY;
+    coordinate_system(wc, &wcX, &wcY);
+    if (len2(vsub(p, Pcenter)) - q.radius * q.radius < 1e-4f) return shape_sample_area(sc, s, u1, u2, ns);
+    float sinThetaMax2 = q.radius * q.radius / len2(vsub(p, Pcenter));
+    float cosThetaMax = sqrtf(stdmaxf(0.f, 1.f - sinThetaMax2));
+    Ray r; r.o = p; r.d = uniform_sample_cone(u1, u2, cosThetaMax, wcX, wcY, wc); r.mint = 1e-3f; r.maxt = SPT_INF;
+    float thit;
+    if (!sphere_intersect(sc, q, s.flags, r, &thit, nullptr)) thit = dot(vsub(Pcenter, p), normalize(r.d));
+    v3 ps = ray_at(r, thit);
+    *ns = normalize(vsub(ps, Pcenter));
+    if (s.flags & SPT_PF_REVERSE) *ns = vmul(*ns, -1.f);
+    return ps;
+}
+// Shape::Pdf(p,wi) shape.cpp:78-91; Sphere::Pdf sphere.cpp:255-266
+__device__ inline float shape_pdf(const DevScene &sc, const SptLightShape &s, v3 p, v3 wi) {
+    if (s.kind == SPT_PRIM_SPHERE) {
+        const SptQuadric &q = sc.quadrics[s.data];
+        const SptXform &xf = sc.xforms[q.xform];
+        v3 Pcenter = xf_point(xf.m, V(0, 0, 0));
+        if (!(len2(vsub(p, Pcenter)) - q.radius * q.radius < 1e-4f)) {
+            float sinThetaMax2 = q.radius * q.radius / len2(vsub(p, Pcenter));
+            float cosThetaMax = sqrtf(stdmaxf(0.f, 1.f - sinThetaMax2));
+            return uniform_cone_pdf(cosThetaMax);
+        }
+    }
+    Ray ray; ray.o = p; ray.d = wi; ray.mint = 1e-3f; ray.maxt = SPT_INF;
+    Hit h;
+    if (!shape_intersect(sc, s.kind, s.flags, (uint32_t)s.data, ray, &h)) return 0.f;
+    float pdf = len2(vsub(p, ray_at(ray, h.t))) / (absdot(h.nn, vneg(wi)) * s.area);
+    if (isinf(pdf)) pdf = 0.f;
+    return pdf;
+}
+__device__ inline float shapeset_pdf(const DevScene &sc, const SptLight &l, v3 p, v3 wi) {    // light.cpp:156-161
+    float pdf = 0.f;
+    for (int i = 0; i < l.shape_count; ++i) {
+        const SptLightShape &s = sc.light_shapes[l.shape_first + i];
+        pdf += s.area * shape_pdf(sc, s, p, wi);
+    }
+    return pdf / l.sum_area;
+}
+
+// Result of Light::Sample_L (diffuse.cpp:61-73 + light.cpp:137-149, point.cpp:42-49,
+// infinite.cpp:187-213) with the VisibilityTester segment (light.h:79-88). The radiance is kept as
+// {kind, aux}: AREA on/off (x Lemit), POINT 1/d2 divisor, INFINITE rgb.
+struct LightSampleResult { bool delta; bool black; v3 wi; float pdf; v3 shadow_d; float shadow_maxt; float aux[3]; };
+
+__device__ inline void light_sample(const DevScene &sc, int lightIdx, v3 p, float u0, float u1, float uComp,
+                                    LightSampleResult *out) {
+    const SptLight &l = sc.lights[lightIdx];
+    out->delta = false; out->black = true; out->pdf = 0.f;
+    out->aux[0] = out->aux[1] = out->aux[2] = 0.f;
+    out->wi = V(0, 0, 1); out->shadow_d = V(0, 0, 1); out->shadow_maxt = 0.f;
+    if (l.type == SPT_LIGHT_POINT) {
+        v3 lp = V(l.pos[0], l.pos[1], l.pos[2]);
+        out->delta = true;
+        out->wi = normalize(vsub(lp, p));
+        out->pdf = 1.f;
+        float dist = sqrtf(len2(vsub(p, lp)));
+        out->shadow_d = vdiv(vsub(lp, p), dist);
+        out->shadow_maxt = dist * (1.f - 0.f);
+        out->aux[0] = len2(vsub(lp, p));
+        out->black = false;
+        return;
+    }
+    if (l.type == SPT_LIGHT_AREA) {
+        const float *cdf = sc.light_cdf + l.shape_first + lightIdx;
+        int sn = cdf_find(cdf, l.shape_count, uComp);
+        v3 ns;
+        v3 pt = shape_sample_from(sc, sc.light_shapes[l.shape_first + sn], p, u0, u1, &ns);
+        Ray r; r.o = p; r.d = vsub(pt, p); r.mint = 1e-3f; r.maxt = SPT_INF;
+        float thit = 1.f;
+        bool anyHit = false;
+        v3 nnHit = ns;
+        for (int i = 0; i < l.shape_count; ++i) {            // unclipped ray, LAST hit wins (light.cpp:141-149)
+            const SptLightShape &s = sc.light_shapes[l.shape_first + i];
+            Hit hh;
+            if (shape_intersect(sc, s.kind, s.flags, (uint32_t)s.data, r, &hh)) { anyHit = true; nnHit = hh.nn; thit = hh.t; }
+        }
+        if (anyHit) ns = nnHit;
+        v3 ps = ray_at(r, thit);
+        out->wi = normalize(vsub(ps, p));
+        out->pdf = shapeset_pdf(sc, l, p, out->wi);
+        float dist = sqrtf(len2(vsub(p, ps)));
+        out->shadow_d = vdiv(vsub(ps, p), dist);
+        out->shadow_maxt = dist * (1.f - 1e-3f);
+        out->black = !(dot(ns, vneg(out->wi)) > 0.f);
+        return;
+    }
+    float uv[2], pdfs[2];
+    int v;
+    uv[1] = dist1d_sample_continuous(sc.env_marg_func, sc.env_marg_cdf, sc.env_marg_int, sc.env_h, u1, &pdfs[1], &v);
+    uv[0] = dist1d_sample_continuous(sc.env_func + (size_t)v * sc.env_w, sc.env_cdf + (size_t)v * (sc.env_w + 1),
+                                     sc.env_func_int[v], sc.env_w, u0, &pdfs[0], nullptr);
+    float mapPdf = pdfs[0] * pdfs[1];
+    if (mapPdf == 0.f) return;
+    float theta = uv[1] * PI_F, phi = uv[0] * 2.f * PI_F;
+    float costheta = cosf(theta), sintheta = sinf(theta);
+    float sinphi = sinf(phi), cosphi = cosf(phi);
+    const SptXform &xf = sc.xforms[l.xform];
+    out->wi = xf_vector(xf.m, V(sintheta * cosphi, sintheta * sinphi, costheta));
+    out->pdf = mapPdf / (2.f * PI_F * PI_F * sintheta);
+    if (sintheta == 0.f) out->pdf = 0.f;
+    out->shadow_d = out->wi;
+    out->shadow_maxt = SPT_INF;
+    env_lookup(sc, uv[0], uv[1], out->aux);
+    // black iff every band of FromRGB(...) clamps to zero
+    IllumCoefs k = illum_coefs(out->aux);
+    bool black = true;
+    for (int c = 0; c < NB; ++c) if (illum_band(*sc.tables, k, c) != 0.f) { black = false; break; }
+    out->black = black;
+}
+// Light::Pdf(p,wi): diffuse.cpp:76-78, infinite.cpp:216-226
+__device__ inline float light_pdf(const DevScene &sc, int lightIdx, v3 p, v3 w) {
+    const SptLight &l = sc.lights[lightIdx];
+    if (l.type == SPT_LIGHT_AREA) return shapeset_pdf(sc, l, p, w);
+    if (l.type == SPT_LIGHT_POINT) return 0.f;
+    const SptXform &xf = sc.xforms[l.xform];
+    v3 wi = xf_vector(xf.minv, w);
+    float theta = spherical_theta(wi), phi = spherical_phi(wi);
+    float sintheta = sinf(theta);
+    if (sintheta == 0.f) return 0.f;
+    return env_pdf_uv(sc, phi * INV_TWOPI_F, theta * INV_PI_F) / (2.f * PI_F * PI_F * sintheta);
+}

@@ -1,0 +1,578 @@
+// spt_api.cu — the C ABI of include/spt.h: scene upload, wavefront scheduling, film.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false --shared -Xcompiler -fPIC
+// There is no CPU path: without a CUDA device every computing entry point returns SPT_ERR_CUDA.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "spt_kernels.cuh"
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    g_err = std::string(#call) + ": " + cudaGetErrorString(e_); return SPT_ERR_CUDA; } } while (0)
+#define CUP(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    g_err = std::string(#call) + ": " + cudaGetErrorString(e_); return nullptr; } } while (0)
+
+namespace {
+
+struct DevMem {
+    std::vector<void *> ptrs;
+    template <typename T> T *alloc(size_t n) {
+        void *p = nullptr;
+        if (n == 0) n = 1;
+        if (cudaMalloc(&p, n * sizeof(T)) != cudaSuccess) return nullptr;
+        ptrs.push_back(p);
+        return (T *)p;
+    }
+    template <typename T> T *upload(const T *host, size_t n) {
+        T *d = alloc<T>(n);
+        if (d && n && host && cudaMemcpy(d, host, n * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+        return d;
+    }
+    void release() { for (void *p : ptrs) cudaFree(p); ptrs.clear(); }
+};
+
+int num_sms() {
+    static int n = 0;
+    if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
+    return n;
+}
+
+}  // namespace
+
+struct SptScene {
+    DevMem mem;
+    DevScene dev;
+    std::vector<uint32_t> prim_id_host;
+    uint32_t *prim_id_dev = nullptr;
+    bool counters_on = false;
+    unsigned long long *counters = nullptr;
+    // wave buffers, allocated on first use and reused
+    DevMem wave_mem;
+    WaveBuffers wb{};
+    uint32_t *counts = nullptr;      // device queue lengths: per wave slot, (max_depth+2) x 4
+    size_t counts_len = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    SptStats stats{};
+    uint64_t launches = 0;
+};
+
+struct SptFilm {
+    SptFilmDesc desc;
+    float *pix = nullptr;           // [y][x][NB+1]
+    bool owned = true;
+    float *table = nullptr;
+    size_t npix() const { return (size_t)desc.x_pixel_count * desc.y_pixel_count; }
+};
+
+extern "C" {
+
+int spt_nbands(void) { return NB; }
+const char *spt_last_error(void) { return g_err.c_str(); }
+int spt_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
+int spt_set_device(int ordinal) { CU(cudaSetDevice(ordinal)); return SPT_OK; }
+
+SptScene *spt_scene_create(const SptSceneDesc *d) {
+    if (!d) { g_err = "null scene desc"; return nullptr; }
+    if (d->nbands != NB) { g_err = "scene band count does not match the library's SPT_NBANDS"; return nullptr; }
+    if (spt_device_count() <= 0) { g_err = "no CUDA device: this library has no CPU path"; return nullptr; }
+    SptScene *s = new SptScene();
+    DevScene &v = s->dev;
+    memset(&v, 0, sizeof(v));
+    // nodes: byte-identical copy, plus the hasQuadric bit in the reference's pad byte for leaves
+    std::vector<uint8_t> nodes((const uint8_t *)d->bvh_nodes, (const uint8_t *)d->bvh_nodes + (size_t)d->n_nodes * 32);
+    for (uint32_t n = 0; n < d->n_nodes; ++n) {
+        uint8_t *nd = &nodes[(size_t)n * 32];
+        uint32_t off; memcpy(&off, nd + 24, 4);
+        uint8_t np = nd[28];
+        nd[30] = 0; nd[31] = 0;
+        for (uint32_t i = 0; i < np; ++i)
+            if (off + i < d->n_prims && d->prim_kind[off + i] != SPT_PRIM_TRIANGLE) nd[30] = 1;
+    }
+    // pre-gathered triangle vertices per BVH slot
+    std::vector<float4> tv((size_t)d->n_prims * 3, make_float4(0, 0, 0, 0));
+    for (uint32_t p = 0; p < d->n_prims; ++p) {
+        if (d->prim_kind[p] != SPT_PRIM_TRIANGLE) continue;
+        const int32_t *vi = d->tri_vidx + 3 * (size_t)d->prim_data[p];
+        for (int k = 0; k < 3; ++k) {
+            const float *P = d->P + 3 * (size_t)vi[k];
+            tv[(size_t)p * 3 + k] = make_float4(P[0], P[1], P[2], 0.f);
+        }
+    }
+    // Distribution1D of each area light's ShapeSet (montecarlo.h:48-68), same fp32 recurrence
+    std::vector<float> cdf(d->n_light_shapes + d->n_lights + 1, 0.f);
+    for (uint32_t li = 0; li < d->n_lights; ++li) {
+        const SptLight &l = d->lights[li];
+        if (l.type != SPT_LIGHT_AREA) continue;
+        float *c = &cdf[l.shape_first + li];
+        int n = l.shape_count;
+        c[0] = 0.f;
+        for (int i = 1; i < n + 1; ++i) c[i] = c[i - 1] + d->light_shapes[l.shape_first + i - 1].area / n;
+        float funcInt = c[n];
+        if (funcInt == 0.f) for (int i = 1; i < n + 1; ++i) c[i] = float(i) / float(n);
+        else for (int i = 1; i < n + 1; ++i) c[i] /= funcInt;
+    }
+    DevMem &m = s->mem;
+    bool ok = true;
+#define UP(dst, src, n) do { dst = m.upload(src, (size_t)(n)); if (!dst) ok = false; } while (0)
+    const float4 *nodes4; UP(nodes4, (const float4 *)nodes.data(), (size_t)d->n_nodes * 2); v.nodes = nodes4;
+    UP(v.tri_verts, tv.data(), tv.size());
+    v.n_nodes = d->n_nodes; v.n_prims = d->n_prims;
+    UP(v.prim_kind, d->prim_kind, d->n_prims); UP(v.prim_flags, d->prim_flags, d->n_prims);
+    UP(v.prim_id, d->prim_id, d->n_prims); UP(v.prim_data, d->prim_data, d->n_prims);
+    UP(v.prim_material, d->prim_material, d->n_prims); UP(v.prim_light, d->prim_light, d->n_prims);
+    UP(v.prim_xform, d->prim_xform, d->n_prims);
+    UP(v.tri_vidx, d->tri_vidx, (size_t)d->n_tris * 3);
+    UP(v.P, d->P, (size_t)d->n_verts * 3); UP(v.N, d->N, (size_t)d->n_verts * 3); UP(v.UV, d->UV, (size_t)d->n_verts * 2);
+    UP(v.quadrics, d->quadrics, d->n_quadrics); UP(v.xforms, d->xforms, d->n_xforms);
+    UP(v.materials, d->materials, d->n_materials); UP(v.lights, d->lights, d->n_lights);
+    UP(v.light_shapes, d->light_shapes, d->n_light_shapes);
+    UP(v.light_cdf, cdf.data(), cdf.size());
+    v.n_lights = d->n_lights;
+    UP(v.tables, &d->tables, 1);
+    v.env_w = d->env_w; v.env_h = d->env_h;
+    size_t ew = (size_t)d->env_w, eh = (size_t)d->env_h;
+    UP(v.env_rgb, d->env_rgb, 3 * ew * eh); UP(v.env_func, d->env_func, ew * eh);
+    UP(v.env_cdf, d->env_cdf, (ew + 1) * eh); UP(v.env_func_int, d->env_func_int, eh);
+    UP(v.env_marg_func, d->env_marg_func, eh); UP(v.env_marg_cdf, d->env_marg_cdf, eh ? eh + 1 : 0);
+    v.env_marg_int = d->env_marg_int;
+#undef UP
+    s->counters = m.alloc<unsigned long long>(2);
+    if (!ok || !s->counters || cudaMemset(s->counters, 0, 16) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess) {
+        g_err = std::string("scene upload failed: ") + cudaGetErrorString(cudaGetLastError());
+        m.release();
+        delete s;
+        return nullptr;
+    }
+    v.counters = nullptr;
+    return s;
+}
+
+void spt_scene_destroy(SptScene *s) {
+    if (!s) return;
+    cudaDeviceSynchronize();
+    s->mem.release();
+    s->wave_mem.release();
+    if (s->stream) cudaStreamDestroy(s->stream);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    delete s;
+}
+
+int spt_scene_enable_counters(SptScene *s, int on) {
+    if (!s) return fail(SPT_ERR_ARG, "null scene");
+    s->counters_on = on != 0;
+    s->dev.counters = on ? s->counters : nullptr;
+    CU(cudaMemset(s->counters, 0, 16));
+    s->stats.node_visits = s->stats.prim_tests = 0;
+    return SPT_OK;
+}
+
+int spt_get_stats(SptScene *s, SptStats *out) {
+    if (!s || !out) return fail(SPT_ERR_ARG, "null argument");
+    if (s->counters_on) {
+        unsigned long long c[2];
+        CU(cudaMemcpy(c, s->counters, 16, cudaMemcpyDeviceToHost));
+        s->stats.node_visits = c[0]; s->stats.prim_tests = c[1];
+    }
+    s->stats.kernel_launches = s->launches;
+    *out = s->stats;
+    return SPT_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+static int ensure_wave(SptScene *s, uint32_t cap, int max_depth, size_t n_waves) {
+    size_t need_counts = n_waves * (size_t)(max_depth + 2) * 4;
+    if (s->wb.cap < cap) {
+        s->wave_mem.release();
+        s->counts = nullptr; s->counts_len = 0;
+        DevMem &m = s->wave_mem;
+        WaveBuffers &w = s->wb;
+        w.cap = cap;
+        bool ok = true;
+#define AL(field, T, n) do { field = m.alloc<T>((size_t)(n)); if (!field) ok = false; } while (0)
+        AL(w.ray_o, float4, cap); AL(w.ray_d, float4, cap); AL(w.hit_slot, uint32_t, cap); AL(w.hit_t, float, cap);
+        AL(w.g0, float4, cap); AL(w.g1, float4, cap); AL(w.g2, float4, cap); AL(w.g3, float4, cap);
+        AL(w.mis_slot, uint32_t, cap); AL(w.mis_t, float, cap); AL(w.sh_slot, uint32_t, cap);
+        AL(w.r0, float4, cap); AL(w.r1, float4, cap); AL(w.r2, float4, cap); AL(w.r3, float4, cap);
+        AL(w.r4, float4, cap); AL(w.r5, float4, cap); AL(w.r6, uint4, cap);
+        AL(w.img_xy, float2, cap);
+        AL(w.T, float, (size_t)cap * NB); AL(w.L, float, (size_t)cap * NB);
+        AL(w.pathQ[0], uint32_t, cap); AL(w.pathQ[1], uint32_t, cap); AL(w.shadowQ, uint32_t, cap); AL(w.misQ, uint32_t, cap);
+#undef AL
+        if (!ok) { s->wb.cap = 0; m.release(); return fail(SPT_ERR_CUDA, "out of device memory for wave buffers"); }
+    }
+    if (s->counts_len < need_counts) {
+        s->counts = s->wave_mem.alloc<uint32_t>(need_counts);
+        if (!s->counts) return fail(SPT_ERR_CUDA, "out of device memory for queue counters");
+        s->counts_len = need_counts;
+    }
+    return SPT_OK;
+}
+
+// Runs one wave: K1, then (K2, K5, K3, K2, K6) per bounce. counts: (max_depth+2) x 4 device words,
+// zeroed; row b = {path rays into bounce b, shadow rays of bounce b, MIS rays of bounce b, -}.
+static void run_wave(SptScene *s, const RenderCfg &cfg, const SampleSource &src, uint32_t *counts) {
+    cudaStream_t st = s->stream;
+    const WaveBuffers &wb = s->wb;
+    const DevScene &sc = s->dev;
+    int sms = num_sms();
+    int gridLight = sms * 8;
+    uint32_t n = cfg.n_samples;
+    int gridN = (int)std::min<uint64_t>(((uint64_t)n + 255) / 256, (uint64_t)sms * 16);
+    if (gridN < 1) gridN = 1;
+    k_gen_camera<<<gridN, 256, 0, st>>>(cfg, src, wb, counts + 0);
+    s->launches += 1;
+    int gridT = (int)std::min<uint64_t>(((uint64_t)n + 127) / 128, (uint64_t)sms * 16);
+    if (gridT < 1) gridT = 1;
+    (void)gridLight;
+    for (int b = 0; b <= cfg.max_depth; ++b) {
+        uint32_t *row = counts + 4 * b, *next = counts + 4 * (b + 1);
+        uint32_t *q = wb.pathQ[b & 1], *qn = wb.pathQ[(b + 1) & 1];
+        if (s->counters_on) k_trace<false, true><<<gridT, 128, 0, st>>>(sc, q, row + 0, wb.ray_o, wb.ray_d, wb.hit_slot, wb.hit_t);
+        else k_trace<false, false><<<gridT, 128, 0, st>>>(sc, q, row + 0, wb.ray_o, wb.ray_d, wb.hit_slot, wb.hit_t);
+        k_shade<<<gridT, 128, 0, st>>>(sc, cfg, src, wb, b, q, row + 0, row + 1, row + 2);
+        if (sc.n_lights > 0) {
+            if (s->counters_on) {
+                k_trace<true, true><<<gridT, 128, 0, st>>>(sc, wb.shadowQ, row + 1, wb.g0, wb.g1, wb.sh_slot, nullptr);
+                k_trace<false, true><<<gridT, 128, 0, st>>>(sc, wb.misQ, row + 2, wb.g0, wb.g2, wb.mis_slot, wb.mis_t);
+            } else {
+                k_trace<true, false><<<gridT, 128, 0, st>>>(sc, wb.shadowQ, row + 1, wb.g0, wb.g1, wb.sh_slot, nullptr);
+                k_trace<false, false><<<gridT, 128, 0, st>>>(sc, wb.misQ, row + 2, wb.g0, wb.g2, wb.mis_slot, wb.mis_t);
+            }
+            s->launches += 2;
+        }
+        k_accumulate<<<gridT, 128, 0, st>>>(sc, cfg, wb, b, q, row + 0, qn, next + 0);
+        s->launches += 3;
+    }
+}
+
+static void add_ray_stats(SptScene *s, const std::vector<uint32_t> &counts, int max_depth, size_t n_waves) {
+    for (size_t w = 0; w < n_waves; ++w)
+        for (int b = 0; b <= max_depth; ++b) {
+            const uint32_t *row = &counts[(w * (size_t)(max_depth + 2) + b) * 4];
+            s->stats.closest_rays += row[0] + row[2];
+            s->stats.any_rays += row[1];
+        }
+}
+
+extern "C" {
+
+int spt_camera_rays(const SptCameraDesc *cam, const float *samples, uint64_t n, float *out_rays) {
+    if (!cam || !samples || !out_rays) return fail(SPT_ERR_ARG, "null argument");
+    if (spt_device_count() <= 0) return fail(SPT_ERR_CUDA, "no CUDA device: this library has no CPU path");
+    if (n == 0) return SPT_OK;
+    DevMem m;
+    float *ds = m.upload(samples, n * 5), *dr = m.alloc<float>(n * 8);
+    if (!ds || !dr) { m.release(); return fail(SPT_ERR_CUDA, "device allocation failed"); }
+    k_camera_rays<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 65535), 256>>>(*cam, ds, (uint32_t)n, dr);
+    cudaError_t e = cudaMemcpy(out_rays, dr, n * 8 * sizeof(float), cudaMemcpyDeviceToHost);
+    m.release();
+    if (e != cudaSuccess) return fail(SPT_ERR_CUDA, cudaGetErrorString(e));
+    return SPT_OK;
+}
+
+static int trace_dev(SptScene *s, bool any, const float4 *ro, const float4 *rd, uint64_t n, uint32_t *slot, float *t,
+                     uint32_t *count_dev) {
+    int sms = num_sms();
+    int grid = (int)std::min<uint64_t>((n + 127) / 128, (uint64_t)sms * 16);
+    if (grid < 1) grid = 1;
+    cudaStream_t st = s->stream;
+    cudaEventRecord(s->ev0, st);
+    if (any) {
+        if (s->counters_on) k_trace<true, true><<<grid, 128, 0, st>>>(s->dev, nullptr, count_dev, ro, rd, slot, t);
+        else k_trace<true, false><<<grid, 128, 0, st>>>(s->dev, nullptr, count_dev, ro, rd, slot, t);
+    } else {
+        if (s->counters_on) k_trace<false, true><<<grid, 128, 0, st>>>(s->dev, nullptr, count_dev, ro, rd, slot, t);
+        else k_trace<false, false><<<grid, 128, 0, st>>>(s->dev, nullptr, count_dev, ro, rd, slot, t);
+    }
+    cudaEventRecord(s->ev1, st);
+    s->launches += 1;
+    CU(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, s->ev0, s->ev1);
+    s->stats.trace_ms = ms;
+    if (any) s->stats.any_rays += n; else s->stats.closest_rays += n;
+    return SPT_OK;
+}
+
+static int trace_host(SptScene *s, bool any, const float *rays, uint64_t n, uint32_t *out_slot, uint32_t *out_id,
+                      float *out_t, uint8_t *out_hit) {
+    if (!s || !rays) return fail(SPT_ERR_ARG, "null argument");
+    if (n == 0) return SPT_OK;
+    if (n > 0x7fffffffull) return fail(SPT_ERR_ARG, "too many rays for one call");
+    DevMem m;
+    float *dr = m.upload(rays, n * 8);
+    float4 *ro = m.alloc<float4>(n), *rd = m.alloc<float4>(n);
+    uint32_t *slot = m.alloc<uint32_t>(n), *ids = m.alloc<uint32_t>(n), *cnt = m.alloc<uint32_t>(1);
+    float *t = m.alloc<float>(n);
+    uint8_t *flag = m.alloc<uint8_t>(n);
+    if (!dr || !ro || !rd || !slot || !ids || !cnt || !t || !flag) { m.release(); return fail(SPT_ERR_CUDA, "device allocation failed"); }
+    uint32_t n32 = (uint32_t)n;
+    cudaMemcpyAsync(cnt, &n32, 4, cudaMemcpyHostToDevice, s->stream);
+    unsigned g = (unsigned)std::min<uint64_t>((n + 255) / 256, 65535);
+    k_split_rays<<<g, 256, 0, s->stream>>>(dr, n32, ro, rd);
+    int rc = trace_dev(s, any, ro, rd, n, slot, t, cnt);
+    if (rc == SPT_OK) {
+        cudaError_t e = cudaSuccess;
+        if (any) {
+            k_slot_to_flag<<<g, 256, 0, s->stream>>>(slot, n32, flag);
+            if (out_hit) e = cudaMemcpyAsync(out_hit, flag, n, cudaMemcpyDeviceToHost, s->stream);
+        } else {
+            k_slot_to_id<<<g, 256, 0, s->stream>>>(slot, s->dev.prim_id, n32, ids);
+            if (out_slot) e = cudaMemcpyAsync(out_slot, slot, n * 4, cudaMemcpyDeviceToHost, s->stream);
+            if (e == cudaSuccess && out_id) e = cudaMemcpyAsync(out_id, ids, n * 4, cudaMemcpyDeviceToHost, s->stream);
+            if (e == cudaSuccess && out_t) e = cudaMemcpyAsync(out_t, t, n * 4, cudaMemcpyDeviceToHost, s->stream);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+        if (e != cudaSuccess) rc = fail(SPT_ERR_CUDA, cudaGetErrorString(e));
+    }
+    m.release();
+    return rc;
+}
+
+int spt_trace_closest(SptScene *s, const float *rays, uint64_t n, uint32_t *out_slot, uint32_t *out_prim_id, float *out_t) {
+    return trace_host(s, false, rays, n, out_slot, out_prim_id, out_t, nullptr);
+}
+int spt_trace_any(SptScene *s, const float *rays, uint64_t n, uint8_t *out_hit) {
+    return trace_host(s, true, rays, n, nullptr, nullptr, nullptr, out_hit);
+}
+
+// Device-resident variants: rays_dev is n x 8 floats in HBM; outputs are device arrays.
+static int trace_resident(SptScene *s, bool any, const float *rays_dev, uint64_t n, uint32_t *slot_dev, float *t_dev,
+                          uint8_t *hit_dev) {
+    if (!s || !rays_dev) return fail(SPT_ERR_ARG, "null argument");
+    if (n == 0) return SPT_OK;
+    // scratch (split rays + count) is cached in the wave allocator's lifetime
+    static thread_local DevMem scratch;
+    static thread_local uint64_t scratch_n = 0;
+    static thread_local float4 *ro = nullptr, *rd = nullptr;
+    static thread_local uint32_t *cnt = nullptr, *slot_tmp = nullptr;
+    if (scratch_n < n) {
+        scratch.release();
+        ro = scratch.alloc<float4>(n); rd = scratch.alloc<float4>(n); cnt = scratch.alloc<uint32_t>(1);
+        slot_tmp = scratch.alloc<uint32_t>(n);
+        if (!ro || !rd || !cnt || !slot_tmp) { scratch.release(); scratch_n = 0; return fail(SPT_ERR_CUDA, "device allocation failed"); }
+        scratch_n = n;
+    }
+    uint32_t n32 = (uint32_t)n;
+    cudaMemcpyAsync(cnt, &n32, 4, cudaMemcpyHostToDevice, s->stream);
+    unsigned g = (unsigned)std::min<uint64_t>((n + 255) / 256, 65535);
+    k_split_rays<<<g, 256, 0, s->stream>>>(rays_dev, n32, ro, rd);
+    uint32_t *slot = any ? slot_tmp : (slot_dev ? slot_dev : slot_tmp);
+    int rc = trace_dev(s, any, ro, rd, n, slot, t_dev, cnt);
+    if (rc != SPT_OK) return rc;
+    if (any && hit_dev) { k_slot_to_flag<<<g, 256, 0, s->stream>>>(slot, n32, hit_dev); CU(cudaStreamSynchronize(s->stream)); }
+    return SPT_OK;
+}
+int spt_trace_closest_dev(SptScene *s, const float *rays_dev, uint64_t n, uint32_t *out_slot_dev, float *out_t_dev) {
+    if (!out_t_dev) return fail(SPT_ERR_ARG, "out_t_dev is required");
+    return trace_resident(s, false, rays_dev, n, out_slot_dev, out_t_dev, nullptr);
+}
+int spt_trace_any_dev(SptScene *s, const float *rays_dev, uint64_t n, uint8_t *out_hit_dev) {
+    return trace_resident(s, true, rays_dev, n, nullptr, nullptr, out_hit_dev);
+}
+
+int spt_shade_samples(SptScene *s, const SptCameraDesc *cam, int32_t max_depth, const float *samples, const float *rng,
+                      int32_t n_rng, uint64_t n, float *out_L) {
+    if (!s || !cam || !samples || !out_L) return fail(SPT_ERR_ARG, "null argument");
+    if (n == 0) return SPT_OK;
+    if (n > (1u << 26)) return fail(SPT_ERR_ARG, "too many samples for one call");
+    int rc = ensure_wave(s, (uint32_t)n, max_depth, 1);
+    if (rc != SPT_OK) return rc;
+    DevMem m;
+    float *dsmp = m.upload(samples, n * 37);
+    float *drng = (rng && n_rng > 0) ? m.upload(rng, n * (size_t)n_rng) : nullptr;
+    float *dout = m.alloc<float>(n * NB);
+    if (!dsmp || !dout || (rng && n_rng > 0 && !drng)) { m.release(); return fail(SPT_ERR_CUDA, "device allocation failed"); }
+    RenderCfg cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.cam = *cam; cfg.spp = 1; cfg.max_depth = max_depth; cfg.n_samples = (uint32_t)n;
+    cfg.tile = 1; cfg.tilesX = 1; cfg.tilesY = 1; cfg.nranks = 1;
+    SampleSource src; src.smp = dsmp; src.rng = drng; src.n_rng = drng ? n_rng : 0; src.seed = 0; src.spp = 1;
+    size_t nc = (size_t)(max_depth + 2) * 4;
+    cudaMemsetAsync(s->counts, 0, nc * 4, s->stream);
+    run_wave(s, cfg, src, s->counts);
+    k_gather_L<<<(unsigned)std::min<uint64_t>((n * NB + 255) / 256, 65535), 256, 0, s->stream>>>(s->wb.L, s->wb.cap, (uint32_t)n, dout);
+    std::vector<uint32_t> hc(nc);
+    cudaMemcpyAsync(hc.data(), s->counts, nc * 4, cudaMemcpyDeviceToHost, s->stream);
+    cudaError_t e = cudaMemcpyAsync(out_L, dout, n * NB * sizeof(float), cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    m.release();
+    if (e != cudaSuccess) return fail(SPT_ERR_CUDA, cudaGetErrorString(e));
+    s->stats.camera_samples += n;
+    add_ray_stats(s, hc, max_depth, 1);
+    return SPT_OK;
+}
+
+// ---- film ---------------------------------------------------------------------------------------
+static SptFilm *film_new(const SptFilmDesc *d, float *ext) {
+    if (!d) { g_err = "null film desc"; return nullptr; }
+    if (d->x_pixel_count <= 0 || d->y_pixel_count <= 0) { g_err = "empty film"; return nullptr; }
+    if (spt_device_count() <= 0) { g_err = "no CUDA device: this library has no CPU path"; return nullptr; }
+    SptFilm *f = new SptFilm();
+    f->desc = *d;
+    f->owned = ext == nullptr;
+    f->pix = ext;
+    size_t bytes = f->npix() * (NB + 1) * sizeof(float);
+    if (!ext) {
+        if (cudaMalloc((void **)&f->pix, bytes) != cudaSuccess || cudaMemset(f->pix, 0, bytes) != cudaSuccess) {
+            g_err = std::string("film allocation failed: ") + cudaGetErrorString(cudaGetLastError());
+            delete f; return nullptr;
+        }
+    }
+    if (cudaMalloc((void **)&f->table, 256 * sizeof(float)) != cudaSuccess ||
+        cudaMemcpy(f->table, d->filter_table, 256 * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+        g_err = "film filter table upload failed";
+        if (f->owned) cudaFree(f->pix);
+        delete f; return nullptr;
+    }
+    return f;
+}
+SptFilm *spt_film_create(const SptFilmDesc *d) { return film_new(d, nullptr); }
+SptFilm *spt_film_create_external(const SptFilmDesc *d, float *pixels_dev) {
+    if (!pixels_dev) { g_err = "null device buffer"; return nullptr; }
+    return film_new(d, pixels_dev);
+}
+void spt_film_destroy(SptFilm *f) {
+    if (!f) return;
+    cudaDeviceSynchronize();
+    if (f->owned) cudaFree(f->pix);
+    cudaFree(f->table);
+    delete f;
+}
+int spt_film_clear(SptFilm *f) {
+    if (!f) return fail(SPT_ERR_ARG, "null film");
+    CU(cudaMemset(f->pix, 0, f->npix() * (NB + 1) * sizeof(float)));
+    return SPT_OK;
+}
+float *spt_film_device_ptr(SptFilm *f) { return f ? f->pix : nullptr; }
+
+int spt_film_download(SptFilm *f, float *c, float *weight) {
+    if (!f) return fail(SPT_ERR_ARG, "null film");
+    size_t np = f->npix();
+    std::vector<float> host(np * (NB + 1));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(host.data(), f->pix, host.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    for (size_t p = 0; p < np; ++p) {
+        if (c) memcpy(c + p * NB, &host[p * (NB + 1)], NB * sizeof(float));
+        if (weight) weight[p] = host[p * (NB + 1) + NB];
+    }
+    return SPT_OK;
+}
+
+int spt_film_write_dat(SptFilm *f, const char *path) {
+    if (!f || !path) return fail(SPT_ERR_ARG, "null argument");
+    size_t np = f->npix();
+    std::vector<float> c(np * NB);
+    int rc = spt_film_download(f, c.data(), nullptr);
+    if (rc != SPT_OK) return rc;
+    FILE *fp = fopen(path, "wb");
+    if (!fp) return fail(SPT_ERR_IO, std::string("cannot open ") + path);
+    int W = f->desc.x_pixel_count, H = f->desc.y_pixel_count;
+    // spectralImage.cpp:344-352: dimensions line, then the lens line (focalLength fStop fieldOfView;
+    // uninitialised in the reference for non-lens cameras, SURVEY.md F5 — zeros here)
+    fprintf(fp, "%d %d %d\n", W, H, NB);
+    fprintf(fp, "0 0 0\n");
+    // spectralImage.cpp:283-296,320-369: clamp at zero, no division by weightSum, [band][x][y] doubles
+    std::vector<double> plane(np);
+    for (int b = 0; b < NB; ++b) {
+        for (int x = 0; x < W; ++x)
+            for (int y = 0; y < H; ++y) {
+                float v = c[((size_t)y * W + x) * NB + b];
+                plane[(size_t)x * H + y] = (double)(v > 0.f ? v : 0.f);
+            }
+        fwrite(plane.data(), sizeof(double), np, fp);
+    }
+    fclose(fp);
+    return SPT_OK;
+}
+
+int spt_film_add_samples(SptFilm *f, const SptSpectralTables *tables, const float *image_xy, const float *L, uint64_t n) {
+    if (!f || !tables || !image_xy || !L) return fail(SPT_ERR_ARG, "null argument");
+    if (n == 0) return SPT_OK;
+    DevMem m;
+    SptSpectralTables *dt = m.upload(tables, 1);
+    float2 *dxy = (float2 *)m.upload(image_xy, n * 2);
+    float *dl = m.upload(L, n * NB), *soa = m.alloc<float>(n * NB);
+    if (!dt || !dxy || !dl || !soa) { m.release(); return fail(SPT_ERR_CUDA, "device allocation failed"); }
+    unsigned g = (unsigned)std::min<uint64_t>((n * NB + 255) / 256, 65535);
+    k_scatter_L<<<g, 256>>>(dl, (uint32_t)n, (uint32_t)n, soa);
+    FilmView fv; fv.d = f->desc; fv.pix = f->pix; fv.table = f->table;
+    unsigned gw = (unsigned)std::min<uint64_t>((n * 32 + 255) / 256, (uint64_t)num_sms() * 16);
+    k_film_add<<<gw, 256>>>(fv, dt, dxy, soa, (uint32_t)n, (uint32_t)n, 1);
+    cudaError_t e = cudaDeviceSynchronize();
+    m.release();
+    if (e != cudaSuccess) return fail(SPT_ERR_CUDA, cudaGetErrorString(e));
+    return SPT_OK;
+}
+
+// ---- the whole job -------------------------------------------------------------------------------
+int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRenderParams *rp) {
+    if (!s || !cam || !film || !rp) return fail(SPT_ERR_ARG, "null argument");
+    if (rp->spp <= 0 || (rp->spp & (rp->spp - 1))) return fail(SPT_ERR_ARG, "spp must be a power of two (LDSampler rounds up)");
+    if (rp->max_depth < 0 || rp->max_depth > 64) return fail(SPT_ERR_ARG, "max_depth out of range");
+    int nranks = rp->tile_nranks > 0 ? rp->tile_nranks : 1;
+    if (rp->tile_rank < 0 || rp->tile_rank >= nranks) return fail(SPT_ERR_ARG, "tile_rank out of range");
+    RenderCfg cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.cam = *cam; cfg.spp = rp->spp; cfg.max_depth = rp->max_depth;
+    cfg.x0 = rp->x_start; cfg.y0 = rp->y_start; cfg.x1 = rp->x_end; cfg.y1 = rp->y_end;
+    const SptFilmDesc &fd = film->desc;
+    if (rp->skip_border) {
+        cfg.x1 = std::min(cfg.x1, fd.x_pixel_start + fd.x_pixel_count);
+        cfg.y1 = std::min(cfg.y1, fd.y_pixel_start + fd.y_pixel_count);
+    }
+    if (cfg.x1 <= cfg.x0 || cfg.y1 <= cfg.y0) return fail(SPT_ERR_ARG, "empty sample extent");
+    cfg.tile = rp->tile_size > 0 ? rp->tile_size : 32;
+    cfg.tilesX = (cfg.x1 - cfg.x0 + cfg.tile - 1) / cfg.tile;
+    cfg.tilesY = (cfg.y1 - cfg.y0 + cfg.tile - 1) / cfg.tile;
+    cfg.rank = rp->tile_rank; cfg.nranks = nranks;
+    cfg.seed = (uint32_t)(rp->seed ^ (rp->seed >> 32));
+    uint64_t ntiles = (uint64_t)cfg.tilesX * cfg.tilesY;
+    uint64_t local_tiles = ntiles > (uint64_t)cfg.rank ? (ntiles - cfg.rank + nranks - 1) / nranks : 0;
+    uint64_t local_pixels = local_tiles * (uint64_t)cfg.tile * cfg.tile;
+    uint64_t wave_pixels = rp->wave_pixels > 0 ? (uint64_t)rp->wave_pixels : std::max<uint64_t>(1, (1u << 22) / (uint64_t)rp->spp);
+    wave_pixels = std::min<uint64_t>(wave_pixels, std::max<uint64_t>(local_pixels, 1));
+    if (wave_pixels * rp->spp > (1ull << 27)) wave_pixels = (1ull << 27) / rp->spp;
+    size_t n_waves = (size_t)((local_pixels + wave_pixels - 1) / wave_pixels);
+    int rc = ensure_wave(s, (uint32_t)(wave_pixels * rp->spp), rp->max_depth, std::max<size_t>(n_waves, 1));
+    if (rc != SPT_OK) return rc;
+    size_t per_wave = (size_t)(rp->max_depth + 2) * 4;
+    cudaStream_t st = s->stream;
+    CU(cudaMemsetAsync(s->counts, 0, std::max<size_t>(n_waves, 1) * per_wave * 4, st));
+    SampleSource src; src.smp = nullptr; src.rng = nullptr; src.n_rng = 0; src.seed = cfg.seed; src.spp = (uint32_t)rp->spp;
+    FilmView fv; fv.d = film->desc; fv.pix = film->pix; fv.table = film->table;
+    CU(cudaEventRecord(s->ev0, st));
+    uint64_t samples = 0;
+    for (size_t w = 0; w < n_waves; ++w) {
+        cfg.pixel_base = (uint64_t)w * wave_pixels;
+        uint64_t np = std::min<uint64_t>(wave_pixels, local_pixels - cfg.pixel_base);
+        cfg.n_samples = (uint32_t)(np * rp->spp);
+        run_wave(s, cfg, src, s->counts + w * per_wave);
+        unsigned gw = (unsigned)std::min<uint64_t>((np * 32 + 255) / 256, (uint64_t)num_sms() * 16);
+        k_film_add<<<gw, 256, 0, st>>>(fv, s->dev.tables, s->wb.img_xy, s->wb.L, s->wb.cap, cfg.n_samples, rp->spp);
+        s->launches += 1;
+    }
+    CU(cudaEventRecord(s->ev1, st));
+    std::vector<uint32_t> hc(std::max<size_t>(n_waves, 1) * per_wave);
+    CU(cudaMemcpyAsync(hc.data(), s->counts, hc.size() * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, s->ev0, s->ev1);
+    s->stats.render_ms = ms;
+    for (size_t w = 0; w < n_waves; ++w) samples += hc[w * per_wave];
+    s->stats.camera_samples += samples;
+    add_ray_stats(s, hc, rp->max_depth, n_waves);
+    return SPT_OK;
+}
+
+}  // extern "C"

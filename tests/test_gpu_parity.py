@@ -1,0 +1,124 @@
+"""-m gpu: the CUDA path (through the C ABI, host buffers) against the reference-pinned oracle and
+the golden vectors the reference itself produced."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from pbrt_v2_spectral_b200 import capi, ctypes_defs as D
+
+pytestmark = pytest.mark.gpu
+CASES = O.golden_cases()
+
+
+@pytest.fixture(scope="module", params=CASES, ids=[c[0] for c in CASES])
+def case(request):
+    name, sp, gp = request.param
+    lowered, g = O.load_case(sp, gp)
+    scene = capi.Scene(lowered)
+    yield name, lowered, scene, g
+    scene.close()
+
+
+def test_camera_rays_bit_exact(case):
+    _, lowered, _, g = case
+    rays = capi.camera_rays(lowered.camera, g["samples"][:, :5])
+    assert np.array_equal(rays.view(np.uint32), g["rays"].view(np.uint32))
+
+
+def test_first_hit_ids_bit_exact_t_1e5(case):
+    """north_star: camera-ray first-hit ids bit-exact, t within 1e-5 relative (here: identical bits)."""
+    _, _, scene, g = case
+    slot, pid, t = scene.trace_closest(g["rays"])
+    assert np.array_equal(pid, g["prim_id"])
+    hit = pid != 0
+    rel = np.abs(t[hit] - g["t_hit"][hit]) / g["t_hit"][hit]
+    assert rel.max() <= 1e-5
+    assert np.array_equal(t.view(np.uint32), g["t_hit"].view(np.uint32))
+
+
+def test_secondary_rays(case):
+    _, _, scene, g = case
+    m = g["prim_id"] != 0
+    unbounded = g["rays2"][m].copy()
+    unbounded[:, 7] = np.inf
+    slot, pid, t = scene.trace_closest(unbounded)
+    assert np.array_equal(pid, g["prim_id2"][m])
+    assert np.array_equal(t.view(np.uint32), g["t_hit2"][m].view(np.uint32))
+    assert np.array_equal(scene.trace_any(g["rays2"][m]), g["any2"][m])
+
+
+def test_path_radiance_vs_reference(case):
+    """PathIntegrator::Li for the reference's own sample vectors and RNG draws. CUDA's sinf/cosf/powf/
+    atan2f/acosf differ from glibc's by an ulp or two, so radiance is compared at 2e-4 relative per
+    sample, with a small allowance for samples where that ulp flips a discrete decision."""
+    name, _, scene, g = case
+    L = scene.shade_samples(g["samples"], g["rng"])
+    ref = g["L"]
+    scale = np.maximum(np.abs(ref).max(axis=1), 1e-6)
+    err = np.abs(L - ref).max(axis=1) / scale
+    bad = err > 2e-4
+    assert bad.mean() < 2e-3, "%s: %d of %d samples differ (worst %g)" % (name, bad.sum(), len(bad), err.max())
+    tot = ref.sum(0)
+    assert np.all(np.abs(L.sum(0) - tot) <= 2e-3 * tot + 1e-6), "per-band totals drift"
+
+
+def test_film_add_samples(case):
+    name, lowered, scene, g = case
+    xy = g["samples"][:, :2].copy()
+    L = g["L"].copy()
+    # exercise the guards (NaN / inf -> black) and a sample that rounds onto a pixel edge
+    L[0, 3] = np.nan
+    L[1, 5] = np.inf
+    xy[2, 0] = np.floor(xy[2, 0])
+    film = capi.Film(lowered.film)
+    film.add_samples(lowered.tables, xy, L)
+    c, w = film.download()
+    film.close()
+    oc, ow = O.film_add_samples(lowered, xy, L)
+    assert np.array_equal(w, ow)
+    assert np.allclose(c, oc, rtol=1e-5, atol=1e-6)
+
+
+def test_render_matches_oracle_render():
+    """Whole job (K1..K7 with the product sampler, compaction, film) against the oracle running the
+    same sampler on the CPU, small image."""
+    lowered, _ = O.load_case(*CASES[0][1:])
+    scene = capi.Scene(lowered)
+    rp = D.SptRenderParams.from_buffer_copy(bytes(lowered.params))
+    rp.spp = 8
+    rp.seed = 7
+    rp.wave_pixels = 600          # several waves
+    film = capi.Film(lowered.film)
+    scene.render(film, rp)
+    c, w = film.download()
+    st = scene.stats()
+    film.close(); scene.close()
+    oc, ow = O.render(lowered, rp)
+    assert np.array_equal(w, ow)
+    assert st["camera_samples"] == (rp.x_end - rp.x_start) * (rp.y_end - rp.y_start) * rp.spp
+    scale = np.maximum(oc.max(axis=2, keepdims=True), 1e-3)
+    err = (np.abs(c - oc) / scale).max(axis=2)
+    assert (err > 1e-3).mean() < 5e-3, "pixels differ: %d of %d (worst %g)" % ((err > 1e-3).sum(), err.size, err.max())
+    assert np.allclose(c.sum((0, 1)), oc.sum((0, 1)), rtol=2e-3)
+
+
+def test_tile_sets_partition_the_image():
+    """Multi-GPU split: rendering the N tile sets separately and summing equals the single render."""
+    lowered, _ = O.load_case(*CASES[0][1:])
+    scene = capi.Scene(lowered)
+    rp = D.SptRenderParams.from_buffer_copy(bytes(lowered.params))
+    rp.spp = 4
+    rp.tile_size = 8
+    film = capi.Film(lowered.film)
+    scene.render(film, rp)
+    c1, w1 = film.download()
+    film.clear()
+    for r in range(3):
+        rp.tile_rank, rp.tile_nranks = r, 3
+        scene.render(film, rp)
+    c3, w3 = film.download()
+    film.close(); scene.close()
+    assert np.array_equal(w1, w3)
+    assert np.allclose(c1, c3, rtol=1e-5, atol=1e-6)
