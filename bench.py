@@ -1,0 +1,349 @@
+#!/usr/bin/env python3
+"""bench.py — measures BASELINE.json's metric (Msamples/s of the spectral path trace) on its
+config 1: killeroo-simple, path integrator maxdepth 5, 32-band SampledSpectrum as the reference
+ships it, LD sampler 64 spp, 700x700, box filter.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]          # this repo's CUDA path
+    python bench.py --impl reference [...]                       # the reference's own CPU renderer
+
+A step is one whole render of the frame (every camera sample of the sample extent, 701 x 701 x 64 =
+31 449 664, the same count the reference traces). `value` times spt_render with the scene resident
+in HBM (CUDA events on the library's stream); `e2e` times the C-ABI call sequence a host makes with
+HOST buffers: spt_scene_create (H2D of every scene table) -> spt_film_create -> spt_render ->
+spt_film_download (D2H of the film). Multi-GPU: scene replicated, image tile sets per rank, film
+reduced to rank 0 with NCCL; device-timed, max over ranks.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import re
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "killeroo_path"
+WORKLOAD_DESC = "scenes/killeroo-simple.pbrt, path integrator maxdepth 5, SampledSpectrum 32 bands (as shipped), LD 64 spp, 700x700, box filter"
+SCENE_SPT = os.path.join(ROOT, "assets", "_lowered", WORKLOAD + ".spt")
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "bin", "pbrt")
+REF_SCENES = os.path.join(ROOT, "oracle", "_ref", "scenes")
+CPU_SAMPLE_SPP = 16          # bounded sample of the workload for the CPU arm: same frame, 16 of the 64 spp
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = "index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.rows = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([v.strip() for v in line.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 7 for k in range(4) if r[3 + k].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------------
+def reference_run(scene_text, ncores):
+    """One run of the reference binary on scene_text; returns wall seconds."""
+    d = tempfile.mkdtemp(prefix="sptref_")
+    try:
+        for sub in ("geometry", "spds", "brdfs"):
+            os.symlink(os.path.join(REF_SCENES, sub), os.path.join(d, sub))
+        with open(os.path.join(d, "scene.pbrt"), "w") as f:
+            f.write(scene_text)
+        t0 = time.perf_counter()
+        subprocess.run([REF_BIN, "--quiet", "--ncores", str(ncores), "scene.pbrt"], cwd=d, check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        return time.perf_counter() - t0
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+def reference_scene(spp, res=None):
+    s = open(os.path.join(REF_SCENES, WORKLOAD + ".pbrt")).read()
+    s = re.sub(r'"integer pixelsamples" \[\d+\]', '"integer pixelsamples" [%d]' % spp, s)
+    if res:
+        s = re.sub(r'"integer xresolution" \[\d+\] "integer yresolution" \[\d+\]',
+                   '"integer xresolution" [%d] "integer yresolution" [%d]' % (res, res), s, count=1)
+    return s
+
+
+def cpu_reference_msamples(runs=1):
+    """Msamples/s of the unmodified reference (oracle/_ref/bin/pbrt, all host cores) on the bounded
+    sample: the workload's frame at CPU_SAMPLE_SPP spp. Parse + BVH build time (the same scene at 8x8, 1 spp)
+    is subtracted, SURVEY.md 8d."""
+    ncores = os.cpu_count() or 1
+    setup = min(reference_run(reference_scene(1, 8), ncores) for _ in range(2))
+    best = min(reference_run(reference_scene(CPU_SAMPLE_SPP), ncores) for _ in range(runs))
+    n_samples = 701 * 701 * CPU_SAMPLE_SPP
+    render = max(best - setup, 1e-6)
+    return n_samples / render / 1e6, ncores, render, setup
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    if not os.path.exists(REF_BIN):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/bin/pbrt not built (build() needs /root/reference)"}))
+        return
+    ncores = os.cpu_count() or 1
+    setup = min(reference_run(reference_scene(1, 8), ncores) for _ in range(2))
+    times = []
+    for i in range(args.warmup + args.steps):
+        t = reference_run(reference_scene(CPU_SAMPLE_SPP), ncores)
+        if i >= args.warmup:
+            times.append(max(t - setup, 1e-6))
+    n_samples = 701 * 701 * CPU_SAMPLE_SPP
+    ms = 1e3 * sum(times) / len(times)
+    value = n_samples / (ms / 1e3) / 1e6
+    sample = "same frame (700x700, sample extent 701x701) at %d of the 64 spp per step; parse+BVH build (%.2fs, 8x8 1spp run) subtracted" % (CPU_SAMPLE_SPP, setup)
+    print(json.dumps({
+        "impl": "reference", "metric": "Msamples/sec (32-band spectral path trace)", "value": value, "unit": "Msamples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "reference scene file (killeroo-simple) derived per SURVEY.md F9",
+        "config": {"workload": WORKLOAD_DESC, "reference_binary": "oracle/_ref/bin/pbrt (unmodified reference, g++ -O2 -m64)"},
+        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": ncores, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--wave-pixels", type=int, default=0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import numpy as np
+    import torch
+    from pbrt_v2_spectral_b200 import capi, ctypes_defs as D
+    from pbrt_v2_spectral_b200.scene_io import LoweredScene
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    capi.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    if not os.path.exists(SCENE_SPT):
+        raise SystemExit("lowered workload scene %s missing: run __graft_entry__.build() where the reference tree is" % SCENE_SPT)
+    lowered = LoweredScene.load(SCENE_SPT)
+    rp = D.SptRenderParams.from_buffer_copy(bytes(lowered.params))
+    rp.seed = 1
+    rp.tile_rank, rp.tile_nranks, rp.tile_size = rank, world, 32
+    rp.wave_pixels = args.wave_pixels
+    fd = lowered.film
+    n_samples_total = (rp.x_end - rp.x_start) * (rp.y_end - rp.y_start) * rp.spp
+
+    scene = capi.Scene(lowered)
+    film_t = torch.zeros((fd.y_pixel_count, fd.x_pixel_count, D.NBANDS + 1), dtype=torch.float32, device=dev)
+    film = capi.Film(fd, film_t.data_ptr())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- untimed counted pass: BVH nodes visited / primitives tested per ray class (roofline's algorithmic bytes)
+    scene.enable_counters(True)
+    scene.render(film, rp)
+    cst = scene.stats()
+    scene.enable_counters(False)
+    rays_path = max(cst["class_rays"][D.K_TRACE_PATH], 1)
+    rays_mis = cst["class_rays"][D.K_TRACE_MIS]
+    rays_sh = max(cst["class_rays"][D.K_TRACE_SHADOW], 1)
+    nodes_per_closest = cst["node_visits_closest"] / max(rays_path + rays_mis, 1)
+    prims_per_closest = cst["prim_tests_closest"] / max(rays_path + rays_mis, 1)
+    nodes_per_any = cst["node_visits_any"] / rays_sh
+    prims_per_any = cst["prim_tests_any"] / rays_sh
+
+    # ---- warm-up, then the timed steps
+    for _ in range(max(args.warmup, 3)):
+        film_t.zero_()
+        scene.render(film, rp)
+        if dist is not None:
+            dist.reduce(film_t, dst=0)
+    barrier()
+    launches0 = scene.stats()["kernel_launches"]
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    class_ms = [0.0] * D.K_CLASSES
+    class_launches = [0] * D.K_CLASSES
+    class_rays = [0] * D.K_CLASSES
+    render_ms = 0.0
+    e0.record()
+    for _ in range(args.steps):
+        film_t.zero_()
+        scene.render(film, rp)                       # blocks until the library's stream has drained
+        if dist is not None:
+            dist.reduce(film_t, dst=0)               # film gather over NVLink
+        st = scene.stats()
+        render_ms += st["render_ms"]
+        for k in range(D.K_CLASSES):
+            class_ms[k] += st["class_ms"][k]; class_launches[k] += st["class_launches"][k]; class_rays[k] += st["class_rays"][k]
+    e1.record()
+    barrier()
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join()
+    step_ms = e0.elapsed_time(e1) / args.steps
+    launches = scene.stats()["kernel_launches"] - launches0
+    if dist is not None:
+        t = torch.tensor([step_ms, render_ms / args.steps], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        step_ms, render_only_ms = float(t[0]), float(t[1])
+        lt = torch.tensor([launches], device=dev, dtype=torch.int64)
+        dist.all_reduce(lt)
+        launches = int(lt[0])
+    else:
+        render_only_ms = render_ms / args.steps
+    # N=1: the job is spt_render itself (library events); N>1: render + NCCL reduce (max over ranks)
+    ms_per_step = render_only_ms if world == 1 else step_ms
+    value = n_samples_total / (ms_per_step / 1e3) / 1e6
+    image_sum = float(film_t[..., :D.NBANDS].sum()) if rank == 0 else 0.0
+
+    # ---- e2e through the C ABI with host buffers (rank-local: each rank uploads, renders its tiles, downloads)
+    scene_bytes = int(sum(v.nbytes for k, v in lowered.a.items() if k not in ("camera", "film", "params", "film_filename")))
+    film_bytes = fd.x_pixel_count * fd.y_pixel_count * (D.NBANDS + 1) * 4
+    c_host = np.empty((fd.y_pixel_count, fd.x_pixel_count, D.NBANDS), np.float32)
+    w_host = np.empty((fd.y_pixel_count, fd.x_pixel_count), np.float32)
+    e2e_times = []
+    for i in range(1 + args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        sc2 = capi.Scene(lowered)                    # H2D: every scene table from host memory
+        f2 = capi.Film(fd)
+        sc2.render(f2, rp)
+        f2.download((c_host, w_host))                # D2H: the film
+        t1 = time.perf_counter()
+        f2.close(); sc2.close()
+        if i > 0:
+            e2e_times.append(t1 - t0)
+    e2e_s = sum(e2e_times) / len(e2e_times)
+    if dist is not None:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t[0])
+    e2e_value = n_samples_total / e2e_s / 1e6
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel class (algorithmic bytes: SURVEY.md 8d)
+    peak, peak_src = read_peaks()
+    dom = max(range(D.K_CLASSES), key=lambda k: class_ms[k])
+    def ray_bytes(k):
+        if k in (D.K_TRACE_PATH, D.K_TRACE_MIS):
+            return 32.0 * nodes_per_closest + 48.0 * prims_per_closest + 40.0
+        if k == D.K_TRACE_SHADOW:
+            return 32.0 * nodes_per_any + 48.0 * prims_per_any + 40.0
+        return None
+    # trace classes are the roofline subject; if a shading class ever dominates, report the trace class with most time
+    if ray_bytes(dom) is None:
+        dom = max((D.K_TRACE_PATH, D.K_TRACE_SHADOW, D.K_TRACE_MIS), key=lambda k: class_ms[k])
+    bytes_total = ray_bytes(dom) * class_rays[dom]
+    dom_ms = class_ms[dom]
+    achieved = bytes_total / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(D.K_NAMES[dom])
+        except Exception:
+            traffic = None
+    total_class = sum(class_ms)
+    roofline = {
+        "bound": "hbm", "kernel": "k_trace (%s)" % D.K_NAMES[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+        "bytes_per_ray": ray_bytes(dom), "rays_per_launch": class_rays[dom] / max(class_launches[dom], 1),
+        "avg_launch_ms": dom_ms / max(class_launches[dom], 1), "share_of_step": dom_ms / total_class if total_class else None,
+        "nodes_per_closest_ray": nodes_per_closest, "prim_tests_per_closest_ray": prims_per_closest,
+        "nodes_per_shadow_ray": nodes_per_any, "prim_tests_per_shadow_ray": prims_per_any,
+        "note": "BVH (4 MB) is L2-resident on this workload: the fraction is of the HBM copy peak, the bound in practice is L2/latency",
+    }
+    rays_total = class_rays[D.K_TRACE_PATH] + class_rays[D.K_TRACE_MIS] + class_rays[D.K_TRACE_SHADOW]
+    out = {
+        "metric": "Msamples/sec (32-band spectral path trace)", "value": value, "unit": "Msamples/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "reference scene file (killeroo-simple) lowered by the host side; no synthetic substitution",
+        "config": {"workload": WORKLOAD_DESC, "camera_samples_per_step": n_samples_total,
+                   "parallelism": "image tile sets (32x32, round-robin) x%d, scene replicated, NCCL film reduce" % world,
+                   "l2": "per-step wave state (>2 GB) and film are larger than L2; no explicit flush"},
+        "mrays_per_s": rays_total / args.steps / (ms_per_step / 1e3) / 1e6 if world == 1 else None,
+        "rays_per_sample": rays_total / args.steps / (n_samples_total / world) if world else None,
+        "kernel_ms_per_step": {D.K_NAMES[k]: class_ms[k] / args.steps for k in range(D.K_CLASSES) if class_launches[k]},
+        "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": scene_bytes, "d2h_bytes_per_step": film_bytes,
+                "ms_per_step": e2e_s * 1e3, "path": "spt_scene_create+spt_film_create+spt_render+spt_film_download, host buffers"},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "clocks": sampler.summary() if sampler else None,
+        "image_checksum": image_sum,
+    }
+    if world == 1 and not args.no_cpu_baseline and os.path.exists(REF_BIN):
+        v, cores, render_s, setup_s = cpu_reference_msamples()
+        out["cpu_baseline"] = {"value": v, "unit": "Msamples/s", "cores": cores, "kind": "reference",
+                               "sample": "reference pbrt on the same frame at %d of 64 spp (%.1f s render, %.2f s parse+BVH subtracted)" % (CPU_SAMPLE_SPP, render_s, setup_s)}
+    else:
+        out["cpu_baseline"] = None
+    print(json.dumps(out))
+    film.close(); scene.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

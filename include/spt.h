@@ -177,13 +177,21 @@ typedef struct SptRenderParams {
                                        box filter rejects */
 } SptRenderParams;
 
+/* kernel classes of the wavefront, for per-class device time (CUDA events on the launching stream) */
+enum { SPT_K_GEN = 0, SPT_K_TRACE_PATH = 1, SPT_K_SHADE = 2, SPT_K_TRACE_SHADOW = 3, SPT_K_TRACE_MIS = 4,
+       SPT_K_ACCUMULATE = 5, SPT_K_FILM = 6, SPT_K_CLASSES = 8 };
+
 typedef struct SptStats {
-    uint64_t camera_samples;        /* samples traced */
-    uint64_t closest_rays, any_rays;
-    uint64_t node_visits, prim_tests;     /* only when counters are enabled */
-    uint64_t kernel_launches;
-    double   render_ms;             /* CUDA-event time of the last spt_render */
-    double   trace_ms;              /* CUDA-event time of the last spt_trace_* kernel */
+    uint64_t camera_samples;        /* samples traced (cumulative) */
+    uint64_t closest_rays, any_rays;    /* rays traced (cumulative) */
+    /* device counters, only while spt_scene_enable_counters(on): BVH nodes visited / primitives tested */
+    uint64_t node_visits_closest, prim_tests_closest, node_visits_any, prim_tests_any;
+    uint64_t kernel_launches;       /* cumulative */
+    double   render_ms;             /* CUDA-event time of the last spt_render, first launch -> film final */
+    double   trace_ms;              /* CUDA-event time of the last stand-alone spt_trace_* kernel */
+    double   class_ms[SPT_K_CLASSES];        /* last spt_render: device time per kernel class */
+    uint64_t class_launches[SPT_K_CLASSES];  /* last spt_render: launches per kernel class */
+    uint64_t class_rays[SPT_K_CLASSES];      /* last spt_render: rays (or paths) processed per class */
 } SptStats;
 
 typedef struct SptScene SptScene;

@@ -23,6 +23,7 @@ OUT = os.path.join(HERE, "_ref")
 SCENES = os.path.join(OUT, "scenes")
 GOLDEN = os.path.join(OUT, "golden")
 TESTS_GOLDEN = os.path.join(REPO, "tests", "golden")
+LOWERED = os.path.join(REPO, "assets", "_lowered")
 
 
 def read(p):
@@ -142,7 +143,10 @@ def main():
         subprocess.run([os.path.join(OUT, "bin/oracle_dump"), "--quiet", name + ".gpu.pbrt"],
                        cwd=SCENES, env=env, check=True, stdout=subprocess.DEVNULL)
         if not npix:
+            # full-size workloads: only the lowered scene is kept, where bench.py looks for it
             os.remove(prefix + ".golden")
+            os.makedirs(LOWERED, exist_ok=True)
+            shutil.move(prefix + ".spt", os.path.join(LOWERED, name + ".spt"))
         print("%-16s lowered + golden in %.1fs" % (name, time.time() - t0), flush=True)
         if args.images and img_spp:
             iname = "%s_%dspp" % (name, img_spp)

@@ -118,7 +118,11 @@ class Scene:
     def stats(self):
         st = D.SptStats()
         _check(lib().spt_get_stats(self.h, C.byref(st)))
-        return {k: getattr(st, k) for k, _ in D.SptStats._fields_}
+        out = {}
+        for k, _ in D.SptStats._fields_:
+            v = getattr(st, k)
+            out[k] = list(v) if hasattr(v, "__len__") else v
+        return out
 
     def trace_closest(self, rays):
         r = np.ascontiguousarray(rays, np.float32)

@@ -58,6 +58,16 @@ struct SptScene {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     SptStats stats{};
     uint64_t launches = 0;
+    // per-launch timing: an event after every launch of a render, attributed to the launch's class
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<int> ev_class;       // class of the launch that precedes event k (-1: start marker)
+    size_t ev_used = 0;
+    void mark(int cls) {
+        if (ev_used == ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); ev_pool.push_back(e); ev_class.push_back(0); }
+        ev_class[ev_used] = cls;
+        cudaEventRecord(ev_pool[ev_used++], stream);
+        if (cls >= 0) { ++launches; ++stats.class_launches[cls]; }
+    }
 };
 
 struct SptFilm {
@@ -140,8 +150,8 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
     UP(v.env_marg_func, d->env_marg_func, eh); UP(v.env_marg_cdf, d->env_marg_cdf, eh ? eh + 1 : 0);
     v.env_marg_int = d->env_marg_int;
 #undef UP
-    s->counters = m.alloc<unsigned long long>(2);
-    if (!ok || !s->counters || cudaMemset(s->counters, 0, 16) != cudaSuccess ||
+    s->counters = m.alloc<unsigned long long>(4);
+    if (!ok || !s->counters || cudaMemset(s->counters, 0, 32) != cudaSuccess ||
         cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess) {
         g_err = std::string("scene upload failed: ") + cudaGetErrorString(cudaGetLastError());
@@ -161,6 +171,7 @@ void spt_scene_destroy(SptScene *s) {
     if (s->stream) cudaStreamDestroy(s->stream);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
+    for (cudaEvent_t e : s->ev_pool) cudaEventDestroy(e);
     delete s;
 }
 
@@ -168,17 +179,19 @@ int spt_scene_enable_counters(SptScene *s, int on) {
     if (!s) return fail(SPT_ERR_ARG, "null scene");
     s->counters_on = on != 0;
     s->dev.counters = on ? s->counters : nullptr;
-    CU(cudaMemset(s->counters, 0, 16));
-    s->stats.node_visits = s->stats.prim_tests = 0;
+    CU(cudaMemset(s->counters, 0, 32));
+    s->stats.node_visits_closest = s->stats.prim_tests_closest = 0;
+    s->stats.node_visits_any = s->stats.prim_tests_any = 0;
     return SPT_OK;
 }
 
 int spt_get_stats(SptScene *s, SptStats *out) {
     if (!s || !out) return fail(SPT_ERR_ARG, "null argument");
     if (s->counters_on) {
-        unsigned long long c[2];
-        CU(cudaMemcpy(c, s->counters, 16, cudaMemcpyDeviceToHost));
-        s->stats.node_visits = c[0]; s->stats.prim_tests = c[1];
+        unsigned long long c[4];
+        CU(cudaMemcpy(c, s->counters, 32, cudaMemcpyDeviceToHost));
+        s->stats.node_visits_closest = c[0]; s->stats.prim_tests_closest = c[1];
+        s->stats.node_visits_any = c[2]; s->stats.prim_tests_any = c[3];
     }
     s->stats.kernel_launches = s->launches;
     *out = s->stats;
@@ -224,34 +237,48 @@ static void run_wave(SptScene *s, const RenderCfg &cfg, const SampleSource &src,
     const WaveBuffers &wb = s->wb;
     const DevScene &sc = s->dev;
     int sms = num_sms();
-    int gridLight = sms * 8;
     uint32_t n = cfg.n_samples;
     int gridN = (int)std::min<uint64_t>(((uint64_t)n + 255) / 256, (uint64_t)sms * 16);
     if (gridN < 1) gridN = 1;
+    s->mark(-1);
     k_gen_camera<<<gridN, 256, 0, st>>>(cfg, src, wb, counts + 0);
-    s->launches += 1;
+    s->mark(SPT_K_GEN);
     int gridT = (int)std::min<uint64_t>(((uint64_t)n + 127) / 128, (uint64_t)sms * 16);
     if (gridT < 1) gridT = 1;
-    (void)gridLight;
     for (int b = 0; b <= cfg.max_depth; ++b) {
         uint32_t *row = counts + 4 * b, *next = counts + 4 * (b + 1);
         uint32_t *q = wb.pathQ[b & 1], *qn = wb.pathQ[(b + 1) & 1];
         if (s->counters_on) k_trace<false, true><<<gridT, 128, 0, st>>>(sc, q, row + 0, wb.ray_o, wb.ray_d, wb.hit_slot, wb.hit_t);
         else k_trace<false, false><<<gridT, 128, 0, st>>>(sc, q, row + 0, wb.ray_o, wb.ray_d, wb.hit_slot, wb.hit_t);
+        s->mark(SPT_K_TRACE_PATH);
         k_shade<<<gridT, 128, 0, st>>>(sc, cfg, src, wb, b, q, row + 0, row + 1, row + 2);
+        s->mark(SPT_K_SHADE);
         if (sc.n_lights > 0) {
-            if (s->counters_on) {
-                k_trace<true, true><<<gridT, 128, 0, st>>>(sc, wb.shadowQ, row + 1, wb.g0, wb.g1, wb.sh_slot, nullptr);
-                k_trace<false, true><<<gridT, 128, 0, st>>>(sc, wb.misQ, row + 2, wb.g0, wb.g2, wb.mis_slot, wb.mis_t);
-            } else {
-                k_trace<true, false><<<gridT, 128, 0, st>>>(sc, wb.shadowQ, row + 1, wb.g0, wb.g1, wb.sh_slot, nullptr);
-                k_trace<false, false><<<gridT, 128, 0, st>>>(sc, wb.misQ, row + 2, wb.g0, wb.g2, wb.mis_slot, wb.mis_t);
-            }
-            s->launches += 2;
+            if (s->counters_on) k_trace<true, true><<<gridT, 128, 0, st>>>(sc, wb.shadowQ, row + 1, wb.g0, wb.g1, wb.sh_slot, nullptr);
+            else k_trace<true, false><<<gridT, 128, 0, st>>>(sc, wb.shadowQ, row + 1, wb.g0, wb.g1, wb.sh_slot, nullptr);
+            s->mark(SPT_K_TRACE_SHADOW);
+            if (s->counters_on) k_trace<false, true><<<gridT, 128, 0, st>>>(sc, wb.misQ, row + 2, wb.g0, wb.g2, wb.mis_slot, wb.mis_t);
+            else k_trace<false, false><<<gridT, 128, 0, st>>>(sc, wb.misQ, row + 2, wb.g0, wb.g2, wb.mis_slot, wb.mis_t);
+            s->mark(SPT_K_TRACE_MIS);
         }
         k_accumulate<<<gridT, 128, 0, st>>>(sc, cfg, wb, b, q, row + 0, qn, next + 0);
-        s->launches += 3;
+        s->mark(SPT_K_ACCUMULATE);
     }
+}
+
+// after the stream has drained: fold the per-launch event deltas into stats.class_ms
+static void collect_class_times(SptScene *s) {
+    for (size_t k = 1; k < s->ev_used; ++k) {
+        int cls = s->ev_class[k];
+        if (cls < 0) continue;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, s->ev_pool[k - 1], s->ev_pool[k]) == cudaSuccess) s->stats.class_ms[cls] += ms;
+    }
+    s->ev_used = 0;
+}
+static void reset_class_stats(SptScene *s) {
+    for (int k = 0; k < SPT_K_CLASSES; ++k) { s->stats.class_ms[k] = 0.; s->stats.class_launches[k] = 0; s->stats.class_rays[k] = 0; }
+    s->ev_used = 0;
 }
 
 static void add_ray_stats(SptScene *s, const std::vector<uint32_t> &counts, int max_depth, size_t n_waves) {
@@ -260,6 +287,11 @@ static void add_ray_stats(SptScene *s, const std::vector<uint32_t> &counts, int 
             const uint32_t *row = &counts[(w * (size_t)(max_depth + 2) + b) * 4];
             s->stats.closest_rays += row[0] + row[2];
             s->stats.any_rays += row[1];
+            s->stats.class_rays[SPT_K_TRACE_PATH] += row[0];
+            s->stats.class_rays[SPT_K_SHADE] += row[0];
+            s->stats.class_rays[SPT_K_ACCUMULATE] += row[0];
+            s->stats.class_rays[SPT_K_TRACE_SHADOW] += row[1];
+            s->stats.class_rays[SPT_K_TRACE_MIS] += row[2];
         }
 }
 
@@ -399,6 +431,7 @@ int spt_shade_samples(SptScene *s, const SptCameraDesc *cam, int32_t max_depth, 
     SampleSource src; src.smp = dsmp; src.rng = drng; src.n_rng = drng ? n_rng : 0; src.seed = 0; src.spp = 1;
     size_t nc = (size_t)(max_depth + 2) * 4;
     cudaMemsetAsync(s->counts, 0, nc * 4, s->stream);
+    reset_class_stats(s);
     run_wave(s, cfg, src, s->counts);
     k_gather_L<<<(unsigned)std::min<uint64_t>((n * NB + 255) / 256, 65535), 256, 0, s->stream>>>(s->wb.L, s->wb.cap, (uint32_t)n, dout);
     std::vector<uint32_t> hc(nc);
@@ -407,6 +440,7 @@ int spt_shade_samples(SptScene *s, const SptCameraDesc *cam, int32_t max_depth, 
     if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
     m.release();
     if (e != cudaSuccess) return fail(SPT_ERR_CUDA, cudaGetErrorString(e));
+    collect_class_times(s);
     s->stats.camera_samples += n;
     add_ray_stats(s, hc, max_depth, 1);
     return SPT_OK;
@@ -550,6 +584,7 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
     CU(cudaMemsetAsync(s->counts, 0, std::max<size_t>(n_waves, 1) * per_wave * 4, st));
     SampleSource src; src.smp = nullptr; src.rng = nullptr; src.n_rng = 0; src.seed = cfg.seed; src.spp = (uint32_t)rp->spp;
     FilmView fv; fv.d = film->desc; fv.pix = film->pix; fv.table = film->table;
+    reset_class_stats(s);
     CU(cudaEventRecord(s->ev0, st));
     uint64_t samples = 0;
     for (size_t w = 0; w < n_waves; ++w) {
@@ -559,7 +594,7 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
         run_wave(s, cfg, src, s->counts + w * per_wave);
         unsigned gw = (unsigned)std::min<uint64_t>((np * 32 + 255) / 256, (uint64_t)num_sms() * 16);
         k_film_add<<<gw, 256, 0, st>>>(fv, s->dev.tables, s->wb.img_xy, s->wb.L, s->wb.cap, cfg.n_samples, rp->spp);
-        s->launches += 1;
+        s->mark(SPT_K_FILM);
     }
     CU(cudaEventRecord(s->ev1, st));
     std::vector<uint32_t> hc(std::max<size_t>(n_waves, 1) * per_wave);
@@ -569,7 +604,9 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
     float ms = 0.f;
     cudaEventElapsedTime(&ms, s->ev0, s->ev1);
     s->stats.render_ms = ms;
+    collect_class_times(s);
     for (size_t w = 0; w < n_waves; ++w) samples += hc[w * per_wave];
+    s->stats.class_rays[SPT_K_GEN] = samples; s->stats.class_rays[SPT_K_FILM] = samples;
     s->stats.camera_samples += samples;
     add_ray_stats(s, hc, rp->max_depth, n_waves);
     return SPT_OK;

@@ -105,5 +105,5 @@ struct DevScene {
     int env_w, env_h;
     const float *env_rgb, *env_func, *env_cdf, *env_func_int, *env_marg_func, *env_marg_cdf;
     float env_marg_int;
-    unsigned long long *counters;    // [0] node visits, [1] primitive tests (NULL when disabled)
+    unsigned long long *counters;    // closest: [0] nodes, [1] prim tests; any-hit: [2], [3] (NULL when disabled)
 };

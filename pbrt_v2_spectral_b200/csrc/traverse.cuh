@@ -239,7 +239,7 @@ __device__ __forceinline__ uint32_t bvh_traverse(const DevScene &sc, Ray &ray) {
                     }
                     if (h) {
                         if (ANY) {
-                            if (COUNT && sc.counters) { atomicAdd(&sc.counters[0], cn); atomicAdd(&sc.counters[1], cp); }
+                            if (COUNT && sc.counters) { atomicAdd(&sc.counters[2], cn); atomicAdd(&sc.counters[3], cp); }
                             return s;
                         }
                         ray.maxt = t;
@@ -259,6 +259,6 @@ __device__ __forceinline__ uint32_t bvh_traverse(const DevScene &sc, Ray &ray) {
             nodeNum = todo[--todoOffset];
         }
     }
-    if (COUNT && sc.counters) { atomicAdd(&sc.counters[0], cn); atomicAdd(&sc.counters[1], cp); }
+    if (COUNT && sc.counters) { atomicAdd(&sc.counters[ANY ? 2 : 0], cn); atomicAdd(&sc.counters[ANY ? 3 : 1], cp); }
     return best;
 }

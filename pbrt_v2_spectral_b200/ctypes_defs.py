@@ -54,10 +54,18 @@ class SptRenderParams(C.Structure):
                 ("wave_pixels", C.c_int32), ("skip_border", C.c_int32)]
 
 
+K_GEN, K_TRACE_PATH, K_SHADE, K_TRACE_SHADOW, K_TRACE_MIS, K_ACCUMULATE, K_FILM, K_CLASSES = 0, 1, 2, 3, 4, 5, 6, 8
+K_NAMES = ["gen_camera", "trace_closest_path", "shade", "trace_any_shadow", "trace_closest_mis", "accumulate", "film_add", "-"]
+
+
 class SptStats(C.Structure):
     _fields_ = [("camera_samples", C.c_uint64), ("closest_rays", C.c_uint64), ("any_rays", C.c_uint64),
-                ("node_visits", C.c_uint64), ("prim_tests", C.c_uint64), ("kernel_launches", C.c_uint64),
-                ("render_ms", C.c_double), ("trace_ms", C.c_double)]
+                ("node_visits_closest", C.c_uint64), ("prim_tests_closest", C.c_uint64),
+                ("node_visits_any", C.c_uint64), ("prim_tests_any", C.c_uint64),
+                ("kernel_launches", C.c_uint64),
+                ("render_ms", C.c_double), ("trace_ms", C.c_double),
+                ("class_ms", C.c_double * K_CLASSES), ("class_launches", C.c_uint64 * K_CLASSES),
+                ("class_rays", C.c_uint64 * K_CLASSES)]
 
 
 # row sizes of the table structs (bytes), for sanity checks against the container file
