@@ -1,0 +1,45 @@
+"""-m gpu: converged-image parity against .dat files rendered by the unmodified reference binary
+(oracle/make_golden.py --images). north_star: "within 1 % mean relative error per spectral band";
+as SURVEY.md 8c measured, the per-pixel-averaged form cannot pass even reference-vs-reference
+(3 % Monte-Carlo noise at 1024 spp), so the aggregate form is used: per band
+    sum_pixels |gpu - ref| / sum_pixels ref  <= 1 %      (reference-vs-reference floor: 0.15 %)
+plus the band-mean bias |mean(gpu) - mean(ref)| / mean(ref) <= 0.3 %, the sensitive detector of
+systematic shading errors. Both films hold un-normalised sums: divided by spp here."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from pbrt_v2_spectral_b200 import capi, ctypes_defs as D
+from pbrt_v2_spectral_b200.scene_io import LoweredScene
+
+pytestmark = pytest.mark.gpu
+
+IMAGES = [("killeroo_small", 1024), ("bunny_small", 256), ("metal_small", 512)]
+
+
+@pytest.mark.parametrize("name,spp", IMAGES, ids=[n for n, _ in IMAGES])
+def test_converged_image_within_1_percent_per_band(name, spp):
+    dat = os.path.join(O.GOLDEN_BIG, "%s_%dspp.dat" % (name, spp))
+    spt = os.path.join(O.GOLDEN_BIG, name + ".spt")
+    if not (os.path.exists(dat) and os.path.exists(spt)):
+        pytest.skip("reference image %s not generated (oracle/make_golden.py --images)" % dat)
+    ref = capi.read_dat(dat) / spp
+    lowered = LoweredScene.load(spt)
+    scene = capi.Scene(lowered)
+    rp = D.SptRenderParams.from_buffer_copy(bytes(lowered.params))
+    gpu_spp = 4 * spp                       # the GPU side's own noise is pushed below the reference's
+    rp.spp = gpu_spp
+    rp.seed = 2024
+    film = capi.Film(lowered.film)
+    scene.render(film, rp)
+    c, w = film.download()
+    film.close(); scene.close()
+    img = c.astype(np.float64) / gpu_spp
+    assert img.shape == ref.shape
+    l1 = np.abs(img - ref).sum((0, 1)) / ref.sum((0, 1))
+    bias = np.abs(img.mean((0, 1)) - ref.mean((0, 1))) / ref.mean((0, 1))
+    print("%s: per-band aggregate L1 error max %.3f%%, band-mean bias max %.3f%%" % (name, 100 * l1.max(), 100 * bias.max()))
+    assert l1.max() <= 0.01, l1
+    assert bias.max() <= 0.003, bias
