@@ -105,7 +105,7 @@ CONFIGS = {
     "killeroo_small":  (killeroo, 176, 176, 4, 6000, 40, 1024),
     # config 2: first-hit parity on bunny (all camera rays of a 4-spp 320x240 frame)
     "bunny_path":      (bunny, 640, 480, 256, 0, 0, 0),
-    "bunny_small":     (bunny, 320, 240, 4, 20000, 40, 256),
+    "bunny_small":     (bunny, 320, 240, 4, 8000, 40, 4096),
     # config 3 (metal teapot, Au SPDs) with the substitutions noted above
     "metal_small":     (metal, 200, 200, 4, 6000, 40, 512),
     # small committed fixture

@@ -1129,13 +1129,8 @@ static uint32_t mix32(uint32_t x) {
     x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
     return x;
 }
-static uint32_t hash4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    uint32_t h = mix32(a + 0x9e3779b9U);
-    h = mix32(h ^ (b + 0x85ebca6bU));
-    h = mix32(h ^ (c + 0xc2b2ae35U));
-    h = mix32(h ^ (d + 0x27d4eb2fU));
-    return h;
-}
+static uint32_t pixel_key(uint32_t seed, uint32_t pix) { return mix32(mix32(seed + 0x9e3779b9U) ^ (pix + 0x85ebca6bU)); }
+static uint32_t dim_key(uint32_t pkey, uint32_t dim) { return mix32(pkey + dim * 0x9e3779b9U); }
 /* random permutation of [0,n), n a power of two: invertible mixing on log2(n) bits */
 static uint32_t permute_pow2(uint32_t i, uint32_t n, uint32_t key) {
     uint32_t mask = n - 1;
@@ -1161,29 +1156,32 @@ static float sobol2(uint32_t n, uint32_t scramble) {                  /* core/mo
         if (n & 0x1) scramble ^= v;
     return stdminf(((scramble >> 8) & 0xffffff) / (float)(1 << 24), ONE_MINUS_EPS);
 }
-static float ld1(uint32_t seed, uint32_t pix, uint32_t dim, uint32_t s, uint32_t spp) {
-    uint32_t idx = permute_pow2(s, spp, hash4(seed, pix, dim, 0u));
-    return van_der_corput(idx, hash4(seed, pix, dim, 1u));
+static float ld1(uint32_t pkey, uint32_t dim, uint32_t s, uint32_t spp) {
+    uint32_t h = dim_key(pkey, dim);
+    uint32_t idx = permute_pow2(s, spp, h);
+    return van_der_corput(idx, mix32(h ^ 0x68bc21ebU));
 }
-static void ld2(uint32_t seed, uint32_t pix, uint32_t dim, uint32_t s, uint32_t spp, float *out) {
-    uint32_t idx = permute_pow2(s, spp, hash4(seed, pix, dim, 0u));
-    out[0] = van_der_corput(idx, hash4(seed, pix, dim, 1u));
-    out[1] = sobol2(idx, hash4(seed, pix, dim, 2u));
+static void ld2(uint32_t pkey, uint32_t dim, uint32_t s, uint32_t spp, float *out) {
+    uint32_t h = dim_key(pkey, dim);
+    uint32_t idx = permute_pow2(s, spp, h);
+    out[0] = van_der_corput(idx, mix32(h ^ 0x68bc21ebU));
+    out[1] = sobol2(idx, mix32(h ^ 0x02e5be93U));
 }
 void orc_gen_sample(uint64_t seed64, int32_t px, int32_t py, int32_t s, int32_t spp, float so, float sc_,
                     int32_t n_rng, float *o, float *rng) {
     uint32_t seed = (uint32_t)(seed64 ^ (seed64 >> 32));
-    uint32_t pix = ((uint32_t)py << 16) ^ (uint32_t)px;
+    uint32_t pkey = pixel_key(seed, ((uint32_t)py << 16) ^ (uint32_t)px);
     float t2[2];
-    ld2(seed, pix, 0, s, spp, t2);
+    ld2(pkey, 0, s, spp, t2);
     o[0] = px + t2[0]; o[1] = py + t2[1];
-    ld2(seed, pix, 1, s, spp, t2);
+    ld2(pkey, 1, s, spp, t2);
     o[2] = t2[0]; o[3] = t2[1];
-    o[4] = lerpf(ld1(seed, pix, 2, s, spp), so, sc_);
-    for (int k = 0; k < 14; ++k) o[5 + k] = (k < 12) ? ld1(seed, pix, 3 + k, s, spp) : 0.f;
-    for (int k = 0; k < 9; ++k) ld2(seed, pix, 17 + k, s, spp, o + 19 + 2 * k);
+    o[4] = lerpf(ld1(pkey, 2, s, spp), so, sc_);
+    for (int k = 0; k < 14; ++k) o[5 + k] = (k < 12) ? ld1(pkey, 3 + k, s, spp) : 0.f;
+    for (int k = 0; k < 9; ++k) ld2(pkey, 17 + k, s, spp, o + 19 + 2 * k);
+    uint32_t rkey = mix32(pkey ^ (0x10000u + (uint32_t)s) * 0xc2b2ae35U);
     for (int k = 0; k < n_rng; ++k)
-        rng[k] = (hash4(seed, pix, 0x10000u + (uint32_t)s, (uint32_t)k) & 0xffffff) / (float)(1 << 24);
+        rng[k] = (mix32(rkey + (uint32_t)k * 0x27d4eb2fU) & 0xffffff) / (float)(1 << 24);
 }
 
 void orc_render(const SptSceneDesc *sc, const SptCameraDesc *cam, const SptFilmDesc *fd, const SptRenderParams *rp,

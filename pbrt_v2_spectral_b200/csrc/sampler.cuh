@@ -16,13 +16,11 @@ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
     x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
     return x;
 }
-__device__ __forceinline__ uint32_t hash4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    uint32_t h = mix32(a + 0x9e3779b9U);
-    h = mix32(h ^ (b + 0x85ebca6bU));
-    h = mix32(h ^ (c + 0xc2b2ae35U));
-    h = mix32(h ^ (d + 0x27d4eb2fU));
-    return h;
+// per-(seed, pixel) key, computed once per path vertex; every dimension derives from it with one mix
+__device__ __forceinline__ uint32_t pixel_key(uint32_t seed, uint32_t pix) {
+    return mix32(mix32(seed + 0x9e3779b9U) ^ (pix + 0x85ebca6bU));
 }
+__device__ __forceinline__ uint32_t dim_key(uint32_t pkey, uint32_t dim) { return mix32(pkey + dim * 0x9e3779b9U); }
 // random permutation of [0,n), n a power of two (invertible mixing restricted to log2 n bits)
 __device__ __forceinline__ uint32_t permute_pow2(uint32_t i, uint32_t n, uint32_t key) {
     uint32_t mask = n - 1;
@@ -44,17 +42,20 @@ __device__ __forceinline__ float sobol2(uint32_t n, uint32_t scramble) {        
         if (n & 0x1) scramble ^= v;
     return stdminf(((scramble >> 8) & 0xffffff) / (float)(1 << 24), ONE_MINUS_EPS);
 }
-__device__ __forceinline__ float ld1(uint32_t seed, uint32_t pix, uint32_t dim, uint32_t s, uint32_t spp) {
-    uint32_t idx = permute_pow2(s, spp, hash4(seed, pix, dim, 0u));
-    return van_der_corput(idx, hash4(seed, pix, dim, 1u));
+__device__ __forceinline__ float ld1(uint32_t pkey, uint32_t dim, uint32_t s, uint32_t spp) {
+    uint32_t h = dim_key(pkey, dim);
+    uint32_t idx = permute_pow2(s, spp, h);
+    return van_der_corput(idx, mix32(h ^ 0x68bc21ebU));
 }
-__device__ __forceinline__ void ld2(uint32_t seed, uint32_t pix, uint32_t dim, uint32_t s, uint32_t spp, float *out) {
-    uint32_t idx = permute_pow2(s, spp, hash4(seed, pix, dim, 0u));
-    out[0] = van_der_corput(idx, hash4(seed, pix, dim, 1u));
-    out[1] = sobol2(idx, hash4(seed, pix, dim, 2u));
+__device__ __forceinline__ void ld2(uint32_t pkey, uint32_t dim, uint32_t s, uint32_t spp, float *out) {
+    uint32_t h = dim_key(pkey, dim);
+    uint32_t idx = permute_pow2(s, spp, h);
+    out[0] = van_der_corput(idx, mix32(h ^ 0x68bc21ebU));
+    out[1] = sobol2(idx, mix32(h ^ 0x02e5be93U));
 }
-__device__ __forceinline__ float rng_float(uint32_t seed, uint32_t pix, uint32_t s, uint32_t k) {
-    return (hash4(seed, pix, 0x10000u + s, k) & 0xffffff) / (float)(1 << 24);   // RNG::RandomFloat, rng.cpp:51-57
+__device__ __forceinline__ uint32_t rng_key(uint32_t pkey, uint32_t s) { return mix32(pkey ^ (0x10000u + s) * 0xc2b2ae35U); }
+__device__ __forceinline__ float rng_float(uint32_t rkey, uint32_t k) {
+    return (mix32(rkey + k * 0x27d4eb2fU) & 0xffffff) / (float)(1 << 24);          // RNG::RandomFloat, rng.cpp:51-57
 }
 
 // Where a path's sample values come from: generated (production) or caller-supplied arrays in the
@@ -65,11 +66,12 @@ struct SampleSource {
     int n_rng;
     uint32_t seed, spp;
 };
+// `pkey` below is pixel_key(seed, pix) of the path's sampler pixel
 
 // The ten values bounce `b` consumes: {lightNum, lightPos0, lightPos1, lightComp, bsdfDir0,
 // bsdfDir1, bsdfComp, pathDir0, pathDir1, pathComp} (src/integrators/path.cpp:33-41,63-83;
 // src/core/integrator.cpp:84-99), and the Russian-roulette draw (path.cpp:97).
-__device__ inline void bounce_dims(const SampleSource &src, uint64_t idx, uint32_t pix, uint32_t s, int b,
+__device__ inline void bounce_dims(const SampleSource &src, uint64_t idx, uint32_t pkey, uint32_t s, int b,
                                    bool haveLights, float u[10], float *rr) {
     if (b < 3) {
         if (src.smp) {
@@ -80,13 +82,13 @@ __device__ inline void bounce_dims(const SampleSource &src, uint64_t idx, uint32
             u[7] = twoD[4]; u[8] = twoD[5]; u[9] = oneD[3];
         } else {
             float t[2];
-            u[3] = ld1(src.seed, pix, 3 + 4 * b + 0, s, src.spp);
-            u[0] = ld1(src.seed, pix, 3 + 4 * b + 1, s, src.spp);
-            u[6] = ld1(src.seed, pix, 3 + 4 * b + 2, s, src.spp);
-            u[9] = ld1(src.seed, pix, 3 + 4 * b + 3, s, src.spp);
-            ld2(src.seed, pix, 17 + 3 * b + 0, s, src.spp, t); u[1] = t[0]; u[2] = t[1];
-            ld2(src.seed, pix, 17 + 3 * b + 1, s, src.spp, t); u[4] = t[0]; u[5] = t[1];
-            ld2(src.seed, pix, 17 + 3 * b + 2, s, src.spp, t); u[7] = t[0]; u[8] = t[1];
+            u[3] = ld1(pkey, 3 + 4 * b + 0, s, src.spp);
+            u[0] = ld1(pkey, 3 + 4 * b + 1, s, src.spp);
+            u[6] = ld1(pkey, 3 + 4 * b + 2, s, src.spp);
+            u[9] = ld1(pkey, 3 + 4 * b + 3, s, src.spp);
+            ld2(pkey, 17 + 3 * b + 0, s, src.spp, t); u[1] = t[0]; u[2] = t[1];
+            ld2(pkey, 17 + 3 * b + 1, s, src.spp, t); u[4] = t[0]; u[5] = t[1];
+            ld2(pkey, 17 + 3 * b + 2, s, src.spp, t); u[7] = t[0]; u[8] = t[1];
         }
         *rr = 0.f;
         return;
@@ -95,10 +97,11 @@ __device__ inline void bounce_dims(const SampleSource &src, uint64_t idx, uint32
     int perBounce = (haveLights ? 7 : 0) + 3;
     int k = (b - 3) * perBounce + (b > 4 ? b - 4 : 0);
     float v[11];
+    uint32_t rkey = rng_key(pkey, s);
     for (int j = 0; j < perBounce + 1; ++j) {
         int kk = k + j;
         if (src.rng) v[j] = kk < src.n_rng ? src.rng[(size_t)src.n_rng * idx + kk] : 0.5f;
-        else v[j] = rng_float(src.seed, pix, s, (uint32_t)kk);
+        else v[j] = rng_float(rkey, (uint32_t)kk);
     }
     int j = 0;
     if (haveLights) { for (; j < 7; ++j) u[j] = v[j]; }

@@ -179,15 +179,24 @@ __device__ __forceinline__ float fr_cond(float cosi, float eta, float k) {      
     return (Rparl2 + Rperp2) / 2.f;
 }
 
+// x^e for x in [0,1], e >= 0 as exp2(e*log2(x)): ~35 instructions instead of powf's ~100. log2f is
+// accurate to 1 ulp, so the error of the exponent argument is e*|log2 x|*6e-8: negligible wherever the
+// result is not vanishing (radiance tests compare at 2e-4 relative).
+__device__ __forceinline__ float pow01(float x, float e) { return exp2f(e * log2f(x)); }
+
 // scalar part of BSDF::f (reflection.cpp:604-618, with Lambertian :165-167, OrenNayar :170-193,
-// Microfacet :203-214, G reflection.h:395-402, Blinn::D reflection.h:419-422)
-__device__ inline void bsdf_terms(const Bsdf &b, v3 woW, v3 wiW, v3 wo, v3 wi, DirTerms *t) {
+// Microfacet :203-214, G reflection.h:395-402, Blinn::D reflection.h:419-422) and, from the same
+// half-vector and the same cos^e, BSDF::Pdf (reflection.cpp:575-590: BxDF::Pdf :312-315,
+// Microfacet::Pdf :331-335, Blinn::Pdf :356-366) averaged over the components.
+__device__ inline void bsdf_terms(const Bsdf &b, v3 woW, v3 wiW, v3 wo, v3 wi, DirTerms *t, float *pdfAll) {
     t->a0 = t->a1 = t->a2 = t->a3 = 0.f;
     t->mf = false;
     t->reflect = dot(wiW, b.ng) * dot(woW, b.ng) > 0;
-    if (!t->reflect) return;
+    bool same = same_hemisphere(wo, wi);
+    float cosPdf = same ? abs_cos_theta(wi) * INV_PI_F : 0.f;
     if (b.mtype == SPT_MAT_MATTE) {
-        if (b.orenNayar) {
+        *pdfAll = cosPdf / 1;
+        if (t->reflect && b.orenNayar) {
             float sinthetai = sin_theta(wi), sinthetao = sin_theta(wo);
             float maxcos = 0.f;
             if ((double)sinthetai > 1e-4 && (double)sinthetao > 1e-4) {
@@ -203,21 +212,32 @@ __device__ inline void bsdf_terms(const Bsdf &b, v3 woW, v3 wiW, v3 wo, v3 wi, D
         }
         return;
     }
-    float cosThetaO = abs_cos_theta(wo), cosThetaI = abs_cos_theta(wi);
-    if (cosThetaI == 0.f || cosThetaO == 0.f) return;
+    // microfacet component: one half-vector, one cos^e shared by D and the Blinn pdf
     v3 wh = vadd(wi, wo);
-    if (wh.x == 0.f && wh.y == 0.f && wh.z == 0.f) return;
+    bool whZero = (wh.x == 0.f && wh.y == 0.f && wh.z == 0.f);
     wh = normalize(wh);
+    float cosH = abs_cos_theta(wh);
+    float pw = pow01(cosH, b.exponent);
+    float woh = dot(wo, wh);
+    float blinnPdf = 0.f;
+    if (same) {
+        blinnPdf = ((b.exponent + 1.f) * pw) / (2.f * PI_F * 4.f * woh);
+        if (woh <= 0.f) blinnPdf = 0.f;
+    }
+    *pdfAll = (b.mtype == SPT_MAT_PLASTIC) ? (cosPdf + blinnPdf) / 2 : blinnPdf / 1;
+    if (!t->reflect) return;
+    float cosThetaO = abs_cos_theta(wo), cosThetaI = abs_cos_theta(wi);
+    if (cosThetaI == 0.f || cosThetaO == 0.f || whZero) return;
     float cosThetaH = dot(wi, wh);
-    t->a0 = (b.exponent + 2) * INV_TWOPI_F * powf(abs_cos_theta(wh), b.exponent);
-    float NdotWh = abs_cos_theta(wh), NdotWo = abs_cos_theta(wo), NdotWi = abs_cos_theta(wi);
-    float WOdotWh = absdot(wo, wh);
-    t->a1 = stdminf(1.f, stdminf((2.f * NdotWh * NdotWo / WOdotWh), (2.f * NdotWh * NdotWi / WOdotWh)));
+    t->a0 = (b.exponent + 2) * INV_TWOPI_F * pw;
+    float WOdotWh = fabsf(woh);
+    t->a1 = stdminf(1.f, stdminf((2.f * cosH * cosThetaO / WOdotWh), (2.f * cosH * cosThetaI / WOdotWh)));
     t->a2 = (b.mtype == SPT_MAT_PLASTIC) ? fresnel_dielectric(cosThetaH, 1.5f, 1.f) : fabsf(cosThetaH);
     t->a3 = (4.f * cosThetaI * cosThetaO);
     t->mf = true;
 }
-// f for band c from the staged terms, in the reference's operation order
+// f for band c from the staged terms, in the reference's operation order (used by the parity
+// helpers; the accumulate kernel folds the scalar factors once per vertex instead)
 __device__ __forceinline__ float f_band(const SptMaterial &m, bool orenNayar, const DirTerms &t, int c) {
     if (!t.reflect) return 0.f;
     float f = 0.f;
@@ -232,23 +252,6 @@ __device__ __forceinline__ float f_band(const SptMaterial &m, bool orenNayar, co
     }
     return f;
 }
-// Pdf of component i (BxDF::Pdf reflection.cpp:312-315, Microfacet::Pdf :331-335, Blinn::Pdf :356-366)
-__device__ inline float bxdf_pdf(const Bsdf &b, int i, v3 wo, v3 wi) {
-    bool mf = (b.mtype == SPT_MAT_METAL) || (b.mtype == SPT_MAT_PLASTIC && i == 1);
-    if (!mf) return same_hemisphere(wo, wi) ? abs_cos_theta(wi) * INV_PI_F : 0.f;
-    if (!same_hemisphere(wo, wi)) return 0.f;
-    v3 wh = normalize(vadd(wo, wi));
-    float costheta = abs_cos_theta(wh);
-    float blinn_pdf = ((b.exponent + 1.f) * powf(costheta, b.exponent)) / (2.f * PI_F * 4.f * dot(wo, wh));
-    if (dot(wo, wh) <= 0.f) blinn_pdf = 0.f;
-    return blinn_pdf;
-}
-__device__ inline float bsdf_pdf(const Bsdf &b, v3 wo, v3 wi) {                              // reflection.cpp:575-590
-    int n = bsdf_ncomp(b);
-    float pdf = 0.f;
-    for (int i = 0; i < n; ++i) pdf += bxdf_pdf(b, i, wo, wi);
-    return pdf / n;
-}
 // BSDF::Sample_f (reflection.cpp:514-572): direction + pdf + scalar terms. pdf == 0: no sample.
 __device__ inline void bsdf_sample(const Bsdf &b, v3 woW, v3 wo, float uComp, float u1, float u2,
                                    v3 *wiW, float *pdf, DirTerms *t) {
@@ -259,29 +262,26 @@ __device__ inline void bsdf_sample(const Bsdf &b, v3 woW, v3 wo, float uComp, fl
     v3 wi;
     *pdf = 0.f;
     t->a0 = t->a1 = t->a2 = t->a3 = 0.f; t->mf = false; t->reflect = false;
+    bool chosenZero;
     if (!mf) {                                                       // BxDF::Sample_f, reflection.cpp:303-310
         wi = cosine_sample_hemisphere(u1, u2);
         if (wo.z < 0.f) wi.z *= -1.f;
-        *pdf = bxdf_pdf(b, which, wo, wi);
+        chosenZero = !(same_hemisphere(wo, wi) && abs_cos_theta(wi) * INV_PI_F != 0.f);
     } else {                                                         // Blinn::Sample_f, reflection.cpp:338-354
-        float costheta = powf(u1, 1.f / (b.exponent + 1));
+        float costheta = pow01(u1, 1.f / (b.exponent + 1));
         float sintheta = sqrtf(stdmaxf(0.f, 1.f - costheta * costheta));
         float phi = u2 * 2.f * PI_F;
-        v3 wh = V(sintheta * cosf(phi), sintheta * sinf(phi), costheta);
+        float sp, cp;
+        sincosf(phi, &sp, &cp);
+        v3 wh = V(sintheta * cp, sintheta * sp, costheta);
         if (!same_hemisphere(wo, wh)) wh = vneg(wh);
-        wi = vadd(vneg(wo), vmul(wh, 2.f * dot(wo, wh)));
-        float blinn_pdf = ((b.exponent + 1.f) * powf(costheta, b.exponent)) / (2.f * PI_F * 4.f * dot(wo, wh));
-        if (dot(wo, wh) <= 0.f) blinn_pdf = 0.f;
-        *pdf = blinn_pdf;
+        float woh = dot(wo, wh);
+        wi = vadd(vneg(wo), vmul(wh, 2.f * woh));
+        chosenZero = woh <= 0.f || costheta == 0.f;
     }
-    if (*pdf == 0.f) return;
+    if (chosenZero) return;
     *wiW = l2w(b, wi);
-    if (matching > 1) {
-        for (int i = 0; i < matching; ++i)
-            if (i != which) *pdf += bxdf_pdf(b, i, wo, wi);
-        *pdf /= matching;
-    }
-    bsdf_terms(b, woW, *wiW, wo, wi, t);
+    bsdf_terms(b, woW, *wiW, wo, wi, t, pdf);
 }
 
 // ---- spectral tables ----------------------------------------------------------------------------

@@ -202,7 +202,7 @@ int spt_get_stats(SptScene *s, SptStats *out) {
 
 // ---------------------------------------------------------------------------------------------
 static int ensure_wave(SptScene *s, uint32_t cap, int max_depth, size_t n_waves) {
-    size_t need_counts = n_waves * (size_t)(max_depth + 2) * 4;
+    size_t need_counts = n_waves * (size_t)(max_depth + 2) * 8;
     if (s->wb.cap < cap) {
         s->wave_mem.release();
         s->counts = nullptr; s->counts_len = 0;
@@ -245,20 +245,21 @@ static void run_wave(SptScene *s, const RenderCfg &cfg, const SampleSource &src,
     s->mark(SPT_K_GEN);
     int gridT = (int)std::min<uint64_t>(((uint64_t)n + 127) / 128, (uint64_t)sms * 16);
     if (gridT < 1) gridT = 1;
+    int gridP = std::min(gridT, sms * 8);      // persistent trace kernels: resident blocks only
     for (int b = 0; b <= cfg.max_depth; ++b) {
-        uint32_t *row = counts + 4 * b, *next = counts + 4 * (b + 1);
+        uint32_t *row = counts + 8 * b, *next = counts + 8 * (b + 1);
         uint32_t *q = wb.pathQ[b & 1], *qn = wb.pathQ[(b + 1) & 1];
-        if (s->counters_on) k_trace<false, true><<<gridT, 128, 0, st>>>(sc, q, row + 0, wb.ray_o, wb.ray_d, wb.hit_slot, wb.hit_t);
-        else k_trace<false, false><<<gridT, 128, 0, st>>>(sc, q, row + 0, wb.ray_o, wb.ray_d, wb.hit_slot, wb.hit_t);
+        if (s->counters_on) k_trace<false, true><<<gridP, 128, 0, st>>>(sc, q, row + 0, row + 4, wb.ray_o, wb.ray_d, wb.hit_slot, wb.hit_t);
+        else k_trace<false, false><<<gridP, 128, 0, st>>>(sc, q, row + 0, row + 4, wb.ray_o, wb.ray_d, wb.hit_slot, wb.hit_t);
         s->mark(SPT_K_TRACE_PATH);
         k_shade<<<gridT, 128, 0, st>>>(sc, cfg, src, wb, b, q, row + 0, row + 1, row + 2);
         s->mark(SPT_K_SHADE);
         if (sc.n_lights > 0) {
-            if (s->counters_on) k_trace<true, true><<<gridT, 128, 0, st>>>(sc, wb.shadowQ, row + 1, wb.g0, wb.g1, wb.sh_slot, nullptr);
-            else k_trace<true, false><<<gridT, 128, 0, st>>>(sc, wb.shadowQ, row + 1, wb.g0, wb.g1, wb.sh_slot, nullptr);
+            if (s->counters_on) k_trace<true, true><<<gridP, 128, 0, st>>>(sc, wb.shadowQ, row + 1, row + 5, wb.g0, wb.g1, wb.sh_slot, nullptr);
+            else k_trace<true, false><<<gridP, 128, 0, st>>>(sc, wb.shadowQ, row + 1, row + 5, wb.g0, wb.g1, wb.sh_slot, nullptr);
             s->mark(SPT_K_TRACE_SHADOW);
-            if (s->counters_on) k_trace<false, true><<<gridT, 128, 0, st>>>(sc, wb.misQ, row + 2, wb.g0, wb.g2, wb.mis_slot, wb.mis_t);
-            else k_trace<false, false><<<gridT, 128, 0, st>>>(sc, wb.misQ, row + 2, wb.g0, wb.g2, wb.mis_slot, wb.mis_t);
+            if (s->counters_on) k_trace<false, true><<<gridP, 128, 0, st>>>(sc, wb.misQ, row + 2, row + 6, wb.g0, wb.g2, wb.mis_slot, wb.mis_t);
+            else k_trace<false, false><<<gridP, 128, 0, st>>>(sc, wb.misQ, row + 2, row + 6, wb.g0, wb.g2, wb.mis_slot, wb.mis_t);
             s->mark(SPT_K_TRACE_MIS);
         }
         k_accumulate<<<gridT, 128, 0, st>>>(sc, cfg, wb, b, q, row + 0, qn, next + 0);
@@ -284,7 +285,7 @@ static void reset_class_stats(SptScene *s) {
 static void add_ray_stats(SptScene *s, const std::vector<uint32_t> &counts, int max_depth, size_t n_waves) {
     for (size_t w = 0; w < n_waves; ++w)
         for (int b = 0; b <= max_depth; ++b) {
-            const uint32_t *row = &counts[(w * (size_t)(max_depth + 2) + b) * 4];
+            const uint32_t *row = &counts[(w * (size_t)(max_depth + 2) + b) * 8];
             s->stats.closest_rays += row[0] + row[2];
             s->stats.any_rays += row[1];
             s->stats.class_rays[SPT_K_TRACE_PATH] += row[0];
@@ -314,16 +315,16 @@ int spt_camera_rays(const SptCameraDesc *cam, const float *samples, uint64_t n, 
 static int trace_dev(SptScene *s, bool any, const float4 *ro, const float4 *rd, uint64_t n, uint32_t *slot, float *t,
                      uint32_t *count_dev) {
     int sms = num_sms();
-    int grid = (int)std::min<uint64_t>((n + 127) / 128, (uint64_t)sms * 16);
+    int grid = (int)std::min<uint64_t>((n + 127) / 128, (uint64_t)sms * 8);
     if (grid < 1) grid = 1;
     cudaStream_t st = s->stream;
     cudaEventRecord(s->ev0, st);
     if (any) {
-        if (s->counters_on) k_trace<true, true><<<grid, 128, 0, st>>>(s->dev, nullptr, count_dev, ro, rd, slot, t);
-        else k_trace<true, false><<<grid, 128, 0, st>>>(s->dev, nullptr, count_dev, ro, rd, slot, t);
+        if (s->counters_on) k_trace<true, true><<<grid, 128, 0, st>>>(s->dev, nullptr, count_dev, count_dev + 1, ro, rd, slot, t);
+        else k_trace<true, false><<<grid, 128, 0, st>>>(s->dev, nullptr, count_dev, count_dev + 1, ro, rd, slot, t);
     } else {
-        if (s->counters_on) k_trace<false, true><<<grid, 128, 0, st>>>(s->dev, nullptr, count_dev, ro, rd, slot, t);
-        else k_trace<false, false><<<grid, 128, 0, st>>>(s->dev, nullptr, count_dev, ro, rd, slot, t);
+        if (s->counters_on) k_trace<false, true><<<grid, 128, 0, st>>>(s->dev, nullptr, count_dev, count_dev + 1, ro, rd, slot, t);
+        else k_trace<false, false><<<grid, 128, 0, st>>>(s->dev, nullptr, count_dev, count_dev + 1, ro, rd, slot, t);
     }
     cudaEventRecord(s->ev1, st);
     s->launches += 1;
@@ -343,12 +344,13 @@ static int trace_host(SptScene *s, bool any, const float *rays, uint64_t n, uint
     DevMem m;
     float *dr = m.upload(rays, n * 8);
     float4 *ro = m.alloc<float4>(n), *rd = m.alloc<float4>(n);
-    uint32_t *slot = m.alloc<uint32_t>(n), *ids = m.alloc<uint32_t>(n), *cnt = m.alloc<uint32_t>(1);
+    uint32_t *slot = m.alloc<uint32_t>(n), *ids = m.alloc<uint32_t>(n), *cnt = m.alloc<uint32_t>(2);
     float *t = m.alloc<float>(n);
     uint8_t *flag = m.alloc<uint8_t>(n);
     if (!dr || !ro || !rd || !slot || !ids || !cnt || !t || !flag) { m.release(); return fail(SPT_ERR_CUDA, "device allocation failed"); }
     uint32_t n32 = (uint32_t)n;
-    cudaMemcpyAsync(cnt, &n32, 4, cudaMemcpyHostToDevice, s->stream);
+    uint32_t cw[2] = { n32, 0 };
+    cudaMemcpyAsync(cnt, cw, 8, cudaMemcpyHostToDevice, s->stream);
     unsigned g = (unsigned)std::min<uint64_t>((n + 255) / 256, 65535);
     k_split_rays<<<g, 256, 0, s->stream>>>(dr, n32, ro, rd);
     int rc = trace_dev(s, any, ro, rd, n, slot, t, cnt);
@@ -389,13 +391,15 @@ static int trace_resident(SptScene *s, bool any, const float *rays_dev, uint64_t
     static thread_local uint32_t *cnt = nullptr, *slot_tmp = nullptr;
     if (scratch_n < n) {
         scratch.release();
-        ro = scratch.alloc<float4>(n); rd = scratch.alloc<float4>(n); cnt = scratch.alloc<uint32_t>(1);
+        ro = scratch.alloc<float4>(n); rd = scratch.alloc<float4>(n); cnt = scratch.alloc<uint32_t>(2);
         slot_tmp = scratch.alloc<uint32_t>(n);
         if (!ro || !rd || !cnt || !slot_tmp) { scratch.release(); scratch_n = 0; return fail(SPT_ERR_CUDA, "device allocation failed"); }
         scratch_n = n;
     }
     uint32_t n32 = (uint32_t)n;
-    cudaMemcpyAsync(cnt, &n32, 4, cudaMemcpyHostToDevice, s->stream);
+    static thread_local uint32_t cw[2];
+    cw[0] = n32; cw[1] = 0;
+    cudaMemcpyAsync(cnt, cw, 8, cudaMemcpyHostToDevice, s->stream);
     unsigned g = (unsigned)std::min<uint64_t>((n + 255) / 256, 65535);
     k_split_rays<<<g, 256, 0, s->stream>>>(rays_dev, n32, ro, rd);
     uint32_t *slot = any ? slot_tmp : (slot_dev ? slot_dev : slot_tmp);
@@ -429,7 +433,7 @@ int spt_shade_samples(SptScene *s, const SptCameraDesc *cam, int32_t max_depth, 
     cfg.cam = *cam; cfg.spp = 1; cfg.max_depth = max_depth; cfg.n_samples = (uint32_t)n;
     cfg.tile = 1; cfg.tilesX = 1; cfg.tilesY = 1; cfg.nranks = 1;
     SampleSource src; src.smp = dsmp; src.rng = drng; src.n_rng = drng ? n_rng : 0; src.seed = 0; src.spp = 1;
-    size_t nc = (size_t)(max_depth + 2) * 4;
+    size_t nc = (size_t)(max_depth + 2) * 8;
     cudaMemsetAsync(s->counts, 0, nc * 4, s->stream);
     reset_class_stats(s);
     run_wave(s, cfg, src, s->counts);
@@ -579,7 +583,7 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
     size_t n_waves = (size_t)((local_pixels + wave_pixels - 1) / wave_pixels);
     int rc = ensure_wave(s, (uint32_t)(wave_pixels * rp->spp), rp->max_depth, std::max<size_t>(n_waves, 1));
     if (rc != SPT_OK) return rc;
-    size_t per_wave = (size_t)(rp->max_depth + 2) * 4;
+    size_t per_wave = (size_t)(rp->max_depth + 2) * 8;
     cudaStream_t st = s->stream;
     CU(cudaMemsetAsync(s->counts, 0, std::max<size_t>(n_waves, 1) * per_wave * 4, st));
     SampleSource src; src.smp = nullptr; src.rng = nullptr; src.n_rng = 0; src.seed = cfg.seed; src.spp = (uint32_t)rp->spp;

@@ -84,11 +84,11 @@ __global__ void __launch_bounds__(256) k_gen_camera(RenderCfg cfg, SampleSource 
             uint32_t s = i % (uint32_t)cfg.spp;
             valid = wave_pixel(cfg, cfg.pixel_base + i / (uint32_t)cfg.spp, &px, &py);
             if (valid) {
-                uint32_t pk = pix_key(px, py);
+                uint32_t pk = pixel_key(src.seed, pix_key(px, py));
                 float t2[2];
-                ld2(src.seed, pk, 0, s, src.spp, t2);
+                ld2(pk, 0, s, src.spp, t2);
                 ix = px + t2[0]; iy = py + t2[1];
-                ld2(src.seed, pk, 1, s, src.spp, t2);
+                ld2(pk, 1, s, src.spp, t2);
                 lu = t2[0]; lv = t2[1];
             }
         }
@@ -106,20 +106,109 @@ __global__ void __launch_bounds__(256) k_gen_camera(RenderCfg cfg, SampleSource 
 }
 
 // ---- K2 / K3 -------------------------------------------------------------------------------------
-// One thread per ray, persistent grid-stride over the device-side queue. Node = two 16-byte loads,
-// triangle = three; todo[] is the reference's 64-entry stack.
+// BVHAccel::Intersect / IntersectP (src/accelerators/bvh.cpp:380-432, :435-481) as a persistent-warp
+// kernel: every lane owns one ray and walks the reference's depth-first node array with the
+// reference's 64-entry todo stack, slab test, near/far rule, leaf order and `t <= maxt` acceptance
+// (ties resolve to the same primitive). Lanes whose ray has terminated sit idle only
+// until fewer than FETCH_THRESHOLD lanes of the warp are still traversing; then the warp drops out
+// of the traversal loop and the idle lanes pull the next rays from the device-side queue with one
+// warp-aggregated atomic (incoherent bounce / MIS rays otherwise leave ~8 of 32 lanes busy).
+// Node = 2 x LDG.128, triangle = 3 x LDG.128 (vertices pre-gathered per BVH slot).
+#define FETCH_THRESHOLD 20
 template <bool ANY, bool COUNT>
-__global__ void __launch_bounds__(128) k_trace(DevScene sc, const uint32_t *queue, const uint32_t *count,
-                                               const float4 *ro, const float4 *rd, uint32_t *out_slot, float *out_t) {
-    uint32_t n = *count;
-    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
-        uint32_t i = queue ? queue[q] : q;
-        float4 o = ro[i], d = rd[i];
-        Ray ray;
-        ray.o = V(o.x, o.y, o.z); ray.d = V(d.x, d.y, d.z); ray.mint = o.w; ray.maxt = d.w;
-        uint32_t s = bvh_traverse<ANY, COUNT>(sc, ray);
-        out_slot[i] = s;
-        if (!ANY) out_t[i] = ray.maxt;
+__global__ void __launch_bounds__(128) k_trace(DevScene sc, const uint32_t *__restrict__ queue, const uint32_t *__restrict__ count,
+                                               uint32_t *__restrict__ work, const float4 *__restrict__ ro,
+                                               const float4 *__restrict__ rd, uint32_t *__restrict__ out_slot,
+                                               float *__restrict__ out_t) {
+    const uint32_t n = *count;
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    uint32_t todo[64];
+    uint32_t todoOffset = 0, nodeNum = 0, best = SPT_MISS, i = 0;
+    Ray ray; ray.o = V(0, 0, 0); ray.d = V(0, 0, 1); ray.mint = 0.f; ray.maxt = 0.f;
+    v3 invDir = V(0, 0, 0);
+    bool negx = false, negy = false, negz = false;
+    bool active = false, exhausted = (n == 0);
+    unsigned long long cn = 0, cp = 0;
+    for (;;) {
+        // ---- fetch: idle lanes take the next rays of the queue
+        unsigned idle = __ballot_sync(FULL, !active);
+        if (!exhausted && idle) {
+            uint32_t base = 0;
+            int leader = __ffs(idle) - 1;
+            if (lane == leader) base = atomicAdd(work, (uint32_t)__popc(idle));
+            base = __shfl_sync(FULL, base, leader);
+            if (!active) {
+                uint32_t q = base + __popc(idle & ((1u << lane) - 1));
+                if (q < n) {
+                    i = queue ? queue[q] : q;
+                    float4 o = ro[i], d = rd[i];
+                    ray.o = V(o.x, o.y, o.z); ray.d = V(d.x, d.y, d.z); ray.mint = o.w; ray.maxt = d.w;
+                    invDir = V(1.f / ray.d.x, 1.f / ray.d.y, 1.f / ray.d.z);
+                    negx = invDir.x < 0; negy = invDir.y < 0; negz = invDir.z < 0;
+                    todoOffset = 0; nodeNum = 0; best = SPT_MISS;
+                    active = true;
+                    if (sc.n_nodes == 0) { out_slot[i] = SPT_MISS; if (!ANY) out_t[i] = ray.maxt; active = false; }
+                }
+            }
+            if (base + (uint32_t)__popc(idle) >= n) exhausted = true;
+        }
+        if (!__any_sync(FULL, active)) break;
+        // ---- traverse until this lane's ray terminates or the warp has gone too idle
+        while (active) {
+            float4 n0 = __ldg(&sc.nodes[2 * (size_t)nodeNum]);
+            float4 n1 = __ldg(&sc.nodes[2 * (size_t)nodeNum + 1]);
+            if (COUNT) ++cn;
+            bool pop = true;
+            if (slab(n0, n1, ray, invDir, negx, negy, negz)) {
+                uint32_t meta = __float_as_uint(n1.w);
+                uint32_t offset = __float_as_uint(n1.z);
+                uint32_t nPrims = meta & 0xff;
+                if (nPrims > 0) {
+                    bool hasQuadric = (meta >> 16) & 1;
+                    for (uint32_t k = 0; k < nPrims; ++k) {
+                        uint32_t s = offset + k;
+                        if (COUNT) ++cp;
+                        float t;
+                        bool h;
+                        if (!hasQuadric || sc.prim_kind[s] == SPT_PRIM_TRIANGLE) {
+                            float4 a = __ldg(&sc.tri_verts[3 * (size_t)s]);
+                            float4 b = __ldg(&sc.tri_verts[3 * (size_t)s + 1]);
+                            float4 c = __ldg(&sc.tri_verts[3 * (size_t)s + 2]);
+                            float b1, b2;
+                            h = tri_test(V(a.x, a.y, a.z), V(b.x, b.y, b.z), V(c.x, c.y, c.z), ray, &t, &b1, &b2);
+                        } else if (sc.prim_kind[s] == SPT_PRIM_SPHERE) {
+                            h = sphere_intersect(sc, sc.quadrics[sc.prim_data[s]], 0, ray, &t, nullptr);
+                        } else {
+                            h = disk_intersect(sc, sc.quadrics[sc.prim_data[s]], 0, ray, &t, nullptr);
+                        }
+                        if (h) {
+                            best = s;
+                            if (ANY) break;            // IntersectP returns at the first accepted primitive
+                            ray.maxt = t;
+                        }
+                    }
+                } else {
+                    uint32_t axis = (meta >> 8) & 0xff;
+                    bool neg = axis == 0 ? negx : (axis == 1 ? negy : negz);
+                    if (neg) { todo[todoOffset++] = nodeNum + 1; nodeNum = offset; }
+                    else { todo[todoOffset++] = offset; nodeNum = nodeNum + 1; }
+                    pop = false;
+                }
+            }
+            if (pop) {
+                if (todoOffset == 0 || (ANY && best != SPT_MISS)) {
+                    out_slot[i] = best;
+                    if (!ANY) out_t[i] = ray.maxt;
+                    active = false;
+                } else nodeNum = todo[--todoOffset];
+            }
+            if (active && !exhausted && __popc(__activemask()) < FETCH_THRESHOLD) break;
+        }
+    }
+    if (COUNT && sc.counters && (cn | cp)) {
+        atomicAdd(&sc.counters[ANY ? 2 : 0], cn);
+        atomicAdd(&sc.counters[ANY ? 3 : 1], cp);
     }
 }
 
@@ -175,7 +264,7 @@ __global__ void __launch_bounds__(128) k_shade(DevScene sc, RenderCfg cfg, Sampl
                 if (!src.smp) {
                     int px, py;
                     wave_pixel(cfg, cfg.pixel_base + i / (uint32_t)cfg.spp, &px, &py);
-                    pk = pix_key(px, py);
+                    pk = pixel_key(src.seed, pix_key(px, py));
                 }
                 float u[10], rr;
                 bounce_dims(src, i, pk, s_idx, bounce, sc.n_lights > 0, u, &rr);
@@ -194,12 +283,12 @@ __global__ void __launch_bounds__(128) k_shade(DevScene sc, RenderCfg cfg, Sampl
                     if (lr.pdf > 0.f && !lr.black) {
                         DirTerms t;
                         v3 wi = w2l(bsdf, lr.wi);
-                        bsdf_terms(bsdf, woW, lr.wi, wo, wi, &t);
+                        float bsdfPdf;
+                        bsdf_terms(bsdf, woW, lr.wi, wo, wi, &t, &bsdfPdf);
                         if (t.reflect) {
                             float sL;
                             if (lr.delta) sL = (absdot(lr.wi, n_s) / lr.pdf);
                             else {
-                                float bsdfPdf = bsdf_pdf(bsdf, wo, wi);
                                 float weight = power_heuristic(lr.pdf, bsdfPdf);
                                 sL = (absdot(lr.wi, n_s) * weight / lr.pdf);
                             }
@@ -250,12 +339,43 @@ __global__ void __launch_bounds__(128) k_shade(DevScene sc, RenderCfg cfg, Sampl
 }
 
 // ---- K6 ----------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_accumulate(DevScene sc, RenderCfg cfg, WaveBuffers wb, int bounce,
-                                                    const uint32_t *queue, const uint32_t *count,
-                                                    uint32_t *next_queue, uint32_t *next_count) {
+// Per-direction BSDF value rebuilt per band from wavelength-independent coefficients:
+//   matte / plastic:  f[c] = spec0[c]*u0 + spec1[c]*u1     (Lambert/Oren-Nayar + Blinn microfacet x dielectric Fresnel)
+//   metal:            f[c] = w * FrCond(cosH, eta[c], k[c])
+// The scalar factors (D*G*F/(4 cosI cosO), |cos|*weight/pdf, ...) are folded once per vertex instead of
+// once per band as the reference's Spectrum arithmetic does; this reassociation moves results by
+// rounding only (tests compare radiance at 2e-4 relative).
+struct DirCoef { float u0, u1, w, cosH; };
+__device__ __forceinline__ DirCoef dir_coef(int mtype, bool on, bool reflect, bool mf, float4 a) {
+    DirCoef d; d.u0 = d.u1 = d.w = 0.f; d.cosH = 1.f;
+    if (!reflect) return d;
+    if (mtype == SPT_MAT_MATTE) d.u0 = on ? INV_PI_F * a.x : INV_PI_F;
+    else if (mtype == SPT_MAT_PLASTIC) { d.u0 = INV_PI_F; if (mf) d.u1 = a.x * a.y * a.z / a.w; }
+    else if (mf) { d.w = a.x * a.y / a.w; d.cosH = a.z; }
+    return d;
+}
+// FrCond (reflection.cpp:63-71) with the two quotients combined into one division
+__device__ __forceinline__ float fr_cond_fast(float cosi, float c2, float eta, float k) {
+    float A = fmaf(eta, eta, k * k);
+    float e2 = 2.f * eta * cosi;
+    float Ac2 = A * c2;
+    float n1 = Ac2 - e2 + 1.f, d1 = Ac2 + e2 + 1.f;
+    float n2 = A - e2 + c2, d2 = A + e2 + c2;
+    return 0.5f * __fdividef(fmaf(n1, d2, n2 * d1), d1 * d2);
+}
+struct LightBand { int kind; const float *spec; IllumCoefs k; };   // kind: 0 none, 1 table spectrum, 2 rgb illuminant
+__device__ __forceinline__ float light_band(const SptSpectralTables &tb, const LightBand &l, int c) {
+    return l.kind == 1 ? __ldg(l.spec + c) : (l.kind == 2 ? illum_band(tb, l.k, c) : 0.f);
+}
+
+__global__ void __launch_bounds__(128, 4) k_accumulate(DevScene sc, RenderCfg cfg, WaveBuffers wb, int bounce,
+                                                       const uint32_t *__restrict__ queue, const uint32_t *__restrict__ count,
+                                                       uint32_t *__restrict__ next_queue, uint32_t *__restrict__ next_count) {
     uint32_t n = *count;
     const uint32_t cap = wb.cap;
     const SptSpectralTables &tb = *sc.tables;
+    float *__restrict__ Tg = wb.T;
+    float *__restrict__ Lg = wb.L;
     for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < ((n + 31u) & ~31u); q += gridDim.x * blockDim.x) {
         bool active = q < n;
         uint32_t i = active ? queue[q] : 0;
@@ -264,27 +384,26 @@ __global__ void __launch_bounds__(128) k_accumulate(DevScene sc, RenderCfg cfg, 
         if (active && r6.x != 0xffffffffu) {
             uint32_t flags = r6.x;
             const SptMaterial &m = sc.materials[r6.y];
+            const int mtype = m.type;
             int lightIdx = (int)r6.z;
             bool on = (flags & RF_ON) != 0;
             float4 r3 = wb.r3[i], r4 = wb.r4[i];
             float4 g0 = wb.g0[i];
-            // --- light-sample term (integrator.cpp:122-137)
-            bool useL = (flags & RF_L) && wb.sh_slot[i] == SPT_MISS;
-            DirTerms tL, tB, tP;
-            int ltype = 0; float laux0 = 0.f; IllumCoefs lk;
-            const float *lspec = nullptr;
-            if (useL) {
-                float4 r0 = wb.r0[i], r5 = wb.r5[i];
-                tL.a0 = r0.x; tL.a1 = r0.y; tL.a2 = r0.z; tL.a3 = r0.w; tL.reflect = true; tL.mf = (flags & RF_L_MF) != 0;
+            // --- light-sample term (integrator.cpp:122-137): visible iff the shadow ray found nothing
+            DirCoef cL = dir_coef(mtype, on, false, false, make_float4(0, 0, 0, 0)), cB = cL, cP = cL;
+            LightBand lbL, lbB; lbL.kind = 0; lbB.kind = 0; lbL.spec = lbB.spec = nullptr;
+            float sL = 0.f, sB = 0.f, sP = 0.f;
+            if ((flags & RF_L) && wb.sh_slot[i] == SPT_MISS) {
+                float4 r5 = wb.r5[i];
+                cL = dir_coef(mtype, on, true, (flags & RF_L_MF) != 0, wb.r0[i]);
                 const SptLight &l = sc.lights[lightIdx];
-                ltype = l.type; lspec = l.spectrum; laux0 = r5.x;
-                if (ltype == SPT_LIGHT_INFINITE) { float rgb[3] = { r5.x, r5.y, r5.z }; lk = illum_coefs(rgb); }
+                sL = r3.x;
+                if (l.type == SPT_LIGHT_INFINITE) { float rgb[3] = { r5.x, r5.y, r5.z }; lbL.kind = 2; lbL.k = illum_coefs(rgb); }
+                else { lbL.kind = 1; lbL.spec = l.spectrum; if (l.type == SPT_LIGHT_POINT) sL = sL / r5.x; }
             }
             // --- BSDF-sample term (integrator.cpp:139-163): radiance from what the MIS ray found
-            bool useB = false; int btype = 0; IllumCoefs bk; const float *bspec = nullptr;
             if (flags & RF_B) {
-                float4 r1 = wb.r1[i], g2 = wb.g2[i];
-                tB.a0 = r1.x; tB.a1 = r1.y; tB.a2 = r1.z; tB.a3 = r1.w; tB.reflect = true; tB.mf = (flags & RF_B_MF) != 0;
+                float4 g2 = wb.g2[i];
                 uint32_t ms = wb.mis_slot[i];
                 const SptLight &l = sc.lights[lightIdx];
                 v3 wi = V(g2.x, g2.y, g2.z);
@@ -293,42 +412,58 @@ __global__ void __launch_bounds__(128) k_accumulate(DevScene sc, RenderCfg cfg, 
                         Ray ray; ray.o = V(g0.x, g0.y, g0.z); ray.d = wi; ray.mint = g0.w; ray.maxt = SPT_INF;
                         Hit h;
                         if (shape_intersect(sc, sc.prim_kind[ms], sc.prim_flags[ms], sc.prim_data[ms], ray, &h) &&
-                            dot(h.nn, vneg(wi)) > 0.f) { useB = true; btype = SPT_LIGHT_AREA; bspec = l.spectrum; }
+                            dot(h.nn, vneg(wi)) > 0.f) { lbB.kind = 1; lbB.spec = l.spectrum; }
                     }
                 } else if (l.type == SPT_LIGHT_INFINITE) {
                     float rgb[3];
                     infinite_le_rgb(sc, l, wi, rgb);
-                    bk = illum_coefs(rgb);
-                    useB = true; btype = SPT_LIGHT_INFINITE;
+                    lbB.kind = 2; lbB.k = illum_coefs(rgb);
                 }
+                if (lbB.kind) { cB = dir_coef(mtype, on, true, (flags & RF_B_MF) != 0, wb.r1[i]); sB = r3.y * r3.z / r3.w; }
             }
             bool haveP = (flags & RF_P) != 0;
-            if (haveP) {
-                float4 r2 = wb.r2[i];
-                tP.a0 = r2.x; tP.a1 = r2.y; tP.a2 = r2.z; tP.a3 = r2.w;
-                tP.reflect = (flags & RF_P_REFL) != 0; tP.mf = (flags & RF_P_MF) != 0;
-            }
-            float nL = (float)sc.n_lights;
+            if (haveP) { cP = dir_coef(mtype, on, (flags & RF_P_REFL) != 0, (flags & RF_P_MF) != 0, wb.r2[i]); sP = r4.x / r4.y; }
+            const float nL = (float)sc.n_lights;
+            sL *= nL; sB *= nL;
+            const bool metal = mtype == SPT_MAT_METAL;
+            const float cL2 = cL.cosH * cL.cosH, cB2 = cB.cosH * cB.cosH, cP2 = cP.cosH * cP.cosH;
             float yy = 0.f;
             bool fBlack = true;
+            const float *__restrict__ s0p = m.spec0;
+            const float *__restrict__ s1p = m.spec1;
             // the one band loop of the bounce: L += T * Ld * nLights ; T *= f |cos| / pdf
-            for (int c = 0; c < NB; ++c) {
-                float T = bounce == 0 ? 1.f : wb.T[(size_t)c * cap + i];
-                float Ld = 0.f;
-                if (useL) {
-                    float Li = ltype == SPT_LIGHT_AREA ? lspec[c] : (ltype == SPT_LIGHT_POINT ? lspec[c] / laux0 : illum_band(tb, lk, c));
-                    Ld += f_band(m, on, tL, c) * Li * r3.x;
+            // (8 bands per trip: 16 independent loads in flight before any store)
+#pragma unroll 1
+            for (int c0 = 0; c0 < NB; c0 += 8) {
+                float Tv[8], Lv[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    size_t off = (size_t)(c0 + k) * cap + i;
+                    Tv[k] = bounce == 0 ? 1.f : Tg[off];
+                    Lv[k] = Lg[off];
                 }
-                if (useB) {
-                    float Li = btype == SPT_LIGHT_AREA ? bspec[c] : illum_band(tb, bk, c);
-                    Ld += f_band(m, on, tB, c) * Li * r3.y * r3.z / r3.w;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int c = c0 + k;
+                    float s0 = __ldg(s0p + c), s1 = __ldg(s1p + c);
+                    float fL, fB, fP;
+                    if (metal) {
+                        fL = cL.w != 0.f ? cL.w * fr_cond_fast(cL.cosH, cL2, s0, s1) : 0.f;
+                        fB = cB.w != 0.f ? cB.w * fr_cond_fast(cB.cosH, cB2, s0, s1) : 0.f;
+                        fP = cP.w != 0.f ? cP.w * fr_cond_fast(cP.cosH, cP2, s0, s1) : 0.f;
+                    } else {
+                        fL = fmaf(s0, cL.u0, s1 * cL.u1);
+                        fB = fmaf(s0, cB.u0, s1 * cB.u1);
+                        fP = fmaf(s0, cP.u0, s1 * cP.u1);
+                    }
+                    float Ld = fL * light_band(tb, lbL, c) * sL + fB * light_band(tb, lbB, c) * sB;
+                    size_t off = (size_t)c * cap + i;
+                    Lg[off] = fmaf(Tv[k], Ld, Lv[k]);
+                    if (fP != 0.f) fBlack = false;
+                    float Tn = Tv[k] * (fP * sP);
+                    Tg[off] = Tn;
+                    yy = fmaf(tb.cie_y[c], Tn, yy);
                 }
-                if (sc.n_lights > 0) wb.L[(size_t)c * cap + i] += T * (Ld * nL);
-                float f = haveP ? f_band(m, on, tP, c) : 0.f;
-                if (f != 0.f) fBlack = false;
-                float Tn = T * (f * r4.x / r4.y);
-                wb.T[(size_t)c * cap + i] = Tn;
-                yy += tb.cie_y[c] * Tn;
             }
             // path.cpp:88-104
             if (haveP && !fBlack) {
@@ -336,8 +471,10 @@ __global__ void __launch_bounds__(128) k_accumulate(DevScene sc, RenderCfg cfg, 
                 if (bounce > 3) {
                     float continueProbability = stdminf(.5f, yy / tb.yint);
                     if (r4.z > continueProbability) alive = false;
-                    else if (bounce != cfg.max_depth)
-                        for (int c = 0; c < NB; ++c) wb.T[(size_t)c * cap + i] /= continueProbability;
+                    else if (bounce != cfg.max_depth) {
+                        float inv = 1.f / continueProbability;
+                        for (int c = 0; c < NB; ++c) Tg[(size_t)c * cap + i] *= inv;
+                    }
                 }
                 if (bounce == cfg.max_depth) alive = false;
                 if (alive) {

@@ -198,67 +198,3 @@ __device__ __forceinline__ bool slab(const float4 &n0, const float4 &n1, const R
     return (tmin < ray.maxt) && (tmax > ray.mint);
 }
 
-// ---- BVHAccel::Intersect / IntersectP (src/accelerators/bvh.cpp:380-432, :435-481) ------------
-// Same node order, near/far rule, leaf order and `t <= maxt` acceptance as the reference, so ties
-// resolve to the same primitive. ANY: return at the first accepted primitive.
-// Returns the BVH slot of the closest hit (or SPT_MISS); ray.maxt is shrunk to the hit distance.
-template <bool ANY, bool COUNT>
-__device__ __forceinline__ uint32_t bvh_traverse(const DevScene &sc, Ray &ray) {
-    uint32_t best = SPT_MISS;
-    if (sc.n_nodes == 0) return best;
-    v3 invDir = V(1.f / ray.d.x, 1.f / ray.d.y, 1.f / ray.d.z);
-    bool negx = invDir.x < 0, negy = invDir.y < 0, negz = invDir.z < 0;
-    uint32_t todo[64];
-    uint32_t todoOffset = 0, nodeNum = 0;
-    unsigned long long cn = 0, cp = 0;
-    while (true) {
-        float4 n0 = __ldg(&sc.nodes[2 * (size_t)nodeNum]);
-        float4 n1 = __ldg(&sc.nodes[2 * (size_t)nodeNum + 1]);
-        if (COUNT) ++cn;
-        if (slab(n0, n1, ray, invDir, negx, negy, negz)) {
-            uint32_t meta = __float_as_uint(n1.w);
-            uint32_t offset = __float_as_uint(n1.z);
-            uint32_t nPrims = meta & 0xff;
-            if (nPrims > 0) {
-                bool hasQuadric = (meta >> 16) & 1;
-                for (uint32_t i = 0; i < nPrims; ++i) {
-                    uint32_t s = offset + i;
-                    if (COUNT) ++cp;
-                    float t;
-                    bool h;
-                    if (!hasQuadric || sc.prim_kind[s] == SPT_PRIM_TRIANGLE) {
-                        float4 a = __ldg(&sc.tri_verts[3 * (size_t)s]);
-                        float4 b = __ldg(&sc.tri_verts[3 * (size_t)s + 1]);
-                        float4 c = __ldg(&sc.tri_verts[3 * (size_t)s + 2]);
-                        float b1, b2;
-                        h = tri_test(V(a.x, a.y, a.z), V(b.x, b.y, b.z), V(c.x, c.y, c.z), ray, &t, &b1, &b2);
-                    } else if (sc.prim_kind[s] == SPT_PRIM_SPHERE) {
-                        h = sphere_intersect(sc, sc.quadrics[sc.prim_data[s]], 0, ray, &t, nullptr);
-                    } else {
-                        h = disk_intersect(sc, sc.quadrics[sc.prim_data[s]], 0, ray, &t, nullptr);
-                    }
-                    if (h) {
-                        if (ANY) {
-                            if (COUNT && sc.counters) { atomicAdd(&sc.counters[2], cn); atomicAdd(&sc.counters[3], cp); }
-                            return s;
-                        }
-                        ray.maxt = t;
-                        best = s;
-                    }
-                }
-                if (todoOffset == 0) break;
-                nodeNum = todo[--todoOffset];
-            } else {
-                uint32_t axis = (meta >> 8) & 0xff;
-                bool neg = axis == 0 ? negx : (axis == 1 ? negy : negz);
-                if (neg) { todo[todoOffset++] = nodeNum + 1; nodeNum = offset; }
-                else { todo[todoOffset++] = offset; nodeNum = nodeNum + 1; }
-            }
-        } else {
-            if (todoOffset == 0) break;
-            nodeNum = todo[--todoOffset];
-        }
-    }
-    if (COUNT && sc.counters) { atomicAdd(&sc.counters[ANY ? 2 : 0], cn); atomicAdd(&sc.counters[ANY ? 3 : 1], cp); }
-    return best;
-}
