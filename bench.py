@@ -256,8 +256,10 @@ def main():
     # ---- e2e through the C ABI with host buffers (rank-local: each rank uploads, renders its tiles, downloads)
     scene_bytes = int(sum(v.nbytes for k, v in lowered.a.items() if k not in ("camera", "film", "params", "film_filename")))
     film_bytes = fd.x_pixel_count * fd.y_pixel_count * (D.NBANDS + 1) * 4
-    c_host = np.empty((fd.y_pixel_count, fd.x_pixel_count, D.NBANDS), np.float32)
-    w_host = np.empty((fd.y_pixel_count, fd.x_pixel_count), np.float32)
+    # the host's film buffers are page-locked (spt_host_alloc), as a host that reads a film back every frame would hold them
+    c_pin = capi.HostBuffer((fd.y_pixel_count, fd.x_pixel_count, D.NBANDS))
+    w_pin = capi.HostBuffer((fd.y_pixel_count, fd.x_pixel_count))
+    c_host, w_host = c_pin.array, w_pin.array
     e2e_times = []
     for i in range(1 + args.steps):
         barrier()
@@ -271,6 +273,9 @@ def main():
         if i > 0:
             e2e_times.append(t1 - t0)
     e2e_s = sum(e2e_times) / len(e2e_times)
+    e2e_checksum = float(c_host.sum(dtype=np.float64))
+    c_host = w_host = None
+    c_pin.close(); w_pin.close()
     if dist is not None:
         t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -327,7 +332,8 @@ def main():
         "rays_per_sample": rays_total / args.steps / (n_samples_total / world) if world else None,
         "kernel_ms_per_step": {D.K_NAMES[k]: class_ms[k] / args.steps for k in range(D.K_CLASSES) if class_launches[k]},
         "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": scene_bytes, "d2h_bytes_per_step": film_bytes,
-                "ms_per_step": e2e_s * 1e3, "path": "spt_scene_create+spt_film_create+spt_render+spt_film_download, host buffers"},
+                "ms_per_step": e2e_s * 1e3, "path": "spt_scene_create+spt_film_create+spt_render+spt_film_download, host buffers (film read into page-locked host memory)",
+                "image_checksum": e2e_checksum},
         "gpu_launches": launches,
         "roofline": roofline,
         "clocks": sampler.summary() if sampler else None,

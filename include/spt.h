@@ -201,6 +201,13 @@ int         spt_nbands(void);
 const char *spt_last_error(void);
 int         spt_device_count(void);
 int         spt_set_device(int ordinal);
+/* Page-locked host memory for buffers that cross the boundary every frame (the film a host reads
+ * back, scene tables it uploads): copies to and from it run at full PCIe rate. Plain malloc'ed
+ * buffers are accepted everywhere as well. Returns NULL on failure. */
+void       *spt_host_alloc(uint64_t bytes);
+void        spt_host_free(void *p);
+/* Releases the device memory the library caches between scenes (wave state of destroyed scenes). */
+void        spt_trim(void);
 
 /* Scene: uploads every table to HBM (replaces nothing in the reference; it is the hand-off). */
 SptScene *spt_scene_create(const SptSceneDesc *desc);

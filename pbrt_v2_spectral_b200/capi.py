@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libspt.so")
 
 # every symbol include/spt.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
-    "spt_nbands", "spt_last_error", "spt_device_count", "spt_set_device",
+    "spt_nbands", "spt_last_error", "spt_device_count", "spt_set_device", "spt_host_alloc", "spt_host_free", "spt_trim",
     "spt_scene_create", "spt_scene_destroy", "spt_scene_enable_counters", "spt_get_stats",
     "spt_camera_rays", "spt_trace_closest", "spt_trace_any", "spt_trace_closest_dev", "spt_trace_any_dev",
     "spt_shade_samples",
@@ -38,6 +38,10 @@ def lib():
             raise SptError("libspt.so is not built (python -m pbrt_v2_spectral_b200.build); there is no fallback path")
         L = C.CDLL(LIB_PATH)
         L.spt_last_error.restype = C.c_char_p
+        L.spt_host_alloc.restype = C.c_void_p
+        L.spt_host_alloc.argtypes = [C.c_uint64]
+        L.spt_host_free.argtypes = [C.c_void_p]
+        L.spt_trim.restype = None
         L.spt_scene_create.restype = C.c_void_p
         L.spt_scene_create.argtypes = [C.POINTER(D.SptSceneDesc)]
         L.spt_scene_destroy.argtypes = [C.c_void_p]
@@ -83,6 +87,28 @@ def device_count():
 
 def set_device(i):
     _check(lib().spt_set_device(int(i)))
+
+
+class HostBuffer:
+    """Page-locked host array (spt_host_alloc) viewed as numpy; free with close()."""
+
+    def __init__(self, shape, dtype=np.float32):
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self.ptr = lib().spt_host_alloc(n)
+        if not self.ptr:
+            raise SptError("spt_host_alloc: " + (lib().spt_last_error() or b"").decode())
+        buf = (C.c_char * n).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def close(self):
+        if self.ptr:
+            self.array = None
+            lib().spt_host_free(self.ptr)
+            self.ptr = None
+
+
+def trim():
+    lib().spt_trim()
 
 
 def camera_rays(camera, samples5):

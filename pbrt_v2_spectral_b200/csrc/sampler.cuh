@@ -58,14 +58,7 @@ __device__ __forceinline__ float rng_float(uint32_t rkey, uint32_t k) {
     return (mix32(rkey + k * 0x27d4eb2fU) & 0xffffff) / (float)(1 << 24);          // RNG::RandomFloat, rng.cpp:51-57
 }
 
-// Where a path's sample values come from: generated (production) or caller-supplied arrays in the
-// reference's Sample memory order (spt_shade_samples).
-struct SampleSource {
-    const float *smp;       // n x 37, or NULL
-    const float *rng;       // n x n_rng, or NULL
-    int n_rng;
-    uint32_t seed, spp;
-};
+#include "sampler_source.h"
 // `pkey` below is pixel_key(seed, pix) of the path's sampler pixel
 
 // The ten values bounce `b` consumes: {lightNum, lightPos0, lightPos1, lightComp, bsdfDir0,

@@ -3,10 +3,12 @@
 // There is no CPU path: without a CUDA device every computing entry point returns SPT_ERR_CUDA.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
-#include "spt_kernels.cuh"
+#include "launch.h"
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string &msg) { g_err = msg; return code; }
@@ -40,6 +42,13 @@ int num_sms() {
     return n;
 }
 
+// Wave state (2.4 GB at the default capacity) outlives the scene that allocated it: a host that
+// renders frame after frame (scene_create -> render -> destroy) gets the same buffers back instead
+// of paying cudaMalloc/cudaFree of gigabytes per frame. One entry per device; spt_trim() frees them.
+struct WaveCache { int device; DevMem mem; WaveBuffers wb; uint32_t *counts; size_t counts_len; };
+std::mutex g_wave_mu;
+std::vector<WaveCache> g_wave_cache;
+
 }  // namespace
 
 struct SptScene {
@@ -48,6 +57,9 @@ struct SptScene {
     std::vector<uint32_t> prim_id_host;
     uint32_t *prim_id_dev = nullptr;
     bool counters_on = false;
+    int trace_variant = 2;           // trace_kernels.cuh
+    uint32_t leaf_wait = 6;
+    bool has_env = false;            // an infinite light is present (escaped camera rays pick up Le)
     unsigned long long *counters = nullptr;
     // wave buffers, allocated on first use and reused
     DevMem wave_mem;
@@ -75,6 +87,7 @@ struct SptFilm {
     float *pix = nullptr;           // [y][x][NB+1]
     bool owned = true;
     float *table = nullptr;
+    float *split = nullptr;         // download staging: [y][x][NB] followed by [y][x] weights
     size_t npix() const { return (size_t)desc.x_pixel_count * desc.y_pixel_count; }
 };
 
@@ -84,12 +97,25 @@ int spt_nbands(void) { return NB; }
 const char *spt_last_error(void) { return g_err.c_str(); }
 int spt_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
 int spt_set_device(int ordinal) { CU(cudaSetDevice(ordinal)); return SPT_OK; }
+void *spt_host_alloc(uint64_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { g_err = "cudaMallocHost failed"; cudaGetLastError(); return nullptr; }
+    return p;
+}
+void spt_host_free(void *p) { if (p) cudaFreeHost(p); }
+void spt_trim(void) {
+    std::lock_guard<std::mutex> lk(g_wave_mu);
+    for (WaveCache &c : g_wave_cache) c.mem.release();
+    g_wave_cache.clear();
+}
 
 SptScene *spt_scene_create(const SptSceneDesc *d) {
     if (!d) { g_err = "null scene desc"; return nullptr; }
     if (d->nbands != NB) { g_err = "scene band count does not match the library's SPT_NBANDS"; return nullptr; }
     if (spt_device_count() <= 0) { g_err = "no CUDA device: this library has no CPU path"; return nullptr; }
     SptScene *s = new SptScene();
+    if (const char *e = getenv("SPT_TRACE_VARIANT")) s->trace_variant = atoi(e);
+    if (const char *e = getenv("SPT_LEAF_WAIT")) s->leaf_wait = (uint32_t)atoi(e);
     DevScene &v = s->dev;
     memset(&v, 0, sizeof(v));
     // nodes: byte-identical copy, plus the hasQuadric bit in the reference's pad byte for leaves
@@ -101,6 +127,32 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
         nd[30] = 0; nd[31] = 0;
         for (uint32_t i = 0; i < np; ++i)
             if (off + i < d->n_prims && d->prim_kind[off + i] != SPT_PRIM_TRIANGLE) nd[30] = 1;
+    }
+    // pair nodes: compact array over the interior nodes of the reference's depth-first layout
+    std::vector<float4> pn;
+    uint2 root_code = make_uint2(0, 0);
+    {
+        struct RefNode { float b[6]; uint32_t off; uint8_t np, axis, hasq, pad; };
+        const RefNode *rn = (const RefNode *)nodes.data();
+        std::vector<uint32_t> pidx(d->n_nodes, 0xffffffffu);
+        uint32_t nint = 0;
+        for (uint32_t n = 0; n < d->n_nodes; ++n) if (rn[n].np == 0) pidx[n] = nint++;
+        pn.assign((size_t)nint * 4, make_float4(0, 0, 0, 0));
+        auto code = [&](uint32_t c) { return rn[c].np ? rn[c].off : pidx[c]; };
+        auto meta = [&](uint32_t c) { return (uint32_t)rn[c].np | ((uint32_t)(rn[c].hasq ? 1 : 0) << 8); };
+        for (uint32_t n = 0; n < d->n_nodes; ++n) {
+            if (rn[n].np) continue;
+            uint32_t c0 = n + 1, c1 = rn[n].off;
+            if (c0 >= d->n_nodes || c1 >= d->n_nodes) { g_err = "malformed BVH: child index out of range"; delete s; return nullptr; }
+            float4 *q = &pn[(size_t)pidx[n] * 4];
+            const float *a = rn[c0].b, *b = rn[c1].b;
+            q[0] = make_float4(a[0], a[1], a[2], a[3]);
+            q[1] = make_float4(a[4], a[5], b[0], b[1]);
+            q[2] = make_float4(b[2], b[3], b[4], b[5]);
+            uint32_t w[4] = { code(c0), code(c1), (uint32_t)(rn[n].axis & 3) | (meta(c0) << 8) | (meta(c1) << 17), 0u };
+            memcpy(&q[3], w, 16);
+        }
+        if (d->n_nodes) root_code = make_uint2(code(0), meta(0));
     }
     // pre-gathered triangle vertices per BVH slot
     std::vector<float4> tv((size_t)d->n_prims * 3, make_float4(0, 0, 0, 0));
@@ -130,6 +182,8 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
 #define UP(dst, src, n) do { dst = m.upload(src, (size_t)(n)); if (!dst) ok = false; } while (0)
     const float4 *nodes4; UP(nodes4, (const float4 *)nodes.data(), (size_t)d->n_nodes * 2); v.nodes = nodes4;
     UP(v.tri_verts, tv.data(), tv.size());
+    UP(v.pnodes, pn.data(), pn.size());
+    v.root_code = root_code;
     v.n_nodes = d->n_nodes; v.n_prims = d->n_prims;
     UP(v.prim_kind, d->prim_kind, d->n_prims); UP(v.prim_flags, d->prim_flags, d->n_prims);
     UP(v.prim_id, d->prim_id, d->n_prims); UP(v.prim_data, d->prim_data, d->n_prims);
@@ -142,6 +196,7 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
     UP(v.light_shapes, d->light_shapes, d->n_light_shapes);
     UP(v.light_cdf, cdf.data(), cdf.size());
     v.n_lights = d->n_lights;
+    for (uint32_t li = 0; li < d->n_lights; ++li) if (d->lights[li].type == SPT_LIGHT_INFINITE) s->has_env = true;
     UP(v.tables, &d->tables, 1);
     v.env_w = d->env_w; v.env_h = d->env_h;
     size_t ew = (size_t)d->env_w, eh = (size_t)d->env_h;
@@ -167,6 +222,17 @@ void spt_scene_destroy(SptScene *s) {
     if (!s) return;
     cudaDeviceSynchronize();
     s->mem.release();
+    if (s->wb.cap) {
+        int dev = 0; cudaGetDevice(&dev);
+        std::lock_guard<std::mutex> lk(g_wave_mu);
+        bool kept = false;
+        for (WaveCache &c : g_wave_cache)
+            if (c.device == dev) {
+                if (c.wb.cap < s->wb.cap) { c.mem.release(); c.mem = s->wave_mem; c.wb = s->wb; c.counts = s->counts; c.counts_len = s->counts_len; s->wave_mem.ptrs.clear(); }
+                kept = true;
+            }
+        if (!kept) { g_wave_cache.push_back(WaveCache{dev, s->wave_mem, s->wb, s->counts, s->counts_len}); s->wave_mem.ptrs.clear(); }
+    }
     s->wave_mem.release();
     if (s->stream) cudaStreamDestroy(s->stream);
     if (s->ev0) cudaEventDestroy(s->ev0);
@@ -202,7 +268,20 @@ int spt_get_stats(SptScene *s, SptStats *out) {
 
 // ---------------------------------------------------------------------------------------------
 static int ensure_wave(SptScene *s, uint32_t cap, int max_depth, size_t n_waves) {
+    cap = (cap + 31u) & ~31u;            // band_off() tiles 32 paths
     size_t need_counts = n_waves * (size_t)(max_depth + 2) * 8;
+    if (s->wb.cap < cap) {
+        int dev = 0; cudaGetDevice(&dev);
+        std::lock_guard<std::mutex> lk(g_wave_mu);
+        for (size_t k = 0; k < g_wave_cache.size(); ++k)
+            if (g_wave_cache[k].device == dev && g_wave_cache[k].wb.cap >= cap) {
+                WaveCache &c = g_wave_cache[k];
+                s->wave_mem.release();
+                s->wave_mem = c.mem; s->wb = c.wb; s->counts = c.counts; s->counts_len = c.counts_len;
+                g_wave_cache.erase(g_wave_cache.begin() + k);
+                break;
+            }
+    }
     if (s->wb.cap < cap) {
         s->wave_mem.release();
         s->counts = nullptr; s->counts_len = 0;
@@ -219,6 +298,7 @@ static int ensure_wave(SptScene *s, uint32_t cap, int max_depth, size_t n_waves)
         AL(w.img_xy, float2, cap);
         AL(w.T, float, (size_t)cap * NB); AL(w.L, float, (size_t)cap * NB);
         AL(w.pathQ[0], uint32_t, cap); AL(w.pathQ[1], uint32_t, cap); AL(w.shadowQ, uint32_t, cap); AL(w.misQ, uint32_t, cap);
+        AL(w.hitQ, uint32_t, cap); AL(w.missQ, uint32_t, cap);
 #undef AL
         if (!ok) { s->wb.cap = 0; m.release(); return fail(SPT_ERR_CUDA, "out of device memory for wave buffers"); }
     }
@@ -228,6 +308,15 @@ static int ensure_wave(SptScene *s, uint32_t cap, int max_depth, size_t n_waves)
         s->counts_len = need_counts;
     }
     return SPT_OK;
+}
+
+// One launch of the traversal kernel (variant chosen per scene; SPT_TRACE_VARIANT overrides for experiments).
+template <bool ANY>
+static void launch_trace(SptScene *s, int grid, const uint32_t *queue, const uint32_t *count, uint32_t *work,
+                         const float4 *ro, const float4 *rd, uint32_t *out_slot, float *out_t) {
+    TraceArgs a; a.queue = queue; a.count = count; a.work = work; a.ro = ro; a.rd = rd; a.out_slot = out_slot; a.out_t = out_t;
+    a.leaf_wait = s->leaf_wait;
+    spt_launch_trace(ANY, s->trace_variant, s->counters_on, grid, s->stream, s->dev, a);
 }
 
 // Runs one wave: K1, then (K2, K5, K3, K2, K6) per bounce. counts: (max_depth+2) x 4 device words,
@@ -241,7 +330,7 @@ static void run_wave(SptScene *s, const RenderCfg &cfg, const SampleSource &src,
     int gridN = (int)std::min<uint64_t>(((uint64_t)n + 255) / 256, (uint64_t)sms * 16);
     if (gridN < 1) gridN = 1;
     s->mark(-1);
-    k_gen_camera<<<gridN, 256, 0, st>>>(cfg, src, wb, counts + 0);
+    spt_launch_gen_camera(gridN, st, cfg, src, wb, counts + 0);
     s->mark(SPT_K_GEN);
     int gridT = (int)std::min<uint64_t>(((uint64_t)n + 127) / 128, (uint64_t)sms * 16);
     if (gridT < 1) gridT = 1;
@@ -249,20 +338,22 @@ static void run_wave(SptScene *s, const RenderCfg &cfg, const SampleSource &src,
     for (int b = 0; b <= cfg.max_depth; ++b) {
         uint32_t *row = counts + 8 * b, *next = counts + 8 * (b + 1);
         uint32_t *q = wb.pathQ[b & 1], *qn = wb.pathQ[(b + 1) & 1];
-        if (s->counters_on) k_trace<false, true><<<gridP, 128, 0, st>>>(sc, q, row + 0, row + 4, wb.ray_o, wb.ray_d, wb.hit_slot, wb.hit_t);
-        else k_trace<false, false><<<gridP, 128, 0, st>>>(sc, q, row + 0, row + 4, wb.ray_o, wb.ray_d, wb.hit_slot, wb.hit_t);
+        // camera rays that escape pick up the environment light (samplerrenderer.cpp:239-243)
+        uint32_t *mq = (b == 0 && s->has_env) ? wb.missQ : nullptr;
+        launch_trace<false>(s, gridP, q, row + 0, row + 4, wb.ray_o, wb.ray_d, wb.hit_slot, wb.hit_t);
         s->mark(SPT_K_TRACE_PATH);
-        k_shade<<<gridT, 128, 0, st>>>(sc, cfg, src, wb, b, q, row + 0, row + 1, row + 2);
+        spt_launch_compact_hits(gridN, st, q, row + 0, wb.hit_slot, wb.hitQ, row + 3, mq, row + 7);
+        s->mark(SPT_K_SHADE);
+        if (mq) { spt_launch_miss_env(gridT, st, sc, wb, mq, row + 7); s->mark(SPT_K_SHADE); }
+        spt_launch_shade(gridT, st, sc, cfg, src, wb, b, wb.hitQ, row + 3, row + 1, row + 2);
         s->mark(SPT_K_SHADE);
         if (sc.n_lights > 0) {
-            if (s->counters_on) k_trace<true, true><<<gridP, 128, 0, st>>>(sc, wb.shadowQ, row + 1, row + 5, wb.g0, wb.g1, wb.sh_slot, nullptr);
-            else k_trace<true, false><<<gridP, 128, 0, st>>>(sc, wb.shadowQ, row + 1, row + 5, wb.g0, wb.g1, wb.sh_slot, nullptr);
+            launch_trace<true>(s, gridP, wb.shadowQ, row + 1, row + 5, wb.g0, wb.g1, wb.sh_slot, nullptr);
             s->mark(SPT_K_TRACE_SHADOW);
-            if (s->counters_on) k_trace<false, true><<<gridP, 128, 0, st>>>(sc, wb.misQ, row + 2, row + 6, wb.g0, wb.g2, wb.mis_slot, wb.mis_t);
-            else k_trace<false, false><<<gridP, 128, 0, st>>>(sc, wb.misQ, row + 2, row + 6, wb.g0, wb.g2, wb.mis_slot, wb.mis_t);
+            launch_trace<false>(s, gridP, wb.misQ, row + 2, row + 6, wb.g0, wb.g2, wb.mis_slot, wb.mis_t);
             s->mark(SPT_K_TRACE_MIS);
         }
-        k_accumulate<<<gridT, 128, 0, st>>>(sc, cfg, wb, b, q, row + 0, qn, next + 0);
+        spt_launch_accumulate(gridT, st, sc, cfg, wb, b, wb.hitQ, row + 3, qn, next + 0);
         s->mark(SPT_K_ACCUMULATE);
     }
 }
@@ -289,8 +380,8 @@ static void add_ray_stats(SptScene *s, const std::vector<uint32_t> &counts, int 
             s->stats.closest_rays += row[0] + row[2];
             s->stats.any_rays += row[1];
             s->stats.class_rays[SPT_K_TRACE_PATH] += row[0];
-            s->stats.class_rays[SPT_K_SHADE] += row[0];
-            s->stats.class_rays[SPT_K_ACCUMULATE] += row[0];
+            s->stats.class_rays[SPT_K_SHADE] += row[3];
+            s->stats.class_rays[SPT_K_ACCUMULATE] += row[3];
             s->stats.class_rays[SPT_K_TRACE_SHADOW] += row[1];
             s->stats.class_rays[SPT_K_TRACE_MIS] += row[2];
         }
@@ -305,7 +396,7 @@ int spt_camera_rays(const SptCameraDesc *cam, const float *samples, uint64_t n, 
     DevMem m;
     float *ds = m.upload(samples, n * 5), *dr = m.alloc<float>(n * 8);
     if (!ds || !dr) { m.release(); return fail(SPT_ERR_CUDA, "device allocation failed"); }
-    k_camera_rays<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 65535), 256>>>(*cam, ds, (uint32_t)n, dr);
+    spt_launch_camera_rays(0, *cam, ds, (uint32_t)n, dr);
     cudaError_t e = cudaMemcpy(out_rays, dr, n * 8 * sizeof(float), cudaMemcpyDeviceToHost);
     m.release();
     if (e != cudaSuccess) return fail(SPT_ERR_CUDA, cudaGetErrorString(e));
@@ -319,13 +410,8 @@ static int trace_dev(SptScene *s, bool any, const float4 *ro, const float4 *rd, 
     if (grid < 1) grid = 1;
     cudaStream_t st = s->stream;
     cudaEventRecord(s->ev0, st);
-    if (any) {
-        if (s->counters_on) k_trace<true, true><<<grid, 128, 0, st>>>(s->dev, nullptr, count_dev, count_dev + 1, ro, rd, slot, t);
-        else k_trace<true, false><<<grid, 128, 0, st>>>(s->dev, nullptr, count_dev, count_dev + 1, ro, rd, slot, t);
-    } else {
-        if (s->counters_on) k_trace<false, true><<<grid, 128, 0, st>>>(s->dev, nullptr, count_dev, count_dev + 1, ro, rd, slot, t);
-        else k_trace<false, false><<<grid, 128, 0, st>>>(s->dev, nullptr, count_dev, count_dev + 1, ro, rd, slot, t);
-    }
+    if (any) launch_trace<true>(s, grid, nullptr, count_dev, count_dev + 1, ro, rd, slot, t);
+    else launch_trace<false>(s, grid, nullptr, count_dev, count_dev + 1, ro, rd, slot, t);
     cudaEventRecord(s->ev1, st);
     s->launches += 1;
     CU(cudaStreamSynchronize(st));
@@ -352,15 +438,15 @@ static int trace_host(SptScene *s, bool any, const float *rays, uint64_t n, uint
     uint32_t cw[2] = { n32, 0 };
     cudaMemcpyAsync(cnt, cw, 8, cudaMemcpyHostToDevice, s->stream);
     unsigned g = (unsigned)std::min<uint64_t>((n + 255) / 256, 65535);
-    k_split_rays<<<g, 256, 0, s->stream>>>(dr, n32, ro, rd);
+    spt_launch_split_rays(s->stream, dr, n32, ro, rd);
     int rc = trace_dev(s, any, ro, rd, n, slot, t, cnt);
     if (rc == SPT_OK) {
         cudaError_t e = cudaSuccess;
         if (any) {
-            k_slot_to_flag<<<g, 256, 0, s->stream>>>(slot, n32, flag);
+            spt_launch_slot_to_flag(s->stream, slot, n32, flag);
             if (out_hit) e = cudaMemcpyAsync(out_hit, flag, n, cudaMemcpyDeviceToHost, s->stream);
         } else {
-            k_slot_to_id<<<g, 256, 0, s->stream>>>(slot, s->dev.prim_id, n32, ids);
+            spt_launch_slot_to_id(s->stream, slot, s->dev.prim_id, n32, ids);
             if (out_slot) e = cudaMemcpyAsync(out_slot, slot, n * 4, cudaMemcpyDeviceToHost, s->stream);
             if (e == cudaSuccess && out_id) e = cudaMemcpyAsync(out_id, ids, n * 4, cudaMemcpyDeviceToHost, s->stream);
             if (e == cudaSuccess && out_t) e = cudaMemcpyAsync(out_t, t, n * 4, cudaMemcpyDeviceToHost, s->stream);
@@ -401,11 +487,11 @@ static int trace_resident(SptScene *s, bool any, const float *rays_dev, uint64_t
     cw[0] = n32; cw[1] = 0;
     cudaMemcpyAsync(cnt, cw, 8, cudaMemcpyHostToDevice, s->stream);
     unsigned g = (unsigned)std::min<uint64_t>((n + 255) / 256, 65535);
-    k_split_rays<<<g, 256, 0, s->stream>>>(rays_dev, n32, ro, rd);
+    spt_launch_split_rays(s->stream, rays_dev, n32, ro, rd);
     uint32_t *slot = any ? slot_tmp : (slot_dev ? slot_dev : slot_tmp);
     int rc = trace_dev(s, any, ro, rd, n, slot, t_dev, cnt);
     if (rc != SPT_OK) return rc;
-    if (any && hit_dev) { k_slot_to_flag<<<g, 256, 0, s->stream>>>(slot, n32, hit_dev); CU(cudaStreamSynchronize(s->stream)); }
+    if (any && hit_dev) { spt_launch_slot_to_flag(s->stream, slot, n32, hit_dev); CU(cudaStreamSynchronize(s->stream)); }
     return SPT_OK;
 }
 int spt_trace_closest_dev(SptScene *s, const float *rays_dev, uint64_t n, uint32_t *out_slot_dev, float *out_t_dev) {
@@ -437,7 +523,7 @@ int spt_shade_samples(SptScene *s, const SptCameraDesc *cam, int32_t max_depth, 
     cudaMemsetAsync(s->counts, 0, nc * 4, s->stream);
     reset_class_stats(s);
     run_wave(s, cfg, src, s->counts);
-    k_gather_L<<<(unsigned)std::min<uint64_t>((n * NB + 255) / 256, 65535), 256, 0, s->stream>>>(s->wb.L, s->wb.cap, (uint32_t)n, dout);
+    spt_launch_gather_L(s->stream, s->wb.L, s->wb.cap, (uint32_t)n, dout);
     std::vector<uint32_t> hc(nc);
     cudaMemcpyAsync(hc.data(), s->counts, nc * 4, cudaMemcpyDeviceToHost, s->stream);
     cudaError_t e = cudaMemcpyAsync(out_L, dout, n * NB * sizeof(float), cudaMemcpyDeviceToHost, s->stream);
@@ -484,6 +570,7 @@ void spt_film_destroy(SptFilm *f) {
     cudaDeviceSynchronize();
     if (f->owned) cudaFree(f->pix);
     cudaFree(f->table);
+    if (f->split) cudaFree(f->split);
     delete f;
 }
 int spt_film_clear(SptFilm *f) {
@@ -496,13 +583,15 @@ float *spt_film_device_ptr(SptFilm *f) { return f ? f->pix : nullptr; }
 int spt_film_download(SptFilm *f, float *c, float *weight) {
     if (!f) return fail(SPT_ERR_ARG, "null film");
     size_t np = f->npix();
-    std::vector<float> host(np * (NB + 1));
+    if (!f->split) CU(cudaMalloc((void **)&f->split, np * (NB + 1) * sizeof(float)));
+    // [y][x][NB+1] -> {[y][x][NB], [y][x]} on the device, then one copy per host array (DMA at full
+    // rate when the caller's buffers are page-locked, spt_host_alloc)
     CU(cudaDeviceSynchronize());
-    CU(cudaMemcpy(host.data(), f->pix, host.size() * sizeof(float), cudaMemcpyDeviceToHost));
-    for (size_t p = 0; p < np; ++p) {
-        if (c) memcpy(c + p * NB, &host[p * (NB + 1)], NB * sizeof(float));
-        if (weight) weight[p] = host[p * (NB + 1) + NB];
-    }
+    unsigned g = (unsigned)std::min<size_t>((np * (NB + 1) + 255) / 256, (size_t)num_sms() * 16);
+    spt_launch_film_split((int)g, 0, f->pix, np, f->split, f->split + np * NB);
+    if (c) CU(cudaMemcpy(c, f->split, np * NB * sizeof(float), cudaMemcpyDeviceToHost));
+    if (weight) CU(cudaMemcpy(weight, f->split + np * NB, np * sizeof(float), cudaMemcpyDeviceToHost));
+    CU(cudaGetLastError());
     return SPT_OK;
 }
 
@@ -539,13 +628,13 @@ int spt_film_add_samples(SptFilm *f, const SptSpectralTables *tables, const floa
     DevMem m;
     SptSpectralTables *dt = m.upload(tables, 1);
     float2 *dxy = (float2 *)m.upload(image_xy, n * 2);
-    float *dl = m.upload(L, n * NB), *soa = m.alloc<float>(n * NB);
+    float *dl = m.upload(L, n * NB), *soa = m.alloc<float>(((n + 31) / 32 * 32) * NB);
     if (!dt || !dxy || !dl || !soa) { m.release(); return fail(SPT_ERR_CUDA, "device allocation failed"); }
     unsigned g = (unsigned)std::min<uint64_t>((n * NB + 255) / 256, 65535);
-    k_scatter_L<<<g, 256>>>(dl, (uint32_t)n, (uint32_t)n, soa);
+    spt_launch_scatter_L(0, dl, (uint32_t)n, (uint32_t)n, soa);
     FilmView fv; fv.d = f->desc; fv.pix = f->pix; fv.table = f->table;
     unsigned gw = (unsigned)std::min<uint64_t>((n * 32 + 255) / 256, (uint64_t)num_sms() * 16);
-    k_film_add<<<gw, 256>>>(fv, dt, dxy, soa, (uint32_t)n, (uint32_t)n, 1);
+    spt_launch_film_add((int)gw, 0, fv, dt, dxy, soa, (uint32_t)n, (uint32_t)n, 1);
     cudaError_t e = cudaDeviceSynchronize();
     m.release();
     if (e != cudaSuccess) return fail(SPT_ERR_CUDA, cudaGetErrorString(e));
@@ -577,7 +666,7 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
     uint64_t ntiles = (uint64_t)cfg.tilesX * cfg.tilesY;
     uint64_t local_tiles = ntiles > (uint64_t)cfg.rank ? (ntiles - cfg.rank + nranks - 1) / nranks : 0;
     uint64_t local_pixels = local_tiles * (uint64_t)cfg.tile * cfg.tile;
-    uint64_t wave_pixels = rp->wave_pixels > 0 ? (uint64_t)rp->wave_pixels : std::max<uint64_t>(1, (1u << 22) / (uint64_t)rp->spp);
+    uint64_t wave_pixels = rp->wave_pixels > 0 ? (uint64_t)rp->wave_pixels : std::max<uint64_t>(1, (1u << 25) / (uint64_t)rp->spp);   // 2^25 paths of state = 17 GB of the 180 GB
     wave_pixels = std::min<uint64_t>(wave_pixels, std::max<uint64_t>(local_pixels, 1));
     if (wave_pixels * rp->spp > (1ull << 27)) wave_pixels = (1ull << 27) / rp->spp;
     size_t n_waves = (size_t)((local_pixels + wave_pixels - 1) / wave_pixels);
@@ -597,7 +686,7 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
         cfg.n_samples = (uint32_t)(np * rp->spp);
         run_wave(s, cfg, src, s->counts + w * per_wave);
         unsigned gw = (unsigned)std::min<uint64_t>((np * 32 + 255) / 256, (uint64_t)num_sms() * 16);
-        k_film_add<<<gw, 256, 0, st>>>(fv, s->dev.tables, s->wb.img_xy, s->wb.L, s->wb.cap, cfg.n_samples, rp->spp);
+        spt_launch_film_add((int)gw, st, fv, s->dev.tables, s->wb.img_xy, s->wb.L, s->wb.cap, cfg.n_samples, rp->spp);
         s->mark(SPT_K_FILM);
     }
     CU(cudaEventRecord(s->ev1, st));

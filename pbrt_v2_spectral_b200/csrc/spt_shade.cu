@@ -1,0 +1,492 @@
+// spt_shade.cu — everything after a hit is known: hit compaction, K4 (miss), K5 shade, K6 accumulate,
+// K7 film. Compiled -fmad=false like the traversal: radiance is compared with the reference per sample at
+// 2e-4 relative, which holds only while the rounding sequence of the reference's (in places
+// ill-conditioned) formulas is reproduced; hit records are rebuilt without re-deciding the hit.
+#include "launch.h"
+#include "shade.cuh"
+#include "sampler.cuh"
+
+// ---- hit compaction --------------------------------------------------------------------------------
+// The persistent trace kernel finishes rays in no particular order, so the surviving paths are
+// filtered here, in queue order (one atomic per warp keeps runs of neighbouring samples together:
+// the SoA spectra of the shading kernels stay coalesced and the next bounce's rays stay coherent).
+// Hits go to hit_queue; escaped rays to miss_queue when one is given (camera rays under an
+// environment light).
+__global__ void __launch_bounds__(256) k_compact_hits(const uint32_t *__restrict__ queue, const uint32_t *__restrict__ count,
+                                                      const uint32_t *__restrict__ hit_slot, uint32_t *__restrict__ hit_queue,
+                                                      uint32_t *__restrict__ hit_count, uint32_t *__restrict__ miss_queue,
+                                                      uint32_t *__restrict__ miss_count) {
+    uint32_t n = *count;
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < ((n + 31u) & ~31u); q += gridDim.x * blockDim.x) {
+        bool active = q < n;
+        uint32_t i = active ? queue[q] : 0;
+        bool hit = active && hit_slot[i] != SPT_MISS;
+        queue_push(hit_queue, hit_count, hit, i);
+        if (miss_queue) queue_push(miss_queue, miss_count, active && !hit, i);
+    }
+}
+
+// ---- K4 (miss) -----------------------------------------------------------------------------------
+// SamplerRenderer::Li miss branch (samplerrenderer.cpp:239-243): sum of Light::Le over all lights for
+// camera rays that escape; only the infinite light is non-zero. Later bounces add Le only after a
+// specular bounce (path.cpp:106-108), which the lowered BxDFs never produce.
+__global__ void __launch_bounds__(128) k_miss_env(DevScene sc, WaveBuffers wb, const uint32_t *queue, const uint32_t *count) {
+    uint32_t n = *count;
+    const uint32_t cap = wb.cap;
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        uint32_t i = queue[q];
+        float4 d4 = wb.ray_d[i];
+        for (uint32_t l = 0; l < sc.n_lights; ++l)
+            if (sc.lights[l].type == SPT_LIGHT_INFINITE) {
+                float rgb[3];
+                infinite_le_rgb(sc, sc.lights[l], V(d4.x, d4.y, d4.z), rgb);
+                IllumCoefs k = illum_coefs(rgb);
+                for (int c = 0; c < NB; ++c) wb.L[band_off(i, c)] += illum_band(*sc.tables, k, c);
+            }
+    }
+}
+
+// ---- K5 ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_shade(DevScene sc, RenderCfg cfg, SampleSource src, WaveBuffers wb, int bounce,
+                                               const uint32_t *queue, const uint32_t *count,
+                                               uint32_t *shadow_count, uint32_t *mis_count) {
+    uint32_t n = *count;
+    const uint32_t cap = wb.cap;
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < ((n + 31u) & ~31u); q += gridDim.x * blockDim.x) {
+        bool active = q < n;
+        uint32_t i = active ? queue[q] : 0;
+        bool pushShadow = false, pushMis = false;
+        if (active) {
+            uint32_t slot = wb.hit_slot[i];
+            float4 o4 = wb.ray_o[i], d4 = wb.ray_d[i];
+            Ray ray;
+            ray.o = V(o4.x, o4.y, o4.z); ray.d = V(d4.x, d4.y, d4.z); ray.mint = o4.w; ray.maxt = SPT_INF;
+            uint32_t flags = 0;
+            {
+                Hit hit;
+                shape_record(sc, sc.prim_kind[slot], sc.prim_flags[slot], sc.prim_data[slot], ray, wb.hit_t[i], &hit);
+                // emitted light at the first vertex (path.cpp:55-56; Intersection::Le, intersection.cpp:53-56)
+                if (bounce == 0) {
+                    int li = sc.prim_light[slot];
+                    if (li >= 0 && dot(hit.nn, vneg(ray.d)) > 0.f)
+                        for (int c = 0; c < NB; ++c) wb.L[band_off(i, c)] = sc.lights[li].spectrum[c];
+                }
+                Bsdf bsdf;
+                make_bsdf(sc, slot, hit, &bsdf);
+                v3 p = hit.p, n_s = bsdf.nn, woW = vneg(ray.d);
+                v3 wo = w2l(bsdf, woW);
+                float eps = hit.rayEpsilon;
+                uint32_t s_idx = src.smp ? 0u : (i % (uint32_t)cfg.spp);
+                uint32_t pk = 0;
+                if (!src.smp) {
+                    int px, py;
+                    wave_pixel(cfg, cfg.pixel_base + i / (uint32_t)cfg.spp, &px, &py);
+                    pk = pixel_key(src.seed, pix_key(px, py));
+                }
+                float u[10], rr;
+                bounce_dims(src, i, pk, s_idx, bounce, sc.n_lights > 0, u, &rr);
+
+                float4 r0 = make_float4(0, 0, 0, 0), r1 = r0, r2 = r0, r3 = r0, r4 = r0, r5 = r0;
+                float4 g1 = r0, g2 = r0, g3 = r0;
+                int lightIdx = 0;
+                if (bsdf.orenNayar) flags |= RF_ON;
+                if (sc.n_lights > 0) {
+                    // UniformSampleOneLight (integrator.cpp:74-106) + EstimateDirect (:109-166)
+                    int nLights = (int)sc.n_lights;
+                    lightIdx = (int)floorf(u[0] * nLights);
+                    if (nLights - 1 < lightIdx) lightIdx = nLights - 1;
+                    LightSampleResult lr;
+                    light_sample(sc, lightIdx, p, u[1], u[2], u[3], &lr);
+                    if (lr.pdf > 0.f && !lr.black) {
+                        DirTerms t;
+                        v3 wi = w2l(bsdf, lr.wi);
+                        float bsdfPdf;
+                        bsdf_terms(bsdf, woW, lr.wi, wo, wi, &t, &bsdfPdf);
+                        if (t.reflect) {
+                            float sL;
+                            if (lr.delta) sL = (absdot(lr.wi, n_s) / lr.pdf);
+                            else {
+                                float weight = power_heuristic(lr.pdf, bsdfPdf);
+                                sL = (absdot(lr.wi, n_s) * weight / lr.pdf);
+                            }
+                            flags |= RF_L | (lr.delta ? RF_LDELTA : 0) | RF_L_REFL | (t.mf ? RF_L_MF : 0);
+                            r0 = make_float4(t.a0, t.a1, t.a2, t.a3);
+                            r3.x = sL;
+                            r5 = make_float4(lr.aux[0], lr.aux[1], lr.aux[2], 0.f);
+                            g1 = make_float4(lr.shadow_d.x, lr.shadow_d.y, lr.shadow_d.z, lr.shadow_maxt);
+                            pushShadow = true;
+                        }
+                    }
+                    if (!lr.delta) {
+                        v3 wiW; float bsdfPdf; DirTerms t;
+                        bsdf_sample(bsdf, woW, wo, u[6], u[4], u[5], &wiW, &bsdfPdf, &t);
+                        if (bsdfPdf > 0.f && t.reflect) {
+                            float lightPdf = light_pdf(sc, lightIdx, p, wiW);
+                            if (lightPdf != 0.f) {
+                                float weight = power_heuristic(bsdfPdf, lightPdf);
+                                flags |= RF_B | RF_B_REFL | (t.mf ? RF_B_MF : 0);
+                                r1 = make_float4(t.a0, t.a1, t.a2, t.a3);
+                                r3.y = absdot(wiW, n_s); r3.z = weight; r3.w = bsdfPdf;
+                                g2 = make_float4(wiW.x, wiW.y, wiW.z, SPT_INF);
+                                pushMis = true;
+                            }
+                        }
+                    }
+                }
+                {   // continuation direction (path.cpp:75-92)
+                    v3 wiW; float pdf; DirTerms t;
+                    bsdf_sample(bsdf, woW, wo, u[9], u[7], u[8], &wiW, &pdf, &t);
+                    if (pdf != 0.f) {
+                        flags |= RF_P | (t.reflect ? RF_P_REFL : 0) | (t.mf ? RF_P_MF : 0);
+                        r2 = make_float4(t.a0, t.a1, t.a2, t.a3);
+                        r4.x = absdot(wiW, n_s); r4.y = pdf;
+                        g3 = make_float4(wiW.x, wiW.y, wiW.z, 0.f);
+                    }
+                    r4.z = rr;
+                }
+                wb.g0[i] = make_float4(p.x, p.y, p.z, eps);
+                wb.g1[i] = g1; wb.g2[i] = g2; wb.g3[i] = g3;
+                wb.r0[i] = r0; wb.r1[i] = r1; wb.r2[i] = r2; wb.r3[i] = r3; wb.r4[i] = r4; wb.r5[i] = r5;
+                wb.r6[i] = make_uint4(flags, (uint32_t)sc.prim_material[slot], (uint32_t)lightIdx, 0);
+            }
+        }
+        queue_push(wb.shadowQ, shadow_count, pushShadow, i);
+        queue_push(wb.misQ, mis_count, pushMis, i);
+    }
+}
+
+// ---- K6 ----------------------------------------------------------------------------------------
+// Per-direction BSDF value rebuilt per band from wavelength-independent coefficients:
+//   matte / plastic:  f[c] = spec0[c]*u0 + spec1[c]*u1     (Lambert/Oren-Nayar + Blinn microfacet x dielectric Fresnel)
+//   metal:            f[c] = w * FrCond(cosH, eta[c], k[c])
+// The scalar factors (D*G*F/(4 cosI cosO), |cos|*weight/pdf, ...) are folded once per vertex instead of
+// once per band as the reference's Spectrum arithmetic does; this reassociation moves results by
+// rounding only (tests compare radiance at 2e-4 relative).
+struct DirCoef { float u0, u1, w, cosH; };
+__device__ __forceinline__ DirCoef dir_coef(int mtype, bool on, bool reflect, bool mf, float4 a) {
+    DirCoef d; d.u0 = d.u1 = d.w = 0.f; d.cosH = 1.f;
+    if (!reflect) return d;
+    if (mtype == SPT_MAT_MATTE) d.u0 = on ? INV_PI_F * a.x : INV_PI_F;
+    else if (mtype == SPT_MAT_PLASTIC) { d.u0 = INV_PI_F; if (mf) d.u1 = a.x * a.y * a.z / a.w; }
+    else if (mf) { d.w = a.x * a.y / a.w; d.cosH = a.z; }
+    return d;
+}
+// FrCond (reflection.cpp:63-71) with the two quotients combined into one division
+__device__ __forceinline__ float fr_cond_fast(float cosi, float c2, float eta, float k) {
+    float A = fmaf(eta, eta, k * k);
+    float e2 = 2.f * eta * cosi;
+    float Ac2 = A * c2;
+    float n1 = Ac2 - e2 + 1.f, d1 = Ac2 + e2 + 1.f;
+    float n2 = A - e2 + c2, d2 = A + e2 + c2;
+    return 0.5f * __fdividef(fmaf(n1, d2, n2 * d1), d1 * d2);
+}
+// Radiance of a light direction, per band: kind 0 none, 1 the light's table spectrum, 2 RGB illuminant
+// (three basis spectra, coefficients k0..k2)
+struct LightBand { int kind; IllumCoefs k; };
+
+// Two phases per batch of 32 path vertices, one batch per warp:
+//   A  lane = vertex: everything wavelength-independent (which terms survive the shadow / MIS rays,
+//      the folded scalar factors), staged in shared memory as 7 x float4 per vertex;
+//   B  lane = band: for each vertex of the batch the warp reads the staged scalars (broadcast),
+//      the material row, the light spectrum and the path's T and L rows - every access a
+//      coalesced 128-byte line - and updates L += T*Ld, T *= f|cos|/pdf. y(T) is a warp sum, the
+//      Russian-roulette decision and the 1/q scaling are warp-uniform, so T is written once.
+//   C  lane = vertex again: surviving paths write their next ray and join the next path queue.
+#define ACC_WARPS 4
+#define ACC_GROUP 4          // vertices whose T/L rows are in flight together in phase B
+__global__ void __launch_bounds__(32 * ACC_WARPS) k_accumulate(DevScene sc, RenderCfg cfg, WaveBuffers wb, int bounce,
+                                                               const uint32_t *__restrict__ queue, const uint32_t *__restrict__ count,
+                                                               uint32_t *__restrict__ next_queue, uint32_t *__restrict__ next_count) {
+    __shared__ float4 stage_all[ACC_WARPS][32][7];
+    const uint32_t n = *count;
+    const SptSpectralTables &tb = *sc.tables;
+    float *__restrict__ Tg = wb.T;
+    float *__restrict__ Lg = wb.L;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4 (*stage)[7] = stage_all[warp];
+    const unsigned FULL = 0xffffffffu;
+    const float cieY = tb.cie_y[lane];
+    const float nL = (float)sc.n_lights;
+    const uint32_t nwarps = gridDim.x * ACC_WARPS;
+    for (uint32_t base = (blockIdx.x * ACC_WARPS + warp) * 32u; base < n; base += nwarps * 32u) {
+        // ---- phase A
+        const uint32_t q = base + lane;
+        const bool active = q < n;
+        const uint32_t i = active ? queue[q] : 0;
+        float4 g0 = make_float4(0, 0, 0, 0);
+        if (active) {
+            uint4 r6 = wb.r6[i];
+            uint32_t flags = r6.x;
+            const int mtype = sc.materials[r6.y].type;
+            int lightIdx = (int)r6.z;
+            bool on = (flags & RF_ON) != 0;
+            float4 r3 = wb.r3[i], r4 = wb.r4[i];
+            g0 = wb.g0[i];
+            // --- light-sample term (integrator.cpp:122-137): visible iff the shadow ray found nothing
+            DirCoef cL = dir_coef(mtype, on, false, false, make_float4(0, 0, 0, 0)), cB = cL, cP = cL;
+            LightBand lbL, lbB; lbL.kind = 0; lbB.kind = 0;
+            lbL.k.k0 = lbL.k.k1 = lbL.k.k2 = 0.f; lbL.k.b1 = lbL.k.b2 = 0; lbB.k = lbL.k;
+            float sL = 0.f, sB = 0.f, sP = 0.f;
+            if ((flags & RF_L) && wb.sh_slot[i] == SPT_MISS) {
+                float4 r5 = wb.r5[i];
+                cL = dir_coef(mtype, on, true, (flags & RF_L_MF) != 0, wb.r0[i]);
+                const SptLight &l = sc.lights[lightIdx];
+                sL = r3.x;
+                if (l.type == SPT_LIGHT_INFINITE) { float rgb[3] = { r5.x, r5.y, r5.z }; lbL.kind = 2; lbL.k = illum_coefs(rgb); }
+                else { lbL.kind = 1; if (l.type == SPT_LIGHT_POINT) sL = sL / r5.x; }
+            }
+            // --- BSDF-sample term (integrator.cpp:139-163): radiance from what the MIS ray found
+            if (flags & RF_B) {
+                float4 g2 = wb.g2[i];
+                uint32_t ms = wb.mis_slot[i];
+                const SptLight &l = sc.lights[lightIdx];
+                v3 wi = V(g2.x, g2.y, g2.z);
+                if (ms != SPT_MISS) {
+                    if (sc.prim_light[ms] == lightIdx) {
+                        Ray ray; ray.o = V(g0.x, g0.y, g0.z); ray.d = wi; ray.mint = g0.w; ray.maxt = SPT_INF;
+                        Hit h;
+                        shape_record(sc, sc.prim_kind[ms], sc.prim_flags[ms], sc.prim_data[ms], ray, wb.mis_t[i], &h);
+                        if (dot(h.nn, vneg(wi)) > 0.f) lbB.kind = 1;
+                    }
+                } else if (l.type == SPT_LIGHT_INFINITE) {
+                    float rgb[3];
+                    infinite_le_rgb(sc, l, wi, rgb);
+                    lbB.kind = 2; lbB.k = illum_coefs(rgb);
+                }
+                if (lbB.kind) { cB = dir_coef(mtype, on, true, (flags & RF_B_MF) != 0, wb.r1[i]); sB = r3.y * r3.z / r3.w; }
+            }
+            bool haveP = (flags & RF_P) != 0;
+            if (haveP) { cP = dir_coef(mtype, on, (flags & RF_P_REFL) != 0, (flags & RF_P_MF) != 0, wb.r2[i]); sP = r4.x / r4.y; }
+            sL *= nL; sB *= nL;
+            stage[lane][0] = make_float4(cL.u0, cL.u1, cL.w, cL.cosH);
+            stage[lane][1] = make_float4(cB.u0, cB.u1, cB.w, cB.cosH);
+            stage[lane][2] = make_float4(cP.u0, cP.u1, cP.w, cP.cosH);
+            stage[lane][3] = make_float4(sL, sB, sP, r4.z);
+            stage[lane][4] = make_float4(lbL.k.k0, lbL.k.k1, lbL.k.k2, __uint_as_float((uint32_t)lbL.kind | (uint32_t)lbL.k.b1 << 4 | (uint32_t)lbL.k.b2 << 8));
+            stage[lane][5] = make_float4(lbB.k.k0, lbB.k.k1, lbB.k.k2, __uint_as_float((uint32_t)lbB.kind | (uint32_t)lbB.k.b1 << 4 | (uint32_t)lbB.k.b2 << 8));
+            stage[lane][6] = make_float4(__uint_as_float(i), __uint_as_float(r6.y), __uint_as_float((uint32_t)lightIdx),
+                                         __uint_as_float((haveP ? 1u : 0u) | (mtype == SPT_MAT_METAL ? 2u : 0u)));
+        }
+        __syncwarp();
+        // ---- phase B
+        const uint32_t cnt = min(32u, n - base);
+        uint32_t aliveMask = 0;
+        for (uint32_t v0 = 0; v0 < cnt; v0 += ACC_GROUP) {
+            float Tv[ACC_GROUP], Lv[ACC_GROUP];
+            uint32_t iv[ACC_GROUP];
+#pragma unroll
+            for (int k = 0; k < ACC_GROUP; ++k) {
+                uint32_t v = min(v0 + k, cnt - 1);                       // clamped: tail entries repeat the last vertex (not stored)
+                iv[k] = __float_as_uint(stage[v][6].x);
+                size_t off = band_off(iv[k], lane);
+                Tv[k] = bounce == 0 ? 1.f : Tg[off];
+                Lv[k] = Lg[off];
+            }
+#pragma unroll
+            for (int k = 0; k < ACC_GROUP; ++k) {
+                const uint32_t v = v0 + k;
+                if (v >= cnt) break;
+                const float4 fL4 = stage[v][0], fB4 = stage[v][1], fP4 = stage[v][2], sc4 = stage[v][3];
+                const float4 lL4 = stage[v][4], lB4 = stage[v][5], id4 = stage[v][6];
+                const SptMaterial &m = sc.materials[__float_as_uint(id4.y)];
+                const SptLight &lt = sc.lights[__float_as_uint(id4.z)];
+                const uint32_t misc = __float_as_uint(id4.w);
+                const bool haveP = misc & 1u, metal = (misc & 2u) != 0;
+                const float s0 = __ldg(m.spec0 + lane), s1 = __ldg(m.spec1 + lane);
+                float fL, fB, fP;
+                if (metal) {
+                    fL = fL4.z != 0.f ? fL4.z * fr_cond_fast(fL4.w, fL4.w * fL4.w, s0, s1) : 0.f;
+                    fB = fB4.z != 0.f ? fB4.z * fr_cond_fast(fB4.w, fB4.w * fB4.w, s0, s1) : 0.f;
+                    fP = fP4.z != 0.f ? fP4.z * fr_cond_fast(fP4.w, fP4.w * fP4.w, s0, s1) : 0.f;
+                } else {
+                    fL = fmaf(s0, fL4.x, s1 * fL4.y);
+                    fB = fmaf(s0, fB4.x, s1 * fB4.y);
+                    fP = fmaf(s0, fP4.x, s1 * fP4.y);
+                }
+                const uint32_t kL = __float_as_uint(lL4.w), kB = __float_as_uint(lB4.w);
+                float LcL = 0.f, LcB = 0.f;
+                if ((kL & 15u) == 1u) LcL = __ldg(lt.spectrum + lane);
+                else if ((kL & 15u) == 2u) { IllumCoefs kk; kk.k0 = lL4.x; kk.k1 = lL4.y; kk.k2 = lL4.z; kk.b1 = (kL >> 4) & 15; kk.b2 = (kL >> 8) & 15; LcL = illum_band(tb, kk, lane); }
+                if ((kB & 15u) == 1u) LcB = __ldg(lt.spectrum + lane);
+                else if ((kB & 15u) == 2u) { IllumCoefs kk; kk.k0 = lB4.x; kk.k1 = lB4.y; kk.k2 = lB4.z; kk.b1 = (kB >> 4) & 15; kk.b2 = (kB >> 8) & 15; LcB = illum_band(tb, kk, lane); }
+                // L += T * Ld * nLights ; T *= f |cos| / pdf   (integrator.cpp:122-163, path.cpp:88-90)
+                const float Ld = fL * LcL * sc4.x + fB * LcB * sc4.y;
+                const size_t off = band_off(iv[k], lane);
+                Lg[off] = fmaf(Tv[k], Ld, Lv[k]);
+                float Tn = Tv[k] * (fP * sc4.z);
+                const bool fBlack = !__any_sync(FULL, fP != 0.f);
+                // path.cpp:88-104
+                bool alive = false;
+                if (haveP && !fBlack) {
+                    alive = true;
+                    if (bounce > 3) {
+                        float yy = cieY * Tn;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) yy += __shfl_xor_sync(FULL, yy, o);
+                        float continueProbability = stdminf(.5f, yy / tb.yint);
+                        if (sc4.w > continueProbability) alive = false;
+                        else if (bounce != cfg.max_depth) Tn *= 1.f / continueProbability;
+                    }
+                    if (bounce == cfg.max_depth) alive = false;
+                }
+                if (alive) { Tg[off] = Tn; aliveMask |= 1u << v; }
+            }
+        }
+        // ---- phase C
+        bool alive = active && ((aliveMask >> lane) & 1u);
+        if (alive) {
+            float4 g3 = wb.g3[i];
+            wb.ray_o[i] = g0;
+            wb.ray_d[i] = make_float4(g3.x, g3.y, g3.z, SPT_INF);
+        }
+        queue_push(next_queue, next_count, alive, i);
+        __syncwarp();
+    }
+}
+
+// ---- K7 ----------------------------------------------------------------------------------------
+// Radiance guards (samplerrenderer.cpp:119-133) + SpectralImageFilm::AddSample
+// (spectralImage.cpp:77-152). One warp per sampler pixel: lanes stride over the pixel's samples;
+// contributions whose footprint is exactly that pixel are reduced across the warp with shuffles and
+// flushed with one atomic per band; anything else (wide filters, samples rounding onto a pixel
+// edge) goes straight to global atomics.
+__global__ void __launch_bounds__(256) k_film_add(FilmView film, const SptSpectralTables *tables, const float2 *img_xy,
+                                                  const float *L, uint32_t cap, uint32_t n_samples, int spp) {
+    const SptSpectralTables &tb = *tables;
+    int lane = threadIdx.x & 31;
+    uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    uint32_t npix = (n_samples + spp - 1) / spp;
+    const SptFilmDesc &fd = film.d;
+    for (uint32_t pixel = warp; pixel < npix; pixel += nwarps) {
+        // the pixel this warp reduces into: the one the first sample of the group falls in
+        float2 xy0 = img_xy[(size_t)pixel * spp];
+        int mainx = (int)floorf(xy0.x), mainy = (int)floorf(xy0.y);
+        bool mainInside = mainx >= fd.x_pixel_start && mainx < fd.x_pixel_start + fd.x_pixel_count &&
+                          mainy >= fd.y_pixel_start && mainy < fd.y_pixel_start + fd.y_pixel_count;
+        float wsum = 0.f;
+        for (int s0 = 0; s0 < spp; s0 += 32) {
+            int s = s0 + lane;
+            uint32_t i = pixel * spp + s;
+            bool have = s < spp && i < n_samples;
+            float2 xy = have ? img_xy[i] : make_float2(-1e30f, -1e30f);
+            have = have && xy.x > -1e29f;
+            bool bad = false;
+            float y = 0.f;
+            if (have) {
+                for (int c = 0; c < NB; ++c) {
+                    float v = L[band_off(i, c)];
+                    if (isnan(v)) bad = true;
+                    y += tb.cie_y[c] * v;
+                }
+                y = y / tb.yint;
+                if ((double)y < -1e-5 || isinf(y)) bad = true;
+            }
+            int x0 = 0, x1 = -1, y0 = 0, y1 = -1;
+            float dimageX = xy.x - 0.5f, dimageY = xy.y - 0.5f;
+            if (have) {
+                x0 = (int)ceilf(dimageX - fd.filter_xwidth); x1 = (int)floorf(dimageX + fd.filter_xwidth);
+                y0 = (int)ceilf(dimageY - fd.filter_ywidth); y1 = (int)floorf(dimageY + fd.filter_ywidth);
+                x0 = max(x0, fd.x_pixel_start); x1 = min(x1, fd.x_pixel_start + fd.x_pixel_count - 1);
+                y0 = max(y0, fd.y_pixel_start); y1 = min(y1, fd.y_pixel_start + fd.y_pixel_count - 1);
+            }
+            bool any = have && (x1 - x0) >= 0 && (y1 - y0) >= 0;
+            bool fast = any && mainInside && x0 == x1 && y0 == y1 && x0 == mainx && y0 == mainy;
+            float wfast = 0.f;
+            if (fast) {
+                float fx = fabsf((x0 - dimageX) * fd.filter_inv_xwidth * 16);
+                float fy = fabsf((y0 - dimageY) * fd.filter_inv_ywidth * 16);
+                int ix = min((int)floorf(fx), 15), iy = min((int)floorf(fy), 15);
+                wfast = film.table[iy * 16 + ix];
+            }
+            if (any && !fast) {
+                for (int yy = y0; yy <= y1; ++yy) {
+                    float fy = fabsf((yy - dimageY) * fd.filter_inv_ywidth * 16);
+                    int iy = min((int)floorf(fy), 15);
+                    for (int xx = x0; xx <= x1; ++xx) {
+                        float fx = fabsf((xx - dimageX) * fd.filter_inv_xwidth * 16);
+                        int ix = min((int)floorf(fx), 15);
+                        float wt = film.table[iy * 16 + ix];
+                        float *dst = film.pix + ((size_t)(yy - fd.y_pixel_start) * fd.x_pixel_count + (xx - fd.x_pixel_start)) * (NB + 1);
+                        for (int c = 0; c < NB; ++c) atomicAdd(dst + c, wt * (bad ? 0.f : L[band_off(i, c)]));
+                        atomicAdd(dst + NB, wt);
+                    }
+                }
+            }
+            // warp reduction of the fast-path contributions, band by band (fixed shuffle tree)
+            float *dst = film.pix + ((size_t)(mainy - fd.y_pixel_start) * fd.x_pixel_count + (mainx - fd.x_pixel_start)) * (NB + 1);
+            if (__any_sync(0xffffffffu, fast)) {
+                for (int c = 0; c < NB; ++c) {
+                    float v = (fast && !bad) ? wfast * L[band_off(i, c)] : 0.f;
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+                    if (lane == 0) atomicAdd(dst + c, v);
+                }
+                float w = fast ? wfast : 0.f;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) w += __shfl_xor_sync(0xffffffffu, w, off);
+                wsum += w;
+            }
+        }
+        if (lane == 0 && wsum != 0.f && mainInside) {
+            float *dst = film.pix + ((size_t)(mainy - fd.y_pixel_start) * fd.x_pixel_count + (mainx - fd.x_pixel_start)) * (NB + 1);
+            atomicAdd(dst + NB, wsum);
+        }
+    }
+}
+
+// film [pixel][NB+1] -> c [pixel][NB] and weight [pixel] (spt_film_download)
+__global__ void k_film_split(const float *pix, size_t npix, float *c, float *w) {
+    size_t total = npix * (NB + 1);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        size_t p = i / (NB + 1);
+        int b = (int)(i % (NB + 1));
+        float v = pix[i];
+        if (b < NB) c[p * NB + b] = v; else w[p] = v;
+    }
+}
+// SoA [NB][cap] -> AoS [n][NB] (spt_shade_samples output)
+__global__ void k_gather_L(const float *L, uint32_t cap, uint32_t n, float *out) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n * NB; i += gridDim.x * blockDim.x) {
+        uint32_t s = i / NB, c = i % NB;
+        out[i] = L[band_off(s, c)];
+    }
+}
+// AoS [n][NB] -> SoA, for spt_film_add_samples
+__global__ void k_scatter_L(const float *in, uint32_t cap, uint32_t n, float *L) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n * NB; i += gridDim.x * blockDim.x) {
+        uint32_t s = i / NB, c = i % NB;
+        L[band_off(s, c)] = in[i];
+    }
+}
+
+// ---- launchers -------------------------------------------------------------------------------------
+static inline unsigned grid1d(uint64_t n, int per, unsigned cap) { uint64_t g = (n + per - 1) / per; return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g)); }
+void spt_launch_compact_hits(int grid, cudaStream_t st, const uint32_t *queue, const uint32_t *count, const uint32_t *hit_slot,
+                             uint32_t *hit_queue, uint32_t *hit_count, uint32_t *miss_queue, uint32_t *miss_count) {
+    k_compact_hits<<<grid, 256, 0, st>>>(queue, count, hit_slot, hit_queue, hit_count, miss_queue, miss_count);
+}
+void spt_launch_miss_env(int grid, cudaStream_t st, const DevScene &sc, const WaveBuffers &wb, const uint32_t *queue, const uint32_t *count) {
+    k_miss_env<<<grid, 128, 0, st>>>(sc, wb, queue, count);
+}
+void spt_launch_shade(int grid, cudaStream_t st, const DevScene &sc, const RenderCfg &cfg, const SampleSource &src, const WaveBuffers &wb,
+                      int bounce, const uint32_t *queue, const uint32_t *count, uint32_t *shadow_count, uint32_t *mis_count) {
+    k_shade<<<grid, 128, 0, st>>>(sc, cfg, src, wb, bounce, queue, count, shadow_count, mis_count);
+}
+void spt_launch_accumulate(int grid, cudaStream_t st, const DevScene &sc, const RenderCfg &cfg, const WaveBuffers &wb, int bounce,
+                           const uint32_t *queue, const uint32_t *count, uint32_t *next_queue, uint32_t *next_count) {
+    k_accumulate<<<grid, 128, 0, st>>>(sc, cfg, wb, bounce, queue, count, next_queue, next_count);
+}
+void spt_launch_film_add(int grid, cudaStream_t st, const FilmView &film, const SptSpectralTables *tables, const float2 *img_xy,
+                         const float *L, uint32_t cap, uint32_t n_samples, int spp) {
+    k_film_add<<<grid, 256, 0, st>>>(film, tables, img_xy, L, cap, n_samples, spp);
+}
+void spt_launch_film_split(int grid, cudaStream_t st, const float *pix, size_t npix, float *c, float *w) {
+    k_film_split<<<grid, 256, 0, st>>>(pix, npix, c, w);
+}
+void spt_launch_gather_L(cudaStream_t st, const float *L, uint32_t cap, uint32_t n, float *out) {
+    k_gather_L<<<grid1d((uint64_t)n * NB, 256, 65535), 256, 0, st>>>(L, cap, n, out);
+}
+void spt_launch_scatter_L(cudaStream_t st, const float *in, uint32_t cap, uint32_t n, float *L) {
+    k_scatter_L<<<grid1d((uint64_t)n * NB, 256, 65535), 256, 0, st>>>(in, cap, n, L);
+}

@@ -1,0 +1,13 @@
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+struct TraceArgs {
+    const uint32_t *queue;      // ray indices, or NULL for 0..n-1
+    const uint32_t *count;      // number of rays (device word)
+    uint32_t *work;             // next unclaimed queue position (device word, zeroed)
+    const float4 *ro, *rd;      // {o, mint}, {d, maxt}
+    uint32_t *out_slot;         // BVH slot of the accepted primitive, SPT_MISS if none
+    float *out_t;               // closest hit: ray.maxt after the traversal (NULL for any-hit)
+    uint32_t leaf_wait;         // two-phase variant: leave the node phase when this few lanes still search
+};
+

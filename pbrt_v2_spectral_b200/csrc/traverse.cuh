@@ -38,15 +38,9 @@ __device__ __forceinline__ void tri_uvs(const DevScene &sc, int flags, const int
     }
 }
 
-// Full Triangle::Intersect with DifferentialGeometry, given triangle number `tri` (index path).
-__device__ inline bool tri_intersect_full(const DevScene &sc, uint32_t tri, int flags, const Ray &ray, Hit *hit) {
-    const int32_t *vi = sc.tri_vidx + 3 * (size_t)tri;
-    int32_t i0 = vi[0], i1 = vi[1], i2 = vi[2];
-    v3 p1 = V(sc.P[3 * (size_t)i0], sc.P[3 * (size_t)i0 + 1], sc.P[3 * (size_t)i0 + 2]);
-    v3 p2 = V(sc.P[3 * (size_t)i1], sc.P[3 * (size_t)i1 + 1], sc.P[3 * (size_t)i1 + 2]);
-    v3 p3 = V(sc.P[3 * (size_t)i2], sc.P[3 * (size_t)i2 + 1], sc.P[3 * (size_t)i2 + 2]);
-    float t, b1, b2;
-    if (!tri_test(p1, p2, p3, ray, &t, &b1, &b2)) return false;
+// DifferentialGeometry of a triangle hit (trianglemesh.cpp:146-200) for barycentrics b1,b2 and distance t.
+__device__ inline void tri_fill(const DevScene &sc, int flags, const int32_t *vi, v3 p1, v3 p2, v3 p3, const Ray &ray,
+                                float t, float b1, float b2, Hit *hit) {
     v3 e1 = vsub(p2, p1), e2 = vsub(p3, p1);
     v3 dpdu, dpdv;
     float uvs[3][2];
@@ -68,7 +62,38 @@ __device__ inline bool tri_intersect_full(const DevScene &sc, uint32_t tri, int 
     dg_init(hit, ray_at(ray, t), dpdu, dpdv, tu, tv, flags);
     hit->t = t;
     hit->rayEpsilon = 1e-3f * t;
+}
+__device__ __forceinline__ void tri_load(const DevScene &sc, uint32_t tri, const int32_t **vi, v3 *p1, v3 *p2, v3 *p3) {
+    const int32_t *v = sc.tri_vidx + 3 * (size_t)tri;
+    int32_t i0 = v[0], i1 = v[1], i2 = v[2];
+    *vi = v;
+    *p1 = V(sc.P[3 * (size_t)i0], sc.P[3 * (size_t)i0 + 1], sc.P[3 * (size_t)i0 + 2]);
+    *p2 = V(sc.P[3 * (size_t)i1], sc.P[3 * (size_t)i1 + 1], sc.P[3 * (size_t)i1 + 2]);
+    *p3 = V(sc.P[3 * (size_t)i2], sc.P[3 * (size_t)i2 + 1], sc.P[3 * (size_t)i2 + 2]);
+}
+// Full Triangle::Intersect with DifferentialGeometry, given triangle number `tri` (index path).
+__device__ inline bool tri_intersect_full(const DevScene &sc, uint32_t tri, int flags, const Ray &ray, Hit *hit) {
+    const int32_t *vi; v3 p1, p2, p3;
+    tri_load(sc, tri, &vi, &p1, &p2, &p3);
+    float t, b1, b2;
+    if (!tri_test(p1, p2, p3, ray, &t, &b1, &b2)) return false;
+    tri_fill(sc, flags, vi, p1, p2, p3, ray, t, b1, b2, hit);
     return true;
+}
+// The hit record of a triangle the traversal has ALREADY accepted at distance t: same arithmetic as
+// Triangle::Intersect for b1,b2, none of its rejection tests (they were decided, in the reference's
+// rounding, by the traversal kernel; re-deciding them under FMA contraction could disagree).
+__device__ inline void tri_record(const DevScene &sc, uint32_t tri, int flags, const Ray &ray, float t, Hit *hit) {
+    const int32_t *vi; v3 p1, p2, p3;
+    tri_load(sc, tri, &vi, &p1, &p2, &p3);
+    v3 e1 = vsub(p2, p1), e2 = vsub(p3, p1);
+    v3 s1 = cross(ray.d, e2);
+    float invDivisor = 1.f / dot(s1, e1);
+    v3 d = vsub(ray.o, p1);
+    float b1 = dot(d, s1) * invDivisor;
+    v3 s2 = cross(d, e1);
+    float b2 = dot(ray.d, s2) * invDivisor;
+    tri_fill(sc, flags, vi, p1, p2, p3, ray, t, b1, b2, hit);
 }
 
 __device__ __forceinline__ bool quadratic(float A, float B, float C, float *t0, float *t1) {   // pbrt.h:297-311
@@ -84,6 +109,7 @@ __device__ __forceinline__ bool quadratic(float A, float B, float C, float *t0, 
     return true;
 }
 
+__device__ inline void sphere_fill(const SptQuadric &q, const SptXform &xf, int flags, v3 phit, float phi, float thit, Hit *hit);
 // Sphere (src/shapes/sphere.cpp:50-149, :152-201). hit == NULL: accept test only.
 __device__ inline bool sphere_intersect(const DevScene &sc, const SptQuadric &q, int flags, const Ray &r,
                                         float *tout, Hit *hit) {
@@ -119,6 +145,12 @@ __device__ inline bool sphere_intersect(const DevScene &sc, const SptQuadric &q,
     }
     *tout = thit;
     if (!hit) return true;
+    sphere_fill(q, xf, flags, phit, phi, thit, hit);
+    return true;
+}
+// DifferentialGeometry of a sphere hit at object-space point phit (sphere.cpp:105-149)
+__device__ inline void sphere_fill(const SptQuadric &q, const SptXform &xf, int flags, v3 phit, float phi, float thit, Hit *hit) {
+    float radius = q.radius, phiMax = q.phiMax;
     float u = phi / phiMax;
     float theta = acosf(clampf(phit.z / radius, -1.f, 1.f));
     float v = (theta - q.thetaMin) / (q.thetaMax - q.thetaMin);
@@ -131,9 +163,21 @@ __device__ inline bool sphere_intersect(const DevScene &sc, const SptQuadric &q,
     dg_init(hit, xf_point(xf.m, phit), xf_vector(xf.m, dpdu), xf_vector(xf.m, dpdv), u, v, flags);
     hit->t = thit;
     hit->rayEpsilon = 5e-4f * thit;
-    return true;
+}
+// The hit record of a sphere the traversal accepted at distance t (no re-decision, see tri_record)
+__device__ inline void sphere_record(const DevScene &sc, const SptQuadric &q, int flags, const Ray &r, float t, Hit *hit) {
+    const SptXform &xf = sc.xforms[q.xform];
+    Ray ray = r;
+    ray.o = xf_point(xf.minv, r.o);
+    ray.d = xf_vector(xf.minv, r.d);
+    v3 phit = ray_at(ray, t);
+    if (phit.x == 0.f && phit.y == 0.f) phit.x = 1e-5f * q.radius;
+    float phi = atan2f(phit.y, phit.x);
+    if (phi < 0.f) phi += 2.f * PI_F;
+    sphere_fill(q, xf, flags, phit, phi, t, hit);
 }
 
+__device__ inline void disk_fill(const SptQuadric &q, const SptXform &xf, int flags, v3 phit, float phi, float dist2, float thit, Hit *hit);
 // Disk (src/shapes/disk.cpp:48-95, :98-121)
 __device__ inline bool disk_intersect(const DevScene &sc, const SptQuadric &q, int flags, const Ray &r,
                                       float *tout, Hit *hit) {
@@ -153,6 +197,11 @@ __device__ inline bool disk_intersect(const DevScene &sc, const SptQuadric &q, i
     if (phi > phiMax) return false;
     *tout = thit;
     if (!hit) return true;
+    disk_fill(q, xf, flags, phit, phi, dist2, thit, hit);
+    return true;
+}
+__device__ inline void disk_fill(const SptQuadric &q, const SptXform &xf, int flags, v3 phit, float phi, float dist2, float thit, Hit *hit) {
+    float radius = q.radius, innerRadius = q.zmax, phiMax = q.phiMax;
     float u = phi / phiMax;
     float oneMinusV = ((sqrtf(dist2) - innerRadius) / (radius - innerRadius));
     float invOneMinusV = (oneMinusV > 0.f) ? (1.f / oneMinusV) : 0.f;
@@ -164,7 +213,17 @@ __device__ inline bool disk_intersect(const DevScene &sc, const SptQuadric &q, i
     dg_init(hit, xf_point(xf.m, phit), xf_vector(xf.m, dpdu), xf_vector(xf.m, dpdv), u, v, flags);
     hit->t = thit;
     hit->rayEpsilon = 5e-4f * thit;
-    return true;
+}
+__device__ inline void disk_record(const DevScene &sc, const SptQuadric &q, int flags, const Ray &r, float t, Hit *hit) {
+    const SptXform &xf = sc.xforms[q.xform];
+    Ray ray = r;
+    ray.o = xf_point(xf.minv, r.o);
+    ray.d = xf_vector(xf.minv, r.d);
+    v3 phit = ray_at(ray, t);
+    float dist2 = phit.x * phit.x + phit.y * phit.y;
+    float phi = atan2f(phit.y, phit.x);
+    if (phi < 0) phi = (float)((double)phi + 2. * (double)PI_F);
+    disk_fill(q, xf, flags, phit, phi, dist2, t, hit);
 }
 
 // Shape::Intersect by (kind, flags, data); used for recomputing the hit record in the shading
@@ -174,6 +233,13 @@ __device__ inline bool shape_intersect(const DevScene &sc, int kind, int flags, 
     if (kind == SPT_PRIM_TRIANGLE) return tri_intersect_full(sc, data, flags, ray, hit);
     if (kind == SPT_PRIM_SPHERE) return sphere_intersect(sc, sc.quadrics[data], flags, ray, &t, hit);
     return disk_intersect(sc, sc.quadrics[data], flags, ray, &t, hit);
+}
+
+// The hit record of the primitive the traversal accepted at distance t
+__device__ inline void shape_record(const DevScene &sc, int kind, int flags, uint32_t data, const Ray &ray, float t, Hit *hit) {
+    if (kind == SPT_PRIM_TRIANGLE) tri_record(sc, data, flags, ray, t, hit);
+    else if (kind == SPT_PRIM_SPHERE) sphere_record(sc, sc.quadrics[data], flags, ray, t, hit);
+    else disk_record(sc, sc.quadrics[data], flags, ray, t, hit);
 }
 
 // ---- slab test (src/accelerators/bvh.cpp:118-140) ----------------------------------------------

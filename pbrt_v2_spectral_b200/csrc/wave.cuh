@@ -1,0 +1,84 @@
+// wave.cuh — per-wave path state in HBM and the device-side queues, shared by both kernel
+// translation units (exact: camera + traversal; shading: everything after a hit is known).
+//
+// A WAVE is a batch of camera samples (whole sampler pixels x spp). Per-path state lives in HBM as
+// SoA arrays indexed by the path's slot in the wave; kernels walk compacted index queues whose
+// lengths stay on the device, so the host never synchronises inside a wave:
+//
+//   K1 gen_camera      sample -> camera ray                                   (Sampler + Camera)
+//   per bounce b:
+//     K2 trace<closest>  path-ray queue                                       (BVHAccel::Intersect)
+//     K5 shade           hit -> shading frame, light sample, MIS sample, continuation sample;
+//                        stages scalar BSDF terms + shadow / MIS rays         (PathIntegrator::Li body)
+//     K3 trace<any>      shadow-ray queue                                     (BVHAccel::IntersectP)
+//     K2 trace<closest>  MIS-ray queue
+//     K6 accumulate      one 32-band loop: L += T*Ld, T *= f|cos|/pdf, Russian roulette,
+//                        warp-aggregated compaction into the next path queue
+//   K7 film_add        radiance guards + SpectralImageFilm::AddSample with a warp-per-pixel reduction
+#pragma once
+#include "spt_device.cuh"
+
+struct WaveBuffers {
+    uint32_t cap;
+    float4 *ray_o, *ray_d;            // path rays: {o, mint}, {d, maxt}
+    uint32_t *hit_slot; float *hit_t;
+    float4 *g0, *g1, *g2, *g3;        // {p, eps}, {shadow d, shadow maxt}, {mis d, inf}, {path d, -}
+    uint32_t *mis_slot; float *mis_t; uint32_t *sh_slot;
+    float4 *r0, *r1, *r2, *r3, *r4, *r5;
+    uint4 *r6;
+    float2 *img_xy;
+    float *T, *L;                     // [cap][NB]: band_off()
+    uint32_t *pathQ[2], *shadowQ, *misQ;
+    uint32_t *hitQ, *missQ;           // path rays of the bounce that found a surface / escaped (bounce 0, env light)
+};
+
+// Spectral path state layout: one 128-byte row of NB bands per path. The accumulate and film kernels
+// work lane-per-band, so every access is one coalesced line whatever the order of the paths in the
+// queues, and all bands of a path sit in one page (a [NB][cap] array strides by the wave capacity
+// - tens of MB - between bands and thrashes the TLB).
+__device__ __forceinline__ size_t band_off(uint32_t i, int c) { return (size_t)i * NB + (uint32_t)c; }
+
+struct RenderCfg {
+    SptCameraDesc cam;
+    int spp, max_depth;
+    int x0, x1, y0, y1;               // sample extent (x1,y1 exclusive, already border-trimmed)
+    int tile, tilesX, tilesY, rank, nranks;
+    uint32_t seed;
+    uint64_t pixel_base;              // first rank-local pixel of this wave
+    uint32_t n_samples;               // samples in this wave
+};
+
+// flags in r6.x
+enum { RF_L = 1, RF_LDELTA = 2, RF_B = 4, RF_P = 8, RF_L_REFL = 16, RF_L_MF = 32, RF_B_REFL = 64, RF_B_MF = 128,
+       RF_P_REFL = 256, RF_P_MF = 512, RF_ON = 1024 };
+
+__device__ __forceinline__ bool wave_pixel(const RenderCfg &cfg, uint64_t j, int *px, int *py) {
+    uint32_t tp = (uint32_t)(cfg.tile * cfg.tile);
+    uint64_t lt = j / tp;
+    uint32_t w = (uint32_t)(j % tp);
+    uint64_t tile = lt * (uint64_t)cfg.nranks + (uint64_t)cfg.rank;
+    if (tile >= (uint64_t)cfg.tilesX * cfg.tilesY) return false;
+    int tx = (int)(tile % cfg.tilesX), ty = (int)(tile / cfg.tilesX);
+    *px = cfg.x0 + tx * cfg.tile + (int)(w % cfg.tile);
+    *py = cfg.y0 + ty * cfg.tile + (int)(w / cfg.tile);
+    return *px < cfg.x1 && *py < cfg.y1;
+}
+__device__ __forceinline__ uint32_t pix_key(int px, int py) { return ((uint32_t)py << 16) ^ (uint32_t)px; }
+
+// warp-aggregated append: one atomicAdd per warp
+__device__ __forceinline__ void queue_push(uint32_t *queue, uint32_t *count, bool pred, uint32_t value) {
+    unsigned mask = __ballot_sync(__activemask(), pred);
+    if (!pred) return;
+    int lane = threadIdx.x & 31;
+    int leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(count, (uint32_t)__popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    queue[base + __popc(mask & ((1u << lane) - 1))] = value;
+}
+
+struct FilmView {
+    SptFilmDesc d;
+    float *pix;            // [y][x][NB+1]
+    const float *table;    // 256 filter weights in global memory
+};
