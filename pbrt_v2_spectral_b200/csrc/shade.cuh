@@ -188,16 +188,14 @@ __device__ __forceinline__ float f_band(const SptMaterial &m, bool orenNayar, co
     }
     return f;
 }
-// BSDF::Sample_f (reflection.cpp:514-572): direction + pdf + scalar terms. pdf == 0: no sample.
-__device__ inline void bsdf_sample(const Bsdf &b, v3 woW, v3 wo, float uComp, float u1, float u2,
-                                   v3 *wiW, float *pdf, DirTerms *t) {
+// BSDF::Sample_f (reflection.cpp:514-572), first half: the component is chosen and its direction
+// sampled (local frame). Returns false when the chosen component yields no sample (pdf == 0).
+__device__ inline bool bsdf_sample_dir(const Bsdf &b, v3 wo, float uComp, float u1, float u2, v3 *wiOut) {
     int matching = bsdf_ncomp(b);
     int which = (int)floorf(uComp * matching);
     if (matching - 1 < which) which = matching - 1;
     bool mf = (b.mtype == SPT_MAT_METAL) || (b.mtype == SPT_MAT_PLASTIC && which == 1);
     v3 wi;
-    *pdf = 0.f;
-    t->a0 = t->a1 = t->a2 = t->a3 = 0.f; t->mf = false; t->reflect = false;
     bool chosenZero;
     if (!mf) {                                                       // BxDF::Sample_f, reflection.cpp:303-310
         wi = cosine_sample_hemisphere(u1, u2);
@@ -215,7 +213,16 @@ __device__ inline void bsdf_sample(const Bsdf &b, v3 woW, v3 wo, float uComp, fl
         wi = vadd(vneg(wo), vmul(wh, 2.f * woh));
         chosenZero = woh <= 0.f || costheta == 0.f;
     }
-    if (chosenZero) return;
+    *wiOut = wi;
+    return !chosenZero;
+}
+// Second half: value and pdf over all components for the sampled direction. pdf == 0: no sample.
+__device__ inline void bsdf_sample(const Bsdf &b, v3 woW, v3 wo, float uComp, float u1, float u2,
+                                   v3 *wiW, float *pdf, DirTerms *t) {
+    v3 wi;
+    *pdf = 0.f;
+    t->a0 = t->a1 = t->a2 = t->a3 = 0.f; t->mf = false; t->reflect = false;
+    if (!bsdf_sample_dir(b, wo, uComp, u1, u2, &wi)) return;
     *wiW = l2w(b, wi);
     bsdf_terms(b, woW, *wiW, wo, wi, t, pdf);
 }
@@ -379,12 +386,14 @@ __device__ inline float shapeset_pdf(const DevScene &sc, const SptLight &l, v3 p
 // Result of Light::Sample_L (diffuse.cpp:61-73 + light.cpp:137-149, point.cpp:42-49,
 // infinite.cpp:187-213) with the VisibilityTester segment (light.h:79-88). The radiance is kept as
 // {kind, aux}: AREA on/off (x Lemit), POINT 1/d2 divisor, INFINITE rgb.
-struct LightSampleResult { bool delta; bool black; v3 wi; float pdf; v3 shadow_d; float shadow_maxt; float aux[3]; };
+struct LightSampleResult { bool delta; bool black; bool pdfPending; v3 wi; float pdf; v3 shadow_d; float shadow_maxt; float aux[3]; };
 
+// deferPdf: leave an area light's pdf (ShapeSet::Pdf of the sampled direction) to the caller, which
+// evaluates Light::Pdf for this and the BSDF-sampled direction from one call site (pdfPending is set).
 __device__ inline void light_sample(const DevScene &sc, int lightIdx, v3 p, float u0, float u1, float uComp,
-                                    LightSampleResult *out) {
+                                    LightSampleResult *out, bool deferPdf = false) {
     const SptLight &l = sc.lights[lightIdx];
-    out->delta = false; out->black = true; out->pdf = 0.f;
+    out->delta = false; out->black = true; out->pdf = 0.f; out->pdfPending = false;
     out->aux[0] = out->aux[1] = out->aux[2] = 0.f;
     out->wi = V(0, 0, 1); out->shadow_d = V(0, 0, 1); out->shadow_maxt = 0.f;
     if (l.type == SPT_LIGHT_POINT) {
@@ -403,20 +412,28 @@ __device__ inline void light_sample(const DevScene &sc, int lightIdx, v3 p, floa
         const float *cdf = sc.light_cdf + l.shape_first + lightIdx;
         int sn = cdf_find(cdf, l.shape_count, uComp);
         v3 ns;
-        v3 pt = shape_sample_from(sc, sc.light_shapes[l.shape_first + sn], p, u0, u1, &ns);
-        Ray r; r.o = p; r.d = vsub(pt, p); r.mint = 1e-3f; r.maxt = SPT_INF;
-        float thit = 1.f;
-        bool anyHit = false;
-        v3 nnHit = ns;
-        for (int i = 0; i < l.shape_count; ++i) {            // unclipped ray, LAST hit wins (light.cpp:141-149)
-            const SptLightShape &s = sc.light_shapes[l.shape_first + i];
-            Hit hh;
-            if (shape_intersect(sc, s.kind, s.flags, (uint32_t)s.data, r, &hh)) { anyHit = true; nnHit = hh.nn; thit = hh.t; }
+        const SptLightShape &chosen = sc.light_shapes[l.shape_first + sn];
+        v3 pt = shape_sample_from(sc, chosen, p, u0, u1, &ns);
+        v3 ps = pt;
+        // ShapeSet::Sample re-intersects every shape of the set with the unclipped ray p -> pt and keeps
+        // the LAST hit (light.cpp:141-149). For a set of one sphere that hit is pt itself with the same
+        // outward normal (Sphere::Sample's and DifferentialGeometry's orientations agree), up to rounding.
+        if (!(l.shape_count == 1 && chosen.kind == SPT_PRIM_SPHERE)) {
+            Ray r; r.o = p; r.d = vsub(pt, p); r.mint = 1e-3f; r.maxt = SPT_INF;
+            float thit = 1.f;
+            bool anyHit = false;
+            v3 nnHit = ns;
+            for (int i = 0; i < l.shape_count; ++i) {
+                const SptLightShape &s = sc.light_shapes[l.shape_first + i];
+                Hit hh;
+                if (shape_intersect(sc, s.kind, s.flags, (uint32_t)s.data, r, &hh)) { anyHit = true; nnHit = hh.nn; thit = hh.t; }
+            }
+            if (anyHit) ns = nnHit;
+            ps = ray_at(r, thit);
         }
-        if (anyHit) ns = nnHit;
-        v3 ps = ray_at(r, thit);
         out->wi = normalize(vsub(ps, p));
-        out->pdf = shapeset_pdf(sc, l, p, out->wi);
+        if (deferPdf) out->pdfPending = true;
+        else out->pdf = shapeset_pdf(sc, l, p, out->wi);
         float dist = sqrtf(len2(vsub(p, ps)));
         out->shadow_d = vdiv(vsub(ps, p), dist);
         out->shadow_maxt = dist * (1.f - 1e-3f);

@@ -57,7 +57,7 @@ struct SptScene {
     std::vector<uint32_t> prim_id_host;
     uint32_t *prim_id_dev = nullptr;
     bool counters_on = false;
-    int trace_variant = 2;           // trace_kernels.cuh
+    int trace_variant = 1;           // trace_kernels.cuh: 0 reference nodes, 1 pair nodes (default), 2 node/leaf phases
     uint32_t leaf_wait = 6;
     bool has_env = false;            // an infinite light is present (escaped camera rays pick up Le)
     unsigned long long *counters = nullptr;

@@ -90,60 +90,81 @@ __global__ void __launch_bounds__(128) k_shade(DevScene sc, RenderCfg cfg, Sampl
                 float4 g1 = r0, g2 = r0, g3 = r0;
                 int lightIdx = 0;
                 if (bsdf.orenNayar) flags |= RF_ON;
-                if (sc.n_lights > 0) {
-                    // UniformSampleOneLight (integrator.cpp:74-106) + EstimateDirect (:109-166)
+                const bool haveLights = sc.n_lights > 0;
+                // The three directions of a path vertex: 0 the light sample (UniformSampleOneLight,
+                // integrator.cpp:74-106; EstimateDirect :109-137), 1 the BSDF sample of the MIS estimate
+                // (:139-163), 2 the continuation (path.cpp:75-92). Each stage below runs ONCE over the
+                // directions that need it (rolled loops: one copy of the sampling, Light::Pdf and BSDF::f/Pdf
+                // code in the instruction cache instead of one per direction).
+                LightSampleResult lr;
+                lr.delta = false; lr.black = true; lr.pdfPending = false; lr.pdf = 0.f; lr.wi = V(0, 0, 1);
+                if (haveLights) {
                     int nLights = (int)sc.n_lights;
                     lightIdx = (int)floorf(u[0] * nLights);
                     if (nLights - 1 < lightIdx) lightIdx = nLights - 1;
-                    LightSampleResult lr;
-                    light_sample(sc, lightIdx, p, u[1], u[2], u[3], &lr);
-                    if (lr.pdf > 0.f && !lr.black) {
-                        DirTerms t;
-                        v3 wi = w2l(bsdf, lr.wi);
-                        float bsdfPdf;
-                        bsdf_terms(bsdf, woW, lr.wi, wo, wi, &t, &bsdfPdf);
-                        if (t.reflect) {
-                            float sL;
-                            if (lr.delta) sL = (absdot(lr.wi, n_s) / lr.pdf);
-                            else {
-                                float weight = power_heuristic(lr.pdf, bsdfPdf);
-                                sL = (absdot(lr.wi, n_s) * weight / lr.pdf);
-                            }
-                            flags |= RF_L | (lr.delta ? RF_LDELTA : 0) | RF_L_REFL | (t.mf ? RF_L_MF : 0);
-                            r0 = make_float4(t.a0, t.a1, t.a2, t.a3);
-                            r3.x = sL;
-                            r5 = make_float4(lr.aux[0], lr.aux[1], lr.aux[2], 0.f);
-                            g1 = make_float4(lr.shadow_d.x, lr.shadow_d.y, lr.shadow_d.z, lr.shadow_maxt);
-                            pushShadow = true;
-                        }
-                    }
-                    if (!lr.delta) {
-                        v3 wiW; float bsdfPdf; DirTerms t;
-                        bsdf_sample(bsdf, woW, wo, u[6], u[4], u[5], &wiW, &bsdfPdf, &t);
-                        if (bsdfPdf > 0.f && t.reflect) {
-                            float lightPdf = light_pdf(sc, lightIdx, p, wiW);
-                            if (lightPdf != 0.f) {
-                                float weight = power_heuristic(bsdfPdf, lightPdf);
-                                flags |= RF_B | RF_B_REFL | (t.mf ? RF_B_MF : 0);
-                                r1 = make_float4(t.a0, t.a1, t.a2, t.a3);
-                                r3.y = absdot(wiW, n_s); r3.z = weight; r3.w = bsdfPdf;
-                                g2 = make_float4(wiW.x, wiW.y, wiW.z, SPT_INF);
-                                pushMis = true;
-                            }
-                        }
-                    }
+                    light_sample(sc, lightIdx, p, u[1], u[2], u[3], &lr, true);
                 }
-                {   // continuation direction (path.cpp:75-92)
-                    v3 wiW; float pdf; DirTerms t;
-                    bsdf_sample(bsdf, woW, wo, u[9], u[7], u[8], &wiW, &pdf, &t);
-                    if (pdf != 0.f) {
-                        flags |= RF_P | (t.reflect ? RF_P_REFL : 0) | (t.mf ? RF_P_MF : 0);
-                        r2 = make_float4(t.a0, t.a1, t.a2, t.a3);
-                        r4.x = absdot(wiW, n_s); r4.y = pdf;
-                        g3 = make_float4(wiW.x, wiW.y, wiW.z, 0.f);
-                    }
-                    r4.z = rr;
+                v3 wl1 = V(0, 0, 1), wl2 = wl1, wiW1 = wl1, wiW2 = wl1;
+                bool have1 = false, have2 = false;
+#pragma unroll 1
+                for (int d = 1; d <= 2; ++d) {
+                    if (d == 1 && (!haveLights || lr.delta)) continue;
+                    float uc = d == 1 ? u[6] : u[9], ua = d == 1 ? u[4] : u[7], ub = d == 1 ? u[5] : u[8];
+                    v3 wl;
+                    bool ok = bsdf_sample_dir(bsdf, wo, uc, ua, ub, &wl);
+                    v3 wW = l2w(bsdf, wl);
+                    if (d == 1) { have1 = ok; wl1 = wl; wiW1 = wW; } else { have2 = ok; wl2 = wl; wiW2 = wW; }
                 }
+                float lightPdf1 = 0.f;
+#pragma unroll 1
+                for (int d = 0; d <= 1; ++d) {
+                    if (!(d == 0 ? lr.pdfPending : have1)) continue;
+                    float pdf = light_pdf(sc, lightIdx, p, d == 0 ? lr.wi : wiW1);
+                    if (d == 0) lr.pdf = pdf; else lightPdf1 = pdf;
+                }
+                const bool have0 = haveLights && lr.pdf > 0.f && !lr.black;
+                const v3 wl0 = w2l(bsdf, lr.wi);
+                DirTerms t0, t1, t2;
+                t0.a0 = t0.a1 = t0.a2 = t0.a3 = 0.f; t0.reflect = t0.mf = false; t1 = t0; t2 = t0;
+                float pdf0 = 0.f, pdf1 = 0.f, pdf2 = 0.f;
+#pragma unroll 1
+                for (int d = 0; d < 3; ++d) {
+                    if (!(d == 0 ? have0 : (d == 1 ? have1 : have2))) continue;
+                    v3 wW = d == 0 ? lr.wi : (d == 1 ? wiW1 : wiW2);
+                    v3 wl = d == 0 ? wl0 : (d == 1 ? wl1 : wl2);
+                    DirTerms t; float pdf;
+                    bsdf_terms(bsdf, woW, wW, wo, wl, &t, &pdf);
+                    if (d == 0) { t0 = t; pdf0 = pdf; } else if (d == 1) { t1 = t; pdf1 = pdf; } else { t2 = t; pdf2 = pdf; }
+                }
+                if (have0 && t0.reflect) {
+                    float sL;
+                    if (lr.delta) sL = (absdot(lr.wi, n_s) / lr.pdf);
+                    else {
+                        float weight = power_heuristic(lr.pdf, pdf0);
+                        sL = (absdot(lr.wi, n_s) * weight / lr.pdf);
+                    }
+                    flags |= RF_L | (lr.delta ? RF_LDELTA : 0) | RF_L_REFL | (t0.mf ? RF_L_MF : 0);
+                    r0 = make_float4(t0.a0, t0.a1, t0.a2, t0.a3);
+                    r3.x = sL;
+                    r5 = make_float4(lr.aux[0], lr.aux[1], lr.aux[2], 0.f);
+                    g1 = make_float4(lr.shadow_d.x, lr.shadow_d.y, lr.shadow_d.z, lr.shadow_maxt);
+                    pushShadow = true;
+                }
+                if (have1 && pdf1 > 0.f && t1.reflect && lightPdf1 != 0.f) {
+                    float weight = power_heuristic(pdf1, lightPdf1);
+                    flags |= RF_B | RF_B_REFL | (t1.mf ? RF_B_MF : 0);
+                    r1 = make_float4(t1.a0, t1.a1, t1.a2, t1.a3);
+                    r3.y = absdot(wiW1, n_s); r3.z = weight; r3.w = pdf1;
+                    g2 = make_float4(wiW1.x, wiW1.y, wiW1.z, SPT_INF);
+                    pushMis = true;
+                }
+                if (have2 && pdf2 != 0.f) {
+                    flags |= RF_P | (t2.reflect ? RF_P_REFL : 0) | (t2.mf ? RF_P_MF : 0);
+                    r2 = make_float4(t2.a0, t2.a1, t2.a2, t2.a3);
+                    r4.x = absdot(wiW2, n_s); r4.y = pdf2;
+                    g3 = make_float4(wiW2.x, wiW2.y, wiW2.z, 0.f);
+                }
+                r4.z = rr;
                 wb.g0[i] = make_float4(p.x, p.y, p.z, eps);
                 wb.g1[i] = g1; wb.g2[i] = g2; wb.g3[i] = g3;
                 wb.r0[i] = r0; wb.r1[i] = r1; wb.r2[i] = r2; wb.r3[i] = r3; wb.r4[i] = r4; wb.r5[i] = r5;
@@ -192,6 +213,7 @@ struct LightBand { int kind; IllumCoefs k; };
 //      coalesced 128-byte line - and updates L += T*Ld, T *= f|cos|/pdf. y(T) is a warp sum, the
 //      Russian-roulette decision and the 1/q scaling are warp-uniform, so T is written once.
 //   C  lane = vertex again: surviving paths write their next ray and join the next path queue.
+static_assert(NB == 32, "k_accumulate and k_film_add map one band to one lane");
 #define ACC_WARPS 4
 #define ACC_GROUP 4          // vertices whose T/L rows are in flight together in phase B
 __global__ void __launch_bounds__(32 * ACC_WARPS) k_accumulate(DevScene sc, RenderCfg cfg, WaveBuffers wb, int bounce,
@@ -346,91 +368,84 @@ __global__ void __launch_bounds__(32 * ACC_WARPS) k_accumulate(DevScene sc, Rend
 
 // ---- K7 ----------------------------------------------------------------------------------------
 // Radiance guards (samplerrenderer.cpp:119-133) + SpectralImageFilm::AddSample
-// (spectralImage.cpp:77-152). One warp per sampler pixel: lanes stride over the pixel's samples;
-// contributions whose footprint is exactly that pixel are reduced across the warp with shuffles and
-// flushed with one atomic per band; anything else (wide filters, samples rounding onto a pixel
-// edge) goes straight to global atomics.
+// (spectralImage.cpp:77-152). One warp per sampler pixel, lane = band: each sample's radiance row
+// is one coalesced 128-byte load; y(L) for the guards is a warp sum. Samples whose footprint is
+// exactly the warp's own pixel (all of them under the box filter, up to rounding onto a pixel edge)
+// accumulate in a register per band and are flushed with one atomic per band per pixel; any other
+// footprint (wide filters) goes to global atomics, one coalesced 32-band atomic row per touched pixel.
+#define FILM_GROUP 8
 __global__ void __launch_bounds__(256) k_film_add(FilmView film, const SptSpectralTables *tables, const float2 *img_xy,
                                                   const float *L, uint32_t cap, uint32_t n_samples, int spp) {
     const SptSpectralTables &tb = *tables;
-    int lane = threadIdx.x & 31;
-    uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-    uint32_t npix = (n_samples + spp - 1) / spp;
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t npix = (n_samples + spp - 1) / spp;
     const SptFilmDesc &fd = film.d;
+    const float cieY = tb.cie_y[lane], yint = tb.yint;
+    const int xs = fd.x_pixel_start, ys = fd.y_pixel_start, xe = xs + fd.x_pixel_count - 1, ye = ys + fd.y_pixel_count - 1;
     for (uint32_t pixel = warp; pixel < npix; pixel += nwarps) {
-        // the pixel this warp reduces into: the one the first sample of the group falls in
-        float2 xy0 = img_xy[(size_t)pixel * spp];
-        int mainx = (int)floorf(xy0.x), mainy = (int)floorf(xy0.y);
-        bool mainInside = mainx >= fd.x_pixel_start && mainx < fd.x_pixel_start + fd.x_pixel_count &&
-                          mainy >= fd.y_pixel_start && mainy < fd.y_pixel_start + fd.y_pixel_count;
-        float wsum = 0.f;
-        for (int s0 = 0; s0 < spp; s0 += 32) {
-            int s = s0 + lane;
-            uint32_t i = pixel * spp + s;
-            bool have = s < spp && i < n_samples;
-            float2 xy = have ? img_xy[i] : make_float2(-1e30f, -1e30f);
-            have = have && xy.x > -1e29f;
-            bool bad = false;
-            float y = 0.f;
-            if (have) {
-                for (int c = 0; c < NB; ++c) {
-                    float v = L[band_off(i, c)];
-                    if (isnan(v)) bad = true;
-                    y += tb.cie_y[c] * v;
-                }
-                y = y / tb.yint;
+        const uint32_t first = pixel * (uint32_t)spp;
+        const uint32_t ns = min((uint32_t)spp, n_samples - first);
+        // the pixel this warp accumulates for: the one the first sample of the group falls in
+        float2 xy0 = img_xy[first];
+        const int mainx = (int)floorf(xy0.x), mainy = (int)floorf(xy0.y);
+        const bool mainInside = mainx >= xs && mainx <= xe && mainy >= ys && mainy <= ye;
+        float acc = 0.f, wsum = 0.f;
+        for (uint32_t s0 = 0; s0 < ns; s0 += FILM_GROUP) {
+            float2 xyv[FILM_GROUP]; float Lv[FILM_GROUP];
+#pragma unroll
+            for (int k = 0; k < FILM_GROUP; ++k) {
+                uint32_t i = first + min(s0 + k, ns - 1);
+                xyv[k] = img_xy[i];
+                Lv[k] = L[band_off(i, lane)];
+            }
+#pragma unroll
+            for (int k = 0; k < FILM_GROUP; ++k) {
+                if (s0 + k >= ns) break;
+                const float2 xy = xyv[k];
+                if (!(xy.x > -1e29f)) continue;                         // sample outside this rank's tile set
+                float v = Lv[k];
+                bool bad = __any_sync(FULL, isnan(v));
+                float y = cieY * v;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) y += __shfl_xor_sync(FULL, y, o);
+                y = y / yint;
                 if ((double)y < -1e-5 || isinf(y)) bad = true;
-            }
-            int x0 = 0, x1 = -1, y0 = 0, y1 = -1;
-            float dimageX = xy.x - 0.5f, dimageY = xy.y - 0.5f;
-            if (have) {
-                x0 = (int)ceilf(dimageX - fd.filter_xwidth); x1 = (int)floorf(dimageX + fd.filter_xwidth);
-                y0 = (int)ceilf(dimageY - fd.filter_ywidth); y1 = (int)floorf(dimageY + fd.filter_ywidth);
-                x0 = max(x0, fd.x_pixel_start); x1 = min(x1, fd.x_pixel_start + fd.x_pixel_count - 1);
-                y0 = max(y0, fd.y_pixel_start); y1 = min(y1, fd.y_pixel_start + fd.y_pixel_count - 1);
-            }
-            bool any = have && (x1 - x0) >= 0 && (y1 - y0) >= 0;
-            bool fast = any && mainInside && x0 == x1 && y0 == y1 && x0 == mainx && y0 == mainy;
-            float wfast = 0.f;
-            if (fast) {
-                float fx = fabsf((x0 - dimageX) * fd.filter_inv_xwidth * 16);
-                float fy = fabsf((y0 - dimageY) * fd.filter_inv_ywidth * 16);
-                int ix = min((int)floorf(fx), 15), iy = min((int)floorf(fy), 15);
-                wfast = film.table[iy * 16 + ix];
-            }
-            if (any && !fast) {
-                for (int yy = y0; yy <= y1; ++yy) {
-                    float fy = fabsf((yy - dimageY) * fd.filter_inv_ywidth * 16);
-                    int iy = min((int)floorf(fy), 15);
-                    for (int xx = x0; xx <= x1; ++xx) {
-                        float fx = fabsf((xx - dimageX) * fd.filter_inv_xwidth * 16);
-                        int ix = min((int)floorf(fx), 15);
-                        float wt = film.table[iy * 16 + ix];
-                        float *dst = film.pix + ((size_t)(yy - fd.y_pixel_start) * fd.x_pixel_count + (xx - fd.x_pixel_start)) * (NB + 1);
-                        for (int c = 0; c < NB; ++c) atomicAdd(dst + c, wt * (bad ? 0.f : L[band_off(i, c)]));
-                        atomicAdd(dst + NB, wt);
+                if (bad) v = 0.f;
+                const float dimageX = xy.x - 0.5f, dimageY = xy.y - 0.5f;
+                int x0 = (int)ceilf(dimageX - fd.filter_xwidth), x1 = (int)floorf(dimageX + fd.filter_xwidth);
+                int y0 = (int)ceilf(dimageY - fd.filter_ywidth), y1 = (int)floorf(dimageY + fd.filter_ywidth);
+                x0 = max(x0, xs); x1 = min(x1, xe); y0 = max(y0, ys); y1 = min(y1, ye);
+                if ((x1 - x0) < 0 || (y1 - y0) < 0) continue;
+                if (mainInside && x0 == x1 && y0 == y1 && x0 == mainx && y0 == mainy) {
+                    float fx = fabsf((x0 - dimageX) * fd.filter_inv_xwidth * 16);
+                    float fy = fabsf((y0 - dimageY) * fd.filter_inv_ywidth * 16);
+                    int ix = min((int)floorf(fx), 15), iy = min((int)floorf(fy), 15);
+                    float wt = film.table[iy * 16 + ix];
+                    acc += wt * v;
+                    wsum += wt;
+                } else {
+                    for (int yy = y0; yy <= y1; ++yy) {
+                        float fy = fabsf((yy - dimageY) * fd.filter_inv_ywidth * 16);
+                        int iy = min((int)floorf(fy), 15);
+                        for (int xx = x0; xx <= x1; ++xx) {
+                            float fx = fabsf((xx - dimageX) * fd.filter_inv_xwidth * 16);
+                            int ix = min((int)floorf(fx), 15);
+                            float wt = film.table[iy * 16 + ix];
+                            float *dst = film.pix + ((size_t)(yy - ys) * fd.x_pixel_count + (xx - xs)) * (NB + 1);
+                            atomicAdd(dst + lane, wt * v);
+                            if (lane == 0) atomicAdd(dst + NB, wt);
+                        }
                     }
                 }
             }
-            // warp reduction of the fast-path contributions, band by band (fixed shuffle tree)
-            float *dst = film.pix + ((size_t)(mainy - fd.y_pixel_start) * fd.x_pixel_count + (mainx - fd.x_pixel_start)) * (NB + 1);
-            if (__any_sync(0xffffffffu, fast)) {
-                for (int c = 0; c < NB; ++c) {
-                    float v = (fast && !bad) ? wfast * L[band_off(i, c)] : 0.f;
-#pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-                    if (lane == 0) atomicAdd(dst + c, v);
-                }
-                float w = fast ? wfast : 0.f;
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) w += __shfl_xor_sync(0xffffffffu, w, off);
-                wsum += w;
-            }
         }
-        if (lane == 0 && wsum != 0.f && mainInside) {
-            float *dst = film.pix + ((size_t)(mainy - fd.y_pixel_start) * fd.x_pixel_count + (mainx - fd.x_pixel_start)) * (NB + 1);
-            atomicAdd(dst + NB, wsum);
+        if (mainInside && wsum != 0.f) {
+            float *dst = film.pix + ((size_t)(mainy - ys) * fd.x_pixel_count + (mainx - xs)) * (NB + 1);
+            atomicAdd(dst + lane, acc);
+            if (lane == 0) atomicAdd(dst + NB, wsum);
         }
     }
 }
