@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -19,13 +20,50 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
 
 namespace {
 
-struct DevMem {
-    std::vector<void *> ptrs;
-    template <typename T> T *alloc(size_t n) {
+// Device allocations go through a per-process cache of freed blocks keyed by (device, size): a host
+// that renders frame after frame (scene_create -> render -> download -> destroy) asks for the same
+// sizes every frame, and cudaMalloc/cudaFree of tens of buffers (the film alone is 65 MB, the wave
+// state gigabytes) costs milliseconds and synchronises the device. spt_trim() returns the cache to
+// the driver.
+struct BlockCache {
+    std::mutex mu;
+    std::multimap<std::pair<int, size_t>, void *> free_blocks;
+    void *get(size_t bytes) {
+        int dev = 0; cudaGetDevice(&dev);
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            auto it = free_blocks.find({dev, bytes});
+            if (it != free_blocks.end()) { void *p = it->second; free_blocks.erase(it); return p; }
+        }
         void *p = nullptr;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            trim();                                   // out of memory: give the cache back and retry once
+            if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        }
+        return p;
+    }
+    void put(void *p, size_t bytes) {
+        int dev = 0; cudaGetDevice(&dev);
+        std::lock_guard<std::mutex> lk(mu);
+        free_blocks.insert({{dev, bytes}, p});
+    }
+    void trim() {
+        std::lock_guard<std::mutex> lk(mu);
+        for (auto &kv : free_blocks) cudaFree(kv.second);
+        free_blocks.clear();
+    }
+};
+BlockCache g_blocks;
+
+struct DevMem {
+    std::vector<std::pair<void *, size_t>> ptrs;
+    template <typename T> T *alloc(size_t n) {
         if (n == 0) n = 1;
-        if (cudaMalloc(&p, n * sizeof(T)) != cudaSuccess) return nullptr;
-        ptrs.push_back(p);
+        size_t bytes = (n * sizeof(T) + 255) & ~(size_t)255;
+        void *p = g_blocks.get(bytes);
+        if (!p) return nullptr;
+        ptrs.push_back({p, bytes});
         return (T *)p;
     }
     template <typename T> T *upload(const T *host, size_t n) {
@@ -33,7 +71,8 @@ struct DevMem {
         if (d && n && host && cudaMemcpy(d, host, n * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
         return d;
     }
-    void release() { for (void *p : ptrs) cudaFree(p); ptrs.clear(); }
+    // callers synchronise the device (or the stream that last touched the blocks) before releasing
+    void release() { for (auto &p : ptrs) g_blocks.put(p.first, p.second); ptrs.clear(); }
 };
 
 int num_sms() {
@@ -88,6 +127,7 @@ struct SptFilm {
     bool owned = true;
     float *table = nullptr;
     float *split = nullptr;         // download staging: [y][x][NB] followed by [y][x] weights
+    DevMem mem;                     // owned device blocks (pixels unless external, filter table, staging)
     size_t npix() const { return (size_t)desc.x_pixel_count * desc.y_pixel_count; }
 };
 
@@ -107,6 +147,8 @@ void spt_trim(void) {
     std::lock_guard<std::mutex> lk(g_wave_mu);
     for (WaveCache &c : g_wave_cache) c.mem.release();
     g_wave_cache.clear();
+    cudaDeviceSynchronize();
+    g_blocks.trim();
 }
 
 SptScene *spt_scene_create(const SptSceneDesc *d) {
@@ -547,16 +589,16 @@ static SptFilm *film_new(const SptFilmDesc *d, float *ext) {
     f->pix = ext;
     size_t bytes = f->npix() * (NB + 1) * sizeof(float);
     if (!ext) {
-        if (cudaMalloc((void **)&f->pix, bytes) != cudaSuccess || cudaMemset(f->pix, 0, bytes) != cudaSuccess) {
+        f->pix = f->mem.alloc<float>(bytes / sizeof(float));
+        if (!f->pix || cudaMemset(f->pix, 0, bytes) != cudaSuccess) {
             g_err = std::string("film allocation failed: ") + cudaGetErrorString(cudaGetLastError());
-            delete f; return nullptr;
+            f->mem.release(); delete f; return nullptr;
         }
     }
-    if (cudaMalloc((void **)&f->table, 256 * sizeof(float)) != cudaSuccess ||
-        cudaMemcpy(f->table, d->filter_table, 256 * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+    f->table = f->mem.upload(d->filter_table, 256);
+    if (!f->table) {
         g_err = "film filter table upload failed";
-        if (f->owned) cudaFree(f->pix);
-        delete f; return nullptr;
+        f->mem.release(); delete f; return nullptr;
     }
     return f;
 }
@@ -568,9 +610,7 @@ SptFilm *spt_film_create_external(const SptFilmDesc *d, float *pixels_dev) {
 void spt_film_destroy(SptFilm *f) {
     if (!f) return;
     cudaDeviceSynchronize();
-    if (f->owned) cudaFree(f->pix);
-    cudaFree(f->table);
-    if (f->split) cudaFree(f->split);
+    f->mem.release();
     delete f;
 }
 int spt_film_clear(SptFilm *f) {
@@ -583,7 +623,8 @@ float *spt_film_device_ptr(SptFilm *f) { return f ? f->pix : nullptr; }
 int spt_film_download(SptFilm *f, float *c, float *weight) {
     if (!f) return fail(SPT_ERR_ARG, "null film");
     size_t np = f->npix();
-    if (!f->split) CU(cudaMalloc((void **)&f->split, np * (NB + 1) * sizeof(float)));
+    if (!f->split) f->split = f->mem.alloc<float>(np * (NB + 1));
+    if (!f->split) return fail(SPT_ERR_CUDA, "out of device memory for the film staging buffer");
     // [y][x][NB+1] -> {[y][x][NB], [y][x]} on the device, then one copy per host array (DMA at full
     // rate when the caller's buffers are page-locked, spt_host_alloc)
     CU(cudaDeviceSynchronize());

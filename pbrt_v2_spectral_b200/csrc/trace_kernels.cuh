@@ -20,6 +20,7 @@
 // per-lane ray state shared by the variants
 struct LaneRay {
     Ray ray; v3 invDir; bool negx, negy, negz;
+    bool exact;                 // a component of invDir is inf/NaN: 0 * inf can appear in the slab test, take the literal code
     uint32_t i, best;
 };
 
@@ -41,6 +42,7 @@ __device__ __forceinline__ bool lane_fetch(const TraceArgs &a, uint32_t n, int l
                 L.ray.o = V(o.x, o.y, o.z); L.ray.d = V(d.x, d.y, d.z); L.ray.mint = o.w; L.ray.maxt = d.w;
                 L.invDir = V(1.f / L.ray.d.x, 1.f / L.ray.d.y, 1.f / L.ray.d.z);
                 L.negx = L.invDir.x < 0; L.negy = L.invDir.y < 0; L.negz = L.invDir.z < 0;
+                L.exact = !(isfinite(L.invDir.x) && isfinite(L.invDir.y) && isfinite(L.invDir.z));
                 L.best = SPT_MISS;
                 got = true;
             }
@@ -237,6 +239,22 @@ __device__ __forceinline__ bool slab6(float x0, float x1, float y0, float y1, fl
 // maxt current THEN; of that test only `tmin < maxt` depends on maxt, so the far child is tested
 // at push time, dropped if it already fails, and its tmin is kept on the stack and re-compared with
 // the (possibly shrunk) maxt at pop time - the same decision, bit for bit.
+// The same decision without the sign selects and early outs, for rays whose invDir is finite (no
+// 0 * inf = NaN can occur): per axis near = min(t1, t2), far = max(t1, t2) are exactly the
+// reference's bounds[dirIsNeg] / bounds[1-dirIsNeg] products (rounding is monotonic), its four
+// early-out comparisons hold iff max(near) <= min(far), and its running tmin / tmax are those
+// max / min. x0..z0 = pMin, x1..z1 = pMax.
+__device__ __forceinline__ bool slab6_finite(float x0, float x1, float y0, float y1, float z0, float z1, const Ray &ray,
+                                             v3 invDir, float *tminOut) {
+    float tx0 = (x0 - ray.o.x) * invDir.x, tx1 = (x1 - ray.o.x) * invDir.x;
+    float ty0 = (y0 - ray.o.y) * invDir.y, ty1 = (y1 - ray.o.y) * invDir.y;
+    float tz0 = (z0 - ray.o.z) * invDir.z, tz1 = (z1 - ray.o.z) * invDir.z;
+    float tmin = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fminf(tz0, tz1));
+    float tmax = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fmaxf(tz0, tz1));
+    *tminOut = tmin;
+    return (tmin <= tmax) && (tmin < ray.maxt) && (tmax > ray.mint);
+}
+
 template <bool ANY, bool COUNT>
 __global__ void __launch_bounds__(128) k_trace_v1(DevScene sc, TraceArgs a) {
     const uint32_t n = *a.count;
@@ -274,10 +292,16 @@ __global__ void __launch_bounds__(128) k_trace_v1(DevScene sc, TraceArgs a) {
                 if (COUNT) cn += 2;
                 // child 0: min (q0.x,q0.y,q0.z) max (q0.w,q1.x,q1.y); child 1: min (q1.z,q1.w,q2.x) max (q2.y,q2.z,q2.w)
                 float t0, t1;
-                bool h0 = slab6(L.negx ? q0.w : q0.x, L.negx ? q0.x : q0.w, L.negy ? q1.x : q0.y, L.negy ? q0.y : q1.x,
-                                L.negz ? q1.y : q0.z, L.negz ? q0.z : q1.y, L.ray, L.invDir, &t0);
-                bool h1 = slab6(L.negx ? q2.y : q1.z, L.negx ? q1.z : q2.y, L.negy ? q2.z : q1.w, L.negy ? q1.w : q2.z,
-                                L.negz ? q2.w : q2.x, L.negz ? q2.x : q2.w, L.ray, L.invDir, &t1);
+                bool h0, h1;
+                if (!L.exact) {
+                    h0 = slab6_finite(q0.x, q0.w, q0.y, q1.x, q0.z, q1.y, L.ray, L.invDir, &t0);
+                    h1 = slab6_finite(q1.z, q2.y, q1.w, q2.z, q2.x, q2.w, L.ray, L.invDir, &t1);
+                } else {
+                    h0 = slab6(L.negx ? q0.w : q0.x, L.negx ? q0.x : q0.w, L.negy ? q1.x : q0.y, L.negy ? q0.y : q1.x,
+                               L.negz ? q1.y : q0.z, L.negz ? q0.z : q1.y, L.ray, L.invDir, &t0);
+                    h1 = slab6(L.negx ? q2.y : q1.z, L.negx ? q1.z : q2.y, L.negy ? q2.z : q1.w, L.negy ? q1.w : q2.z,
+                               L.negz ? q2.w : q2.x, L.negz ? q2.x : q2.w, L.ray, L.invDir, &t1);
+                }
                 uint32_t c0 = __float_as_uint(q3.x), c1 = __float_as_uint(q3.y), meta = __float_as_uint(q3.z);
                 uint32_t axis = meta & 3;
                 uint32_t m0 = (meta >> 8) & 0x1ff, m1 = (meta >> 17) & 0x1ff;      // nPrims | hasQuadric << 8
