@@ -383,6 +383,23 @@ __device__ inline float shapeset_pdf(const DevScene &sc, const SptLight &l, v3 p
     return pdf / l.sum_area;
 }
 
+// Can the BSDF-sampled ray of the MIS estimate (integrator.cpp:139-163) reach this area light at all?
+// EstimateDirect traces it through the whole scene and keeps Le only when the CLOSEST primitive
+// belongs to the light (:153-156); a ray that misses every shape of the light therefore contributes
+// exactly nothing and need not be traced. Only spheres need the test: every other shape's
+// Shape::Pdf already intersects it (pdf 0 on a miss, shape.cpp:78-91), while Sphere::Pdf returns
+// the cone pdf for ANY direction (sphere.cpp:255-266). Same sphere_intersect, same ray as the BVH
+// leaf would see, so "miss" here is the traversal's "miss". Conservative (true) for mixed sets.
+__device__ inline bool light_ray_may_hit(const DevScene &sc, const SptLight &l, const Ray &ray) {
+    for (int i = 0; i < l.shape_count; ++i) {
+        const SptLightShape &s = sc.light_shapes[l.shape_first + i];
+        if (s.kind != SPT_PRIM_SPHERE) return true;
+        float t;
+        if (sphere_intersect(sc, sc.quadrics[s.data], 0, ray, &t, nullptr)) return true;
+    }
+    return false;
+}
+
 // Result of Light::Sample_L (diffuse.cpp:61-73 + light.cpp:137-149, point.cpp:42-49,
 // infinite.cpp:187-213) with the VisibilityTester segment (light.h:79-88). The radiance is kept as
 // {kind, aux}: AREA on/off (x Lemit), POINT 1/d2 divisor, INFINITE rgb.

@@ -122,6 +122,11 @@ __global__ void __launch_bounds__(128) k_shade(DevScene sc, RenderCfg cfg, Sampl
                     float pdf = light_pdf(sc, lightIdx, p, d == 0 ? lr.wi : wiW1);
                     if (d == 0) lr.pdf = pdf; else lightPdf1 = pdf;
                 }
+                // a BSDF-sampled ray that cannot reach the light contributes exactly zero: not traced
+                if (have1 && lightPdf1 != 0.f && sc.lights[lightIdx].type == SPT_LIGHT_AREA) {
+                    Ray mr; mr.o = p; mr.d = wiW1; mr.mint = eps; mr.maxt = SPT_INF;
+                    if (!light_ray_may_hit(sc, sc.lights[lightIdx], mr)) have1 = false;
+                }
                 const bool have0 = haveLights && lr.pdf > 0.f && !lr.black;
                 const v3 wl0 = w2l(bsdf, lr.wi);
                 DirTerms t0, t1, t2;
