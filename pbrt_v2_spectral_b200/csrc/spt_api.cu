@@ -155,6 +155,7 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
     if (!d) { g_err = "null scene desc"; return nullptr; }
     if (d->nbands != NB) { g_err = "scene band count does not match the library's SPT_NBANDS"; return nullptr; }
     if (spt_device_count() <= 0) { g_err = "no CUDA device: this library has no CPU path"; return nullptr; }
+    if (d->n_materials > 0xffffu || d->n_lights > 0xfffeu) { g_err = "more than 65535 materials or 65534 lights"; return nullptr; }
     SptScene *s = new SptScene();
     if (const char *e = getenv("SPT_TRACE_VARIANT")) s->trace_variant = atoi(e);
     if (const char *e = getenv("SPT_LEAF_WAIT")) s->leaf_wait = (uint32_t)atoi(e);
@@ -335,8 +336,8 @@ static int ensure_wave(SptScene *s, uint32_t cap, int max_depth, size_t n_waves)
         AL(w.ray_o, float4, cap); AL(w.ray_d, float4, cap); AL(w.hit_slot, uint32_t, cap); AL(w.hit_t, float, cap);
         AL(w.g0, float4, cap); AL(w.g1, float4, cap); AL(w.g2, float4, cap); AL(w.g3, float4, cap);
         AL(w.mis_slot, uint32_t, cap); AL(w.mis_t, float, cap); AL(w.sh_slot, uint32_t, cap);
-        AL(w.r0, float4, cap); AL(w.r1, float4, cap); AL(w.r2, float4, cap); AL(w.r3, float4, cap);
-        AL(w.r4, float4, cap); AL(w.r5, float4, cap); AL(w.r6, uint4, cap);
+        AL(w.rec0, float4, cap); AL(w.rec1, float4, cap); AL(w.rec2, float4, cap);
+        AL(w.laux, float4, cap);
         AL(w.img_xy, float2, cap);
         AL(w.T, float, (size_t)cap * NB); AL(w.L, float, (size_t)cap * NB);
         AL(w.pathQ[0], uint32_t, cap); AL(w.pathQ[1], uint32_t, cap); AL(w.shadowQ, uint32_t, cap); AL(w.misQ, uint32_t, cap);
@@ -384,7 +385,7 @@ static void run_wave(SptScene *s, const RenderCfg &cfg, const SampleSource &src,
         uint32_t *mq = (b == 0 && s->has_env) ? wb.missQ : nullptr;
         launch_trace<false>(s, gridP, q, row + 0, row + 4, wb.ray_o, wb.ray_d, wb.hit_slot, wb.hit_t);
         s->mark(SPT_K_TRACE_PATH);
-        spt_launch_compact_hits(gridN, st, q, row + 0, wb.hit_slot, wb.hitQ, row + 3, mq, row + 7);
+        spt_launch_compact_hits(gridN, st, q, row + 0, wb.hit_slot, wb.hitQ, row + 3, mq, row + 7, (b == 0 && !s->has_env) ? wb.L : nullptr);
         s->mark(SPT_K_SHADE);
         if (mq) { spt_launch_miss_env(gridT, st, sc, wb, mq, row + 7); s->mark(SPT_K_SHADE); }
         spt_launch_shade(gridT, st, sc, cfg, src, wb, b, wb.hitQ, row + 3, row + 1, row + 2);

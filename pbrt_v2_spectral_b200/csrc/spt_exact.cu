@@ -37,14 +37,6 @@ __global__ void __launch_bounds__(256) k_gen_camera(RenderCfg cfg, SampleSource 
         } else {
             wb.img_xy[i] = make_float2(-1e30f, -1e30f);
         }
-        // L starts black; emitted / environment radiance of the camera ray is added by k_shade / k_miss_env.
-        // The warp's 32 rows are contiguous: zeroed row by row, lane = band.
-        {
-            const uint32_t lane = threadIdx.x & 31u, i0 = i - lane;
-            const uint32_t rows = min(32u, cfg.n_samples - i0);
-            for (uint32_t k = 0; k < rows; ++k)
-                for (uint32_t c = lane; c < NB; c += 32) wb.L[band_off(i0 + k, c)] = 0.f;
-        }
         queue_push(wb.pathQ[0], count_out, valid, i);
     }
 }

@@ -15,7 +15,7 @@
 __global__ void __launch_bounds__(256) k_compact_hits(const uint32_t *__restrict__ queue, const uint32_t *__restrict__ count,
                                                       const uint32_t *__restrict__ hit_slot, uint32_t *__restrict__ hit_queue,
                                                       uint32_t *__restrict__ hit_count, uint32_t *__restrict__ miss_queue,
-                                                      uint32_t *__restrict__ miss_count) {
+                                                      uint32_t *__restrict__ miss_count, float *__restrict__ black_L) {
     uint32_t n = *count;
     for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < ((n + 31u) & ~31u); q += gridDim.x * blockDim.x) {
         bool active = q < n;
@@ -23,6 +23,13 @@ __global__ void __launch_bounds__(256) k_compact_hits(const uint32_t *__restrict
         bool hit = active && hit_slot[i] != SPT_MISS;
         queue_push(hit_queue, hit_count, hit, i);
         if (miss_queue) queue_push(miss_queue, miss_count, active && !hit, i);
+        // camera rays that escape with no environment light: the sample's radiance row is black
+        // (rows of hit samples are first written by K6, which starts them from the emitted radiance)
+        if (black_L && active && !hit) {
+            float4 *row = (float4 *)(black_L + band_off(i, 0));
+#pragma unroll
+            for (int c = 0; c < NB / 4; ++c) row[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     }
 }
 
@@ -36,17 +43,31 @@ __global__ void __launch_bounds__(128) k_miss_env(DevScene sc, WaveBuffers wb, c
     for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
         uint32_t i = queue[q];
         float4 d4 = wb.ray_d[i];
+        float Le[NB];
+        for (int c = 0; c < NB; ++c) Le[c] = 0.f;
         for (uint32_t l = 0; l < sc.n_lights; ++l)
             if (sc.lights[l].type == SPT_LIGHT_INFINITE) {
                 float rgb[3];
                 infinite_le_rgb(sc, sc.lights[l], V(d4.x, d4.y, d4.z), rgb);
                 IllumCoefs k = illum_coefs(rgb);
-                for (int c = 0; c < NB; ++c) wb.L[band_off(i, c)] += illum_band(*sc.tables, k, c);
+                for (int c = 0; c < NB; ++c) Le[c] += illum_band(*sc.tables, k, c);
             }
+        for (int c = 0; c < NB; ++c) wb.L[band_off(i, c)] = Le[c];
     }
 }
 
 // ---- K5 ----------------------------------------------------------------------------------------
+// BSDF::f of one direction folded to two wavelength-independent coefficients (see WaveBuffers::rec0):
+//   matte:   {1/pi [* Oren-Nayar factor], 0}          plastic: {1/pi, D*G*F / (4 cosI cosO)}
+//   metal:   {D*G / (4 cosI cosO), |cos theta_h|}     (the conductor Fresnel term is per band)
+__device__ __forceinline__ float2 dir_coef(int mtype, bool on, const DirTerms &t) {
+    float2 d = make_float2(0.f, mtype == SPT_MAT_METAL ? 1.f : 0.f);
+    if (!t.reflect) return d;
+    if (mtype == SPT_MAT_MATTE) d.x = on ? INV_PI_F * t.a0 : INV_PI_F;
+    else if (mtype == SPT_MAT_PLASTIC) { d.x = INV_PI_F; if (t.mf) d.y = t.a0 * t.a1 * t.a2 / t.a3; }
+    else if (t.mf) { d.x = t.a0 * t.a1 / t.a3; d.y = t.a2; }
+    return d;
+}
 __global__ void __launch_bounds__(128) k_shade(DevScene sc, RenderCfg cfg, SampleSource src, WaveBuffers wb, int bounce,
                                                const uint32_t *queue, const uint32_t *count,
                                                uint32_t *shadow_count, uint32_t *mis_count) {
@@ -65,11 +86,12 @@ __global__ void __launch_bounds__(128) k_shade(DevScene sc, RenderCfg cfg, Sampl
             {
                 Hit hit;
                 shape_record(sc, sc.prim_kind[slot], sc.prim_flags[slot], sc.prim_data[slot], ray, wb.hit_t[i], &hit);
-                // emitted light at the first vertex (path.cpp:55-56; Intersection::Le, intersection.cpp:53-56)
+                // emitted light at the first vertex (path.cpp:55-56; Intersection::Le, intersection.cpp:53-56):
+                // K6 starts L from the emitter's spectrum instead of from black
+                int emitter = -1;
                 if (bounce == 0) {
                     int li = sc.prim_light[slot];
-                    if (li >= 0 && dot(hit.nn, vneg(ray.d)) > 0.f)
-                        for (int c = 0; c < NB; ++c) wb.L[band_off(i, c)] = sc.lights[li].spectrum[c];
+                    if (li >= 0 && dot(hit.nn, vneg(ray.d)) > 0.f) emitter = li;
                 }
                 Bsdf bsdf;
                 make_bsdf(sc, slot, hit, &bsdf);
@@ -86,8 +108,11 @@ __global__ void __launch_bounds__(128) k_shade(DevScene sc, RenderCfg cfg, Sampl
                 float u[10], rr;
                 bounce_dims(src, i, pk, s_idx, bounce, sc.n_lights > 0, u, &rr);
 
-                float4 r0 = make_float4(0, 0, 0, 0), r1 = r0, r2 = r0, r3 = r0, r4 = r0, r5 = r0;
-                float4 g1 = r0, g2 = r0, g3 = r0;
+                float4 g1 = make_float4(0, 0, 0, 0), g2 = g1, g3 = g1, laux = g1;
+                const int mtype = bsdf.mtype;
+                const bool on = bsdf.orenNayar;
+                float2 cL = make_float2(0.f, mtype == SPT_MAT_METAL ? 1.f : 0.f), cB = cL, cP = cL;
+                float sL = 0.f, sB = 0.f, sP = 0.f;
                 int lightIdx = 0;
                 if (bsdf.orenNayar) flags |= RF_ON;
                 const bool haveLights = sc.n_lights > 0;
@@ -142,38 +167,42 @@ __global__ void __launch_bounds__(128) k_shade(DevScene sc, RenderCfg cfg, Sampl
                     if (d == 0) { t0 = t; pdf0 = pdf; } else if (d == 1) { t1 = t; pdf1 = pdf; } else { t2 = t; pdf2 = pdf; }
                 }
                 if (have0 && t0.reflect) {
-                    float sL;
                     if (lr.delta) sL = (absdot(lr.wi, n_s) / lr.pdf);
                     else {
                         float weight = power_heuristic(lr.pdf, pdf0);
                         sL = (absdot(lr.wi, n_s) * weight / lr.pdf);
                     }
-                    flags |= RF_L | (lr.delta ? RF_LDELTA : 0) | RF_L_REFL | (t0.mf ? RF_L_MF : 0);
-                    r0 = make_float4(t0.a0, t0.a1, t0.a2, t0.a3);
-                    r3.x = sL;
-                    r5 = make_float4(lr.aux[0], lr.aux[1], lr.aux[2], 0.f);
+                    if (sc.lights[lightIdx].type == SPT_LIGHT_POINT) sL = sL / lr.aux[0];     // I / d^2 (point.cpp:42-49)
+                    flags |= RF_L | (lr.delta ? RF_LDELTA : 0);
+                    cL = dir_coef(mtype, on, t0);
+                    laux = make_float4(lr.aux[0], lr.aux[1], lr.aux[2], 0.f);
                     g1 = make_float4(lr.shadow_d.x, lr.shadow_d.y, lr.shadow_d.z, lr.shadow_maxt);
                     pushShadow = true;
                 }
                 if (have1 && pdf1 > 0.f && t1.reflect && lightPdf1 != 0.f) {
                     float weight = power_heuristic(pdf1, lightPdf1);
-                    flags |= RF_B | RF_B_REFL | (t1.mf ? RF_B_MF : 0);
-                    r1 = make_float4(t1.a0, t1.a1, t1.a2, t1.a3);
-                    r3.y = absdot(wiW1, n_s); r3.z = weight; r3.w = pdf1;
+                    flags |= RF_B;
+                    cB = dir_coef(mtype, on, t1);
+                    sB = absdot(wiW1, n_s) * weight / pdf1;
                     g2 = make_float4(wiW1.x, wiW1.y, wiW1.z, SPT_INF);
                     pushMis = true;
                 }
                 if (have2 && pdf2 != 0.f) {
-                    flags |= RF_P | (t2.reflect ? RF_P_REFL : 0) | (t2.mf ? RF_P_MF : 0);
-                    r2 = make_float4(t2.a0, t2.a1, t2.a2, t2.a3);
-                    r4.x = absdot(wiW2, n_s); r4.y = pdf2;
+                    flags |= RF_P;
+                    cP = dir_coef(mtype, on, t2);
+                    sP = absdot(wiW2, n_s) / pdf2;
                     g3 = make_float4(wiW2.x, wiW2.y, wiW2.z, 0.f);
                 }
-                r4.z = rr;
+                if (mtype == SPT_MAT_METAL) flags |= RF_METAL;
                 wb.g0[i] = make_float4(p.x, p.y, p.z, eps);
-                wb.g1[i] = g1; wb.g2[i] = g2; wb.g3[i] = g3;
-                wb.r0[i] = r0; wb.r1[i] = r1; wb.r2[i] = r2; wb.r3[i] = r3; wb.r4[i] = r4; wb.r5[i] = r5;
-                wb.r6[i] = make_uint4(flags, (uint32_t)sc.prim_material[slot], (uint32_t)lightIdx, 0);
+                if (pushShadow) wb.g1[i] = g1;
+                if (pushMis) wb.g2[i] = g2;
+                if (flags & RF_P) wb.g3[i] = g3;
+                wb.rec0[i] = make_float4(cL.x, cL.y, cB.x, cB.y);
+                wb.rec1[i] = make_float4(cP.x, cP.y, sL, sB);
+                wb.rec2[i] = make_float4(sP, rr, __uint_as_float(flags | (uint32_t)lightIdx << 12),
+                                         __uint_as_float((uint32_t)sc.prim_material[slot] | (uint32_t)(emitter + 1) << 16));
+                if (pushShadow && sc.lights[lightIdx].type == SPT_LIGHT_INFINITE) wb.laux[i] = laux;
             }
         }
         queue_push(wb.shadowQ, shadow_count, pushShadow, i);
@@ -188,15 +217,6 @@ __global__ void __launch_bounds__(128) k_shade(DevScene sc, RenderCfg cfg, Sampl
 // The scalar factors (D*G*F/(4 cosI cosO), |cos|*weight/pdf, ...) are folded once per vertex instead of
 // once per band as the reference's Spectrum arithmetic does; this reassociation moves results by
 // rounding only (tests compare radiance at 2e-4 relative).
-struct DirCoef { float u0, u1, w, cosH; };
-__device__ __forceinline__ DirCoef dir_coef(int mtype, bool on, bool reflect, bool mf, float4 a) {
-    DirCoef d; d.u0 = d.u1 = d.w = 0.f; d.cosH = 1.f;
-    if (!reflect) return d;
-    if (mtype == SPT_MAT_MATTE) d.u0 = on ? INV_PI_F * a.x : INV_PI_F;
-    else if (mtype == SPT_MAT_PLASTIC) { d.u0 = INV_PI_F; if (mf) d.u1 = a.x * a.y * a.z / a.w; }
-    else if (mf) { d.w = a.x * a.y / a.w; d.cosH = a.z; }
-    return d;
-}
 // FrCond (reflection.cpp:63-71) with the two quotients combined into one division
 __device__ __forceinline__ float fr_cond_fast(float cosi, float c2, float eta, float k) {
     float A = fmaf(eta, eta, k * k);
@@ -212,7 +232,7 @@ struct LightBand { int kind; IllumCoefs k; };
 
 // Two phases per batch of 32 path vertices, one batch per warp:
 //   A  lane = vertex: everything wavelength-independent (which terms survive the shadow / MIS rays,
-//      the folded scalar factors), staged in shared memory as 7 x float4 per vertex;
+//      the folded scalar factors), staged in shared memory as 6 x float4 per vertex;
 //   B  lane = band: for each vertex of the batch the warp reads the staged scalars (broadcast),
 //      the material row, the light spectrum and the path's T and L rows - every access a
 //      coalesced 128-byte line - and updates L += T*Ld, T *= f|cos|/pdf. y(T) is a warp sum, the
@@ -224,13 +244,13 @@ static_assert(NB == 32, "k_accumulate and k_film_add map one band to one lane");
 __global__ void __launch_bounds__(32 * ACC_WARPS) k_accumulate(DevScene sc, RenderCfg cfg, WaveBuffers wb, int bounce,
                                                                const uint32_t *__restrict__ queue, const uint32_t *__restrict__ count,
                                                                uint32_t *__restrict__ next_queue, uint32_t *__restrict__ next_count) {
-    __shared__ float4 stage_all[ACC_WARPS][32][7];
+    __shared__ float4 stage_all[ACC_WARPS][32][6];
     const uint32_t n = *count;
     const SptSpectralTables &tb = *sc.tables;
     float *__restrict__ Tg = wb.T;
     float *__restrict__ Lg = wb.L;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float4 (*stage)[7] = stage_all[warp];
+    float4 (*stage)[6] = stage_all[warp];
     const unsigned FULL = 0xffffffffu;
     const float cieY = tb.cie_y[lane];
     const float nL = (float)sc.n_lights;
@@ -242,28 +262,29 @@ __global__ void __launch_bounds__(32 * ACC_WARPS) k_accumulate(DevScene sc, Rend
         const uint32_t i = active ? queue[q] : 0;
         float4 g0 = make_float4(0, 0, 0, 0);
         if (active) {
-            uint4 r6 = wb.r6[i];
-            uint32_t flags = r6.x;
-            const int mtype = sc.materials[r6.y].type;
-            int lightIdx = (int)r6.z;
-            bool on = (flags & RF_ON) != 0;
-            float4 r3 = wb.r3[i], r4 = wb.r4[i];
-            g0 = wb.g0[i];
-            // --- light-sample term (integrator.cpp:122-137): visible iff the shadow ray found nothing
-            DirCoef cL = dir_coef(mtype, on, false, false, make_float4(0, 0, 0, 0)), cB = cL, cP = cL;
+            const float4 c0 = wb.rec0[i], c1 = wb.rec1[i], c2 = wb.rec2[i];
+            const uint32_t bits0 = __float_as_uint(c2.z), bits1 = __float_as_uint(c2.w);
+            const uint32_t flags = bits0 & 0xfffu;
+            const int lightIdx = (int)(bits0 >> 12);
+            const bool metal = (flags & RF_METAL) != 0;
+            const float2 none = make_float2(0.f, metal ? 1.f : 0.f);
+            float2 cL = none, cB = none, cP = make_float2(c1.x, c1.y);
             LightBand lbL, lbB; lbL.kind = 0; lbB.kind = 0;
             lbL.k.k0 = lbL.k.k1 = lbL.k.k2 = 0.f; lbL.k.b1 = lbL.k.b2 = 0; lbB.k = lbL.k;
-            float sL = 0.f, sB = 0.f, sP = 0.f;
+            float sL = 0.f, sB = 0.f;
+            // --- light-sample term (integrator.cpp:122-137): visible iff the shadow ray found nothing
             if ((flags & RF_L) && wb.sh_slot[i] == SPT_MISS) {
-                float4 r5 = wb.r5[i];
-                cL = dir_coef(mtype, on, true, (flags & RF_L_MF) != 0, wb.r0[i]);
-                const SptLight &l = sc.lights[lightIdx];
-                sL = r3.x;
-                if (l.type == SPT_LIGHT_INFINITE) { float rgb[3] = { r5.x, r5.y, r5.z }; lbL.kind = 2; lbL.k = illum_coefs(rgb); }
-                else { lbL.kind = 1; if (l.type == SPT_LIGHT_POINT) sL = sL / r5.x; }
+                cL = make_float2(c0.x, c0.y);
+                sL = c1.z;
+                if (sc.lights[lightIdx].type == SPT_LIGHT_INFINITE) {
+                    float4 r5 = wb.laux[i];
+                    float rgb[3] = { r5.x, r5.y, r5.z };
+                    lbL.kind = 2; lbL.k = illum_coefs(rgb);
+                } else lbL.kind = 1;
             }
             // --- BSDF-sample term (integrator.cpp:139-163): radiance from what the MIS ray found
             if (flags & RF_B) {
+                g0 = wb.g0[i];
                 float4 g2 = wb.g2[i];
                 uint32_t ms = wb.mis_slot[i];
                 const SptLight &l = sc.lights[lightIdx];
@@ -280,19 +301,17 @@ __global__ void __launch_bounds__(32 * ACC_WARPS) k_accumulate(DevScene sc, Rend
                     infinite_le_rgb(sc, l, wi, rgb);
                     lbB.kind = 2; lbB.k = illum_coefs(rgb);
                 }
-                if (lbB.kind) { cB = dir_coef(mtype, on, true, (flags & RF_B_MF) != 0, wb.r1[i]); sB = r3.y * r3.z / r3.w; }
+                if (lbB.kind) { cB = make_float2(c0.z, c0.w); sB = c1.w; }
             }
-            bool haveP = (flags & RF_P) != 0;
-            if (haveP) { cP = dir_coef(mtype, on, (flags & RF_P_REFL) != 0, (flags & RF_P_MF) != 0, wb.r2[i]); sP = r4.x / r4.y; }
+            const bool haveP = (flags & RF_P) != 0;
             sL *= nL; sB *= nL;
-            stage[lane][0] = make_float4(cL.u0, cL.u1, cL.w, cL.cosH);
-            stage[lane][1] = make_float4(cB.u0, cB.u1, cB.w, cB.cosH);
-            stage[lane][2] = make_float4(cP.u0, cP.u1, cP.w, cP.cosH);
-            stage[lane][3] = make_float4(sL, sB, sP, r4.z);
-            stage[lane][4] = make_float4(lbL.k.k0, lbL.k.k1, lbL.k.k2, __uint_as_float((uint32_t)lbL.kind | (uint32_t)lbL.k.b1 << 4 | (uint32_t)lbL.k.b2 << 8));
-            stage[lane][5] = make_float4(lbB.k.k0, lbB.k.k1, lbB.k.k2, __uint_as_float((uint32_t)lbB.kind | (uint32_t)lbB.k.b1 << 4 | (uint32_t)lbB.k.b2 << 8));
-            stage[lane][6] = make_float4(__uint_as_float(i), __uint_as_float(r6.y), __uint_as_float((uint32_t)lightIdx),
-                                         __uint_as_float((haveP ? 1u : 0u) | (mtype == SPT_MAT_METAL ? 2u : 0u)));
+            stage[lane][0] = make_float4(cL.x, cL.y, cB.x, cB.y);
+            stage[lane][1] = make_float4(cP.x, cP.y, sL, sB);
+            stage[lane][2] = make_float4(haveP ? c2.x : 0.f, c2.y, __uint_as_float(i),
+                                         __uint_as_float((haveP ? 1u : 0u) | (metal ? 2u : 0u) | (uint32_t)lightIdx << 2));
+            stage[lane][3] = make_float4(lbL.k.k0, lbL.k.k1, lbL.k.k2, __uint_as_float((uint32_t)lbL.kind | (uint32_t)lbL.k.b1 << 4 | (uint32_t)lbL.k.b2 << 8));
+            stage[lane][4] = make_float4(lbB.k.k0, lbB.k.k1, lbB.k.k2, __uint_as_float((uint32_t)lbB.kind | (uint32_t)lbB.k.b1 << 4 | (uint32_t)lbB.k.b2 << 8));
+            stage[lane][5] = make_float4(__uint_as_float(bits1 & 0xffffu), __uint_as_float(bits1 >> 16), 0.f, 0.f);
         }
         __syncwarp();
         // ---- phase B
@@ -304,31 +323,35 @@ __global__ void __launch_bounds__(32 * ACC_WARPS) k_accumulate(DevScene sc, Rend
 #pragma unroll
             for (int k = 0; k < ACC_GROUP; ++k) {
                 uint32_t v = min(v0 + k, cnt - 1);                       // clamped: tail entries repeat the last vertex (not stored)
-                iv[k] = __float_as_uint(stage[v][6].x);
+                iv[k] = __float_as_uint(stage[v][2].z);
                 size_t off = band_off(iv[k], lane);
-                Tv[k] = bounce == 0 ? 1.f : Tg[off];
-                Lv[k] = Lg[off];
+                if (bounce == 0) {
+                    // the path starts here: T = 1, L = what the first vertex emits towards the camera (path.cpp:55-56)
+                    uint32_t emit = __float_as_uint(stage[v][5].y);
+                    Tv[k] = 1.f;
+                    Lv[k] = emit ? __ldg(sc.lights[emit - 1].spectrum + lane) : 0.f;
+                } else { Tv[k] = Tg[off]; Lv[k] = Lg[off]; }
             }
 #pragma unroll
             for (int k = 0; k < ACC_GROUP; ++k) {
                 const uint32_t v = v0 + k;
                 if (v >= cnt) break;
-                const float4 fL4 = stage[v][0], fB4 = stage[v][1], fP4 = stage[v][2], sc4 = stage[v][3];
-                const float4 lL4 = stage[v][4], lB4 = stage[v][5], id4 = stage[v][6];
-                const SptMaterial &m = sc.materials[__float_as_uint(id4.y)];
-                const SptLight &lt = sc.lights[__float_as_uint(id4.z)];
-                const uint32_t misc = __float_as_uint(id4.w);
+                const float4 cLB = stage[v][0], cPs = stage[v][1], m4 = stage[v][2];
+                const float4 lL4 = stage[v][3], lB4 = stage[v][4];
+                const uint32_t misc = __float_as_uint(m4.w);
+                const SptMaterial &m = sc.materials[__float_as_uint(stage[v][5].x)];
+                const SptLight &lt = sc.lights[misc >> 2];
                 const bool haveP = misc & 1u, metal = (misc & 2u) != 0;
                 const float s0 = __ldg(m.spec0 + lane), s1 = __ldg(m.spec1 + lane);
                 float fL, fB, fP;
                 if (metal) {
-                    fL = fL4.z != 0.f ? fL4.z * fr_cond_fast(fL4.w, fL4.w * fL4.w, s0, s1) : 0.f;
-                    fB = fB4.z != 0.f ? fB4.z * fr_cond_fast(fB4.w, fB4.w * fB4.w, s0, s1) : 0.f;
-                    fP = fP4.z != 0.f ? fP4.z * fr_cond_fast(fP4.w, fP4.w * fP4.w, s0, s1) : 0.f;
+                    fL = cLB.x != 0.f ? cLB.x * fr_cond_fast(cLB.y, cLB.y * cLB.y, s0, s1) : 0.f;
+                    fB = cLB.z != 0.f ? cLB.z * fr_cond_fast(cLB.w, cLB.w * cLB.w, s0, s1) : 0.f;
+                    fP = cPs.x != 0.f ? cPs.x * fr_cond_fast(cPs.y, cPs.y * cPs.y, s0, s1) : 0.f;
                 } else {
-                    fL = fmaf(s0, fL4.x, s1 * fL4.y);
-                    fB = fmaf(s0, fB4.x, s1 * fB4.y);
-                    fP = fmaf(s0, fP4.x, s1 * fP4.y);
+                    fL = fmaf(s0, cLB.x, s1 * cLB.y);
+                    fB = fmaf(s0, cLB.z, s1 * cLB.w);
+                    fP = fmaf(s0, cPs.x, s1 * cPs.y);
                 }
                 const uint32_t kL = __float_as_uint(lL4.w), kB = __float_as_uint(lB4.w);
                 float LcL = 0.f, LcB = 0.f;
@@ -337,10 +360,10 @@ __global__ void __launch_bounds__(32 * ACC_WARPS) k_accumulate(DevScene sc, Rend
                 if ((kB & 15u) == 1u) LcB = __ldg(lt.spectrum + lane);
                 else if ((kB & 15u) == 2u) { IllumCoefs kk; kk.k0 = lB4.x; kk.k1 = lB4.y; kk.k2 = lB4.z; kk.b1 = (kB >> 4) & 15; kk.b2 = (kB >> 8) & 15; LcB = illum_band(tb, kk, lane); }
                 // L += T * Ld * nLights ; T *= f |cos| / pdf   (integrator.cpp:122-163, path.cpp:88-90)
-                const float Ld = fL * LcL * sc4.x + fB * LcB * sc4.y;
+                const float Ld = fL * LcL * cPs.z + fB * LcB * cPs.w;
                 const size_t off = band_off(iv[k], lane);
                 Lg[off] = fmaf(Tv[k], Ld, Lv[k]);
-                float Tn = Tv[k] * (fP * sc4.z);
+                float Tn = Tv[k] * (fP * m4.x);
                 const bool fBlack = !__any_sync(FULL, fP != 0.f);
                 // path.cpp:88-104
                 bool alive = false;
@@ -351,7 +374,7 @@ __global__ void __launch_bounds__(32 * ACC_WARPS) k_accumulate(DevScene sc, Rend
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) yy += __shfl_xor_sync(FULL, yy, o);
                         float continueProbability = stdminf(.5f, yy / tb.yint);
-                        if (sc4.w > continueProbability) alive = false;
+                        if (m4.y > continueProbability) alive = false;
                         else if (bounce != cfg.max_depth) Tn *= 1.f / continueProbability;
                     }
                     if (bounce == cfg.max_depth) alive = false;
@@ -363,6 +386,7 @@ __global__ void __launch_bounds__(32 * ACC_WARPS) k_accumulate(DevScene sc, Rend
         bool alive = active && ((aliveMask >> lane) & 1u);
         if (alive) {
             float4 g3 = wb.g3[i];
+            g0 = wb.g0[i];
             wb.ray_o[i] = g0;
             wb.ray_d[i] = make_float4(g3.x, g3.y, g3.z, SPT_INF);
         }
@@ -483,8 +507,8 @@ __global__ void k_scatter_L(const float *in, uint32_t cap, uint32_t n, float *L)
 // ---- launchers -------------------------------------------------------------------------------------
 static inline unsigned grid1d(uint64_t n, int per, unsigned cap) { uint64_t g = (n + per - 1) / per; return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g)); }
 void spt_launch_compact_hits(int grid, cudaStream_t st, const uint32_t *queue, const uint32_t *count, const uint32_t *hit_slot,
-                             uint32_t *hit_queue, uint32_t *hit_count, uint32_t *miss_queue, uint32_t *miss_count) {
-    k_compact_hits<<<grid, 256, 0, st>>>(queue, count, hit_slot, hit_queue, hit_count, miss_queue, miss_count);
+                             uint32_t *hit_queue, uint32_t *hit_count, uint32_t *miss_queue, uint32_t *miss_count, float *black_L) {
+    k_compact_hits<<<grid, 256, 0, st>>>(queue, count, hit_slot, hit_queue, hit_count, miss_queue, miss_count, black_L);
 }
 void spt_launch_miss_env(int grid, cudaStream_t st, const DevScene &sc, const WaveBuffers &wb, const uint32_t *queue, const uint32_t *count) {
     k_miss_env<<<grid, 128, 0, st>>>(sc, wb, queue, count);

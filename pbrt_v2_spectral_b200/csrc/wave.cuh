@@ -24,8 +24,13 @@ struct WaveBuffers {
     uint32_t *hit_slot; float *hit_t;
     float4 *g0, *g1, *g2, *g3;        // {p, eps}, {shadow d, shadow maxt}, {mis d, inf}, {path d, -}
     uint32_t *mis_slot; float *mis_t; uint32_t *sh_slot;
-    float4 *r0, *r1, *r2, *r3, *r4, *r5;
-    uint4 *r6;
+    // K5 -> K6 record of a path vertex, 48 bytes: the BSDF value of each direction folded to two
+    // wavelength-independent coefficients {a, b}: matte/plastic f[c] = spec0[c]*a + spec1[c]*b, metal
+    // f[c] = a * FrCond(b, eta[c], k[c]).
+    float4 *rec0;                     // {light dir a, b, MIS dir a, b}
+    float4 *rec1;                     // {continuation a, b, sL = |cos| weight / pdf of the light sample, sB likewise for the MIS sample}
+    float4 *rec2;                     // {sP = |cos| / pdf of the continuation, Russian-roulette draw, RF_* flags | light << 12, material | (emitter+1) << 16}
+    float4 *laux;                     // infinite light only: RGB radiance of the sampled direction
     float2 *img_xy;
     float *T, *L;                     // [cap][NB]: band_off()
     uint32_t *pathQ[2], *shadowQ, *misQ;
@@ -48,9 +53,9 @@ struct RenderCfg {
     uint32_t n_samples;               // samples in this wave
 };
 
-// flags in r6.x
+// flags in rec2.z (low 12 bits)
 enum { RF_L = 1, RF_LDELTA = 2, RF_B = 4, RF_P = 8, RF_L_REFL = 16, RF_L_MF = 32, RF_B_REFL = 64, RF_B_MF = 128,
-       RF_P_REFL = 256, RF_P_MF = 512, RF_ON = 1024 };
+       RF_P_REFL = 256, RF_P_MF = 512, RF_ON = 1024, RF_METAL = 2048 };
 
 __device__ __forceinline__ bool wave_pixel(const RenderCfg &cfg, uint64_t j, int *px, int *py) {
     uint32_t tp = (uint32_t)(cfg.tile * cfg.tile);
