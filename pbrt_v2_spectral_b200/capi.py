@@ -10,7 +10,7 @@ import numpy as np
 from . import ctypes_defs as D
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libspt.so")
+LIB_PATH = os.environ.get("SPT_LIB") or os.path.join(HERE, "libspt.so")   # SPT_LIB: A/B builds of the same ABI (profiles/tools)
 
 # every symbol include/spt.h declares (checked by tests/test_abi.py)
 SYMBOLS = [

@@ -96,8 +96,8 @@ struct SptScene {
     std::vector<uint32_t> prim_id_host;
     uint32_t *prim_id_dev = nullptr;
     bool counters_on = false;
-    int trace_variant = 1;           // trace_kernels.cuh: 0 reference nodes, 1 pair nodes (default), 2 node/leaf phases
-    uint32_t leaf_wait = 6;
+    int trace_variant = 1;           // trace_kernels.cuh: 0 reference nodes, 1 pair nodes (default)
+    uint32_t fetch_threshold = 14;
     bool has_env = false;            // an infinite light is present (escaped camera rays pick up Le)
     unsigned long long *counters = nullptr;
     // wave buffers, allocated on first use and reused
@@ -158,7 +158,7 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
     if (d->n_materials > 0xffffu || d->n_lights > 0xfffeu) { g_err = "more than 65535 materials or 65534 lights"; return nullptr; }
     SptScene *s = new SptScene();
     if (const char *e = getenv("SPT_TRACE_VARIANT")) s->trace_variant = atoi(e);
-    if (const char *e = getenv("SPT_LEAF_WAIT")) s->leaf_wait = (uint32_t)atoi(e);
+    if (const char *e = getenv("SPT_FETCH_THRESHOLD")) s->fetch_threshold = (uint32_t)atoi(e);
     DevScene &v = s->dev;
     memset(&v, 0, sizeof(v));
     // nodes: byte-identical copy, plus the hasQuadric bit in the reference's pad byte for leaves
@@ -171,31 +171,38 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
         for (uint32_t i = 0; i < np; ++i)
             if (off + i < d->n_prims && d->prim_kind[off + i] != SPT_PRIM_TRIANGLE) nd[30] = 1;
     }
-    // pair nodes: compact array over the interior nodes of the reference's depth-first layout
+    // pair nodes: compact array over the interior nodes of the reference's depth-first layout. Child
+    // codes pack a leaf's {hasQuadric, nPrims-1, first slot} into one word; a tree that does not fit
+    // (leaves of more than 8 primitives, 2^27 primitives) is walked on the reference layout (variant 0).
     std::vector<float4> pn;
-    uint2 root_code = make_uint2(0, 0);
+    uint32_t root_code = 0xffffffffu;
+    bool pairs_ok = d->n_prims < (1u << 27) - 1u;
     {
         struct RefNode { float b[6]; uint32_t off; uint8_t np, axis, hasq, pad; };
         const RefNode *rn = (const RefNode *)nodes.data();
         std::vector<uint32_t> pidx(d->n_nodes, 0xffffffffu);
         uint32_t nint = 0;
-        for (uint32_t n = 0; n < d->n_nodes; ++n) if (rn[n].np == 0) pidx[n] = nint++;
-        pn.assign((size_t)nint * 4, make_float4(0, 0, 0, 0));
-        auto code = [&](uint32_t c) { return rn[c].np ? rn[c].off : pidx[c]; };
-        auto meta = [&](uint32_t c) { return (uint32_t)rn[c].np | ((uint32_t)(rn[c].hasq ? 1 : 0) << 8); };
-        for (uint32_t n = 0; n < d->n_nodes; ++n) {
-            if (rn[n].np) continue;
-            uint32_t c0 = n + 1, c1 = rn[n].off;
-            if (c0 >= d->n_nodes || c1 >= d->n_nodes) { g_err = "malformed BVH: child index out of range"; delete s; return nullptr; }
-            float4 *q = &pn[(size_t)pidx[n] * 4];
-            const float *a = rn[c0].b, *b = rn[c1].b;
-            q[0] = make_float4(a[0], a[1], a[2], a[3]);
-            q[1] = make_float4(a[4], a[5], b[0], b[1]);
-            q[2] = make_float4(b[2], b[3], b[4], b[5]);
-            uint32_t w[4] = { code(c0), code(c1), (uint32_t)(rn[n].axis & 3) | (meta(c0) << 8) | (meta(c1) << 17), 0u };
-            memcpy(&q[3], w, 16);
-        }
-        if (d->n_nodes) root_code = make_uint2(code(0), meta(0));
+        for (uint32_t n = 0; n < d->n_nodes; ++n) { if (rn[n].np == 0) pidx[n] = nint++; else if (rn[n].np > 8) pairs_ok = false; }
+        if (nint >= 0x80000000u) pairs_ok = false;
+        auto code = [&](uint32_t c) {
+            return rn[c].np ? (0x80000000u | (rn[c].hasq ? 0x40000000u : 0u) | ((uint32_t)(rn[c].np - 1) << 27) | rn[c].off) : pidx[c];
+        };
+        if (pairs_ok) {
+            pn.assign((size_t)nint * 4, make_float4(0, 0, 0, 0));
+            for (uint32_t n = 0; n < d->n_nodes; ++n) {
+                if (rn[n].np) continue;
+                uint32_t c0 = n + 1, c1 = rn[n].off;
+                if (c0 >= d->n_nodes || c1 >= d->n_nodes) { g_err = "malformed BVH: child index out of range"; delete s; return nullptr; }
+                float4 *q = &pn[(size_t)pidx[n] * 4];
+                const float *a = rn[c0].b, *b = rn[c1].b;
+                q[0] = make_float4(a[0], a[1], a[2], a[3]);
+                q[1] = make_float4(a[4], a[5], b[0], b[1]);
+                q[2] = make_float4(b[2], b[3], b[4], b[5]);
+                uint32_t w[4] = { code(c0), code(c1), (uint32_t)(rn[n].axis & 3), 0u };
+                memcpy(&q[3], w, 16);
+            }
+            if (d->n_nodes) root_code = code(0);
+        } else s->trace_variant = 0;
     }
     // pre-gathered triangle vertices per BVH slot
     std::vector<float4> tv((size_t)d->n_prims * 3, make_float4(0, 0, 0, 0));
@@ -358,7 +365,7 @@ template <bool ANY>
 static void launch_trace(SptScene *s, int grid, const uint32_t *queue, const uint32_t *count, uint32_t *work,
                          const float4 *ro, const float4 *rd, uint32_t *out_slot, float *out_t) {
     TraceArgs a; a.queue = queue; a.count = count; a.work = work; a.ro = ro; a.rd = rd; a.out_slot = out_slot; a.out_t = out_t;
-    a.leaf_wait = s->leaf_wait;
+    a.fetch_threshold = s->fetch_threshold;
     spt_launch_trace(ANY, s->trace_variant, s->counters_on, grid, s->stream, s->dev, a);
 }
 

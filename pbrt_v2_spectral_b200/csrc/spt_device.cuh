@@ -83,14 +83,14 @@ struct Hit { float t, rayEpsilon; v3 p, dpdu, dpdv, nn; float u, v; };
 // Scene tables resident in HBM. Layouts:
 //   nodes      2 x float4 per LinearBVHNode, byte-identical to the reference's 32-byte node
 //              (bvh.cpp:105-115): {pMin.xyz, pMax.x} {pMax.yz, offset, nPrims|axis<<8|hasQuadric<<16}
-//   pnodes     64 B per INTERIOR node: child0 min/max, child1 min/max (12 floats), child codes
-//              (pair index, or first BVH slot for a leaf), meta = axis | (nPrims|hasQuadric<<8) << 8 | ... << 17
+//   pnodes     64 B per INTERIOR node: child0 min/max, child1 min/max (12 floats), the two child codes
+//              (pair index, or 1<<31 | hasQuadric<<30 | (nPrims-1)<<27 | first BVH slot for a leaf), split axis
 //   tri_verts  3 x float4 per BVH slot (pre-gathered world-space p1,p2,p3; w unused) so a leaf test
 //              is three 16-byte loads with no index indirection
 struct DevScene {
     const float4 *nodes;
     const float4 *pnodes;            // pair nodes: 4 x float4 per interior node (both children's bounds + codes)
-    uint2 root_code;                 // {pair index | prim offset, nPrims | hasQuadric << 8} of the root
+    uint32_t root_code;              // child code of the root
     const float4 *tri_verts;
     uint32_t n_nodes, n_prims;
     const uint8_t *prim_kind, *prim_flags;

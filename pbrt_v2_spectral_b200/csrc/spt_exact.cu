@@ -79,7 +79,6 @@ void spt_launch_trace(bool any, int variant, bool count, int grid, cudaStream_t 
         if (any) { if (count) K<true, true><<<grid, 128, 0, st>>>(sc, a); else K<true, false><<<grid, 128, 0, st>>>(sc, a); } \
         else { if (count) K<false, true><<<grid, 128, 0, st>>>(sc, a); else K<false, false><<<grid, 128, 0, st>>>(sc, a); } } while (0)
     if (variant == 0) SPT_T(k_trace_v0);
-    else if (variant == 2) SPT_T(k_trace_v2);
     else SPT_T(k_trace_v1);
 #undef SPT_T
 }

@@ -68,7 +68,7 @@ __device__ __forceinline__ float2 dir_coef(int mtype, bool on, const DirTerms &t
     else if (t.mf) { d.x = t.a0 * t.a1 / t.a3; d.y = t.a2; }
     return d;
 }
-__global__ void __launch_bounds__(128) k_shade(DevScene sc, RenderCfg cfg, SampleSource src, WaveBuffers wb, int bounce,
+__global__ void __launch_bounds__(128, 4) k_shade(DevScene sc, RenderCfg cfg, SampleSource src, WaveBuffers wb, int bounce,
                                                const uint32_t *queue, const uint32_t *count,
                                                uint32_t *shadow_count, uint32_t *mis_count) {
     uint32_t n = *count;

@@ -8,6 +8,6 @@ struct TraceArgs {
     const float4 *ro, *rd;      // {o, mint}, {d, maxt}
     uint32_t *out_slot;         // BVH slot of the accepted primitive, SPT_MISS if none
     float *out_t;               // closest hit: ray.maxt after the traversal (NULL for any-hit)
-    uint32_t leaf_wait;         // two-phase variant: leave the node phase when this few lanes still search
+    uint32_t fetch_threshold;   // refill the warp from the queue when fewer lanes than this still traverse
 };
 

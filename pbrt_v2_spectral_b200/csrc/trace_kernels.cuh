@@ -1,9 +1,9 @@
 // trace_kernels.cuh — K2 / K3: BVHAccel::Intersect / IntersectP (src/accelerators/bvh.cpp:380-432,
 // :435-481) as persistent-warp kernels. Every lane owns one ray; idle lanes refill from the
-// device-side queue with one warp-aggregated atomic once fewer than FETCH_THRESHOLD lanes of the
+// device-side queue with one warp-aggregated atomic once fewer than fetch_threshold lanes of the
 // warp are still traversing (incoherent bounce / MIS rays otherwise leave ~8 of 32 lanes busy).
 //
-// All variants visit the reference's nodes in the reference's order (near child first, far child
+// Both variants visit the reference's nodes in the reference's order (near child first, far child
 // from the 64-entry todo stack, leaves in slot order, `t <= maxt` acceptance), with the reference's
 // slab arithmetic (bvh.cpp:118-140) and triangle test (trianglemesh.cpp:119-273): the same
 // primitives are tested in the same order against the same maxt, so ids and t match bit for bit
@@ -12,7 +12,6 @@
 #pragma once
 #include "traverse.cuh"
 
-#define FETCH_THRESHOLD 20
 #define PN_NONE 0xffffffffu
 
 #include "trace_args.h"
@@ -125,7 +124,7 @@ __global__ void __launch_bounds__(128) k_trace_v0(DevScene sc, TraceArgs a) {
                     active = false;
                 } else nodeNum = todo[--todoOffset];
             }
-            if (active && !exhausted && __popc(__activemask()) < FETCH_THRESHOLD) break;
+            if (active && !exhausted && (uint32_t)__popc(__activemask()) < a.fetch_threshold) break;
         }
     }
     if (COUNT && sc.counters && (cn | cp)) {
@@ -134,86 +133,8 @@ __global__ void __launch_bounds__(128) k_trace_v0(DevScene sc, TraceArgs a) {
     }
 }
 
-// ---- variant 2: node phase / leaf phase ----------------------------------------------------------
-// With one loop, an iteration in which ANY lane sits on a leaf runs the ~150-instruction primitive
-// test for the whole warp while ~92 % of the lanes only wanted a ~60-instruction node step. Here
-// the warp alternates between two converged phases: lanes step through nodes until they hold a
-// leaf (then they wait), and once at most `leaf_wait` lanes are still searching, every lane that
-// holds a leaf tests its primitives. A lane stops searching as soon as it holds a leaf, so every
-// primitive test sees the maxt the reference would have at that visit.
-template <bool ANY, bool COUNT>
-__global__ void __launch_bounds__(128) k_trace_v2(DevScene sc, TraceArgs a) {
-    const uint32_t n = *a.count;
-    const int lane = threadIdx.x & 31;
-    const unsigned FULL = 0xffffffffu;
-    uint32_t todo[64];
-    uint32_t sp = 0, cur = PN_NONE, leafOff = 0, leafMeta = 0;      // leafMeta & 0xff = pending primitives
-    LaneRay L; L.ray.o = V(0, 0, 0); L.ray.d = V(0, 0, 1); L.ray.mint = 0.f; L.ray.maxt = 0.f; L.invDir = V(0, 0, 0);
-    L.negx = L.negy = L.negz = false; L.i = 0; L.best = SPT_MISS;
-    bool active = false, exhausted = (n == 0);
-    unsigned long long cn = 0, cp = 0;
-    for (;;) {
-        if (lane_fetch(a, n, lane, active, exhausted, L)) {
-            sp = 0; cur = 0; leafMeta = 0; active = true;
-            if (sc.n_nodes == 0) { a.out_slot[L.i] = SPT_MISS; if (!ANY) a.out_t[L.i] = L.ray.maxt; active = false; }
-        }
-        unsigned act = __ballot_sync(FULL, active);
-        if (!act) break;
-        for (;;) {
-            // ---- node phase
-            for (;;) {
-                bool searching = active && (leafMeta & 0xff) == 0;
-                if (searching) {
-                    if (cur == PN_NONE) {
-                        if (sp == 0) {
-                            a.out_slot[L.i] = L.best;
-                            if (!ANY) a.out_t[L.i] = L.ray.maxt;
-                            active = false; searching = false;
-                        } else cur = todo[--sp];
-                    }
-                    if (searching) {
-                        float4 n0 = __ldg(&sc.nodes[2 * (size_t)cur]);
-                        float4 n1 = __ldg(&sc.nodes[2 * (size_t)cur + 1]);
-                        if (COUNT) ++cn;
-                        if (slab(n0, n1, L.ray, L.invDir, L.negx, L.negy, L.negz)) {
-                            uint32_t meta = __float_as_uint(n1.w);
-                            uint32_t offset = __float_as_uint(n1.z);
-                            if (meta & 0xff) { leafOff = offset; leafMeta = meta; cur = PN_NONE; searching = false; }
-                            else {
-                                uint32_t axis = (meta >> 8) & 0xff;
-                                bool neg = axis == 0 ? L.negx : (axis == 1 ? L.negy : L.negz);
-                                if (neg) { todo[sp++] = cur + 1; cur = offset; }
-                                else { todo[sp++] = offset; cur = cur + 1; }
-                            }
-                        } else cur = PN_NONE;
-                    }
-                }
-                unsigned still = __ballot_sync(FULL, searching);
-                if (!still) break;
-                if ((uint32_t)__popc(still) <= a.leaf_wait && __any_sync(FULL, active && (leafMeta & 0xff))) break;
-            }
-            // ---- leaf phase
-            if (active && (leafMeta & 0xff)) {
-                bool finished = leaf_test<ANY, COUNT>(sc, leafOff, leafMeta & 0xff, (leafMeta >> 16) & 1, L, cp);
-                leafMeta = 0;
-                if (finished) {
-                    a.out_slot[L.i] = L.best;
-                    if (!ANY) a.out_t[L.i] = L.ray.maxt;
-                    active = false;
-                }
-            }
-            unsigned now = __ballot_sync(FULL, active);
-            if (!now) break;
-            if (!exhausted && __popc(now) < FETCH_THRESHOLD) break;
-        }
-    }
-    if (COUNT && sc.counters && (cn | cp)) {
-        atomicAdd(&sc.counters[ANY ? 2 : 0], cn);
-        atomicAdd(&sc.counters[ANY ? 3 : 1], cp);
-    }
-}
-
-// slab test of one child box; returns hit and the clipped tmin (valid when the boxes overlap)
+// slab test of one child box with the reference's literal sequence (bvh.cpp:118-140); returns hit and
+// the clipped tmin (valid when the boxes overlap). x0 = the bound selected by dirIsNeg, x1 the other.
 __device__ __forceinline__ bool slab6(float x0, float x1, float y0, float y1, float z0, float z1, const Ray &ray,
                                       v3 invDir, float *tminOut) {
     float tmin = (x0 - ray.o.x) * invDir.x;
@@ -231,14 +152,6 @@ __device__ __forceinline__ bool slab6(float x0, float x1, float y0, float y1, fl
     *tminOut = tmin;
     return (tmin < ray.maxt) && (tmax > ray.mint);
 }
-
-// ---- variant 1: pair nodes ------------------------------------------------------------------------
-// One 64-byte record per INTERIOR node holds the bounds of both children (built in
-// spt_scene_create): one step fetches four 16-byte words, slab-tests both children and descends.
-// The reference pushes the far child unconditionally and slab-tests it when popped, against the
-// maxt current THEN; of that test only `tmin < maxt` depends on maxt, so the far child is tested
-// at push time, dropped if it already fails, and its tmin is kept on the stack and re-compared with
-// the (possibly shrunk) maxt at pop time - the same decision, bit for bit.
 // The same decision without the sign selects and early outs, for rays whose invDir is finite (no
 // 0 * inf = NaN can occur): per axis near = min(t1, t2), far = max(t1, t2) are exactly the
 // reference's bounds[dirIsNeg] / bounds[1-dirIsNeg] products (rounding is monotonic), its four
@@ -255,38 +168,57 @@ __device__ __forceinline__ bool slab6_finite(float x0, float x1, float y0, float
     return (tmin <= tmax) && (tmin < ray.maxt) && (tmax > ray.mint);
 }
 
+// ---- variant 1: pair nodes ------------------------------------------------------------------------
+// One 64-byte record per INTERIOR node holds the bounds of both children (built in
+// spt_scene_create): one step fetches four 16-byte words, slab-tests both children and descends.
+// A child is one 32-bit code: a pair index, or PN_LEAF | hasQuadric << 30 | (nPrims-1) << 27 | first slot.
+//
+// Closest hit: the reference pushes the far child unconditionally and slab-tests it when popped,
+// against the maxt current THEN; of that test only `tmin < maxt` depends on maxt, so the far child
+// is tested at push time, dropped if it already fails, and its tmin is kept on the stack and
+// re-compared with the (possibly shrunk) maxt at pop time - the same decision, bit for bit.
+// Any hit: maxt never changes during IntersectP, the answer is the OR over the same set of leaves
+// whatever their order, so the stack holds bare codes.
+#define PN_LEAF 0x80000000u
 template <bool ANY, bool COUNT>
 __global__ void __launch_bounds__(128) k_trace_v1(DevScene sc, TraceArgs a) {
     const uint32_t n = *a.count;
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
-    uint2 stk[64];           // {child code, child meta}
-    float stk_t[64];         // tmin of the child's slab test at push time
-    uint32_t sp = 0, cur = PN_NONE;
+    uint2 stk[ANY ? 1 : 64];         // closest: {child code, tmin of the child's slab test at push time}
+    uint32_t stk1[ANY ? 64 : 1];     // any hit: child code
+    uint32_t sp = 0, cur = PN_NONE, negMask = 0;
     LaneRay L; L.ray.o = V(0, 0, 0); L.ray.d = V(0, 0, 1); L.ray.mint = 0.f; L.ray.maxt = 0.f; L.invDir = V(0, 0, 0);
-    L.negx = L.negy = L.negz = false; L.i = 0; L.best = SPT_MISS;
+    L.negx = L.negy = L.negz = false; L.exact = false; L.i = 0; L.best = SPT_MISS;
     bool active = false, exhausted = (n == 0);
     unsigned long long cn = 0, cp = 0;
     for (;;) {
         if (lane_fetch(a, n, lane, active, exhausted, L)) {
             sp = 0; cur = PN_NONE; active = true;
+            negMask = (L.negx ? 1u : 0u) | (L.negy ? 2u : 0u) | (L.negz ? 4u : 0u);
             // the root: the one node whose own box is tested from the reference array
-            bool rootHit = false;
             if (sc.n_nodes) {
                 float4 n0 = __ldg(&sc.nodes[0]), n1 = __ldg(&sc.nodes[1]);
                 if (COUNT) ++cn;
-                rootHit = slab(n0, n1, L.ray, L.invDir, L.negx, L.negy, L.negz);
-            }
-            if (rootHit) {
-                if (sc.root_code.y & 0xff) { stk[0] = sc.root_code; stk_t[0] = -SPT_INF; sp = 1; }   // leaf root
-                else cur = sc.root_code.x;
+                if (slab(n0, n1, L.ray, L.invDir, L.negx, L.negy, L.negz)) cur = sc.root_code;
             }
         }
         if (!__any_sync(FULL, active)) break;
         while (active) {
-            uint2 leaf = make_uint2(0, 0);          // leaf.y & 0xff = nPrims (0: none pending)
             bool done = false;
-            if (cur != PN_NONE) {
+            if (cur == PN_NONE) {                                      // pop
+                if (ANY) {
+                    if (sp == 0) done = true; else cur = stk1[--sp];
+                } else {
+                    for (;;) {
+                        if (sp == 0) { done = true; break; }
+                        uint2 e = stk[--sp];
+                        // the far child's slab test completes here with the current maxt
+                        if (__uint_as_float(e.y) < L.ray.maxt) { cur = e.x; break; }
+                    }
+                }
+            }
+            if (cur < PN_LEAF) {                                        // interior: one pair step
                 const float4 *pn = sc.pnodes + 4 * (size_t)cur;
                 float4 q0 = __ldg(pn), q1 = __ldg(pn + 1), q2 = __ldg(pn + 2), q3 = __ldg(pn + 3);
                 if (COUNT) cn += 2;
@@ -302,43 +234,27 @@ __global__ void __launch_bounds__(128) k_trace_v1(DevScene sc, TraceArgs a) {
                     h1 = slab6(L.negx ? q2.y : q1.z, L.negx ? q1.z : q2.y, L.negy ? q2.z : q1.w, L.negy ? q1.w : q2.z,
                                L.negz ? q2.w : q2.x, L.negz ? q2.x : q2.w, L.ray, L.invDir, &t1);
                 }
-                uint32_t c0 = __float_as_uint(q3.x), c1 = __float_as_uint(q3.y), meta = __float_as_uint(q3.z);
-                uint32_t axis = meta & 3;
-                uint32_t m0 = (meta >> 8) & 0x1ff, m1 = (meta >> 17) & 0x1ff;      // nPrims | hasQuadric << 8
-                bool neg = axis == 0 ? L.negx : (axis == 1 ? L.negy : L.negz);
+                const uint32_t c0 = __float_as_uint(q3.x), c1 = __float_as_uint(q3.y), axis = __float_as_uint(q3.z);
                 // reference: dirIsNeg[axis] ? second child first : first child first
-                bool nearHit = neg ? h1 : h0, farHit = neg ? h0 : h1;
-                uint32_t nearC = neg ? c1 : c0, farC = neg ? c0 : c1;
-                uint32_t nearM = neg ? m1 : m0, farM = neg ? m0 : m1;
-                float farT = neg ? t0 : t1;
-                if (farHit) { stk[sp] = make_uint2(farC, farM); stk_t[sp] = farT; ++sp; }
+                const bool swap = (negMask >> axis) & 1u;
+                const uint32_t nearC = swap ? c1 : c0, farC = swap ? c0 : c1;
+                const bool nearHit = swap ? h1 : h0, farHit = swap ? h0 : h1;
+                if (farHit) {
+                    if (ANY) stk1[sp++] = farC;
+                    else stk[sp++] = make_uint2(farC, __float_as_uint(swap ? t0 : t1));
+                }
+                cur = nearHit ? nearC : PN_NONE;
+            }
+            if (cur >= PN_LEAF && cur != PN_NONE) {                     // leaf: its primitives in slot order
+                if (leaf_test<ANY, COUNT>(sc, cur & 0x07ffffffu, ((cur >> 27) & 7u) + 1u, (cur >> 30) & 1u, L, cp)) done = true;
                 cur = PN_NONE;
-                if (nearHit) {
-                    if (nearM & 0xff) leaf = make_uint2(nearC, nearM);
-                    else cur = nearC;
-                }
-            }
-            if (cur == PN_NONE && (leaf.y & 0xff) == 0) {
-                // pop: the far child's slab test completes here with the current maxt
-                for (;;) {
-                    if (sp == 0) { done = true; break; }
-                    --sp;
-                    if (stk_t[sp] < L.ray.maxt) {
-                        uint2 e = stk[sp];
-                        if (e.y & 0xff) leaf = e; else cur = e.x;
-                        break;
-                    }
-                }
-            }
-            if (leaf.y & 0xff) {
-                if (leaf_test<ANY, COUNT>(sc, leaf.x, leaf.y & 0xff, (leaf.y >> 8) & 1, L, cp)) done = true;
             }
             if (done) {
                 a.out_slot[L.i] = L.best;
                 if (!ANY) a.out_t[L.i] = L.ray.maxt;
                 active = false;
             }
-            if (active && !exhausted && __popc(__activemask()) < FETCH_THRESHOLD) break;
+            if (active && !exhausted && (uint32_t)__popc(__activemask()) < a.fetch_threshold) break;
         }
     }
     if (COUNT && sc.counters && (cn | cp)) {
