@@ -566,8 +566,8 @@ int spt_shade_samples(SptScene *s, const SptCameraDesc *cam, int32_t max_depth, 
     if (!dsmp || !dout || (rng && n_rng > 0 && !drng)) { m.release(); return fail(SPT_ERR_CUDA, "device allocation failed"); }
     RenderCfg cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.cam = *cam; cfg.spp = 1; cfg.max_depth = max_depth; cfg.n_samples = (uint32_t)n;
-    cfg.tile = 1; cfg.tilesX = 1; cfg.tilesY = 1; cfg.nranks = 1;
+    cfg.cam = *cam; cfg.spp = 1; cfg.spp_shift = 0; cfg.max_depth = max_depth; cfg.n_samples = (uint32_t)n;
+    cfg.tile = 1; cfg.tile_shift = 0; cfg.tilesX = 1; cfg.tilesY = 1; cfg.nranks = 1;
     SampleSource src; src.smp = dsmp; src.rng = drng; src.n_rng = drng ? n_rng : 0; src.seed = 0; src.spp = 1;
     size_t nc = (size_t)(max_depth + 2) * 8;
     cudaMemsetAsync(s->counts, 0, nc * 4, s->stream);
@@ -700,6 +700,7 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
     RenderCfg cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.cam = *cam; cfg.spp = rp->spp; cfg.max_depth = rp->max_depth;
+    for (cfg.spp_shift = 0; (1 << cfg.spp_shift) < cfg.spp; ++cfg.spp_shift) {}
     cfg.x0 = rp->x_start; cfg.y0 = rp->y_start; cfg.x1 = rp->x_end; cfg.y1 = rp->y_end;
     const SptFilmDesc &fd = film->desc;
     if (rp->skip_border) {
@@ -708,6 +709,8 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
     }
     if (cfg.x1 <= cfg.x0 || cfg.y1 <= cfg.y0) return fail(SPT_ERR_ARG, "empty sample extent");
     cfg.tile = rp->tile_size > 0 ? rp->tile_size : 32;
+    if (cfg.tile & (cfg.tile - 1)) return fail(SPT_ERR_ARG, "tile_size must be a power of two");
+    for (cfg.tile_shift = 0; (1 << cfg.tile_shift) < cfg.tile; ++cfg.tile_shift) {}
     cfg.tilesX = (cfg.x1 - cfg.x0 + cfg.tile - 1) / cfg.tile;
     cfg.tilesY = (cfg.y1 - cfg.y0 + cfg.tile - 1) / cfg.tile;
     cfg.rank = rp->tile_rank; cfg.nranks = nranks;

@@ -17,8 +17,8 @@ __global__ void __launch_bounds__(256) k_gen_camera(RenderCfg cfg, SampleSource 
             ix = s[0]; iy = s[1]; lu = s[2]; lv = s[3];
         } else {
             int px, py;
-            uint32_t s = i % (uint32_t)cfg.spp;
-            valid = wave_pixel(cfg, cfg.pixel_base + i / (uint32_t)cfg.spp, &px, &py);
+            uint32_t s = i & ((uint32_t)cfg.spp - 1u);                       // spp is a power of two (LDSampler rounds up)
+            valid = wave_pixel(cfg, cfg.pixel_base + (i >> cfg.spp_shift), &px, &py);
             if (valid) {
                 uint32_t pk = pixel_key(src.seed, pix_key(px, py));
                 float t2[2];

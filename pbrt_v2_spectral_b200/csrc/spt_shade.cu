@@ -98,11 +98,11 @@ __global__ void __launch_bounds__(128, 4) k_shade(DevScene sc, RenderCfg cfg, Sa
                 v3 p = hit.p, n_s = bsdf.nn, woW = vneg(ray.d);
                 v3 wo = w2l(bsdf, woW);
                 float eps = hit.rayEpsilon;
-                uint32_t s_idx = src.smp ? 0u : (i % (uint32_t)cfg.spp);
+                uint32_t s_idx = src.smp ? 0u : (i & ((uint32_t)cfg.spp - 1u));
                 uint32_t pk = 0;
                 if (!src.smp) {
                     int px, py;
-                    wave_pixel(cfg, cfg.pixel_base + i / (uint32_t)cfg.spp, &px, &py);
+                    wave_pixel(cfg, cfg.pixel_base + (i >> cfg.spp_shift), &px, &py);
                     pk = pixel_key(src.seed, pix_key(px, py));
                 }
                 float u[10], rr;
@@ -254,6 +254,7 @@ __global__ void __launch_bounds__(32 * ACC_WARPS) k_accumulate(DevScene sc, Rend
     const unsigned FULL = 0xffffffffu;
     const float cieY = tb.cie_y[lane];
     const float nL = (float)sc.n_lights;
+    const float light0 = sc.n_lights ? sc.lights[0].spectrum[lane] : 0.f;    // most scenes: the one light's row, read once
     const uint32_t nwarps = gridDim.x * ACC_WARPS;
     for (uint32_t base = (blockIdx.x * ACC_WARPS + warp) * 32u; base < n; base += nwarps * 32u) {
         // ---- phase A
@@ -308,7 +309,8 @@ __global__ void __launch_bounds__(32 * ACC_WARPS) k_accumulate(DevScene sc, Rend
             stage[lane][0] = make_float4(cL.x, cL.y, cB.x, cB.y);
             stage[lane][1] = make_float4(cP.x, cP.y, sL, sB);
             stage[lane][2] = make_float4(haveP ? c2.x : 0.f, c2.y, __uint_as_float(i),
-                                         __uint_as_float((haveP ? 1u : 0u) | (metal ? 2u : 0u) | (uint32_t)lightIdx << 2));
+                                         __uint_as_float((haveP ? 1u : 0u) | (metal ? 2u : 0u) | (lbL.kind == 2 ? 4u : 0u) |
+                                                         (lbB.kind == 2 ? 8u : 0u) | (uint32_t)lightIdx << 4));
             stage[lane][3] = make_float4(lbL.k.k0, lbL.k.k1, lbL.k.k2, __uint_as_float((uint32_t)lbL.kind | (uint32_t)lbL.k.b1 << 4 | (uint32_t)lbL.k.b2 << 8));
             stage[lane][4] = make_float4(lbB.k.k0, lbB.k.k1, lbB.k.k2, __uint_as_float((uint32_t)lbB.kind | (uint32_t)lbB.k.b1 << 4 | (uint32_t)lbB.k.b2 << 8));
             stage[lane][5] = make_float4(__uint_as_float(bits1 & 0xffffu), __uint_as_float(bits1 >> 16), 0.f, 0.f);
@@ -329,7 +331,7 @@ __global__ void __launch_bounds__(32 * ACC_WARPS) k_accumulate(DevScene sc, Rend
                     // the path starts here: T = 1, L = what the first vertex emits towards the camera (path.cpp:55-56)
                     uint32_t emit = __float_as_uint(stage[v][5].y);
                     Tv[k] = 1.f;
-                    Lv[k] = emit ? __ldg(sc.lights[emit - 1].spectrum + lane) : 0.f;
+                    Lv[k] = emit == 0 ? 0.f : (emit == 1 ? light0 : __ldg(sc.lights[emit - 1].spectrum + lane));
                 } else { Tv[k] = Tg[off]; Lv[k] = Lg[off]; }
             }
 #pragma unroll
@@ -337,10 +339,9 @@ __global__ void __launch_bounds__(32 * ACC_WARPS) k_accumulate(DevScene sc, Rend
                 const uint32_t v = v0 + k;
                 if (v >= cnt) break;
                 const float4 cLB = stage[v][0], cPs = stage[v][1], m4 = stage[v][2];
-                const float4 lL4 = stage[v][3], lB4 = stage[v][4];
                 const uint32_t misc = __float_as_uint(m4.w);
+                const uint32_t lightIdx = misc >> 4;
                 const SptMaterial &m = sc.materials[__float_as_uint(stage[v][5].x)];
-                const SptLight &lt = sc.lights[misc >> 2];
                 const bool haveP = misc & 1u, metal = (misc & 2u) != 0;
                 const float s0 = __ldg(m.spec0 + lane), s1 = __ldg(m.spec1 + lane);
                 float fL, fB, fP;
@@ -353,12 +354,18 @@ __global__ void __launch_bounds__(32 * ACC_WARPS) k_accumulate(DevScene sc, Rend
                     fB = fmaf(s0, cLB.z, s1 * cLB.w);
                     fP = fmaf(s0, cPs.x, s1 * cPs.y);
                 }
-                const uint32_t kL = __float_as_uint(lL4.w), kB = __float_as_uint(lB4.w);
+                // radiance arriving along the light / MIS direction: the light's table row, or (misc bits 2,3:
+                // infinite light) an RGB illuminant rebuilt from the staged coefficients
                 float LcL = 0.f, LcB = 0.f;
-                if ((kL & 15u) == 1u) LcL = __ldg(lt.spectrum + lane);
-                else if ((kL & 15u) == 2u) { IllumCoefs kk; kk.k0 = lL4.x; kk.k1 = lL4.y; kk.k2 = lL4.z; kk.b1 = (kL >> 4) & 15; kk.b2 = (kL >> 8) & 15; LcL = illum_band(tb, kk, lane); }
-                if ((kB & 15u) == 1u) LcB = __ldg(lt.spectrum + lane);
-                else if ((kB & 15u) == 2u) { IllumCoefs kk; kk.k0 = lB4.x; kk.k1 = lB4.y; kk.k2 = lB4.z; kk.b1 = (kB >> 4) & 15; kk.b2 = (kB >> 8) & 15; LcB = illum_band(tb, kk, lane); }
+                if (misc & 12u) {
+                    const float4 lL4 = stage[v][3], lB4 = stage[v][4];
+                    const uint32_t kL = __float_as_uint(lL4.w), kB = __float_as_uint(lB4.w);
+                    if ((kL & 15u) == 2u) { IllumCoefs kk; kk.k0 = lL4.x; kk.k1 = lL4.y; kk.k2 = lL4.z; kk.b1 = (kL >> 4) & 15; kk.b2 = (kL >> 8) & 15; LcL = illum_band(tb, kk, lane); }
+                    if ((kB & 15u) == 2u) { IllumCoefs kk; kk.k0 = lB4.x; kk.k1 = lB4.y; kk.k2 = lB4.z; kk.b1 = (kB >> 4) & 15; kk.b2 = (kB >> 8) & 15; LcB = illum_band(tb, kk, lane); }
+                } else {
+                    // a direction without a light term has zero coefficients / scale, so the row can be applied unconditionally
+                    LcL = LcB = lightIdx == 0 ? light0 : __ldg(sc.lights[lightIdx].spectrum + lane);
+                }
                 // L += T * Ld * nLights ; T *= f |cos| / pdf   (integrator.cpp:122-163, path.cpp:88-90)
                 const float Ld = fL * LcL * cPs.z + fB * LcB * cPs.w;
                 const size_t off = band_off(iv[k], lane);
@@ -402,7 +409,11 @@ __global__ void __launch_bounds__(32 * ACC_WARPS) k_accumulate(DevScene sc, Rend
 // exactly the warp's own pixel (all of them under the box filter, up to rounding onto a pixel edge)
 // accumulate in a register per band and are flushed with one atomic per band per pixel; any other
 // footprint (wide filters) goes to global atomics, one coalesced 32-band atomic row per touched pixel.
+// Samples are handled eight at a time: their rows are loaded together; lanes 0-7 each work out one
+// sample's filter footprint; the eight y(L) sums share one butterfly (9 shuffles instead of 40: after
+// exchanging over lane bits 4, 3, 2 each group of four lanes owns one sample, bits 1, 0 finish it).
 #define FILM_GROUP 8
+__device__ __forceinline__ int film_y_lane(int k) { return ((k & 1) << 4) | ((k & 2) << 2) | (k & 4); }   // a lane that ends up holding y of sample k
 __global__ void __launch_bounds__(256) k_film_add(FilmView film, const SptSpectralTables *tables, const float2 *img_xy,
                                                   const float *L, uint32_t cap, uint32_t n_samples, int spp) {
     const SptSpectralTables &tb = *tables;
@@ -423,49 +434,84 @@ __global__ void __launch_bounds__(256) k_film_add(FilmView film, const SptSpectr
         const bool mainInside = mainx >= xs && mainx <= xe && mainy >= ys && mainy <= ye;
         float acc = 0.f, wsum = 0.f;
         for (uint32_t s0 = 0; s0 < ns; s0 += FILM_GROUP) {
-            float2 xyv[FILM_GROUP]; float Lv[FILM_GROUP];
+            float Lv[FILM_GROUP];
+#pragma unroll
+            for (int k = 0; k < FILM_GROUP; ++k) Lv[k] = L[band_off(first + min(s0 + k, ns - 1), lane)];
+            // ---- footprint of sample s0 + lane (lanes 0-7): 0 nothing to add, 1 exactly the warp's pixel, 2 anything else
+            int kind = 0;
+            float wt = 0.f;
+            if (lane < FILM_GROUP && s0 + lane < ns) {
+                const float2 xy = img_xy[first + s0 + lane];
+                if (xy.x > -1e29f) {                                    // else: sample outside this rank's tile set
+                    const float dimageX = xy.x - 0.5f, dimageY = xy.y - 0.5f;
+                    int x0 = (int)ceilf(dimageX - fd.filter_xwidth), x1 = (int)floorf(dimageX + fd.filter_xwidth);
+                    int y0 = (int)ceilf(dimageY - fd.filter_ywidth), y1 = (int)floorf(dimageY + fd.filter_ywidth);
+                    x0 = max(x0, xs); x1 = min(x1, xe); y0 = max(y0, ys); y1 = min(y1, ye);
+                    if ((x1 - x0) >= 0 && (y1 - y0) >= 0) {
+                        if (mainInside && x0 == x1 && y0 == y1 && x0 == mainx && y0 == mainy) {
+                            float fx = fabsf((x0 - dimageX) * fd.filter_inv_xwidth * 16);
+                            float fy = fabsf((y0 - dimageY) * fd.filter_inv_ywidth * 16);
+                            int ix = min((int)floorf(fx), 15), iy = min((int)floorf(fy), 15);
+                            wt = film.table[iy * 16 + ix];
+                            kind = 1;
+                        } else kind = 2;
+                    }
+                }
+            }
+            const unsigned fastMask = __ballot_sync(FULL, kind == 1), slowMask = __ballot_sync(FULL, kind == 2);
+            // ---- radiance guards (samplerrenderer.cpp:119-133): NaN anywhere, y < -1e-5, y infinite -> black
+            unsigned nanBits = 0;
+            float y[FILM_GROUP];
 #pragma unroll
             for (int k = 0; k < FILM_GROUP; ++k) {
-                uint32_t i = first + min(s0 + k, ns - 1);
-                xyv[k] = img_xy[i];
-                Lv[k] = L[band_off(i, lane)];
+                if (__any_sync(FULL, isnan(Lv[k]))) nanBits |= 1u << k;
+                y[k] = cieY * Lv[k];
+            }
+            float z[4], w2[2], yy;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {                               // lane bit 4 picks sample 2j or 2j+1
+                float send = (lane & 16) ? y[2 * j] : y[2 * j + 1];
+                float keep = (lane & 16) ? y[2 * j + 1] : y[2 * j];
+                z[j] = keep + __shfl_xor_sync(FULL, send, 16);
             }
 #pragma unroll
-            for (int k = 0; k < FILM_GROUP; ++k) {
-                if (s0 + k >= ns) break;
-                const float2 xy = xyv[k];
-                if (!(xy.x > -1e29f)) continue;                         // sample outside this rank's tile set
-                float v = Lv[k];
-                bool bad = __any_sync(FULL, isnan(v));
-                float y = cieY * v;
+            for (int j = 0; j < 2; ++j) {                               // lane bit 3 picks pair 2j or 2j+1
+                float send = (lane & 8) ? z[2 * j] : z[2 * j + 1];
+                float keep = (lane & 8) ? z[2 * j + 1] : z[2 * j];
+                w2[j] = keep + __shfl_xor_sync(FULL, send, 8);
+            }
+            {
+                float send = (lane & 4) ? w2[0] : w2[1];
+                float keep = (lane & 4) ? w2[1] : w2[0];
+                yy = keep + __shfl_xor_sync(FULL, send, 4);
+            }
+            yy += __shfl_xor_sync(FULL, yy, 2);
+            yy += __shfl_xor_sync(FULL, yy, 1);
+            yy = yy / yint;
+            const unsigned yBad = __ballot_sync(FULL, (double)yy < -1e-5 || isinf(yy));
+            // ---- accumulate
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) y += __shfl_xor_sync(FULL, y, o);
-                y = y / yint;
-                if ((double)y < -1e-5 || isinf(y)) bad = true;
-                if (bad) v = 0.f;
-                const float dimageX = xy.x - 0.5f, dimageY = xy.y - 0.5f;
-                int x0 = (int)ceilf(dimageX - fd.filter_xwidth), x1 = (int)floorf(dimageX + fd.filter_xwidth);
-                int y0 = (int)ceilf(dimageY - fd.filter_ywidth), y1 = (int)floorf(dimageY + fd.filter_ywidth);
-                x0 = max(x0, xs); x1 = min(x1, xe); y0 = max(y0, ys); y1 = min(y1, ye);
-                if ((x1 - x0) < 0 || (y1 - y0) < 0) continue;
-                if (mainInside && x0 == x1 && y0 == y1 && x0 == mainx && y0 == mainy) {
-                    float fx = fabsf((x0 - dimageX) * fd.filter_inv_xwidth * 16);
-                    float fy = fabsf((y0 - dimageY) * fd.filter_inv_ywidth * 16);
-                    int ix = min((int)floorf(fx), 15), iy = min((int)floorf(fy), 15);
-                    float wt = film.table[iy * 16 + ix];
-                    acc += wt * v;
-                    wsum += wt;
-                } else {
-                    for (int yy = y0; yy <= y1; ++yy) {
-                        float fy = fabsf((yy - dimageY) * fd.filter_inv_ywidth * 16);
+            for (int k = 0; k < FILM_GROUP; ++k) {
+                const bool bad = ((nanBits >> k) & 1u) || ((yBad >> film_y_lane(k)) & 1u);
+                const float v = bad ? 0.f : Lv[k];
+                const float w = __shfl_sync(FULL, wt, k);
+                if ((fastMask >> k) & 1u) { acc += w * v; wsum += w; }
+                else if ((slowMask >> k) & 1u) {
+                    const float2 xy = img_xy[first + s0 + k];
+                    const float dimageX = xy.x - 0.5f, dimageY = xy.y - 0.5f;
+                    int x0 = (int)ceilf(dimageX - fd.filter_xwidth), x1 = (int)floorf(dimageX + fd.filter_xwidth);
+                    int y0 = (int)ceilf(dimageY - fd.filter_ywidth), y1 = (int)floorf(dimageY + fd.filter_ywidth);
+                    x0 = max(x0, xs); x1 = min(x1, xe); y0 = max(y0, ys); y1 = min(y1, ye);
+                    for (int py = y0; py <= y1; ++py) {
+                        float fy = fabsf((py - dimageY) * fd.filter_inv_ywidth * 16);
                         int iy = min((int)floorf(fy), 15);
-                        for (int xx = x0; xx <= x1; ++xx) {
-                            float fx = fabsf((xx - dimageX) * fd.filter_inv_xwidth * 16);
+                        for (int px = x0; px <= x1; ++px) {
+                            float fx = fabsf((px - dimageX) * fd.filter_inv_xwidth * 16);
                             int ix = min((int)floorf(fx), 15);
-                            float wt = film.table[iy * 16 + ix];
-                            float *dst = film.pix + ((size_t)(yy - ys) * fd.x_pixel_count + (xx - xs)) * (NB + 1);
-                            atomicAdd(dst + lane, wt * v);
-                            if (lane == 0) atomicAdd(dst + NB, wt);
+                            float wpx = film.table[iy * 16 + ix];
+                            float *dst = film.pix + ((size_t)(py - ys) * fd.x_pixel_count + (px - xs)) * (NB + 1);
+                            atomicAdd(dst + lane, wpx * v);
+                            if (lane == 0) atomicAdd(dst + NB, wpx);
                         }
                     }
                 }

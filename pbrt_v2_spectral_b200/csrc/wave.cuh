@@ -45,9 +45,9 @@ __device__ __forceinline__ size_t band_off(uint32_t i, int c) { return (size_t)i
 
 struct RenderCfg {
     SptCameraDesc cam;
-    int spp, max_depth;
+    int spp, spp_shift, max_depth;       // spp = 1 << spp_shift
     int x0, x1, y0, y1;               // sample extent (x1,y1 exclusive, already border-trimmed)
-    int tile, tilesX, tilesY, rank, nranks;
+    int tile, tile_shift, tilesX, tilesY, rank, nranks;
     uint32_t seed;
     uint64_t pixel_base;              // first rank-local pixel of this wave
     uint32_t n_samples;               // samples in this wave
@@ -57,15 +57,17 @@ struct RenderCfg {
 enum { RF_L = 1, RF_LDELTA = 2, RF_B = 4, RF_P = 8, RF_L_REFL = 16, RF_L_MF = 32, RF_B_REFL = 64, RF_B_MF = 128,
        RF_P_REFL = 256, RF_P_MF = 512, RF_ON = 1024, RF_METAL = 2048 };
 
+// j-th pixel of this rank's tile set -> raster coordinates. Tiles are square with a power-of-two side
+// (tile_shift = log2), dealt round-robin to ranks; 32-bit arithmetic (spt_render bounds the counts).
 __device__ __forceinline__ bool wave_pixel(const RenderCfg &cfg, uint64_t j, int *px, int *py) {
-    uint32_t tp = (uint32_t)(cfg.tile * cfg.tile);
-    uint64_t lt = j / tp;
-    uint32_t w = (uint32_t)(j % tp);
-    uint64_t tile = lt * (uint64_t)cfg.nranks + (uint64_t)cfg.rank;
-    if (tile >= (uint64_t)cfg.tilesX * cfg.tilesY) return false;
-    int tx = (int)(tile % cfg.tilesX), ty = (int)(tile / cfg.tilesX);
-    *px = cfg.x0 + tx * cfg.tile + (int)(w % cfg.tile);
-    *py = cfg.y0 + ty * cfg.tile + (int)(w / cfg.tile);
+    const uint32_t ts = (uint32_t)cfg.tile_shift;
+    uint32_t lt = (uint32_t)(j >> (2 * ts));
+    uint32_t w = (uint32_t)j & ((1u << (2 * ts)) - 1u);
+    uint32_t tile = lt * (uint32_t)cfg.nranks + (uint32_t)cfg.rank;
+    if (tile >= (uint32_t)(cfg.tilesX * cfg.tilesY)) return false;
+    uint32_t ty = tile / (uint32_t)cfg.tilesX, tx = tile - ty * (uint32_t)cfg.tilesX;
+    *px = cfg.x0 + (int)(tx << ts) + (int)(w & ((1u << ts) - 1u));
+    *py = cfg.y0 + (int)(ty << ts) + (int)(w >> ts);
     return *px < cfg.x1 && *py < cfg.y1;
 }
 __device__ __forceinline__ uint32_t pix_key(int px, int py) { return ((uint32_t)py << 16) ^ (uint32_t)px; }
