@@ -145,7 +145,7 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -155,6 +155,8 @@ def main():
         run_reference_arm(args)
         return
 
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"        # keep stdout to the one JSON line
     import numpy as np
     import torch
     from pbrt_v2_spectral_b200 import capi, ctypes_defs as D
@@ -221,6 +223,8 @@ def main():
     class_ms = [0.0] * D.K_CLASSES
     class_launches = [0] * D.K_CLASSES
     class_rays = [0] * D.K_CLASSES
+    elided = 0
+    first_vertices = 0
     render_ms = 0.0
     e0.record()
     for _ in range(args.steps):
@@ -230,6 +234,8 @@ def main():
             dist.reduce(film_t, dst=0)               # film gather over NVLink
         st = scene.stats()
         render_ms += st["render_ms"]
+        elided += st["mis_rays_elided"]
+        first_vertices += st["first_vertices"]
         for k in range(D.K_CLASSES):
             class_ms[k] += st["class_ms"][k]; class_launches[k] += st["class_launches"][k]; class_rays[k] += st["class_rays"][k]
     e1.record()
@@ -287,38 +293,47 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel class (algorithmic bytes: SURVEY.md 8d)
+    # ---- rooflines (algorithmic bytes per unit: SURVEY.md 8d for rays, DESIGN.md 3 for the other kernels)
     peak, peak_src = read_peaks()
-    dom = max(range(D.K_CLASSES), key=lambda k: class_ms[k])
-    def ray_bytes(k):
-        if k in (D.K_TRACE_PATH, D.K_TRACE_MIS):
-            return 32.0 * nodes_per_closest + 48.0 * prims_per_closest + 40.0
-        if k == D.K_TRACE_SHADOW:
-            return 32.0 * nodes_per_any + 48.0 * prims_per_any + 40.0
-        return None
-    # trace classes are the roofline subject; if a shading class ever dominates, report the trace class with most time
-    if ray_bytes(dom) is None:
-        dom = max((D.K_TRACE_PATH, D.K_TRACE_SHADOW, D.K_TRACE_MIS), key=lambda k: class_ms[k])
-    bytes_total = ray_bytes(dom) * class_rays[dom]
-    dom_ms = class_ms[dom]
-    achieved = bytes_total / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
-    traffic = None
+    traffic_all = {}
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(D.K_NAMES[dom])
+            traffic_all = json.load(open(tp))
         except Exception:
-            traffic = None
+            traffic_all = {}
+    closest_bytes = 32.0 * nodes_per_closest + 48.0 * prims_per_closest + 40.0
+    any_bytes = 32.0 * nodes_per_any + 48.0 * prims_per_any + 40.0
+    v_all, v_first = class_rays[D.K_ACCUMULATE], first_vertices
+    unit_bytes = {                                   # class -> (unit, algorithmic bytes moved by the class over the timed steps)
+        D.K_GEN: ("camera sample", 44.0 * class_rays[D.K_GEN]),
+        D.K_TRACE_PATH: ("ray", closest_bytes * class_rays[D.K_TRACE_PATH]),
+        D.K_TRACE_MIS: ("ray", closest_bytes * class_rays[D.K_TRACE_MIS]),
+        D.K_TRACE_SHADOW: ("ray", any_bytes * class_rays[D.K_TRACE_SHADOW]),
+        D.K_SHADE: ("path vertex", 250.0 * class_rays[D.K_SHADE]),
+        D.K_ACCUMULATE: ("path vertex", 380.0 * v_first + 636.0 * max(v_all - v_first, 0)),
+        D.K_FILM: ("camera sample", 136.0 * class_rays[D.K_FILM] + 132.0 * class_rays[D.K_FILM] / max(rp.spp, 1)),
+    }
     total_class = sum(class_ms)
-    roofline = {
-        "bound": "hbm", "kernel": "k_trace (%s)" % D.K_NAMES[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-        "bytes_per_ray": ray_bytes(dom), "rays_per_launch": class_rays[dom] / max(class_launches[dom], 1),
-        "avg_launch_ms": dom_ms / max(class_launches[dom], 1), "share_of_step": dom_ms / total_class if total_class else None,
+    def roof(k):
+        ms = class_ms[k]
+        unit, nbytes = unit_bytes[k]
+        ach = nbytes / (ms / 1e3) / 1e9 if ms > 0 else 0.0
+        return {"bound": "hbm", "kernel": D.K_KERNELS[k] + " (" + D.K_NAMES[k] + ")", "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": ach / peak, "traffic": traffic_all.get(D.K_NAMES[k]), "peak_source": peak_src,
+                "bytes_per_unit": nbytes / max(class_rays[k], 1), "unit_of_work": unit,
+                "units_per_launch": class_rays[k] / max(class_launches[k], 1),
+                "avg_launch_ms": ms / max(class_launches[k], 1), "share_of_step": ms / total_class if total_class else None}
+    dom = max((k for k in unit_bytes if class_launches[k]), key=lambda k: class_ms[k])
+    roofline = roof(dom)
+    roofline.update({
         "nodes_per_closest_ray": nodes_per_closest, "prim_tests_per_closest_ray": prims_per_closest,
         "nodes_per_shadow_ray": nodes_per_any, "prim_tests_per_shadow_ray": prims_per_any,
-        "note": "BVH (4 MB) is L2-resident on this workload: the fraction is of the HBM copy peak, the bound in practice is L2/latency",
-    }
+        "note": "k_shade is FP32/FP64/INT instruction-issue bound (ncu: issue slots 41 % busy at 16 warps/SM, DRAM 7 %), the traversal "
+                "kernels walk a 4 MB BVH that stays in L2/L1 (DRAM traffic = ray I/O): for both the HBM fraction is indicative only; "
+                "k_accumulate is the HBM-streaming kernel. Per-kernel lines in roofline_by_kernel; traffic from profiles/traffic.json "
+                "(ncu --set full, mean of the captured launches)"})
+    roofline_by_kernel = {D.K_NAMES[k]: roof(k) for k in unit_bytes if class_launches[k]}
     rays_total = class_rays[D.K_TRACE_PATH] + class_rays[D.K_TRACE_MIS] + class_rays[D.K_TRACE_SHADOW]
     out = {
         "metric": "Msamples/sec (32-band spectral path trace)", "value": value, "unit": "Msamples/s",
@@ -330,12 +345,16 @@ def main():
                    "l2": "per-step wave state (>2 GB) and film are larger than L2; no explicit flush"},
         "mrays_per_s": rays_total / args.steps / (ms_per_step / 1e3) / 1e6 if world == 1 else None,
         "rays_per_sample": rays_total / args.steps / (n_samples_total / world) if world else None,
+        "rays_per_sample_reference": (rays_total + elided) / args.steps / (n_samples_total / world) if world else None,
+        "rays_note": "rays_per_sample counts rays traced; the reference also traces the BSDF-sampled MIS rays of EstimateDirect that cannot "
+                     "reach the sampled sphere light (contribution exactly zero) - counted in rays_per_sample_reference, not traced here",
         "kernel_ms_per_step": {D.K_NAMES[k]: class_ms[k] / args.steps for k in range(D.K_CLASSES) if class_launches[k]},
         "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": scene_bytes, "d2h_bytes_per_step": film_bytes,
                 "ms_per_step": e2e_s * 1e3, "path": "spt_scene_create+spt_film_create+spt_render+spt_film_download, host buffers (film read into page-locked host memory)",
                 "image_checksum": e2e_checksum},
         "gpu_launches": launches,
         "roofline": roofline,
+        "roofline_by_kernel": roofline_by_kernel,
         "clocks": sampler.summary() if sampler else None,
         "image_checksum": image_sum,
     }

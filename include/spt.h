@@ -192,6 +192,11 @@ typedef struct SptStats {
     double   class_ms[SPT_K_CLASSES];        /* last spt_render: device time per kernel class */
     uint64_t class_launches[SPT_K_CLASSES];  /* last spt_render: launches per kernel class */
     uint64_t class_rays[SPT_K_CLASSES];      /* last spt_render: rays (or paths) processed per class */
+    /* last spt_render: BSDF-sampled MIS rays of EstimateDirect (src/core/integrator.cpp:139-163) that were
+     * NOT traced because they miss every shape of the sampled area light, so their contribution is exactly
+     * zero; the reference traces them (they are counted in its rays/sample figure) */
+    uint64_t mis_rays_elided;
+    uint64_t first_vertices;        /* last spt_render: camera rays that found a surface (path vertices of bounce 0) */
 } SptStats;
 
 typedef struct SptScene SptScene;

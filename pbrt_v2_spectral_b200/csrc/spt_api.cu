@@ -317,9 +317,13 @@ int spt_get_stats(SptScene *s, SptStats *out) {
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------------
+// Device-side counters of one bounce: {path rays, shadow rays, MIS rays traced, hits, 3 x trace work
+// cursors, escaped camera rays, MIS rays elided (could not reach the light), -}
+#define SPT_ROW 16
+
 static int ensure_wave(SptScene *s, uint32_t cap, int max_depth, size_t n_waves) {
     cap = (cap + 31u) & ~31u;            // band_off() tiles 32 paths
-    size_t need_counts = n_waves * (size_t)(max_depth + 2) * 8;
+    size_t need_counts = n_waves * (size_t)(max_depth + 2) * SPT_ROW;
     if (s->wb.cap < cap) {
         int dev = 0; cudaGetDevice(&dev);
         std::lock_guard<std::mutex> lk(g_wave_mu);
@@ -386,7 +390,7 @@ static void run_wave(SptScene *s, const RenderCfg &cfg, const SampleSource &src,
     if (gridT < 1) gridT = 1;
     int gridP = std::min(gridT, sms * 8);      // persistent trace kernels: resident blocks only
     for (int b = 0; b <= cfg.max_depth; ++b) {
-        uint32_t *row = counts + 8 * b, *next = counts + 8 * (b + 1);
+        uint32_t *row = counts + SPT_ROW * b, *next = counts + SPT_ROW * (b + 1);
         uint32_t *q = wb.pathQ[b & 1], *qn = wb.pathQ[(b + 1) & 1];
         // camera rays that escape pick up the environment light (samplerrenderer.cpp:239-243)
         uint32_t *mq = (b == 0 && s->has_env) ? wb.missQ : nullptr;
@@ -395,7 +399,7 @@ static void run_wave(SptScene *s, const RenderCfg &cfg, const SampleSource &src,
         spt_launch_compact_hits(gridN, st, q, row + 0, wb.hit_slot, wb.hitQ, row + 3, mq, row + 7, (b == 0 && !s->has_env) ? wb.L : nullptr);
         s->mark(SPT_K_SHADE);
         if (mq) { spt_launch_miss_env(gridT, st, sc, wb, mq, row + 7); s->mark(SPT_K_SHADE); }
-        spt_launch_shade(gridT, st, sc, cfg, src, wb, b, wb.hitQ, row + 3, row + 1, row + 2);
+        spt_launch_shade(gridT, st, sc, cfg, src, wb, b, wb.hitQ, row + 3, row + 1, row + 2, row + 8);
         s->mark(SPT_K_SHADE);
         if (sc.n_lights > 0) {
             launch_trace<true>(s, gridP, wb.shadowQ, row + 1, row + 5, wb.g0, wb.g1, wb.sh_slot, nullptr);
@@ -420,13 +424,14 @@ static void collect_class_times(SptScene *s) {
 }
 static void reset_class_stats(SptScene *s) {
     for (int k = 0; k < SPT_K_CLASSES; ++k) { s->stats.class_ms[k] = 0.; s->stats.class_launches[k] = 0; s->stats.class_rays[k] = 0; }
+    s->stats.mis_rays_elided = 0; s->stats.first_vertices = 0;
     s->ev_used = 0;
 }
 
 static void add_ray_stats(SptScene *s, const std::vector<uint32_t> &counts, int max_depth, size_t n_waves) {
     for (size_t w = 0; w < n_waves; ++w)
         for (int b = 0; b <= max_depth; ++b) {
-            const uint32_t *row = &counts[(w * (size_t)(max_depth + 2) + b) * 8];
+            const uint32_t *row = &counts[(w * (size_t)(max_depth + 2) + b) * SPT_ROW];
             s->stats.closest_rays += row[0] + row[2];
             s->stats.any_rays += row[1];
             s->stats.class_rays[SPT_K_TRACE_PATH] += row[0];
@@ -434,6 +439,8 @@ static void add_ray_stats(SptScene *s, const std::vector<uint32_t> &counts, int 
             s->stats.class_rays[SPT_K_ACCUMULATE] += row[3];
             s->stats.class_rays[SPT_K_TRACE_SHADOW] += row[1];
             s->stats.class_rays[SPT_K_TRACE_MIS] += row[2];
+            s->stats.mis_rays_elided += row[8];
+            if (b == 0) s->stats.first_vertices += row[3];
         }
 }
 
@@ -569,7 +576,7 @@ int spt_shade_samples(SptScene *s, const SptCameraDesc *cam, int32_t max_depth, 
     cfg.cam = *cam; cfg.spp = 1; cfg.spp_shift = 0; cfg.max_depth = max_depth; cfg.n_samples = (uint32_t)n;
     cfg.tile = 1; cfg.tile_shift = 0; cfg.tilesX = 1; cfg.tilesY = 1; cfg.nranks = 1;
     SampleSource src; src.smp = dsmp; src.rng = drng; src.n_rng = drng ? n_rng : 0; src.seed = 0; src.spp = 1;
-    size_t nc = (size_t)(max_depth + 2) * 8;
+    size_t nc = (size_t)(max_depth + 2) * SPT_ROW;
     cudaMemsetAsync(s->counts, 0, nc * 4, s->stream);
     reset_class_stats(s);
     run_wave(s, cfg, src, s->counts);
@@ -724,7 +731,7 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
     size_t n_waves = (size_t)((local_pixels + wave_pixels - 1) / wave_pixels);
     int rc = ensure_wave(s, (uint32_t)(wave_pixels * rp->spp), rp->max_depth, std::max<size_t>(n_waves, 1));
     if (rc != SPT_OK) return rc;
-    size_t per_wave = (size_t)(rp->max_depth + 2) * 8;
+    size_t per_wave = (size_t)(rp->max_depth + 2) * SPT_ROW;
     cudaStream_t st = s->stream;
     CU(cudaMemsetAsync(s->counts, 0, std::max<size_t>(n_waves, 1) * per_wave * 4, st));
     SampleSource src; src.smp = nullptr; src.rng = nullptr; src.n_rng = 0; src.seed = cfg.seed; src.spp = (uint32_t)rp->spp;

@@ -70,13 +70,13 @@ __device__ __forceinline__ float2 dir_coef(int mtype, bool on, const DirTerms &t
 }
 __global__ void __launch_bounds__(128, 4) k_shade(DevScene sc, RenderCfg cfg, SampleSource src, WaveBuffers wb, int bounce,
                                                const uint32_t *queue, const uint32_t *count,
-                                               uint32_t *shadow_count, uint32_t *mis_count) {
+                                               uint32_t *shadow_count, uint32_t *mis_count, uint32_t *elided_count) {
     uint32_t n = *count;
     const uint32_t cap = wb.cap;
     for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < ((n + 31u) & ~31u); q += gridDim.x * blockDim.x) {
         bool active = q < n;
         uint32_t i = active ? queue[q] : 0;
-        bool pushShadow = false, pushMis = false;
+        bool pushShadow = false, pushMis = false, elided = false;
         if (active) {
             uint32_t slot = wb.hit_slot[i];
             float4 o4 = wb.ray_o[i], d4 = wb.ray_d[i];
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(128, 4) k_shade(DevScene sc, RenderCfg cfg, Sa
                 // a BSDF-sampled ray that cannot reach the light contributes exactly zero: not traced
                 if (have1 && lightPdf1 != 0.f && sc.lights[lightIdx].type == SPT_LIGHT_AREA) {
                     Ray mr; mr.o = p; mr.d = wiW1; mr.mint = eps; mr.maxt = SPT_INF;
-                    if (!light_ray_may_hit(sc, sc.lights[lightIdx], mr)) have1 = false;
+                    if (!light_ray_may_hit(sc, sc.lights[lightIdx], mr)) { have1 = false; elided = true; }
                 }
                 const bool have0 = haveLights && lr.pdf > 0.f && !lr.black;
                 const v3 wl0 = w2l(bsdf, lr.wi);
@@ -207,6 +207,8 @@ __global__ void __launch_bounds__(128, 4) k_shade(DevScene sc, RenderCfg cfg, Sa
         }
         queue_push(wb.shadowQ, shadow_count, pushShadow, i);
         queue_push(wb.misQ, mis_count, pushMis, i);
+        unsigned em = __ballot_sync(0xffffffffu, elided);
+        if (em && (threadIdx.x & 31) == 0) atomicAdd(elided_count, (uint32_t)__popc(em));
     }
 }
 
@@ -560,8 +562,9 @@ void spt_launch_miss_env(int grid, cudaStream_t st, const DevScene &sc, const Wa
     k_miss_env<<<grid, 128, 0, st>>>(sc, wb, queue, count);
 }
 void spt_launch_shade(int grid, cudaStream_t st, const DevScene &sc, const RenderCfg &cfg, const SampleSource &src, const WaveBuffers &wb,
-                      int bounce, const uint32_t *queue, const uint32_t *count, uint32_t *shadow_count, uint32_t *mis_count) {
-    k_shade<<<grid, 128, 0, st>>>(sc, cfg, src, wb, bounce, queue, count, shadow_count, mis_count);
+                      int bounce, const uint32_t *queue, const uint32_t *count, uint32_t *shadow_count, uint32_t *mis_count,
+                      uint32_t *elided_count) {
+    k_shade<<<grid, 128, 0, st>>>(sc, cfg, src, wb, bounce, queue, count, shadow_count, mis_count, elided_count);
 }
 void spt_launch_accumulate(int grid, cudaStream_t st, const DevScene &sc, const RenderCfg &cfg, const WaveBuffers &wb, int bounce,
                            const uint32_t *queue, const uint32_t *count, uint32_t *next_queue, uint32_t *next_count) {

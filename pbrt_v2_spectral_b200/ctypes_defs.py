@@ -55,6 +55,7 @@ class SptRenderParams(C.Structure):
 
 
 K_GEN, K_TRACE_PATH, K_SHADE, K_TRACE_SHADOW, K_TRACE_MIS, K_ACCUMULATE, K_FILM, K_CLASSES = 0, 1, 2, 3, 4, 5, 6, 8
+K_KERNELS = ["k_gen_camera", "k_trace_v1<closest>", "k_compact_hits + k_shade", "k_trace_v1<any>", "k_trace_v1<closest>", "k_accumulate", "k_film_add", "-"]
 K_NAMES = ["gen_camera", "trace_closest_path", "shade", "trace_any_shadow", "trace_closest_mis", "accumulate", "film_add", "-"]
 
 
@@ -65,7 +66,7 @@ class SptStats(C.Structure):
                 ("kernel_launches", C.c_uint64),
                 ("render_ms", C.c_double), ("trace_ms", C.c_double),
                 ("class_ms", C.c_double * K_CLASSES), ("class_launches", C.c_uint64 * K_CLASSES),
-                ("class_rays", C.c_uint64 * K_CLASSES)]
+                ("class_rays", C.c_uint64 * K_CLASSES), ("mis_rays_elided", C.c_uint64), ("first_vertices", C.c_uint64)]
 
 
 # row sizes of the table structs (bytes), for sanity checks against the container file
