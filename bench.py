@@ -159,7 +159,7 @@ def main():
         os.environ["NCCL_DEBUG"] = "WARN"        # keep stdout to the one JSON line
     import numpy as np
     import torch
-    from pbrt_v2_spectral_b200 import capi, ctypes_defs as D
+    from pbrt_v2_spectral_b200 import capi, ctypes_defs as D, multi
     from pbrt_v2_spectral_b200.scene_io import LoweredScene
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -179,7 +179,7 @@ def main():
     lowered = LoweredScene.load(SCENE_SPT)
     rp = D.SptRenderParams.from_buffer_copy(bytes(lowered.params))
     rp.seed = 1
-    rp.tile_rank, rp.tile_nranks, rp.tile_size = rank, world, 32
+    rp = multi.rank_params(rp, rank, world)            # this rank's tile set (32x32 tiles, round-robin)
     rp.wave_pixels = args.wave_pixels
     fd = lowered.film
     n_samples_total = (rp.x_end - rp.x_start) * (rp.y_end - rp.y_start) * rp.spp
@@ -211,8 +211,7 @@ def main():
     for _ in range(max(args.warmup, 3)):
         film_t.zero_()
         scene.render(film, rp)
-        if dist is not None:
-            dist.reduce(film_t, dst=0)
+        multi.reduce_film(film_t)
     barrier()
     launches0 = scene.stats()["kernel_launches"]
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -230,8 +229,7 @@ def main():
     for _ in range(args.steps):
         film_t.zero_()
         scene.render(film, rp)                       # blocks until the library's stream has drained
-        if dist is not None:
-            dist.reduce(film_t, dst=0)               # film gather over NVLink
+        multi.reduce_film(film_t)                    # N > 1: the film is summed onto rank 0 over NVLink (NCCL)
         st = scene.stats()
         render_ms += st["render_ms"]
         elided += st["mis_rays_elided"]

@@ -93,6 +93,65 @@ def metal(w, h, spp, name, maxdepth=5):
     return set_filename(set_spp(set_res(s, w, h), spp), name)
 
 
+def exr_to_pfm(src, dst):
+    """The reference build here has no OpenEXR; its PFM reader does not flip rows
+    (src/core/imageio.cpp:601-678), so the EXR's row order is kept."""
+    os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
+    import cv2
+    import numpy as np
+    img = cv2.imread(src, cv2.IMREAD_UNCHANGED)
+    assert img is not None, src
+    rgb = np.ascontiguousarray(img[..., 2::-1].astype("<f4"))
+    os.makedirs(os.path.dirname(dst), exist_ok=True)
+    with open(dst, "wb") as f:
+        f.write(b"PF\n%d %d\n-1.0\n" % (rgb.shape[1], rgb.shape[0]))
+        f.write(rgb.tobytes())
+
+
+def envmap(w, h, spp, name, maxdepth=5):
+    """BASELINE config 4 (ss-envmap): infinite area light with the grace lat-long map, importance sampled."""
+    s = read(os.path.join(REF, "scenes/ss-envmap.pbrt"))
+    s = re.sub(r'SurfaceIntegrator "dipolesubsurface".*\n\s*"float maxerror".*\n', 'SurfaceIntegrator "path" "integer maxdepth" [%d]\n' % maxdepth, s)
+    s = s.replace("textures/grace_latlong.exr", "textures/grace_latlong.pfm")
+    # floor: substrate + image textures + bump are "next" (SURVEY.md 8f N2): matte Kd 0.5
+    s = re.sub(r'Texture "tmap".*?"texture bumpmap" "sbump" \n', 'Material "matte" "color Kd" [.5 .5 .5]\n', s, flags=re.S)
+    # the teapot's `subsurface` material is a specular reflection BSDF under the path integrator
+    # (subsurface.cpp:52-56); specular BxDFs are not lowered yet: plastic stands in
+    s = re.sub(r'Material "subsurface".*\n\s*"color sigma_prime_s".*\n',
+               'Material "plastic" "color Kd" [.4 .35 .3] "color Ks" [.5 .5 .5] "float roughness" [.05]\n', s)
+    return set_filename(set_spp(set_res(s, w, h), spp), name)
+
+
+def synth(w, h, spp, name, maxdepth=5, ntris=200000, chunks=8):
+    """BASELINE config 5 recipe at test size: random triangle soup in [-1,1]^3, half matte /
+    half plastic, a sphere area light plus a constant infinite light (two lights: exercises the light choice)."""
+    import numpy as np
+    rng = np.random.default_rng(12345)
+    out = ['LookAt 0 -4 0  0 0 0  0 0 1', 'Camera "perspective" "float fov" [40]',
+           'Film "image" "integer xresolution" [%d] "integer yresolution" [%d] "string filename" "%s.exr"' % (w, h, name),
+           'Sampler "lowdiscrepancy" "integer pixelsamples" [%d]' % spp, 'PixelFilter "box"',
+           'SurfaceIntegrator "path" "integer maxdepth" [%d]' % maxdepth, 'WorldBegin',
+           'AttributeBegin', 'AreaLightSource "diffuse" "color L" [50 50 50]', 'Translate 0 0 3',
+           'Shape "sphere" "float radius" [.2]', 'AttributeEnd',
+           'LightSource "infinite" "color L" [.5 .5 .5]']
+    per = ntris // chunks
+    for c in range(chunks):
+        centre = rng.uniform(-1, 1, (per, 3))
+        def edge():
+            d = rng.normal(size=(per, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+            return d * rng.uniform(0.002, 0.02, (per, 1))
+        P = np.stack([centre, centre + edge(), centre + edge()], 1).reshape(-1, 3).astype(np.float32)
+        kd = rng.uniform(0.2, 0.8, 3)
+        if c % 2 == 0:
+            out.append('Material "matte" "color Kd" [%g %g %g]' % tuple(kd))
+        else:
+            out.append('Material "plastic" "color Kd" [%g %g %g] "color Ks" [.3 .3 .3] "float roughness" [%g]' % (*kd, rng.uniform(0.01, 0.3)))
+        out.append('Shape "trianglemesh" "integer indices" [' + " ".join(map(str, range(3 * per))) + ']')
+        out.append('"point P" [' + " ".join("%.9g" % v for v in P.ravel()) + ']')
+    out.append('WorldEnd')
+    return "\n".join(out) + "\n"
+
+
 def tiny(w, h, spp, name, maxdepth=5):
     s = read(os.path.join(TESTS_GOLDEN, "tiny.pbrt"))
     return set_filename(set_spp(set_res(s, w, h), spp), name)
@@ -108,6 +167,10 @@ CONFIGS = {
     "bunny_small":     (bunny, 320, 240, 4, 8000, 40, 4096),
     # config 3 (metal teapot, Au SPDs) with the substitutions noted above
     "metal_small":     (metal, 200, 200, 4, 6000, 40, 512),
+    # config 4 (ss-envmap): grace environment map, Distribution2D importance sampling
+    "envmap_small":    (envmap, 200, 200, 4, 6000, 40, 8192),
+    # config 5 recipe at test size: 200 000 random triangles, two lights
+    "synth_small":     (synth, 256, 144, 4, 6000, 40, 2048),
     # small committed fixture
     "tiny":            (tiny, 48, 48, 4, 700, 40, 0),
 }
@@ -130,6 +193,9 @@ def main():
         dst = os.path.join(SCENES, d)
         if not os.path.isdir(dst):
             shutil.copytree(os.path.join(REF, "scenes", d), dst)
+    pfm = os.path.join(SCENES, "textures", "grace_latlong.pfm")
+    if not os.path.exists(pfm):
+        exr_to_pfm(os.path.join(REF, "scenes", "textures", "grace_latlong.exr"), pfm)
     names = [n for n in CONFIGS if not args.only or n in args.only.split(",")]
     for name in names:
         build, w, h, spp, npix, nrng, img_spp = CONFIGS[name]

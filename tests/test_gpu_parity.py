@@ -81,6 +81,29 @@ def test_film_add_samples(case):
     assert np.allclose(c, oc, rtol=1e-5, atol=1e-6)
 
 
+def test_film_wide_filter():
+    """AddSample with a footprint of several pixels (Gaussian, width 2): the per-pixel atomic path of K7."""
+    lowered, g = O.load_case(*CASES[0][1:])
+    fd = D.SptFilmDesc.from_buffer_copy(bytes(lowered.film))
+    fd.filter_xwidth = fd.filter_ywidth = 2.0
+    fd.filter_inv_xwidth = fd.filter_inv_ywidth = 0.5
+    alpha, ex = 2.0, np.exp(-2.0 * 2.0 * 2.0)
+    for y in range(16):                               # the 16x16 table of spectralImage.cpp:61-70 for GaussianFilter(2, 2, alpha 2)
+        for x in range(16):
+            fx, fy = (x + 0.5) * 2.0 / 16, (y + 0.5) * 2.0 / 16
+            fd.filter_table[y * 16 + x] = max(0.0, np.exp(-alpha * fx * fx) - ex) * max(0.0, np.exp(-alpha * fy * fy) - ex)
+    xy = g["samples"][:, :2].copy()
+    L = g["L"].copy()
+    L[3, 1] = np.nan
+    film = capi.Film(fd)
+    film.add_samples(lowered.tables, xy, L)
+    c, w = film.download()
+    film.close()
+    oc, ow = O.film_add_samples(lowered, xy, L, film=fd)
+    assert np.allclose(w, ow, rtol=1e-5, atol=1e-6)
+    assert np.allclose(c, oc, rtol=2e-5, atol=1e-6)
+
+
 def test_render_matches_oracle_render():
     """Whole job (K1..K7 with the product sampler, compaction, film) against the oracle running the
     same sampler on the CPU, small image."""
