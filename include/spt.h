@@ -67,8 +67,11 @@ typedef struct SptXform { float m[16]; float minv[16]; } SptXform;
  *   MATTE   spec0 = Kd.Clamp(), p0 = sigma clamped to [0,90]        (src/materials/matte.cpp:34-60)
  *   PLASTIC spec0 = Kd.Clamp(), spec1 = Ks.Clamp(), p0 = roughness  (src/materials/plastic.cpp:34-61)
  *   METAL   spec0 = eta, spec1 = k, p0 = roughness                  (src/materials/metal.cpp:44-68)
- *   MIRROR  spec0 = Kr.Clamp()                                      (src/materials/mirror.cpp)
- *   GLASS   spec0 = Kr.Clamp(), spec1 = Kt.Clamp(), p0 = index      (src/materials/glass.cpp)
+ *   MIRROR  spec0 = Kr.Clamp(): SpecularReflection(Kr, FresnelNoOp) (src/materials/mirror.cpp:34-55)
+ *   GLASS   spec0 = Kr.Clamp(), spec1 = Kt.Clamp(), p0 = index: SpecularReflection(Kr, FresnelDielectric(1, index))
+ *           + SpecularTransmission(Kt, 1, index), each only if its spectrum is not black (src/materials/glass.cpp:34-58).
+ *           `subsurface` lowers to GLASS with Kt = 0, index = eta: its BSDF under the path integrator
+ *           (src/materials/subsurface.cpp:40-58)
  */
 enum { SPT_MAT_MATTE = 0, SPT_MAT_PLASTIC = 1, SPT_MAT_METAL = 2, SPT_MAT_MIRROR = 3, SPT_MAT_GLASS = 4 };
 typedef struct SptMaterial {

@@ -152,6 +152,26 @@ def synth(w, h, spp, name, maxdepth=5, ntris=200000, chunks=8):
     return "\n".join(out) + "\n"
 
 
+def ssenv(w, h, spp, name, maxdepth=5):
+    """BASELINE config 4 with the teapot's shipped `subsurface` material: under the path integrator its BSDF is a
+    specular reflection with dielectric Fresnel (subsurface.cpp:40-58). Floor as in envmap()."""
+    s = read(os.path.join(REF, "scenes/ss-envmap.pbrt"))
+    s = re.sub(r'SurfaceIntegrator "dipolesubsurface".*\n\s*"float maxerror".*\n', 'SurfaceIntegrator "path" "integer maxdepth" [%d]\n' % maxdepth, s)
+    s = s.replace("textures/grace_latlong.exr", "textures/grace_latlong.pfm")
+    s = re.sub(r'Texture "tmap".*?"texture bumpmap" "sbump" \n', 'Material "matte" "color Kd" [.5 .5 .5]\n', s, flags=re.S)
+    return set_filename(set_spp(set_res(s, w, h), spp), name)
+
+
+def specular(w, h, spp, name, maxdepth=5):
+    """killeroo-simple with one killeroo of glass and one mirror: specular reflection / transmission,
+    emitted light seen through specular bounces (path.cpp:55-56)."""
+    s = killeroo(w, h, spp, name, maxdepth)
+    s = s.replace('Material "plastic" "color Kd" [.4 .2 .2] "color Ks" [.5 .5 .5]', 'Material "glass" "color Kr" [.9 .9 .9] "color Kt" [.9 .8 .7] "float index" [1.5]')
+    s = s.replace('Material "plastic" "color Ks" [.3 .3 .3] "color Kd" [.4 .5 .4]', 'Material "mirror" "color Kr" [.8 .85 .9]')
+    assert "glass" in s and "mirror" in s
+    return s
+
+
 def tiny(w, h, spp, name, maxdepth=5):
     s = read(os.path.join(TESTS_GOLDEN, "tiny.pbrt"))
     return set_filename(set_spp(set_res(s, w, h), spp), name)
@@ -171,6 +191,9 @@ CONFIGS = {
     "envmap_small":    (envmap, 200, 200, 4, 6000, 40, 8192),
     # config 5 recipe at test size: 200 000 random triangles, two lights
     "synth_small":     (synth, 256, 144, 4, 6000, 40, 2048),
+    # config 4 with the shipped subsurface teapot (specular reflection BSDF); glass + mirror killeroos
+    "ssenv_small":     (ssenv, 200, 200, 4, 6000, 40, 4096),
+    "specular_small":  (specular, 176, 176, 4, 6000, 40, 2048),
     # small committed fixture
     "tiny":            (tiny, 48, 48, 4, 700, 40, 0),
 }

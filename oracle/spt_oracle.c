@@ -443,7 +443,10 @@ static float power_heuristic(int nf, float fPdf, int ng, float gPdf) {
 /* BSDF: core/reflection.cpp. A BSDF here is the frame (reflection.cpp:593-601) plus the material
  * row; its BxDF list is implied by the material type (materials/matte.cpp:34-60,
  * plastic.cpp:34-61, metal.cpp:44-68). */
-enum { BX_LAMBERT = 0, BX_ORENNAYAR = 1, BX_MICROFACET_DIEL = 2, BX_MICROFACET_COND = 3 };
+enum { BX_LAMBERT = 0, BX_ORENNAYAR = 1, BX_MICROFACET_DIEL = 2, BX_MICROFACET_COND = 3,
+       /* specular: reflection.cpp:130-160 */
+       BX_SPEC_REFL_NOOP = 4, BX_SPEC_REFL_DIEL = 5, BX_SPEC_TRANS = 6 };
+#define BX_IS_SPECULAR(k) ((k) >= BX_SPEC_REFL_NOOP)
 typedef struct {
     v3 nn, sn, tn, ng;
     int nBxDFs;
@@ -452,6 +455,7 @@ typedef struct {
     const float *eta, *k;       /* conductor */
     float exponent;             /* Blinn */
     float A, B;                 /* Oren-Nayar */
+    float ior;                  /* glass / subsurface: FresnelDielectric(1, ior) */
 } BSDF;
 
 static v3 w2l(const BSDF *b, v3 v) { return V(dot(v, b->sn), dot(v, b->tn), dot(v, b->nn)); }
@@ -467,6 +471,7 @@ static inline float sin_theta(v3 w) { return sqrtf(sin_theta2(w)); }
 static inline float cos_phi(v3 w) { float s = sin_theta(w); if (s == 0.f) return 1.f; return clampf(w.x / s, -1.f, 1.f); }
 static inline float sin_phi(v3 w) { float s = sin_theta(w); if (s == 0.f) return 0.f; return clampf(w.y / s, -1.f, 1.f); }
 
+static int is_black(const float *s);
 static float blinn_exponent(float e) { if (e > 10000.f || isnan(e)) e = 10000.f; return e; }   /* reflection.h:416-417 */
 
 /* Material::Bump constant-0 path + GetBSDF (core/material.cpp:39-82) */
@@ -529,11 +534,19 @@ static void make_bsdf(const SptSceneDesc *sc, uint32_t slot, const Hit *dg, BSDF
         b->kind[0] = BX_LAMBERT; b->R[0] = m->spec0;
         b->kind[1] = BX_MICROFACET_DIEL; b->R[1] = m->spec1;
         b->exponent = blinn_exponent(1.f / m->p0);
-    } else {
+    } else if (m->type == SPT_MAT_METAL) {
         b->nBxDFs = 1;
         b->kind[0] = BX_MICROFACET_COND; b->R[0] = NULL;
         b->eta = m->spec0; b->k = m->spec1;
         b->exponent = blinn_exponent(1.f / m->p0);
+    } else if (m->type == SPT_MAT_MIRROR) {                     /* materials/mirror.cpp:34-55 */
+        b->nBxDFs = 0;
+        if (!is_black(m->spec0)) { b->kind[0] = BX_SPEC_REFL_NOOP; b->R[0] = m->spec0; b->nBxDFs = 1; }
+    } else {                                                   /* materials/glass.cpp:34-58; subsurface.cpp:40-58 = reflection only */
+        b->nBxDFs = 0;
+        b->ior = m->p0;
+        if (!is_black(m->spec0)) { b->kind[b->nBxDFs] = BX_SPEC_REFL_DIEL; b->R[b->nBxDFs] = m->spec0; b->nBxDFs++; }
+        if (!is_black(m->spec1)) { b->kind[b->nBxDFs] = BX_SPEC_TRANS; b->R[b->nBxDFs] = m->spec1; b->nBxDFs++; }
     }
 }
 
@@ -626,8 +639,8 @@ static void bsdf_f(const BSDF *b, v3 woW, v3 wiW, float *f) {
     v3 wi = w2l(b, wiW), wo = w2l(b, woW);
     int reflect = dot(wiW, b->ng) * dot(woW, b->ng) > 0;
     for (int c = 0; c < NB; ++c) f[c] = 0.f;
-    if (!reflect) return;           /* BRDFs ignored; there are no BTDFs */
-    for (int i = 0; i < b->nBxDFs; ++i) bxdf_f(b, i, wo, wi, f);
+    if (!reflect) return;           /* BRDFs ignored; the only BTDF is specular */
+    for (int i = 0; i < b->nBxDFs; ++i) if (!BX_IS_SPECULAR(b->kind[i])) bxdf_f(b, i, wo, wi, f);
 }
 /* BSDF::Pdf, reflection.cpp:575-590 */
 static float bsdf_pdf(const BSDF *b, v3 woW, v3 wiW) {
@@ -635,20 +648,54 @@ static float bsdf_pdf(const BSDF *b, v3 woW, v3 wiW) {
     v3 wo = w2l(b, woW), wi = w2l(b, wiW);
     float pdf = 0.f;
     int matching = 0;
-    for (int i = 0; i < b->nBxDFs; ++i) { ++matching; pdf += bxdf_pdf(b, i, wo, wi); }
+    for (int i = 0; i < b->nBxDFs; ++i) if (!BX_IS_SPECULAR(b->kind[i])) { ++matching; pdf += bxdf_pdf(b, i, wo, wi); }
     return matching > 0 ? pdf / matching : 0.f;
 }
-/* BSDF::Sample_f, reflection.cpp:514-572. Returns 0 if f is to be treated as Spectrum(0). */
-static void bsdf_sample_f(const BSDF *b, v3 woW, v3 *wiW, float uComp, float u1, float u2, float *pdf, float *f) {
-    int matching = b->nBxDFs;
+/* BSDF::Sample_f, reflection.cpp:514-572. allowSpecular: flags = BSDF_ALL (path continuation), else
+ * BSDF_ALL & ~BSDF_SPECULAR (EstimateDirect). A lowered BSDF is either all specular (mirror, glass) or has
+ * no specular component. *specular: the sampled BxDF's type has BSDF_SPECULAR. */
+static void bsdf_sample_f(const BSDF *b, v3 woW, v3 *wiW, float uComp, float u1, float u2, float *pdf, float *f,
+                          int allowSpecular, int *specular) {
+    int matching = 0;
+    int idx[2];
+    for (int i = 0; i < b->nBxDFs; ++i) if (allowSpecular || !BX_IS_SPECULAR(b->kind[i])) idx[matching++] = i;
     for (int c = 0; c < NB; ++c) f[c] = 0.f;
+    if (specular) *specular = 0;
     if (matching == 0) { *pdf = 0.f; return; }
     int which = (int)floorf(uComp * matching);
     if (matching - 1 < which) which = matching - 1;
+    which = idx[which];
     v3 wo = w2l(b, woW);
     v3 wi;
     *pdf = 0.f;
     int kind = b->kind[which];
+    if (BX_IS_SPECULAR(kind)) {
+        float fr = 1.f;                                        /* FresnelNoOp */
+        if (kind != BX_SPEC_REFL_NOOP) fr = fresnel_dielectric(wo.z, 1.f, b->ior);
+        if (kind == BX_SPEC_TRANS) {                           /* SpecularTransmission::Sample_f, reflection.cpp:139-162 */
+            int entering = wo.z > 0.;
+            float ei = 1.f, et = b->ior;
+            if (!entering) { float t = ei; ei = et; et = t; }
+            float sini2 = sin_theta2(wo);
+            float eta = ei / et;
+            float sint2 = eta * eta * sini2;
+            if (sint2 >= 1.) return;                           /* total internal reflection: pdf stays 0 */
+            float cost = sqrtf(stdmaxf(0.f, 1.f - sint2));
+            if (entering) cost = -cost;
+            float sintOverSini = eta;
+            wi = V(sintOverSini * -wo.x, sintOverSini * -wo.y, cost);
+            *pdf = 1.f;
+            for (int c = 0; c < NB; ++c) f[c] = (1.f - fr) * b->R[which][c] / abs_cos_theta(wi);
+        } else {                                               /* SpecularReflection::Sample_f, reflection.cpp:130-136 */
+            wi = V(-wo.x, -wo.y, wo.z);
+            *pdf = 1.f;
+            for (int c = 0; c < NB; ++c) f[c] = fr * b->R[which][c] / abs_cos_theta(wi);
+        }
+        if (specular) *specular = 1;
+        *wiW = l2w(b, wi);
+        if (matching > 1) *pdf /= matching;
+        return;
+    }
     if (kind == BX_LAMBERT || kind == BX_ORENNAYAR) {          /* BxDF::Sample_f, reflection.cpp:303-310 */
         wi = cosine_sample_hemisphere(u1, u2);
         if (wo.z < 0.) wi.z *= -1.f;
@@ -970,7 +1017,7 @@ static void estimate_direct(const SptSceneDesc *sc, const SptLight *light, int l
     if (!lr.is_delta) {
         v3 wi;
         float bsdfPdf;
-        bsdf_sample_f(bsdf, wo, &wi, bs[2], bs[0], bs[1], &bsdfPdf, f);
+        bsdf_sample_f(bsdf, wo, &wi, bs[2], bs[0], bs[1], &bsdfPdf, f, 0, NULL);
         if (!is_black(f) && bsdfPdf > 0.) {
             float weight = 1.f;
             float lightPdf = light_pdf(sc, light, p, wi);
@@ -1048,9 +1095,10 @@ static void li_sample(const SptSceneDesc *sc, const SptCameraDesc *cam, int maxD
             u[0] = smp[19 + 6 * bounces + 4]; u[1] = smp[19 + 6 * bounces + 5]; u[2] = smp[5 + 4 * bounces + 3];
         } else { u[0] = rng_next(&rng); u[1] = rng_next(&rng); u[2] = rng_next(&rng); }
         v3 wi; float pdf; float f[NB];
-        bsdf_sample_f(&bsdf, wo, &wi, u[2], u[0], u[1], &pdf, f);
+        int spec;
+        bsdf_sample_f(&bsdf, wo, &wi, u[2], u[0], u[1], &pdf, f, 1, &spec);
         if (is_black(f) || pdf == 0.) break;
-        specularBounce = 0;
+        specularBounce = spec;
         float ad = absdot(wi, n);
         for (int c = 0; c < NB; ++c) T[c] *= f[c] * ad / pdf;
         float eps = isect.rayEpsilon;

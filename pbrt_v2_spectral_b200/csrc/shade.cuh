@@ -17,6 +17,8 @@ struct Bsdf {
     int mtype;            // SPT_MAT_*
     bool orenNayar;
     float exponent, A, B;
+    float ior;            // GLASS: FresnelDielectric(1, ior)
+    int compMask;         // MIRROR / GLASS: bit 0 the reflection component exists (Kr not black), bit 1 the transmission (Kt)
 };
 // Wavelength-independent factors of BSDF::f(wo,wi) for one direction.
 //   Oren-Nayar: a0 = A + B*maxcos*sinalpha*tanbeta
@@ -79,8 +81,11 @@ __device__ inline void make_bsdf(const DevScene &sc, uint32_t slot, const Hit &d
     b->tn = cross(b->nn, b->sn);
     const SptMaterial &m = sc.materials[sc.prim_material[slot]];
     b->mtype = m.type;
-    b->orenNayar = false; b->exponent = 0.f; b->A = b->B = 0.f;
-    if (m.type == SPT_MAT_MATTE) {
+    b->orenNayar = false; b->exponent = 0.f; b->A = b->B = 0.f; b->ior = 1.f; b->compMask = 0;
+    if (m.type == SPT_MAT_MIRROR || m.type == SPT_MAT_GLASS) {       // mirror.cpp:34-55, glass.cpp:34-58
+        b->ior = m.p0;
+        b->compMask = (int)m.p1;                                      // which spectra are not black: set by spt_scene_create
+    } else if (m.type == SPT_MAT_MATTE) {
         if (m.p0 != 0.f) {                                           // OrenNayar ctor, reflection.h:363-370
             b->orenNayar = true;
             float sigma = (PI_F / 180.f) * m.p0;
@@ -92,7 +97,9 @@ __device__ inline void make_bsdf(const DevScene &sc, uint32_t slot, const Hit &d
         b->exponent = blinn_exponent(1.f / m.p0);
     }
 }
-__device__ __forceinline__ int bsdf_ncomp(const Bsdf &b) { return b.mtype == SPT_MAT_PLASTIC ? 2 : 1; }
+__device__ __forceinline__ bool bsdf_is_specular(const Bsdf &b) { return b.mtype == SPT_MAT_MIRROR || b.mtype == SPT_MAT_GLASS; }
+__device__ __forceinline__ int bsdf_ncomp(const Bsdf &b) { return b.mtype == SPT_MAT_PLASTIC ? 2 : 1; }     // non-specular materials
+__device__ __forceinline__ int specular_ncomp(const Bsdf &b) { return (b.compMask & 1) + ((b.compMask >> 1) & 1); }
 
 __device__ inline float fresnel_dielectric(float cosi, float eta_i, float eta_t) {          // reflection.cpp:107-127,52-60
     cosi = clampf(cosi, -1.f, 1.f);
@@ -225,6 +232,42 @@ __device__ inline void bsdf_sample(const Bsdf &b, v3 woW, v3 wo, float uComp, fl
     if (!bsdf_sample_dir(b, wo, uComp, u1, u2, &wi)) return;
     *wiW = l2w(b, wi);
     bsdf_terms(b, woW, *wiW, wo, wi, t, pdf);
+}
+
+// BSDF::Sample_f for an all-specular BSDF (mirror, glass; reflection.cpp:514-572 with SpecularReflection::Sample_f
+// :130-136 and SpecularTransmission::Sample_f :139-162). The value is f[c] = Kr[c] * coefR + Kt[c] * coefT with
+// coefR = F / |cos theta_i| (F = 1 for the mirror's FresnelNoOp), coefT = (1 - F) / |cos theta_i| (no eta^2 scaling,
+// as the reference); pdf = 1 / number of components. Returns false when there is no sample (no component, or total
+// internal reflection on the transmission component).
+__device__ inline bool specular_sample(const Bsdf &b, v3 wo, float uComp, v3 *wiOut, float *coefR, float *coefT, float *pdf) {
+    int matching = specular_ncomp(b);
+    *coefR = *coefT = 0.f; *pdf = 0.f;
+    if (matching == 0) return false;
+    int which = (int)floorf(uComp * matching);
+    if (matching - 1 < which) which = matching - 1;
+    bool transmit = (b.compMask & 1) ? which == 1 : true;             // component order: reflection, transmission
+    float F = b.mtype == SPT_MAT_MIRROR ? 1.f : fresnel_dielectric(wo.z, 1.f, b.ior);
+    v3 wi;
+    if (!transmit) {
+        wi = V(-wo.x, -wo.y, wo.z);
+        *coefR = F / abs_cos_theta(wi);
+    } else {
+        bool entering = wo.z > 0.f;
+        float ei = 1.f, et = b.ior;
+        if (!entering) { float tmp = ei; ei = et; et = tmp; }
+        float sini2 = stdmaxf(0.f, 1.f - wo.z * wo.z);
+        float eta = ei / et;
+        float sint2 = eta * eta * sini2;
+        if (sint2 >= 1.f) return false;
+        float cost = sqrtf(stdmaxf(0.f, 1.f - sint2));
+        if (entering) cost = -cost;
+        wi = V(eta * -wo.x, eta * -wo.y, cost);
+        *coefT = (1.f - F) / abs_cos_theta(wi);
+    }
+    *wiOut = wi;
+    *pdf = 1.f;
+    if (matching > 1) *pdf /= matching;
+    return true;
 }
 
 // ---- spectral tables ----------------------------------------------------------------------------

@@ -242,7 +242,16 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
     UP(v.tri_vidx, d->tri_vidx, (size_t)d->n_tris * 3);
     UP(v.P, d->P, (size_t)d->n_verts * 3); UP(v.N, d->N, (size_t)d->n_verts * 3); UP(v.UV, d->UV, (size_t)d->n_verts * 2);
     UP(v.quadrics, d->quadrics, d->n_quadrics); UP(v.xforms, d->xforms, d->n_xforms);
-    UP(v.materials, d->materials, d->n_materials); UP(v.lights, d->lights, d->n_lights);
+    // materials: p1 of a mirror / glass row records which of its spectra are not black (the BxDFs GetBSDF adds)
+    std::vector<SptMaterial> mats(d->materials, d->materials + d->n_materials);
+    for (SptMaterial &mt : mats)
+        if (mt.type == SPT_MAT_MIRROR || mt.type == SPT_MAT_GLASS) {
+            int mask = 0;
+            for (int c = 0; c < NB; ++c) { if (mt.spec0[c] != 0.f) mask |= 1; if (mt.type == SPT_MAT_GLASS && mt.spec1[c] != 0.f) mask |= 2; }
+            mt.p1 = (float)mask;
+            v.has_specular = 1;
+        }
+    UP(v.materials, mats.data(), d->n_materials); UP(v.lights, d->lights, d->n_lights);
     UP(v.light_shapes, d->light_shapes, d->n_light_shapes);
     UP(v.light_cdf, cdf.data(), cdf.size());
     v.n_lights = d->n_lights;
@@ -348,7 +357,7 @@ static int ensure_wave(SptScene *s, uint32_t cap, int max_depth, size_t n_waves)
         AL(w.g0, float4, cap); AL(w.g1, float4, cap); AL(w.g2, float4, cap); AL(w.g3, float4, cap);
         AL(w.mis_slot, uint32_t, cap); AL(w.mis_t, float, cap); AL(w.sh_slot, uint32_t, cap);
         AL(w.rec0, float4, cap); AL(w.rec1, float4, cap); AL(w.rec2, float4, cap);
-        AL(w.laux, float4, cap);
+        AL(w.laux, float4, cap); AL(w.pflags, uint32_t, cap);
         AL(w.img_xy, float2, cap);
         AL(w.T, float, (size_t)cap * NB); AL(w.L, float, (size_t)cap * NB);
         AL(w.pathQ[0], uint32_t, cap); AL(w.pathQ[1], uint32_t, cap); AL(w.shadowQ, uint32_t, cap); AL(w.misQ, uint32_t, cap);
@@ -393,12 +402,12 @@ static void run_wave(SptScene *s, const RenderCfg &cfg, const SampleSource &src,
         uint32_t *row = counts + SPT_ROW * b, *next = counts + SPT_ROW * (b + 1);
         uint32_t *q = wb.pathQ[b & 1], *qn = wb.pathQ[(b + 1) & 1];
         // camera rays that escape pick up the environment light (samplerrenderer.cpp:239-243)
-        uint32_t *mq = (b == 0 && s->has_env) ? wb.missQ : nullptr;
+        uint32_t *mq = (s->has_env && (b == 0 || sc.has_specular)) ? wb.missQ : nullptr;
         launch_trace<false>(s, gridP, q, row + 0, row + 4, wb.ray_o, wb.ray_d, wb.hit_slot, wb.hit_t);
         s->mark(SPT_K_TRACE_PATH);
         spt_launch_compact_hits(gridN, st, q, row + 0, wb.hit_slot, wb.hitQ, row + 3, mq, row + 7, (b == 0 && !s->has_env) ? wb.L : nullptr);
         s->mark(SPT_K_SHADE);
-        if (mq) { spt_launch_miss_env(gridT, st, sc, wb, mq, row + 7); s->mark(SPT_K_SHADE); }
+        if (mq) { spt_launch_miss_env(gridT, st, sc, wb, b, mq, row + 7); s->mark(SPT_K_SHADE); }
         spt_launch_shade(gridT, st, sc, cfg, src, wb, b, wb.hitQ, row + 3, row + 1, row + 2, row + 8);
         s->mark(SPT_K_SHADE);
         if (sc.n_lights > 0) {

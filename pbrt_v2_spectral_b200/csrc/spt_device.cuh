@@ -105,6 +105,7 @@ struct DevScene {
     const SptLightShape *light_shapes;
     const float *light_cdf;          // per light: shape_count+1 floats at offset shape_first + light index
     uint32_t n_lights;
+    int has_specular;                // some material is a mirror / glass: paths carry the specularBounce flag (path.cpp:50,86)
     const SptSpectralTables *tables;
     int env_w, env_h;
     const float *env_rgb, *env_func, *env_cdf, *env_func_int, *env_marg_func, *env_marg_cdf;

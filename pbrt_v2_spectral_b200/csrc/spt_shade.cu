@@ -34,14 +34,14 @@ __global__ void __launch_bounds__(256) k_compact_hits(const uint32_t *__restrict
 }
 
 // ---- K4 (miss) -----------------------------------------------------------------------------------
-// SamplerRenderer::Li miss branch (samplerrenderer.cpp:239-243): sum of Light::Le over all lights for
-// camera rays that escape; only the infinite light is non-zero. Later bounces add Le only after a
-// specular bounce (path.cpp:106-108), which the lowered BxDFs never produce.
-__global__ void __launch_bounds__(128) k_miss_env(DevScene sc, WaveBuffers wb, const uint32_t *queue, const uint32_t *count) {
+// Camera rays that escape: SamplerRenderer::Li's miss branch (samplerrenderer.cpp:239-243), the sum of
+// Light::Le over all lights - only the infinite light is non-zero. Later bounces: the same sum times the
+// throughput, but only for a ray that left a specular bounce (path.cpp:106-108).
+__global__ void __launch_bounds__(128) k_miss_env(DevScene sc, WaveBuffers wb, int bounce, const uint32_t *queue, const uint32_t *count) {
     uint32_t n = *count;
-    const uint32_t cap = wb.cap;
     for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
         uint32_t i = queue[q];
+        if (bounce > 0 && !(wb.pflags[i] & 1u)) continue;
         float4 d4 = wb.ray_d[i];
         float Le[NB];
         for (int c = 0; c < NB; ++c) Le[c] = 0.f;
@@ -52,7 +52,8 @@ __global__ void __launch_bounds__(128) k_miss_env(DevScene sc, WaveBuffers wb, c
                 IllumCoefs k = illum_coefs(rgb);
                 for (int c = 0; c < NB; ++c) Le[c] += illum_band(*sc.tables, k, c);
             }
-        for (int c = 0; c < NB; ++c) wb.L[band_off(i, c)] = Le[c];
+        if (bounce == 0) { for (int c = 0; c < NB; ++c) wb.L[band_off(i, c)] = Le[c]; }
+        else for (int c = 0; c < NB; ++c) wb.L[band_off(i, c)] += wb.T[band_off(i, c)] * Le[c];
     }
 }
 
@@ -68,6 +69,9 @@ __device__ __forceinline__ float2 dir_coef(int mtype, bool on, const DirTerms &t
     else if (t.mf) { d.x = t.a0 * t.a1 / t.a3; d.y = t.a2; }
     return d;
 }
+// SPEC: the scene has mirror / glass materials (a second instantiation keeps their code, and the
+// specularBounce flag traffic, out of the kernel every other scene runs).
+template <bool SPEC>
 __global__ void __launch_bounds__(128, 4) k_shade(DevScene sc, RenderCfg cfg, SampleSource src, WaveBuffers wb, int bounce,
                                                const uint32_t *queue, const uint32_t *count,
                                                uint32_t *shadow_count, uint32_t *mis_count, uint32_t *elided_count) {
@@ -89,7 +93,7 @@ __global__ void __launch_bounds__(128, 4) k_shade(DevScene sc, RenderCfg cfg, Sa
                 // emitted light at the first vertex (path.cpp:55-56; Intersection::Le, intersection.cpp:53-56):
                 // K6 starts L from the emitter's spectrum instead of from black
                 int emitter = -1;
-                if (bounce == 0) {
+                if (bounce == 0 || (SPEC && (wb.pflags[i] & 1u))) {
                     int li = sc.prim_light[slot];
                     if (li >= 0 && dot(hit.nn, vneg(ray.d)) > 0.f) emitter = li;
                 }
@@ -115,7 +119,8 @@ __global__ void __launch_bounds__(128, 4) k_shade(DevScene sc, RenderCfg cfg, Sa
                 float sL = 0.f, sB = 0.f, sP = 0.f;
                 int lightIdx = 0;
                 if (bsdf.orenNayar) flags |= RF_ON;
-                const bool haveLights = sc.n_lights > 0;
+                const bool specMat = SPEC && bsdf_is_specular(bsdf);     // mirror / glass: no non-specular component, so
+                const bool haveLights = sc.n_lights > 0 && !specMat;      // EstimateDirect contributes nothing and traces nothing
                 // The three directions of a path vertex: 0 the light sample (UniformSampleOneLight,
                 // integrator.cpp:74-106; EstimateDirect :109-137), 1 the BSDF sample of the MIS estimate
                 // (:139-163), 2 the continuation (path.cpp:75-92). Each stage below runs ONCE over the
@@ -132,8 +137,15 @@ __global__ void __launch_bounds__(128, 4) k_shade(DevScene sc, RenderCfg cfg, Sa
                 v3 wl1 = V(0, 0, 1), wl2 = wl1, wiW1 = wl1, wiW2 = wl1;
                 bool have1 = false, have2 = false;
 #pragma unroll 1
+                float specR = 0.f, specT = 0.f, specPdf = 0.f;
                 for (int d = 1; d <= 2; ++d) {
                     if (d == 1 && (!haveLights || lr.delta)) continue;
+                    if (specMat) {                                      // only d == 2 gets here
+                        v3 wl;
+                        have2 = specular_sample(bsdf, wo, u[9], &wl, &specR, &specT, &specPdf);
+                        wl2 = wl; wiW2 = l2w(bsdf, wl);
+                        continue;
+                    }
                     float uc = d == 1 ? u[6] : u[9], ua = d == 1 ? u[4] : u[7], ub = d == 1 ? u[5] : u[8];
                     v3 wl;
                     bool ok = bsdf_sample_dir(bsdf, wo, uc, ua, ub, &wl);
@@ -159,7 +171,7 @@ __global__ void __launch_bounds__(128, 4) k_shade(DevScene sc, RenderCfg cfg, Sa
                 float pdf0 = 0.f, pdf1 = 0.f, pdf2 = 0.f;
 #pragma unroll 1
                 for (int d = 0; d < 3; ++d) {
-                    if (!(d == 0 ? have0 : (d == 1 ? have1 : have2))) continue;
+                    if (!(d == 0 ? have0 : (d == 1 ? have1 : (have2 && !specMat)))) continue;
                     v3 wW = d == 0 ? lr.wi : (d == 1 ? wiW1 : wiW2);
                     v3 wl = d == 0 ? wl0 : (d == 1 ? wl1 : wl2);
                     DirTerms t; float pdf;
@@ -173,7 +185,7 @@ __global__ void __launch_bounds__(128, 4) k_shade(DevScene sc, RenderCfg cfg, Sa
                         sL = (absdot(lr.wi, n_s) * weight / lr.pdf);
                     }
                     if (sc.lights[lightIdx].type == SPT_LIGHT_POINT) sL = sL / lr.aux[0];     // I / d^2 (point.cpp:42-49)
-                    flags |= RF_L | (lr.delta ? RF_LDELTA : 0);
+                    flags |= RF_L;
                     cL = dir_coef(mtype, on, t0);
                     laux = make_float4(lr.aux[0], lr.aux[1], lr.aux[2], 0.f);
                     g1 = make_float4(lr.shadow_d.x, lr.shadow_d.y, lr.shadow_d.z, lr.shadow_maxt);
@@ -187,7 +199,14 @@ __global__ void __launch_bounds__(128, 4) k_shade(DevScene sc, RenderCfg cfg, Sa
                     g2 = make_float4(wiW1.x, wiW1.y, wiW1.z, SPT_INF);
                     pushMis = true;
                 }
-                if (have2 && pdf2 != 0.f) {
+                if (specMat) {
+                    if (have2) {
+                        flags |= RF_P | RF_P_SPEC;
+                        cP = make_float2(specR, specT);                  // f[c] = Kr[c] * specR + Kt[c] * specT
+                        sP = absdot(wiW2, n_s) / specPdf;
+                        g3 = make_float4(wiW2.x, wiW2.y, wiW2.z, 0.f);
+                    }
+                } else if (have2 && pdf2 != 0.f) {
                     flags |= RF_P;
                     cP = dir_coef(mtype, on, t2);
                     sP = absdot(wiW2, n_s) / pdf2;
@@ -264,6 +283,7 @@ __global__ void __launch_bounds__(32 * ACC_WARPS) k_accumulate(DevScene sc, Rend
         const bool active = q < n;
         const uint32_t i = active ? queue[q] : 0;
         float4 g0 = make_float4(0, 0, 0, 0);
+        bool specBounce = false;
         if (active) {
             const float4 c0 = wb.rec0[i], c1 = wb.rec1[i], c2 = wb.rec2[i];
             const uint32_t bits0 = __float_as_uint(c2.z), bits1 = __float_as_uint(c2.w);
@@ -307,6 +327,7 @@ __global__ void __launch_bounds__(32 * ACC_WARPS) k_accumulate(DevScene sc, Rend
                 if (lbB.kind) { cB = make_float2(c0.z, c0.w); sB = c1.w; }
             }
             const bool haveP = (flags & RF_P) != 0;
+            specBounce = (flags & RF_P_SPEC) != 0;
             sL *= nL; sB *= nL;
             stage[lane][0] = make_float4(cL.x, cL.y, cB.x, cB.y);
             stage[lane][1] = make_float4(cP.x, cP.y, sL, sB);
@@ -334,7 +355,12 @@ __global__ void __launch_bounds__(32 * ACC_WARPS) k_accumulate(DevScene sc, Rend
                     uint32_t emit = __float_as_uint(stage[v][5].y);
                     Tv[k] = 1.f;
                     Lv[k] = emit == 0 ? 0.f : (emit == 1 ? light0 : __ldg(sc.lights[emit - 1].spectrum + lane));
-                } else { Tv[k] = Tg[off]; Lv[k] = Lg[off]; }
+                } else {
+                    Tv[k] = Tg[off]; Lv[k] = Lg[off];
+                    // a vertex reached through a specular bounce adds what it emits (path.cpp:55-56)
+                    uint32_t emit = __float_as_uint(stage[v][5].y);
+                    if (emit) Lv[k] = Lv[k] + Tv[k] * (emit == 1 ? light0 : __ldg(sc.lights[emit - 1].spectrum + lane));
+                }
             }
 #pragma unroll
             for (int k = 0; k < ACC_GROUP; ++k) {
@@ -398,6 +424,7 @@ __global__ void __launch_bounds__(32 * ACC_WARPS) k_accumulate(DevScene sc, Rend
             g0 = wb.g0[i];
             wb.ray_o[i] = g0;
             wb.ray_d[i] = make_float4(g3.x, g3.y, g3.z, SPT_INF);
+            if (sc.has_specular) wb.pflags[i] = specBounce ? 1u : 0u;
         }
         queue_push(next_queue, next_count, alive, i);
         __syncwarp();
@@ -558,13 +585,14 @@ void spt_launch_compact_hits(int grid, cudaStream_t st, const uint32_t *queue, c
                              uint32_t *hit_queue, uint32_t *hit_count, uint32_t *miss_queue, uint32_t *miss_count, float *black_L) {
     k_compact_hits<<<grid, 256, 0, st>>>(queue, count, hit_slot, hit_queue, hit_count, miss_queue, miss_count, black_L);
 }
-void spt_launch_miss_env(int grid, cudaStream_t st, const DevScene &sc, const WaveBuffers &wb, const uint32_t *queue, const uint32_t *count) {
-    k_miss_env<<<grid, 128, 0, st>>>(sc, wb, queue, count);
+void spt_launch_miss_env(int grid, cudaStream_t st, const DevScene &sc, const WaveBuffers &wb, int bounce, const uint32_t *queue, const uint32_t *count) {
+    k_miss_env<<<grid, 128, 0, st>>>(sc, wb, bounce, queue, count);
 }
 void spt_launch_shade(int grid, cudaStream_t st, const DevScene &sc, const RenderCfg &cfg, const SampleSource &src, const WaveBuffers &wb,
                       int bounce, const uint32_t *queue, const uint32_t *count, uint32_t *shadow_count, uint32_t *mis_count,
                       uint32_t *elided_count) {
-    k_shade<<<grid, 128, 0, st>>>(sc, cfg, src, wb, bounce, queue, count, shadow_count, mis_count, elided_count);
+    if (sc.has_specular) k_shade<true><<<grid, 128, 0, st>>>(sc, cfg, src, wb, bounce, queue, count, shadow_count, mis_count, elided_count);
+    else k_shade<false><<<grid, 128, 0, st>>>(sc, cfg, src, wb, bounce, queue, count, shadow_count, mis_count, elided_count);
 }
 void spt_launch_accumulate(int grid, cudaStream_t st, const DevScene &sc, const RenderCfg &cfg, const WaveBuffers &wb, int bounce,
                            const uint32_t *queue, const uint32_t *count, uint32_t *next_queue, uint32_t *next_count) {

@@ -31,6 +31,7 @@ struct WaveBuffers {
     float4 *rec1;                     // {continuation a, b, sL = |cos| weight / pdf of the light sample, sB likewise for the MIS sample}
     float4 *rec2;                     // {sP = |cos| / pdf of the continuation, Russian-roulette draw, RF_* flags | light << 12, material | (emitter+1) << 16}
     float4 *laux;                     // infinite light only: RGB radiance of the sampled direction
+    uint32_t *pflags;                 // scenes with specular materials: bit 0 = the ray of this path left a specular bounce
     float2 *img_xy;
     float *T, *L;                     // [cap][NB]: band_off()
     uint32_t *pathQ[2], *shadowQ, *misQ;
@@ -54,8 +55,12 @@ struct RenderCfg {
 };
 
 // flags in rec2.z (low 12 bits)
-enum { RF_L = 1, RF_LDELTA = 2, RF_B = 4, RF_P = 8, RF_L_REFL = 16, RF_L_MF = 32, RF_B_REFL = 64, RF_B_MF = 128,
-       RF_P_REFL = 256, RF_P_MF = 512, RF_ON = 1024, RF_METAL = 2048 };
+enum { RF_L = 1,          // the light sample has a BSDF value: a shadow ray decides whether it counts
+       RF_P_SPEC = 2,     // the continuation was sampled from a specular BxDF (path.cpp:86)
+       RF_B = 4,          // the BSDF sample of the MIS estimate was traced
+       RF_P = 8,          // there is a continuation direction
+       RF_ON = 1024,      // matte with Oren-Nayar
+       RF_METAL = 2048 };
 
 // j-th pixel of this rank's tile set -> raster coordinates. Tiles are square with a power-of-two side
 // (tile_shift = log2), dealt round-robin to ranks; 32-bit arithmetic (spt_render bounds the counts).

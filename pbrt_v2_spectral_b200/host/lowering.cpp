@@ -45,6 +45,9 @@
 #include "materials/matte.h"
 #include "materials/plastic.h"
 #include "materials/metal.h"
+#include "materials/mirror.h"
+#include "materials/glass.h"
+#include "materials/subsurface.h"
 #include "lights/diffuse.h"
 #include "lights/point.h"
 #include "lights/infinite.h"
@@ -306,6 +309,27 @@ struct Lowerer {
             CopySpectrum(eta, row.spec0);
             CopySpectrum(k, row.spec1);
             row.p0 = rough;
+        } else if (const MirrorMaterial *mi = dynamic_cast<const MirrorMaterial *>(m)) {
+            Spectrum kr;
+            if (!CheckFlat(mi->bumpMap, mi->normalMap) || !ConstTex(mi->Kr, &kr, "Kr")) return false;
+            row.type = SPT_MAT_MIRROR;                            // SpecularReflection(Kr, FresnelNoOp), mirror.cpp:34-55
+            CopySpectrum(kr.Clamp(), row.spec0);
+        } else if (const GlassMaterial *gl = dynamic_cast<const GlassMaterial *>(m)) {
+            Spectrum kr, kt; float ior;
+            if (!CheckFlat(gl->bumpMap, gl->normalMap) || !ConstTex(gl->Kr, &kr, "Kr") || !ConstTex(gl->Kt, &kt, "Kt") ||
+                !ConstTex(gl->index, &ior, "index")) return false;
+            row.type = SPT_MAT_GLASS;                             // glass.cpp:34-58
+            CopySpectrum(kr.Clamp(), row.spec0);
+            CopySpectrum(kt.Clamp(), row.spec1);
+            row.p0 = ior;
+        } else if (const SubsurfaceMaterial *su = dynamic_cast<const SubsurfaceMaterial *>(m)) {
+            // Under a surface integrator that ignores the BSSRDF (path), the material is its BSDF:
+            // SpecularReflection(Kr, FresnelDielectric(1, eta)) - subsurface.cpp:40-58 - i.e. glass without Kt.
+            Spectrum kr; float eta;
+            if (!CheckFlat(su->bumpMap, su->normalMap) || !ConstTex(su->Kr, &kr, "Kr") || !ConstTex(su->eta, &eta, "eta")) return false;
+            row.type = SPT_MAT_GLASS;
+            CopySpectrum(kr.Clamp(), row.spec0);
+            row.p0 = eta;
         } else {
             return fail(std::string("unsupported material type ") + typeid(*m).name());
         }
