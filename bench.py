@@ -219,30 +219,49 @@ def main():
         sampler.start()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
-    class_ms = [0.0] * D.K_CLASSES
-    class_launches = [0] * D.K_CLASSES
-    class_rays = [0] * D.K_CLASSES
-    elided = 0
-    first_vertices = 0
     render_ms = 0.0
+    lanes_used = 1
     e0.record()
     for _ in range(args.steps):
         film_t.zero_()
-        scene.render(film, rp)                       # blocks until the library's stream has drained
+        scene.render(film, rp)                       # blocks until the library's streams have drained
         multi.reduce_film(film_t)                    # N > 1: the film is summed onto rank 0 over NVLink (NCCL)
         st = scene.stats()
         render_ms += st["render_ms"]
-        elided += st["mis_rays_elided"]
-        first_vertices += st["first_vertices"]
-        for k in range(D.K_CLASSES):
-            class_ms[k] += st["class_ms"][k]; class_launches[k] += st["class_launches"][k]; class_rays[k] += st["class_rays"][k]
+        lanes_used = st["lanes_used"]
     e1.record()
     barrier()
     if sampler:
         sampler.stop_flag = True
         sampler.join()
-    step_ms = e0.elapsed_time(e1) / args.steps
     launches = scene.stats()["kernel_launches"] - launches0
+    # ---- per-kernel device time: in the timed region the waves of a frame overlap on two streams, so the
+    # CUDA-event deltas of a kernel there include the other lane's work. The same frames are rendered
+    # again with every wave on ONE stream and each kernel timed between its own events.
+    class_ms = [0.0] * D.K_CLASSES
+    class_launches = [0] * D.K_CLASSES
+    class_rays = [0] * D.K_CLASSES
+    elided = 0
+    first_vertices = 0
+    serial_ms = 0.0
+    prof_steps = max(1, min(args.steps, 5))
+    scene.set_lanes(1)
+    scene.render(film, rp)
+    for _ in range(prof_steps):
+        film_t.zero_()
+        scene.render(film, rp)
+        st = scene.stats()
+        serial_ms += st["render_ms"]
+        elided += st["mis_rays_elided"]
+        first_vertices += st["first_vertices"]
+        for k in range(D.K_CLASSES):
+            class_ms[k] += st["class_ms"][k]; class_launches[k] += st["class_launches"][k]; class_rays[k] += st["class_rays"][k]
+    scene.set_lanes(2)
+    film_t.zero_()
+    scene.render(film, rp)
+    multi.reduce_film(film_t)
+    barrier()
+    step_ms = e0.elapsed_time(e1) / args.steps
     if dist is not None:
         t = torch.tensor([step_ms, render_ms / args.steps], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -341,12 +360,14 @@ def main():
         "config": {"workload": WORKLOAD_DESC, "camera_samples_per_step": n_samples_total,
                    "parallelism": "image tile sets (32x32, round-robin) x%d, scene replicated, NCCL film reduce" % world,
                    "l2": "per-step wave state (>2 GB) and film are larger than L2; no explicit flush"},
-        "mrays_per_s": rays_total / args.steps / (ms_per_step / 1e3) / 1e6 if world == 1 else None,
-        "rays_per_sample": rays_total / args.steps / (n_samples_total / world) if world else None,
-        "rays_per_sample_reference": (rays_total + elided) / args.steps / (n_samples_total / world) if world else None,
+        "mrays_per_s": rays_total / prof_steps / (ms_per_step / 1e3) / 1e6 if world == 1 else None,
+        "rays_per_sample": rays_total / prof_steps / (n_samples_total / world) if world else None,
+        "rays_per_sample_reference": (rays_total + elided) / prof_steps / (n_samples_total / world) if world else None,
         "rays_note": "rays_per_sample counts rays traced; the reference also traces the BSDF-sampled MIS rays of EstimateDirect that cannot "
                      "reach the sampled sphere light (contribution exactly zero) - counted in rays_per_sample_reference, not traced here",
-        "kernel_ms_per_step": {D.K_NAMES[k]: class_ms[k] / args.steps for k in range(D.K_CLASSES) if class_launches[k]},
+        "kernel_ms_per_step": {D.K_NAMES[k]: class_ms[k] / prof_steps for k in range(D.K_CLASSES) if class_launches[k]},
+        "kernel_ms_note": "timed region: the frame's waves overlap on %d streams (ms_per_step); per-kernel times, rooflines and ray counts come "
+                          "from %d more frames rendered with every wave on one stream (%.2f ms per frame), each kernel between its own CUDA events" % (lanes_used, prof_steps, serial_ms / prof_steps),
         "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": scene_bytes, "d2h_bytes_per_step": film_bytes,
                 "ms_per_step": e2e_s * 1e3, "path": "spt_scene_create+spt_film_create+spt_render+spt_film_download, host buffers (film read into page-locked host memory)",
                 "image_checksum": e2e_checksum},

@@ -81,13 +81,6 @@ int num_sms() {
     return n;
 }
 
-// Wave state (2.4 GB at the default capacity) outlives the scene that allocated it: a host that
-// renders frame after frame (scene_create -> render -> destroy) gets the same buffers back instead
-// of paying cudaMalloc/cudaFree of gigabytes per frame. One entry per device; spt_trim() frees them.
-struct WaveCache { int device; DevMem mem; WaveBuffers wb; uint32_t *counts; size_t counts_len; };
-std::mutex g_wave_mu;
-std::vector<WaveCache> g_wave_cache;
-
 }  // namespace
 
 struct SptScene {
@@ -98,25 +91,37 @@ struct SptScene {
     bool counters_on = false;
     int trace_variant = 1;           // trace_kernels.cuh: 0 reference nodes, 1 pair nodes (default)
     uint32_t fetch_threshold = 14;
+    int max_lanes = 2;               // spt_scene_set_lanes: 1 = every wave on one stream (per-kernel timing is then exact)
     bool has_env = false;            // an infinite light is present (escaped camera rays pick up Le)
     unsigned long long *counters = nullptr;
-    // wave buffers, allocated on first use and reused
-    DevMem wave_mem;
-    WaveBuffers wb{};
-    uint32_t *counts = nullptr;      // device queue lengths: per wave slot, (max_depth+2) x 4
+    // Wave state, allocated on first use (the blocks come back from the block cache frame after frame).
+    // Two LANES = two streams, each with its own wave buffers: spt_render deals the waves of a frame to
+    // them alternately, so the drain of one wave's persistent trace kernel (a few long rays keep a
+    // handful of warps busy for ~50-90 us while the machine empties) is covered by the other wave's
+    // kernels instead of being paid 18 times per frame per GPU.
+    struct Lane {
+        cudaStream_t stream = nullptr;
+        DevMem mem;
+        WaveBuffers wb{};
+        cudaEvent_t last = nullptr;  // previous mark of this lane
+        bool have_last = false;
+    } lane[2];
+    DevMem counts_mem;
+    uint32_t *counts = nullptr;      // device queue lengths: per wave, (max_depth+2) rows of SPT_ROW words
     size_t counts_len = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t stream = nullptr;   // = lane[0].stream
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evj = nullptr;
     SptStats stats{};
     uint64_t launches = 0;
-    // per-launch timing: an event after every launch of a render, attributed to the launch's class
-    std::vector<cudaEvent_t> ev_pool;
-    std::vector<int> ev_class;       // class of the launch that precedes event k (-1: start marker)
+    // per-launch timing: an event after every launch of a render, attributed to the launch's class;
+    // deltas are taken between consecutive events of the same lane
+    struct Mark { cudaEvent_t e; int cls; int lane; };
+    std::vector<Mark> marks;
     size_t ev_used = 0;
-    void mark(int cls) {
-        if (ev_used == ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); ev_pool.push_back(e); ev_class.push_back(0); }
-        ev_class[ev_used] = cls;
-        cudaEventRecord(ev_pool[ev_used++], stream);
+    void mark(int cls, int ln = 0) {
+        if (ev_used == marks.size()) { cudaEvent_t e; cudaEventCreate(&e); marks.push_back(Mark{e, 0, 0}); }
+        marks[ev_used].cls = cls; marks[ev_used].lane = ln;
+        cudaEventRecord(marks[ev_used++].e, lane[ln].stream);
         if (cls >= 0) { ++launches; ++stats.class_launches[cls]; }
     }
 };
@@ -144,9 +149,6 @@ void *spt_host_alloc(uint64_t bytes) {
 }
 void spt_host_free(void *p) { if (p) cudaFreeHost(p); }
 void spt_trim(void) {
-    std::lock_guard<std::mutex> lk(g_wave_mu);
-    for (WaveCache &c : g_wave_cache) c.mem.release();
-    g_wave_cache.clear();
     cudaDeviceSynchronize();
     g_blocks.trim();
 }
@@ -159,6 +161,7 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
     SptScene *s = new SptScene();
     if (const char *e = getenv("SPT_TRACE_VARIANT")) s->trace_variant = atoi(e);
     if (const char *e = getenv("SPT_FETCH_THRESHOLD")) s->fetch_threshold = (uint32_t)atoi(e);
+    if (const char *e = getenv("SPT_LANES")) s->max_lanes = atoi(e) >= 2 ? 2 : 1;
     DevScene &v = s->dev;
     memset(&v, 0, sizeof(v));
     // nodes: byte-identical copy, plus the hasQuadric bit in the reference's pad byte for leaves
@@ -266,7 +269,9 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
 #undef UP
     s->counters = m.alloc<unsigned long long>(4);
     if (!ok || !s->counters || cudaMemset(s->counters, 0, 32) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&s->lane[0].stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&s->lane[1].stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->evj, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess) {
         g_err = std::string("scene upload failed: ") + cudaGetErrorString(cudaGetLastError());
         m.release();
@@ -274,6 +279,7 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
         return nullptr;
     }
     v.counters = nullptr;
+    s->stream = s->lane[0].stream;
     return s;
 }
 
@@ -281,22 +287,12 @@ void spt_scene_destroy(SptScene *s) {
     if (!s) return;
     cudaDeviceSynchronize();
     s->mem.release();
-    if (s->wb.cap) {
-        int dev = 0; cudaGetDevice(&dev);
-        std::lock_guard<std::mutex> lk(g_wave_mu);
-        bool kept = false;
-        for (WaveCache &c : g_wave_cache)
-            if (c.device == dev) {
-                if (c.wb.cap < s->wb.cap) { c.mem.release(); c.mem = s->wave_mem; c.wb = s->wb; c.counts = s->counts; c.counts_len = s->counts_len; s->wave_mem.ptrs.clear(); }
-                kept = true;
-            }
-        if (!kept) { g_wave_cache.push_back(WaveCache{dev, s->wave_mem, s->wb, s->counts, s->counts_len}); s->wave_mem.ptrs.clear(); }
-    }
-    s->wave_mem.release();
-    if (s->stream) cudaStreamDestroy(s->stream);
+    s->counts_mem.release();
+    for (auto &ln : s->lane) { ln.mem.release(); if (ln.stream) cudaStreamDestroy(ln.stream); }
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
-    for (cudaEvent_t e : s->ev_pool) cudaEventDestroy(e);
+    if (s->evj) cudaEventDestroy(s->evj);
+    for (auto &m : s->marks) cudaEventDestroy(m.e);
     delete s;
 }
 
@@ -307,6 +303,12 @@ int spt_scene_enable_counters(SptScene *s, int on) {
     CU(cudaMemset(s->counters, 0, 32));
     s->stats.node_visits_closest = s->stats.prim_tests_closest = 0;
     s->stats.node_visits_any = s->stats.prim_tests_any = 0;
+    return SPT_OK;
+}
+
+int spt_scene_set_lanes(SptScene *s, int lanes) {
+    if (!s || lanes < 1 || lanes > 2) return fail(SPT_ERR_ARG, "lanes must be 1 or 2");
+    s->max_lanes = lanes;
     return SPT_OK;
 }
 
@@ -330,26 +332,15 @@ int spt_get_stats(SptScene *s, SptStats *out) {
 // cursors, escaped camera rays, MIS rays elided (could not reach the light), -}
 #define SPT_ROW 16
 
-static int ensure_wave(SptScene *s, uint32_t cap, int max_depth, size_t n_waves) {
-    cap = (cap + 31u) & ~31u;            // band_off() tiles 32 paths
+static int ensure_wave(SptScene *s, int n_lanes, uint32_t cap, int max_depth, size_t n_waves) {
+    cap = (cap + 31u) & ~31u;
     size_t need_counts = n_waves * (size_t)(max_depth + 2) * SPT_ROW;
-    if (s->wb.cap < cap) {
-        int dev = 0; cudaGetDevice(&dev);
-        std::lock_guard<std::mutex> lk(g_wave_mu);
-        for (size_t k = 0; k < g_wave_cache.size(); ++k)
-            if (g_wave_cache[k].device == dev && g_wave_cache[k].wb.cap >= cap) {
-                WaveCache &c = g_wave_cache[k];
-                s->wave_mem.release();
-                s->wave_mem = c.mem; s->wb = c.wb; s->counts = c.counts; s->counts_len = c.counts_len;
-                g_wave_cache.erase(g_wave_cache.begin() + k);
-                break;
-            }
-    }
-    if (s->wb.cap < cap) {
-        s->wave_mem.release();
-        s->counts = nullptr; s->counts_len = 0;
-        DevMem &m = s->wave_mem;
-        WaveBuffers &w = s->wb;
+    for (int li = 0; li < n_lanes; ++li) {
+        SptScene::Lane &ln = s->lane[li];
+        if (ln.wb.cap >= cap) continue;
+        ln.mem.release();
+        DevMem &m = ln.mem;
+        WaveBuffers &w = ln.wb;
         w.cap = cap;
         bool ok = true;
 #define AL(field, T, n) do { field = m.alloc<T>((size_t)(n)); if (!field) ok = false; } while (0)
@@ -363,11 +354,12 @@ static int ensure_wave(SptScene *s, uint32_t cap, int max_depth, size_t n_waves)
         AL(w.pathQ[0], uint32_t, cap); AL(w.pathQ[1], uint32_t, cap); AL(w.shadowQ, uint32_t, cap); AL(w.misQ, uint32_t, cap);
         AL(w.hitQ, uint32_t, cap); AL(w.missQ, uint32_t, cap);
 #undef AL
-        if (!ok) { s->wb.cap = 0; m.release(); return fail(SPT_ERR_CUDA, "out of device memory for wave buffers"); }
+        if (!ok) { w.cap = 0; m.release(); return fail(SPT_ERR_CUDA, "out of device memory for wave buffers"); }
     }
     if (s->counts_len < need_counts) {
-        s->counts = s->wave_mem.alloc<uint32_t>(need_counts);
-        if (!s->counts) return fail(SPT_ERR_CUDA, "out of device memory for queue counters");
+        s->counts_mem.release();
+        s->counts = s->counts_mem.alloc<uint32_t>(need_counts);
+        if (!s->counts) { s->counts_len = 0; return fail(SPT_ERR_CUDA, "out of device memory for queue counters"); }
         s->counts_len = need_counts;
     }
     return SPT_OK;
@@ -375,26 +367,26 @@ static int ensure_wave(SptScene *s, uint32_t cap, int max_depth, size_t n_waves)
 
 // One launch of the traversal kernel (variant chosen per scene; SPT_TRACE_VARIANT overrides for experiments).
 template <bool ANY>
-static void launch_trace(SptScene *s, int grid, const uint32_t *queue, const uint32_t *count, uint32_t *work,
+static void launch_trace(SptScene *s, cudaStream_t st, int grid, const uint32_t *queue, const uint32_t *count, uint32_t *work,
                          const float4 *ro, const float4 *rd, uint32_t *out_slot, float *out_t) {
     TraceArgs a; a.queue = queue; a.count = count; a.work = work; a.ro = ro; a.rd = rd; a.out_slot = out_slot; a.out_t = out_t;
     a.fetch_threshold = s->fetch_threshold;
-    spt_launch_trace(ANY, s->trace_variant, s->counters_on, grid, s->stream, s->dev, a);
+    spt_launch_trace(ANY, s->trace_variant, s->counters_on, grid, st, s->dev, a);
 }
 
 // Runs one wave: K1, then (K2, K5, K3, K2, K6) per bounce. counts: (max_depth+2) x 4 device words,
 // zeroed; row b = {path rays into bounce b, shadow rays of bounce b, MIS rays of bounce b, -}.
-static void run_wave(SptScene *s, const RenderCfg &cfg, const SampleSource &src, uint32_t *counts) {
-    cudaStream_t st = s->stream;
-    const WaveBuffers &wb = s->wb;
+static void run_wave(SptScene *s, const RenderCfg &cfg, const SampleSource &src, uint32_t *counts, int li = 0) {
+    cudaStream_t st = s->lane[li].stream;
+    const WaveBuffers &wb = s->lane[li].wb;
     const DevScene &sc = s->dev;
     int sms = num_sms();
     uint32_t n = cfg.n_samples;
     int gridN = (int)std::min<uint64_t>(((uint64_t)n + 255) / 256, (uint64_t)sms * 16);
     if (gridN < 1) gridN = 1;
-    s->mark(-1);
+    s->mark(-1, li);
     spt_launch_gen_camera(gridN, st, cfg, src, wb, counts + 0);
-    s->mark(SPT_K_GEN);
+    s->mark(SPT_K_GEN, li);
     int gridT = (int)std::min<uint64_t>(((uint64_t)n + 127) / 128, (uint64_t)sms * 16);
     if (gridT < 1) gridT = 1;
     int gridP = std::min(gridT, sms * 8);      // persistent trace kernels: resident blocks only
@@ -403,31 +395,34 @@ static void run_wave(SptScene *s, const RenderCfg &cfg, const SampleSource &src,
         uint32_t *q = wb.pathQ[b & 1], *qn = wb.pathQ[(b + 1) & 1];
         // camera rays that escape pick up the environment light (samplerrenderer.cpp:239-243)
         uint32_t *mq = (s->has_env && (b == 0 || sc.has_specular)) ? wb.missQ : nullptr;
-        launch_trace<false>(s, gridP, q, row + 0, row + 4, wb.ray_o, wb.ray_d, wb.hit_slot, wb.hit_t);
-        s->mark(SPT_K_TRACE_PATH);
+        launch_trace<false>(s, st, gridP, q, row + 0, row + 4, wb.ray_o, wb.ray_d, wb.hit_slot, wb.hit_t);
+        s->mark(SPT_K_TRACE_PATH, li);
         spt_launch_compact_hits(gridN, st, q, row + 0, wb.hit_slot, wb.hitQ, row + 3, mq, row + 7, (b == 0 && !s->has_env) ? wb.L : nullptr);
-        s->mark(SPT_K_SHADE);
-        if (mq) { spt_launch_miss_env(gridT, st, sc, wb, b, mq, row + 7); s->mark(SPT_K_SHADE); }
+        s->mark(SPT_K_SHADE, li);
+        if (mq) { spt_launch_miss_env(gridT, st, sc, wb, b, mq, row + 7); s->mark(SPT_K_SHADE, li); }
         spt_launch_shade(gridT, st, sc, cfg, src, wb, b, wb.hitQ, row + 3, row + 1, row + 2, row + 8);
-        s->mark(SPT_K_SHADE);
+        s->mark(SPT_K_SHADE, li);
         if (sc.n_lights > 0) {
-            launch_trace<true>(s, gridP, wb.shadowQ, row + 1, row + 5, wb.g0, wb.g1, wb.sh_slot, nullptr);
-            s->mark(SPT_K_TRACE_SHADOW);
-            launch_trace<false>(s, gridP, wb.misQ, row + 2, row + 6, wb.g0, wb.g2, wb.mis_slot, wb.mis_t);
-            s->mark(SPT_K_TRACE_MIS);
+            launch_trace<true>(s, st, gridP, wb.shadowQ, row + 1, row + 5, wb.g0, wb.g1, wb.sh_slot, nullptr);
+            s->mark(SPT_K_TRACE_SHADOW, li);
+            launch_trace<false>(s, st, gridP, wb.misQ, row + 2, row + 6, wb.g0, wb.g2, wb.mis_slot, wb.mis_t);
+            s->mark(SPT_K_TRACE_MIS, li);
         }
         spt_launch_accumulate(gridT, st, sc, cfg, wb, b, wb.hitQ, row + 3, qn, next + 0);
-        s->mark(SPT_K_ACCUMULATE);
+        s->mark(SPT_K_ACCUMULATE, li);
     }
 }
 
 // after the stream has drained: fold the per-launch event deltas into stats.class_ms
 static void collect_class_times(SptScene *s) {
-    for (size_t k = 1; k < s->ev_used; ++k) {
-        int cls = s->ev_class[k];
-        if (cls < 0) continue;
-        float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, s->ev_pool[k - 1], s->ev_pool[k]) == cudaSuccess) s->stats.class_ms[cls] += ms;
+    cudaEvent_t last[2] = { nullptr, nullptr };
+    for (size_t k = 0; k < s->ev_used; ++k) {
+        const SptScene::Mark &m = s->marks[k];
+        if (m.cls >= 0 && last[m.lane]) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, last[m.lane], m.e) == cudaSuccess) s->stats.class_ms[m.cls] += ms;
+        }
+        last[m.lane] = m.e;
     }
     s->ev_used = 0;
 }
@@ -476,8 +471,8 @@ static int trace_dev(SptScene *s, bool any, const float4 *ro, const float4 *rd, 
     if (grid < 1) grid = 1;
     cudaStream_t st = s->stream;
     cudaEventRecord(s->ev0, st);
-    if (any) launch_trace<true>(s, grid, nullptr, count_dev, count_dev + 1, ro, rd, slot, t);
-    else launch_trace<false>(s, grid, nullptr, count_dev, count_dev + 1, ro, rd, slot, t);
+    if (any) launch_trace<true>(s, st, grid, nullptr, count_dev, count_dev + 1, ro, rd, slot, t);
+    else launch_trace<false>(s, st, grid, nullptr, count_dev, count_dev + 1, ro, rd, slot, t);
     cudaEventRecord(s->ev1, st);
     s->launches += 1;
     CU(cudaStreamSynchronize(st));
@@ -573,7 +568,7 @@ int spt_shade_samples(SptScene *s, const SptCameraDesc *cam, int32_t max_depth, 
     if (!s || !cam || !samples || !out_L) return fail(SPT_ERR_ARG, "null argument");
     if (n == 0) return SPT_OK;
     if (n > (1u << 26)) return fail(SPT_ERR_ARG, "too many samples for one call");
-    int rc = ensure_wave(s, (uint32_t)n, max_depth, 1);
+    int rc = ensure_wave(s, 1, (uint32_t)n, max_depth, 1);
     if (rc != SPT_OK) return rc;
     DevMem m;
     float *dsmp = m.upload(samples, n * 37);
@@ -589,7 +584,7 @@ int spt_shade_samples(SptScene *s, const SptCameraDesc *cam, int32_t max_depth, 
     cudaMemsetAsync(s->counts, 0, nc * 4, s->stream);
     reset_class_stats(s);
     run_wave(s, cfg, src, s->counts);
-    spt_launch_gather_L(s->stream, s->wb.L, s->wb.cap, (uint32_t)n, dout);
+    spt_launch_gather_L(s->stream, s->lane[0].wb.L, s->lane[0].wb.cap, (uint32_t)n, dout);
     std::vector<uint32_t> hc(nc);
     cudaMemcpyAsync(hc.data(), s->counts, nc * 4, cudaMemcpyDeviceToHost, s->stream);
     cudaError_t e = cudaMemcpyAsync(out_L, dout, n * NB * sizeof(float), cudaMemcpyDeviceToHost, s->stream);
@@ -734,11 +729,22 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
     uint64_t ntiles = (uint64_t)cfg.tilesX * cfg.tilesY;
     uint64_t local_tiles = ntiles > (uint64_t)cfg.rank ? (ntiles - cfg.rank + nranks - 1) / nranks : 0;
     uint64_t local_pixels = local_tiles * (uint64_t)cfg.tile * cfg.tile;
-    uint64_t wave_pixels = rp->wave_pixels > 0 ? (uint64_t)rp->wave_pixels : std::max<uint64_t>(1, (1u << 25) / (uint64_t)rp->spp);   // 2^25 paths of state = 17 GB of the 180 GB
+    // Waves: by default the rank's pixels are cut into an even number of waves of at most 2^24 paths
+    // (8.6 GB of state each) dealt alternately to the two lanes; small jobs run as one wave on one lane.
+    const uint64_t local_samples = local_pixels * (uint64_t)rp->spp;
+    const uint64_t lane_cap_pixels = std::max<uint64_t>(1, (1u << 24) / (uint64_t)rp->spp);
+    uint64_t wave_pixels;
+    if (rp->wave_pixels > 0) wave_pixels = (uint64_t)rp->wave_pixels;
+    else if (s->max_lanes >= 2 && local_samples >= (1u << 21)) {
+        uint64_t nw = std::max<uint64_t>(2, (local_pixels + lane_cap_pixels - 1) / lane_cap_pixels);
+        nw += nw & 1;
+        wave_pixels = (local_pixels + nw - 1) / nw;
+    } else wave_pixels = 2 * lane_cap_pixels;
     wave_pixels = std::min<uint64_t>(wave_pixels, std::max<uint64_t>(local_pixels, 1));
     if (wave_pixels * rp->spp > (1ull << 27)) wave_pixels = (1ull << 27) / rp->spp;
     size_t n_waves = (size_t)((local_pixels + wave_pixels - 1) / wave_pixels);
-    int rc = ensure_wave(s, (uint32_t)(wave_pixels * rp->spp), rp->max_depth, std::max<size_t>(n_waves, 1));
+    const int n_lanes = (s->max_lanes >= 2 && n_waves >= 2) ? 2 : 1;
+    int rc = ensure_wave(s, n_lanes, (uint32_t)(wave_pixels * rp->spp), rp->max_depth, std::max<size_t>(n_waves, 1));
     if (rc != SPT_OK) return rc;
     size_t per_wave = (size_t)(rp->max_depth + 2) * SPT_ROW;
     cudaStream_t st = s->stream;
@@ -747,17 +753,25 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
     FilmView fv; fv.d = film->desc; fv.pix = film->pix; fv.table = film->table;
     reset_class_stats(s);
     CU(cudaEventRecord(s->ev0, st));
+    if (n_lanes == 2) CU(cudaStreamWaitEvent(s->lane[1].stream, s->ev0, 0));       // fork
     uint64_t samples = 0;
     for (size_t w = 0; w < n_waves; ++w) {
+        const int li = (int)(w % (size_t)n_lanes);
         cfg.pixel_base = (uint64_t)w * wave_pixels;
         uint64_t np = std::min<uint64_t>(wave_pixels, local_pixels - cfg.pixel_base);
         cfg.n_samples = (uint32_t)(np * rp->spp);
-        run_wave(s, cfg, src, s->counts + w * per_wave);
+        run_wave(s, cfg, src, s->counts + w * per_wave, li);
         unsigned gw = (unsigned)std::min<uint64_t>((np * 32 + 255) / 256, (uint64_t)num_sms() * 16);
-        spt_launch_film_add((int)gw, st, fv, s->dev.tables, s->wb.img_xy, s->wb.L, s->wb.cap, cfg.n_samples, rp->spp);
-        s->mark(SPT_K_FILM);
+        const WaveBuffers &wb = s->lane[li].wb;
+        spt_launch_film_add((int)gw, s->lane[li].stream, fv, s->dev.tables, wb.img_xy, wb.L, wb.cap, cfg.n_samples, rp->spp);
+        s->mark(SPT_K_FILM, li);
+    }
+    if (n_lanes == 2) {                                                             // join
+        CU(cudaEventRecord(s->evj, s->lane[1].stream));
+        CU(cudaStreamWaitEvent(st, s->evj, 0));
     }
     CU(cudaEventRecord(s->ev1, st));
+    s->stats.lanes_used = n_lanes;
     std::vector<uint32_t> hc(std::max<size_t>(n_waves, 1) * per_wave);
     CU(cudaMemcpyAsync(hc.data(), s->counts, hc.size() * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));

@@ -66,7 +66,8 @@ class SptStats(C.Structure):
                 ("kernel_launches", C.c_uint64),
                 ("render_ms", C.c_double), ("trace_ms", C.c_double),
                 ("class_ms", C.c_double * K_CLASSES), ("class_launches", C.c_uint64 * K_CLASSES),
-                ("class_rays", C.c_uint64 * K_CLASSES), ("mis_rays_elided", C.c_uint64), ("first_vertices", C.c_uint64)]
+                ("class_rays", C.c_uint64 * K_CLASSES), ("mis_rays_elided", C.c_uint64), ("first_vertices", C.c_uint64),
+                ("lanes_used", C.c_int32), ("pad_", C.c_int32)]
 
 
 # row sizes of the table structs (bytes), for sanity checks against the container file
