@@ -256,12 +256,13 @@ def main():
         first_vertices += st["first_vertices"]
         for k in range(D.K_CLASSES):
             class_ms[k] += st["class_ms"][k]; class_launches[k] += st["class_launches"][k]; class_rays[k] += st["class_rays"][k]
-    scene.set_lanes(2)
+    scene.set_lanes(int(os.environ.get("SPT_LANES", "4")))
     film_t.zero_()
     scene.render(film, rp)
     multi.reduce_film(film_t)
     barrier()
     step_ms = e0.elapsed_time(e1) / args.steps
+    sys.stderr.write("[rank %d] render %.3f ms/step (library events), step incl. film zero + reduce %.3f ms, serialized kernels %.3f ms\n" % (rank, render_ms / args.steps, step_ms, serial_ms / prof_steps))
     if dist is not None:
         t = torch.tensor([step_ms, render_ms / args.steps], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -372,6 +373,7 @@ def main():
                 "ms_per_step": e2e_s * 1e3, "path": "spt_scene_create+spt_film_create+spt_render+spt_film_download, host buffers (film read into page-locked host memory)",
                 "image_checksum": e2e_checksum},
         "gpu_launches": launches,
+        "render_ms_max_rank": render_only_ms, "step_ms_max_rank": step_ms,
         "roofline": roofline,
         "roofline_by_kernel": roofline_by_kernel,
         "clocks": sampler.summary() if sampler else None,

@@ -200,8 +200,8 @@ typedef struct SptStats {
      * zero; the reference traces them (they are counted in its rays/sample figure) */
     uint64_t mis_rays_elided;
     uint64_t first_vertices;        /* last spt_render: camera rays that found a surface (path vertices of bounce 0) */
-    int32_t  lanes_used;            /* last spt_render: streams the waves were dealt to (1 or 2); with 2, kernels of the
-                                       two lanes overlap and class_ms sums per-lane event deltas (can exceed render_ms) */
+    int32_t  lanes_used;            /* last spt_render: streams the waves were dealt to; with more than one, kernels of the
+                                       lanes overlap and class_ms sums per-lane event deltas (can exceed render_ms) */
     int32_t  pad_;
 } SptStats;
 
@@ -223,8 +223,9 @@ void        spt_trim(void);
 /* Scene: uploads every table to HBM (replaces nothing in the reference; it is the hand-off). */
 SptScene *spt_scene_create(const SptSceneDesc *desc);
 void      spt_scene_destroy(SptScene *scene);
-/* Waves of a frame are dealt to two streams by default so that the drain of one wave's persistent trace
- * kernel overlaps the other wave's work; lanes = 1 keeps everything on one stream (exact per-kernel times). */
+/* Waves of a frame are dealt to several streams ("lanes", 1..4, default 4) so that the drain of one wave's
+ * persistent trace kernel overlaps the other waves' work; lanes = 1 keeps everything on one stream (exact
+ * per-kernel times). */
 int       spt_scene_set_lanes(SptScene *scene, int lanes);
 int       spt_scene_enable_counters(SptScene *scene, int on);
 int       spt_get_stats(SptScene *scene, SptStats *out);

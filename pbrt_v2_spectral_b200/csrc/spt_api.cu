@@ -83,6 +83,7 @@ int num_sms() {
 
 }  // namespace
 
+#define SPT_MAX_LANES 4
 struct SptScene {
     DevMem mem;
     DevScene dev;
@@ -91,7 +92,8 @@ struct SptScene {
     bool counters_on = false;
     int trace_variant = 1;           // trace_kernels.cuh: 0 reference nodes, 1 pair nodes (default)
     uint32_t fetch_threshold = 14;
-    int max_lanes = 2;               // spt_scene_set_lanes: 1 = every wave on one stream (per-kernel timing is then exact)
+    int max_lanes = 4;               // spt_scene_set_lanes: 1 = every wave on one stream (per-kernel timing is then exact)
+    cudaEvent_t evjoin[SPT_MAX_LANES] = {};
     bool has_env = false;            // an infinite light is present (escaped camera rays pick up Le)
     unsigned long long *counters = nullptr;
     // Wave state, allocated on first use (the blocks come back from the block cache frame after frame).
@@ -105,12 +107,12 @@ struct SptScene {
         WaveBuffers wb{};
         cudaEvent_t last = nullptr;  // previous mark of this lane
         bool have_last = false;
-    } lane[2];
+    } lane[SPT_MAX_LANES];
     DevMem counts_mem;
     uint32_t *counts = nullptr;      // device queue lengths: per wave, (max_depth+2) rows of SPT_ROW words
     size_t counts_len = 0;
     cudaStream_t stream = nullptr;   // = lane[0].stream
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evj = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     SptStats stats{};
     uint64_t launches = 0;
     // per-launch timing: an event after every launch of a render, attributed to the launch's class;
@@ -125,6 +127,13 @@ struct SptScene {
         if (cls >= 0) { ++launches; ++stats.class_launches[cls]; }
     }
 };
+
+static bool make_lanes(SptScene *s) {
+    for (int k = 0; k < SPT_MAX_LANES; ++k)
+        if (cudaStreamCreateWithFlags(&s->lane[k].stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s->evjoin[k], cudaEventDisableTiming) != cudaSuccess) return false;
+    return true;
+}
 
 struct SptFilm {
     SptFilmDesc desc;
@@ -161,7 +170,7 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
     SptScene *s = new SptScene();
     if (const char *e = getenv("SPT_TRACE_VARIANT")) s->trace_variant = atoi(e);
     if (const char *e = getenv("SPT_FETCH_THRESHOLD")) s->fetch_threshold = (uint32_t)atoi(e);
-    if (const char *e = getenv("SPT_LANES")) s->max_lanes = atoi(e) >= 2 ? 2 : 1;
+    if (const char *e = getenv("SPT_LANES")) s->max_lanes = std::min(std::max(atoi(e), 1), SPT_MAX_LANES);
     DevScene &v = s->dev;
     memset(&v, 0, sizeof(v));
     // nodes: byte-identical copy, plus the hasQuadric bit in the reference's pad byte for leaves
@@ -269,9 +278,7 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
 #undef UP
     s->counters = m.alloc<unsigned long long>(4);
     if (!ok || !s->counters || cudaMemset(s->counters, 0, 32) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&s->lane[0].stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&s->lane[1].stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&s->evj, cudaEventDisableTiming) != cudaSuccess ||
+        !make_lanes(s) ||
         cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess) {
         g_err = std::string("scene upload failed: ") + cudaGetErrorString(cudaGetLastError());
         m.release();
@@ -291,7 +298,7 @@ void spt_scene_destroy(SptScene *s) {
     for (auto &ln : s->lane) { ln.mem.release(); if (ln.stream) cudaStreamDestroy(ln.stream); }
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
-    if (s->evj) cudaEventDestroy(s->evj);
+    for (cudaEvent_t e : s->evjoin) if (e) cudaEventDestroy(e);
     for (auto &m : s->marks) cudaEventDestroy(m.e);
     delete s;
 }
@@ -307,7 +314,7 @@ int spt_scene_enable_counters(SptScene *s, int on) {
 }
 
 int spt_scene_set_lanes(SptScene *s, int lanes) {
-    if (!s || lanes < 1 || lanes > 2) return fail(SPT_ERR_ARG, "lanes must be 1 or 2");
+    if (!s || lanes < 1 || lanes > SPT_MAX_LANES) return fail(SPT_ERR_ARG, "lanes must be 1..4");
     s->max_lanes = lanes;
     return SPT_OK;
 }
@@ -415,7 +422,7 @@ static void run_wave(SptScene *s, const RenderCfg &cfg, const SampleSource &src,
 
 // after the stream has drained: fold the per-launch event deltas into stats.class_ms
 static void collect_class_times(SptScene *s) {
-    cudaEvent_t last[2] = { nullptr, nullptr };
+    cudaEvent_t last[SPT_MAX_LANES] = {};
     for (size_t k = 0; k < s->ev_used; ++k) {
         const SptScene::Mark &m = s->marks[k];
         if (m.cls >= 0 && last[m.lane]) {
@@ -729,21 +736,24 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
     uint64_t ntiles = (uint64_t)cfg.tilesX * cfg.tilesY;
     uint64_t local_tiles = ntiles > (uint64_t)cfg.rank ? (ntiles - cfg.rank + nranks - 1) / nranks : 0;
     uint64_t local_pixels = local_tiles * (uint64_t)cfg.tile * cfg.tile;
-    // Waves: by default the rank's pixels are cut into an even number of waves of at most 2^24 paths
-    // (8.6 GB of state each) dealt alternately to the two lanes; small jobs run as one wave on one lane.
+    // Waves: by default the rank's pixels are cut into a multiple of max_lanes waves, each at most
+    // 2^25 / max_lanes paths (17 GB of state over all lanes), dealt to the lanes in turn; small jobs
+    // (< 2^19 paths per wave) use fewer lanes, down to one wave on one lane.
     const uint64_t local_samples = local_pixels * (uint64_t)rp->spp;
-    const uint64_t lane_cap_pixels = std::max<uint64_t>(1, (1u << 24) / (uint64_t)rp->spp);
+    int want_lanes = s->max_lanes;
+    while (want_lanes > 1 && local_samples < ((uint64_t)want_lanes << 19)) --want_lanes;
+    const uint64_t lane_cap_pixels = std::max<uint64_t>(1, ((1u << 25) / (uint64_t)want_lanes) / (uint64_t)rp->spp);
     uint64_t wave_pixels;
     if (rp->wave_pixels > 0) wave_pixels = (uint64_t)rp->wave_pixels;
-    else if (s->max_lanes >= 2 && local_samples >= (1u << 21)) {
-        uint64_t nw = std::max<uint64_t>(2, (local_pixels + lane_cap_pixels - 1) / lane_cap_pixels);
-        nw += nw & 1;
+    else {
+        uint64_t nw = std::max<uint64_t>((uint64_t)want_lanes, (local_pixels + lane_cap_pixels - 1) / lane_cap_pixels);
+        nw = (nw + want_lanes - 1) / want_lanes * want_lanes;
         wave_pixels = (local_pixels + nw - 1) / nw;
-    } else wave_pixels = 2 * lane_cap_pixels;
+    }
     wave_pixels = std::min<uint64_t>(wave_pixels, std::max<uint64_t>(local_pixels, 1));
     if (wave_pixels * rp->spp > (1ull << 27)) wave_pixels = (1ull << 27) / rp->spp;
     size_t n_waves = (size_t)((local_pixels + wave_pixels - 1) / wave_pixels);
-    const int n_lanes = (s->max_lanes >= 2 && n_waves >= 2) ? 2 : 1;
+    const int n_lanes = (int)std::min<size_t>((size_t)s->max_lanes, std::max<size_t>(n_waves, 1));
     int rc = ensure_wave(s, n_lanes, (uint32_t)(wave_pixels * rp->spp), rp->max_depth, std::max<size_t>(n_waves, 1));
     if (rc != SPT_OK) return rc;
     size_t per_wave = (size_t)(rp->max_depth + 2) * SPT_ROW;
@@ -753,7 +763,7 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
     FilmView fv; fv.d = film->desc; fv.pix = film->pix; fv.table = film->table;
     reset_class_stats(s);
     CU(cudaEventRecord(s->ev0, st));
-    if (n_lanes == 2) CU(cudaStreamWaitEvent(s->lane[1].stream, s->ev0, 0));       // fork
+    for (int k = 1; k < n_lanes; ++k) CU(cudaStreamWaitEvent(s->lane[k].stream, s->ev0, 0));       // fork
     uint64_t samples = 0;
     for (size_t w = 0; w < n_waves; ++w) {
         const int li = (int)(w % (size_t)n_lanes);
@@ -766,9 +776,9 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
         spt_launch_film_add((int)gw, s->lane[li].stream, fv, s->dev.tables, wb.img_xy, wb.L, wb.cap, cfg.n_samples, rp->spp);
         s->mark(SPT_K_FILM, li);
     }
-    if (n_lanes == 2) {                                                             // join
-        CU(cudaEventRecord(s->evj, s->lane[1].stream));
-        CU(cudaStreamWaitEvent(st, s->evj, 0));
+    for (int k = 1; k < n_lanes; ++k) {                                              // join
+        CU(cudaEventRecord(s->evjoin[k], s->lane[k].stream));
+        CU(cudaStreamWaitEvent(st, s->evjoin[k], 0));
     }
     CU(cudaEventRecord(s->ev1, st));
     s->stats.lanes_used = n_lanes;
