@@ -262,7 +262,7 @@ struct LightBand { int kind; IllumCoefs k; };
 static_assert(NB == 32, "k_accumulate and k_film_add map one band to one lane");
 #define ACC_WARPS 4
 #define ACC_GROUP 4          // vertices whose T/L rows are in flight together in phase B
-__global__ void __launch_bounds__(32 * ACC_WARPS) k_accumulate(DevScene sc, RenderCfg cfg, WaveBuffers wb, int bounce,
+__global__ void __launch_bounds__(32 * ACC_WARPS, 8) k_accumulate(DevScene sc, RenderCfg cfg, WaveBuffers wb, int bounce,
                                                                const uint32_t *__restrict__ queue, const uint32_t *__restrict__ count,
                                                                uint32_t *__restrict__ next_queue, uint32_t *__restrict__ next_count) {
     __shared__ float4 stage_all[ACC_WARPS][32][6];

@@ -129,11 +129,19 @@ __device__ inline bool sphere_intersect(const DevScene &sc, const SptQuadric &q,
         thit = t1;
         if (thit > ray.maxt) return false;
     }
-    v3 phit = ray_at(ray, thit);
-    if (phit.x == 0.f && phit.y == 0.f) phit.x = 1e-5f * radius;
-    float phi = atan2f(phit.y, phit.x);
-    if (phi < 0.f) phi += 2.f * PI_F;
-    if ((zmin > -radius && phit.z < zmin) || (zmax < radius && phit.z > zmax) || phi > phiMax) {
+    // A sphere that is not clipped (zmin <= -r, zmax >= r, phiMax = 2 pi: Radians(360) rounds to the float
+    // nearest 2 pi, which atan2f(...) + 2 pi never exceeds) accepts its first root: the phi / z tests
+    // of sphere.cpp:81-99 cannot reject, so an accept-only query skips atan2f.
+    const bool clipped = zmin > -radius || zmax < radius || phiMax < 2.f * PI_F;
+    v3 phit = V(0, 0, 0);
+    float phi = 0.f;
+    if (clipped || hit) {
+        phit = ray_at(ray, thit);
+        if (phit.x == 0.f && phit.y == 0.f) phit.x = 1e-5f * radius;
+        phi = atan2f(phit.y, phit.x);
+        if (phi < 0.f) phi += 2.f * PI_F;
+    }
+    if (clipped && ((zmin > -radius && phit.z < zmin) || (zmax < radius && phit.z > zmax) || phi > phiMax)) {
         if (thit == t1) return false;
         if (t1 > ray.maxt) return false;
         thit = t1;
