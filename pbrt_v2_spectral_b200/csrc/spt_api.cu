@@ -397,14 +397,16 @@ static void run_wave(SptScene *s, const RenderCfg &cfg, const SampleSource &src,
     int gridT = (int)std::min<uint64_t>(((uint64_t)n + 127) / 128, (uint64_t)sms * 16);
     if (gridT < 1) gridT = 1;
     int gridP = std::min(gridT, sms * 8);      // persistent trace kernels: resident blocks only
+    int gridC = (int)std::min<uint64_t>(((uint64_t)n + 2047) / 2048, (uint64_t)sms * 8);
+    if (gridC < 1) gridC = 1;
     for (int b = 0; b <= cfg.max_depth; ++b) {
         uint32_t *row = counts + SPT_ROW * b, *next = counts + SPT_ROW * (b + 1);
-        uint32_t *q = wb.pathQ[b & 1], *qn = wb.pathQ[(b + 1) & 1];
+        uint32_t *q = b == 0 ? nullptr : wb.pathQ[b & 1], *qn = wb.pathQ[(b + 1) & 1];     // camera rays: sample order, no queue
         // camera rays that escape pick up the environment light (samplerrenderer.cpp:239-243)
         uint32_t *mq = (s->has_env && (b == 0 || sc.has_specular)) ? wb.missQ : nullptr;
         launch_trace<false>(s, st, gridP, q, row + 0, row + 4, wb.ray_o, wb.ray_d, wb.hit_slot, wb.hit_t);
         s->mark(SPT_K_TRACE_PATH, li);
-        spt_launch_compact_hits(gridN, st, q, row + 0, wb.hit_slot, wb.hitQ, row + 3, mq, row + 7, (b == 0 && !s->has_env) ? wb.L : nullptr);
+        spt_launch_compact_hits(gridC, st, q, row + 0, wb.hit_slot, wb.hitQ, row + 3, mq, row + 7, (b == 0 && !s->has_env) ? wb.L : nullptr);
         s->mark(SPT_K_SHADE, li);
         if (mq) { spt_launch_miss_env(gridT, st, sc, wb, b, mq, row + 7); s->mark(SPT_K_SHADE, li); }
         spt_launch_shade(gridT, st, sc, cfg, src, wb, b, wb.hitQ, row + 3, row + 1, row + 2, row + 8);
@@ -790,10 +792,22 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
     cudaEventElapsedTime(&ms, s->ev0, s->ev1);
     s->stats.render_ms = ms;
     collect_class_times(s);
-    for (size_t w = 0; w < n_waves; ++w) samples += hc[w * per_wave];
+    // sample slots of tiles that overhang the sample extent carry rays that cannot hit anything: not samples
+    uint64_t slots = 0, valid_pixels = 0;
+    for (size_t w = 0; w < n_waves; ++w) slots += hc[w * per_wave];
+    for (uint64_t k = 0; k < local_tiles; ++k) {
+        uint64_t t = k * (uint64_t)nranks + (uint64_t)cfg.rank;
+        int tx = (int)(t % cfg.tilesX), ty = (int)(t / cfg.tilesX);
+        int w = std::min(cfg.tile, cfg.x1 - (cfg.x0 + tx * cfg.tile)), h = std::min(cfg.tile, cfg.y1 - (cfg.y0 + ty * cfg.tile));
+        if (w > 0 && h > 0) valid_pixels += (uint64_t)w * h;
+    }
+    samples = valid_pixels * (uint64_t)rp->spp;
     s->stats.class_rays[SPT_K_GEN] = samples; s->stats.class_rays[SPT_K_FILM] = samples;
     s->stats.camera_samples += samples;
     add_ray_stats(s, hc, rp->max_depth, n_waves);
+    const uint64_t overhang = slots > samples ? slots - samples : 0;
+    s->stats.closest_rays -= overhang;
+    s->stats.class_rays[SPT_K_TRACE_PATH] -= overhang;
     return SPT_OK;
 }
 

@@ -35,10 +35,16 @@ __global__ void __launch_bounds__(256) k_gen_camera(RenderCfg cfg, SampleSource 
             wb.ray_d[i] = make_float4(ray.d.x, ray.d.y, ray.d.z, ray.maxt);
             wb.img_xy[i] = make_float2(ix, iy);
         } else {
+            // a sample slot outside the sample extent (tiles overhang the image): a ray with an empty
+            // parameter range, which no box or primitive test accepts, and a film position K7 skips
+            wb.ray_o[i] = make_float4(0.f, 0.f, 0.f, 1.f);
+            wb.ray_d[i] = make_float4(0.f, 0.f, 1.f, -1.f);
             wb.img_xy[i] = make_float2(-1e30f, -1e30f);
         }
-        queue_push(wb.pathQ[0], count_out, valid, i);
     }
+    // bounce 0 walks the wave in sample order: no queue (queue == NULL means identity), one counter write
+    // instead of a million same-address atomics
+    if (blockIdx.x == 0 && threadIdx.x == 0) *count_out = cfg.n_samples;
 }
 
 __global__ void k_camera_rays(SptCameraDesc cam, const float *samples, uint32_t n, float *out) {
