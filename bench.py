@@ -150,6 +150,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--wave-pixels", type=int, default=0)
+    ap.add_argument("--workload", default=WORKLOAD, help="lowered scene under assets/_lowered (default: BASELINE config 1); "
+                    "synth_1m = config 5's recipe at 1 M triangles, BVH larger than L2 (no CPU arm)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -174,9 +176,20 @@ def main():
     capi.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
 
-    if not os.path.exists(SCENE_SPT):
-        raise SystemExit("lowered workload scene %s missing: run __graft_entry__.build() where the reference tree is" % SCENE_SPT)
-    lowered = LoweredScene.load(SCENE_SPT)
+    scene_spt = os.path.join(ROOT, "assets", "_lowered", args.workload + ".spt")
+    if not os.path.exists(scene_spt) and args.workload.startswith("synth") and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "bin", "oracle_dump")):
+        # synthetic workloads are generated on the spot (text -> the built reference's parser + BVH build -> lowered scene)
+        if rank == 0:
+            subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "make_golden.py"), "--only", args.workload], check=True,
+                           stdout=sys.stderr)
+        if dist is not None:
+            dist.barrier()
+    if not os.path.exists(scene_spt):
+        raise SystemExit("lowered workload scene %s missing: run __graft_entry__.build() where the reference tree is" % scene_spt)
+    lowered = LoweredScene.load(scene_spt)
+    workload_desc = WORKLOAD_DESC if args.workload == WORKLOAD else {
+        "synth_1m": "synthetic random-triangle scene (BASELINE config 5 recipe, SURVEY 8d) at 1 000 000 triangles, matte + plastic, sphere area light + "
+                    "constant infinite light, path maxdepth 5, 1024x576, LD 16 spp, box filter"}.get(args.workload, args.workload)
     rp = D.SptRenderParams.from_buffer_copy(bytes(lowered.params))
     rp.seed = 1
     rp = multi.rank_params(rp, rank, world)            # this rank's tile set (32x32 tiles, round-robin)
@@ -347,7 +360,7 @@ def main():
     roofline.update({
         "nodes_per_closest_ray": nodes_per_closest, "prim_tests_per_closest_ray": prims_per_closest,
         "nodes_per_shadow_ray": nodes_per_any, "prim_tests_per_shadow_ray": prims_per_any,
-        "note": "k_shade is FP32/FP64/INT instruction-issue bound (ncu: issue slots 41 % busy at 16 warps/SM, DRAM 7 %), the traversal "
+        "note": "config 1: k_shade is FP32/FP64/INT instruction-issue bound (ncu: issue slots 48 % busy at 16 warps/SM, DRAM 9 %), the traversal "
                 "kernels walk a 4 MB BVH that stays in L2/L1 (DRAM traffic = ray I/O): for both the HBM fraction is indicative only; "
                 "k_accumulate is the HBM-streaming kernel. Per-kernel lines in roofline_by_kernel; traffic from profiles/traffic.json "
                 "(ncu --set full, mean of the captured launches)"})
@@ -357,8 +370,9 @@ def main():
         "metric": "Msamples/sec (32-band spectral path trace)", "value": value, "unit": "Msamples/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-        "data": "reference scene file (killeroo-simple) lowered by the host side; no synthetic substitution",
-        "config": {"workload": WORKLOAD_DESC, "camera_samples_per_step": n_samples_total,
+        "data": "reference scene file (killeroo-simple) lowered by the host side; no synthetic substitution" if args.workload == WORKLOAD
+                else "synthetic scene written as .pbrt text, parsed, BVH-built and lowered by the reference's own code (oracle/make_golden.py)",
+        "config": {"workload": workload_desc, "camera_samples_per_step": n_samples_total,
                    "parallelism": "image tile sets (32x32, round-robin) x%d, scene replicated, NCCL film reduce" % world,
                    "l2": "per-step wave state (>2 GB) and film are larger than L2; no explicit flush"},
         "mrays_per_s": rays_total / prof_steps / (ms_per_step / 1e3) / 1e6 if world == 1 else None,
@@ -379,7 +393,7 @@ def main():
         "clocks": sampler.summary() if sampler else None,
         "image_checksum": image_sum,
     }
-    if world == 1 and not args.no_cpu_baseline and os.path.exists(REF_BIN):
+    if world == 1 and not args.no_cpu_baseline and os.path.exists(REF_BIN) and args.workload == WORKLOAD:
         v, cores, render_s, setup_s = cpu_reference_msamples()
         out["cpu_baseline"] = {"value": v, "unit": "Msamples/s", "cores": cores, "kind": "reference",
                                "sample": "reference pbrt on the same frame at %d of 64 spp (%.1f s render, %.2f s parse+BVH subtracted)" % (CPU_SAMPLE_SPP, render_s, setup_s)}

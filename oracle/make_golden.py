@@ -194,6 +194,8 @@ CONFIGS = {
     # config 4 with the shipped subsurface teapot (specular reflection BSDF); glass + mirror killeroos
     "ssenv_small":     (ssenv, 200, 200, 4, 6000, 40, 4096),
     "specular_small":  (specular, 176, 176, 4, 6000, 40, 2048),
+    # config 5 recipe at 1 M triangles (BVH + pair nodes + vertices = 176 MB, larger than L2): optional bench workload
+    "synth_1m":        (lambda w, h, spp, name, maxdepth=5: synth(w, h, spp, name, maxdepth, ntris=1000000, chunks=10), 1024, 576, 16, 0, 0, 0),
     # small committed fixture
     "tiny":            (tiny, 48, 48, 4, 700, 40, 0),
 }
@@ -208,18 +210,22 @@ def main():
     ap.add_argument("--images", action="store_true", help="also render reference .dat images")
     ap.add_argument("--only", default="", help="comma-separated config names")
     args = ap.parse_args()
-    if not os.path.isdir(REF):
+    names = [n for n in CONFIGS if not args.only or n in args.only.split(",")]
+    # the synthetic scenes are written from scratch and lowered by the BUILT reference (oracle/_ref/bin/oracle_dump,
+    # which travels with the repo): they can be generated where the reference source tree is absent (the GPU box)
+    need_ref = any(not n.startswith("synth") for n in names)
+    if need_ref and not os.path.isdir(REF):
         sys.exit("reference tree %s not present: golden vectors can only be generated where it is" % REF)
     os.makedirs(SCENES, exist_ok=True)
     os.makedirs(GOLDEN, exist_ok=True)
-    for d in ("geometry", "spds", "brdfs"):
-        dst = os.path.join(SCENES, d)
-        if not os.path.isdir(dst):
-            shutil.copytree(os.path.join(REF, "scenes", d), dst)
-    pfm = os.path.join(SCENES, "textures", "grace_latlong.pfm")
-    if not os.path.exists(pfm):
-        exr_to_pfm(os.path.join(REF, "scenes", "textures", "grace_latlong.exr"), pfm)
-    names = [n for n in CONFIGS if not args.only or n in args.only.split(",")]
+    if need_ref:
+        for d in ("geometry", "spds", "brdfs"):
+            dst = os.path.join(SCENES, d)
+            if not os.path.isdir(dst):
+                shutil.copytree(os.path.join(REF, "scenes", d), dst)
+        pfm = os.path.join(SCENES, "textures", "grace_latlong.pfm")
+        if not os.path.exists(pfm):
+            exr_to_pfm(os.path.join(REF, "scenes", "textures", "grace_latlong.exr"), pfm)
     for name in names:
         build, w, h, spp, npix, nrng, img_spp = CONFIGS[name]
         s = build(w, h, spp, name)
@@ -237,6 +243,10 @@ def main():
             os.makedirs(LOWERED, exist_ok=True)
             shutil.move(prefix + ".spt", os.path.join(LOWERED, name + ".spt"))
         print("%-16s lowered + golden in %.1fs" % (name, time.time() - t0), flush=True)
+        if name.startswith("synth"):                 # tens of MB of text per scene: regenerable, not shipped
+            for f in (name + ".pbrt", name + ".gpu.pbrt"):
+                if not (args.images and img_spp) or f.endswith(".gpu.pbrt"):
+                    os.remove(os.path.join(SCENES, f))
         if args.images and img_spp:
             iname = "%s_%dspp" % (name, img_spp)
             write(os.path.join(SCENES, iname + ".pbrt"), build(w, h, img_spp, iname))
@@ -245,6 +255,10 @@ def main():
             subprocess.run([os.path.join(OUT, "bin/pbrt"), "--quiet", "--ncores", str(ncores), iname + ".pbrt"],
                            cwd=SCENES, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
             shutil.move(os.path.join(SCENES, iname + ".dat"), os.path.join(GOLDEN, iname + ".dat"))
+            if name.startswith("synth"):
+                for f in (name + ".pbrt", iname + ".pbrt"):
+                    if os.path.exists(os.path.join(SCENES, f)):
+                        os.remove(os.path.join(SCENES, f))
             write(os.path.join(GOLDEN, iname + ".txt"), "ncores=%d seconds=%.1f\n" % (ncores, time.time() - t0))
             print("%-16s reference image %d spp in %.1fs" % (name, img_spp, time.time() - t0), flush=True)
 

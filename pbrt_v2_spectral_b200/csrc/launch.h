@@ -20,7 +20,7 @@ void spt_launch_compact_hits(int grid, cudaStream_t st, const uint32_t *queue, c
 void spt_launch_miss_env(int grid, cudaStream_t st, const DevScene &sc, const WaveBuffers &wb, int bounce, const uint32_t *queue, const uint32_t *count);
 void spt_launch_shade(int grid, cudaStream_t st, const DevScene &sc, const RenderCfg &cfg, const SampleSource &src, const WaveBuffers &wb,
                       int bounce, const uint32_t *queue, const uint32_t *count, uint32_t *shadow_count, uint32_t *mis_count,
-                      uint32_t *elided_count);
+                      uint32_t *elided_count, uint32_t *mis_any_count);
 void spt_launch_accumulate(int grid, cudaStream_t st, const DevScene &sc, const RenderCfg &cfg, const WaveBuffers &wb, int bounce,
                            const uint32_t *queue, const uint32_t *count, uint32_t *next_queue, uint32_t *next_count);
 void spt_launch_film_add(int grid, cudaStream_t st, const FilmView &film, const SptSpectralTables *tables, const float2 *img_xy,

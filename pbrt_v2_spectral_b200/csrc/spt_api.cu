@@ -336,7 +336,7 @@ int spt_get_stats(SptScene *s, SptStats *out) {
 
 // ---------------------------------------------------------------------------------------------
 // Device-side counters of one bounce: {path rays, shadow rays, MIS rays traced, hits, 3 x trace work
-// cursors, escaped camera rays, MIS rays elided (could not reach the light), -}
+// cursors, escaped camera rays, MIS rays elided (could not reach the light), MIS rays traced as any-hit + their cursor}
 #define SPT_ROW 16
 
 static int ensure_wave(SptScene *s, int n_lanes, uint32_t cap, int max_depth, size_t n_waves) {
@@ -359,7 +359,7 @@ static int ensure_wave(SptScene *s, int n_lanes, uint32_t cap, int max_depth, si
         AL(w.img_xy, float2, cap);
         AL(w.T, float, (size_t)cap * NB); AL(w.L, float, (size_t)cap * NB);
         AL(w.pathQ[0], uint32_t, cap); AL(w.pathQ[1], uint32_t, cap); AL(w.shadowQ, uint32_t, cap); AL(w.misQ, uint32_t, cap);
-        AL(w.hitQ, uint32_t, cap); AL(w.missQ, uint32_t, cap);
+        AL(w.hitQ, uint32_t, cap); AL(w.missQ, uint32_t, cap); AL(w.misAnyQ, uint32_t, cap);
 #undef AL
         if (!ok) { w.cap = 0; m.release(); return fail(SPT_ERR_CUDA, "out of device memory for wave buffers"); }
     }
@@ -409,13 +409,19 @@ static void run_wave(SptScene *s, const RenderCfg &cfg, const SampleSource &src,
         spt_launch_compact_hits(gridC, st, q, row + 0, wb.hit_slot, wb.hitQ, row + 3, mq, row + 7, (b == 0 && !s->has_env) ? wb.L : nullptr);
         s->mark(SPT_K_SHADE, li);
         if (mq) { spt_launch_miss_env(gridT, st, sc, wb, b, mq, row + 7); s->mark(SPT_K_SHADE, li); }
-        spt_launch_shade(gridT, st, sc, cfg, src, wb, b, wb.hitQ, row + 3, row + 1, row + 2, row + 8);
+        spt_launch_shade(gridT, st, sc, cfg, src, wb, b, wb.hitQ, row + 3, row + 1, row + 2, row + 8, row + 9);
         s->mark(SPT_K_SHADE, li);
         if (sc.n_lights > 0) {
             launch_trace<true>(s, st, gridP, wb.shadowQ, row + 1, row + 5, wb.g0, wb.g1, wb.sh_slot, nullptr);
             s->mark(SPT_K_TRACE_SHADOW, li);
             launch_trace<false>(s, st, gridP, wb.misQ, row + 2, row + 6, wb.g0, wb.g2, wb.mis_slot, wb.mis_t);
             s->mark(SPT_K_TRACE_MIS, li);
+            if (s->has_env) {
+                // EstimateDirect's BSDF-sampled ray towards an INFINITE light contributes Le iff it escapes
+                // (integrator.cpp:151-158: a hit primitive never is that light): an any-hit query
+                launch_trace<true>(s, st, gridP, wb.misAnyQ, row + 9, row + 10, wb.g0, wb.g2, wb.mis_slot, nullptr);
+                s->mark(SPT_K_TRACE_MIS, li);
+            }
         }
         spt_launch_accumulate(gridT, st, sc, cfg, wb, b, wb.hitQ, row + 3, qn, next + 0);
         s->mark(SPT_K_ACCUMULATE, li);
@@ -451,7 +457,8 @@ static void add_ray_stats(SptScene *s, const std::vector<uint32_t> &counts, int 
             s->stats.class_rays[SPT_K_SHADE] += row[3];
             s->stats.class_rays[SPT_K_ACCUMULATE] += row[3];
             s->stats.class_rays[SPT_K_TRACE_SHADOW] += row[1];
-            s->stats.class_rays[SPT_K_TRACE_MIS] += row[2];
+            s->stats.class_rays[SPT_K_TRACE_MIS] += row[2] + row[9];
+            s->stats.any_rays += row[9];
             s->stats.mis_rays_elided += row[8];
             if (b == 0) s->stats.first_vertices += row[3];
         }

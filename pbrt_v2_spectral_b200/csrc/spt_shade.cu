@@ -117,13 +117,13 @@ __device__ __forceinline__ float2 dir_coef(int mtype, bool on, const DirTerms &t
 template <bool SPEC>
 __global__ void __launch_bounds__(128, 4) k_shade(DevScene sc, RenderCfg cfg, SampleSource src, WaveBuffers wb, int bounce,
                                                const uint32_t *queue, const uint32_t *count,
-                                               uint32_t *shadow_count, uint32_t *mis_count, uint32_t *elided_count) {
+                                               uint32_t *shadow_count, uint32_t *mis_count, uint32_t *elided_count, uint32_t *mis_any_count) {
     uint32_t n = *count;
     const uint32_t cap = wb.cap;
     for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < ((n + 31u) & ~31u); q += gridDim.x * blockDim.x) {
         bool active = q < n;
         uint32_t i = active ? queue[q] : 0;
-        bool pushShadow = false, pushMis = false, elided = false;
+        bool pushShadow = false, pushMis = false, pushMisAny = false, elided = false;
         if (active) {
             uint32_t slot = wb.hit_slot[i];
             float4 o4 = wb.ray_o[i], d4 = wb.ray_d[i];
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(128, 4) k_shade(DevScene sc, RenderCfg cfg, Sa
                     cB = dir_coef(mtype, on, t1);
                     sB = absdot(wiW1, n_s) * weight / pdf1;
                     g2 = make_float4(wiW1.x, wiW1.y, wiW1.z, SPT_INF);
-                    pushMis = true;
+                    if (sc.lights[lightIdx].type == SPT_LIGHT_INFINITE) pushMisAny = true; else pushMis = true;
                 }
                 if (specMat) {
                     if (have2) {
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(128, 4) k_shade(DevScene sc, RenderCfg cfg, Sa
                 if (mtype == SPT_MAT_METAL) flags |= RF_METAL;
                 wb.g0[i] = make_float4(p.x, p.y, p.z, eps);
                 if (pushShadow) wb.g1[i] = g1;
-                if (pushMis) wb.g2[i] = g2;
+                if (pushMis || pushMisAny) wb.g2[i] = g2;
                 if (flags & RF_P) wb.g3[i] = g3;
                 wb.rec0[i] = make_float4(cL.x, cL.y, cB.x, cB.y);
                 wb.rec1[i] = make_float4(cP.x, cP.y, sL, sB);
@@ -269,6 +269,7 @@ __global__ void __launch_bounds__(128, 4) k_shade(DevScene sc, RenderCfg cfg, Sa
         }
         queue_push(wb.shadowQ, shadow_count, pushShadow, i);
         queue_push(wb.misQ, mis_count, pushMis, i);
+        queue_push(wb.misAnyQ, mis_any_count, pushMisAny, i);
         unsigned em = __ballot_sync(0xffffffffu, elided);
         if (em && (threadIdx.x & 31) == 0) atomicAdd(elided_count, (uint32_t)__popc(em));
     }
@@ -633,9 +634,9 @@ void spt_launch_miss_env(int grid, cudaStream_t st, const DevScene &sc, const Wa
 }
 void spt_launch_shade(int grid, cudaStream_t st, const DevScene &sc, const RenderCfg &cfg, const SampleSource &src, const WaveBuffers &wb,
                       int bounce, const uint32_t *queue, const uint32_t *count, uint32_t *shadow_count, uint32_t *mis_count,
-                      uint32_t *elided_count) {
-    if (sc.has_specular) k_shade<true><<<grid, 128, 0, st>>>(sc, cfg, src, wb, bounce, queue, count, shadow_count, mis_count, elided_count);
-    else k_shade<false><<<grid, 128, 0, st>>>(sc, cfg, src, wb, bounce, queue, count, shadow_count, mis_count, elided_count);
+                      uint32_t *elided_count, uint32_t *mis_any_count) {
+    if (sc.has_specular) k_shade<true><<<grid, 128, 0, st>>>(sc, cfg, src, wb, bounce, queue, count, shadow_count, mis_count, elided_count, mis_any_count);
+    else k_shade<false><<<grid, 128, 0, st>>>(sc, cfg, src, wb, bounce, queue, count, shadow_count, mis_count, elided_count, mis_any_count);
 }
 void spt_launch_accumulate(int grid, cudaStream_t st, const DevScene &sc, const RenderCfg &cfg, const WaveBuffers &wb, int bounce,
                            const uint32_t *queue, const uint32_t *count, uint32_t *next_queue, uint32_t *next_count) {

@@ -35,6 +35,7 @@ struct WaveBuffers {
     float2 *img_xy;
     float *T, *L;                     // [cap][NB]: band_off()
     uint32_t *pathQ[2], *shadowQ, *misQ;
+    uint32_t *misAnyQ;                // MIS rays towards an infinite light: only hit-or-escape matters, traced as any-hit rays
     uint32_t *hitQ, *missQ;           // path rays of the bounce that found a surface / escaped (bounce 0, env light)
 };
 

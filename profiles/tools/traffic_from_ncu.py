@@ -15,8 +15,8 @@ for r in rows[2:]:
         cls = "trace_closest_path"
     elif name.startswith("void k_trace"):
         cls = "trace_any_shadow"
-    elif name.startswith("k_shade"): cls = "shade"
-    elif name.startswith("k_accumulate"): cls = "accumulate"
+    elif "k_shade" in name.split("(")[0]: cls = "shade"
+    elif "k_accumulate" in name.split("(")[0]: cls = "accumulate"
     if not cls: continue
     b = float(r[ri]) * scale[units[ri]] + float(r[wi]) * scale[units[wi]]
     if float(r[ti]) < 0.5 and cls.startswith("trace"): continue      # the near-empty MIS launches
