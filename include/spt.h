@@ -72,14 +72,44 @@ typedef struct SptXform { float m[16]; float minv[16]; } SptXform;
  *           + SpecularTransmission(Kt, 1, index), each only if its spectrum is not black (src/materials/glass.cpp:34-58).
  *           `subsurface` lowers to GLASS with Kt = 0, index = eta: its BSDF under the path integrator
  *           (src/materials/subsurface.cpp:40-58)
+ *   SUBSTRATE spec0 = Kd.Clamp(), spec1 = Ks.Clamp(), p0 = uroughness, p1 = vroughness: FresnelBlend(Kd, Ks,
+ *           Anisotropic(1/u, 1/v))                                   (src/materials/substrate.cpp:34-56)
+ * Textured parameters: tex_kd >= 0 replaces spec0 of MATTE / PLASTIC / SUBSTRATE by the image
+ * texture textures[tex_kd] evaluated at the hit (Kd->Evaluate(dgs).Clamp()); tex_bump >= 0 is the displacement
+ * texture handed to Material::Bump (src/core/material.cpp:39-82). -1: the constant in the row / the constant-0
+ * displacement every reference material carries.
  */
-enum { SPT_MAT_MATTE = 0, SPT_MAT_PLASTIC = 1, SPT_MAT_METAL = 2, SPT_MAT_MIRROR = 3, SPT_MAT_GLASS = 4 };
+enum { SPT_MAT_MATTE = 0, SPT_MAT_PLASTIC = 1, SPT_MAT_METAL = 2, SPT_MAT_MIRROR = 3, SPT_MAT_GLASS = 4,
+       SPT_MAT_SUBSTRATE = 5 };
 typedef struct SptMaterial {
     int32_t type;
     float p0, p1, p2;
     float spec0[SPT_NBANDS];
     float spec1[SPT_NBANDS];
+    int32_t tex_kd, tex_bump;
+    int32_t pad_[2];
 } SptMaterial;
+
+/* Image texture = ImageTexture<RGBSpectrum,Spectrum> / ImageTexture<float,float> over a UVMapping2D
+ * (src/textures/imagemap.h:60-100, src/core/texture.cpp:80-90) with the MIPMap pyramid the reference built
+ * (src/core/mipmap.h:120-215: power-of-two resample, box-filtered levels), optionally under ScaleTextures whose
+ * other operand is a constant float (src/textures/scale.h:40-58; float textures only).
+ * Texels: level 0 starts at tex_texels[texel_offset], row-major [t][s], `channels` floats per texel (RGB as
+ * RGBSpectrum::ToRGB gives it, or the float); level l+1 (max(1,w/2) x max(1,h/2)) follows level l. */
+enum { SPT_WRAP_REPEAT = 0, SPT_WRAP_BLACK = 1, SPT_WRAP_CLAMP = 2 };    /* ImageWrap, src/core/mipmap.h:37-41 */
+typedef struct SptTexture {
+    int32_t channels;               /* 3: spectrum image map, 1: float image map */
+    int32_t width, height;          /* level 0 */
+    int32_t n_levels;
+    int32_t wrap;                   /* SPT_WRAP_* */
+    int32_t trilinear;              /* MIPMap::doTrilinear */
+    int32_t no_filter;              /* MIPMap::noFiltering (fork addition, mipmap.h:217-226) */
+    float   max_aniso;
+    float   su, sv, du, dv;         /* UVMapping2D */
+    float   scale;                  /* product of the constant operands of enclosing ScaleTextures (1: none) */
+    int32_t pad_;
+    uint64_t texel_offset;
+} SptTexture;
 
 /* Light table row.
  *   AREA     spectrum = Lemit; shapes [shape_first, shape_first+shape_count) of light_shapes[]
@@ -112,6 +142,7 @@ typedef struct SptSpectralTables {
     float cie_y[SPT_NBANDS];
     float yint;
     float rgb_illum[7][SPT_NBANDS];
+    float rgb_refl[7][SPT_NBANDS];  /* rgbRefl2Spect*, same order: FromRGB(rgb, SPECTRUM_REFLECTANCE) of image textures */
 } SptSpectralTables;
 
 typedef struct SptSceneDesc {
@@ -149,6 +180,10 @@ typedef struct SptSceneDesc {
     const float *env_func, *env_cdf, *env_func_int;
     const float *env_marg_func, *env_marg_cdf;
     float env_marg_int;
+    /* image textures */
+    uint32_t n_textures;   const SptTexture *textures;
+    uint64_t n_texels;     const float *tex_texels;
+    const float *ewa_weight_lut;    /* MIPMap::weightLut[128] as the reference computed it (mipmap.h:205-213), or NULL */
 } SptSceneDesc;
 
 /* PerspectiveCamera (src/cameras/perspective.cpp:33-106, src/core/camera.cpp:84-103). */
@@ -157,6 +192,8 @@ typedef struct SptCameraDesc {
     float camera_to_world[16];      /* CameraToWorld.startTransform->m (static scenes) */
     float lens_radius, focal_distance;
     float shutter_open, shutter_close;
+    float dx_camera[3], dy_camera[3];   /* PerspectiveCamera::dxCamera/dyCamera (perspective.cpp:45-46): the offset rays
+                                           of GenerateRayDifferential (:73-106) that image textures are filtered with */
 } SptCameraDesc;
 
 /* SpectralImageFilm (src/film/spectralImage.cpp:40-75,176-194). */
@@ -248,13 +285,15 @@ int spt_trace_any_dev(SptScene *scene, const float *rays_dev, uint64_t n, uint8_
 
 /* SamplerRenderer::Li + PathIntegrator::Li for caller-supplied sample vectors
  * (src/renderers/samplerrenderer.cpp:225-247, src/integrators/path.cpp:44-115).
+ * spp: Sampler::samplesPerPixel - the camera ray differentials are scaled by 1/sqrt(spp)
+ * (src/renderers/samplerrenderer.cpp:91, src/core/geometry.h:368-373) before image textures are filtered with them.
  * samples: n x 37 floats in the reference's Sample memory order {imageX,imageY,lensU,lensV,time,
  * oneD[0..13], twoD[0..8][2]} (src/core/sampler.cpp:88-117, src/integrators/path.cpp:33-41);
  * rng: n x n_rng floats consumed in order where the reference draws from RNG (bounces >= 3 and
  * Russian roulette, src/integrators/path.cpp:82,97; src/core/integrator.cpp:84-99).
  * out_L: n x SPT_NBANDS radiance BEFORE the NaN/negative/inf guards of
  * src/renderers/samplerrenderer.cpp:119-133. */
-int spt_shade_samples(SptScene *scene, const SptCameraDesc *cam, int32_t max_depth,
+int spt_shade_samples(SptScene *scene, const SptCameraDesc *cam, int32_t max_depth, int32_t spp,
                       const float *samples, const float *rng, int32_t n_rng, uint64_t n, float *out_L);
 
 /* Film: SpectralImageFilm pixels {c[SPT_NBANDS], weightSum} (src/film/spectralImage.h:74-84). */

@@ -162,6 +162,30 @@ def ssenv(w, h, spp, name, maxdepth=5):
     return set_filename(set_spp(set_res(s, w, h), spp), name)
 
 
+def metal_shipped(w, h, spp, name, maxdepth=5):
+    """BASELINE config 3 as shipped: Au teapot on the `substrate` floor with the lines.exr image map as Kd and,
+    scaled by -0.25, as bump map. Only what cannot run here is replaced: the Metropolis
+    renderer lines (path integrator instead, as BASELINE.json names it), .exr -> .pfm (no OpenEXR in this
+    build), and the uffizi environment map that is absent from the checkout -> the grace map."""
+    s = read(os.path.join(REF, "scenes/metal.pbrt"))
+    s = re.sub(r'^Renderer "metropolis".*\n', '', s, flags=re.M)
+    s = re.sub(r'^\s*"bool dodirectseparately".*\n', '', s, flags=re.M)
+    s = s.replace("textures/uffizi_latlong.exr", "textures/grace_latlong.pfm").replace("textures/lines.exr", "textures/lines.pfm")
+    s = s.replace("WorldBegin", 'SurfaceIntegrator "path" "integer maxdepth" [%d]\nWorldBegin' % maxdepth, 1)
+    assert "substrate" in s and "sbump" in s
+    return set_filename(set_spp(set_res(s, w, h), spp), name)
+
+
+def ssenv_shipped(w, h, spp, name, maxdepth=5):
+    """BASELINE config 4 as shipped (subsurface teapot, substrate floor with image-mapped Kd and bump map, grace
+    environment light): path integrator instead of dipolesubsurface, .exr -> .pfm."""
+    s = read(os.path.join(REF, "scenes/ss-envmap.pbrt"))
+    s = re.sub(r'SurfaceIntegrator "dipolesubsurface".*\n\s*"float maxerror".*\n', 'SurfaceIntegrator "path" "integer maxdepth" [%d]\n' % maxdepth, s)
+    s = s.replace("textures/grace_latlong.exr", "textures/grace_latlong.pfm").replace("textures/lines.exr", "textures/lines.pfm")
+    assert "substrate" in s and "sbump" in s
+    return set_filename(set_spp(set_res(s, w, h), spp), name)
+
+
 def specular(w, h, spp, name, maxdepth=5):
     """killeroo-simple with one killeroo of glass and one mirror: specular reflection / transmission,
     emitted light seen through specular bounces (path.cpp:55-56)."""
@@ -194,6 +218,9 @@ CONFIGS = {
     # config 4 with the shipped subsurface teapot (specular reflection BSDF); glass + mirror killeroos
     "ssenv_small":     (ssenv, 200, 200, 4, 6000, 40, 4096),
     "specular_small":  (specular, 176, 176, 4, 6000, 40, 2048),
+    # configs 3 and 4 with their shipped floor: substrate (FresnelBlend + Anisotropic), image-mapped Kd (EWA), bump map
+    "metal_shipped_small":  (metal_shipped, 200, 200, 4, 6000, 40, 1024),
+    "ssenv_shipped_small":  (ssenv_shipped, 200, 200, 4, 6000, 40, 4096),
     # config 5 recipe at 1 M triangles (BVH + pair nodes + vertices = 176 MB, larger than L2): optional bench workload
     "synth_1m":        (lambda w, h, spp, name, maxdepth=5: synth(w, h, spp, name, maxdepth, ntris=1000000, chunks=10), 1024, 576, 16, 0, 0, 0),
     # small committed fixture
@@ -223,9 +250,10 @@ def main():
             dst = os.path.join(SCENES, d)
             if not os.path.isdir(dst):
                 shutil.copytree(os.path.join(REF, "scenes", d), dst)
-        pfm = os.path.join(SCENES, "textures", "grace_latlong.pfm")
-        if not os.path.exists(pfm):
-            exr_to_pfm(os.path.join(REF, "scenes", "textures", "grace_latlong.exr"), pfm)
+        for tex in ("grace_latlong", "lines"):
+            pfm = os.path.join(SCENES, "textures", tex + ".pfm")
+            if not os.path.exists(pfm):
+                exr_to_pfm(os.path.join(REF, "scenes", "textures", tex + ".exr"), pfm)
     for name in names:
         build, w, h, spp, npix, nrng, img_spp = CONFIGS[name]
         s = build(w, h, spp, name)

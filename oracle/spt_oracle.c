@@ -77,11 +77,14 @@ typedef struct { v3 o, d; float mint, maxt; int depth; } Ray;
 static inline v3 ray_at(const Ray *r, float t) { return vadd(r->o, vmul(r->d, t)); }
 
 /* ------------------------------------------------------------------------------------------ */
-/* K1: PerspectiveCamera::GenerateRayDifferential, cameras/perspective.cpp:73-106 (differentials are
- * not consumed by the lowered constant-texture materials, SURVEY.md 8a T2, and are not produced) */
+/* K1: PerspectiveCamera::GenerateRayDifferential, cameras/perspective.cpp:73-106. The offset rays
+ * (rd != NULL) are consumed by image textures only; they are scaled as
+ * RayDifferential::ScaleDifferentials does for 1/sqrt(spp) (renderers/samplerrenderer.cpp:91,
+ * core/geometry.h:368-373). */
+typedef struct { int has; v3 rxo, ryo, rxd, ryd; } RayDiff;
 static void concentric_sample_disk(float u1, float u2, float *dx, float *dy);
 
-static void camera_ray(const SptCameraDesc *cam, const float *s, Ray *ray) {
+static void camera_ray_diff(const SptCameraDesc *cam, const float *s, int spp, Ray *ray, RayDiff *rd) {
     v3 Pras = V(s[0], s[1], 0.f);
     v3 Pcamera = xf_point(cam->raster_to_camera, Pras);
     v3 dir = normalize(Pcamera);
@@ -100,9 +103,25 @@ static void camera_ray(const SptCameraDesc *cam, const float *s, Ray *ray) {
         ray->o = V(lensU, lensV, 0.f);
         ray->d = normalize(vsub(Pfocus, ray->o));
     }
+    if (rd) {
+        v3 rxd = normalize(vadd(Pcamera, V(cam->dx_camera[0], cam->dx_camera[1], cam->dx_camera[2])));
+        v3 ryd = normalize(vadd(Pcamera, V(cam->dy_camera[0], cam->dy_camera[1], cam->dy_camera[2])));
+        rd->rxo = rd->ryo = xf_point(cam->camera_to_world, ray->o);
+        rd->rxd = xf_vector(cam->camera_to_world, rxd);
+        rd->ryd = xf_vector(cam->camera_to_world, ryd);
+        rd->has = 1;
+    }
     ray->o = xf_point(cam->camera_to_world, ray->o);
     ray->d = xf_vector(cam->camera_to_world, ray->d);
+    if (rd) {
+        float sc = 1.f / sqrtf((float)spp);
+        rd->rxo = vadd(ray->o, vmul(vsub(rd->rxo, ray->o), sc));
+        rd->ryo = vadd(ray->o, vmul(vsub(rd->ryo, ray->o), sc));
+        rd->rxd = vadd(ray->d, vmul(vsub(rd->rxd, ray->d), sc));
+        rd->ryd = vadd(ray->d, vmul(vsub(rd->ryd, ray->d), sc));
+    }
 }
+static void camera_ray(const SptCameraDesc *cam, const float *s, Ray *ray) { camera_ray_diff(cam, s, 1, ray, NULL); }
 
 void orc_camera_rays(const SptCameraDesc *cam, const float *samples, uint64_t n, float *out) {
     for (uint64_t i = 0; i < n; ++i) {
@@ -445,8 +464,10 @@ static float power_heuristic(int nf, float fPdf, int ng, float gPdf) {
  * plastic.cpp:34-61, metal.cpp:44-68). */
 enum { BX_LAMBERT = 0, BX_ORENNAYAR = 1, BX_MICROFACET_DIEL = 2, BX_MICROFACET_COND = 3,
        /* specular: reflection.cpp:130-160 */
-       BX_SPEC_REFL_NOOP = 4, BX_SPEC_REFL_DIEL = 5, BX_SPEC_TRANS = 6 };
-#define BX_IS_SPECULAR(k) ((k) >= BX_SPEC_REFL_NOOP)
+       BX_SPEC_REFL_NOOP = 4, BX_SPEC_REFL_DIEL = 5, BX_SPEC_TRANS = 6,
+       /* FresnelBlend over an Anisotropic distribution (substrate): reflection.cpp:217-236,369-459 */
+       BX_FRESNEL_BLEND = 7 };
+#define BX_IS_SPECULAR(k) ((k) >= BX_SPEC_REFL_NOOP && (k) <= BX_SPEC_TRANS)
 typedef struct {
     v3 nn, sn, tn, ng;
     int nBxDFs;
@@ -456,6 +477,8 @@ typedef struct {
     float exponent;             /* Blinn */
     float A, B;                 /* Oren-Nayar */
     float ior;                  /* glass / subsurface: FresnelDielectric(1, ior) */
+    float ex, ey;               /* Anisotropic */
+    float Rtex[NB];             /* Kd evaluated from an image texture at this hit (R[0] points here) */
 } BSDF;
 
 static v3 w2l(const BSDF *b, v3 v) { return V(dot(v, b->sn), dot(v, b->tn), dot(v, b->nn)); }
@@ -474,10 +497,205 @@ static inline float sin_phi(v3 w) { float s = sin_theta(w); if (s == 0.f) return
 static int is_black(const float *s);
 static float blinn_exponent(float e) { if (e > 10000.f || isnan(e)) e = 10000.f; return e; }   /* reflection.h:416-417 */
 
-/* Material::Bump constant-0 path + GetBSDF (core/material.cpp:39-82) */
-static void make_bsdf(const SptSceneDesc *sc, uint32_t slot, const Hit *dg, BSDF *b, v3 *n_shading) {
+
+/* ------------------------------------------------------------------------------------------ */
+/* Image textures: DifferentialGeometry::ComputeDifferentials, UVMapping2D::Map,
+ * MIPMap::Lookup (EWA / trilinear / the fork's noFiltering), FromRGB(SPECTRUM_REFLECTANCE). */
+typedef struct { float dudx, dvdx, dudy, dvdy; } UVDiff;
+
+static int solve2x2(const float A[2][2], const float B[2], float *x0, float *x1) {   /* core/transform.cpp:31-41 */
+    float det = A[0][0] * A[1][1] - A[0][1] * A[1][0];
+    if (fabsf(det) < 1e-10f) return 0;
+    *x0 = (A[1][1] * B[0] - A[0][1] * B[1]) / det;
+    *x1 = (A[0][0] * B[1] - A[1][0] * B[0]) / det;
+    if (isnan(*x0) || isnan(*x1)) return 0;
+    return 1;
+}
+static inline float vcomp(v3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+
+/* core/diffgeom.cpp:50-107 */
+static void compute_differentials(const Hit *dg, const RayDiff *rd, UVDiff *o) {
+    o->dudx = o->dvdx = o->dudy = o->dvdy = 0.f;
+    if (!rd || !rd->has) return;
+    v3 nn = dg->nn, p = dg->p;
+    float d = -dot(nn, p);
+    float tx = -(dot(nn, rd->rxo) + d) / dot(nn, rd->rxd);
+    if (isnan(tx)) return;
+    v3 px = vadd(rd->rxo, vmul(rd->rxd, tx));
+    float ty = -(dot(nn, rd->ryo) + d) / dot(nn, rd->ryd);
+    if (isnan(ty)) return;
+    v3 py = vadd(rd->ryo, vmul(rd->ryd, ty));
+    int axes[2];
+    if (fabsf(nn.x) > fabsf(nn.y) && fabsf(nn.x) > fabsf(nn.z)) { axes[0] = 1; axes[1] = 2; }
+    else if (fabsf(nn.y) > fabsf(nn.z)) { axes[0] = 0; axes[1] = 2; }
+    else { axes[0] = 0; axes[1] = 1; }
+    float A[2][2], Bx[2], By[2];
+    A[0][0] = vcomp(dg->dpdu, axes[0]); A[0][1] = vcomp(dg->dpdv, axes[0]);
+    A[1][0] = vcomp(dg->dpdu, axes[1]); A[1][1] = vcomp(dg->dpdv, axes[1]);
+    Bx[0] = vcomp(px, axes[0]) - vcomp(p, axes[0]); Bx[1] = vcomp(px, axes[1]) - vcomp(p, axes[1]);
+    By[0] = vcomp(py, axes[0]) - vcomp(p, axes[0]); By[1] = vcomp(py, axes[1]) - vcomp(p, axes[1]);
+    if (!solve2x2(A, Bx, &o->dudx, &o->dvdx)) { o->dudx = 0.f; o->dvdx = 0.f; }
+    if (!solve2x2(A, By, &o->dudy, &o->dvdy)) { o->dudy = 0.f; o->dvdy = 0.f; }
+}
+
+static int imod(int a, int b);
+static inline float log2_pbrt(float x) { float invLog2 = 1.f / logf(2.f); return logf(x) * invLog2; }   /* core/pbrt.h:243-246 */
+
+typedef struct { const float *texels; int w, h; } TexLevel;
+static TexLevel tex_level(const SptSceneDesc *sc, const SptTexture *t, int level) {
+    TexLevel l; l.texels = sc->tex_texels + t->texel_offset; l.w = t->width; l.h = t->height;
+    for (int i = 0; i < level; ++i) {
+        l.texels += (size_t)l.w * l.h * t->channels;
+        l.w = l.w / 2 > 1 ? l.w / 2 : 1; l.h = l.h / 2 > 1 ? l.h / 2 : 1;
+    }
+    return l;
+}
+/* MIPMap::Texel, core/mipmap.h:177-201 */
+static void tex_texel(const SptSceneDesc *sc, const SptTexture *t, int level, int s, int tt, float *out) {
+    TexLevel l = tex_level(sc, t, level);
+    if (t->wrap == SPT_WRAP_REPEAT) { s = imod(s, l.w); tt = imod(tt, l.h); }
+    else if (t->wrap == SPT_WRAP_CLAMP) { s = clampi(s, 0, l.w - 1); tt = clampi(tt, 0, l.h - 1); }
+    else if (s < 0 || s >= l.w || tt < 0 || tt >= l.h) { for (int k = 0; k < t->channels; ++k) out[k] = 0.f; return; }
+    const float *px = l.texels + ((size_t)tt * l.w + s) * t->channels;
+    for (int k = 0; k < t->channels; ++k) out[k] = px[k];
+}
+/* MIPMap::triangle, core/mipmap.h:258-270 */
+static void tex_triangle(const SptSceneDesc *sc, const SptTexture *t, int level, float s, float tt, float *out) {
+    level = clampi(level, 0, t->n_levels - 1);
+    TexLevel l = tex_level(sc, t, level);
+    s = s * l.w - 0.5f;
+    tt = tt * l.h - 0.5f;
+    int s0 = (int)floorf(s), t0 = (int)floorf(tt);
+    float ds = s - s0, dt = tt - t0;
+    float a[3], b[3], c[3], d[3];
+    tex_texel(sc, t, level, s0, t0, a); tex_texel(sc, t, level, s0, t0 + 1, b);
+    tex_texel(sc, t, level, s0 + 1, t0, c); tex_texel(sc, t, level, s0 + 1, t0 + 1, d);
+    for (int k = 0; k < t->channels; ++k)
+        out[k] = a[k] * ((1.f - ds) * (1.f - dt)) + b[k] * ((1.f - ds) * dt) + c[k] * (ds * (1.f - dt)) + d[k] * (ds * dt);
+}
+/* MIPMap::EWA, core/mipmap.h:322-377 */
+static void tex_ewa(const SptSceneDesc *sc, const SptTexture *t, int level, float s, float tt,
+                    float ds0, float dt0, float ds1, float dt1, float *out) {
+    if (level >= t->n_levels) { tex_texel(sc, t, t->n_levels - 1, 0, 0, out); return; }
+    TexLevel l = tex_level(sc, t, level);
+    s = s * l.w - 0.5f;
+    tt = tt * l.h - 0.5f;
+    ds0 *= l.w; dt0 *= l.h; ds1 *= l.w; dt1 *= l.h;
+    float A = dt0 * dt0 + dt1 * dt1 + 1;
+    float B = -2.f * (ds0 * dt0 + ds1 * dt1);
+    float C = ds0 * ds0 + ds1 * ds1 + 1;
+    float invF = 1.f / (A * C - B * B * 0.25f);
+    A *= invF; B *= invF; C *= invF;
+    float det = -B * B + 4.f * A * C;
+    float invDet = 1.f / det;
+    float uSqrt = sqrtf(det * C), vSqrt = sqrtf(A * det);
+    int s0 = (int)ceilf(s - 2.f * invDet * uSqrt), s1 = (int)floorf(s + 2.f * invDet * uSqrt);
+    int t0 = (int)ceilf(tt - 2.f * invDet * vSqrt), t1 = (int)floorf(tt + 2.f * invDet * vSqrt);
+    float sum[3] = { 0.f, 0.f, 0.f }, sumWts = 0.f;
+    for (int it = t0; it <= t1; ++it) {
+        float ttt = it - tt;
+        for (int is = s0; is <= s1; ++is) {
+            float ss = is - s;
+            float r2 = A * ss * ss + B * ss * ttt + C * ttt * ttt;
+            if (r2 < 1.) {
+                int li = (int)(r2 * 128);
+                float weight = sc->ewa_weight_lut[li < 127 ? li : 127];
+                float tx[3];
+                tex_texel(sc, t, level, is, it, tx);
+                for (int k = 0; k < t->channels; ++k) sum[k] += tx[k] * weight;
+                sumWts += weight;
+            }
+        }
+    }
+    for (int k = 0; k < t->channels; ++k) out[k] = sum[k] / sumWts;
+}
+/* MIPMap::Lookup(s,t,width), core/mipmap.h:215-255 */
+static void tex_lookup_tri(const SptSceneDesc *sc, const SptTexture *t, float s, float tt, float width, float *out) {
+    if (t->no_filter) {
+        s = s * t->width - 0.5f;
+        tt = tt * t->height - 0.5f;
+        tex_texel(sc, t, 0, (int)floorf(s + 0.5f), (int)floorf(tt + 0.5f), out);
+        return;
+    }
+    float level = t->n_levels - 1 + log2_pbrt(stdmaxf(width, 1e-8f));
+    if (level < 0) tex_triangle(sc, t, 0, s, tt, out);
+    else if (level >= t->n_levels - 1) tex_texel(sc, t, t->n_levels - 1, 0, 0, out);
+    else {
+        int iLevel = (int)floorf(level);
+        float delta = level - iLevel;
+        float a[3], b[3];
+        tex_triangle(sc, t, iLevel, s, tt, a);
+        tex_triangle(sc, t, iLevel + 1, s, tt, b);
+        for (int k = 0; k < t->channels; ++k) out[k] = a[k] * (1.f - delta) + b[k] * delta;
+    }
+}
+/* MIPMap::Lookup(s,t,ds0,dt0,ds1,dt1), core/mipmap.h:273-319 */
+static void tex_lookup(const SptSceneDesc *sc, const SptTexture *t, float s, float tt,
+                       float ds0, float dt0, float ds1, float dt1, float *out) {
+    if (t->trilinear || t->no_filter) {
+        tex_lookup_tri(sc, t, s, tt, 2.f * stdmaxf(stdmaxf(fabsf(ds0), fabsf(dt0)), stdmaxf(fabsf(ds1), fabsf(dt1))), out);
+        return;
+    }
+    if (ds0 * ds0 + dt0 * dt0 < ds1 * ds1 + dt1 * dt1) {
+        float tmp = ds0; ds0 = ds1; ds1 = tmp;
+        tmp = dt0; dt0 = dt1; dt1 = tmp;
+    }
+    float majorLength = sqrtf(ds0 * ds0 + dt0 * dt0);
+    float minorLength = sqrtf(ds1 * ds1 + dt1 * dt1);
+    if (minorLength * t->max_aniso < majorLength && minorLength > 0.f) {
+        float scale = majorLength / (minorLength * t->max_aniso);
+        ds1 *= scale; dt1 *= scale; minorLength *= scale;
+    }
+    if (minorLength == 0.f) { tex_triangle(sc, t, 0, s, tt, out); return; }
+    float lod = stdmaxf(0.f, t->n_levels - 1.f + log2_pbrt(minorLength));
+    int ilod = (int)floorf(lod);
+    float d = lod - ilod;
+    float a[3], b[3];
+    tex_ewa(sc, t, ilod, s, tt, ds0, dt0, ds1, dt1, a);
+    tex_ewa(sc, t, ilod + 1, s, tt, ds0, dt0, ds1, dt1, b);
+    for (int k = 0; k < t->channels; ++k) out[k] = a[k] * (1.f - d) + b[k] * d;
+}
+/* ImageTexture::Evaluate (textures/imagemap.cpp:88-97) over UVMapping2D::Map (core/texture.cpp:80-90); a float
+ * image is then multiplied by the constant of an enclosing ScaleTexture (textures/scale.h:45-47) */
+static void tex_evaluate(const SptSceneDesc *sc, const SptTexture *t, float u, float v, const UVDiff *df, float *out) {
+    float s = t->su * u + t->du, tt = t->sv * v + t->dv;
+    float dsdx = t->su * df->dudx, dtdx = t->sv * df->dvdx, dsdy = t->su * df->dudy, dtdy = t->sv * df->dvdy;
+    tex_lookup(sc, t, s, tt, dsdx, dtdx, dsdy, dtdy, out);
+    if (t->channels == 1) out[0] = out[0] * t->scale;
+}
+/* SampledSpectrum::FromRGB(rgb, SPECTRUM_REFLECTANCE), core/spectrum.cpp:92-133,175 */
+static void from_rgb_refl(const SptSpectralTables *t, const float rgb[3], float *r) {
+    enum { W = 0, Cy = 1, Mg = 2, Ye = 3, Rd = 4, Gr = 5, Bl = 6 };
+    for (int c = 0; c < NB; ++c) r[c] = 0.f;
+#define ADDR(coef, basis) do { float k_ = (coef); for (int c = 0; c < NB; ++c) r[c] += t->rgb_refl[basis][c] * k_; } while (0)
+    if (rgb[0] <= rgb[1] && rgb[0] <= rgb[2]) {
+        ADDR(rgb[0], W);
+        if (rgb[1] <= rgb[2]) { ADDR(rgb[1] - rgb[0], Cy); ADDR(rgb[2] - rgb[1], Bl); }
+        else { ADDR(rgb[2] - rgb[0], Cy); ADDR(rgb[1] - rgb[2], Gr); }
+    } else if (rgb[1] <= rgb[0] && rgb[1] <= rgb[2]) {
+        ADDR(rgb[1], W);
+        if (rgb[0] <= rgb[2]) { ADDR(rgb[0] - rgb[1], Mg); ADDR(rgb[2] - rgb[0], Bl); }
+        else { ADDR(rgb[2] - rgb[1], Mg); ADDR(rgb[0] - rgb[2], Rd); }
+    } else {
+        ADDR(rgb[2], W);
+        if (rgb[0] <= rgb[1]) { ADDR(rgb[0] - rgb[2], Ye); ADDR(rgb[1] - rgb[0], Gr); }
+        else { ADDR(rgb[1] - rgb[2], Ye); ADDR(rgb[0] - rgb[1], Rd); }
+    }
+#undef ADDR
+    for (int c = 0; c < NB; ++c) { r[c] *= .94f; r[c] = clampf(r[c], 0.f, INFINITY); }
+}
+
+/* Intersection::GetBSDF (core/intersection.cpp:39-47): ComputeDifferentials, GetShadingGeometry, then
+ * Material::Bump (core/material.cpp:39-82; the constant-0 displacement of SURVEY.md F6, or a float image map) and
+ * the material's GetBSDF. rd: the camera ray's offset rays at the first vertex, NULL afterwards (path.cpp:93). */
+static void make_bsdf(const SptSceneDesc *sc, uint32_t slot, const Hit *dg, const RayDiff *rd, BSDF *b, v3 *n_shading) {
     int flags = sc->prim_flags[slot];
+    const SptMaterial *m = sc->materials + sc->prim_material[slot];
+    const int textured = m->tex_kd >= 0 || m->tex_bump >= 0;
+    UVDiff df = { 0.f, 0.f, 0.f, 0.f };
+    if (textured) compute_differentials(dg, rd, &df);
     v3 s_dpdu = dg->dpdu, s_dpdv = dg->dpdv;      /* dgShading */
+    v3 s_nn = dg->nn, dndu = V(0, 0, 0), dndv = V(0, 0, 0);
     if (sc->prim_kind[slot] == SPT_PRIM_TRIANGLE && (flags & SPT_PF_HAS_N)) {
         /* Triangle::GetShadingGeometry, shapes/trianglemesh.cpp:285-360 */
         const int32_t *vi = sc->tri_vidx + 3 * (size_t)sc->prim_data[slot];
@@ -507,6 +725,36 @@ static void make_bsdf(const SptSceneDesc *sc, uint32_t slot, const Hit *dg, BSDF
         if (len2(ts) > 0.f) { ts = normalize(ts); ss = cross(ts, ns); }
         else coordinate_system(ns, &ss, &ts);
         s_dpdu = ss; s_dpdv = ts;
+        if (m->tex_bump >= 0) {
+            /* dndu, dndv (trianglemesh.cpp:331-351) and the shading DifferentialGeometry's own normal (diffgeom.cpp:32-47) */
+            float du1 = uv[0][0] - uv[2][0], du2 = uv[1][0] - uv[2][0];
+            float dv1 = uv[0][1] - uv[2][1], dv2 = uv[1][1] - uv[2][1];
+            v3 N0 = V(n0[0], n0[1], n0[2]), N1 = V(n1[0], n1[1], n1[2]), N2 = V(n2[0], n2[1], n2[2]);
+            v3 dn1 = vsub(N0, N2), dn2 = vsub(N1, N2);
+            float determinant = du1 * dv2 - dv1 * du2;
+            if (determinant != 0.f) {
+                float invdet = 1.f / determinant;
+                dndu = vmul(vsub(vmul(dn1, dv2), vmul(dn2, dv1)), invdet);
+                dndv = vmul(vadd(vmul(dn1, -du2), vmul(dn2, du1)), invdet);
+            }
+            dndu = xf_normal(xf->minv, dndu);
+            dndv = xf_normal(xf->minv, dndv);
+            s_nn = normalize(cross(ss, ts));
+            if (flags & SPT_PF_FLIP_NORMAL) s_nn = vmul(s_nn, -1.f);
+        }
+    }
+    if (m->tex_bump >= 0) {                                    /* Material::Bump, core/material.cpp:39-82 */
+        const SptTexture *bt = sc->textures + m->tex_bump;
+        float du = .5f * (fabsf(df.dudx) + fabsf(df.dudy));
+        if (du == 0.f) du = .01f;
+        float uDisplace, vDisplace, displace;
+        tex_evaluate(sc, bt, dg->u + du, dg->v, &df, &uDisplace);
+        float dv = .5f * (fabsf(df.dvdx) + fabsf(df.dvdy));
+        if (dv == 0.f) dv = .01f;
+        tex_evaluate(sc, bt, dg->u, dg->v + dv, &df, &vDisplace);
+        tex_evaluate(sc, bt, dg->u, dg->v, &df, &displace);
+        s_dpdu = vadd(vadd(s_dpdu, vmul(s_nn, (uDisplace - displace) / du)), vmul(dndu, displace));
+        s_dpdv = vadd(vadd(s_dpdv, vmul(s_nn, (vDisplace - displace) / dv)), vmul(dndv, displace));
     }
     /* Bump with a constant-0 displacement leaves dpdu/dpdv unchanged and recomputes the normal */
     v3 nn = normalize(cross(s_dpdu, s_dpdv));
@@ -517,10 +765,22 @@ static void make_bsdf(const SptSceneDesc *sc, uint32_t slot, const Hit *dg, BSDF
     b->sn = normalize(s_dpdu);
     b->tn = cross(b->nn, b->sn);
     *n_shading = nn;
-    const SptMaterial *m = sc->materials + sc->prim_material[slot];
-    b->eta = b->k = NULL; b->exponent = 0.f; b->A = b->B = 0.f;
-    if (m->type == SPT_MAT_MATTE) {
-        b->nBxDFs = 1; b->R[0] = m->spec0;
+    b->eta = b->k = NULL; b->exponent = 0.f; b->A = b->B = 0.f; b->ex = b->ey = 0.f;
+    const float *kd = m->spec0;
+    if (m->tex_kd >= 0) {                                      /* Kd->Evaluate(dgs).Clamp(): imagemap.cpp:88-97, imagemap.h:88-92 */
+        float rgb[3];
+        tex_evaluate(sc, sc->textures + m->tex_kd, dg->u, dg->v, &df, rgb);
+        from_rgb_refl(&sc->tables, rgb, b->Rtex);
+        kd = b->Rtex;
+    }
+    if (m->type == SPT_MAT_SUBSTRATE) {                        /* materials/substrate.cpp:34-56, reflection.h:433-437 */
+        b->nBxDFs = 1;
+        b->kind[0] = BX_FRESNEL_BLEND; b->R[0] = kd; b->R[1] = m->spec1;
+        b->ex = 1.f / m->p0; b->ey = 1.f / m->p1;
+        if (b->ex > 10000.f || isnan(b->ex)) b->ex = 10000.f;
+        if (b->ey > 10000.f || isnan(b->ey)) b->ey = 10000.f;
+    } else if (m->type == SPT_MAT_MATTE) {
+        b->nBxDFs = 1; b->R[0] = kd;
         if (m->p0 == 0.) b->kind[0] = BX_LAMBERT;
         else {
             b->kind[0] = BX_ORENNAYAR;                         /* reflection.h:363-370 */
@@ -531,7 +791,7 @@ static void make_bsdf(const SptSceneDesc *sc, uint32_t slot, const Hit *dg, BSDF
         }
     } else if (m->type == SPT_MAT_PLASTIC) {
         b->nBxDFs = 2;
-        b->kind[0] = BX_LAMBERT; b->R[0] = m->spec0;
+        b->kind[0] = BX_LAMBERT; b->R[0] = kd;
         b->kind[1] = BX_MICROFACET_DIEL; b->R[1] = m->spec1;
         b->exponent = blinn_exponent(1.f / m->p0);
     } else if (m->type == SPT_MAT_METAL) {
@@ -596,6 +856,30 @@ static void bxdf_f(const BSDF *b, int i, v3 wo, v3 wi, float *out) {
         for (int c = 0; c < NB; ++c) out[c] += b->R[i][c] * INV_PI_F * s;
         return;
     }
+    if (kind == BX_FRESNEL_BLEND) {                            /* reflection.cpp:224-236; Anisotropic::D reflection.h:438-444 */
+        const float *Rd = b->R[0], *Rs = b->R[1];
+        float k0 = (28.f / (23.f * PI_F));
+        float a1 = (1.f - powf(1.f - .5f * abs_cos_theta(wi), 5));
+        float a2 = (1.f - powf(1.f - .5f * abs_cos_theta(wo), 5));
+        v3 wh = vadd(wi, wo);
+        if (wh.x == 0. && wh.y == 0. && wh.z == 0.) return;
+        wh = normalize(wh);
+        float costhetah = abs_cos_theta(wh);
+        float dd = 1.f - costhetah * costhetah;
+        float D = 0.f;
+        if (dd != 0.f) {
+            float e = (b->ex * wh.x * wh.x + b->ey * wh.y * wh.y) / dd;
+            D = sqrtf((b->ex + 2.f) * (b->ey + 2.f)) * INV_TWOPI_F * powf(costhetah, e);
+        }
+        float sc_ = D / (4.f * absdot(wi, wh) * stdmaxf(abs_cos_theta(wi), abs_cos_theta(wo)));
+        float p5 = powf(1 - dot(wi, wh), 5.f);
+        for (int c = 0; c < NB; ++c) {
+            float diffuse = Rd[c] * k0 * (1.f - Rs[c]) * a1 * a2;
+            float specular = (Rs[c] + (1.f - Rs[c]) * p5) * sc_;
+            out[c] += diffuse + specular;
+        }
+        return;
+    }
     /* Microfacet::f, reflection.cpp:203-214; G reflection.h:395-402; Blinn::D reflection.h:419-422 */
     float cosThetaO = abs_cos_theta(wo), cosThetaI = abs_cos_theta(wi);
     if (cosThetaI == 0.f || cosThetaO == 0.f) return;
@@ -619,12 +903,33 @@ static void bxdf_f(const BSDF *b, int i, v3 wo, v3 wi, float *out) {
 
 static int bxdf_is_reflection(const BSDF *b, int i) { (void)b; (void)i; return 1; }   /* all lowered BxDFs are BRDFs */
 
+/* Anisotropic::Pdf, reflection.cpp:420-432 (and the tail of Anisotropic::Sample_f :396-405) for a half vector */
+static float anisotropic_pdf(const BSDF *b, v3 wo, v3 wh) {
+    float costhetah = abs_cos_theta(wh);
+    float ds = 1.f - costhetah * costhetah;
+    float pdf = 0.f;
+    if (ds > 0.f && dot(wo, wh) > 0.f) {
+        float e = (b->ex * wh.x * wh.x + b->ey * wh.y * wh.y) / ds;
+        float d = sqrtf((b->ex + 1.f) * (b->ey + 1.f)) * INV_TWOPI_F * powf(costhetah, e);
+        pdf = d / (4.f * dot(wo, wh));
+    }
+    return pdf;
+}
+/* Anisotropic::sampleFirstQuadrant, reflection.cpp:408-417 */
+static void aniso_first_quadrant(const BSDF *b, float u1, float u2, float *phi, float *costheta) {
+    if (b->ex == b->ey) *phi = PI_F * u1 * 0.5f;
+    else *phi = atanf(sqrtf((b->ex + 1.f) / (b->ey + 1.f)) * tanf(PI_F * u1 * 0.5f));
+    float cosphi = cosf(*phi), sinphi = sinf(*phi);
+    *costheta = powf(u2, 1.f / (b->ex * cosphi * cosphi + b->ey * sinphi * sinphi + 1));
+}
 /* Blinn::Pdf reflection.cpp:356-366 / BxDF::Pdf :312-315 / Microfacet::Pdf :331-335 */
 static float bxdf_pdf(const BSDF *b, int i, v3 wo, v3 wi) {
     int kind = b->kind[i];
     if (kind == BX_LAMBERT || kind == BX_ORENNAYAR)
         return same_hemisphere(wo, wi) ? abs_cos_theta(wi) * INV_PI_F : 0.f;
     if (!same_hemisphere(wo, wi)) return 0.f;
+    if (kind == BX_FRESNEL_BLEND)                              /* FresnelBlend::Pdf, reflection.cpp:453-456 */
+        return .5f * (abs_cos_theta(wi) * INV_PI_F + anisotropic_pdf(b, wo, normalize(vadd(wo, wi))));
     v3 wh = normalize(vadd(wo, wi));
     float costheta = abs_cos_theta(wh);
     float blinn_pdf = ((b->exponent + 1.f) * powf(costheta, b->exponent)) / (2.f * PI_F * 4.f * dot(wo, wh));
@@ -700,6 +1005,27 @@ static void bsdf_sample_f(const BSDF *b, v3 woW, v3 *wiW, float uComp, float u1,
         wi = cosine_sample_hemisphere(u1, u2);
         if (wo.z < 0.) wi.z *= -1.f;
         *pdf = bxdf_pdf(b, which, wo, wi);
+    } else if (kind == BX_FRESNEL_BLEND) {                     /* FresnelBlend::Sample_f, reflection.cpp:435-450 */
+        int keepPdf = 0;
+        if (u1 < .5) {
+            u1 = 2.f * u1;
+            wi = cosine_sample_hemisphere(u1, u2);
+            if (wo.z < 0.) wi.z *= -1.f;
+        } else {                                               /* Anisotropic::Sample_f, reflection.cpp:369-405 */
+            u1 = 2.f * (u1 - .5f);
+            float phi, costheta;
+            if (u1 < .25f) aniso_first_quadrant(b, 4.f * u1, u2, &phi, &costheta);
+            else if (u1 < .5f) { u1 = 4.f * (.5f - u1); aniso_first_quadrant(b, u1, u2, &phi, &costheta); phi = PI_F - phi; }
+            else if (u1 < .75f) { u1 = 4.f * (u1 - .5f); aniso_first_quadrant(b, u1, u2, &phi, &costheta); phi += PI_F; }
+            else { u1 = 4.f * (1.f - u1); aniso_first_quadrant(b, u1, u2, &phi, &costheta); phi = 2.f * PI_F - phi; }
+            float sintheta = sqrtf(stdmaxf(0.f, 1.f - costheta * costheta));
+            v3 wh = V(sintheta * cosf(phi), sintheta * sinf(phi), costheta);
+            if (!same_hemisphere(wo, wh)) wh = vneg(wh);
+            wi = vadd(vneg(wo), vmul(wh, 2.f * dot(wo, wh)));
+            *pdf = anisotropic_pdf(b, wo, wh);
+            if (!same_hemisphere(wo, wi)) keepPdf = 1;          /* returns before *pdf = Pdf(wo, *wi) */
+        }
+        if (!keepPdf) *pdf = bxdf_pdf(b, which, wo, wi);
     } else {                                                   /* Microfacet::Sample_f :324-329, Blinn::Sample_f :338-354 */
         float costheta = powf(u1, 1.f / (b->exponent + 1));
         float sintheta = sqrtf(stdmaxf(0.f, 1.f - costheta * costheta));
@@ -1041,11 +1367,12 @@ static void estimate_direct(const SptSceneDesc *sc, const SptLight *light, int l
  * sample37 layout: core/sampler.cpp:88-117 with the Add1D/Add2D order of integrators/path.cpp:33-41:
  *   1-D [5 + 4*i + {0 lightComp, 1 lightNum, 2 bsdfComp, 3 pathComp}], i < 3; [17],[18] emission (unused)
  *   2-D [19 + 6*i + {0 lightPos, 2 bsdfDir, 4 pathDir}]                                               */
-static void li_sample(const SptSceneDesc *sc, const SptCameraDesc *cam, int maxDepth, const float *smp,
+static void li_sample(const SptSceneDesc *sc, const SptCameraDesc *cam, int maxDepth, int spp, const float *smp,
                       const float *rngv, int nrng, float *Lout) {
     RngStream rng = { rngv, nrng, 0 };
     Ray ray;
-    camera_ray(cam, smp, &ray);
+    RayDiff rd;
+    camera_ray_diff(cam, smp, spp, &ray, &rd);
     float L[NB], T[NB];
     for (int c = 0; c < NB; ++c) { L[c] = 0.f; T[c] = 1.f; }
     uint32_t slot; Hit isect;
@@ -1067,7 +1394,7 @@ static void li_sample(const SptSceneDesc *sc, const SptCameraDesc *cam, int maxD
             for (int c = 0; c < NB; ++c) L[c] += T[c] * le[c];
         }
         BSDF bsdf; v3 n;
-        make_bsdf(sc, slot, &isect, &bsdf, &n);
+        make_bsdf(sc, slot, &isect, bounces == 0 ? &rd : NULL, &bsdf, &n);
         v3 p = isect.p;
         v3 wo = vneg(ray.d);
         /* UniformSampleOneLight */
@@ -1122,11 +1449,11 @@ static void li_sample(const SptSceneDesc *sc, const SptCameraDesc *cam, int maxD
     memcpy(Lout, L, sizeof(L));
 }
 
-void orc_shade_samples(const SptSceneDesc *sc, const SptCameraDesc *cam, int32_t max_depth,
+void orc_shade_samples(const SptSceneDesc *sc, const SptCameraDesc *cam, int32_t max_depth, int32_t spp,
                        const float *samples, const float *rng, int32_t n_rng, uint64_t n, float *out_L) {
 #pragma omp parallel for schedule(dynamic, 64)
     for (int64_t i = 0; i < (int64_t)n; ++i)
-        li_sample(sc, cam, max_depth, samples + 37 * i, rng ? rng + (size_t)n_rng * i : NULL, rng ? n_rng : 0,
+        li_sample(sc, cam, max_depth, spp, samples + 37 * i, rng ? rng + (size_t)n_rng * i : NULL, rng ? n_rng : 0,
                   out_L + (size_t)NB * i);
 }
 
@@ -1254,7 +1581,7 @@ void orc_render(const SptSceneDesc *sc, const SptCameraDesc *cam, const SptFilmD
             for (int s = 0; s < rp->spp; ++s) {
                 orc_gen_sample(rp->seed, px, py, s, rp->spp, cam->shutter_open, cam->shutter_close, nrng,
                                smp + 37 * s, rng + nrng * s);
-                li_sample(sc, cam, rp->max_depth, smp + 37 * s, rng + nrng * s, nrng, L + NB * s);
+                li_sample(sc, cam, rp->max_depth, rp->spp, smp + 37 * s, rng + nrng * s, nrng, L + NB * s);
             }
 #pragma omp critical
             for (int s = 0; s < rp->spp; ++s) film_add(fd, &sc->tables, smp[37 * s], smp[37 * s + 1], L + NB * s, c, weight);

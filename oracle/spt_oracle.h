@@ -19,7 +19,7 @@ void orc_trace_any(const SptSceneDesc *scene, const float *rays, uint64_t n, uin
  * algorithmic bytes) */
 void orc_trace_closest_counted(const SptSceneDesc *scene, const float *rays, uint64_t n,
                                uint64_t *nodes, uint64_t *prim_tests);
-void orc_shade_samples(const SptSceneDesc *scene, const SptCameraDesc *cam, int32_t max_depth,
+void orc_shade_samples(const SptSceneDesc *scene, const SptCameraDesc *cam, int32_t max_depth, int32_t spp,
                        const float *samples, const float *rng, int32_t n_rng, uint64_t n, float *out_L);
 void orc_film_add_samples(const SptFilmDesc *film, const SptSpectralTables *tables,
                           const float *image_xy, const float *L, uint64_t n, float *c, float *weight);

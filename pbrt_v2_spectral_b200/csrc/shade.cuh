@@ -19,10 +19,14 @@ struct Bsdf {
     float exponent, A, B;
     float ior;            // GLASS: FresnelDielectric(1, ior)
     int compMask;         // MIRROR / GLASS: bit 0 the reflection component exists (Kr not black), bit 1 the transmission (Kt)
+    float ex, ey;         // SUBSTRATE: Anisotropic exponents (reflection.h:433-437)
+    bool texKd;           // Kd came from an image texture: kd_rgb replaces the material row's spec0
+    float kd_rgb[3];
 };
 // Wavelength-independent factors of BSDF::f(wo,wi) for one direction.
 //   Oren-Nayar: a0 = A + B*maxcos*sinalpha*tanbeta
 //   Microfacet: a0 = D, a1 = G, a2 = F (dielectric) or |cos theta_h| (conductor), a3 = 4 cosI cosO
+//   FresnelBlend: a0 = diffuse scalar, a1 = D / (4 |wi.wh| max(cosI, cosO)), a2 = (1 - wi.wh)^5
 struct DirTerms { float a0, a1, a2, a3; bool reflect, mf; };
 
 __device__ __forceinline__ v3 w2l(const Bsdf &b, v3 v) { return V(dot(v, b.sn), dot(v, b.tn), dot(v, b.nn)); }
@@ -37,11 +41,203 @@ __device__ __forceinline__ float cos_phi(v3 w) { float s = sin_theta(w); if (s =
 __device__ __forceinline__ float sin_phi(v3 w) { float s = sin_theta(w); if (s == 0.f) return 0.f; return clampf(w.y / s, -1.f, 1.f); }
 __device__ __forceinline__ float blinn_exponent(float e) { if (e > 10000.f || isnan(e)) e = 10000.f; return e; }
 
+
+// ---- image textures -----------------------------------------------------------
+// The camera ray's offset rays (perspective.cpp:96-101) after ScaleDifferentials (geometry.h:368-373)
+struct RayDiff { v3 rxo, ryo, rxd, ryd; };
+struct UVDiff { float dudx, dvdx, dudy, dvdy; };
+__device__ __forceinline__ int imod(int a, int b) { int n = (int)(a / b); a -= n * b; if (a < 0) a += b; return a; }
+
+__device__ inline void camera_ray_diff(const SptCameraDesc &cam, float imageX, float imageY, float scale, const Ray &ray, RayDiff *rd) {
+    v3 Pcamera = xf_point(cam.raster_to_camera, V(imageX, imageY, 0.f));
+    v3 rxd = normalize(vadd(Pcamera, V(cam.dx_camera[0], cam.dx_camera[1], cam.dx_camera[2])));
+    v3 ryd = normalize(vadd(Pcamera, V(cam.dy_camera[0], cam.dy_camera[1], cam.dy_camera[2])));
+    rxd = xf_vector(cam.camera_to_world, rxd);
+    ryd = xf_vector(cam.camera_to_world, ryd);
+    // rxOrigin = ryOrigin = the ray's own origin (also with a lens): o + (o - o) * s = o
+    rd->rxo = rd->ryo = ray.o;
+    rd->rxd = vadd(ray.d, vmul(vsub(rxd, ray.d), scale));
+    rd->ryd = vadd(ray.d, vmul(vsub(ryd, ray.d), scale));
+}
+__device__ __forceinline__ bool solve2x2(const float A[2][2], const float B[2], float *x0, float *x1) {   // transform.cpp:31-41
+    float det = A[0][0] * A[1][1] - A[0][1] * A[1][0];
+    if (fabsf(det) < 1e-10f) return false;
+    *x0 = (A[1][1] * B[0] - A[0][1] * B[1]) / det;
+    *x1 = (A[0][0] * B[1] - A[1][0] * B[0]) / det;
+    return !(isnan(*x0) || isnan(*x1));
+}
+__device__ __forceinline__ float vcomp(v3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+// DifferentialGeometry::ComputeDifferentials, diffgeom.cpp:50-107
+__device__ inline void compute_differentials(const Hit &dg, const RayDiff *rd, UVDiff *o) {
+    o->dudx = o->dvdx = o->dudy = o->dvdy = 0.f;
+    if (!rd) return;
+    v3 nn = dg.nn, p = dg.p;
+    float d = -dot(nn, p);
+    float tx = -(dot(nn, rd->rxo) + d) / dot(nn, rd->rxd);
+    if (isnan(tx)) return;
+    v3 px = vadd(rd->rxo, vmul(rd->rxd, tx));
+    float ty = -(dot(nn, rd->ryo) + d) / dot(nn, rd->ryd);
+    if (isnan(ty)) return;
+    v3 py = vadd(rd->ryo, vmul(rd->ryd, ty));
+    int a0, a1;
+    if (fabsf(nn.x) > fabsf(nn.y) && fabsf(nn.x) > fabsf(nn.z)) { a0 = 1; a1 = 2; }
+    else if (fabsf(nn.y) > fabsf(nn.z)) { a0 = 0; a1 = 2; }
+    else { a0 = 0; a1 = 1; }
+    float A[2][2], Bx[2], By[2];
+    A[0][0] = vcomp(dg.dpdu, a0); A[0][1] = vcomp(dg.dpdv, a0);
+    A[1][0] = vcomp(dg.dpdu, a1); A[1][1] = vcomp(dg.dpdv, a1);
+    Bx[0] = vcomp(px, a0) - vcomp(p, a0); Bx[1] = vcomp(px, a1) - vcomp(p, a1);
+    By[0] = vcomp(py, a0) - vcomp(p, a0); By[1] = vcomp(py, a1) - vcomp(p, a1);
+    if (!solve2x2(A, Bx, &o->dudx, &o->dvdx)) { o->dudx = 0.f; o->dvdx = 0.f; }
+    if (!solve2x2(A, By, &o->dudy, &o->dvdy)) { o->dudy = 0.f; o->dvdy = 0.f; }
+}
+__device__ __forceinline__ float log2_pbrt(float x) { return logf(x) * (1.f / 0.693147180559945309417f); }   // pbrt.h:243-246
+
+struct TexLevel { const float *texels; int w, h; };
+__device__ inline TexLevel tex_level(const DevScene &sc, const SptTexture &t, int level) {
+    TexLevel l; l.texels = sc.tex_texels + t.texel_offset; l.w = t.width; l.h = t.height;
+    for (int i = 0; i < level; ++i) {
+        l.texels += (size_t)l.w * l.h * t.channels;
+        l.w = max(l.w / 2, 1); l.h = max(l.h / 2, 1);
+    }
+    return l;
+}
+// MIPMap::Texel, mipmap.h:177-201. C = channels per texel (3: RGB, 1: float)
+template <int C> __device__ inline void tex_texel(const SptTexture &t, const TexLevel &l, int s, int tt, float *out) {
+    if (t.wrap == SPT_WRAP_REPEAT) { s = imod(s, l.w); tt = imod(tt, l.h); }
+    else if (t.wrap == SPT_WRAP_CLAMP) { s = clampi(s, 0, l.w - 1); tt = clampi(tt, 0, l.h - 1); }
+    else if (s < 0 || s >= l.w || tt < 0 || tt >= l.h) {
+#pragma unroll
+        for (int k = 0; k < C; ++k) out[k] = 0.f;
+        return;
+    }
+    const float *px = l.texels + ((size_t)tt * l.w + s) * C;
+#pragma unroll
+    for (int k = 0; k < C; ++k) out[k] = __ldg(px + k);
+}
+// MIPMap::triangle, mipmap.h:258-270
+template <int C> __device__ inline void tex_triangle(const DevScene &sc, const SptTexture &t, int level, float s, float tt, float *out) {
+    level = clampi(level, 0, t.n_levels - 1);
+    TexLevel l = tex_level(sc, t, level);
+    s = s * l.w - 0.5f;
+    tt = tt * l.h - 0.5f;
+    int s0 = (int)floorf(s), t0 = (int)floorf(tt);
+    float ds = s - s0, dt = tt - t0;
+    float a[C], b[C], c[C], d[C];
+    tex_texel<C>(t, l, s0, t0, a); tex_texel<C>(t, l, s0, t0 + 1, b);
+    tex_texel<C>(t, l, s0 + 1, t0, c); tex_texel<C>(t, l, s0 + 1, t0 + 1, d);
+#pragma unroll
+    for (int k = 0; k < C; ++k)
+        out[k] = a[k] * ((1.f - ds) * (1.f - dt)) + b[k] * ((1.f - ds) * dt) + c[k] * (ds * (1.f - dt)) + d[k] * (ds * dt);
+}
+// MIPMap::EWA, mipmap.h:322-377
+template <int C> __device__ inline void tex_ewa(const DevScene &sc, const SptTexture &t, int level, float s, float tt,
+                                               float ds0, float dt0, float ds1, float dt1, float *out) {
+    if (level >= t.n_levels) { TexLevel top = tex_level(sc, t, t.n_levels - 1); tex_texel<C>(t, top, 0, 0, out); return; }
+    TexLevel l = tex_level(sc, t, level);
+    s = s * l.w - 0.5f;
+    tt = tt * l.h - 0.5f;
+    ds0 *= l.w; dt0 *= l.h; ds1 *= l.w; dt1 *= l.h;
+    float A = dt0 * dt0 + dt1 * dt1 + 1;
+    float B = -2.f * (ds0 * dt0 + ds1 * dt1);
+    float Cc = ds0 * ds0 + ds1 * ds1 + 1;
+    float invF = 1.f / (A * Cc - B * B * 0.25f);
+    A *= invF; B *= invF; Cc *= invF;
+    float det = -B * B + 4.f * A * Cc;
+    float invDet = 1.f / det;
+    float uSqrt = sqrtf(det * Cc), vSqrt = sqrtf(A * det);
+    int s0 = (int)ceilf(s - 2.f * invDet * uSqrt), s1 = (int)floorf(s + 2.f * invDet * uSqrt);
+    int t0 = (int)ceilf(tt - 2.f * invDet * vSqrt), t1 = (int)floorf(tt + 2.f * invDet * vSqrt);
+    float sum[C], sumWts = 0.f;
+#pragma unroll
+    for (int k = 0; k < C; ++k) sum[k] = 0.f;
+    for (int it = t0; it <= t1; ++it) {
+        float ttt = it - tt;
+        for (int is = s0; is <= s1; ++is) {
+            float ss = is - s;
+            float r2 = A * ss * ss + B * ss * ttt + Cc * ttt * ttt;
+            if (r2 < 1.f) {
+                float weight = __ldg(sc.ewa_lut + min((int)(r2 * 128), 127));
+                float tx[C];
+                tex_texel<C>(t, l, is, it, tx);
+#pragma unroll
+                for (int k = 0; k < C; ++k) sum[k] += tx[k] * weight;
+                sumWts += weight;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < C; ++k) out[k] = sum[k] / sumWts;
+}
+// MIPMap::Lookup(s,t,width), mipmap.h:215-255
+template <int C> __device__ inline void tex_lookup_tri(const DevScene &sc, const SptTexture &t, float s, float tt, float width, float *out) {
+    if (t.no_filter) {
+        TexLevel l = tex_level(sc, t, 0);
+        s = s * t.width - 0.5f;
+        tt = tt * t.height - 0.5f;
+        tex_texel<C>(t, l, (int)floorf(s + 0.5f), (int)floorf(tt + 0.5f), out);
+        return;
+    }
+    float level = t.n_levels - 1 + log2_pbrt(stdmaxf(width, 1e-8f));
+    if (level < 0) tex_triangle<C>(sc, t, 0, s, tt, out);
+    else if (level >= t.n_levels - 1) { TexLevel top = tex_level(sc, t, t.n_levels - 1); tex_texel<C>(t, top, 0, 0, out); }
+    else {
+        int iLevel = (int)floorf(level);
+        float delta = level - iLevel;
+        float a[C], b[C];
+        tex_triangle<C>(sc, t, iLevel, s, tt, a);
+        tex_triangle<C>(sc, t, iLevel + 1, s, tt, b);
+#pragma unroll
+        for (int k = 0; k < C; ++k) out[k] = a[k] * (1.f - delta) + b[k] * delta;
+    }
+}
+// ImageTexture::Evaluate (imagemap.cpp:88-97): UVMapping2D::Map (texture.cpp:80-90), then MIPMap::Lookup with
+// differentials (mipmap.h:273-319); a float image is multiplied by its ScaleTexture constant (scale.h:45-47)
+template <int C> __device__ inline void tex_evaluate(const DevScene &sc, const SptTexture &t, float u, float v, const UVDiff &df, float *out) {
+    float s = t.su * u + t.du, tt = t.sv * v + t.dv;
+    float ds0 = t.su * df.dudx, dt0 = t.sv * df.dvdx, ds1 = t.su * df.dudy, dt1 = t.sv * df.dvdy;
+    if (t.trilinear || t.no_filter) {
+        tex_lookup_tri<C>(sc, t, s, tt, 2.f * stdmaxf(stdmaxf(fabsf(ds0), fabsf(dt0)), stdmaxf(fabsf(ds1), fabsf(dt1))), out);
+    } else {
+        if (ds0 * ds0 + dt0 * dt0 < ds1 * ds1 + dt1 * dt1) {
+            float tmp = ds0; ds0 = ds1; ds1 = tmp;
+            tmp = dt0; dt0 = dt1; dt1 = tmp;
+        }
+        float majorLength = sqrtf(ds0 * ds0 + dt0 * dt0);
+        float minorLength = sqrtf(ds1 * ds1 + dt1 * dt1);
+        if (minorLength * t.max_aniso < majorLength && minorLength > 0.f) {
+            float scale = majorLength / (minorLength * t.max_aniso);
+            ds1 *= scale; dt1 *= scale; minorLength *= scale;
+        }
+        if (minorLength == 0.f) tex_triangle<C>(sc, t, 0, s, tt, out);
+        else {
+            float lod = stdmaxf(0.f, t.n_levels - 1.f + log2_pbrt(minorLength));
+            int ilod = (int)floorf(lod);
+            float d = lod - ilod;
+            float a[C], b[C];
+            tex_ewa<C>(sc, t, ilod, s, tt, ds0, dt0, ds1, dt1, a);
+            tex_ewa<C>(sc, t, ilod + 1, s, tt, ds0, dt0, ds1, dt1, b);
+#pragma unroll
+            for (int k = 0; k < C; ++k) out[k] = a[k] * (1.f - d) + b[k] * d;
+        }
+    }
+    if (C == 1) out[0] = out[0] * t.scale;
+}
+
 // Triangle::GetShadingGeometry (trianglemesh.cpp:285-360) + Material::Bump with the constant-0
 // displacement every reference material carries (material.cpp:39-82) + BSDF frame
 // (reflection.cpp:593-601) + the BxDF set of matte/plastic/metal (materials/*.cpp).
-__device__ inline void make_bsdf(const DevScene &sc, uint32_t slot, const Hit &dg, Bsdf *b) {
+// EXT (scenes with a substrate / image-mapped Kd / bump-mapped material): Intersection::GetBSDF's
+// ComputeDifferentials (rd: the camera ray's offset rays at the first vertex, NULL afterwards), Bump with a float
+// image map, Kd->Evaluate(dgs).
+template <bool EXT>
+__device__ inline void make_bsdf(const DevScene &sc, uint32_t slot, const Hit &dg, const RayDiff *rd, Bsdf *b) {
     int flags = sc.prim_flags[slot];
+    const SptMaterial &m = sc.materials[sc.prim_material[slot]];
+    UVDiff df; df.dudx = df.dvdx = df.dudy = df.dvdy = 0.f;
+    const bool bump = EXT && m.tex_bump >= 0;
+    if (EXT && (m.tex_kd >= 0 || m.tex_bump >= 0)) compute_differentials(dg, rd, &df);
+    v3 s_nn = dg.nn, dndu = V(0, 0, 0), dndv = V(0, 0, 0);
     v3 s_dpdu = dg.dpdu, s_dpdv = dg.dpdv;
     if (sc.prim_kind[slot] == SPT_PRIM_TRIANGLE && (flags & SPT_PF_HAS_N)) {
         const int32_t *vi = sc.tri_vidx + 3 * (size_t)sc.prim_data[slot];
@@ -71,6 +267,37 @@ __device__ inline void make_bsdf(const DevScene &sc, uint32_t slot, const Hit &d
         if (len2(ts) > 0.f) { ts = normalize(ts); ss = cross(ts, ns); }
         else coordinate_system(ns, &ss, &ts);
         s_dpdu = ss; s_dpdv = ts;
+        if (bump) {
+            // dndu, dndv (trianglemesh.cpp:331-351) and the shading DifferentialGeometry's own normal (diffgeom.cpp:32-47)
+            float du1 = uv[0][0] - uv[2][0], du2 = uv[1][0] - uv[2][0];
+            float dv1 = uv[0][1] - uv[2][1], dv2 = uv[1][1] - uv[2][1];
+            v3 N0 = V(n0[0], n0[1], n0[2]), N1 = V(n1[0], n1[1], n1[2]), N2 = V(n2[0], n2[1], n2[2]);
+            v3 dn1 = vsub(N0, N2), dn2 = vsub(N1, N2);
+            float determinant = du1 * dv2 - dv1 * du2;
+            if (determinant != 0.f) {
+                float invdet = 1.f / determinant;
+                dndu = vmul(vsub(vmul(dn1, dv2), vmul(dn2, dv1)), invdet);
+                dndv = vmul(vadd(vmul(dn1, -du2), vmul(dn2, du1)), invdet);
+            }
+            dndu = xf_normal(xf.minv, dndu);
+            dndv = xf_normal(xf.minv, dndv);
+            s_nn = normalize(cross(ss, ts));
+            if (flags & SPT_PF_FLIP_NORMAL) s_nn = vmul(s_nn, -1.f);
+        }
+    }
+    if (bump) {                                                      // Material::Bump, material.cpp:39-82
+        const SptTexture &bt = sc.textures[m.tex_bump];
+        float du = .5f * (fabsf(df.dudx) + fabsf(df.dudy));
+        if (du == 0.f) du = .01f;
+        float dv = .5f * (fabsf(df.dvdx) + fabsf(df.dvdy));
+        if (dv == 0.f) dv = .01f;
+        float disp[3];
+#pragma unroll 1
+        for (int k = 0; k < 3; ++k)                                  // one copy of the filtered lookup in the instruction cache
+            tex_evaluate<1>(sc, bt, dg.u + (k == 0 ? du : 0.f), dg.v + (k == 1 ? dv : 0.f), df, &disp[k]);
+        const float uDisplace = disp[0], vDisplace = disp[1], displace = disp[2];
+        s_dpdu = vadd(vadd(s_dpdu, vmul(s_nn, (uDisplace - displace) / du)), vmul(dndu, displace));
+        s_dpdv = vadd(vadd(s_dpdv, vmul(s_nn, (vDisplace - displace) / dv)), vmul(dndv, displace));
     }
     v3 nn = normalize(cross(s_dpdu, s_dpdv));
     if (flags & SPT_PF_FLIP_NORMAL) nn = vmul(nn, -1.f);
@@ -79,10 +306,18 @@ __device__ inline void make_bsdf(const DevScene &sc, uint32_t slot, const Hit &d
     b->ng = dg.nn;
     b->sn = normalize(s_dpdu);
     b->tn = cross(b->nn, b->sn);
-    const SptMaterial &m = sc.materials[sc.prim_material[slot]];
     b->mtype = m.type;
     b->orenNayar = false; b->exponent = 0.f; b->A = b->B = 0.f; b->ior = 1.f; b->compMask = 0;
-    if (m.type == SPT_MAT_MIRROR || m.type == SPT_MAT_GLASS) {       // mirror.cpp:34-55, glass.cpp:34-58
+    b->ex = b->ey = 0.f; b->texKd = false;
+    if (EXT && m.tex_kd >= 0) {                                      // Kd->Evaluate(dgs): imagemap.cpp:88-97
+        tex_evaluate<3>(sc, sc.textures[m.tex_kd], dg.u, dg.v, df, b->kd_rgb);
+        b->texKd = true;
+    }
+    if (EXT && m.type == SPT_MAT_SUBSTRATE) {                        // substrate.cpp:34-56, reflection.h:433-437
+        b->ex = 1.f / m.p0; b->ey = 1.f / m.p1;
+        if (b->ex > 10000.f || isnan(b->ex)) b->ex = 10000.f;
+        if (b->ey > 10000.f || isnan(b->ey)) b->ey = 10000.f;
+    } else if (m.type == SPT_MAT_MIRROR || m.type == SPT_MAT_GLASS) {       // mirror.cpp:34-55, glass.cpp:34-58
         b->ior = m.p0;
         b->compMask = (int)m.p1;                                      // which spectra are not black: set by spt_scene_create
     } else if (m.type == SPT_MAT_MATTE) {
@@ -131,6 +366,7 @@ __device__ __forceinline__ float pow01(float x, float e) { return exp2f(e * log2
 // Microfacet :203-214, G reflection.h:395-402, Blinn::D reflection.h:419-422) and, from the same
 // half-vector and the same cos^e, BSDF::Pdf (reflection.cpp:575-590: BxDF::Pdf :312-315,
 // Microfacet::Pdf :331-335, Blinn::Pdf :356-366) averaged over the components.
+template <bool EXT>
 __device__ inline void bsdf_terms(const Bsdf &b, v3 woW, v3 wiW, v3 wo, v3 wi, DirTerms *t, float *pdfAll) {
     t->a0 = t->a1 = t->a2 = t->a3 = 0.f;
     t->mf = false;
@@ -153,6 +389,25 @@ __device__ inline void bsdf_terms(const Bsdf &b, v3 woW, v3 wiW, v3 wo, v3 wi, D
             else { sinalpha = sinthetai; tanbeta = sinthetao / abs_cos_theta(wo); }
             t->a0 = (b.A + b.B * maxcos * sinalpha * tanbeta);
         }
+        return;
+    }
+    if (EXT && b.mtype == SPT_MAT_SUBSTRATE) {                       // FresnelBlend::f / ::Pdf, reflection.cpp:224-236,453-456
+        v3 wh = vadd(wi, wo);
+        const bool whZero = (wh.x == 0.f && wh.y == 0.f && wh.z == 0.f);
+        wh = normalize(wh);
+        const float costhetah = abs_cos_theta(wh);
+        const float ds = 1.f - costhetah * costhetah;
+        const float e = (b.ex * wh.x * wh.x + b.ey * wh.y * wh.y) / ds;
+        const float pw = powf(costhetah, e);
+        float anisoPdf = 0.f;                                        // Anisotropic::Pdf, reflection.cpp:420-432
+        if (ds > 0.f && dot(wo, wh) > 0.f) anisoPdf = (sqrtf((b.ex + 1.f) * (b.ey + 1.f)) * INV_TWOPI_F * pw) / (4.f * dot(wo, wh));
+        *pdfAll = same ? .5f * (abs_cos_theta(wi) * INV_PI_F + anisoPdf) : 0.f;
+        if (!t->reflect || whZero) return;
+        t->a0 = (28.f / (23.f * PI_F)) * (1.f - powf(1.f - .5f * abs_cos_theta(wi), 5.f)) * (1.f - powf(1.f - .5f * abs_cos_theta(wo), 5.f));
+        const float D = ds == 0.f ? 0.f : sqrtf((b.ex + 2.f) * (b.ey + 2.f)) * INV_TWOPI_F * pw;      // Anisotropic::D, reflection.h:438-444
+        t->a1 = D / (4.f * absdot(wi, wh) * stdmaxf(abs_cos_theta(wi), abs_cos_theta(wo)));
+        t->a2 = powf(1 - dot(wi, wh), 5.f);
+        t->mf = true;
         return;
     }
     // microfacet component: one half-vector, one cos^e shared by D and the Blinn pdf
@@ -197,7 +452,49 @@ __device__ __forceinline__ float f_band(const SptMaterial &m, bool orenNayar, co
 }
 // BSDF::Sample_f (reflection.cpp:514-572), first half: the component is chosen and its direction
 // sampled (local frame). Returns false when the chosen component yields no sample (pdf == 0).
-__device__ inline bool bsdf_sample_dir(const Bsdf &b, v3 wo, float uComp, float u1, float u2, v3 *wiOut) {
+// Anisotropic::sampleFirstQuadrant, reflection.cpp:408-417
+__device__ inline void aniso_first_quadrant(const Bsdf &b, float u1, float u2, float *phi, float *costheta) {
+    if (b.ex == b.ey) *phi = PI_F * u1 * 0.5f;
+    else *phi = atanf(sqrtf((b.ex + 1.f) / (b.ey + 1.f)) * tanf(PI_F * u1 * 0.5f));
+    float cosphi = cosf(*phi), sinphi = sinf(*phi);
+    *costheta = powf(u2, 1.f / (b.ex * cosphi * cosphi + b.ey * sinphi * sinphi + 1));
+}
+// pdfOverride (substrate only): FresnelBlend::Sample_f returns before `*pdf = Pdf(wo, *wi)` when the direction
+// sampled from the microfacet distribution falls in the other hemisphere (reflection.cpp:444-446), leaving the
+// distribution's own pdf in place; < 0 otherwise.
+template <bool EXT>
+__device__ inline bool bsdf_sample_dir(const Bsdf &b, v3 wo, float uComp, float u1, float u2, v3 *wiOut, float *pdfOverride) {
+    *pdfOverride = -1.f;
+    if (EXT && b.mtype == SPT_MAT_SUBSTRATE) {                              // FresnelBlend::Sample_f, reflection.cpp:435-450
+        v3 wi;
+        if (u1 < .5f) {
+            u1 = 2.f * u1;
+            wi = cosine_sample_hemisphere(u1, u2);
+            if (wo.z < 0.f) wi.z *= -1.f;
+        } else {                                                     // Anisotropic::Sample_f, reflection.cpp:369-405
+            u1 = 2.f * (u1 - .5f);
+            float phi, costheta;
+            if (u1 < .25f) aniso_first_quadrant(b, 4.f * u1, u2, &phi, &costheta);
+            else if (u1 < .5f) { u1 = 4.f * (.5f - u1); aniso_first_quadrant(b, u1, u2, &phi, &costheta); phi = PI_F - phi; }
+            else if (u1 < .75f) { u1 = 4.f * (u1 - .5f); aniso_first_quadrant(b, u1, u2, &phi, &costheta); phi += PI_F; }
+            else { u1 = 4.f * (1.f - u1); aniso_first_quadrant(b, u1, u2, &phi, &costheta); phi = 2.f * PI_F - phi; }
+            float sintheta = sqrtf(stdmaxf(0.f, 1.f - costheta * costheta));
+            v3 wh = V(sintheta * cosf(phi), sintheta * sinf(phi), costheta);
+            if (!same_hemisphere(wo, wh)) wh = vneg(wh);
+            wi = vadd(vneg(wo), vmul(wh, 2.f * dot(wo, wh)));
+            if (!same_hemisphere(wo, wi)) {
+                const float costhetah = abs_cos_theta(wh), ds = 1.f - costhetah * costhetah;
+                float pdf = 0.f;
+                if (ds > 0.f && dot(wo, wh) > 0.f) {
+                    float e = (b.ex * wh.x * wh.x + b.ey * wh.y * wh.y) / ds;
+                    pdf = (sqrtf((b.ex + 1.f) * (b.ey + 1.f)) * INV_TWOPI_F * powf(costhetah, e)) / (4.f * dot(wo, wh));
+                }
+                *pdfOverride = pdf;
+            }
+        }
+        *wiOut = wi;
+        return true;                                                 // pdf == 0 is caught by the caller (one component)
+    }
     int matching = bsdf_ncomp(b);
     int which = (int)floorf(uComp * matching);
     if (matching - 1 < which) which = matching - 1;
@@ -229,9 +526,11 @@ __device__ inline void bsdf_sample(const Bsdf &b, v3 woW, v3 wo, float uComp, fl
     v3 wi;
     *pdf = 0.f;
     t->a0 = t->a1 = t->a2 = t->a3 = 0.f; t->mf = false; t->reflect = false;
-    if (!bsdf_sample_dir(b, wo, uComp, u1, u2, &wi)) return;
+    float pdfOverride;
+    if (!bsdf_sample_dir<true>(b, wo, uComp, u1, u2, &wi, &pdfOverride)) return;
     *wiW = l2w(b, wi);
-    bsdf_terms(b, woW, *wiW, wo, wi, t, pdf);
+    bsdf_terms<true>(b, woW, *wiW, wo, wi, t, pdf);
+    if (pdfOverride >= 0.f) *pdf = pdfOverride;
 }
 
 // BSDF::Sample_f for an all-specular BSDF (mirror, glass; reflection.cpp:514-572 with SpecularReflection::Sample_f
@@ -300,7 +599,16 @@ __device__ __forceinline__ float illum_band(const SptSpectralTables &t, const Il
     r *= .86445f;
     return clampf(r, 0.f, SPT_INF);
 }
-__device__ __forceinline__ int imod(int a, int b) { int n = (int)(a / b); a -= n * b; if (a < 0) a += b; return a; }
+// FromRGB(rgb, SPECTRUM_REFLECTANCE) (spectrum.cpp:92-133,175): same basis choice as the illuminant form, the
+// rgbRefl2Spect* tables, scale .94
+__device__ __forceinline__ float refl_band(const SptSpectralTables &t, const IllumCoefs &k, int c) {
+    float r = 0.f;
+    r += t.rgb_refl[0][c] * k.k0;
+    r += t.rgb_refl[k.b1][c] * k.k1;
+    r += t.rgb_refl[k.b2][c] * k.k2;
+    r *= .94f;
+    return clampf(r, 0.f, SPT_INF);
+}
 // MIPMap::Lookup(s,t) -> triangle(0,s,t), repeat wrap (src/core/mipmap.h:198-221,233-274)
 __device__ inline void env_lookup(const DevScene &sc, float s, float t, float rgb[3]) {
     int w = sc.env_w, h = sc.env_h;

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cmath>
 #include <map>
 #include <mutex>
 #include <string>
@@ -263,7 +264,22 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
             mt.p1 = (float)mask;
             v.has_specular = 1;
         }
+    for (const SptMaterial &mt : mats) {
+        if (mt.type == SPT_MAT_SUBSTRATE || mt.tex_kd >= 0 || mt.tex_bump >= 0) v.has_ext = 1;
+        if (mt.tex_kd >= (int32_t)d->n_textures || mt.tex_bump >= (int32_t)d->n_textures) { g_err = "material references a texture that is not in the scene"; delete s; return nullptr; }
+        if (mt.tex_kd >= 0 && d->textures[mt.tex_kd].channels != 3) { g_err = "Kd texture is not an RGB image map"; delete s; return nullptr; }
+        if (mt.tex_bump >= 0 && d->textures[mt.tex_bump].channels != 1) { g_err = "bump texture is not a float image map"; delete s; return nullptr; }
+    }
+    if (d->n_textures && !d->ewa_weight_lut) { g_err = "image textures need ewa_weight_lut"; delete s; return nullptr; }
+    for (uint32_t p = 0; p < d->n_prims; ++p) {
+        const SptMaterial &mt = d->materials[d->prim_material[p]];
+        if ((mt.tex_kd >= 0 || mt.tex_bump >= 0) && d->prim_kind[p] != SPT_PRIM_TRIANGLE) {
+            g_err = "textured materials are supported on triangles only"; delete s; return nullptr;
+        }
+    }
     UP(v.materials, mats.data(), d->n_materials); UP(v.lights, d->lights, d->n_lights);
+    UP(v.textures, d->textures, d->n_textures); UP(v.tex_texels, d->tex_texels, d->n_texels);
+    UP(v.ewa_lut, d->ewa_weight_lut, d->ewa_weight_lut ? 128 : 0);
     UP(v.light_shapes, d->light_shapes, d->n_light_shapes);
     UP(v.light_cdf, cdf.data(), cdf.size());
     v.n_lights = d->n_lights;
@@ -356,6 +372,7 @@ static int ensure_wave(SptScene *s, int n_lanes, uint32_t cap, int max_depth, si
         AL(w.mis_slot, uint32_t, cap); AL(w.mis_t, float, cap); AL(w.sh_slot, uint32_t, cap);
         AL(w.rec0, float4, cap); AL(w.rec1, float4, cap); AL(w.rec2, float4, cap);
         AL(w.laux, float4, cap); AL(w.pflags, uint32_t, cap);
+        AL(w.rec3, float4, s->dev.has_ext ? cap : 1); AL(w.rec4, float4, s->dev.has_ext ? cap : 1);
         AL(w.img_xy, float2, cap);
         AL(w.T, float, (size_t)cap * NB); AL(w.L, float, (size_t)cap * NB);
         AL(w.pathQ[0], uint32_t, cap); AL(w.pathQ[1], uint32_t, cap); AL(w.shadowQ, uint32_t, cap); AL(w.misQ, uint32_t, cap);
@@ -579,9 +596,10 @@ int spt_trace_any_dev(SptScene *s, const float *rays_dev, uint64_t n, uint8_t *o
     return trace_resident(s, true, rays_dev, n, nullptr, nullptr, out_hit_dev);
 }
 
-int spt_shade_samples(SptScene *s, const SptCameraDesc *cam, int32_t max_depth, const float *samples, const float *rng,
+int spt_shade_samples(SptScene *s, const SptCameraDesc *cam, int32_t max_depth, int32_t spp, const float *samples, const float *rng,
                       int32_t n_rng, uint64_t n, float *out_L) {
     if (!s || !cam || !samples || !out_L) return fail(SPT_ERR_ARG, "null argument");
+    if (spp <= 0) return fail(SPT_ERR_ARG, "spp must be positive");
     if (n == 0) return SPT_OK;
     if (n > (1u << 26)) return fail(SPT_ERR_ARG, "too many samples for one call");
     int rc = ensure_wave(s, 1, (uint32_t)n, max_depth, 1);
@@ -595,6 +613,7 @@ int spt_shade_samples(SptScene *s, const SptCameraDesc *cam, int32_t max_depth, 
     memset(&cfg, 0, sizeof(cfg));
     cfg.cam = *cam; cfg.spp = 1; cfg.spp_shift = 0; cfg.max_depth = max_depth; cfg.n_samples = (uint32_t)n;
     cfg.tile = 1; cfg.tile_shift = 0; cfg.tilesX = 1; cfg.tilesY = 1; cfg.nranks = 1;
+    cfg.diff_scale = 1.f / sqrtf((float)spp);
     SampleSource src; src.smp = dsmp; src.rng = drng; src.n_rng = drng ? n_rng : 0; src.seed = 0; src.spp = 1;
     size_t nc = (size_t)(max_depth + 2) * SPT_ROW;
     cudaMemsetAsync(s->counts, 0, nc * 4, s->stream);
@@ -727,6 +746,7 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
     RenderCfg cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.cam = *cam; cfg.spp = rp->spp; cfg.max_depth = rp->max_depth;
+    cfg.diff_scale = 1.f / sqrtf((float)rp->spp);
     for (cfg.spp_shift = 0; (1 << cfg.spp_shift) < cfg.spp; ++cfg.spp_shift) {}
     cfg.x0 = rp->x_start; cfg.y0 = rp->y_start; cfg.x1 = rp->x_end; cfg.y1 = rp->y_end;
     const SptFilmDesc &fd = film->desc;

@@ -110,5 +110,11 @@ struct DevScene {
     int env_w, env_h;
     const float *env_rgb, *env_func, *env_cdf, *env_func_int, *env_marg_func, *env_marg_cdf;
     float env_marg_int;
+    // image textures (SptTexture rows, the texel pool of their MIP pyramids, MIPMap::weightLut) and whether any
+    // material needs the extended shading kernels (substrate BSDF, image-mapped Kd, bump map)
+    const SptTexture *textures;
+    const float *tex_texels;
+    const float *ewa_lut;
+    int has_ext;
     unsigned long long *counters;    // closest: [0] nodes, [1] prim tests; any-hit: [2], [3] (NULL when disabled)
 };

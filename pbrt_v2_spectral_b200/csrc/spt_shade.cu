@@ -109,12 +109,15 @@ __device__ __forceinline__ float2 dir_coef(int mtype, bool on, const DirTerms &t
     if (!t.reflect) return d;
     if (mtype == SPT_MAT_MATTE) d.x = on ? INV_PI_F * t.a0 : INV_PI_F;
     else if (mtype == SPT_MAT_PLASTIC) { d.x = INV_PI_F; if (t.mf) d.y = t.a0 * t.a1 * t.a2 / t.a3; }
+    else if (mtype == SPT_MAT_SUBSTRATE) { if (t.mf) { d.x = t.a0; d.y = t.a1; } }    // third coefficient (t.a2) goes to rec3
     else if (t.mf) { d.x = t.a0 * t.a1 / t.a3; d.y = t.a2; }
     return d;
 }
 // SPEC: the scene has mirror / glass materials (a second instantiation keeps their code, and the
 // specularBounce flag traffic, out of the kernel every other scene runs).
-template <bool SPEC>
+// EXT: the scene has a substrate, an image-mapped Kd or a bump map (DevScene::has_ext): ray differentials at the
+// first vertex, filtered texture lookups, Material::Bump, FresnelBlend - again kept out of the common kernel.
+template <bool SPEC, bool EXT>
 __global__ void __launch_bounds__(128, 4) k_shade(DevScene sc, RenderCfg cfg, SampleSource src, WaveBuffers wb, int bounce,
                                                const uint32_t *queue, const uint32_t *count,
                                                uint32_t *shadow_count, uint32_t *mis_count, uint32_t *elided_count, uint32_t *mis_any_count) {
@@ -141,7 +144,12 @@ __global__ void __launch_bounds__(128, 4) k_shade(DevScene sc, RenderCfg cfg, Sa
                     if (li >= 0 && dot(hit.nn, vneg(ray.d)) > 0.f) emitter = li;
                 }
                 Bsdf bsdf;
-                make_bsdf(sc, slot, hit, &bsdf);
+                if (EXT) {
+                    RayDiff rdiff;
+                    const bool camRay = bounce == 0;                 // later rays carry no differentials (path.cpp:93)
+                    if (camRay) { float2 xy = wb.img_xy[i]; camera_ray_diff(cfg.cam, xy.x, xy.y, cfg.diff_scale, ray, &rdiff); }
+                    make_bsdf<true>(sc, slot, hit, camRay ? &rdiff : nullptr, &bsdf);
+                } else make_bsdf<false>(sc, slot, hit, nullptr, &bsdf);
                 v3 p = hit.p, n_s = bsdf.nn, woW = vneg(ray.d);
                 v3 wo = w2l(bsdf, woW);
                 float eps = hit.rayEpsilon;
@@ -179,7 +187,7 @@ __global__ void __launch_bounds__(128, 4) k_shade(DevScene sc, RenderCfg cfg, Sa
                 }
                 v3 wl1 = V(0, 0, 1), wl2 = wl1, wiW1 = wl1, wiW2 = wl1;
                 bool have1 = false, have2 = false;
-#pragma unroll 1
+                float pdfOv1 = -1.f, pdfOv2 = -1.f;
                 float specR = 0.f, specT = 0.f, specPdf = 0.f;
                 for (int d = 1; d <= 2; ++d) {
                     if (d == 1 && (!haveLights || lr.delta)) continue;
@@ -191,9 +199,10 @@ __global__ void __launch_bounds__(128, 4) k_shade(DevScene sc, RenderCfg cfg, Sa
                     }
                     float uc = d == 1 ? u[6] : u[9], ua = d == 1 ? u[4] : u[7], ub = d == 1 ? u[5] : u[8];
                     v3 wl;
-                    bool ok = bsdf_sample_dir(bsdf, wo, uc, ua, ub, &wl);
+                    float po;
+                    bool ok = bsdf_sample_dir<EXT>(bsdf, wo, uc, ua, ub, &wl, &po);
                     v3 wW = l2w(bsdf, wl);
-                    if (d == 1) { have1 = ok; wl1 = wl; wiW1 = wW; } else { have2 = ok; wl2 = wl; wiW2 = wW; }
+                    if (d == 1) { have1 = ok; wl1 = wl; wiW1 = wW; pdfOv1 = po; } else { have2 = ok; wl2 = wl; wiW2 = wW; pdfOv2 = po; }
                 }
                 float lightPdf1 = 0.f;
 #pragma unroll 1
@@ -218,9 +227,10 @@ __global__ void __launch_bounds__(128, 4) k_shade(DevScene sc, RenderCfg cfg, Sa
                     v3 wW = d == 0 ? lr.wi : (d == 1 ? wiW1 : wiW2);
                     v3 wl = d == 0 ? wl0 : (d == 1 ? wl1 : wl2);
                     DirTerms t; float pdf;
-                    bsdf_terms(bsdf, woW, wW, wo, wl, &t, &pdf);
+                    bsdf_terms<EXT>(bsdf, woW, wW, wo, wl, &t, &pdf);
                     if (d == 0) { t0 = t; pdf0 = pdf; } else if (d == 1) { t1 = t; pdf1 = pdf; } else { t2 = t; pdf2 = pdf; }
                 }
+                if (EXT) { if (pdfOv1 >= 0.f) pdf1 = pdfOv1; if (pdfOv2 >= 0.f) pdf2 = pdfOv2; }
                 if (have0 && t0.reflect) {
                     if (lr.delta) sL = (absdot(lr.wi, n_s) / lr.pdf);
                     else {
@@ -256,6 +266,14 @@ __global__ void __launch_bounds__(128, 4) k_shade(DevScene sc, RenderCfg cfg, Sa
                     g3 = make_float4(wiW2.x, wiW2.y, wiW2.z, 0.f);
                 }
                 if (mtype == SPT_MAT_METAL) flags |= RF_METAL;
+                if (EXT) {
+                    if (mtype == SPT_MAT_SUBSTRATE) {
+                        flags |= RF_SUBSTRATE;
+                        wb.rec3[i] = make_float4((flags & RF_L) ? t0.a2 : 0.f, (flags & RF_B) ? t1.a2 : 0.f,
+                                                 ((flags & RF_P) && t2.mf) ? t2.a2 : 0.f, 0.f);
+                    }
+                    if (bsdf.texKd) { flags |= RF_TEXKD; wb.rec4[i] = make_float4(bsdf.kd_rgb[0], bsdf.kd_rgb[1], bsdf.kd_rgb[2], 0.f); }
+                }
                 wb.g0[i] = make_float4(p.x, p.y, p.z, eps);
                 if (pushShadow) wb.g1[i] = g1;
                 if (pushMis || pushMisAny) wb.g2[i] = g2;
@@ -306,16 +324,20 @@ struct LightBand { int kind; IllumCoefs k; };
 static_assert(NB == 32, "k_accumulate and k_film_add map one band to one lane");
 #define ACC_WARPS 4
 #define ACC_GROUP 4          // vertices whose T/L rows are in flight together in phase B
+// EXT (DevScene::has_ext): two more staged float4 per vertex - the substrate's third coefficients and the
+// reflectance coefficients of an image-mapped Kd - and the FresnelBlend form of f[c].
+template <bool EXT>
 __global__ void __launch_bounds__(32 * ACC_WARPS, 8) k_accumulate(DevScene sc, RenderCfg cfg, WaveBuffers wb, int bounce,
                                                                const uint32_t *__restrict__ queue, const uint32_t *__restrict__ count,
                                                                uint32_t *__restrict__ next_queue, uint32_t *__restrict__ next_count) {
-    __shared__ float4 stage_all[ACC_WARPS][32][6];
+    constexpr int STAGE = EXT ? 8 : 6;
+    __shared__ float4 stage_all[ACC_WARPS][32][STAGE];
     const uint32_t n = *count;
     const SptSpectralTables &tb = *sc.tables;
     float *__restrict__ Tg = wb.T;
     float *__restrict__ Lg = wb.L;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float4 (*stage)[6] = stage_all[warp];
+    float4 (*stage)[STAGE] = stage_all[warp];
     const unsigned FULL = 0xffffffffu;
     const float cieY = tb.cie_y[lane];
     const float nL = (float)sc.n_lights;
@@ -381,6 +403,20 @@ __global__ void __launch_bounds__(32 * ACC_WARPS, 8) k_accumulate(DevScene sc, R
             stage[lane][3] = make_float4(lbL.k.k0, lbL.k.k1, lbL.k.k2, __uint_as_float((uint32_t)lbL.kind | (uint32_t)lbL.k.b1 << 4 | (uint32_t)lbL.k.b2 << 8));
             stage[lane][4] = make_float4(lbB.k.k0, lbB.k.k1, lbB.k.k2, __uint_as_float((uint32_t)lbB.kind | (uint32_t)lbB.k.b1 << 4 | (uint32_t)lbB.k.b2 << 8));
             stage[lane][5] = make_float4(__uint_as_float(bits1 & 0xffffu), __uint_as_float(bits1 >> 16), 0.f, 0.f);
+            if (EXT) {
+                float4 e3 = make_float4(0.f, 0.f, 0.f, 0.f), e4 = e3;
+                uint32_t ebits = 0;
+                if (flags & RF_SUBSTRATE) { e3 = wb.rec3[i]; ebits |= 1u; }
+                if (flags & RF_TEXKD) {
+                    const float4 r4 = wb.rec4[i];
+                    const float rgb[3] = { r4.x, r4.y, r4.z };
+                    const IllumCoefs kk = illum_coefs(rgb);           // same basis choice for the reflectance tables
+                    e4 = make_float4(kk.k0, kk.k1, kk.k2, 0.f);
+                    ebits |= 2u | (uint32_t)kk.b1 << 4 | (uint32_t)kk.b2 << 8;
+                }
+                e3.w = __uint_as_float(ebits);
+                stage[lane][6] = e3; stage[lane][7] = e4;
+            }
         }
         __syncwarp();
         // ---- phase B
@@ -415,9 +451,27 @@ __global__ void __launch_bounds__(32 * ACC_WARPS, 8) k_accumulate(DevScene sc, R
                 const uint32_t lightIdx = misc >> 4;
                 const SptMaterial &m = sc.materials[__float_as_uint(stage[v][5].x)];
                 const bool haveP = misc & 1u, metal = (misc & 2u) != 0;
-                const float s0 = __ldg(m.spec0 + lane), s1 = __ldg(m.spec1 + lane);
+                float s0 = __ldg(m.spec0 + lane);
+                const float s1 = __ldg(m.spec1 + lane);
                 float fL, fB, fP;
-                if (metal) {
+                uint32_t ebits = 0;
+                float4 e3 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (EXT) {
+                    e3 = stage[v][6];
+                    ebits = __float_as_uint(e3.w);
+                    if (ebits & 2u) {                                // Kd from the image map: FromRGB(rgb, SPECTRUM_REFLECTANCE)
+                        const float4 e4 = stage[v][7];
+                        IllumCoefs kk; kk.k0 = e4.x; kk.k1 = e4.y; kk.k2 = e4.z; kk.b1 = (ebits >> 4) & 15; kk.b2 = (ebits >> 8) & 15;
+                        s0 = refl_band(tb, kk, lane);
+                    }
+                }
+                if (EXT && (ebits & 1u)) {
+                    // FresnelBlend (reflection.cpp:224-236): Kd (1 - Ks) x diffuse scalar + (Ks + (1 - Ks) (1 - wi.wh)^5) x D-term
+                    const float oms = 1.f - s1, dR = s0 * oms;
+                    fL = dR * cLB.x + (s1 + oms * e3.x) * cLB.y;
+                    fB = dR * cLB.z + (s1 + oms * e3.y) * cLB.w;
+                    fP = dR * cPs.x + (s1 + oms * e3.z) * cPs.y;
+                } else if (metal) {
                     fL = cLB.x != 0.f ? cLB.x * fr_cond_fast(cLB.y, cLB.y * cLB.y, s0, s1) : 0.f;
                     fB = cLB.z != 0.f ? cLB.z * fr_cond_fast(cLB.w, cLB.w * cLB.w, s0, s1) : 0.f;
                     fP = cPs.x != 0.f ? cPs.x * fr_cond_fast(cPs.y, cPs.y * cPs.y, s0, s1) : 0.f;
@@ -635,12 +689,15 @@ void spt_launch_miss_env(int grid, cudaStream_t st, const DevScene &sc, const Wa
 void spt_launch_shade(int grid, cudaStream_t st, const DevScene &sc, const RenderCfg &cfg, const SampleSource &src, const WaveBuffers &wb,
                       int bounce, const uint32_t *queue, const uint32_t *count, uint32_t *shadow_count, uint32_t *mis_count,
                       uint32_t *elided_count, uint32_t *mis_any_count) {
-    if (sc.has_specular) k_shade<true><<<grid, 128, 0, st>>>(sc, cfg, src, wb, bounce, queue, count, shadow_count, mis_count, elided_count, mis_any_count);
-    else k_shade<false><<<grid, 128, 0, st>>>(sc, cfg, src, wb, bounce, queue, count, shadow_count, mis_count, elided_count, mis_any_count);
+#define SPT_SHADE(S, E) k_shade<S, E><<<grid, 128, 0, st>>>(sc, cfg, src, wb, bounce, queue, count, shadow_count, mis_count, elided_count, mis_any_count)
+    if (sc.has_ext) { if (sc.has_specular) SPT_SHADE(true, true); else SPT_SHADE(false, true); }
+    else { if (sc.has_specular) SPT_SHADE(true, false); else SPT_SHADE(false, false); }
+#undef SPT_SHADE
 }
 void spt_launch_accumulate(int grid, cudaStream_t st, const DevScene &sc, const RenderCfg &cfg, const WaveBuffers &wb, int bounce,
                            const uint32_t *queue, const uint32_t *count, uint32_t *next_queue, uint32_t *next_count) {
-    k_accumulate<<<grid, 128, 0, st>>>(sc, cfg, wb, bounce, queue, count, next_queue, next_count);
+    if (sc.has_ext) k_accumulate<true><<<grid, 128, 0, st>>>(sc, cfg, wb, bounce, queue, count, next_queue, next_count);
+    else k_accumulate<false><<<grid, 128, 0, st>>>(sc, cfg, wb, bounce, queue, count, next_queue, next_count);
 }
 void spt_launch_film_add(int grid, cudaStream_t st, const FilmView &film, const SptSpectralTables *tables, const float2 *img_xy,
                          const float *L, uint32_t cap, uint32_t n_samples, int spp) {

@@ -30,6 +30,10 @@ struct WaveBuffers {
     float4 *rec0;                     // {light dir a, b, MIS dir a, b}
     float4 *rec1;                     // {continuation a, b, sL = |cos| weight / pdf of the light sample, sB likewise for the MIS sample}
     float4 *rec2;                     // {sP = |cos| / pdf of the continuation, Russian-roulette draw, RF_* flags | light << 12, material | (emitter+1) << 16}
+    // extended materials only (DevScene::has_ext; one element otherwise): third coefficient of a substrate's
+    // directions and the RGB an image-mapped Kd evaluated to at this vertex
+    float4 *rec3;                     // {light dir c, MIS dir c, continuation c, -}: Schlick weight (1 - wi.wh)^5
+    float4 *rec4;                     // {r, g, b, -}
     float4 *laux;                     // infinite light only: RGB radiance of the sampled direction
     uint32_t *pflags;                 // scenes with specular materials: bit 0 = the ray of this path left a specular bounce
     float2 *img_xy;
@@ -53,6 +57,7 @@ struct RenderCfg {
     uint32_t seed;
     uint64_t pixel_base;              // first rank-local pixel of this wave
     uint32_t n_samples;               // samples in this wave
+    float diff_scale;                 // 1/sqrt(samplesPerPixel): RayDifferential::ScaleDifferentials (samplerrenderer.cpp:91)
 };
 
 // flags in rec2.z (low 12 bits)
@@ -60,6 +65,8 @@ enum { RF_L = 1,          // the light sample has a BSDF value: a shadow ray dec
        RF_P_SPEC = 2,     // the continuation was sampled from a specular BxDF (path.cpp:86)
        RF_B = 4,          // the BSDF sample of the MIS estimate was traced
        RF_P = 8,          // there is a continuation direction
+       RF_TEXKD = 256,    // spec0 of the material is replaced by FromRGB(rec4) (image-mapped Kd)
+       RF_SUBSTRATE = 512,// FresnelBlend: f[c] = Kd[c](1-Ks[c]) a + (Ks[c] + (1-Ks[c]) c) b, c in rec3
        RF_ON = 1024,      // matte with Oren-Nayar
        RF_METAL = 2048 };
 

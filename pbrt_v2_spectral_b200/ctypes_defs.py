@@ -5,7 +5,8 @@ NBANDS = 32
 
 
 class SptSpectralTables(C.Structure):
-    _fields_ = [("cie_y", C.c_float * NBANDS), ("yint", C.c_float), ("rgb_illum", (C.c_float * NBANDS) * 7)]
+    _fields_ = [("cie_y", C.c_float * NBANDS), ("yint", C.c_float), ("rgb_illum", (C.c_float * NBANDS) * 7),
+                ("rgb_refl", (C.c_float * NBANDS) * 7)]
 
 
 class SptSceneDesc(C.Structure):
@@ -28,13 +29,17 @@ class SptSceneDesc(C.Structure):
         ("env_rgb", C.c_void_p), ("env_func", C.c_void_p), ("env_cdf", C.c_void_p),
         ("env_func_int", C.c_void_p), ("env_marg_func", C.c_void_p), ("env_marg_cdf", C.c_void_p),
         ("env_marg_int", C.c_float),
+        ("n_textures", C.c_uint32), ("textures", C.c_void_p),
+        ("n_texels", C.c_uint64), ("tex_texels", C.c_void_p),
+        ("ewa_weight_lut", C.c_void_p),
     ]
 
 
 class SptCameraDesc(C.Structure):
     _fields_ = [("raster_to_camera", C.c_float * 16), ("camera_to_world", C.c_float * 16),
                 ("lens_radius", C.c_float), ("focal_distance", C.c_float),
-                ("shutter_open", C.c_float), ("shutter_close", C.c_float)]
+                ("shutter_open", C.c_float), ("shutter_close", C.c_float),
+                ("dx_camera", C.c_float * 3), ("dy_camera", C.c_float * 3)]
 
 
 class SptFilmDesc(C.Structure):
@@ -73,6 +78,7 @@ class SptStats(C.Structure):
 # row sizes of the table structs (bytes), for sanity checks against the container file
 SIZEOF_QUADRIC = 32
 SIZEOF_XFORM = 128
-SIZEOF_MATERIAL = 16 + 2 * 4 * NBANDS
+SIZEOF_MATERIAL = 16 + 2 * 4 * NBANDS + 16
+SIZEOF_TEXTURE = 64
 SIZEOF_LIGHT = 32 + 4 * NBANDS
 SIZEOF_LIGHT_SHAPE = 16

@@ -48,6 +48,9 @@
 #include "materials/mirror.h"
 #include "materials/glass.h"
 #include "materials/subsurface.h"
+#include "materials/substrate.h"
+#include "textures/imagemap.h"
+#include "textures/scale.h"
 #include "lights/diffuse.h"
 #include "lights/point.h"
 #include "lights/infinite.h"
@@ -121,6 +124,11 @@ SptSceneDesc LoweredScene::Desc() const {
     d.env_marg_func = ptr_or_null(env_marg_func);
     d.env_marg_cdf = ptr_or_null(env_marg_cdf);
     d.env_marg_int = env_marg_int;
+    d.n_textures = (uint32_t)textures.size();
+    d.textures = ptr_or_null(textures);
+    d.n_texels = tex_texels.size();
+    d.tex_texels = ptr_or_null(tex_texels);
+    d.ewa_weight_lut = ptr_or_null(ewa_weight_lut);
     return d;
 }
 
@@ -156,6 +164,9 @@ bool LoweredScene::Save(const std::string &path, std::string *err) const {
     w.vec("env_marg_func", 3, env_marg_func);
     w.vec("env_marg_cdf", 3, env_marg_cdf);
     w.put("env_marg_int", 3, &env_marg_int, 4, 1);
+    w.pod("textures", textures);
+    w.vec("tex_texels", 3, tex_texels);
+    w.vec("ewa_weight_lut", 3, ewa_weight_lut);
     w.put("camera", 0, &camera, sizeof(camera), 1, sizeof(camera));
     w.put("film", 0, &film, sizeof(film), 1, sizeof(film));
     w.put("params", 0, &params, sizeof(params), 1, sizeof(params));
@@ -167,6 +178,19 @@ bool LoweredScene::Save(const std::string &path, std::string *err) const {
 // ---------------------------------------------------------------------------------------------
 namespace {
 
+// texel type of an image map -> its Treturn, channel count and how a texel is flattened
+template <typename T> struct ImageRet;
+template <> struct ImageRet<RGBSpectrum> {
+    typedef Spectrum type;
+    enum { channels = 3 };
+    static void push(const RGBSpectrum &v, std::vector<float> *dst) { float rgb[3]; v.ToRGB(rgb); dst->insert(dst->end(), rgb, rgb + 3); }
+};
+template <> struct ImageRet<float> {
+    typedef float type;
+    enum { channels = 1 };
+    static void push(float v, std::vector<float> *dst) { dst->push_back(v); }
+};
+
 struct Lowerer {
     LoweredScene *out;
     std::string err;
@@ -174,6 +198,7 @@ struct Lowerer {
     std::map<const TriangleMesh *, std::pair<uint32_t, uint32_t> > meshBase;  // vertex base, tri base
     std::map<const Shape *, int> quadricIdx;
     std::map<const Light *, int> lightIdx;
+    std::map<const void *, uint64_t> texelBase;                                // MIPMap -> first float in tex_texels
 
     bool fail(const std::string &why) { err = why; return false; }
 
@@ -270,13 +295,82 @@ struct Lowerer {
         return true;
     }
 
-    // materials whose bump/normal maps are the constant-0 defaults only
-    bool CheckFlat(const Reference<Texture<float> > &bump, const Reference<Texture<Spectrum> > &normal) {
-        float b; Spectrum n;
-        if (!ConstTex(bump, &b, "bumpmap") || !ConstTex(normal, &n, "normalmap")) return false;
-        if (b != 0.f) return fail("non-zero constant bump map");
-        if (!n.IsBlack()) return fail("normal map present");
+    // One image map + its UV mapping -> textures[] (de-duplicated by value) and the texel pool.
+    template <typename T> bool AddImageTexture(const ImageTexture<T, typename ImageRet<T>::type> *img, float scale,
+                                               int32_t *idx, const char *what) {
+        const UVMapping2D *uv = dynamic_cast<const UVMapping2D *>(img->mapping);
+        if (!uv) return fail(std::string("texture mapping other than uv for ") + what);
+        const MIPMap<T> *mm = img->mipmap;
+        SptTexture t;
+        memset(&t, 0, sizeof(t));
+        t.channels = ImageRet<T>::channels;
+        t.width = (int32_t)mm->width; t.height = (int32_t)mm->height; t.n_levels = (int32_t)mm->nLevels;
+        t.wrap = mm->wrapMode == TEXTURE_REPEAT ? SPT_WRAP_REPEAT : (mm->wrapMode == TEXTURE_BLACK ? SPT_WRAP_BLACK : SPT_WRAP_CLAMP);
+        t.trilinear = mm->doTrilinear ? 1 : 0;
+        t.no_filter = mm->noFiltering ? 1 : 0;
+        t.max_aniso = mm->maxAnisotropy;
+        t.su = uv->su; t.sv = uv->sv; t.du = uv->du; t.dv = uv->dv;
+        t.scale = scale;
+        std::map<const void *, uint64_t>::iterator it = texelBase.find((const void *)mm);
+        if (it == texelBase.end()) {
+            uint64_t base = out->tex_texels.size();
+            for (uint32_t l = 0; l < mm->nLevels; ++l) {
+                const BlockedArray<T> &lvl = *mm->pyramid[l];
+                for (uint32_t v = 0; v < lvl.vSize(); ++v)
+                    for (uint32_t u = 0; u < lvl.uSize(); ++u) ImageRet<T>::push(lvl(u, v), &out->tex_texels);
+            }
+            texelBase[(const void *)mm] = base;
+            it = texelBase.find((const void *)mm);
+            if (out->ewa_weight_lut.empty() && MIPMap<T>::weightLut)
+                out->ewa_weight_lut.assign(MIPMap<T>::weightLut, MIPMap<T>::weightLut + WEIGHT_LUT_SIZE);
+        }
+        t.texel_offset = it->second;
+        for (size_t i = 0; i < out->textures.size(); ++i)
+            if (!memcmp(&out->textures[i], &t, sizeof(t))) { *idx = (int32_t)i; return true; }
+        out->textures.push_back(t);
+        *idx = (int32_t)out->textures.size() - 1;
         return true;
+    }
+
+    // Kd: a constant (-> spec0) or an RGB image map (-> tex index)
+    bool SpectrumParam(const Reference<Texture<Spectrum> > &tex, float *spec, int32_t *texIdx, const char *what) {
+        *texIdx = -1;
+        if (const ConstantTexture<Spectrum> *c = dynamic_cast<const ConstantTexture<Spectrum> *>(tex.GetPtr())) {
+            CopySpectrum(c->value.Clamp(), spec);
+            return true;
+        }
+        if (const ImageTexture<RGBSpectrum, Spectrum> *img = dynamic_cast<const ImageTexture<RGBSpectrum, Spectrum> *>(tex.GetPtr()))
+            return AddImageTexture<RGBSpectrum>(img, 1.f, texIdx, what);
+        return fail(std::string("texture for ") + what + " is neither constant nor an image map");
+    }
+
+    // bump map: the constant-0 default, a float image map, or ScaleTextures of one with constants;
+    // the normal map must be the constant-black default (the fork's NormalMap path is not lowered)
+    bool BumpParam(const Reference<Texture<float> > &bump, const Reference<Texture<Spectrum> > &normal, int32_t *texIdx) {
+        *texIdx = -1;
+        Spectrum n;
+        if (!ConstTex(normal, &n, "normalmap")) return false;
+        if (!n.IsBlack()) return fail("normal map present");
+        const Texture<float> *t = bump.GetPtr();
+        float scale = 1.f;
+        bool scaled = false;
+        for (;;) {
+            if (const ConstantTexture<float> *c = dynamic_cast<const ConstantTexture<float> *>(t)) {
+                if (scaled || c->value != 0.f) return fail("non-zero constant bump map");
+                return true;
+            }
+            if (const ImageTexture<float, float> *img = dynamic_cast<const ImageTexture<float, float> *>(t))
+                return AddImageTexture<float>(img, scale, texIdx, "bumpmap");
+            if (const ScaleTexture<float, float> *sc = dynamic_cast<const ScaleTexture<float, float> *>(t)) {
+                // tex1->Evaluate(dg) * tex2->Evaluate(dg) (scale.h:45-47): one operand must be a constant
+                const ConstantTexture<float> *c2 = dynamic_cast<const ConstantTexture<float> *>(sc->tex2.GetPtr());
+                if (!c2 || scaled) return fail("bump map: scale texture whose second operand is not a constant (or nested scales)");
+                scale = c2->value; scaled = true;
+                t = sc->tex1.GetPtr();
+                continue;
+            }
+            return fail("bump map texture is not an image map");
+        }
     }
 
     static void CopySpectrum(const Spectrum &s, float *dst) {
@@ -286,24 +380,30 @@ struct Lowerer {
     bool AddMaterial(const Material *m, int32_t *idx) {
         SptMaterial row;
         memset(&row, 0, sizeof(row));
+        row.tex_kd = row.tex_bump = -1;
         if (const MatteMaterial *mm = dynamic_cast<const MatteMaterial *>(m)) {
-            Spectrum kd; float sig;
-            if (!CheckFlat(mm->bumpMap, mm->normalMap) || !ConstTex(mm->Kd, &kd, "Kd") ||
+            float sig;
+            if (!BumpParam(mm->bumpMap, mm->normalMap, &row.tex_bump) || !SpectrumParam(mm->Kd, row.spec0, &row.tex_kd, "Kd") ||
                 !ConstTex(mm->sigma, &sig, "sigma")) return false;
             row.type = SPT_MAT_MATTE;
-            CopySpectrum(kd.Clamp(), row.spec0);
             row.p0 = Clamp(sig, 0.f, 90.f);
         } else if (const PlasticMaterial *pm = dynamic_cast<const PlasticMaterial *>(m)) {
-            Spectrum kd, ks; float rough;
-            if (!CheckFlat(pm->bumpMap, pm->normalMap) || !ConstTex(pm->Kd, &kd, "Kd") ||
+            Spectrum ks; float rough;
+            if (!BumpParam(pm->bumpMap, pm->normalMap, &row.tex_bump) || !SpectrumParam(pm->Kd, row.spec0, &row.tex_kd, "Kd") ||
                 !ConstTex(pm->Ks, &ks, "Ks") || !ConstTex(pm->roughness, &rough, "roughness")) return false;
             row.type = SPT_MAT_PLASTIC;
-            CopySpectrum(kd.Clamp(), row.spec0);
             CopySpectrum(ks.Clamp(), row.spec1);
             row.p0 = rough;
+        } else if (const SubstrateMaterial *sb = dynamic_cast<const SubstrateMaterial *>(m)) {
+            Spectrum ks; float nu, nv;                            // substrate.cpp:34-56
+            if (!BumpParam(sb->bumpMap, sb->normalMap, &row.tex_bump) || !SpectrumParam(sb->Kd, row.spec0, &row.tex_kd, "Kd") ||
+                !ConstTex(sb->Ks, &ks, "Ks") || !ConstTex(sb->nu, &nu, "uroughness") || !ConstTex(sb->nv, &nv, "vroughness")) return false;
+            row.type = SPT_MAT_SUBSTRATE;
+            CopySpectrum(ks.Clamp(), row.spec1);
+            row.p0 = nu; row.p1 = nv;
         } else if (const MetalMaterial *me = dynamic_cast<const MetalMaterial *>(m)) {
             Spectrum eta, k; float rough;
-            if (!CheckFlat(me->bumpMap, me->normalMap) || !ConstTex(me->eta, &eta, "eta") ||
+            if (!BumpParam(me->bumpMap, me->normalMap, &row.tex_bump) || !ConstTex(me->eta, &eta, "eta") ||
                 !ConstTex(me->k, &k, "k") || !ConstTex(me->roughness, &rough, "roughness")) return false;
             row.type = SPT_MAT_METAL;
             CopySpectrum(eta, row.spec0);
@@ -311,12 +411,12 @@ struct Lowerer {
             row.p0 = rough;
         } else if (const MirrorMaterial *mi = dynamic_cast<const MirrorMaterial *>(m)) {
             Spectrum kr;
-            if (!CheckFlat(mi->bumpMap, mi->normalMap) || !ConstTex(mi->Kr, &kr, "Kr")) return false;
+            if (!BumpParam(mi->bumpMap, mi->normalMap, &row.tex_bump) || !ConstTex(mi->Kr, &kr, "Kr")) return false;
             row.type = SPT_MAT_MIRROR;                            // SpecularReflection(Kr, FresnelNoOp), mirror.cpp:34-55
             CopySpectrum(kr.Clamp(), row.spec0);
         } else if (const GlassMaterial *gl = dynamic_cast<const GlassMaterial *>(m)) {
             Spectrum kr, kt; float ior;
-            if (!CheckFlat(gl->bumpMap, gl->normalMap) || !ConstTex(gl->Kr, &kr, "Kr") || !ConstTex(gl->Kt, &kt, "Kt") ||
+            if (!BumpParam(gl->bumpMap, gl->normalMap, &row.tex_bump) || !ConstTex(gl->Kr, &kr, "Kr") || !ConstTex(gl->Kt, &kt, "Kt") ||
                 !ConstTex(gl->index, &ior, "index")) return false;
             row.type = SPT_MAT_GLASS;                             // glass.cpp:34-58
             CopySpectrum(kr.Clamp(), row.spec0);
@@ -326,7 +426,7 @@ struct Lowerer {
             // Under a surface integrator that ignores the BSSRDF (path), the material is its BSDF:
             // SpecularReflection(Kr, FresnelDielectric(1, eta)) - subsurface.cpp:40-58 - i.e. glass without Kt.
             Spectrum kr; float eta;
-            if (!CheckFlat(su->bumpMap, su->normalMap) || !ConstTex(su->Kr, &kr, "Kr") || !ConstTex(su->eta, &eta, "eta")) return false;
+            if (!BumpParam(su->bumpMap, su->normalMap, &row.tex_bump) || !ConstTex(su->Kr, &kr, "Kr") || !ConstTex(su->eta, &eta, "eta")) return false;
             row.type = SPT_MAT_GLASS;
             CopySpectrum(kr.Clamp(), row.spec0);
             row.p0 = eta;
@@ -453,8 +553,16 @@ struct Lowerer {
             &SampledSpectrum::rgbIllum2SpectMagenta, &SampledSpectrum::rgbIllum2SpectYellow,
             &SampledSpectrum::rgbIllum2SpectRed, &SampledSpectrum::rgbIllum2SpectGreen,
             &SampledSpectrum::rgbIllum2SpectBlue };
+        const SampledSpectrum *refl[7] = {
+            &SampledSpectrum::rgbRefl2SpectWhite, &SampledSpectrum::rgbRefl2SpectCyan,
+            &SampledSpectrum::rgbRefl2SpectMagenta, &SampledSpectrum::rgbRefl2SpectYellow,
+            &SampledSpectrum::rgbRefl2SpectRed, &SampledSpectrum::rgbRefl2SpectGreen,
+            &SampledSpectrum::rgbRefl2SpectBlue };
         for (int k = 0; k < 7; ++k)
-            for (int i = 0; i < nSpectralSamples; ++i) out->tables.rgb_illum[k][i] = ill[k]->c[i];
+            for (int i = 0; i < nSpectralSamples; ++i) {
+                out->tables.rgb_illum[k][i] = ill[k]->c[i];
+                out->tables.rgb_refl[k][i] = refl[k]->c[i];
+            }
 
         // camera
         const PerspectiveCamera *pc = dynamic_cast<const PerspectiveCamera *>(camera);
@@ -466,6 +574,7 @@ struct Lowerer {
         out->camera.focal_distance = pc->focalDistance;
         out->camera.shutter_open = pc->shutterOpen;
         out->camera.shutter_close = pc->shutterClose;
+        for (int k = 0; k < 3; ++k) { out->camera.dx_camera[k] = pc->dxCamera[k]; out->camera.dy_camera[k] = pc->dyCamera[k]; }
 
         // film
         const SpectralImageFilm *film = dynamic_cast<const SpectralImageFilm *>(camera->film);

@@ -82,6 +82,9 @@ struct LoweredScene {
     int env_w, env_h;
     std::vector<float> env_rgb, env_func, env_cdf, env_func_int, env_marg_func, env_marg_cdf;
     float env_marg_int;
+    std::vector<SptTexture> textures;
+    std::vector<float> tex_texels;
+    std::vector<float> ewa_weight_lut;
 
     SptCameraDesc camera;
     SptFilmDesc film;

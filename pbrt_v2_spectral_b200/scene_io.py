@@ -64,10 +64,12 @@ class LoweredScene:
     def __init__(self, arrays):
         self.a = {k: np.ascontiguousarray(v) for k, v in arrays.items()}
         a = self.a
+        for key, dt in (("textures", np.uint8), ("tex_texels", np.float32), ("ewa_weight_lut", np.float32)):
+            a.setdefault(key, np.zeros(0, dt))
         if int(a["nbands"][0]) != D.NBANDS:
             raise ValueError("scene has %d bands, library expects %d" % (int(a["nbands"][0]), D.NBANDS))
         for key, size in (("quadrics", D.SIZEOF_QUADRIC), ("xforms", D.SIZEOF_XFORM), ("materials", D.SIZEOF_MATERIAL),
-                          ("lights", D.SIZEOF_LIGHT), ("light_shapes", D.SIZEOF_LIGHT_SHAPE)):
+                          ("lights", D.SIZEOF_LIGHT), ("light_shapes", D.SIZEOF_LIGHT_SHAPE), ("textures", D.SIZEOF_TEXTURE)):
             if a[key].size % size:
                 raise ValueError("table %s: size %d is not a multiple of %d" % (key, a[key].size, size))
         self.camera = _from_bytes(D.SptCameraDesc, a["camera"])
@@ -94,7 +96,8 @@ class LoweredScene:
         d.n_prims = a["prim_kind"].size
         for k in ("prim_kind", "prim_flags", "prim_id", "prim_data", "prim_material", "prim_light", "prim_xform",
                   "tri_vidx", "P", "N", "UV", "quadrics", "xforms", "materials", "lights", "light_shapes",
-                  "env_rgb", "env_func", "env_cdf", "env_func_int", "env_marg_func", "env_marg_cdf"):
+                  "env_rgb", "env_func", "env_cdf", "env_func_int", "env_marg_func", "env_marg_cdf",
+                  "textures", "tex_texels", "ewa_weight_lut"):
             setattr(d, k, self._ptr(k))
         d.n_tris = a["tri_vidx"].size // 3
         d.n_verts = a["P"].size // 3
@@ -106,6 +109,8 @@ class LoweredScene:
         d.tables = self.tables
         d.env_w, d.env_h = int(a["env_dims"][0]), int(a["env_dims"][1])
         d.env_marg_int = float(a["env_marg_int"][0])
+        d.n_textures = a["textures"].size // D.SIZEOF_TEXTURE
+        d.n_texels = a["tex_texels"].size
         return d
 
     @property

@@ -62,13 +62,14 @@ def trace_counts(scene, rays):
     return nodes.value, prims.value
 
 
-def shade_samples(scene, samples37, rng, max_depth=None):
+def shade_samples(scene, samples37, rng, max_depth=None, spp=None):
     s = np.ascontiguousarray(samples37, np.float32)
     g = np.ascontiguousarray(rng, np.float32)
     n = len(s)
     out = np.empty((n, D.NBANDS), np.float32)
     md = scene.params.max_depth if max_depth is None else max_depth
-    lib().orc_shade_samples(C.byref(scene.desc), C.byref(scene.camera), C.c_int32(md), _p(s), _p(g),
+    lib().orc_shade_samples(C.byref(scene.desc), C.byref(scene.camera), C.c_int32(md),
+                            C.c_int32(scene.params.spp if spp is None else spp), _p(s), _p(g),
                             C.c_int32(g.shape[1]), C.c_uint64(n), _p(out))
     return out
 
