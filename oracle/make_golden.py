@@ -219,8 +219,8 @@ CONFIGS = {
     "ssenv_small":     (ssenv, 200, 200, 4, 6000, 40, 4096),
     "specular_small":  (specular, 176, 176, 4, 6000, 40, 2048),
     # configs 3 and 4 with their shipped floor: substrate (FresnelBlend + Anisotropic), image-mapped Kd (EWA), bump map
-    "metal_shipped_small":  (metal_shipped, 200, 200, 4, 6000, 40, 1024),
-    "ssenv_shipped_small":  (ssenv_shipped, 200, 200, 4, 6000, 40, 4096),
+    "metal_shipped_small":  (metal_shipped, 200, 200, 4, 6000, 40, 8192),
+    "ssenv_shipped_small":  (ssenv_shipped, 200, 200, 4, 6000, 40, 8192),
     # config 5 recipe at 1 M triangles (BVH + pair nodes + vertices = 176 MB, larger than L2): optional bench workload
     "synth_1m":        (lambda w, h, spp, name, maxdepth=5: synth(w, h, spp, name, maxdepth, ntris=1000000, chunks=10), 1024, 576, 16, 0, 0, 0),
     # small committed fixture

@@ -52,14 +52,21 @@ def test_secondary_rays(case):
 def test_path_radiance_vs_reference(case):
     """PathIntegrator::Li for the reference's own sample vectors and RNG draws. CUDA's sinf/cosf/powf/
     atan2f/acosf differ from glibc's by an ulp or two, so radiance is compared at 2e-4 relative per
-    sample, with a small allowance for samples where that ulp flips a discrete decision."""
-    name, _, scene, g = case
+    sample, with a small allowance for samples where that ulp flips a discrete decision or is amplified:
+    0.2 %, or three times the fraction of samples the ORACLE itself moves by more than 2e-4 when its inputs
+    move by one ulp (O.ulp_sensitivity: 0.5 % on the shipped metal scene - Blinn exponent 1000 lit by an HDR
+    map - against 0.04 % with the same teapot under a constant light)."""
+    name, lowered, scene, g = case
     L = scene.shade_samples(g["samples"], g["rng"])
     ref = g["L"]
     scale = np.maximum(np.abs(ref).max(axis=1), 1e-6)
     err = np.abs(L - ref).max(axis=1) / scale
     bad = err > 2e-4
-    assert bad.mean() < 2e-3, "%s: %d of %d samples differ (worst %g)" % (name, bad.sum(), len(bad), err.max())
+    allowed = max(2e-3, 3.0 * O.ulp_sensitivity(lowered, g["samples"], g["rng"]))
+    print("%s: %d of %d samples beyond 2e-4 (%.3f %%, allowed %.3f %%), median error %.2g" % (
+        name, bad.sum(), len(bad), 100 * bad.mean(), 100 * allowed, np.median(err)))
+    assert np.median(err) < 2e-5
+    assert bad.mean() < allowed, "%s: %d of %d samples differ (worst %g)" % (name, bad.sum(), len(bad), err.max())
     tot = ref.sum(0)
     assert np.all(np.abs(L.sum(0) - tot) <= 2e-3 * tot + 1e-6), "per-band totals drift"
 
@@ -104,15 +111,22 @@ def test_film_wide_filter():
     assert np.allclose(c, oc, rtol=2e-5, atol=1e-6)
 
 
-def test_render_matches_oracle_render():
+RENDER_CASES = [c for c in CASES if c[0] in ("tiny", "metal_shipped_small", "ssenv_shipped_small")]
+
+
+@pytest.mark.parametrize("rcase", RENDER_CASES, ids=[c[0] for c in RENDER_CASES])
+def test_render_matches_oracle_render(rcase):
     """Whole job (K1..K7 with the product sampler, compaction, film) against the oracle running the
-    same sampler on the CPU, small image."""
-    lowered, _ = O.load_case(*CASES[0][1:])
+    same sampler on the CPU, small image. The shipped-floor scenes add what only spt_render exercises of the
+    textured path: ray differentials rebuilt from the film position and scaled by 1/sqrt(spp)."""
+    lowered, g = O.load_case(*rcase[1:])
     scene = capi.Scene(lowered)
     rp = D.SptRenderParams.from_buffer_copy(bytes(lowered.params))
-    rp.spp = 8
+    rp.spp = 8 if rcase[0] == "tiny" else 2
+    # a pixel sums spp samples: allowance scaled from the per-sample ulp sensitivity of the scene (see above)
+    allowed = max(5e-3, 3.0 * rp.spp * O.ulp_sensitivity(lowered, g["samples"], g["rng"], tol=1e-3))
     rp.seed = 7
-    rp.wave_pixels = 600          # several waves
+    rp.wave_pixels = 600 if rcase[0] == "tiny" else 9000         # several waves
     film = capi.Film(lowered.film)
     scene.render(film, rp)
     c, w = film.download()
@@ -123,7 +137,8 @@ def test_render_matches_oracle_render():
     assert st["camera_samples"] == (rp.x_end - rp.x_start) * (rp.y_end - rp.y_start) * rp.spp
     scale = np.maximum(oc.max(axis=2, keepdims=True), 1e-3)
     err = (np.abs(c - oc) / scale).max(axis=2)
-    assert (err > 1e-3).mean() < 5e-3, "pixels differ: %d of %d (worst %g)" % ((err > 1e-3).sum(), err.size, err.max())
+    print("%s: %d of %d pixels beyond 1e-3 (allowed %.2f %%)" % (rcase[0], (err > 1e-3).sum(), err.size, 100 * allowed))
+    assert (err > 1e-3).mean() < allowed, "pixels differ: %d of %d (worst %g)" % ((err > 1e-3).sum(), err.size, err.max())
     assert np.allclose(c.sum((0, 1)), oc.sum((0, 1)), rtol=2e-3)
 
 
