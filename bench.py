@@ -34,6 +34,8 @@ SCENE_SPT = os.path.join(ROOT, "assets", "_lowered", WORKLOAD + ".spt")
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "bin", "pbrt")
 REF_SCENES = os.path.join(ROOT, "oracle", "_ref", "scenes")
 CPU_SAMPLE_SPP = 16          # bounded sample of the workload for the CPU arm: same frame, 16 of the 64 spp
+# workloads that have a scene file the reference binary can run for the CPU leg: (xres, yres, spp, bounded-sample spp)
+CPU_WORKLOADS = {"killeroo_path": (700, 700, 64, CPU_SAMPLE_SPP), "metal_path": (400, 400, 512, 16), "ssenv_path": (1920, 1080, 1024, 1)}
 
 
 def read_peaks():
@@ -80,7 +82,7 @@ def reference_run(scene_text, ncores):
     """One run of the reference binary on scene_text; returns wall seconds."""
     d = tempfile.mkdtemp(prefix="sptref_")
     try:
-        for sub in ("geometry", "spds", "brdfs"):
+        for sub in ("geometry", "spds", "brdfs", "textures"):
             os.symlink(os.path.join(REF_SCENES, sub), os.path.join(d, sub))
         with open(os.path.join(d, "scene.pbrt"), "w") as f:
             f.write(scene_text)
@@ -92,8 +94,8 @@ def reference_run(scene_text, ncores):
         shutil.rmtree(d, ignore_errors=True)
 
 
-def reference_scene(spp, res=None):
-    s = open(os.path.join(REF_SCENES, WORKLOAD + ".pbrt")).read()
+def reference_scene(spp, res=None, workload=WORKLOAD):
+    s = open(os.path.join(REF_SCENES, workload + ".pbrt")).read()
     s = re.sub(r'"integer pixelsamples" \[\d+\]', '"integer pixelsamples" [%d]' % spp, s)
     if res:
         s = re.sub(r'"integer xresolution" \[\d+\] "integer yresolution" \[\d+\]',
@@ -101,14 +103,15 @@ def reference_scene(spp, res=None):
     return s
 
 
-def cpu_reference_msamples(runs=1):
+def cpu_reference_msamples(runs=1, workload=WORKLOAD):
     """Msamples/s of the unmodified reference (oracle/_ref/bin/pbrt, all host cores) on the bounded
-    sample: the workload's frame at CPU_SAMPLE_SPP spp. Parse + BVH build time (the same scene at 8x8, 1 spp)
+    sample: the workload's frame at a fraction of its spp. Parse + BVH build time (the same scene at 8x8, 1 spp)
     is subtracted, SURVEY.md 8d."""
     ncores = os.cpu_count() or 1
-    setup = min(reference_run(reference_scene(1, 8), ncores) for _ in range(2))
-    best = min(reference_run(reference_scene(CPU_SAMPLE_SPP), ncores) for _ in range(runs))
-    n_samples = 701 * 701 * CPU_SAMPLE_SPP
+    xres, yres, _, cpu_spp = CPU_WORKLOADS[workload]
+    setup = min(reference_run(reference_scene(1, 8, workload), ncores) for _ in range(2))
+    best = min(reference_run(reference_scene(cpu_spp, None, workload), ncores) for _ in range(runs))
+    n_samples = (xres + 1) * (yres + 1) * cpu_spp
     render = max(best - setup, 1e-6)
     return n_samples / render / 1e6, ncores, render, setup
 
@@ -188,6 +191,11 @@ def main():
         raise SystemExit("lowered workload scene %s missing: run __graft_entry__.build() where the reference tree is" % scene_spt)
     lowered = LoweredScene.load(scene_spt)
     workload_desc = WORKLOAD_DESC if args.workload == WORKLOAD else {
+        "metal_path": "scenes/metal.pbrt (BASELINE config 3) with its shipped floor - substrate, lines.exr as EWA-filtered Kd and as bump map - "
+                      "Au teapot (measured eta/k SPDs, Blinn exponent 1000), grace environment map for the absent uffizi map, path maxdepth 5, "
+                      "400x400, LD 512 spp, box filter",
+        "ssenv_path": "scenes/ss-envmap.pbrt (BASELINE config 4) as shipped except the path integrator: subsurface teapot, substrate floor with "
+                      "image-mapped Kd and bump map, grace environment map importance sampled, path maxdepth 5, 1920x1080, LD 1024 spp, box filter",
         "synth_1m": "synthetic random-triangle scene (BASELINE config 5 recipe, SURVEY 8d) at 1 000 000 triangles, matte + plastic, sphere area light + "
                     "constant infinite light, path maxdepth 5, 1024x576, LD 16 spp, box filter"}.get(args.workload, args.workload)
     rp = D.SptRenderParams.from_buffer_copy(bytes(lowered.params))
@@ -363,7 +371,8 @@ def main():
         "note": "config 1: k_shade is FP32/FP64/INT instruction-issue bound (ncu: issue slots 48 % busy at 16 warps/SM, DRAM 9 %), the traversal "
                 "kernels walk a 4 MB BVH that stays in L2/L1 (DRAM traffic = ray I/O): for both the HBM fraction is indicative only; "
                 "k_accumulate is the HBM-streaming kernel. Per-kernel lines in roofline_by_kernel; traffic from profiles/traffic.json "
-                "(ncu --set full, mean of the captured launches)"})
+                "(ncu --set full, mean of the captured launches)" if args.workload == WORKLOAD else
+                "algorithmic bytes per unit as for config 1 (DESIGN.md 3); traffic figures in profiles/traffic.json were captured on config 1"})
     roofline_by_kernel = {D.K_NAMES[k]: roof(k) for k in unit_bytes if class_launches[k]}
     rays_total = class_rays[D.K_TRACE_PATH] + class_rays[D.K_TRACE_MIS] + class_rays[D.K_TRACE_SHADOW]
     out = {
@@ -371,6 +380,7 @@ def main():
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "reference scene file (killeroo-simple) lowered by the host side; no synthetic substitution" if args.workload == WORKLOAD
+                else "reference scene file lowered by the host side (substitutions listed in config.workload)" if not args.workload.startswith("synth")
                 else "synthetic scene written as .pbrt text, parsed, BVH-built and lowered by the reference's own code (oracle/make_golden.py)",
         "config": {"workload": workload_desc, "camera_samples_per_step": n_samples_total,
                    "parallelism": "image tile sets (32x32, round-robin) x%d, scene replicated, NCCL film reduce" % world,
@@ -393,10 +403,12 @@ def main():
         "clocks": sampler.summary() if sampler else None,
         "image_checksum": image_sum,
     }
-    if world == 1 and not args.no_cpu_baseline and os.path.exists(REF_BIN) and args.workload == WORKLOAD:
-        v, cores, render_s, setup_s = cpu_reference_msamples()
+    if world == 1 and not args.no_cpu_baseline and os.path.exists(REF_BIN) and args.workload in CPU_WORKLOADS and \
+            os.path.exists(os.path.join(REF_SCENES, args.workload + ".pbrt")):
+        v, cores, render_s, setup_s = cpu_reference_msamples(workload=args.workload)
         out["cpu_baseline"] = {"value": v, "unit": "Msamples/s", "cores": cores, "kind": "reference",
-                               "sample": "reference pbrt on the same frame at %d of 64 spp (%.1f s render, %.2f s parse+BVH subtracted)" % (CPU_SAMPLE_SPP, render_s, setup_s)}
+                               "sample": "reference pbrt on the same frame at %d of %d spp (%.1f s render, %.2f s parse+BVH subtracted)" % (
+                                   CPU_WORKLOADS[args.workload][3], CPU_WORKLOADS[args.workload][2], render_s, setup_s)}
     else:
         out["cpu_baseline"] = None
     print(json.dumps(out))

@@ -126,6 +126,9 @@ typedef struct SptLight {
     float pos[3];
     float sum_area;                 /* ShapeSet::sumArea as the reference accumulated it */
     float spectrum[SPT_NBANDS];
+    int32_t n_samples;              /* Sampler::RoundSize(Light::nSamples): samples per camera hit under the
+                                       directlighting integrator (src/integrators/directlighting.cpp:53-58); >= 1 */
+    int32_t pad_[3];
 } SptLight;
 
 /* One entry of a ShapeSet (src/core/light.cpp:106-128): a refined, intersectable shape. */
@@ -204,7 +207,14 @@ typedef struct SptFilmDesc {
     float filter_table[256];        /* 16x16, row = y (src/film/spectralImage.cpp:55-66) */
 } SptFilmDesc;
 
-/* What SamplerRenderer + LDSampler + PathIntegrator are configured with. */
+/* Surface integrators.
+ *   PATH        PathIntegrator (src/integrators/path.cpp:44-115)
+ *   DIRECT_ALL  DirectLightingIntegrator with strategy "all" (src/integrators/directlighting.cpp:70-105):
+ *               emitted light + UniformSampleAllLights (src/core/integrator.cpp:39-71) at the camera ray's hit.
+ *               Scenes with specular materials are not lowered under it (its SpecularReflect/Transmit recursion). */
+enum { SPT_INTEGRATOR_PATH = 0, SPT_INTEGRATOR_DIRECT_ALL = 1 };
+
+/* What SamplerRenderer + LDSampler + the surface integrator are configured with. */
 typedef struct SptRenderParams {
     int32_t spp;                    /* LDSampler::nPixelSamples (power of two) */
     int32_t max_depth;              /* PathIntegrator::maxDepth (src/integrators/path.cpp:118-121) */
@@ -215,6 +225,7 @@ typedef struct SptRenderParams {
     int32_t wave_pixels;            /* pixels per wavefront (0 = default) */
     int32_t skip_border;            /* 1: skip the sample-extent border column/row whose samples the
                                        box filter rejects */
+    int32_t integrator;             /* SPT_INTEGRATOR_* */
 } SptRenderParams;
 
 /* kernel classes of the wavefront, for per-class device time (CUDA events on the launching stream) */
@@ -283,17 +294,21 @@ int spt_trace_closest_dev(SptScene *scene, const float *rays_dev, uint64_t n,
                           uint32_t *out_slot_dev, float *out_t_dev);
 int spt_trace_any_dev(SptScene *scene, const float *rays_dev, uint64_t n, uint8_t *out_hit_dev);
 
-/* SamplerRenderer::Li + PathIntegrator::Li for caller-supplied sample vectors
- * (src/renderers/samplerrenderer.cpp:225-247, src/integrators/path.cpp:44-115).
+/* SamplerRenderer::Li + the surface integrator's Li for caller-supplied sample vectors
+ * (src/renderers/samplerrenderer.cpp:225-247, src/integrators/path.cpp:44-115, directlighting.cpp:70-105).
  * spp: Sampler::samplesPerPixel - the camera ray differentials are scaled by 1/sqrt(spp)
  * (src/renderers/samplerrenderer.cpp:91, src/core/geometry.h:368-373) before image textures are filtered with them.
  * samples: n x 37 floats in the reference's Sample memory order {imageX,imageY,lensU,lensV,time,
  * oneD[0..13], twoD[0..8][2]} (src/core/sampler.cpp:88-117, src/integrators/path.cpp:33-41);
  * rng: n x n_rng floats consumed in order where the reference draws from RNG (bounces >= 3 and
  * Russian roulette, src/integrators/path.cpp:82,97; src/core/integrator.cpp:84-99).
+ * integrator = SPT_INTEGRATOR_DIRECT_ALL: samples are n x (7 + 6 N) floats, N = sum of the lights' n_samples, in the
+ * order DirectLightingIntegrator::RequestSamples leaves them (directlighting.cpp:46-60, src/core/light.cpp:56-60,
+ * src/core/reflection.cpp:494-498): {5 camera floats, per light [light component x n_i, bsdf component x n_i],
+ * 2 floats of the volume integrator, per light [light position x 2 n_i, bsdf direction x 2 n_i]}; rng is unused.
  * out_L: n x SPT_NBANDS radiance BEFORE the NaN/negative/inf guards of
  * src/renderers/samplerrenderer.cpp:119-133. */
-int spt_shade_samples(SptScene *scene, const SptCameraDesc *cam, int32_t max_depth, int32_t spp,
+int spt_shade_samples(SptScene *scene, const SptCameraDesc *cam, int32_t integrator, int32_t max_depth, int32_t spp,
                       const float *samples, const float *rng, int32_t n_rng, uint64_t n, float *out_L);
 
 /* Film: SpectralImageFilm pixels {c[SPT_NBANDS], weightSum} (src/film/spectralImage.h:74-84). */

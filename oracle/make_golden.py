@@ -196,6 +196,25 @@ def specular(w, h, spp, name, maxdepth=5):
     return s
 
 
+def killeroo_direct(w, h, spp, name, maxdepth=5):
+    """killeroo-simple.pbrt AS SHIPPED: SurfaceIntegrator "directlighting" (strategy all), the sphere light's
+    nsamples 8."""
+    s = read(os.path.join(REF, "scenes/killeroo-simple.pbrt"))
+    assert 'SurfaceIntegrator "directlighting"' in s
+    return set_filename(set_spp(set_res(s, w, h), spp), name)
+
+
+def bunny_direct(w, h, spp, name, maxdepth=5):
+    """bunny.pbrt as shipped (default directlighting integrator, point light + disk area light with nsamples 4) except
+    its measured BRDF ("next"), for which plastic stands in."""
+    s = read(os.path.join(REF, "scenes/bunny.pbrt"))
+    s = s.replace('Film "image"', 'Film "image" "integer xresolution" [%d] "integer yresolution" [%d]\n'
+                  'Sampler "lowdiscrepancy" "integer pixelsamples" [%d]' % (w, h, spp), 1)
+    s = s.replace('Material "measured" "string filename" "brdfs/mystique.brdf"',
+                  'Material "plastic" "color Kd" [.3 .25 .4] "color Ks" [.4 .4 .4] "float roughness" [.08]')
+    return set_filename(s, name)
+
+
 def tiny(w, h, spp, name, maxdepth=5):
     s = read(os.path.join(TESTS_GOLDEN, "tiny.pbrt"))
     return set_filename(set_spp(set_res(s, w, h), spp), name)
@@ -221,6 +240,13 @@ CONFIGS = {
     # configs 3 and 4 with their shipped floor: substrate (FresnelBlend + Anisotropic), image-mapped Kd (EWA), bump map
     "metal_shipped_small":  (metal_shipped, 200, 200, 4, 6000, 40, 8192),
     "ssenv_shipped_small":  (ssenv_shipped, 200, 200, 4, 6000, 40, 8192),
+    # configs 3 and 4 at BASELINE's full size, shipped floor: optional bench workloads (bench.py --workload metal_path / ssenv_path)
+    "metal_path":      (metal_shipped, 400, 400, 512, 0, 0, 0),
+    "ssenv_path":      (ssenv_shipped, 1920, 1080, 1024, 0, 0, 0),
+    # the shipped scenes under their own integrator (directlighting, strategy all): SURVEY.md 8f N3
+    "killeroo_direct_small": (killeroo_direct, 176, 176, 4, 6000, 8, 1024),
+    "bunny_direct_small":    (bunny_direct, 320, 240, 4, 6000, 8, 1024),
+    "killeroo_direct":       (killeroo_direct, 700, 700, 64, 0, 0, 0),
     # config 5 recipe at 1 M triangles (BVH + pair nodes + vertices = 176 MB, larger than L2): optional bench workload
     "synth_1m":        (lambda w, h, spp, name, maxdepth=5: synth(w, h, spp, name, maxdepth, ntris=1000000, chunks=10), 1024, 576, 16, 0, 0, 0),
     # small committed fixture

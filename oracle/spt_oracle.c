@@ -1449,12 +1449,75 @@ static void li_sample(const SptSceneDesc *sc, const SptCameraDesc *cam, int maxD
     memcpy(Lout, L, sizeof(L));
 }
 
-void orc_shade_samples(const SptSceneDesc *sc, const SptCameraDesc *cam, int32_t max_depth, int32_t spp,
+/* SamplerRenderer::Li (renderers/samplerrenderer.cpp:225-247) + DirectLightingIntegrator::Li with strategy "all"
+ * (integrators/directlighting.cpp:70-105) + UniformSampleAllLights (core/integrator.cpp:39-71). The scene has no
+ * specular BxDF (lowering), so SpecularReflect / SpecularTransmit (core/integrator.cpp:169-236) sample nothing.
+ * Sample layout (directlighting.cpp:46-60, light.cpp:56-60, reflection.cpp:494-498, sampler.cpp:88-117), N = sum n_i:
+ *   1-D from [5]: per light {light component x n_i, bsdf component x n_i}; then 2 volume-integrator floats
+ *   2-D from [7 + 2N]: per light {light position x 2 n_i, bsdf direction x 2 n_i}                              */
+static int direct_sample_floats(const SptSceneDesc *sc) {
+    int N = 0;
+    for (uint32_t i = 0; i < sc->n_lights; ++i) N += sc->lights[i].n_samples;
+    return 7 + 6 * N;
+}
+static void li_sample_direct(const SptSceneDesc *sc, const SptCameraDesc *cam, int spp, const float *smp, float *Lout) {
+    Ray ray;
+    RayDiff rd;
+    camera_ray_diff(cam, smp, spp, &ray, &rd);
+    float L[NB];
+    for (int c = 0; c < NB; ++c) L[c] = 0.f;
+    uint32_t slot; Hit isect;
+    if (!bvh_intersect(sc, &ray, 0, &slot, &isect, NULL, NULL)) {
+        for (uint32_t i = 0; i < sc->n_lights; ++i) {
+            float le[NB];
+            light_le(sc, sc->lights + i, ray.d, le);
+            for (int c = 0; c < NB; ++c) L[c] += le[c];
+        }
+        memcpy(Lout, L, sizeof(L));
+        return;
+    }
+    BSDF bsdf; v3 n;
+    make_bsdf(sc, slot, &isect, &rd, &bsdf, &n);
+    v3 p = isect.p, wo = vneg(ray.d);
+    float le[NB];
+    isect_le(sc, slot, &isect, wo, le);
+    for (int c = 0; c < NB; ++c) L[c] += le[c];
+    int N = 0;
+    for (uint32_t i = 0; i < sc->n_lights; ++i) N += sc->lights[i].n_samples;
+    const float *oneD = smp + 5, *twoD = smp + 7 + 2 * N;
+    float Lall[NB];
+    for (int c = 0; c < NB; ++c) Lall[c] = 0.f;
+    for (uint32_t i = 0; i < sc->n_lights; ++i) {
+        int nSamples = sc->lights[i].n_samples;
+        float Ld[NB];
+        for (int c = 0; c < NB; ++c) Ld[c] = 0.f;
+        for (int j = 0; j < nSamples; ++j) {
+            float ls[3] = { twoD[2 * j], twoD[2 * j + 1], oneD[j] };
+            float bs[3] = { twoD[2 * nSamples + 2 * j], twoD[2 * nSamples + 2 * j + 1], oneD[nSamples + j] };
+            float e[NB];
+            estimate_direct(sc, sc->lights + i, (int)i, p, n, wo, isect.rayEpsilon, &bsdf, ls, bs, e);
+            for (int c = 0; c < NB; ++c) Ld[c] += e[c];
+        }
+        for (int c = 0; c < NB; ++c) Lall[c] += Ld[c] / nSamples;
+        oneD += 2 * nSamples; twoD += 4 * nSamples;
+    }
+    for (int c = 0; c < NB; ++c) L[c] += Lall[c];
+    memcpy(Lout, L, sizeof(L));
+}
+
+int orc_sample_floats(const SptSceneDesc *sc, int32_t integrator) {
+    return integrator == SPT_INTEGRATOR_DIRECT_ALL ? direct_sample_floats(sc) : 37;
+}
+
+void orc_shade_samples(const SptSceneDesc *sc, const SptCameraDesc *cam, int32_t integrator, int32_t max_depth, int32_t spp,
                        const float *samples, const float *rng, int32_t n_rng, uint64_t n, float *out_L) {
+    const int stride = orc_sample_floats(sc, integrator);
 #pragma omp parallel for schedule(dynamic, 64)
-    for (int64_t i = 0; i < (int64_t)n; ++i)
-        li_sample(sc, cam, max_depth, spp, samples + 37 * i, rng ? rng + (size_t)n_rng * i : NULL, rng ? n_rng : 0,
-                  out_L + (size_t)NB * i);
+    for (int64_t i = 0; i < (int64_t)n; ++i) {
+        if (integrator == SPT_INTEGRATOR_DIRECT_ALL) li_sample_direct(sc, cam, spp, samples + (size_t)stride * i, out_L + (size_t)NB * i);
+        else li_sample(sc, cam, max_depth, spp, samples + 37 * i, rng ? rng + (size_t)n_rng * i : NULL, rng ? n_rng : 0,
+                       out_L + (size_t)NB * i);
+    }
 }
 
 /* ------------------------------------------------------------------------------------------ */

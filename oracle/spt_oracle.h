@@ -19,7 +19,9 @@ void orc_trace_any(const SptSceneDesc *scene, const float *rays, uint64_t n, uin
  * algorithmic bytes) */
 void orc_trace_closest_counted(const SptSceneDesc *scene, const float *rays, uint64_t n,
                                uint64_t *nodes, uint64_t *prim_tests);
-void orc_shade_samples(const SptSceneDesc *scene, const SptCameraDesc *cam, int32_t max_depth, int32_t spp,
+/* floats per sample vector: 37 (path) or 7 + 6 * sum of the lights' n_samples (directlighting "all") */
+int orc_sample_floats(const SptSceneDesc *scene, int32_t integrator);
+void orc_shade_samples(const SptSceneDesc *scene, const SptCameraDesc *cam, int32_t integrator, int32_t max_depth, int32_t spp,
                        const float *samples, const float *rng, int32_t n_rng, uint64_t n, float *out_L);
 void orc_film_add_samples(const SptFilmDesc *film, const SptSpectralTables *tables,
                           const float *image_xy, const float *L, uint64_t n, float *c, float *weight);

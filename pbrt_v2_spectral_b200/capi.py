@@ -53,7 +53,7 @@ def lib():
         L.spt_trace_any.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         L.spt_trace_closest_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
         L.spt_trace_any_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
-        L.spt_shade_samples.argtypes = [C.c_void_p, C.POINTER(D.SptCameraDesc), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+        L.spt_shade_samples.argtypes = [C.c_void_p, C.POINTER(D.SptCameraDesc), C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                         C.c_int32, C.c_uint64, C.c_void_p]
         L.spt_film_create.restype = C.c_void_p
         L.spt_film_create.argtypes = [C.POINTER(D.SptFilmDesc)]
@@ -173,14 +173,15 @@ class Scene:
     def trace_any_dev(self, rays_ptr, n, hit_ptr):
         _check(lib().spt_trace_any_dev(self.h, rays_ptr, n, hit_ptr))
 
-    def shade_samples(self, samples37, rng, max_depth=None, camera=None, spp=None):
+    def shade_samples(self, samples37, rng, max_depth=None, camera=None, spp=None, integrator=None):
         s = np.ascontiguousarray(samples37, np.float32)
         g = np.ascontiguousarray(rng, np.float32) if rng is not None else None
         out = np.empty((len(s), D.NBANDS), np.float32)
         md = self.lowered.params.max_depth if max_depth is None else max_depth
         cam = camera if camera is not None else self.lowered.camera
         nspp = self.lowered.params.spp if spp is None else spp
-        _check(lib().spt_shade_samples(self.h, C.byref(cam), md, nspp, _p(s), _p(g), g.shape[1] if g is not None else 0,
+        integ = self.lowered.params.integrator if integrator is None else integrator
+        _check(lib().spt_shade_samples(self.h, C.byref(cam), integ, md, nspp, _p(s), _p(g), g.shape[1] if g is not None else 0,
                                        len(s), _p(out)))
         return out
 

@@ -56,7 +56,10 @@ class SptRenderParams(C.Structure):
                 ("x_start", C.c_int32), ("x_end", C.c_int32), ("y_start", C.c_int32), ("y_end", C.c_int32),
                 ("seed", C.c_uint64),
                 ("tile_rank", C.c_int32), ("tile_nranks", C.c_int32), ("tile_size", C.c_int32),
-                ("wave_pixels", C.c_int32), ("skip_border", C.c_int32)]
+                ("wave_pixels", C.c_int32), ("skip_border", C.c_int32), ("integrator", C.c_int32)]
+
+
+INTEGRATOR_PATH, INTEGRATOR_DIRECT_ALL = 0, 1
 
 
 K_GEN, K_TRACE_PATH, K_SHADE, K_TRACE_SHADOW, K_TRACE_MIS, K_ACCUMULATE, K_FILM, K_CLASSES = 0, 1, 2, 3, 4, 5, 6, 8
@@ -80,5 +83,5 @@ SIZEOF_QUADRIC = 32
 SIZEOF_XFORM = 128
 SIZEOF_MATERIAL = 16 + 2 * 4 * NBANDS + 16
 SIZEOF_TEXTURE = 64
-SIZEOF_LIGHT = 32 + 4 * NBANDS
+SIZEOF_LIGHT = 32 + 4 * NBANDS + 16
 SIZEOF_LIGHT_SHAPE = 16

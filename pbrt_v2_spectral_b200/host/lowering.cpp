@@ -58,6 +58,7 @@
 #include "film/spectralImage.h"
 #include "samplers/lowdiscrepancy.h"
 #include "integrators/path.h"
+#include "integrators/directlighting.h"
 #include "textures/constant.h"
 #undef private
 #undef protected
@@ -440,7 +441,7 @@ struct Lowerer {
         return true;
     }
 
-    bool AddLights(const Scene *scene) {
+    bool AddLights(const Scene *scene, const Sampler *sampler) {
         for (size_t li = 0; li < scene->lights.size(); ++li) {
             const Light *l = scene->lights[li];
             SptLight row;
@@ -499,6 +500,7 @@ struct Lowerer {
             } else {
                 return fail(std::string("unsupported light type ") + typeid(*l).name());
             }
+            row.n_samples = std::max(1, sampler ? ((Sampler *)sampler)->RoundSize(l->nSamples) : l->nSamples);
             lightIdx[l] = (int)out->lights.size();
             out->lights.push_back(row);
         }
@@ -524,7 +526,7 @@ struct Lowerer {
         }
         out->bvh_nodes.assign((const uint8_t *)nodes, (const uint8_t *)nodes + (size_t)nNodes * 32);
 
-        if (!AddLights(scene)) return false;
+        if (!AddLights(scene, sampler)) return false;
 
         size_t np = bvh->primitives.size();
         for (size_t i = 0; i < np; ++i) {
@@ -591,10 +593,20 @@ struct Lowerer {
         // sampler + integrator
         const LDSampler *ld = dynamic_cast<const LDSampler *>(sampler);
         if (!ld) return fail("sampler is not the low-discrepancy sampler");
-        const PathIntegrator *pi = dynamic_cast<const PathIntegrator *>(surf);
-        if (!pi) return fail("surface integrator is not the path integrator");
         out->params.spp = ld->nPixelSamples;
-        out->params.max_depth = pi->maxDepth;
+        if (const PathIntegrator *pi = dynamic_cast<const PathIntegrator *>(surf)) {
+            out->params.integrator = SPT_INTEGRATOR_PATH;
+            out->params.max_depth = pi->maxDepth;
+        } else if (const DirectLightingIntegrator *dl = dynamic_cast<const DirectLightingIntegrator *>(surf)) {
+            // directlighting.cpp:70-105: strategy "all" (the default) = UniformSampleAllLights at the camera hit; its
+            // SpecularReflect / SpecularTransmit recursion only does anything for specular BxDFs, which are not lowered under it
+            if (dl->strategy != SAMPLE_ALL_UNIFORM) return fail("directlighting with strategy \"one\" is not supported");
+            for (size_t i = 0; i < out->materials.size(); ++i)
+                if (out->materials[i].type == SPT_MAT_MIRROR || out->materials[i].type == SPT_MAT_GLASS)
+                    return fail("directlighting integrator with specular materials is not supported");
+            out->params.integrator = SPT_INTEGRATOR_DIRECT_ALL;
+            out->params.max_depth = dl->maxDepth;
+        } else return fail("surface integrator is neither the path nor the directlighting integrator");
         out->params.x_start = ld->xPixelStart; out->params.x_end = ld->xPixelEnd;
         out->params.y_start = ld->yPixelStart; out->params.y_end = ld->yPixelEnd;
         out->params.seed = 0;

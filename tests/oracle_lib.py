@@ -62,13 +62,20 @@ def trace_counts(scene, rays):
     return nodes.value, prims.value
 
 
-def shade_samples(scene, samples37, rng, max_depth=None, spp=None):
+def sample_floats(scene, integrator=None):
+    integ = scene.params.integrator if integrator is None else integrator
+    return int(lib().orc_sample_floats(C.byref(scene.desc), C.c_int32(integ)))
+
+
+def shade_samples(scene, samples37, rng, max_depth=None, spp=None, integrator=None):
     s = np.ascontiguousarray(samples37, np.float32)
+    integ = scene.params.integrator if integrator is None else integrator
+    assert s.shape[1] == sample_floats(scene, integ), "sample vectors do not have the integrator's layout"
     g = np.ascontiguousarray(rng, np.float32)
     n = len(s)
     out = np.empty((n, D.NBANDS), np.float32)
     md = scene.params.max_depth if max_depth is None else max_depth
-    lib().orc_shade_samples(C.byref(scene.desc), C.byref(scene.camera), C.c_int32(md),
+    lib().orc_shade_samples(C.byref(scene.desc), C.byref(scene.camera), C.c_int32(integ), C.c_int32(md),
                             C.c_int32(scene.params.spp if spp is None else spp), _p(s), _p(g),
                             C.c_int32(g.shape[1]), C.c_uint64(n), _p(out))
     return out
