@@ -1622,8 +1622,45 @@ void orc_gen_sample(uint64_t seed64, int32_t px, int32_t py, int32_t s, int32_t 
         rng[k] = (mix32(rkey + (uint32_t)k * 0x27d4eb2fU) & 0xffffff) / (float)(1 << 24);
 }
 
+/* The product's directlighting sample generator restated (csrc/sampler.cuh: direct_dims): fills the
+ * 7 + 6 N floats of sample `s` of sampler pixel (px,py) in the reference's layout. */
+static void gen_sample_direct(const SptSceneDesc *sc, uint64_t seed64, int32_t px, int32_t py, int32_t s, int32_t spp,
+                              float so, float sc_, float *o) {
+    uint32_t seed = (uint32_t)(seed64 ^ (seed64 >> 32));
+    uint32_t pkey = pixel_key(seed, ((uint32_t)py << 16) ^ (uint32_t)px);
+    float t2[2];
+    ld2(pkey, 0, s, spp, t2);
+    o[0] = px + t2[0]; o[1] = py + t2[1];
+    ld2(pkey, 1, s, spp, t2);
+    o[2] = t2[0]; o[3] = t2[1];
+    o[4] = lerpf(ld1(pkey, 2, s, spp), so, sc_);
+    int N = 0;
+    for (uint32_t i = 0; i < sc->n_lights; ++i) N += sc->lights[i].n_samples;
+    float *oneD = o + 5, *twoD = o + 7 + 2 * N;
+    o[5 + 2 * N] = o[6 + 2 * N] = 0.f;
+    for (uint32_t li = 0; li < sc->n_lights; ++li) {
+        int n = sc->lights[li].n_samples;
+        for (int jj = 0; jj < n; ++jj)
+            for (int k = 0; k < 4; ++k) {
+                uint32_t h = dim_key(pkey, 64u + 4u * li + (uint32_t)k);
+                uint32_t idx = permute_pow2((uint32_t)s, (uint32_t)spp, h) * (uint32_t)n +
+                               permute_pow2((uint32_t)jj, (uint32_t)n, mix32(h ^ ((uint32_t)s * 0x9e3779b9U + 0x7f4a7c15U)));
+                float a = van_der_corput(idx, mix32(h ^ 0x68bc21ebU));
+                if (k == 0) oneD[jj] = a;
+                else if (k == 1) oneD[n + jj] = a;
+                else {
+                    float b = sobol2(idx, mix32(h ^ 0x02e5be93U));
+                    if (k == 2) { twoD[2 * jj] = a; twoD[2 * jj + 1] = b; } else { twoD[2 * n + 2 * jj] = a; twoD[2 * n + 2 * jj + 1] = b; }
+                }
+            }
+        oneD += 2 * n; twoD += 4 * n;
+    }
+}
+
 void orc_render(const SptSceneDesc *sc, const SptCameraDesc *cam, const SptFilmDesc *fd, const SptRenderParams *rp,
                 float *c, float *weight) {
+    const int direct = rp->integrator == SPT_INTEGRATOR_DIRECT_ALL;
+    const int stride = orc_sample_floats(sc, rp->integrator);
     int nrng = 11 * (rp->max_depth > 2 ? rp->max_depth - 2 : 0) + 1;
     int x1 = rp->x_end, y1 = rp->y_end;
     if (rp->skip_border) {
@@ -1635,19 +1672,24 @@ void orc_render(const SptSceneDesc *sc, const SptCameraDesc *cam, const SptFilmD
     int tilesX = (x1 - rp->x_start + ts - 1) / ts;
 #pragma omp parallel for schedule(dynamic, 1)
     for (int py = rp->y_start; py < y1; ++py) {
-        float *smp = (float *)malloc(sizeof(float) * 37 * rp->spp);
+        float *smp = (float *)malloc(sizeof(float) * stride * rp->spp);
         float *rng = (float *)malloc(sizeof(float) * nrng * rp->spp);
         float *L = (float *)malloc(sizeof(float) * NB * rp->spp);
         for (int px = rp->x_start; px < x1; ++px) {
             int tile = ((py - rp->y_start) / ts) * tilesX + (px - rp->x_start) / ts;
             if (tile % nranks != rp->tile_rank) continue;
             for (int s = 0; s < rp->spp; ++s) {
-                orc_gen_sample(rp->seed, px, py, s, rp->spp, cam->shutter_open, cam->shutter_close, nrng,
-                               smp + 37 * s, rng + nrng * s);
-                li_sample(sc, cam, rp->max_depth, rp->spp, smp + 37 * s, rng + nrng * s, nrng, L + NB * s);
+                if (direct) {
+                    gen_sample_direct(sc, rp->seed, px, py, s, rp->spp, cam->shutter_open, cam->shutter_close, smp + stride * s);
+                    li_sample_direct(sc, cam, rp->spp, smp + stride * s, L + NB * s);
+                } else {
+                    orc_gen_sample(rp->seed, px, py, s, rp->spp, cam->shutter_open, cam->shutter_close, nrng,
+                                   smp + 37 * s, rng + nrng * s);
+                    li_sample(sc, cam, rp->max_depth, rp->spp, smp + 37 * s, rng + nrng * s, nrng, L + NB * s);
+                }
             }
 #pragma omp critical
-            for (int s = 0; s < rp->spp; ++s) film_add(fd, &sc->tables, smp[37 * s], smp[37 * s + 1], L + NB * s, c, weight);
+            for (int s = 0; s < rp->spp; ++s) film_add(fd, &sc->tables, smp[stride * s], smp[stride * s + 1], L + NB * s, c, weight);
         }
         free(smp); free(rng); free(L);
     }

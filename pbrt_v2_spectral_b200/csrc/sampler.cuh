@@ -102,3 +102,34 @@ __device__ inline void bounce_dims(const SampleSource &src, uint64_t idx, uint32
     u[7] = v[j]; u[8] = v[j + 1]; u[9] = v[j + 2];
     *rr = v[j + 3];
 }
+
+// directlighting (strategy all): the six values light sample jj of light li consumes - {-, lightPos0, lightPos1, lightComp,
+// bsdfDir0, bsdfDir1, bsdfComp} in u[1..6] (src/core/integrator.cpp:51-62). prefix = samples of the lights before li,
+// n = this light's sample count (a power of two: Sampler::RoundSize), N = the sum over all lights.
+// Caller-supplied vectors: the layout DirectLightingIntegrator::RequestSamples leaves (include/spt.h). Generated: the
+// reference draws each array as ONE scrambled (0,2)-sequence of spp*n points, deals n consecutive points to every pixel
+// sample and shuffles both the groups and the points within a group (LDShuffleScrambled1D/2D, montecarlo.h:289-315);
+// here the group of pixel sample s and the place of jj within it are hashed permutations, as for the per-bounce values.
+__device__ inline void direct_dims(const SampleSource &src, uint64_t cs, uint32_t pkey, uint32_t s, int li, int prefix, int n, int jj,
+                                   int N, float u[10]) {
+    if (src.smp) {
+        const float *base = src.smp + (size_t)src.stride * cs;
+        const float *oneD = base + 5 + 2 * prefix, *twoD = base + 7 + 2 * N + 4 * prefix;
+        u[3] = oneD[jj]; u[6] = oneD[n + jj];
+        u[1] = twoD[2 * jj]; u[2] = twoD[2 * jj + 1];
+        u[4] = twoD[2 * n + 2 * jj]; u[5] = twoD[2 * n + 2 * jj + 1];
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        uint32_t h = dim_key(pkey, 64u + 4u * (uint32_t)li + (uint32_t)k);
+        uint32_t idx = permute_pow2(s, src.spp, h) * (uint32_t)n + permute_pow2((uint32_t)jj, (uint32_t)n, mix32(h ^ (s * 0x9e3779b9U + 0x7f4a7c15U)));
+        float a = van_der_corput(idx, mix32(h ^ 0x68bc21ebU));
+        if (k == 0) u[3] = a;
+        else if (k == 1) u[6] = a;
+        else {
+            float b = sobol2(idx, mix32(h ^ 0x02e5be93U));
+            if (k == 2) { u[1] = a; u[2] = b; } else { u[4] = a; u[5] = b; }
+        }
+    }
+}

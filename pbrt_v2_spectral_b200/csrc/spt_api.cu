@@ -96,6 +96,8 @@ struct SptScene {
     int max_lanes = 4;               // spt_scene_set_lanes: 1 = every wave on one stream (per-kernel timing is then exact)
     cudaEvent_t evjoin[SPT_MAX_LANES] = {};
     bool has_env = false;            // an infinite light is present (escaped camera rays pick up Le)
+    int direct_slots = 1;            // sum of the lights' n_samples: slots per camera sample under directlighting
+    bool direct_pow2 = true;         // every light's n_samples is a power of two (the generated sampler needs it)
     unsigned long long *counters = nullptr;
     // Wave state, allocated on first use (the blocks come back from the block cache frame after frame).
     // Two LANES = two streams, each with its own wave buffers: spt_render deals the waves of a frame to
@@ -284,6 +286,16 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
     UP(v.light_cdf, cdf.data(), cdf.size());
     v.n_lights = d->n_lights;
     for (uint32_t li = 0; li < d->n_lights; ++li) if (d->lights[li].type == SPT_LIGHT_INFINITE) s->has_env = true;
+    {
+        int N = 0;
+        for (uint32_t li = 0; li < d->n_lights; ++li) {
+            int ns = d->lights[li].n_samples;
+            if (ns < 1) { g_err = "light n_samples must be >= 1"; delete s; return nullptr; }
+            if (ns & (ns - 1)) s->direct_pow2 = false;
+            N += ns;
+        }
+        s->direct_slots = N > 0 ? N : 1;
+    }
     UP(v.tables, &d->tables, 1);
     v.env_w = d->env_w; v.env_h = d->env_h;
     size_t ew = (size_t)d->env_w, eh = (size_t)d->env_h;
@@ -425,7 +437,7 @@ static void run_wave(SptScene *s, const RenderCfg &cfg, const SampleSource &src,
         s->mark(SPT_K_TRACE_PATH, li);
         spt_launch_compact_hits(gridC, st, q, row + 0, wb.hit_slot, wb.hitQ, row + 3, mq, row + 7, (b == 0 && !s->has_env) ? wb.L : nullptr);
         s->mark(SPT_K_SHADE, li);
-        if (mq) { spt_launch_miss_env(gridT, st, sc, wb, b, mq, row + 7); s->mark(SPT_K_SHADE, li); }
+        if (mq) { spt_launch_miss_env(gridT, st, sc, wb, b, mq, row + 7, cfg.sub); s->mark(SPT_K_SHADE, li); }
         spt_launch_shade(gridT, st, sc, cfg, src, wb, b, wb.hitQ, row + 3, row + 1, row + 2, row + 8, row + 9);
         s->mark(SPT_K_SHADE, li);
         if (sc.n_lights > 0) {
@@ -596,30 +608,38 @@ int spt_trace_any_dev(SptScene *s, const float *rays_dev, uint64_t n, uint8_t *o
     return trace_resident(s, true, rays_dev, n, nullptr, nullptr, out_hit_dev);
 }
 
-int spt_shade_samples(SptScene *s, const SptCameraDesc *cam, int32_t max_depth, int32_t spp, const float *samples, const float *rng,
-                      int32_t n_rng, uint64_t n, float *out_L) {
+int spt_shade_samples(SptScene *s, const SptCameraDesc *cam, int32_t integrator, int32_t max_depth, int32_t spp, const float *samples,
+                      const float *rng, int32_t n_rng, uint64_t n, float *out_L) {
     if (!s || !cam || !samples || !out_L) return fail(SPT_ERR_ARG, "null argument");
     if (spp <= 0) return fail(SPT_ERR_ARG, "spp must be positive");
+    if (integrator != SPT_INTEGRATOR_PATH && integrator != SPT_INTEGRATOR_DIRECT_ALL) return fail(SPT_ERR_ARG, "unknown integrator");
+    const bool direct = integrator == SPT_INTEGRATOR_DIRECT_ALL;
+    if (direct && s->dev.has_specular) return fail(SPT_ERR_UNSUPP, "directlighting with specular materials is not supported");
+    if (direct && s->dev.n_lights == 0) return fail(SPT_ERR_UNSUPP, "directlighting needs at least one light");
     if (n == 0) return SPT_OK;
-    if (n > (1u << 26)) return fail(SPT_ERR_ARG, "too many samples for one call");
-    int rc = ensure_wave(s, 1, (uint32_t)n, max_depth, 1);
+    const int sub = direct ? s->direct_slots : 1;
+    const int stride = direct ? 7 + 6 * s->direct_slots : 37;
+    if (direct) max_depth = 0;
+    if (n * (uint64_t)sub > (1u << 26)) return fail(SPT_ERR_ARG, "too many samples for one call");
+    int rc = ensure_wave(s, 1, (uint32_t)(n * sub), max_depth, 1);
     if (rc != SPT_OK) return rc;
     DevMem m;
-    float *dsmp = m.upload(samples, n * 37);
+    float *dsmp = m.upload(samples, n * (size_t)stride);
     float *drng = (rng && n_rng > 0) ? m.upload(rng, n * (size_t)n_rng) : nullptr;
     float *dout = m.alloc<float>(n * NB);
     if (!dsmp || !dout || (rng && n_rng > 0 && !drng)) { m.release(); return fail(SPT_ERR_CUDA, "device allocation failed"); }
     RenderCfg cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.cam = *cam; cfg.spp = 1; cfg.spp_shift = 0; cfg.max_depth = max_depth; cfg.n_samples = (uint32_t)n;
+    cfg.cam = *cam; cfg.spp = 1; cfg.spp_shift = 0; cfg.max_depth = max_depth; cfg.n_samples = (uint32_t)(n * sub);
+    cfg.integrator = integrator; cfg.sub = sub;
     cfg.tile = 1; cfg.tile_shift = 0; cfg.tilesX = 1; cfg.tilesY = 1; cfg.nranks = 1;
     cfg.diff_scale = 1.f / sqrtf((float)spp);
-    SampleSource src; src.smp = dsmp; src.rng = drng; src.n_rng = drng ? n_rng : 0; src.seed = 0; src.spp = 1;
+    SampleSource src; src.smp = dsmp; src.stride = stride; src.rng = drng; src.n_rng = drng ? n_rng : 0; src.seed = 0; src.spp = 1;
     size_t nc = (size_t)(max_depth + 2) * SPT_ROW;
     cudaMemsetAsync(s->counts, 0, nc * 4, s->stream);
     reset_class_stats(s);
     run_wave(s, cfg, src, s->counts);
-    spt_launch_gather_L(s->stream, s->lane[0].wb.L, s->lane[0].wb.cap, (uint32_t)n, dout);
+    spt_launch_gather_L(s->stream, s->lane[0].wb.L, s->lane[0].wb.cap, (uint32_t)n, sub, dout);
     std::vector<uint32_t> hc(nc);
     cudaMemcpyAsync(hc.data(), s->counts, nc * 4, cudaMemcpyDeviceToHost, s->stream);
     cudaError_t e = cudaMemcpyAsync(out_L, dout, n * NB * sizeof(float), cudaMemcpyDeviceToHost, s->stream);
@@ -729,7 +749,7 @@ int spt_film_add_samples(SptFilm *f, const SptSpectralTables *tables, const floa
     spt_launch_scatter_L(0, dl, (uint32_t)n, (uint32_t)n, soa);
     FilmView fv; fv.d = f->desc; fv.pix = f->pix; fv.table = f->table;
     unsigned gw = (unsigned)std::min<uint64_t>((n * 32 + 255) / 256, (uint64_t)num_sms() * 16);
-    spt_launch_film_add((int)gw, 0, fv, dt, dxy, soa, (uint32_t)n, (uint32_t)n, 1);
+    spt_launch_film_add((int)gw, 0, fv, dt, dxy, soa, (uint32_t)n, (uint32_t)n, 1, 1);
     cudaError_t e = cudaDeviceSynchronize();
     m.release();
     if (e != cudaSuccess) return fail(SPT_ERR_CUDA, cudaGetErrorString(e));
@@ -743,9 +763,16 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
     if (rp->max_depth < 0 || rp->max_depth > 64) return fail(SPT_ERR_ARG, "max_depth out of range");
     int nranks = rp->tile_nranks > 0 ? rp->tile_nranks : 1;
     if (rp->tile_rank < 0 || rp->tile_rank >= nranks) return fail(SPT_ERR_ARG, "tile_rank out of range");
+    if (rp->integrator != SPT_INTEGRATOR_PATH && rp->integrator != SPT_INTEGRATOR_DIRECT_ALL) return fail(SPT_ERR_ARG, "unknown integrator");
+    const bool direct = rp->integrator == SPT_INTEGRATOR_DIRECT_ALL;
+    if (direct && s->dev.has_specular) return fail(SPT_ERR_UNSUPP, "directlighting with specular materials is not supported");
+    if (direct && s->dev.n_lights == 0) return fail(SPT_ERR_UNSUPP, "directlighting needs at least one light");
+    if (direct && !s->direct_pow2) return fail(SPT_ERR_ARG, "directlighting: every light's n_samples must be a power of two (Sampler::RoundSize)");
+    const int sub = direct ? s->direct_slots : 1;                 // slots per camera sample
     RenderCfg cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.cam = *cam; cfg.spp = rp->spp; cfg.max_depth = rp->max_depth;
+    cfg.cam = *cam; cfg.spp = rp->spp; cfg.max_depth = direct ? 0 : rp->max_depth;
+    cfg.integrator = rp->integrator; cfg.sub = sub;
     cfg.diff_scale = 1.f / sqrtf((float)rp->spp);
     for (cfg.spp_shift = 0; (1 << cfg.spp_shift) < cfg.spp; ++cfg.spp_shift) {}
     cfg.x0 = rp->x_start; cfg.y0 = rp->y_start; cfg.x1 = rp->x_end; cfg.y1 = rp->y_end;
@@ -768,10 +795,12 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
     // Waves: by default the rank's pixels are cut into a multiple of max_lanes waves, each at most
     // 2^25 / max_lanes paths (17 GB of state over all lanes), dealt to the lanes in turn; small jobs
     // (< 2^19 paths per wave) use fewer lanes, down to one wave on one lane.
-    const uint64_t local_samples = local_pixels * (uint64_t)rp->spp;
+    const uint64_t slots_pp = (uint64_t)rp->spp * (uint64_t)sub;       // path slots per pixel
+    const int depth = cfg.max_depth;
+    const uint64_t local_samples = local_pixels * slots_pp;
     int want_lanes = s->max_lanes;
     while (want_lanes > 1 && local_samples < ((uint64_t)want_lanes << 19)) --want_lanes;
-    const uint64_t lane_cap_pixels = std::max<uint64_t>(1, ((1u << 25) / (uint64_t)want_lanes) / (uint64_t)rp->spp);
+    const uint64_t lane_cap_pixels = std::max<uint64_t>(1, ((1u << 25) / (uint64_t)want_lanes) / slots_pp);
     uint64_t wave_pixels;
     if (rp->wave_pixels > 0) wave_pixels = (uint64_t)rp->wave_pixels;
     else {
@@ -780,15 +809,15 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
         wave_pixels = (local_pixels + nw - 1) / nw;
     }
     wave_pixels = std::min<uint64_t>(wave_pixels, std::max<uint64_t>(local_pixels, 1));
-    if (wave_pixels * rp->spp > (1ull << 27)) wave_pixels = (1ull << 27) / rp->spp;
+    if (wave_pixels * slots_pp > (1ull << 27)) wave_pixels = std::max<uint64_t>(1, (1ull << 27) / slots_pp);
     size_t n_waves = (size_t)((local_pixels + wave_pixels - 1) / wave_pixels);
     const int n_lanes = (int)std::min<size_t>((size_t)s->max_lanes, std::max<size_t>(n_waves, 1));
-    int rc = ensure_wave(s, n_lanes, (uint32_t)(wave_pixels * rp->spp), rp->max_depth, std::max<size_t>(n_waves, 1));
+    int rc = ensure_wave(s, n_lanes, (uint32_t)(wave_pixels * slots_pp), depth, std::max<size_t>(n_waves, 1));
     if (rc != SPT_OK) return rc;
-    size_t per_wave = (size_t)(rp->max_depth + 2) * SPT_ROW;
+    size_t per_wave = (size_t)(depth + 2) * SPT_ROW;
     cudaStream_t st = s->stream;
     CU(cudaMemsetAsync(s->counts, 0, std::max<size_t>(n_waves, 1) * per_wave * 4, st));
-    SampleSource src; src.smp = nullptr; src.rng = nullptr; src.n_rng = 0; src.seed = cfg.seed; src.spp = (uint32_t)rp->spp;
+    SampleSource src; src.smp = nullptr; src.stride = 0; src.rng = nullptr; src.n_rng = 0; src.seed = cfg.seed; src.spp = (uint32_t)rp->spp;
     FilmView fv; fv.d = film->desc; fv.pix = film->pix; fv.table = film->table;
     reset_class_stats(s);
     CU(cudaEventRecord(s->ev0, st));
@@ -798,11 +827,11 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
         const int li = (int)(w % (size_t)n_lanes);
         cfg.pixel_base = (uint64_t)w * wave_pixels;
         uint64_t np = std::min<uint64_t>(wave_pixels, local_pixels - cfg.pixel_base);
-        cfg.n_samples = (uint32_t)(np * rp->spp);
+        cfg.n_samples = (uint32_t)(np * slots_pp);
         run_wave(s, cfg, src, s->counts + w * per_wave, li);
         unsigned gw = (unsigned)std::min<uint64_t>((np * 32 + 255) / 256, (uint64_t)num_sms() * 16);
         const WaveBuffers &wb = s->lane[li].wb;
-        spt_launch_film_add((int)gw, s->lane[li].stream, fv, s->dev.tables, wb.img_xy, wb.L, wb.cap, cfg.n_samples, rp->spp);
+        spt_launch_film_add((int)gw, s->lane[li].stream, fv, s->dev.tables, wb.img_xy, wb.L, wb.cap, (uint32_t)(np * rp->spp), rp->spp, sub);
         s->mark(SPT_K_FILM, li);
     }
     for (int k = 1; k < n_lanes; ++k) {                                              // join
@@ -831,8 +860,8 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
     samples = valid_pixels * (uint64_t)rp->spp;
     s->stats.class_rays[SPT_K_GEN] = samples; s->stats.class_rays[SPT_K_FILM] = samples;
     s->stats.camera_samples += samples;
-    add_ray_stats(s, hc, rp->max_depth, n_waves);
-    const uint64_t overhang = slots > samples ? slots - samples : 0;
+    add_ray_stats(s, hc, depth, n_waves);
+    const uint64_t overhang = slots > samples * (uint64_t)sub ? slots - samples * (uint64_t)sub : 0;
     s->stats.closest_rays -= overhang;
     s->stats.class_rays[SPT_K_TRACE_PATH] -= overhang;
     return SPT_OK;

@@ -80,11 +80,15 @@ __global__ void __launch_bounds__(256) k_compact_hits(const uint32_t *__restrict
 // Camera rays that escape: SamplerRenderer::Li's miss branch (samplerrenderer.cpp:239-243), the sum of
 // Light::Le over all lights - only the infinite light is non-zero. Later bounces: the same sum times the
 // throughput, but only for a ray that left a specular bounce (path.cpp:106-108).
-__global__ void __launch_bounds__(128) k_miss_env(DevScene sc, WaveBuffers wb, int bounce, const uint32_t *queue, const uint32_t *count) {
+__global__ void __launch_bounds__(128) k_miss_env(DevScene sc, WaveBuffers wb, int bounce, const uint32_t *queue, const uint32_t *count, int sub) {
     uint32_t n = *count;
     for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
         uint32_t i = queue[q];
         if (bounce > 0 && !(wb.pflags[i] & 1u)) continue;
+        if (sub > 1 && (i % (uint32_t)sub)) {                       // directlighting: the first of a camera sample's slots carries Le
+            for (int c = 0; c < NB; ++c) wb.L[band_off(i, c)] = 0.f;
+            continue;
+        }
         float4 d4 = wb.ray_d[i];
         float Le[NB];
         for (int c = 0; c < NB; ++c) Le[c] = 0.f;
@@ -139,7 +143,12 @@ __global__ void __launch_bounds__(128, 4) k_shade(DevScene sc, RenderCfg cfg, Sa
                 // emitted light at the first vertex (path.cpp:55-56; Intersection::Le, intersection.cpp:53-56):
                 // K6 starts L from the emitter's spectrum instead of from black
                 int emitter = -1;
-                if (bounce == 0 || (SPEC && (wb.pflags[i] & 1u))) {
+                // directlighting (EXT kernels only): slot i is light sample `dj` of camera sample `cs`; the emitted light of
+                // the hit (directlighting.cpp:80) is carried by the first slot alone
+                const bool direct = EXT && cfg.integrator == SPT_INTEGRATOR_DIRECT_ALL;
+                uint32_t cs = i, dj = 0;
+                if (direct && cfg.sub > 1) { cs = i / (uint32_t)cfg.sub; dj = i - cs * (uint32_t)cfg.sub; }
+                if ((bounce == 0 && dj == 0) || (SPEC && (wb.pflags[i] & 1u))) {
                     int li = sc.prim_light[slot];
                     if (li >= 0 && dot(hit.nn, vneg(ray.d)) > 0.f) emitter = li;
                 }
@@ -153,15 +162,24 @@ __global__ void __launch_bounds__(128, 4) k_shade(DevScene sc, RenderCfg cfg, Sa
                 v3 p = hit.p, n_s = bsdf.nn, woW = vneg(ray.d);
                 v3 wo = w2l(bsdf, woW);
                 float eps = hit.rayEpsilon;
-                uint32_t s_idx = src.smp ? 0u : (i & ((uint32_t)cfg.spp - 1u));
+                uint32_t s_idx = src.smp ? 0u : (cs & ((uint32_t)cfg.spp - 1u));
                 uint32_t pk = 0;
                 if (!src.smp) {
                     int px, py;
-                    wave_pixel(cfg, cfg.pixel_base + (i >> cfg.spp_shift), &px, &py);
+                    wave_pixel(cfg, cfg.pixel_base + (cs >> cfg.spp_shift), &px, &py);
                     pk = pixel_key(src.seed, pix_key(px, py));
                 }
                 float u[10], rr;
-                bounce_dims(src, i, pk, s_idx, bounce, sc.n_lights > 0, u, &rr);
+                int directLight = 0;
+                if (direct) {
+                    int prefix = 0, jj = (int)dj;
+                    for (; directLight + 1 < (int)sc.n_lights && jj >= sc.lights[directLight].n_samples; ++directLight) {
+                        jj -= sc.lights[directLight].n_samples; prefix += sc.lights[directLight].n_samples;
+                    }
+                    for (int k = 0; k < 10; ++k) u[k] = 0.f;
+                    rr = 0.f;
+                    direct_dims(src, cs, pk, s_idx, directLight, prefix, sc.lights[directLight].n_samples, jj, cfg.sub, u);
+                } else bounce_dims(src, i, pk, s_idx, bounce, sc.n_lights > 0, u, &rr);
 
                 float4 g1 = make_float4(0, 0, 0, 0), g2 = g1, g3 = g1, laux = g1;
                 const int mtype = bsdf.mtype;
@@ -183,6 +201,7 @@ __global__ void __launch_bounds__(128, 4) k_shade(DevScene sc, RenderCfg cfg, Sa
                     int nLights = (int)sc.n_lights;
                     lightIdx = (int)floorf(u[0] * nLights);
                     if (nLights - 1 < lightIdx) lightIdx = nLights - 1;
+                    if (direct) lightIdx = directLight;               // UniformSampleAllLights: every light, n_samples times each
                     light_sample(sc, lightIdx, p, u[1], u[2], u[3], &lr, true);
                 }
                 v3 wl1 = V(0, 0, 1), wl2 = wl1, wiW1 = wl1, wiW2 = wl1;
@@ -191,6 +210,7 @@ __global__ void __launch_bounds__(128, 4) k_shade(DevScene sc, RenderCfg cfg, Sa
                 float specR = 0.f, specT = 0.f, specPdf = 0.f;
                 for (int d = 1; d <= 2; ++d) {
                     if (d == 1 && (!haveLights || lr.delta)) continue;
+                    if (d == 2 && direct) continue;                  // no continuation under directlighting
                     if (specMat) {                                      // only d == 2 gets here
                         v3 wl;
                         have2 = specular_sample(bsdf, wo, u[9], &wl, &specR, &specT, &specPdf);
@@ -394,7 +414,10 @@ __global__ void __launch_bounds__(32 * ACC_WARPS, 8) k_accumulate(DevScene sc, R
             }
             const bool haveP = (flags & RF_P) != 0;
             specBounce = (flags & RF_P_SPEC) != 0;
-            sL *= nL; sB *= nL;
+            // UniformSampleOneLight scales by the light count (integrator.cpp:105); UniformSampleAllLights averages a light's
+            // n_samples estimates (integrator.cpp:68)
+            const float lscale = (EXT && cfg.integrator == SPT_INTEGRATOR_DIRECT_ALL) ? 1.f / (float)sc.lights[lightIdx].n_samples : nL;
+            sL *= lscale; sB *= lscale;
             stage[lane][0] = make_float4(cL.x, cL.y, cB.x, cB.y);
             stage[lane][1] = make_float4(cP.x, cP.y, sL, sB);
             stage[lane][2] = make_float4(haveP ? c2.x : 0.f, c2.y, __uint_as_float(i),
@@ -541,8 +564,10 @@ __global__ void __launch_bounds__(32 * ACC_WARPS, 8) k_accumulate(DevScene sc, R
 // exchanging over lane bits 4, 3, 2 each group of four lanes owns one sample, bits 1, 0 finish it).
 #define FILM_GROUP 8
 __device__ __forceinline__ int film_y_lane(int k) { return ((k & 1) << 4) | ((k & 2) << 2) | (k & 4); }   // a lane that ends up holding y of sample k
+// sub > 1 (directlighting): a camera sample's radiance is the sum of `sub` consecutive rows (its light samples), formed
+// before the guards as the reference guards the integrator's total.
 __global__ void __launch_bounds__(256) k_film_add(FilmView film, const SptSpectralTables *tables, const float2 *img_xy,
-                                                  const float *L, uint32_t cap, uint32_t n_samples, int spp) {
+                                                  const float *L, uint32_t cap, uint32_t n_samples, int spp, int sub) {
     const SptSpectralTables &tb = *tables;
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -556,19 +581,23 @@ __global__ void __launch_bounds__(256) k_film_add(FilmView film, const SptSpectr
         const uint32_t first = pixel * (uint32_t)spp;
         const uint32_t ns = min((uint32_t)spp, n_samples - first);
         // the pixel this warp accumulates for: the one the first sample of the group falls in
-        float2 xy0 = img_xy[first];
+        float2 xy0 = img_xy[(size_t)first * sub];
         const int mainx = (int)floorf(xy0.x), mainy = (int)floorf(xy0.y);
         const bool mainInside = mainx >= xs && mainx <= xe && mainy >= ys && mainy <= ye;
         float acc = 0.f, wsum = 0.f;
         for (uint32_t s0 = 0; s0 < ns; s0 += FILM_GROUP) {
             float Lv[FILM_GROUP];
 #pragma unroll
-            for (int k = 0; k < FILM_GROUP; ++k) Lv[k] = L[band_off(first + min(s0 + k, ns - 1), lane)];
+            for (int k = 0; k < FILM_GROUP; ++k) {
+                const uint32_t row = (first + min(s0 + k, ns - 1)) * (uint32_t)sub;
+                Lv[k] = L[band_off(row, lane)];
+                for (int q = 1; q < sub; ++q) Lv[k] += L[band_off(row + q, lane)];
+            }
             // ---- footprint of sample s0 + lane (lanes 0-7): 0 nothing to add, 1 exactly the warp's pixel, 2 anything else
             int kind = 0;
             float wt = 0.f;
             if (lane < FILM_GROUP && s0 + lane < ns) {
-                const float2 xy = img_xy[first + s0 + lane];
+                const float2 xy = img_xy[(size_t)(first + s0 + lane) * sub];
                 if (xy.x > -1e29f) {                                    // else: sample outside this rank's tile set
                     const float dimageX = xy.x - 0.5f, dimageY = xy.y - 0.5f;
                     int x0 = (int)ceilf(dimageX - fd.filter_xwidth), x1 = (int)floorf(dimageX + fd.filter_xwidth);
@@ -624,7 +653,7 @@ __global__ void __launch_bounds__(256) k_film_add(FilmView film, const SptSpectr
                 const float w = __shfl_sync(FULL, wt, k);
                 if ((fastMask >> k) & 1u) { acc += w * v; wsum += w; }
                 else if ((slowMask >> k) & 1u) {
-                    const float2 xy = img_xy[first + s0 + k];
+                    const float2 xy = img_xy[(size_t)(first + s0 + k) * sub];
                     const float dimageX = xy.x - 0.5f, dimageY = xy.y - 0.5f;
                     int x0 = (int)ceilf(dimageX - fd.filter_xwidth), x1 = (int)floorf(dimageX + fd.filter_xwidth);
                     int y0 = (int)ceilf(dimageY - fd.filter_ywidth), y1 = (int)floorf(dimageY + fd.filter_ywidth);
@@ -663,10 +692,12 @@ __global__ void k_film_split(const float *pix, size_t npix, float *c, float *w) 
     }
 }
 // SoA [NB][cap] -> AoS [n][NB] (spt_shade_samples output)
-__global__ void k_gather_L(const float *L, uint32_t cap, uint32_t n, float *out) {
+__global__ void k_gather_L(const float *L, uint32_t cap, uint32_t n, int sub, float *out) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n * NB; i += gridDim.x * blockDim.x) {
         uint32_t s = i / NB, c = i % NB;
-        out[i] = L[band_off(s, c)];
+        float v = L[band_off(s * (uint32_t)sub, c)];
+        for (int q = 1; q < sub; ++q) v += L[band_off(s * (uint32_t)sub + q, c)];
+        out[i] = v;
     }
 }
 // AoS [n][NB] -> SoA, for spt_film_add_samples
@@ -683,31 +714,31 @@ void spt_launch_compact_hits(int grid, cudaStream_t st, const uint32_t *queue, c
                              uint32_t *hit_queue, uint32_t *hit_count, uint32_t *miss_queue, uint32_t *miss_count, float *black_L) {
     k_compact_hits<<<grid, 256, 0, st>>>(queue, count, hit_slot, hit_queue, hit_count, miss_queue, miss_count, black_L);
 }
-void spt_launch_miss_env(int grid, cudaStream_t st, const DevScene &sc, const WaveBuffers &wb, int bounce, const uint32_t *queue, const uint32_t *count) {
-    k_miss_env<<<grid, 128, 0, st>>>(sc, wb, bounce, queue, count);
+void spt_launch_miss_env(int grid, cudaStream_t st, const DevScene &sc, const WaveBuffers &wb, int bounce, const uint32_t *queue, const uint32_t *count, int sub) {
+    k_miss_env<<<grid, 128, 0, st>>>(sc, wb, bounce, queue, count, sub);
 }
 void spt_launch_shade(int grid, cudaStream_t st, const DevScene &sc, const RenderCfg &cfg, const SampleSource &src, const WaveBuffers &wb,
                       int bounce, const uint32_t *queue, const uint32_t *count, uint32_t *shadow_count, uint32_t *mis_count,
                       uint32_t *elided_count, uint32_t *mis_any_count) {
 #define SPT_SHADE(S, E) k_shade<S, E><<<grid, 128, 0, st>>>(sc, cfg, src, wb, bounce, queue, count, shadow_count, mis_count, elided_count, mis_any_count)
-    if (sc.has_ext) { if (sc.has_specular) SPT_SHADE(true, true); else SPT_SHADE(false, true); }
+    if (sc.has_ext || cfg.integrator != SPT_INTEGRATOR_PATH) { if (sc.has_specular) SPT_SHADE(true, true); else SPT_SHADE(false, true); }
     else { if (sc.has_specular) SPT_SHADE(true, false); else SPT_SHADE(false, false); }
 #undef SPT_SHADE
 }
 void spt_launch_accumulate(int grid, cudaStream_t st, const DevScene &sc, const RenderCfg &cfg, const WaveBuffers &wb, int bounce,
                            const uint32_t *queue, const uint32_t *count, uint32_t *next_queue, uint32_t *next_count) {
-    if (sc.has_ext) k_accumulate<true><<<grid, 128, 0, st>>>(sc, cfg, wb, bounce, queue, count, next_queue, next_count);
+    if (sc.has_ext || cfg.integrator != SPT_INTEGRATOR_PATH) k_accumulate<true><<<grid, 128, 0, st>>>(sc, cfg, wb, bounce, queue, count, next_queue, next_count);
     else k_accumulate<false><<<grid, 128, 0, st>>>(sc, cfg, wb, bounce, queue, count, next_queue, next_count);
 }
 void spt_launch_film_add(int grid, cudaStream_t st, const FilmView &film, const SptSpectralTables *tables, const float2 *img_xy,
-                         const float *L, uint32_t cap, uint32_t n_samples, int spp) {
-    k_film_add<<<grid, 256, 0, st>>>(film, tables, img_xy, L, cap, n_samples, spp);
+                         const float *L, uint32_t cap, uint32_t n_samples, int spp, int sub) {
+    k_film_add<<<grid, 256, 0, st>>>(film, tables, img_xy, L, cap, n_samples, spp, sub);
 }
 void spt_launch_film_split(int grid, cudaStream_t st, const float *pix, size_t npix, float *c, float *w) {
     k_film_split<<<grid, 256, 0, st>>>(pix, npix, c, w);
 }
-void spt_launch_gather_L(cudaStream_t st, const float *L, uint32_t cap, uint32_t n, float *out) {
-    k_gather_L<<<grid1d((uint64_t)n * NB, 256, 65535), 256, 0, st>>>(L, cap, n, out);
+void spt_launch_gather_L(cudaStream_t st, const float *L, uint32_t cap, uint32_t n, int sub, float *out) {
+    k_gather_L<<<grid1d((uint64_t)n * NB, 256, 65535), 256, 0, st>>>(L, cap, n, sub, out);
 }
 void spt_launch_scatter_L(cudaStream_t st, const float *in, uint32_t cap, uint32_t n, float *L) {
     k_scatter_L<<<grid1d((uint64_t)n * NB, 256, 65535), 256, 0, st>>>(in, cap, n, L);

@@ -57,6 +57,9 @@ struct RenderCfg {
     uint32_t seed;
     uint64_t pixel_base;              // first rank-local pixel of this wave
     uint32_t n_samples;               // samples in this wave
+    int integrator;                   // SPT_INTEGRATOR_*
+    int sub;                          // slots per camera sample: 1, or under directlighting the sum of the lights' n_samples -
+                                      // slot i = light sample (i % sub) of camera sample (i / sub), each with its own copy of the camera ray
     float diff_scale;                 // 1/sqrt(samplesPerPixel): RayDifferential::ScaleDifferentials (samplerrenderer.cpp:91)
 };
 

@@ -111,7 +111,8 @@ def test_film_wide_filter():
     assert np.allclose(c, oc, rtol=2e-5, atol=1e-6)
 
 
-RENDER_CASES = [c for c in CASES if c[0] in ("tiny", "metal_shipped_small", "ssenv_shipped_small")]
+RENDER_CASES = [c for c in CASES if c[0] in ("tiny", "metal_shipped_small", "ssenv_shipped_small", "killeroo_direct_small",
+                                             "bunny_direct_small")]
 
 
 @pytest.mark.parametrize("rcase", RENDER_CASES, ids=[c[0] for c in RENDER_CASES])

@@ -19,7 +19,9 @@ pytestmark = pytest.mark.gpu
 IMAGES = [("killeroo_small", 1024), ("bunny_small", 4096), ("metal_small", 512), ("envmap_small", 8192), ("synth_small", 2048),
           ("ssenv_small", 4096), ("specular_small", 2048),
           # configs 3 and 4 with their shipped floor: substrate + image-mapped Kd (EWA) + bump map
-          ("metal_shipped_small", 8192), ("ssenv_shipped_small", 8192)]
+          ("metal_shipped_small", 8192), ("ssenv_shipped_small", 8192),
+          # the shipped scenes under their own integrator: directlighting, strategy all
+          ("killeroo_direct_small", 1024), ("bunny_direct_small", 1024)]
 
 
 @pytest.mark.parametrize("name,spp", IMAGES, ids=[n for n, _ in IMAGES])
