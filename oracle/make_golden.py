@@ -254,6 +254,30 @@ CONFIGS = {
 }
 
 
+# full-size workload -> the small golden scene it shares every table with (same scene file, other resolution / spp)
+DELTA_BASE = {"killeroo_path": "killeroo_small", "bunny_path": "bunny_small", "metal_path": "metal_shipped_small",
+              "ssenv_path": "ssenv_shipped_small", "killeroo_direct": "killeroo_direct_small"}
+
+
+def write_delta(path, name):
+    """Replace a full-size lowered scene by {base_scene, camera, film, params, film_filename} when every other array is
+    byte-identical to its small golden variant (checked): keeps the snapshot shipped to the GPU box small."""
+    base = DELTA_BASE.get(name)
+    base_path = os.path.join(GOLDEN, (base or "") + ".spt")
+    if not base or not os.path.exists(base_path):
+        return
+    sys.path.insert(0, REPO)
+    import numpy as np
+    from pbrt_v2_spectral_b200.scene_io import load_container, save_container
+    a, b = load_container(path), load_container(base_path)
+    own = ("camera", "film", "params", "film_filename")
+    if set(a) != set(b) or any(not np.array_equal(a[k], b[k]) for k in a if k not in own):
+        return
+    delta = {"base_scene": np.frombuffer(os.path.relpath(base_path, os.path.dirname(path)).encode(), np.uint8)}
+    delta.update({k: a[k] for k in own if k in a})
+    save_container(path, delta)
+
+
 def with_gpupath(s):
     return s.replace("WorldBegin", 'Renderer "gpupath"\nWorldBegin', 1)
 
@@ -264,6 +288,7 @@ def main():
     ap.add_argument("--only", default="", help="comma-separated config names")
     args = ap.parse_args()
     names = [n for n in CONFIGS if not args.only or n in args.only.split(",")]
+    names.sort(key=lambda n: n in DELTA_BASE)          # small golden variants first: the full-size workloads refer to them
     # the synthetic scenes are written from scratch and lowered by the BUILT reference (oracle/_ref/bin/oracle_dump,
     # which travels with the repo): they can be generated where the reference source tree is absent (the GPU box)
     need_ref = any(not n.startswith("synth") for n in names)
@@ -295,7 +320,9 @@ def main():
             # full-size workloads: only the lowered scene is kept, where bench.py looks for it
             os.remove(prefix + ".golden")
             os.makedirs(LOWERED, exist_ok=True)
-            shutil.move(prefix + ".spt", os.path.join(LOWERED, name + ".spt"))
+            dst = os.path.join(LOWERED, name + ".spt")
+            shutil.move(prefix + ".spt", dst)
+            write_delta(dst, name)
         print("%-16s lowered + golden in %.1fs" % (name, time.time() - t0), flush=True)
         if name.startswith("synth"):                 # tens of MB of text per scene: regenerable, not shipped
             for f in (name + ".pbrt", name + ".gpu.pbrt"):

@@ -525,6 +525,13 @@ struct Lowerer {
             }
         }
         out->bvh_nodes.assign((const uint8_t *)nodes, (const uint8_t *)nodes + (size_t)nNodes * 32);
+        // the reference never writes LinearBVHNode::pad, nor a leaf's axis (bvh.cpp:105-115,364-369): zero them so that
+        // lowering a scene twice gives the same bytes
+        for (uint32_t n = 0; n < nNodes; ++n) {
+            uint8_t *nd = &out->bvh_nodes[(size_t)n * 32];
+            nd[30] = nd[31] = 0;
+            if (nd[28]) nd[29] = 0;
+        }
 
         if (!AddLights(scene, sampler)) return false;
 

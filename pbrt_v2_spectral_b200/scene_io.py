@@ -81,7 +81,17 @@ class LoweredScene:
 
     @classmethod
     def load(cls, path):
-        return cls(load_container(path))
+        """A container file, or a DELTA file: {"base_scene": file name next to / relative to this one, camera, film,
+        params, film_filename} - the full-size bench workloads share every scene table with their small golden
+        variant and differ in resolution and sample count only (oracle/make_golden.py writes them)."""
+        import os
+        a = load_container(path)
+        if "base_scene" in a:
+            base = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(path)), a["base_scene"].tobytes().decode()))
+            full = load_container(base)
+            full.update({k: v for k, v in a.items() if k != "base_scene"})
+            a = full
+        return cls(a)
 
     def _ptr(self, key):
         arr = self.a[key]
