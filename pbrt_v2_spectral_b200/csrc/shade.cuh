@@ -216,9 +216,17 @@ template <int C> __device__ inline void tex_evaluate(const DevScene &sc, const S
             float d = lod - ilod;
             float a[C], b[C];
             tex_ewa<C>(sc, t, ilod, s, tt, ds0, dt0, ds1, dt1, a);
-            tex_ewa<C>(sc, t, ilod + 1, s, tt, ds0, dt0, ds1, dt1, b);
+            // d == 0 (the usual case at high sample counts: footprints below a texel clamp lod to 0): a*1 + b*0 = a
+            // exactly - b is finite, the filter ellipse has semi-axes >= 1 texel (covariance J J^T + I) and so always
+            // covers a texel centre - and the second level need not be filtered
+            if (d == 0.f) {
 #pragma unroll
-            for (int k = 0; k < C; ++k) out[k] = a[k] * (1.f - d) + b[k] * d;
+                for (int k = 0; k < C; ++k) out[k] = a[k];
+            } else {
+                tex_ewa<C>(sc, t, ilod + 1, s, tt, ds0, dt0, ds1, dt1, b);
+#pragma unroll
+                for (int k = 0; k < C; ++k) out[k] = a[k] * (1.f - d) + b[k] * d;
+            }
         }
     }
     if (C == 1) out[0] = out[0] * t.scale;
