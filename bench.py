@@ -35,7 +35,7 @@ REF_BIN = os.path.join(ROOT, "oracle", "_ref", "bin", "pbrt")
 REF_SCENES = os.path.join(ROOT, "oracle", "_ref", "scenes")
 CPU_SAMPLE_SPP = 16          # bounded sample of the workload for the CPU arm: same frame, 16 of the 64 spp
 # workloads that have a scene file the reference binary can run for the CPU leg: (xres, yres, spp, bounded-sample spp)
-CPU_WORKLOADS = {"killeroo_path": (700, 700, 64, CPU_SAMPLE_SPP), "killeroo_direct": (700, 700, 64, CPU_SAMPLE_SPP), "metal_path": (400, 400, 512, 16), "ssenv_path": (1920, 1080, 1024, 1)}
+CPU_WORKLOADS = {"killeroo_path": (700, 700, 64, CPU_SAMPLE_SPP), "killeroo_direct": (700, 700, 64, CPU_SAMPLE_SPP), "metal_path": (400, 400, 512, 16), "ssenv_path": (1920, 1080, 1024, 8)}
 
 
 def read_peaks():

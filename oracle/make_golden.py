@@ -278,6 +278,36 @@ def write_delta(path, name):
     save_container(path, delta)
 
 
+# Scenes whose per-sample radiance is heavy-tailed (Blinn exponent 1000 under an HDR environment map): two independent
+# 8192-spp estimates of the image differ by more than the 1 % the converged-image test asks for. For these the CPU oracle
+# (bit-identical to the reference per sample) renders the same frame with the PRODUCT's sampler and seed: the GPU image
+# must reproduce that image, and its distance to the reference render must be the oracle's (tests/test_image_parity.py).
+HEAVY_TAILED = {"metal_shipped_small"}
+IMAGE_SEED = 2024
+
+
+def noise_floor(name, spp):
+    sys.path.insert(0, REPO); sys.path.insert(0, os.path.join(REPO, "tests"))
+    import json
+    import numpy as np
+    import oracle_lib as O
+    from pbrt_v2_spectral_b200 import capi, ctypes_defs as D
+    sc, _ = O.load_case(os.path.join(GOLDEN, name + ".spt"), os.path.join(GOLDEN, name + ".golden"))
+    ref = capi.read_dat(os.path.join(GOLDEN, "%s_%dspp.dat" % (name, spp))) / spp
+    rp = D.SptRenderParams.from_buffer_copy(bytes(sc.params)); rp.spp = spp; rp.seed = IMAGE_SEED
+    t0 = time.time()
+    c, _w = O.render(sc, rp)
+    img = c.astype(np.float64) / spp
+    np.save(os.path.join(GOLDEN, "%s_%dspp.oracle.npy" % (name, spp)), img.astype(np.float32))
+    l1 = np.abs(img - ref).sum((0, 1)) / ref.sum((0, 1))
+    bias = np.abs(img.mean((0, 1)) - ref.mean((0, 1))) / ref.mean((0, 1))
+    with open(os.path.join(GOLDEN, "%s_%dspp.noise.json" % (name, spp)), "w") as f:
+        json.dump({"l1_max": float(l1.max()), "bias_max": float(bias.max()), "seed": IMAGE_SEED, "spp": spp,
+                   "how": "oracle/make_golden.py --images: orc_render (CPU oracle, product sampler) vs the reference .dat"}, f)
+    print("%-16s oracle render %d spp in %.1fs: L1 %.3f%%, bias %.3f%% against the reference render" % (
+        name, spp, time.time() - t0, 100 * l1.max(), 100 * bias.max()), flush=True)
+
+
 def with_gpupath(s):
     return s.replace("WorldBegin", 'Renderer "gpupath"\nWorldBegin', 1)
 
@@ -341,6 +371,8 @@ def main():
                     if os.path.exists(os.path.join(SCENES, f)):
                         os.remove(os.path.join(SCENES, f))
             write(os.path.join(GOLDEN, iname + ".txt"), "ncores=%d seconds=%.1f\n" % (ncores, time.time() - t0))
+            if name in HEAVY_TAILED:
+                noise_floor(name, img_spp)
             print("%-16s reference image %d spp in %.1fs" % (name, img_spp, time.time() - t0), flush=True)
 
 

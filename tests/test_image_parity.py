@@ -40,7 +40,7 @@ def test_converged_image_within_1_percent_per_band(name, spp):
         # map's finite-difference step follows them (material.cpp:48-60): the reference's image itself depends on spp
         gpu_spp = spp
     rp.spp = gpu_spp
-    rp.seed = 2024
+    rp.seed = 2024                          # = oracle/make_golden.py IMAGE_SEED
     film = capi.Film(lowered.film)
     scene.render(film, rp)
     c, w = film.download()
@@ -52,5 +52,21 @@ def test_converged_image_within_1_percent_per_band(name, spp):
     l1 = np.abs(img - ref).sum((0, 1)) / ref.sum((0, 1))
     bias = np.abs(img.mean((0, 1)) - ref.mean((0, 1))) / ref.mean((0, 1))
     print("%s: per-band aggregate L1 error max %.3f%%, band-mean bias max %.3f%%" % (name, 100 * l1.max(), 100 * bias.max()))
-    assert l1.max() <= 0.01, l1
-    assert bias.max() <= 0.003, bias
+    l1_allowed, bias_allowed = 0.01, 0.003
+    noise = os.path.join(O.GOLDEN_BIG, "%s_%dspp.noise.json" % (name, spp))
+    if os.path.exists(noise):
+        # heavy-tailed scene (oracle/make_golden.py HEAVY_TAILED): two independent estimates at this sample count differ by
+        # more than 1 % - measured with the CPU oracle, which is bit-identical to the reference per sample, rendering this
+        # frame with the product's sampler and seed. The GPU image must reproduce the oracle's image, and be as close to the
+        # reference render as the oracle's is.
+        import json
+        nz = json.load(open(noise))
+        assert nz["seed"] == rp.seed and nz["spp"] == gpu_spp
+        oimg = np.load(os.path.join(O.GOLDEN_BIG, "%s_%dspp.oracle.npy" % (name, spp))).astype(np.float64)
+        l1o = np.abs(img - oimg).sum((0, 1)) / oimg.sum((0, 1))
+        print("%s: against the oracle's render of the same samples: L1 max %.3f%% (oracle vs reference: L1 %.3f%%, bias %.3f%%)" % (
+            name, 100 * l1o.max(), 100 * nz["l1_max"], 100 * nz["bias_max"]))
+        assert l1o.max() <= 0.003, l1o
+        l1_allowed, bias_allowed = max(l1_allowed, 1.05 * nz["l1_max"]), max(bias_allowed, 1.05 * nz["bias_max"])
+    assert l1.max() <= l1_allowed, l1
+    assert bias.max() <= bias_allowed, bias
