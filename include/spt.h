@@ -80,15 +80,30 @@ typedef struct SptXform { float m[16]; float minv[16]; } SptXform;
  * displacement every reference material carries.
  */
 enum { SPT_MAT_MATTE = 0, SPT_MAT_PLASTIC = 1, SPT_MAT_METAL = 2, SPT_MAT_MIRROR = 3, SPT_MAT_GLASS = 4,
-       SPT_MAT_SUBSTRATE = 5 };
+       SPT_MAT_SUBSTRATE = 5,
+       SPT_MAT_MEASURED = 6    /* IrregIsotropicBRDF over the table brdfs[brdf] (src/materials/measured.cpp:77-120,185-205,
+                                  src/core/reflection.cpp:239-263); spectra unused */
+};
 typedef struct SptMaterial {
     int32_t type;
     float p0, p1, p2;
     float spec0[SPT_NBANDS];
     float spec1[SPT_NBANDS];
     int32_t tex_kd, tex_bump;
-    int32_t pad_[2];
+    int32_t brdf;                   /* MEASURED: row of brdfs[]; -1 otherwise */
+    int32_t pad_;
 } SptMaterial;
+
+/* Measured isotropic BRDF (theta-phi .brdf file): the kd-tree the reference built over the samples' BRDFRemap
+ * coordinates (src/core/kdtree.h:91-140), node for node, so that a radius search visits and sums the samples in the
+ * reference's order. Node k's sample spectrum is brdf_spectra[(node_first + k) * SPT_NBANDS ...]. */
+typedef struct SptKdNode {
+    float split_pos;
+    uint32_t bits;                  /* splitAxis (3 = leaf) | hasLeftChild << 2 | rightChild << 3; the left child is node k+1 */
+    float p[3];                     /* IrregIsotropicBRDFSample::p */
+    float pad_[3];
+} SptKdNode;
+typedef struct SptBrdfTable { uint32_t node_first, n_nodes; } SptBrdfTable;
 
 /* Image texture = ImageTexture<RGBSpectrum,Spectrum> / ImageTexture<float,float> over a UVMapping2D
  * (src/textures/imagemap.h:60-100, src/core/texture.cpp:80-90) with the MIPMap pyramid the reference built
@@ -187,6 +202,10 @@ typedef struct SptSceneDesc {
     uint32_t n_textures;   const SptTexture *textures;
     uint64_t n_texels;     const float *tex_texels;
     const float *ewa_weight_lut;    /* MIPMap::weightLut[128] as the reference computed it (mipmap.h:205-213), or NULL */
+    /* measured BRDFs */
+    uint32_t n_brdfs;      const SptBrdfTable *brdfs;
+    uint32_t n_brdf_nodes; const SptKdNode *brdf_nodes;
+    const float *brdf_spectra;      /* n_brdf_nodes x SPT_NBANDS */
 } SptSceneDesc;
 
 /* PerspectiveCamera (src/cameras/perspective.cpp:33-106, src/core/camera.cpp:84-103). */

@@ -70,14 +70,30 @@ def killeroo(w, h, spp, name, maxdepth=5):
     return set_filename(set_spp(set_res(s, w, h), spp), name)
 
 
-def bunny(w, h, spp, name, maxdepth=5):
+def bunny(w, h, spp, name, maxdepth=5, measured=False):
     s = read(os.path.join(REF, "scenes/bunny.pbrt"))
     s = s.replace('Film "image"', 'Film "image" "integer xresolution" [%d] "integer yresolution" [%d]\n'
                   'Sampler "lowdiscrepancy" "integer pixelsamples" [%d]\n'
                   'SurfaceIntegrator "path" "integer maxdepth" [%d]' % (w, h, spp, maxdepth), 1)
-    # the shipped bunny material is a measured BRDF ("next"); plastic stands in
-    s = s.replace('Material "measured" "string filename" "brdfs/mystique.brdf"',
-                  'Material "plastic" "color Kd" [.3 .25 .4] "color Ks" [.4 .4 .4] "float roughness" [.08]')
+    assert 'Material "measured" "string filename" "brdfs/mystique.brdf"' in s
+    if not measured:
+        # the first golden sets were made before the measured BRDF was lowered: plastic stands in
+        s = s.replace('Material "measured" "string filename" "brdfs/mystique.brdf"',
+                      'Material "plastic" "color Kd" [.3 .25 .4] "color Ks" [.4 .4 .4] "float roughness" [.08]')
+    return set_filename(s, name)
+
+
+def bunny_measured(w, h, spp, name, maxdepth=5):
+    """BASELINE config 2 with the bunny's shipped material: the measured BRDF brdfs/mystique.brdf (IrregIsotropicBRDF)."""
+    return bunny(w, h, spp, name, maxdepth, measured=True)
+
+
+def bunny_shipped(w, h, spp, name, maxdepth=5):
+    """bunny.pbrt AS SHIPPED: default directlighting integrator, measured BRDF; only resolution and spp are set."""
+    s = read(os.path.join(REF, "scenes/bunny.pbrt"))
+    s = s.replace('Film "image"', 'Film "image" "integer xresolution" [%d] "integer yresolution" [%d]\n'
+                  'Sampler "lowdiscrepancy" "integer pixelsamples" [%d]' % (w, h, spp), 1)
+    assert 'Material "measured"' in s
     return set_filename(s, name)
 
 
@@ -247,6 +263,9 @@ CONFIGS = {
     "killeroo_direct_small": (killeroo_direct, 176, 176, 4, 6000, 8, 1024),
     "bunny_direct_small":    (bunny_direct, 320, 240, 4, 6000, 8, 1024),
     "killeroo_direct":       (killeroo_direct, 700, 700, 64, 0, 0, 0),
+    # the bunny with its shipped measured BRDF: under the path integrator (config 2) and as shipped (directlighting)
+    "bunny_measured_small":  (bunny_measured, 320, 240, 4, 6000, 40, 4096),
+    "bunny_shipped_small":   (bunny_shipped, 320, 240, 4, 6000, 8, 1024),
     # config 5 recipe at 1 M triangles (BVH + pair nodes + vertices = 176 MB, larger than L2): optional bench workload
     "synth_1m":        (lambda w, h, spp, name, maxdepth=5: synth(w, h, spp, name, maxdepth, ntris=1000000, chunks=10), 1024, 576, 16, 0, 0, 0),
     # small committed fixture

@@ -466,7 +466,9 @@ enum { BX_LAMBERT = 0, BX_ORENNAYAR = 1, BX_MICROFACET_DIEL = 2, BX_MICROFACET_C
        /* specular: reflection.cpp:130-160 */
        BX_SPEC_REFL_NOOP = 4, BX_SPEC_REFL_DIEL = 5, BX_SPEC_TRANS = 6,
        /* FresnelBlend over an Anisotropic distribution (substrate): reflection.cpp:217-236,369-459 */
-       BX_FRESNEL_BLEND = 7 };
+       BX_FRESNEL_BLEND = 7,
+       /* IrregIsotropicBRDF (measured material): reflection.cpp:239-263 */
+       BX_MEASURED = 8 };
 #define BX_IS_SPECULAR(k) ((k) >= BX_SPEC_REFL_NOOP && (k) <= BX_SPEC_TRANS)
 typedef struct {
     v3 nn, sn, tn, ng;
@@ -479,6 +481,8 @@ typedef struct {
     float ior;                  /* glass / subsurface: FresnelDielectric(1, ior) */
     float ex, ey;               /* Anisotropic */
     float Rtex[NB];             /* Kd evaluated from an image texture at this hit (R[0] points here) */
+    const SptSceneDesc *sc;     /* measured BRDF: the tables */
+    int brdf;
 } BSDF;
 
 static v3 w2l(const BSDF *b, v3 v) { return V(dot(v, b->sn), dot(v, b->tn), dot(v, b->nn)); }
@@ -773,7 +777,10 @@ static void make_bsdf(const SptSceneDesc *sc, uint32_t slot, const Hit *dg, cons
         from_rgb_refl(&sc->tables, rgb, b->Rtex);
         kd = b->Rtex;
     }
-    if (m->type == SPT_MAT_SUBSTRATE) {                        /* materials/substrate.cpp:34-56, reflection.h:433-437 */
+    b->sc = sc; b->brdf = -1;
+    if (m->type == SPT_MAT_MEASURED) {                         /* materials/measured.cpp:185-205 */
+        b->nBxDFs = 1; b->kind[0] = BX_MEASURED; b->R[0] = NULL; b->brdf = m->brdf;
+    } else if (m->type == SPT_MAT_SUBSTRATE) {                 /* materials/substrate.cpp:34-56, reflection.h:433-437 */
         b->nBxDFs = 1;
         b->kind[0] = BX_FRESNEL_BLEND; b->R[0] = kd; b->R[1] = m->spec1;
         b->ex = 1.f / m->p0; b->ey = 1.f / m->p1;
@@ -833,6 +840,59 @@ static float fr_cond(float cosi, float eta, float k) {
     return (Rparl2 + Rperp2) / 2.f;
 }
 
+/* KdTree::privateLookup (core/kdtree.h:143-168) with IrregIsoProc (reflection.cpp:34-47): children first, then the node */
+typedef struct { float v[NB]; float sumWeights; int nFound; } IrregIsoProc;
+static void kd_lookup(const SptKdNode *nodes, const float *spectra, uint32_t nNodes, uint32_t nodeNum, const float p[3],
+                      IrregIsoProc *proc, float maxDistSquared) {
+    const SptKdNode *node = nodes + nodeNum;
+    int axis = (int)(node->bits & 3u);
+    int hasLeft = (int)((node->bits >> 2) & 1u);
+    uint32_t rightChild = node->bits >> 3;
+    if (axis != 3) {
+        float dist2 = (p[axis] - node->split_pos) * (p[axis] - node->split_pos);
+        if (p[axis] <= node->split_pos) {
+            if (hasLeft) kd_lookup(nodes, spectra, nNodes, nodeNum + 1, p, proc, maxDistSquared);
+            if (dist2 < maxDistSquared && rightChild < nNodes) kd_lookup(nodes, spectra, nNodes, rightChild, p, proc, maxDistSquared);
+        } else {
+            if (rightChild < nNodes) kd_lookup(nodes, spectra, nNodes, rightChild, p, proc, maxDistSquared);
+            if (dist2 < maxDistSquared && hasLeft) kd_lookup(nodes, spectra, nNodes, nodeNum + 1, p, proc, maxDistSquared);
+        }
+    }
+    float dx = node->p[0] - p[0], dy = node->p[1] - p[1], dz = node->p[2] - p[2];
+    float d2 = dx * dx + dy * dy + dz * dz;                   /* DistanceSquared -> Vector::LengthSquared, geometry.h */
+    if (d2 < maxDistSquared) {
+        float weight = expf(-100.f * d2);
+        const float *sv = spectra + (size_t)nodeNum * NB;
+        for (int c = 0; c < NB; ++c) proc->v[c] += sv[c] * weight;
+        proc->sumWeights += weight;
+        ++proc->nFound;
+    }
+}
+static float spherical_phi(v3 v);
+/* IrregIsotropicBRDF::f (reflection.cpp:251-263) over BRDFRemap (:239-248), added into out[NB] */
+static void measured_f(const SptSceneDesc *sc, const SptBrdfTable *t, v3 wo, v3 wi, float *out) {
+    float cosi = wi.z, coso = wo.z;
+    float sini = sqrtf(stdmaxf(0.f, 1.f - wi.z * wi.z)), sino = sqrtf(stdmaxf(0.f, 1.f - wo.z * wo.z));
+    float phii = spherical_phi(wi), phio = spherical_phi(wo);
+    float dphi = phii - phio;
+    if (dphi < 0.) dphi += 2.f * PI_F;
+    if (dphi > 2.f * PI_F) dphi -= 2.f * PI_F;
+    if (dphi > PI_F) dphi = 2.f * PI_F - dphi;
+    float m[3] = { sini * sino, dphi / PI_F, cosi * coso };
+    float lastMaxDist2 = .001f;
+    for (;;) {
+        IrregIsoProc proc;
+        for (int c = 0; c < NB; ++c) proc.v[c] = 0.f;
+        proc.sumWeights = 0.f; proc.nFound = 0;
+        kd_lookup(sc->brdf_nodes + t->node_first, sc->brdf_spectra + (size_t)t->node_first * NB, t->n_nodes, 0, m, &proc, lastMaxDist2);
+        if (proc.nFound > 2 || lastMaxDist2 > 1.5f) {
+            for (int c = 0; c < NB; ++c) out[c] += clampf(proc.v[c], 0.f, INFINITY) / proc.sumWeights;
+            return;
+        }
+        lastMaxDist2 *= 2.f;
+    }
+}
+
 /* f of one BxDF in local coordinates, added into out[NB] */
 static void bxdf_f(const BSDF *b, int i, v3 wo, v3 wi, float *out) {
     int kind = b->kind[i];
@@ -856,6 +916,7 @@ static void bxdf_f(const BSDF *b, int i, v3 wo, v3 wi, float *out) {
         for (int c = 0; c < NB; ++c) out[c] += b->R[i][c] * INV_PI_F * s;
         return;
     }
+    if (kind == BX_MEASURED) { measured_f(b->sc, b->sc->brdfs + b->brdf, wo, wi, out); return; }
     if (kind == BX_FRESNEL_BLEND) {                            /* reflection.cpp:224-236; Anisotropic::D reflection.h:438-444 */
         const float *Rd = b->R[0], *Rs = b->R[1];
         float k0 = (28.f / (23.f * PI_F));
@@ -925,7 +986,7 @@ static void aniso_first_quadrant(const BSDF *b, float u1, float u2, float *phi, 
 /* Blinn::Pdf reflection.cpp:356-366 / BxDF::Pdf :312-315 / Microfacet::Pdf :331-335 */
 static float bxdf_pdf(const BSDF *b, int i, v3 wo, v3 wi) {
     int kind = b->kind[i];
-    if (kind == BX_LAMBERT || kind == BX_ORENNAYAR)
+    if (kind == BX_LAMBERT || kind == BX_ORENNAYAR || kind == BX_MEASURED)
         return same_hemisphere(wo, wi) ? abs_cos_theta(wi) * INV_PI_F : 0.f;
     if (!same_hemisphere(wo, wi)) return 0.f;
     if (kind == BX_FRESNEL_BLEND)                              /* FresnelBlend::Pdf, reflection.cpp:453-456 */
@@ -1001,7 +1062,7 @@ static void bsdf_sample_f(const BSDF *b, v3 woW, v3 *wiW, float uComp, float u1,
         if (matching > 1) *pdf /= matching;
         return;
     }
-    if (kind == BX_LAMBERT || kind == BX_ORENNAYAR) {          /* BxDF::Sample_f, reflection.cpp:303-310 */
+    if (kind == BX_LAMBERT || kind == BX_ORENNAYAR || kind == BX_MEASURED) {   /* BxDF::Sample_f, reflection.cpp:303-310 */
         wi = cosine_sample_hemisphere(u1, u2);
         if (wo.z < 0.) wi.z *= -1.f;
         *pdf = bxdf_pdf(b, which, wo, wi);

@@ -32,6 +32,8 @@ class SptSceneDesc(C.Structure):
         ("n_textures", C.c_uint32), ("textures", C.c_void_p),
         ("n_texels", C.c_uint64), ("tex_texels", C.c_void_p),
         ("ewa_weight_lut", C.c_void_p),
+        ("n_brdfs", C.c_uint32), ("brdfs", C.c_void_p),
+        ("n_brdf_nodes", C.c_uint32), ("brdf_nodes", C.c_void_p), ("brdf_spectra", C.c_void_p),
     ]
 
 
@@ -83,5 +85,7 @@ SIZEOF_QUADRIC = 32
 SIZEOF_XFORM = 128
 SIZEOF_MATERIAL = 16 + 2 * 4 * NBANDS + 16
 SIZEOF_TEXTURE = 64
+SIZEOF_BRDF_TABLE = 8
+SIZEOF_KD_NODE = 32
 SIZEOF_LIGHT = 32 + 4 * NBANDS + 16
 SIZEOF_LIGHT_SHAPE = 16

@@ -49,6 +49,9 @@
 #include "materials/glass.h"
 #include "materials/subsurface.h"
 #include "materials/substrate.h"
+#include "materials/measured.h"
+#include "kdtree.h"
+#include "reflection.h"
 #include "textures/imagemap.h"
 #include "textures/scale.h"
 #include "lights/diffuse.h"
@@ -130,6 +133,11 @@ SptSceneDesc LoweredScene::Desc() const {
     d.n_texels = tex_texels.size();
     d.tex_texels = ptr_or_null(tex_texels);
     d.ewa_weight_lut = ptr_or_null(ewa_weight_lut);
+    d.n_brdfs = (uint32_t)brdfs.size();
+    d.brdfs = ptr_or_null(brdfs);
+    d.n_brdf_nodes = (uint32_t)brdf_nodes.size();
+    d.brdf_nodes = ptr_or_null(brdf_nodes);
+    d.brdf_spectra = ptr_or_null(brdf_spectra);
     return d;
 }
 
@@ -168,6 +176,9 @@ bool LoweredScene::Save(const std::string &path, std::string *err) const {
     w.pod("textures", textures);
     w.vec("tex_texels", 3, tex_texels);
     w.vec("ewa_weight_lut", 3, ewa_weight_lut);
+    w.pod("brdfs", brdfs);
+    w.pod("brdf_nodes", brdf_nodes);
+    w.vec("brdf_spectra", 3, brdf_spectra);
     w.put("camera", 0, &camera, sizeof(camera), 1, sizeof(camera));
     w.put("film", 0, &film, sizeof(film), 1, sizeof(film));
     w.put("params", 0, &params, sizeof(params), 1, sizeof(params));
@@ -199,6 +210,7 @@ struct Lowerer {
     std::map<const TriangleMesh *, std::pair<uint32_t, uint32_t> > meshBase;  // vertex base, tri base
     std::map<const Shape *, int> quadricIdx;
     std::map<const Light *, int> lightIdx;
+    std::map<const void *, int> brdfIdx;                                       // KdTree -> row of brdfs[]
     std::map<const void *, uint64_t> texelBase;                                // MIPMap -> first float in tex_texels
 
     bool fail(const std::string &why) { err = why; return false; }
@@ -381,8 +393,34 @@ struct Lowerer {
     bool AddMaterial(const Material *m, int32_t *idx) {
         SptMaterial row;
         memset(&row, 0, sizeof(row));
-        row.tex_kd = row.tex_bump = -1;
-        if (const MatteMaterial *mm = dynamic_cast<const MatteMaterial *>(m)) {
+        row.tex_kd = row.tex_bump = row.brdf = -1;
+        if (const MeasuredMaterial *ms = dynamic_cast<const MeasuredMaterial *>(m)) {
+            // measured.cpp:185-205: IrregIsotropicBRDF over the kd-tree of a theta-phi (.brdf) file
+            if (!BumpParam(ms->bumpMap, ms->normalMap, &row.tex_bump)) return false;
+            if (ms->regularHalfangleData || !ms->thetaPhiData) return fail("measured material: only theta-phi (.brdf) data is supported");
+            row.type = SPT_MAT_MEASURED;
+            const KdTree<IrregIsotropicBRDFSample> *kd = ms->thetaPhiData;
+            std::map<const void *, int>::iterator it = brdfIdx.find((const void *)kd);
+            if (it == brdfIdx.end()) {
+                SptBrdfTable t;
+                t.node_first = (uint32_t)out->brdf_nodes.size(); t.n_nodes = kd->nNodes;
+                for (uint32_t k = 0; k < kd->nNodes; ++k) {
+                    SptKdNode n;
+                    memset(&n, 0, sizeof(n));
+                    n.split_pos = kd->nodes[k].splitPos;
+                    n.bits = (uint32_t)kd->nodes[k].splitAxis | (uint32_t)kd->nodes[k].hasLeftChild << 2 | (uint32_t)kd->nodes[k].rightChild << 3;
+                    n.p[0] = kd->nodeData[k].p.x; n.p[1] = kd->nodeData[k].p.y; n.p[2] = kd->nodeData[k].p.z;
+                    out->brdf_nodes.push_back(n);
+                    float v[nSpectralSamples];
+                    CopySpectrum(kd->nodeData[k].v, v);
+                    out->brdf_spectra.insert(out->brdf_spectra.end(), v, v + nSpectralSamples);
+                }
+                out->brdfs.push_back(t);
+                brdfIdx[(const void *)kd] = (int)out->brdfs.size() - 1;
+                it = brdfIdx.find((const void *)kd);
+            }
+            row.brdf = it->second;
+        } else if (const MatteMaterial *mm = dynamic_cast<const MatteMaterial *>(m)) {
             float sig;
             if (!BumpParam(mm->bumpMap, mm->normalMap, &row.tex_bump) || !SpectrumParam(mm->Kd, row.spec0, &row.tex_kd, "Kd") ||
                 !ConstTex(mm->sigma, &sig, "sigma")) return false;

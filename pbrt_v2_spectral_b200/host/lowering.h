@@ -85,6 +85,9 @@ struct LoweredScene {
     std::vector<SptTexture> textures;
     std::vector<float> tex_texels;
     std::vector<float> ewa_weight_lut;
+    std::vector<SptBrdfTable> brdfs;
+    std::vector<SptKdNode> brdf_nodes;
+    std::vector<float> brdf_spectra;
 
     SptCameraDesc camera;
     SptFilmDesc film;

@@ -64,7 +64,8 @@ class LoweredScene:
     def __init__(self, arrays):
         self.a = {k: np.ascontiguousarray(v) for k, v in arrays.items()}
         a = self.a
-        for key, dt in (("textures", np.uint8), ("tex_texels", np.float32), ("ewa_weight_lut", np.float32)):
+        for key, dt in (("textures", np.uint8), ("tex_texels", np.float32), ("ewa_weight_lut", np.float32),
+                        ("brdfs", np.uint8), ("brdf_nodes", np.uint8), ("brdf_spectra", np.float32)):
             a.setdefault(key, np.zeros(0, dt))
         if int(a["nbands"][0]) != D.NBANDS:
             raise ValueError("scene has %d bands, library expects %d" % (int(a["nbands"][0]), D.NBANDS))
@@ -107,7 +108,7 @@ class LoweredScene:
         for k in ("prim_kind", "prim_flags", "prim_id", "prim_data", "prim_material", "prim_light", "prim_xform",
                   "tri_vidx", "P", "N", "UV", "quadrics", "xforms", "materials", "lights", "light_shapes",
                   "env_rgb", "env_func", "env_cdf", "env_func_int", "env_marg_func", "env_marg_cdf",
-                  "textures", "tex_texels", "ewa_weight_lut"):
+                  "textures", "tex_texels", "ewa_weight_lut", "brdfs", "brdf_nodes", "brdf_spectra"):
             setattr(d, k, self._ptr(k))
         d.n_tris = a["tri_vidx"].size // 3
         d.n_verts = a["P"].size // 3
@@ -121,6 +122,8 @@ class LoweredScene:
         d.env_marg_int = float(a["env_marg_int"][0])
         d.n_textures = a["textures"].size // D.SIZEOF_TEXTURE
         d.n_texels = a["tex_texels"].size
+        d.n_brdfs = a["brdfs"].size // D.SIZEOF_BRDF_TABLE
+        d.n_brdf_nodes = a["brdf_nodes"].size // D.SIZEOF_KD_NODE
         return d
 
     @property
