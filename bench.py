@@ -35,7 +35,8 @@ REF_BIN = os.path.join(ROOT, "oracle", "_ref", "bin", "pbrt")
 REF_SCENES = os.path.join(ROOT, "oracle", "_ref", "scenes")
 CPU_SAMPLE_SPP = 16          # bounded sample of the workload for the CPU arm: same frame, 16 of the 64 spp
 # workloads that have a scene file the reference binary can run for the CPU leg: (xres, yres, spp, bounded-sample spp)
-CPU_WORKLOADS = {"killeroo_path": (700, 700, 64, CPU_SAMPLE_SPP), "killeroo_direct": (700, 700, 64, CPU_SAMPLE_SPP), "metal_path": (400, 400, 512, 16), "ssenv_path": (1920, 1080, 1024, 8)}
+CPU_WORKLOADS = {"killeroo_path": (700, 700, 64, CPU_SAMPLE_SPP), "killeroo_direct": (700, 700, 64, CPU_SAMPLE_SPP),
+                 "bunny_shipped": (640, 480, 256, 8), "metal_path": (400, 400, 512, 16), "ssenv_path": (1920, 1080, 1024, 8)}
 
 
 def read_peaks():
@@ -193,6 +194,8 @@ def main():
     workload_desc = WORKLOAD_DESC if args.workload == WORKLOAD else {
         "killeroo_direct": "scenes/killeroo-simple.pbrt AS SHIPPED: directlighting integrator (strategy all, sphere light nsamples 8), "
                            "LD 64 spp, 700x700, box filter",
+        "bunny_shipped": "scenes/bunny.pbrt AS SHIPPED (BASELINE config 2's scene): directlighting integrator (point light + disk area light, "
+                         "nsamples 4), measured BRDF brdfs/mystique.brdf on the bunny, 640x480, LD 256 spp, box filter",
         "metal_path": "scenes/metal.pbrt (BASELINE config 3) with its shipped floor - substrate, lines.exr as EWA-filtered Kd and as bump map - "
                       "Au teapot (measured eta/k SPDs, Blinn exponent 1000), grace environment map for the absent uffizi map, path maxdepth 5, "
                       "400x400, LD 512 spp, box filter",

@@ -266,6 +266,7 @@ CONFIGS = {
     # the bunny with its shipped measured BRDF: under the path integrator (config 2) and as shipped (directlighting)
     "bunny_measured_small":  (bunny_measured, 320, 240, 4, 6000, 40, 4096),
     "bunny_shipped_small":   (bunny_shipped, 320, 240, 4, 6000, 8, 1024),
+    "bunny_shipped":         (bunny_shipped, 640, 480, 256, 0, 0, 0),
     # config 5 recipe at 1 M triangles (BVH + pair nodes + vertices = 176 MB, larger than L2): optional bench workload
     "synth_1m":        (lambda w, h, spp, name, maxdepth=5: synth(w, h, spp, name, maxdepth, ntris=1000000, chunks=10), 1024, 576, 16, 0, 0, 0),
     # small committed fixture
@@ -275,7 +276,8 @@ CONFIGS = {
 
 # full-size workload -> the small golden scene it shares every table with (same scene file, other resolution / spp)
 DELTA_BASE = {"killeroo_path": "killeroo_small", "bunny_path": "bunny_small", "metal_path": "metal_shipped_small",
-              "ssenv_path": "ssenv_shipped_small", "killeroo_direct": "killeroo_direct_small"}
+              "ssenv_path": "ssenv_shipped_small", "killeroo_direct": "killeroo_direct_small",
+              "bunny_shipped": "bunny_shipped_small"}
 
 
 def write_delta(path, name):
@@ -305,6 +307,16 @@ HEAVY_TAILED = {"metal_shipped_small"}
 IMAGE_SEED = 2024
 
 
+def dat_to_npy(dat, npy):
+    """The reference's .dat ([band][x][y] float64 sums, spectralImage.cpp:319-369) kept as [y][x][band] float32: half the
+    bytes in the snapshot shipped to the GPU box; the 2^-24 relative rounding is far below the images' Monte-Carlo noise."""
+    sys.path.insert(0, REPO)
+    import numpy as np
+    from pbrt_v2_spectral_b200 import capi
+    np.save(npy, capi.read_dat(dat).astype(np.float32))
+    os.remove(dat)
+
+
 def noise_floor(name, spp):
     sys.path.insert(0, REPO); sys.path.insert(0, os.path.join(REPO, "tests"))
     import json
@@ -312,7 +324,7 @@ def noise_floor(name, spp):
     import oracle_lib as O
     from pbrt_v2_spectral_b200 import capi, ctypes_defs as D
     sc, _ = O.load_case(os.path.join(GOLDEN, name + ".spt"), os.path.join(GOLDEN, name + ".golden"))
-    ref = capi.read_dat(os.path.join(GOLDEN, "%s_%dspp.dat" % (name, spp))) / spp
+    ref = np.load(os.path.join(GOLDEN, "%s_%dspp.ref.npy" % (name, spp))).astype(np.float64) / spp
     rp = D.SptRenderParams.from_buffer_copy(bytes(sc.params)); rp.spp = spp; rp.seed = IMAGE_SEED
     t0 = time.time()
     c, _w = O.render(sc, rp)
@@ -384,7 +396,7 @@ def main():
             ncores = os.cpu_count()
             subprocess.run([os.path.join(OUT, "bin/pbrt"), "--quiet", "--ncores", str(ncores), iname + ".pbrt"],
                            cwd=SCENES, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-            shutil.move(os.path.join(SCENES, iname + ".dat"), os.path.join(GOLDEN, iname + ".dat"))
+            dat_to_npy(os.path.join(SCENES, iname + ".dat"), os.path.join(GOLDEN, iname + ".ref.npy"))
             if name.startswith("synth"):
                 for f in (name + ".pbrt", iname + ".pbrt"):
                     if os.path.exists(os.path.join(SCENES, f)):

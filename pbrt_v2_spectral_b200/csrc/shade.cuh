@@ -20,6 +20,7 @@ struct Bsdf {
     float ior;            // GLASS: FresnelDielectric(1, ior)
     int compMask;         // MIRROR / GLASS: bit 0 the reflection component exists (Kr not black), bit 1 the transmission (Kt)
     float ex, ey;         // SUBSTRATE: Anisotropic exponents (reflection.h:433-437)
+    int brdf;             // MEASURED: row of DevScene::brdfs
     bool texKd;           // Kd came from an image texture: kd_rgb replaces the material row's spec0
     float kd_rgb[3];
 };
@@ -318,7 +319,7 @@ __device__ inline void make_bsdf(const DevScene &sc, uint32_t slot, const Hit &d
     b->tn = cross(b->nn, b->sn);
     b->mtype = m.type;
     b->orenNayar = false; b->exponent = 0.f; b->A = b->B = 0.f; b->ior = 1.f; b->compMask = 0;
-    b->ex = b->ey = 0.f; b->texKd = false;
+    b->ex = b->ey = 0.f; b->texKd = false; b->brdf = m.brdf;
     if (EXT && m.tex_kd >= 0) {                                      // Kd->Evaluate(dgs): imagemap.cpp:88-97
         tex_evaluate<3>(sc, sc.textures[m.tex_kd], dg.u, dg.v, df, b->kd_rgb);
         b->texKd = true;
@@ -399,6 +400,11 @@ __device__ inline void bsdf_terms(const Bsdf &b, v3 woW, v3 wiW, v3 wo, v3 wi, D
             else { sinalpha = sinthetai; tanbeta = sinthetao / abs_cos_theta(wo); }
             t->a0 = (b.A + b.B * maxcos * sinalpha * tanbeta);
         }
+        return;
+    }
+    if (EXT && b.mtype == SPT_MAT_MEASURED) {                        // BxDF::Pdf (reflection.cpp:312-315); f is a table look-up (measured_f)
+        *pdfAll = cosPdf;
+        if (t->reflect) { t->a0 = 1.f; t->mf = true; }
         return;
     }
     if (EXT && b.mtype == SPT_MAT_SUBSTRATE) {                       // FresnelBlend::f / ::Pdf, reflection.cpp:224-236,453-456
@@ -609,6 +615,71 @@ __device__ __forceinline__ float illum_band(const SptSpectralTables &t, const Il
     r *= .86445f;
     return clampf(r, 0.f, SPT_INF);
 }
+__device__ __forceinline__ float spherical_theta(v3 v) { return acosf(clampf(v.z, -1.f, 1.f)); }
+__device__ __forceinline__ float spherical_phi(v3 v) { float p = atan2f(v.y, v.x); return (p < 0.f) ? p + 2.f * PI_F : p; }
+// IrregIsotropicBRDF::f (reflection.cpp:251-263): radius search around BRDFRemap(wo, wi) (:239-248) in the reference's
+// kd-tree (kdtree.h:143-168: children first, then the node - the same order, so the same sums up to the rounding of expf),
+// the radius doubling until three samples are found; v = sum of weight * sample spectrum, clamped, over the sum of weights.
+__device__ inline void measured_f(const DevScene &sc, const SptBrdfTable &t, v3 wo, v3 wi, float *v) {
+    const float cosi = wi.z, coso = wo.z;
+    const float sini = sin_theta(wi), sino = sin_theta(wo);
+    const float phii = spherical_phi(wi), phio = spherical_phi(wo);
+    float dphi = phii - phio;
+    if (dphi < 0.f) dphi += 2.f * PI_F;
+    if (dphi > 2.f * PI_F) dphi -= 2.f * PI_F;
+    if (dphi > PI_F) dphi = 2.f * PI_F - dphi;
+    const v3 m = V(sini * sino, dphi / PI_F, cosi * coso);
+    const SptKdNode *nodes = sc.brdf_nodes + t.node_first;
+    const float *spectra = sc.brdf_spectra + (size_t)t.node_first * NB;
+    const uint32_t NONE = 0xffffffffu;
+    float maxD2 = .001f;
+    for (;;) {
+        for (int c = 0; c < NB; ++c) v[c] = 0.f;
+        float sumW = 0.f;
+        int nFound = 0;
+        uint32_t stack[32];                                          // node << 2 | stage: 0 enter, 1 first child done, 2 both done
+        int sp = 0;
+        stack[sp++] = 0u;
+        while (sp) {
+            const uint32_t e = stack[--sp], n = e >> 2, stage = e & 3u;
+            const SptKdNode nd = nodes[n];
+            const int axis = (int)(nd.bits & 3u);
+            if (axis != 3 && stage < 2u) {
+                const bool hasLeft = (nd.bits >> 2) & 1u;
+                const uint32_t right = nd.bits >> 3;
+                const float pa = vcomp(m, axis);
+                const float dist2 = (pa - nd.split_pos) * (pa - nd.split_pos);
+                const bool leftFirst = pa <= nd.split_pos;
+                const uint32_t L = hasLeft ? n + 1 : NONE, R = right < t.n_nodes ? right : NONE;
+                if (stage == 0u) {
+                    stack[sp++] = n << 2 | 1u;
+                    const uint32_t first = leftFirst ? L : R;
+                    if (first != NONE) stack[sp++] = first << 2;
+                } else {
+                    stack[sp++] = n << 2 | 2u;
+                    const uint32_t second = leftFirst ? R : L;
+                    if (dist2 < maxD2 && second != NONE) stack[sp++] = second << 2;
+                }
+                continue;
+            }
+            const float dx = nd.p[0] - m.x, dy = nd.p[1] - m.y, dz = nd.p[2] - m.z;
+            const float d2 = dx * dx + dy * dy + dz * dz;
+            if (d2 < maxD2) {
+                const float weight = expf(-100.f * d2);
+                const float *sv = spectra + (size_t)n * NB;
+                for (int c = 0; c < NB; ++c) v[c] += __ldg(sv + c) * weight;
+                sumW += weight;
+                ++nFound;
+            }
+        }
+        if (nFound > 2 || maxD2 > 1.5f) {
+            for (int c = 0; c < NB; ++c) v[c] = clampf(v[c], 0.f, SPT_INF) / sumW;
+            return;
+        }
+        maxD2 *= 2.f;
+    }
+}
+
 // FromRGB(rgb, SPECTRUM_REFLECTANCE) (spectrum.cpp:92-133,175): same basis choice as the illuminant form, the
 // rgbRefl2Spect* tables, scale .94
 __device__ __forceinline__ float refl_band(const SptSpectralTables &t, const IllumCoefs &k, int c) {
@@ -634,8 +705,6 @@ __device__ inline void env_lookup(const DevScene &sc, float s, float t, float rg
     for (int k = 0; k < 3; ++k)
         rgb[k] = a[k] * ((1.f - ds) * (1.f - dt)) + b[k] * ((1.f - ds) * dt) + c[k] * (ds * (1.f - dt)) + d[k] * (ds * dt);
 }
-__device__ __forceinline__ float spherical_theta(v3 v) { return acosf(clampf(v.z, -1.f, 1.f)); }
-__device__ __forceinline__ float spherical_phi(v3 v) { float p = atan2f(v.y, v.x); return (p < 0.f) ? p + 2.f * PI_F : p; }
 // InfiniteAreaLight::Le (src/lights/infinite.cpp:109-114) as RGB; spectrum via illum_coefs/illum_band
 __device__ inline void infinite_le_rgb(const DevScene &sc, const SptLight &l, v3 d, float rgb[3]) {
     const SptXform &xf = sc.xforms[l.xform];

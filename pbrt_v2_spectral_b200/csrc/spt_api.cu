@@ -267,7 +267,11 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
             v.has_specular = 1;
         }
     for (const SptMaterial &mt : mats) {
-        if (mt.type == SPT_MAT_SUBSTRATE || mt.tex_kd >= 0 || mt.tex_bump >= 0) v.has_ext = 1;
+        if (mt.type == SPT_MAT_SUBSTRATE || mt.type == SPT_MAT_MEASURED || mt.tex_kd >= 0 || mt.tex_bump >= 0) v.has_ext = 1;
+        if (mt.type == SPT_MAT_MEASURED) {
+            v.has_measured = 1;
+            if (mt.brdf < 0 || mt.brdf >= (int32_t)d->n_brdfs) { g_err = "measured material references a BRDF table that is not in the scene"; delete s; return nullptr; }
+        }
         if (mt.tex_kd >= (int32_t)d->n_textures || mt.tex_bump >= (int32_t)d->n_textures) { g_err = "material references a texture that is not in the scene"; delete s; return nullptr; }
         if (mt.tex_kd >= 0 && d->textures[mt.tex_kd].channels != 3) { g_err = "Kd texture is not an RGB image map"; delete s; return nullptr; }
         if (mt.tex_bump >= 0 && d->textures[mt.tex_bump].channels != 1) { g_err = "bump texture is not a float image map"; delete s; return nullptr; }
@@ -282,6 +286,12 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
     UP(v.materials, mats.data(), d->n_materials); UP(v.lights, d->lights, d->n_lights);
     UP(v.textures, d->textures, d->n_textures); UP(v.tex_texels, d->tex_texels, d->n_texels);
     UP(v.ewa_lut, d->ewa_weight_lut, d->ewa_weight_lut ? 128 : 0);
+    for (uint32_t b = 0; b < d->n_brdfs; ++b)
+        if ((uint64_t)d->brdfs[b].node_first + d->brdfs[b].n_nodes > d->n_brdf_nodes || d->brdfs[b].n_nodes == 0 || d->brdfs[b].n_nodes > (1u << 16)) {
+            g_err = "malformed BRDF table"; delete s; return nullptr;       // 2^16 nodes: the look-up's stack of 32 covers depth 16
+        }
+    UP(v.brdfs, d->brdfs, d->n_brdfs); UP(v.brdf_nodes, d->brdf_nodes, d->n_brdf_nodes);
+    UP(v.brdf_spectra, d->brdf_spectra, (size_t)d->n_brdf_nodes * NB);
     UP(v.light_shapes, d->light_shapes, d->n_light_shapes);
     UP(v.light_cdf, cdf.data(), cdf.size());
     v.n_lights = d->n_lights;
@@ -385,6 +395,7 @@ static int ensure_wave(SptScene *s, int n_lanes, uint32_t cap, int max_depth, si
         AL(w.rec0, float4, cap); AL(w.rec1, float4, cap); AL(w.rec2, float4, cap);
         AL(w.laux, float4, cap); AL(w.pflags, uint32_t, cap);
         AL(w.rec3, float4, s->dev.has_ext ? cap : 1); AL(w.rec4, float4, s->dev.has_ext ? cap : 1);
+        AL(w.frow, float, s->dev.has_measured ? (size_t)cap * 3 * NB : 1);
         AL(w.img_xy, float2, cap);
         AL(w.T, float, (size_t)cap * NB); AL(w.L, float, (size_t)cap * NB);
         AL(w.pathQ[0], uint32_t, cap); AL(w.pathQ[1], uint32_t, cap); AL(w.shadowQ, uint32_t, cap); AL(w.misQ, uint32_t, cap);

@@ -116,5 +116,10 @@ struct DevScene {
     const float *tex_texels;
     const float *ewa_lut;
     int has_ext;
+    // measured BRDFs: the reference's kd-trees (SptKdNode rows + one spectrum per node)
+    const SptBrdfTable *brdfs;
+    const SptKdNode *brdf_nodes;
+    const float *brdf_spectra;
+    int has_measured;
     unsigned long long *counters;    // closest: [0] nodes, [1] prim tests; any-hit: [2], [3] (NULL when disabled)
 };

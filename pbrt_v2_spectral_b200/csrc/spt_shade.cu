@@ -114,6 +114,7 @@ __device__ __forceinline__ float2 dir_coef(int mtype, bool on, const DirTerms &t
     if (mtype == SPT_MAT_MATTE) d.x = on ? INV_PI_F * t.a0 : INV_PI_F;
     else if (mtype == SPT_MAT_PLASTIC) { d.x = INV_PI_F; if (t.mf) d.y = t.a0 * t.a1 * t.a2 / t.a3; }
     else if (mtype == SPT_MAT_SUBSTRATE) { if (t.mf) { d.x = t.a0; d.y = t.a1; } }    // third coefficient (t.a2) goes to rec3
+    else if (mtype == SPT_MAT_MEASURED) { if (t.mf) d.x = 1.f; }                      // the value itself is a row of frow
     else if (t.mf) { d.x = t.a0 * t.a1 / t.a3; d.y = t.a2; }
     return d;
 }
@@ -286,6 +287,21 @@ __global__ void __launch_bounds__(128, 4) k_shade(DevScene sc, RenderCfg cfg, Sa
                     g3 = make_float4(wiW2.x, wiW2.y, wiW2.z, 0.f);
                 }
                 if (mtype == SPT_MAT_METAL) flags |= RF_METAL;
+                if (EXT && mtype == SPT_MAT_MEASURED) {
+                    // f of every direction that survived: a table look-up per direction, written as one 128-byte row
+                    flags |= RF_MEASURED;
+                    const SptBrdfTable tb = sc.brdfs[bsdf.brdf];
+#pragma unroll 1
+                    for (int d = 0; d < 3; ++d) {
+                        const bool need = d == 0 ? (flags & RF_L) != 0 : (d == 1 ? (flags & RF_B) != 0 : ((flags & RF_P) != 0 && t2.mf));
+                        if (!need) continue;
+                        float fv[NB];
+                        measured_f(sc, tb, wo, d == 0 ? wl0 : (d == 1 ? wl1 : wl2), fv);
+                        float4 *row = (float4 *)(wb.frow + ((size_t)i * 3 + d) * NB);
+#pragma unroll
+                        for (int c = 0; c < NB / 4; ++c) row[c] = make_float4(fv[4 * c], fv[4 * c + 1], fv[4 * c + 2], fv[4 * c + 3]);
+                    }
+                }
                 if (EXT) {
                     if (mtype == SPT_MAT_SUBSTRATE) {
                         flags |= RF_SUBSTRATE;
@@ -430,6 +446,7 @@ __global__ void __launch_bounds__(32 * ACC_WARPS, 8) k_accumulate(DevScene sc, R
                 float4 e3 = make_float4(0.f, 0.f, 0.f, 0.f), e4 = e3;
                 uint32_t ebits = 0;
                 if (flags & RF_SUBSTRATE) { e3 = wb.rec3[i]; ebits |= 1u; }
+                if (flags & RF_MEASURED) ebits |= 4u;
                 if (flags & RF_TEXKD) {
                     const float4 r4 = wb.rec4[i];
                     const float rgb[3] = { r4.x, r4.y, r4.z };
@@ -488,7 +505,13 @@ __global__ void __launch_bounds__(32 * ACC_WARPS, 8) k_accumulate(DevScene sc, R
                         s0 = refl_band(tb, kk, lane);
                     }
                 }
-                if (EXT && (ebits & 1u)) {
+                if (EXT && (ebits & 4u)) {
+                    // measured BRDF: the three values are rows K5 wrote (coefficient 1 = the direction has a value)
+                    const float *fr = wb.frow + (size_t)iv[k] * 3 * NB + lane;
+                    fL = cLB.x != 0.f ? fr[0] : 0.f;
+                    fB = cLB.z != 0.f ? fr[NB] : 0.f;
+                    fP = cPs.x != 0.f ? fr[2 * NB] : 0.f;
+                } else if (EXT && (ebits & 1u)) {
                     // FresnelBlend (reflection.cpp:224-236): Kd (1 - Ks) x diffuse scalar + (Ks + (1 - Ks) (1 - wi.wh)^5) x D-term
                     const float oms = 1.f - s1, dR = s0 * oms;
                     fL = dR * cLB.x + (s1 + oms * e3.x) * cLB.y;

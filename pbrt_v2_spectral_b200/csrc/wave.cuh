@@ -34,6 +34,8 @@ struct WaveBuffers {
     // directions and the RGB an image-mapped Kd evaluated to at this vertex
     float4 *rec3;                     // {light dir c, MIS dir c, continuation c, -}: Schlick weight (1 - wi.wh)^5
     float4 *rec4;                     // {r, g, b, -}
+    float *frow;                      // measured BRDFs only: [cap][3][NB] - f(wo,wi) of the light / MIS / continuation direction, one
+                                      // 128-byte row each (a table look-up has no wavelength-independent factorisation)
     float4 *laux;                     // infinite light only: RGB radiance of the sampled direction
     uint32_t *pflags;                 // scenes with specular materials: bit 0 = the ray of this path left a specular bounce
     float2 *img_xy;
@@ -68,6 +70,7 @@ enum { RF_L = 1,          // the light sample has a BSDF value: a shadow ray dec
        RF_P_SPEC = 2,     // the continuation was sampled from a specular BxDF (path.cpp:86)
        RF_B = 4,          // the BSDF sample of the MIS estimate was traced
        RF_P = 8,          // there is a continuation direction
+       RF_MEASURED = 128, // f of each direction is a full spectrum in frow (measured BRDF)
        RF_TEXKD = 256,    // spec0 of the material is replaced by FromRGB(rec4) (image-mapped Kd)
        RF_SUBSTRATE = 512,// FresnelBlend: f[c] = Kd[c](1-Ks[c]) a + (Ks[c] + (1-Ks[c]) c) b, c in rec3
        RF_ON = 1024,      // matte with Oren-Nayar

@@ -407,7 +407,7 @@ struct Lowerer {
                 for (uint32_t k = 0; k < kd->nNodes; ++k) {
                     SptKdNode n;
                     memset(&n, 0, sizeof(n));
-                    n.split_pos = kd->nodes[k].splitPos;
+                    n.split_pos = kd->nodes[k].splitAxis == 3 ? 0.f : kd->nodes[k].splitPos;   // a leaf's splitPos is never written (kdtree.h:44-48)
                     n.bits = (uint32_t)kd->nodes[k].splitAxis | (uint32_t)kd->nodes[k].hasLeftChild << 2 | (uint32_t)kd->nodes[k].rightChild << 3;
                     n.p[0] = kd->nodeData[k].p.x; n.p[1] = kd->nodeData[k].p.y; n.p[2] = kd->nodeData[k].p.z;
                     out->brdf_nodes.push_back(n);

@@ -21,16 +21,18 @@ IMAGES = [("killeroo_small", 1024), ("bunny_small", 4096), ("metal_small", 512),
           # configs 3 and 4 with their shipped floor: substrate + image-mapped Kd (EWA) + bump map
           ("metal_shipped_small", 8192), ("ssenv_shipped_small", 8192),
           # the shipped scenes under their own integrator: directlighting, strategy all
-          ("killeroo_direct_small", 1024), ("bunny_direct_small", 1024)]
+          ("killeroo_direct_small", 1024), ("bunny_direct_small", 1024),
+          # the bunny's shipped measured BRDF: under the path integrator (config 2), and bunny.pbrt exactly as shipped
+          ("bunny_measured_small", 4096), ("bunny_shipped_small", 1024)]
 
 
 @pytest.mark.parametrize("name,spp", IMAGES, ids=[n for n, _ in IMAGES])
 def test_converged_image_within_1_percent_per_band(name, spp):
-    dat = os.path.join(O.GOLDEN_BIG, "%s_%dspp.dat" % (name, spp))
+    dat = os.path.join(O.GOLDEN_BIG, "%s_%dspp.ref.npy" % (name, spp))    # the reference's .dat as float32 [y][x][band]
     spt = os.path.join(O.GOLDEN_BIG, name + ".spt")
     if not (os.path.exists(dat) and os.path.exists(spt)):
         pytest.skip("reference image %s not generated (oracle/make_golden.py --images)" % dat)
-    ref = capi.read_dat(dat) / spp
+    ref = np.load(dat).astype(np.float64) / spp
     lowered = LoweredScene.load(spt)
     scene = capi.Scene(lowered)
     rp = D.SptRenderParams.from_buffer_copy(bytes(lowered.params))
