@@ -214,6 +214,10 @@ def main():
     film_t = torch.zeros((fd.y_pixel_count, fd.x_pixel_count, D.NBANDS + 1), dtype=torch.float32, device=dev)
     film = capi.Film(fd, film_t.data_ptr())
 
+    # N > 1: the one exchange of the job - every rank's possibly non-zero film pixels (its tiles grown by the filter's reach)
+    # gathered onto rank 0 over NVLink (NCCL) and added there; same sum as a full-film reduction, 1/N of the bytes
+    exchange = multi.FilmExchange(fd, rp, world, dev)
+
     def barrier():
         torch.cuda.synchronize()
         if dist is not None:
@@ -237,7 +241,7 @@ def main():
     for _ in range(max(args.warmup, 3)):
         film_t.zero_()
         scene.render(film, rp)
-        multi.reduce_film(film_t)
+        exchange.run(film_t, rank)
     barrier()
     launches0 = scene.stats()["kernel_launches"]
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -251,7 +255,7 @@ def main():
     for _ in range(args.steps):
         film_t.zero_()
         scene.render(film, rp)                       # blocks until the library's streams have drained
-        multi.reduce_film(film_t)                    # N > 1: the film is summed onto rank 0 over NVLink (NCCL)
+        exchange.run(film_t, rank)                    # N > 1: the film is summed onto rank 0 over NVLink (NCCL)
         st = scene.stats()
         render_ms += st["render_ms"]
         lanes_used = st["lanes_used"]
@@ -282,10 +286,10 @@ def main():
         first_vertices += st["first_vertices"]
         for k in range(D.K_CLASSES):
             class_ms[k] += st["class_ms"][k]; class_launches[k] += st["class_launches"][k]; class_rays[k] += st["class_rays"][k]
-    scene.set_lanes(int(os.environ.get("SPT_LANES", "4")))
+    scene.set_lanes(int(os.environ.get("SPT_LANES", "2")))
     film_t.zero_()
     scene.render(film, rp)
-    multi.reduce_film(film_t)
+    exchange.run(film_t, rank)
     barrier()
     step_ms = e0.elapsed_time(e1) / args.steps
     sys.stderr.write("[rank %d] render %.3f ms/step (library events), step incl. film zero + reduce %.3f ms, serialized kernels %.3f ms\n" % (rank, render_ms / args.steps, step_ms, serial_ms / prof_steps))
@@ -388,7 +392,7 @@ def main():
                 else "reference scene file lowered by the host side (substitutions listed in config.workload)" if not args.workload.startswith("synth")
                 else "synthetic scene written as .pbrt text, parsed, BVH-built and lowered by the reference's own code (oracle/make_golden.py)",
         "config": {"workload": workload_desc, "camera_samples_per_step": n_samples_total,
-                   "parallelism": "image tile sets (32x32, round-robin) x%d, scene replicated, NCCL film reduce" % world,
+                   "parallelism": "image tile sets (32x32, round-robin) x%d, scene replicated, film pixels of each rank's tiles gathered to rank 0 over NCCL and added" % world,
                    "l2": "per-step wave state (>2 GB) and film are larger than L2; no explicit flush"},
         "mrays_per_s": rays_total / prof_steps / (ms_per_step / 1e3) / 1e6 if world == 1 else None,
         "rays_per_sample": rays_total / prof_steps / (n_samples_total / world) if world else None,

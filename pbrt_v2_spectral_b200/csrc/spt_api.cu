@@ -93,7 +93,8 @@ struct SptScene {
     bool counters_on = false;
     int trace_variant = 1;           // trace_kernels.cuh: 0 reference nodes, 1 pair nodes (default)
     uint32_t fetch_threshold = 14;
-    int max_lanes = 4;               // spt_scene_set_lanes: 1 = every wave on one stream (per-kernel timing is then exact)
+    int max_lanes = 2;               // spt_scene_set_lanes: 1 = every wave on one stream (per-kernel timing is then exact); two lanes
+                                     // measured best at every job size (profiles/r01_rank_emulation.log)
     cudaEvent_t evjoin[SPT_MAX_LANES] = {};
     bool has_env = false;            // an infinite light is present (escaped camera rays pick up Le)
     int direct_slots = 1;            // sum of the lights' n_samples: slots per camera sample under directlighting

@@ -36,8 +36,61 @@ def reduce_film(film_t, dst=0):
     return film_t
 
 
-def render_distributed(render_fn, film_t, params, rank, world, tile=TILE):
-    """Zero the film, render this rank's tile set, reduce. Returns the film tensor (complete on rank 0)."""
+class FilmExchange:
+    """The same exchange moving only what can be non-zero: rank r sends the film pixels its tile set can have touched -
+    its tiles grown by the filter's reach - and rank 0 ADDS them into its own film. With the box filter that is
+    (34/32)^2 / N of the film per rank instead of the whole film through a reduction tree (8 GPUs, 700x700x33 floats:
+    9 MB per rank instead of 65 MB), and the result is the same sum (up to the order of fp32 additions where the
+    grown tiles of two ranks overlap and both are non-zero).
+
+    film: SptFilmDesc-like (x/y_pixel_start/count, filter_x/ywidth); params: SptRenderParams-like (sample extent).
+    Built once per (film, params, world); every rank computes every rank's pixel list (cheap, host side)."""
+
+    def __init__(self, film, params, world, device, tile=TILE):
+        import math
+        self.world = world
+        W, H = film.x_pixel_count, film.y_pixel_count
+        xs, ys = film.x_pixel_start, film.y_pixel_start
+        # a sample at continuous (ix, iy) reaches film pixels ceil(ix - .5 - w) .. floor(ix - .5 + w) (spectralImage.cpp:88-96)
+        hx = int(math.ceil(film.filter_xwidth + 0.5)); hy = int(math.ceil(film.filter_ywidth + 0.5))
+        ntx = (params.x_end - params.x_start + tile - 1) // tile
+        nty = (params.y_end - params.y_start + tile - 1) // tile
+        masks = [torch.zeros((H, W), dtype=torch.bool) for _ in range(world)]
+        for t in range(ntx * nty):
+            ty, tx = divmod(t, ntx)
+            x0 = params.x_start + tx * tile - hx - xs; x1 = params.x_start + (tx + 1) * tile + hx - xs
+            y0 = params.y_start + ty * tile - hy - ys; y1 = params.y_start + (ty + 1) * tile + hy - ys
+            x0, y0, x1, y1 = max(x0, 0), max(y0, 0), min(x1, W), min(y1, H)
+            if x1 > x0 and y1 > y0:
+                masks[t % world][y0:y1, x0:x1] = True
+        idx = [m.reshape(-1).nonzero().reshape(-1) for m in masks]
+        self.n = max(int(i.numel()) for i in idx) if idx else 0
+        # equal lengths for the gather: padded with pixel 0, whose padded rows are zero
+        self.counts = [int(i.numel()) for i in idx]
+        self.idx = [torch.cat([i, i.new_zeros(self.n - i.numel())]).to(device) for i in idx]
+
+    def run(self, film_t, rank, dst=0):
+        if self.world == 1:
+            return film_t
+        flat = film_t.view(-1, film_t.shape[-1])
+        mine = flat.index_select(0, self.idx[rank])
+        if self.counts[rank] < self.n:
+            mine[self.counts[rank]:] = 0
+        if rank == dst:
+            parts = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.gather(mine, parts, dst=dst)
+            for r in range(self.world):
+                if r != dst:
+                    flat.index_add_(0, self.idx[r], parts[r])
+        else:
+            dist.gather(mine, None, dst=dst)
+        return film_t
+
+
+def render_distributed(render_fn, film_t, params, rank, world, tile=TILE, exchange=None):
+    """Zero the film, render this rank's tile set, exchange. Returns the film tensor (complete on rank 0)."""
     film_t.zero_()
     render_fn(rank_params(params, rank, world, tile))
+    if exchange is not None:
+        return exchange.run(film_t, rank)
     return reduce_film(film_t)

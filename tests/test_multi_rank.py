@@ -35,6 +35,12 @@ def _worker(rank, world, port, out_path):
     multi.render_distributed(render_fn, film_t, rp, rank, world, tile=8)
     if rank == 0:
         np.save(out_path, film_t.numpy())
+    # the sparse exchange (only the pixels a rank's tiles can reach) must give the same film as the full reduction
+    ex = multi.FilmExchange(fd, multi.rank_params(rp, rank, world, 8), world, torch.device("cpu"), tile=8)
+    multi.render_distributed(render_fn, film_t, rp, rank, world, tile=8, exchange=ex)
+    if rank == 0:
+        np.save(out_path + ".sparse.npy", film_t.numpy())
+        assert sum(ex.counts) < 2 * film_t.shape[0] * film_t.shape[1]
     dist.barrier()
     dist.destroy_process_group()
 
@@ -52,6 +58,9 @@ def test_two_ranks_reduce_to_the_single_rank_image(tmp_path):
     c, w = O.render(lowered, rp)
     assert np.array_equal(got[..., D.NBANDS], w)
     assert np.allclose(got[..., :D.NBANDS], c, rtol=1e-6, atol=1e-7)
+    sparse = np.load(out + ".sparse.npy")
+    assert np.array_equal(sparse[..., D.NBANDS], w)
+    assert np.allclose(sparse[..., :D.NBANDS], c, rtol=1e-6, atol=1e-7)
 
 
 def test_tile_owner_matches_the_render_partition():
