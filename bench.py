@@ -122,7 +122,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     if not os.path.exists(REF_BIN):
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/bin/pbrt not built (build() needs /root/reference)"}))
+        print_json({"impl": "reference", "unavailable": "oracle/_ref/bin/pbrt not built (build() needs /root/reference)"})
         return
     ncores = os.cpu_count() or 1
     setup = min(reference_run(reference_scene(1, 8), ncores) for _ in range(2))
@@ -135,14 +135,14 @@ def run_reference_arm(args):
     ms = 1e3 * sum(times) / len(times)
     value = n_samples / (ms / 1e3) / 1e6
     sample = "same frame (700x700, sample extent 701x701) at %d of the 64 spp per step; parse+BVH build (%.2fs, 8x8 1spp run) subtracted" % (CPU_SAMPLE_SPP, setup)
-    print(json.dumps({
+    print_json({
         "impl": "reference", "metric": "Msamples/sec (32-band spectral path trace)", "value": value, "unit": "Msamples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "reference scene file (killeroo-simple) derived per SURVEY.md F9",
         "config": {"workload": WORKLOAD_DESC, "reference_binary": "oracle/_ref/bin/pbrt (unmodified reference, g++ -O2 -m64)"},
         "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": ncores, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 # ------------------------------------------------------------------------------------------------
@@ -157,6 +157,15 @@ def main():
     ap.add_argument("--workload", default=WORKLOAD, help="lowered scene under assets/_lowered (default: BASELINE config 1); "
                     "synth_1m = config 5's recipe at 1 M triangles, BVH larger than L2 (no CPU arm)")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: everything else written to file descriptor 1 by this process or by libraries
+    # under it (NCCL's version banner, which it prints itself whatever torch's logging is set to) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    global print_json
+
+    def print_json(obj):
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
     if args.impl == "reference":
         run_reference_arm(args)
         return
@@ -420,7 +429,7 @@ def main():
                                    CPU_WORKLOADS[args.workload][3], CPU_WORKLOADS[args.workload][2], render_s, setup_s)}
     else:
         out["cpu_baseline"] = None
-    print(json.dumps(out))
+    print_json(out)
     film.close(); scene.close()
     if dist is not None:
         dist.destroy_process_group()

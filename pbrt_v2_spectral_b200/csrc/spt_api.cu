@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
+#include <ctime>
 #include <map>
 #include <mutex>
 #include <string>
@@ -166,8 +167,13 @@ void spt_trim(void) {
     g_blocks.trim();
 }
 
+static double now_ms() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+
 SptScene *spt_scene_create(const SptSceneDesc *d) {
     if (!d) { g_err = "null scene desc"; return nullptr; }
+    const bool timing = getenv("SPT_TIMING") != nullptr;
+    double t_mark = now_ms();
+    auto lap = [&](const char *what) { if (timing) { double t = now_ms(); fprintf(stderr, "[spt_scene_create] %-28s %.3f ms\n", what, t - t_mark); t_mark = t; } };
     if (d->nbands != NB) { g_err = "scene band count does not match the library's SPT_NBANDS"; return nullptr; }
     if (spt_device_count() <= 0) { g_err = "no CUDA device: this library has no CPU path"; return nullptr; }
     if (d->n_materials > 0xffffu || d->n_lights > 0xfffeu) { g_err = "more than 65535 materials or 65534 lights"; return nullptr; }
@@ -187,6 +193,7 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
         for (uint32_t i = 0; i < np; ++i)
             if (off + i < d->n_prims && d->prim_kind[off + i] != SPT_PRIM_TRIANGLE) nd[30] = 1;
     }
+    lap("node copy + leaf flags");
     // pair nodes: compact array over the interior nodes of the reference's depth-first layout. Child
     // codes pack a leaf's {hasQuadric, nPrims-1, first slot} into one word; a tree that does not fit
     // (leaves of more than 8 primitives, 2^27 primitives) is walked on the reference layout (variant 0).
@@ -220,6 +227,7 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
             if (d->n_nodes) root_code = code(0);
         } else s->trace_variant = 0;
     }
+    lap("pair nodes");
     // pre-gathered triangle vertices per BVH slot
     std::vector<float4> tv((size_t)d->n_prims * 3, make_float4(0, 0, 0, 0));
     for (uint32_t p = 0; p < d->n_prims; ++p) {
@@ -243,6 +251,7 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
         if (funcInt == 0.f) for (int i = 1; i < n + 1; ++i) c[i] = float(i) / float(n);
         else for (int i = 1; i < n + 1; ++i) c[i] /= funcInt;
     }
+    lap("triangle gather + light cdf");
     DevMem &m = s->mem;
     bool ok = true;
 #define UP(dst, src, n) do { dst = m.upload(src, (size_t)(n)); if (!dst) ok = false; } while (0)
@@ -315,6 +324,7 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
     UP(v.env_marg_func, d->env_marg_func, eh); UP(v.env_marg_cdf, d->env_marg_cdf, eh ? eh + 1 : 0);
     v.env_marg_int = d->env_marg_int;
 #undef UP
+    lap("uploads");
     s->counters = m.alloc<unsigned long long>(4);
     if (!ok || !s->counters || cudaMemset(s->counters, 0, 32) != cudaSuccess ||
         !make_lanes(s) ||
@@ -326,6 +336,7 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
     }
     v.counters = nullptr;
     s->stream = s->lane[0].stream;
+    lap("streams + events");
     return s;
 }
 
