@@ -7,7 +7,8 @@ Three translation units, two floating-point regimes:
   spt_shade.cu   shading, accumulation, film. Also -fmad=false: the reference's own formulas are ill-conditioned
                  in places (1 - cos of a small cone angle in the sphere-light pdf), so radiance only tracks the
                  reference to 2e-4 per sample when the rounding sequence is the same; FMA bought 5 % of one kernel.
-  spt_api.cu     host side of the C ABI (no kernels)."""
+  spt_api.cu     host side of the C ABI (no kernels).
+  spt_build.cu   scene re-layout kernels run once per spt_scene_create (pair nodes, leaf flags, vertex pre-gather)."""
 import os
 import subprocess
 import sys
@@ -18,7 +19,8 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libspt.so")
 OBJ = os.path.join(HERE, "build")
-UNITS = [("spt_exact.cu", ["-fmad=false"]), ("spt_shade.cu", ["-fmad=false"]), ("spt_api.cu", ["-fmad=false"])]
+UNITS = [("spt_exact.cu", ["-fmad=false"]), ("spt_shade.cu", ["-fmad=false"]), ("spt_api.cu", ["-fmad=false"]),
+         ("spt_build.cu", ["-fmad=false"])]
 DEPS = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "spt.h")]
 COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
           "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]

@@ -28,3 +28,9 @@ void spt_launch_film_add(int grid, cudaStream_t st, const FilmView &film, const 
 void spt_launch_film_split(int grid, cudaStream_t st, const float *pix, size_t npix, float *c, float *w);
 void spt_launch_gather_L(cudaStream_t st, const float *L, uint32_t cap, uint32_t n, int sub, float *out);
 void spt_launch_scatter_L(cudaStream_t st, const float *in, uint32_t cap, uint32_t n, float *L);
+
+// spt_build.cu: scene re-layout on the device
+size_t spt_relayout_scratch_bytes(uint32_t n_nodes);
+cudaError_t spt_launch_relayout(cudaStream_t st, void *nodes, uint32_t n_nodes, const uint8_t *prim_kind, const uint32_t *prim_data,
+                                uint32_t n_prims, const int32_t *tri_vidx, const float *P, float4 *pn, float4 *tv, void *scratch,
+                                uint32_t status_host[2]);

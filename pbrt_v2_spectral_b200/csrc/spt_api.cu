@@ -183,8 +183,16 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
     if (const char *e = getenv("SPT_LANES")) s->max_lanes = std::min(std::max(atoi(e), 1), SPT_MAX_LANES);
     DevScene &v = s->dev;
     memset(&v, 0, sizeof(v));
-    // nodes: byte-identical copy, plus the hasQuadric bit in the reference's pad byte for leaves
-    std::vector<uint8_t> nodes((const uint8_t *)d->bvh_nodes, (const uint8_t *)d->bvh_nodes + (size_t)d->n_nodes * 32);
+    // What the traversal kernels read - leaf flags in the reference nodes, pair nodes, per-slot triangle vertices - is built
+    // on the DEVICE from the uploaded arrays (spt_build.cu); SPT_HOST_RELAYOUT=1 keeps the first, host-side builder (1.7 ms per
+    // scene on killeroo) for A/B checks. Both give the same bytes.
+    const bool host_relayout = getenv("SPT_HOST_RELAYOUT") != nullptr;
+    std::vector<uint8_t> nodes;
+    std::vector<float4> pn, tv;
+    uint32_t root_code = 0xffffffffu;
+    bool pairs_ok = d->n_prims < (1u << 27) - 1u;
+    if (host_relayout) {
+    nodes.assign((const uint8_t *)d->bvh_nodes, (const uint8_t *)d->bvh_nodes + (size_t)d->n_nodes * 32);
     for (uint32_t n = 0; n < d->n_nodes; ++n) {
         uint8_t *nd = &nodes[(size_t)n * 32];
         uint32_t off; memcpy(&off, nd + 24, 4);
@@ -197,9 +205,6 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
     // pair nodes: compact array over the interior nodes of the reference's depth-first layout. Child
     // codes pack a leaf's {hasQuadric, nPrims-1, first slot} into one word; a tree that does not fit
     // (leaves of more than 8 primitives, 2^27 primitives) is walked on the reference layout (variant 0).
-    std::vector<float4> pn;
-    uint32_t root_code = 0xffffffffu;
-    bool pairs_ok = d->n_prims < (1u << 27) - 1u;
     {
         struct RefNode { float b[6]; uint32_t off; uint8_t np, axis, hasq, pad; };
         const RefNode *rn = (const RefNode *)nodes.data();
@@ -229,7 +234,7 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
     }
     lap("pair nodes");
     // pre-gathered triangle vertices per BVH slot
-    std::vector<float4> tv((size_t)d->n_prims * 3, make_float4(0, 0, 0, 0));
+    tv.assign((size_t)d->n_prims * 3, make_float4(0, 0, 0, 0));
     for (uint32_t p = 0; p < d->n_prims; ++p) {
         if (d->prim_kind[p] != SPT_PRIM_TRIANGLE) continue;
         const int32_t *vi = d->tri_vidx + 3 * (size_t)d->prim_data[p];
@@ -237,6 +242,7 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
             const float *P = d->P + 3 * (size_t)vi[k];
             tv[(size_t)p * 3 + k] = make_float4(P[0], P[1], P[2], 0.f);
         }
+    }
     }
     // Distribution1D of each area light's ShapeSet (montecarlo.h:48-68), same fp32 recurrence
     std::vector<float> cdf(d->n_light_shapes + d->n_lights + 1, 0.f);
@@ -255,10 +261,18 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
     DevMem &m = s->mem;
     bool ok = true;
 #define UP(dst, src, n) do { dst = m.upload(src, (size_t)(n)); if (!dst) ok = false; } while (0)
-    const float4 *nodes4; UP(nodes4, (const float4 *)nodes.data(), (size_t)d->n_nodes * 2); v.nodes = nodes4;
-    UP(v.tri_verts, tv.data(), tv.size());
-    UP(v.pnodes, pn.data(), pn.size());
-    v.root_code = root_code;
+    float4 *nodes4 = nullptr, *tv_dev = nullptr, *pn_dev = nullptr;
+    if (host_relayout) {
+        UP(nodes4, (const float4 *)nodes.data(), (size_t)d->n_nodes * 2);
+        UP(tv_dev, tv.data(), tv.size());
+        UP(pn_dev, pn.data(), pn.size());
+    } else {
+        UP(nodes4, (const float4 *)d->bvh_nodes, (size_t)d->n_nodes * 2);
+        tv_dev = m.alloc<float4>((size_t)d->n_prims * 3);
+        pn_dev = m.alloc<float4>(((size_t)d->n_nodes / 2 + 1) * 4);       // a binary tree of n nodes has (n - 1) / 2 interior nodes
+        if (!tv_dev || !pn_dev) ok = false;
+    }
+    v.nodes = nodes4; v.tri_verts = tv_dev; v.pnodes = pn_dev;
     v.n_nodes = d->n_nodes; v.n_prims = d->n_prims;
     UP(v.prim_kind, d->prim_kind, d->n_prims); UP(v.prim_flags, d->prim_flags, d->n_prims);
     UP(v.prim_id, d->prim_id, d->n_prims); UP(v.prim_data, d->prim_data, d->n_prims);
@@ -266,6 +280,19 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
     UP(v.prim_xform, d->prim_xform, d->n_prims);
     UP(v.tri_vidx, d->tri_vidx, (size_t)d->n_tris * 3);
     UP(v.P, d->P, (size_t)d->n_verts * 3); UP(v.N, d->N, (size_t)d->n_verts * 3); UP(v.UV, d->UV, (size_t)d->n_verts * 2);
+    if (!host_relayout && ok) {
+        DevMem scratch;
+        void *sc_dev = scratch.alloc<uint8_t>(spt_relayout_scratch_bytes(d->n_nodes));
+        uint32_t status[2] = { 0, 0xffffffffu };
+        cudaError_t e = sc_dev ? spt_launch_relayout(0, nodes4, d->n_nodes, v.prim_kind, v.prim_data, d->n_prims, v.tri_vidx, v.P,
+                                                     pn_dev, tv_dev, sc_dev, status) : cudaErrorMemoryAllocation;
+        scratch.release();
+        if (e != cudaSuccess) { g_err = std::string("scene re-layout failed: ") + cudaGetErrorString(e); m.release(); delete s; return nullptr; }
+        if ((status[0] & 1u) && pairs_ok && !(status[0] & 2u)) { g_err = "malformed BVH: child index out of range"; m.release(); delete s; return nullptr; }
+        if (status[0] & 2u) pairs_ok = false;
+        if (pairs_ok) root_code = d->n_nodes ? status[1] : 0xffffffffu; else s->trace_variant = 0;
+    }
+    v.root_code = root_code;
     UP(v.quadrics, d->quadrics, d->n_quadrics); UP(v.xforms, d->xforms, d->n_xforms);
     // materials: p1 of a mirror / glass row records which of its spectra are not black (the BxDFs GetBSDF adds)
     std::vector<SptMaterial> mats(d->materials, d->materials + d->n_materials);
