@@ -416,31 +416,32 @@ int spt_get_stats(SptScene *s, SptStats *out) {
 // cursors, escaped camera rays, MIS rays elided (could not reach the light), MIS rays traced as any-hit + their cursor}
 #define SPT_ROW 16
 
-static int ensure_wave(SptScene *s, int n_lanes, uint32_t cap, int max_depth, size_t n_waves) {
+static int ensure_wave(SptScene *s, int n_lanes, uint32_t cap, int max_depth, size_t n_waves, uint32_t sub = 1) {
     cap = (cap + 31u) & ~31u;
+    const size_t jcap = (size_t)cap * sub;
     size_t need_counts = n_waves * (size_t)(max_depth + 2) * SPT_ROW;
     for (int li = 0; li < n_lanes; ++li) {
         SptScene::Lane &ln = s->lane[li];
-        if (ln.wb.cap >= cap) continue;
+        if (ln.wb.cap >= cap && ln.wb.jcap >= jcap) continue;
         ln.mem.release();
         DevMem &m = ln.mem;
         WaveBuffers &w = ln.wb;
-        w.cap = cap;
+        w.cap = cap; w.jcap = (uint32_t)jcap;
         bool ok = true;
 #define AL(field, T, n) do { field = m.alloc<T>((size_t)(n)); if (!field) ok = false; } while (0)
         AL(w.ray_o, float4, cap); AL(w.ray_d, float4, cap); AL(w.hit_slot, uint32_t, cap); AL(w.hit_t, float, cap);
-        AL(w.g0, float4, cap); AL(w.g1, float4, cap); AL(w.g2, float4, cap); AL(w.g3, float4, cap);
-        AL(w.mis_slot, uint32_t, cap); AL(w.mis_t, float, cap); AL(w.sh_slot, uint32_t, cap);
-        AL(w.rec0, float4, cap); AL(w.rec1, float4, cap); AL(w.rec2, float4, cap);
-        AL(w.laux, float4, cap); AL(w.pflags, uint32_t, cap);
-        AL(w.rec3, float4, s->dev.has_ext ? cap : 1); AL(w.rec4, float4, s->dev.has_ext ? cap : 1);
-        AL(w.frow, float, s->dev.has_measured ? (size_t)cap * 3 * NB : 1);
+        AL(w.g0, float4, jcap); AL(w.g1, float4, jcap); AL(w.g2, float4, jcap); AL(w.g3, float4, cap);
+        AL(w.mis_slot, uint32_t, jcap); AL(w.mis_t, float, jcap); AL(w.sh_slot, uint32_t, jcap);
+        AL(w.rec0, float4, jcap); AL(w.rec1, float4, jcap); AL(w.rec2, float4, jcap);
+        AL(w.laux, float4, jcap); AL(w.pflags, uint32_t, cap);
+        AL(w.rec3, float4, s->dev.has_ext ? jcap : 1); AL(w.rec4, float4, s->dev.has_ext ? jcap : 1);
+        AL(w.frow, float, s->dev.has_measured ? jcap * 3 * NB : 1);
         AL(w.img_xy, float2, cap);
         AL(w.T, float, (size_t)cap * NB); AL(w.L, float, (size_t)cap * NB);
-        AL(w.pathQ[0], uint32_t, cap); AL(w.pathQ[1], uint32_t, cap); AL(w.shadowQ, uint32_t, cap); AL(w.misQ, uint32_t, cap);
-        AL(w.hitQ, uint32_t, cap); AL(w.missQ, uint32_t, cap); AL(w.misAnyQ, uint32_t, cap);
+        AL(w.pathQ[0], uint32_t, cap); AL(w.pathQ[1], uint32_t, cap); AL(w.shadowQ, uint32_t, jcap); AL(w.misQ, uint32_t, jcap);
+        AL(w.hitQ, uint32_t, cap); AL(w.missQ, uint32_t, cap); AL(w.misAnyQ, uint32_t, jcap);
 #undef AL
-        if (!ok) { w.cap = 0; m.release(); return fail(SPT_ERR_CUDA, "out of device memory for wave buffers"); }
+        if (!ok) { w.cap = 0; w.jcap = 0; m.release(); return fail(SPT_ERR_CUDA, "out of device memory for wave buffers"); }
     }
     if (s->counts_len < need_counts) {
         s->counts_mem.release();
@@ -487,7 +488,7 @@ static void run_wave(SptScene *s, const RenderCfg &cfg, const SampleSource &src,
         s->mark(SPT_K_TRACE_PATH, li);
         spt_launch_compact_hits(gridC, st, q, row + 0, wb.hit_slot, wb.hitQ, row + 3, mq, row + 7, (b == 0 && !s->has_env) ? wb.L : nullptr);
         s->mark(SPT_K_SHADE, li);
-        if (mq) { spt_launch_miss_env(gridT, st, sc, wb, b, mq, row + 7, cfg.sub); s->mark(SPT_K_SHADE, li); }
+        if (mq) { spt_launch_miss_env(gridT, st, sc, wb, b, mq, row + 7, 1); s->mark(SPT_K_SHADE, li); }
         spt_launch_shade(gridT, st, sc, cfg, src, wb, b, wb.hitQ, row + 3, row + 1, row + 2, row + 8, row + 9);
         s->mark(SPT_K_SHADE, li);
         if (sc.n_lights > 0) {
@@ -671,7 +672,7 @@ int spt_shade_samples(SptScene *s, const SptCameraDesc *cam, int32_t integrator,
     const int stride = direct ? 7 + 6 * s->direct_slots : 37;
     if (direct) max_depth = 0;
     if (n * (uint64_t)sub > (1u << 26)) return fail(SPT_ERR_ARG, "too many samples for one call");
-    int rc = ensure_wave(s, 1, (uint32_t)(n * sub), max_depth, 1);
+    int rc = ensure_wave(s, 1, (uint32_t)n, max_depth, 1, (uint32_t)sub);
     if (rc != SPT_OK) return rc;
     DevMem m;
     float *dsmp = m.upload(samples, n * (size_t)stride);
@@ -680,7 +681,7 @@ int spt_shade_samples(SptScene *s, const SptCameraDesc *cam, int32_t integrator,
     if (!dsmp || !dout || (rng && n_rng > 0 && !drng)) { m.release(); return fail(SPT_ERR_CUDA, "device allocation failed"); }
     RenderCfg cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.cam = *cam; cfg.spp = 1; cfg.spp_shift = 0; cfg.max_depth = max_depth; cfg.n_samples = (uint32_t)(n * sub);
+    cfg.cam = *cam; cfg.spp = 1; cfg.spp_shift = 0; cfg.max_depth = max_depth; cfg.n_samples = (uint32_t)n;
     cfg.integrator = integrator; cfg.sub = sub;
     cfg.tile = 1; cfg.tile_shift = 0; cfg.tilesX = 1; cfg.tilesY = 1; cfg.nranks = 1;
     cfg.diff_scale = 1.f / sqrtf((float)spp);
@@ -689,7 +690,7 @@ int spt_shade_samples(SptScene *s, const SptCameraDesc *cam, int32_t integrator,
     cudaMemsetAsync(s->counts, 0, nc * 4, s->stream);
     reset_class_stats(s);
     run_wave(s, cfg, src, s->counts);
-    spt_launch_gather_L(s->stream, s->lane[0].wb.L, s->lane[0].wb.cap, (uint32_t)n, sub, dout);
+    spt_launch_gather_L(s->stream, s->lane[0].wb.L, s->lane[0].wb.cap, (uint32_t)n, 1, dout);
     std::vector<uint32_t> hc(nc);
     cudaMemcpyAsync(hc.data(), s->counts, nc * 4, cudaMemcpyDeviceToHost, s->stream);
     cudaError_t e = cudaMemcpyAsync(out_L, dout, n * NB * sizeof(float), cudaMemcpyDeviceToHost, s->stream);
@@ -818,7 +819,7 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
     if (direct && s->dev.has_specular) return fail(SPT_ERR_UNSUPP, "directlighting with specular materials is not supported");
     if (direct && s->dev.n_lights == 0) return fail(SPT_ERR_UNSUPP, "directlighting needs at least one light");
     if (direct && !s->direct_pow2) return fail(SPT_ERR_ARG, "directlighting: every light's n_samples must be a power of two (Sampler::RoundSize)");
-    const int sub = direct ? s->direct_slots : 1;                 // slots per camera sample
+    const int sub = direct ? s->direct_slots : 1;                 // jobs per camera hit
     RenderCfg cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.cam = *cam; cfg.spp = rp->spp; cfg.max_depth = direct ? 0 : rp->max_depth;
@@ -845,12 +846,13 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
     // Waves: by default the rank's pixels are cut into a multiple of max_lanes waves, each at most
     // 2^25 / max_lanes paths (17 GB of state over all lanes), dealt to the lanes in turn; small jobs
     // (< 2^19 paths per wave) use fewer lanes, down to one wave on one lane.
-    const uint64_t slots_pp = (uint64_t)rp->spp * (uint64_t)sub;       // path slots per pixel
+    const uint64_t slots_pp = (uint64_t)rp->spp;                       // paths per pixel
+    const uint64_t mem_pp = slots_pp * (uint64_t)std::max(1, (sub + 3) / 4);   // directlighting: ~140 B per job on top of ~450 B per path
     const int depth = cfg.max_depth;
     const uint64_t local_samples = local_pixels * slots_pp;
     int want_lanes = s->max_lanes;
     while (want_lanes > 1 && local_samples < ((uint64_t)want_lanes << 19)) --want_lanes;
-    const uint64_t lane_cap_pixels = std::max<uint64_t>(1, ((1u << 25) / (uint64_t)want_lanes) / slots_pp);
+    const uint64_t lane_cap_pixels = std::max<uint64_t>(1, ((1u << 25) / (uint64_t)want_lanes) / mem_pp);
     uint64_t wave_pixels;
     if (rp->wave_pixels > 0) wave_pixels = (uint64_t)rp->wave_pixels;
     else {
@@ -862,7 +864,7 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
     if (wave_pixels * slots_pp > (1ull << 27)) wave_pixels = std::max<uint64_t>(1, (1ull << 27) / slots_pp);
     size_t n_waves = (size_t)((local_pixels + wave_pixels - 1) / wave_pixels);
     const int n_lanes = (int)std::min<size_t>((size_t)s->max_lanes, std::max<size_t>(n_waves, 1));
-    int rc = ensure_wave(s, n_lanes, (uint32_t)(wave_pixels * slots_pp), depth, std::max<size_t>(n_waves, 1));
+    int rc = ensure_wave(s, n_lanes, (uint32_t)(wave_pixels * slots_pp), depth, std::max<size_t>(n_waves, 1), (uint32_t)sub);
     if (rc != SPT_OK) return rc;
     size_t per_wave = (size_t)(depth + 2) * SPT_ROW;
     cudaStream_t st = s->stream;
@@ -881,7 +883,7 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
         run_wave(s, cfg, src, s->counts + w * per_wave, li);
         unsigned gw = (unsigned)std::min<uint64_t>((np * 32 + 255) / 256, (uint64_t)num_sms() * 16);
         const WaveBuffers &wb = s->lane[li].wb;
-        spt_launch_film_add((int)gw, s->lane[li].stream, fv, s->dev.tables, wb.img_xy, wb.L, wb.cap, (uint32_t)(np * rp->spp), rp->spp, sub);
+        spt_launch_film_add((int)gw, s->lane[li].stream, fv, s->dev.tables, wb.img_xy, wb.L, wb.cap, (uint32_t)(np * rp->spp), rp->spp, 1);
         s->mark(SPT_K_FILM, li);
     }
     for (int k = 1; k < n_lanes; ++k) {                                              // join
@@ -911,7 +913,7 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
     s->stats.class_rays[SPT_K_GEN] = samples; s->stats.class_rays[SPT_K_FILM] = samples;
     s->stats.camera_samples += samples;
     add_ray_stats(s, hc, depth, n_waves);
-    const uint64_t overhang = slots > samples * (uint64_t)sub ? slots - samples * (uint64_t)sub : 0;
+    const uint64_t overhang = slots > samples ? slots - samples : 0;
     s->stats.closest_rays -= overhang;
     s->stats.class_rays[SPT_K_TRACE_PATH] -= overhang;
     return SPT_OK;

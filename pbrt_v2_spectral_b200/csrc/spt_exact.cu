@@ -12,7 +12,7 @@ __global__ void __launch_bounds__(256) k_gen_camera(RenderCfg cfg, SampleSource 
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cfg.n_samples; i += gridDim.x * blockDim.x) {
         float ix, iy, lu, lv;
         bool valid = true;
-        const uint32_t cs = cfg.sub > 1 ? i / (uint32_t)cfg.sub : i;         // camera sample of this slot (directlighting: sub slots each)
+        const uint32_t cs = i;
         if (src.smp) {
             const float *s = src.smp + (size_t)src.stride * cs;
             ix = s[0]; iy = s[1]; lu = s[2]; lv = s[3];

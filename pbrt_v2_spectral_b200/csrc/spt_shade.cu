@@ -127,49 +127,54 @@ __global__ void __launch_bounds__(128, 4) k_shade(DevScene sc, RenderCfg cfg, Sa
                                                const uint32_t *queue, const uint32_t *count,
                                                uint32_t *shadow_count, uint32_t *mis_count, uint32_t *elided_count, uint32_t *mis_any_count) {
     uint32_t n = *count;
-    const uint32_t cap = wb.cap;
+    // directlighting (EXT kernels only): a vertex carries `sub` JOBS, one per (light, light sample) of UniformSampleAllLights
+    // (integrator.cpp:39-71); the vertex is set up once and the per-direction part below runs per job, its records and
+    // shadow / MIS rays indexed by r = vertex * sub + job. The path integrator has one job per vertex, r = vertex.
+    const bool direct = EXT && cfg.integrator == SPT_INTEGRATOR_DIRECT_ALL;
+    const uint32_t nj = direct ? (uint32_t)cfg.sub : 1u;
     for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < ((n + 31u) & ~31u); q += gridDim.x * blockDim.x) {
         bool active = q < n;
         uint32_t i = active ? queue[q] : 0;
-        bool pushShadow = false, pushMis = false, pushMisAny = false, elided = false;
+        uint32_t slot = 0, s_idx = 0, pk = 0;
+        Bsdf bsdf;
+        v3 p = V(0, 0, 0), n_s = p, woW = p, wo = p;
+        float eps = 0.f;
+        int emitter = -1;
         if (active) {
-            uint32_t slot = wb.hit_slot[i];
+            slot = wb.hit_slot[i];
             float4 o4 = wb.ray_o[i], d4 = wb.ray_d[i];
             Ray ray;
             ray.o = V(o4.x, o4.y, o4.z); ray.d = V(d4.x, d4.y, d4.z); ray.mint = o4.w; ray.maxt = SPT_INF;
+            Hit hit;
+            shape_record(sc, sc.prim_kind[slot], sc.prim_flags[slot], sc.prim_data[slot], ray, wb.hit_t[i], &hit);
+            // emitted light at the first vertex (path.cpp:55-56, directlighting.cpp:80; Intersection::Le, intersection.cpp:53-56):
+            // K6 starts L from the emitter's spectrum instead of from black
+            if (bounce == 0 || (SPEC && (wb.pflags[i] & 1u))) {
+                int li = sc.prim_light[slot];
+                if (li >= 0 && dot(hit.nn, vneg(ray.d)) > 0.f) emitter = li;
+            }
+            if (EXT) {
+                RayDiff rdiff;
+                const bool camRay = bounce == 0;                 // later rays carry no differentials (path.cpp:93)
+                if (camRay) { float2 xy = wb.img_xy[i]; camera_ray_diff(cfg.cam, xy.x, xy.y, cfg.diff_scale, ray, &rdiff); }
+                make_bsdf<true>(sc, slot, hit, camRay ? &rdiff : nullptr, &bsdf);
+            } else make_bsdf<false>(sc, slot, hit, nullptr, &bsdf);
+            p = hit.p; n_s = bsdf.nn; woW = vneg(ray.d);
+            wo = w2l(bsdf, woW);
+            eps = hit.rayEpsilon;
+            s_idx = src.smp ? 0u : (i & ((uint32_t)cfg.spp - 1u));
+            if (!src.smp) {
+                int px, py;
+                wave_pixel(cfg, cfg.pixel_base + (i >> cfg.spp_shift), &px, &py);
+                pk = pixel_key(src.seed, pix_key(px, py));
+            }
+        }
+        for (uint32_t dj = 0; dj < nj; ++dj) {
+        const uint32_t r = direct ? i * nj + dj : i;
+        bool pushShadow = false, pushMis = false, pushMisAny = false, elided = false;
+        if (active) {
             uint32_t flags = 0;
             {
-                Hit hit;
-                shape_record(sc, sc.prim_kind[slot], sc.prim_flags[slot], sc.prim_data[slot], ray, wb.hit_t[i], &hit);
-                // emitted light at the first vertex (path.cpp:55-56; Intersection::Le, intersection.cpp:53-56):
-                // K6 starts L from the emitter's spectrum instead of from black
-                int emitter = -1;
-                // directlighting (EXT kernels only): slot i is light sample `dj` of camera sample `cs`; the emitted light of
-                // the hit (directlighting.cpp:80) is carried by the first slot alone
-                const bool direct = EXT && cfg.integrator == SPT_INTEGRATOR_DIRECT_ALL;
-                uint32_t cs = i, dj = 0;
-                if (direct && cfg.sub > 1) { cs = i / (uint32_t)cfg.sub; dj = i - cs * (uint32_t)cfg.sub; }
-                if ((bounce == 0 && dj == 0) || (SPEC && (wb.pflags[i] & 1u))) {
-                    int li = sc.prim_light[slot];
-                    if (li >= 0 && dot(hit.nn, vneg(ray.d)) > 0.f) emitter = li;
-                }
-                Bsdf bsdf;
-                if (EXT) {
-                    RayDiff rdiff;
-                    const bool camRay = bounce == 0;                 // later rays carry no differentials (path.cpp:93)
-                    if (camRay) { float2 xy = wb.img_xy[i]; camera_ray_diff(cfg.cam, xy.x, xy.y, cfg.diff_scale, ray, &rdiff); }
-                    make_bsdf<true>(sc, slot, hit, camRay ? &rdiff : nullptr, &bsdf);
-                } else make_bsdf<false>(sc, slot, hit, nullptr, &bsdf);
-                v3 p = hit.p, n_s = bsdf.nn, woW = vneg(ray.d);
-                v3 wo = w2l(bsdf, woW);
-                float eps = hit.rayEpsilon;
-                uint32_t s_idx = src.smp ? 0u : (cs & ((uint32_t)cfg.spp - 1u));
-                uint32_t pk = 0;
-                if (!src.smp) {
-                    int px, py;
-                    wave_pixel(cfg, cfg.pixel_base + (cs >> cfg.spp_shift), &px, &py);
-                    pk = pixel_key(src.seed, pix_key(px, py));
-                }
                 float u[10], rr;
                 int directLight = 0;
                 if (direct) {
@@ -179,7 +184,7 @@ __global__ void __launch_bounds__(128, 4) k_shade(DevScene sc, RenderCfg cfg, Sa
                     }
                     for (int k = 0; k < 10; ++k) u[k] = 0.f;
                     rr = 0.f;
-                    direct_dims(src, cs, pk, s_idx, directLight, prefix, sc.lights[directLight].n_samples, jj, cfg.sub, u);
+                    direct_dims(src, i, pk, s_idx, directLight, prefix, sc.lights[directLight].n_samples, jj, cfg.sub, u);
                 } else bounce_dims(src, i, pk, s_idx, bounce, sc.n_lights > 0, u, &rr);
 
                 float4 g1 = make_float4(0, 0, 0, 0), g2 = g1, g3 = g1, laux = g1;
@@ -297,7 +302,7 @@ __global__ void __launch_bounds__(128, 4) k_shade(DevScene sc, RenderCfg cfg, Sa
                         if (!need) continue;
                         float fv[NB];
                         measured_f(sc, tb, wo, d == 0 ? wl0 : (d == 1 ? wl1 : wl2), fv);
-                        float4 *row = (float4 *)(wb.frow + ((size_t)i * 3 + d) * NB);
+                        float4 *row = (float4 *)(wb.frow + ((size_t)r * 3 + d) * NB);
 #pragma unroll
                         for (int c = 0; c < NB / 4; ++c) row[c] = make_float4(fv[4 * c], fv[4 * c + 1], fv[4 * c + 2], fv[4 * c + 3]);
                     }
@@ -305,27 +310,28 @@ __global__ void __launch_bounds__(128, 4) k_shade(DevScene sc, RenderCfg cfg, Sa
                 if (EXT) {
                     if (mtype == SPT_MAT_SUBSTRATE) {
                         flags |= RF_SUBSTRATE;
-                        wb.rec3[i] = make_float4((flags & RF_L) ? t0.a2 : 0.f, (flags & RF_B) ? t1.a2 : 0.f,
+                        wb.rec3[r] = make_float4((flags & RF_L) ? t0.a2 : 0.f, (flags & RF_B) ? t1.a2 : 0.f,
                                                  ((flags & RF_P) && t2.mf) ? t2.a2 : 0.f, 0.f);
                     }
-                    if (bsdf.texKd) { flags |= RF_TEXKD; wb.rec4[i] = make_float4(bsdf.kd_rgb[0], bsdf.kd_rgb[1], bsdf.kd_rgb[2], 0.f); }
+                    if (bsdf.texKd) { flags |= RF_TEXKD; wb.rec4[r] = make_float4(bsdf.kd_rgb[0], bsdf.kd_rgb[1], bsdf.kd_rgb[2], 0.f); }
                 }
-                wb.g0[i] = make_float4(p.x, p.y, p.z, eps);
-                if (pushShadow) wb.g1[i] = g1;
-                if (pushMis || pushMisAny) wb.g2[i] = g2;
+                wb.g0[r] = make_float4(p.x, p.y, p.z, eps);
+                if (pushShadow) wb.g1[r] = g1;
+                if (pushMis || pushMisAny) wb.g2[r] = g2;
                 if (flags & RF_P) wb.g3[i] = g3;
-                wb.rec0[i] = make_float4(cL.x, cL.y, cB.x, cB.y);
-                wb.rec1[i] = make_float4(cP.x, cP.y, sL, sB);
-                wb.rec2[i] = make_float4(sP, rr, __uint_as_float(flags | (uint32_t)lightIdx << 12),
-                                         __uint_as_float((uint32_t)sc.prim_material[slot] | (uint32_t)(emitter + 1) << 16));
-                if (pushShadow && sc.lights[lightIdx].type == SPT_LIGHT_INFINITE) wb.laux[i] = laux;
+                wb.rec0[r] = make_float4(cL.x, cL.y, cB.x, cB.y);
+                wb.rec1[r] = make_float4(cP.x, cP.y, sL, sB);
+                wb.rec2[r] = make_float4(sP, rr, __uint_as_float(flags | (uint32_t)lightIdx << 12),
+                                         __uint_as_float((uint32_t)sc.prim_material[slot] | (uint32_t)(dj == 0 ? emitter + 1 : 0) << 16));
+                if (pushShadow && sc.lights[lightIdx].type == SPT_LIGHT_INFINITE) wb.laux[r] = laux;
             }
         }
-        queue_push(wb.shadowQ, shadow_count, pushShadow, i);
-        queue_push(wb.misQ, mis_count, pushMis, i);
-        queue_push(wb.misAnyQ, mis_any_count, pushMisAny, i);
+        queue_push(wb.shadowQ, shadow_count, pushShadow, r);
+        queue_push(wb.misQ, mis_count, pushMis, r);
+        queue_push(wb.misAnyQ, mis_any_count, pushMisAny, r);
         unsigned em = __ballot_sync(0xffffffffu, elided);
         if (em && (threadIdx.x & 31) == 0) atomicAdd(elided_count, (uint32_t)__popc(em));
+        }
     }
 }
 
@@ -430,10 +436,8 @@ __global__ void __launch_bounds__(32 * ACC_WARPS, 8) k_accumulate(DevScene sc, R
             }
             const bool haveP = (flags & RF_P) != 0;
             specBounce = (flags & RF_P_SPEC) != 0;
-            // UniformSampleOneLight scales by the light count (integrator.cpp:105); UniformSampleAllLights averages a light's
-            // n_samples estimates (integrator.cpp:68)
-            const float lscale = (EXT && cfg.integrator == SPT_INTEGRATOR_DIRECT_ALL) ? 1.f / (float)sc.lights[lightIdx].n_samples : nL;
-            sL *= lscale; sB *= lscale;
+            // UniformSampleOneLight scales by the light count (integrator.cpp:105)
+            sL *= nL; sB *= nL;
             stage[lane][0] = make_float4(cL.x, cL.y, cB.x, cB.y);
             stage[lane][1] = make_float4(cP.x, cP.y, sL, sB);
             stage[lane][2] = make_float4(haveP ? c2.x : 0.f, c2.y, __uint_as_float(i),
@@ -572,6 +576,99 @@ __global__ void __launch_bounds__(32 * ACC_WARPS, 8) k_accumulate(DevScene sc, R
         }
         queue_push(next_queue, next_count, alive, i);
         __syncwarp();
+    }
+}
+
+// ---- K6, directlighting ---------------------------------------------------------------------------
+// DirectLightingIntegrator::Li after the hit (directlighting.cpp:80-96): L = Le + sum over lights of (sum of the light's
+// n_samples EstimateDirect values) / n_samples (integrator.cpp:39-71). One warp per camera hit, lane = band: the vertex's
+// material row is read once, each job's 48-byte record, shadow-ray verdict and MIS hit are warp-uniform loads, and the
+// radiance row is written once - no throughput, no continuation.
+__global__ void __launch_bounds__(128, 8) k_accumulate_direct(DevScene sc, RenderCfg cfg, WaveBuffers wb,
+                                                              const uint32_t *__restrict__ queue, const uint32_t *__restrict__ count) {
+    const uint32_t n = *count;
+    const SptSpectralTables &tb = *sc.tables;
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t sub = (uint32_t)cfg.sub;
+    for (uint32_t h = warp; h < n; h += nwarps) {
+        const uint32_t i = queue[h];
+        const uint32_t r0 = i * sub;
+        const uint32_t bits1 = __float_as_uint(wb.rec2[r0].w);
+        const SptMaterial &m = sc.materials[bits1 & 0xffffu];
+        const uint32_t emit = bits1 >> 16;
+        float L = emit ? __ldg(sc.lights[emit - 1].spectrum + lane) : 0.f;
+        float s0 = __ldg(m.spec0 + lane);
+        const float s1 = __ldg(m.spec1 + lane);
+        float Ld = 0.f;
+        int curLight = -1;
+        for (uint32_t j = 0; j < sub; ++j) {
+            const uint32_t r = r0 + j;
+            const float4 c0 = wb.rec0[r], c1 = wb.rec1[r], c2 = wb.rec2[r];
+            const uint32_t bits0 = __float_as_uint(c2.z);
+            const uint32_t flags = bits0 & 0xfffu;
+            const int lightIdx = (int)(bits0 >> 12);
+            if (lightIdx != curLight) {
+                if (curLight >= 0) L += Ld / (float)sc.lights[curLight].n_samples;
+                Ld = 0.f; curLight = lightIdx;
+            }
+            const SptLight &l = sc.lights[lightIdx];
+            // which terms survive (warp-uniform): the light sample if its shadow ray found nothing (integrator.cpp:122-137),
+            // the BSDF sample by what its ray found (:139-163)
+            const bool haveL = (flags & RF_L) && wb.sh_slot[r] == SPT_MISS;
+            int kindB = 0;
+            float rgbB[3] = { 0.f, 0.f, 0.f };
+            if (flags & RF_B) {
+                const float4 g0 = wb.g0[r], g2 = wb.g2[r];
+                const uint32_t ms = wb.mis_slot[r];
+                const v3 wi = V(g2.x, g2.y, g2.z);
+                if (ms != SPT_MISS) {
+                    if (sc.prim_light[ms] == lightIdx) {
+                        Ray ray; ray.o = V(g0.x, g0.y, g0.z); ray.d = wi; ray.mint = g0.w; ray.maxt = SPT_INF;
+                        Hit hh;
+                        shape_record(sc, sc.prim_kind[ms], sc.prim_flags[ms], sc.prim_data[ms], ray, wb.mis_t[r], &hh);
+                        if (dot(hh.nn, vneg(wi)) > 0.f) kindB = 1;
+                    }
+                } else if (l.type == SPT_LIGHT_INFINITE) { infinite_le_rgb(sc, l, wi, rgbB); kindB = 2; }
+            }
+            if (!haveL && !kindB) continue;
+            if ((flags & RF_TEXKD) && j == 0) {                       // the image-mapped Kd is a property of the vertex
+                const float4 r4 = wb.rec4[r];
+                const float rgb[3] = { r4.x, r4.y, r4.z };
+                s0 = refl_band(tb, illum_coefs(rgb), lane);
+            }
+            const float2 cL = haveL ? make_float2(c0.x, c0.y) : make_float2(0.f, (flags & RF_METAL) ? 1.f : 0.f);
+            const float2 cB = kindB ? make_float2(c0.z, c0.w) : make_float2(0.f, (flags & RF_METAL) ? 1.f : 0.f);
+            float fL, fB;
+            if (flags & RF_MEASURED) {
+                const float *fr = wb.frow + (size_t)r * 3 * NB + lane;
+                fL = cL.x != 0.f ? fr[0] : 0.f;
+                fB = cB.x != 0.f ? fr[NB] : 0.f;
+            } else if (flags & RF_SUBSTRATE) {
+                const float4 e3 = wb.rec3[r];
+                const float oms = 1.f - s1, dR = s0 * oms;
+                fL = dR * cL.x + (s1 + oms * e3.x) * cL.y;
+                fB = dR * cB.x + (s1 + oms * e3.y) * cB.y;
+            } else if (flags & RF_METAL) {
+                fL = cL.x != 0.f ? cL.x * fr_cond_fast(cL.y, cL.y * cL.y, s0, s1) : 0.f;
+                fB = cB.x != 0.f ? cB.x * fr_cond_fast(cB.y, cB.y * cB.y, s0, s1) : 0.f;
+            } else {
+                fL = fmaf(s0, cL.x, s1 * cL.y);
+                fB = fmaf(s0, cB.x, s1 * cB.y);
+            }
+            // radiance arriving along the two directions: the light's table row, or an RGB illuminant (infinite light)
+            float LcL = 0.f, LcB = 0.f;
+            if (l.type == SPT_LIGHT_INFINITE) {
+                if (haveL) { const float4 la = wb.laux[r]; const float rgb[3] = { la.x, la.y, la.z }; LcL = illum_band(tb, illum_coefs(rgb), lane); }
+                if (kindB == 2) LcB = illum_band(tb, illum_coefs(rgbB), lane);
+            } else {
+                const float row = __ldg(l.spectrum + lane);
+                LcL = row; LcB = row;
+            }
+            Ld += fL * LcL * (haveL ? c1.z : 0.f) + fB * LcB * (kindB ? c1.w : 0.f);
+        }
+        if (curLight >= 0) L += Ld / (float)sc.lights[curLight].n_samples;
+        wb.L[band_off(i, lane)] = L;
     }
 }
 
@@ -750,7 +847,8 @@ void spt_launch_shade(int grid, cudaStream_t st, const DevScene &sc, const Rende
 }
 void spt_launch_accumulate(int grid, cudaStream_t st, const DevScene &sc, const RenderCfg &cfg, const WaveBuffers &wb, int bounce,
                            const uint32_t *queue, const uint32_t *count, uint32_t *next_queue, uint32_t *next_count) {
-    if (sc.has_ext || cfg.integrator != SPT_INTEGRATOR_PATH) k_accumulate<true><<<grid, 128, 0, st>>>(sc, cfg, wb, bounce, queue, count, next_queue, next_count);
+    if (cfg.integrator == SPT_INTEGRATOR_DIRECT_ALL) k_accumulate_direct<<<grid, 128, 0, st>>>(sc, cfg, wb, queue, count);
+    else if (sc.has_ext) k_accumulate<true><<<grid, 128, 0, st>>>(sc, cfg, wb, bounce, queue, count, next_queue, next_count);
     else k_accumulate<false><<<grid, 128, 0, st>>>(sc, cfg, wb, bounce, queue, count, next_queue, next_count);
 }
 void spt_launch_film_add(int grid, cudaStream_t st, const FilmView &film, const SptSpectralTables *tables, const float2 *img_xy,

@@ -19,7 +19,9 @@
 #include "spt_device.cuh"
 
 struct WaveBuffers {
-    uint32_t cap;
+    uint32_t cap;                     // paths
+    uint32_t jcap;                    // jobs = cap x jobs per path vertex (1; under directlighting the sum of the lights' n_samples):
+                                      // g0..g2, the K5->K6 records, shadow / MIS ray results and their queues are per job
     float4 *ray_o, *ray_d;            // path rays: {o, mint}, {d, maxt}
     uint32_t *hit_slot; float *hit_t;
     float4 *g0, *g1, *g2, *g3;        // {p, eps}, {shadow d, shadow maxt}, {mis d, inf}, {path d, -}
@@ -60,8 +62,8 @@ struct RenderCfg {
     uint64_t pixel_base;              // first rank-local pixel of this wave
     uint32_t n_samples;               // samples in this wave
     int integrator;                   // SPT_INTEGRATOR_*
-    int sub;                          // slots per camera sample: 1, or under directlighting the sum of the lights' n_samples -
-                                      // slot i = light sample (i % sub) of camera sample (i / sub), each with its own copy of the camera ray
+    int sub;                          // jobs per path vertex: 1, or under directlighting the sum of the lights' n_samples -
+                                      // job r = vertex * sub + j is light sample j of UniformSampleAllLights
     float diff_scale;                 // 1/sqrt(samplesPerPixel): RayDifferential::ScaleDifferentials (samplerrenderer.cpp:91)
 };
 
