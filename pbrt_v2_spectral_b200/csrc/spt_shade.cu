@@ -581,94 +581,124 @@ __global__ void __launch_bounds__(32 * ACC_WARPS, 8) k_accumulate(DevScene sc, R
 
 // ---- K6, directlighting ---------------------------------------------------------------------------
 // DirectLightingIntegrator::Li after the hit (directlighting.cpp:80-96): L = Le + sum over lights of (sum of the light's
-// n_samples EstimateDirect values) / n_samples (integrator.cpp:39-71). One warp per camera hit, lane = band: the vertex's
-// material row is read once, each job's 48-byte record, shadow-ray verdict and MIS hit are warp-uniform loads, and the
-// radiance row is written once - no throughput, no continuation.
-__global__ void __launch_bounds__(128, 8) k_accumulate_direct(DevScene sc, RenderCfg cfg, WaveBuffers wb,
-                                                              const uint32_t *__restrict__ queue, const uint32_t *__restrict__ count) {
+// n_samples EstimateDirect values) / n_samples (integrator.cpp:39-71). A warp takes floor(32 / sub) camera hits = up to 32
+// jobs per batch. Phase A, lane = job: which terms survived the shadow / MIS rays, folded to three staged float4 per job
+// (coefficients of the light-sample and BSDF-sample directions, their scales - already divided by n_samples - and what
+// radiance arrives). Phase B, lane = band: per hit the material row is read once, its jobs' staged values are shared-memory
+// broadcasts, and the radiance row is written once - no throughput, no continuation.
+#define ACCD_WARPS 4
+__global__ void __launch_bounds__(32 * ACCD_WARPS, 8) k_accumulate_direct(DevScene sc, RenderCfg cfg, WaveBuffers wb,
+                                                                       const uint32_t *__restrict__ queue, const uint32_t *__restrict__ count) {
+    __shared__ float4 stage_all[ACCD_WARPS][32][4];
     const uint32_t n = *count;
     const SptSpectralTables &tb = *sc.tables;
-    const int lane = threadIdx.x & 31;
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4 (*stage)[4] = stage_all[warp];
     const uint32_t sub = (uint32_t)cfg.sub;
-    for (uint32_t h = warp; h < n; h += nwarps) {
-        const uint32_t i = queue[h];
-        const uint32_t r0 = i * sub;
-        const uint32_t bits1 = __float_as_uint(wb.rec2[r0].w);
-        const SptMaterial &m = sc.materials[bits1 & 0xffffu];
-        const uint32_t emit = bits1 >> 16;
-        float L = emit ? __ldg(sc.lights[emit - 1].spectrum + lane) : 0.f;
-        float s0 = __ldg(m.spec0 + lane);
-        const float s1 = __ldg(m.spec1 + lane);
-        float Ld = 0.f;
-        int curLight = -1;
-        for (uint32_t j = 0; j < sub; ++j) {
-            const uint32_t r = r0 + j;
-            const float4 c0 = wb.rec0[r], c1 = wb.rec1[r], c2 = wb.rec2[r];
-            const uint32_t bits0 = __float_as_uint(c2.z);
-            const uint32_t flags = bits0 & 0xfffu;
-            const int lightIdx = (int)(bits0 >> 12);
-            if (lightIdx != curLight) {
-                if (curLight >= 0) L += Ld / (float)sc.lights[curLight].n_samples;
-                Ld = 0.f; curLight = lightIdx;
-            }
-            const SptLight &l = sc.lights[lightIdx];
-            // which terms survive (warp-uniform): the light sample if its shadow ray found nothing (integrator.cpp:122-137),
-            // the BSDF sample by what its ray found (:139-163)
-            const bool haveL = (flags & RF_L) && wb.sh_slot[r] == SPT_MISS;
-            int kindB = 0;
-            float rgbB[3] = { 0.f, 0.f, 0.f };
-            if (flags & RF_B) {
-                const float4 g0 = wb.g0[r], g2 = wb.g2[r];
-                const uint32_t ms = wb.mis_slot[r];
-                const v3 wi = V(g2.x, g2.y, g2.z);
-                if (ms != SPT_MISS) {
-                    if (sc.prim_light[ms] == lightIdx) {
-                        Ray ray; ray.o = V(g0.x, g0.y, g0.z); ray.d = wi; ray.mint = g0.w; ray.maxt = SPT_INF;
-                        Hit hh;
-                        shape_record(sc, sc.prim_kind[ms], sc.prim_flags[ms], sc.prim_data[ms], ray, wb.mis_t[r], &hh);
-                        if (dot(hh.nn, vneg(wi)) > 0.f) kindB = 1;
+    const uint32_t H = sub <= 32u ? 32u / sub : 1u;                  // hits per batch; sub > 32: one hit, jobs in rounds of 32
+    const uint32_t gw = blockIdx.x * ACCD_WARPS + warp, nwarps = gridDim.x * ACCD_WARPS;
+    for (uint32_t h0 = gw * H; h0 < n; h0 += nwarps * H) {
+        const uint32_t nh = min(H, n - h0);
+        float Lacc = 0.f;                                            // sub > 32 only: the hit's sum across rounds
+        for (uint32_t j0 = 0; j0 < sub; j0 += 32u) {                 // one round unless sub > 32
+            // ---- phase A: lane = job
+            const uint32_t hl = sub <= 32u ? (uint32_t)lane / sub : 0u;                  // hit of this lane within the batch
+            const uint32_t j = sub <= 32u ? (uint32_t)lane - hl * sub : j0 + (uint32_t)lane;
+            const bool jobLane = hl < nh && j < sub;
+            if (jobLane) {
+                const uint32_t i = queue[h0 + hl];
+                const uint32_t r = i * sub + j;
+                const float4 c0 = wb.rec0[r], c1 = wb.rec1[r], c2 = wb.rec2[r];
+                const uint32_t bits0 = __float_as_uint(c2.z);
+                const uint32_t flags = bits0 & 0xfffu;
+                const int lightIdx = (int)(bits0 >> 12);
+                const SptLight &l = sc.lights[lightIdx];
+                const float inv = 1.f / (float)l.n_samples;
+                const float2 none = make_float2(0.f, (flags & RF_METAL) ? 1.f : 0.f);
+                float2 cL = none, cB = none;
+                float sL = 0.f, sB = 0.f;
+                uint32_t kindL = 0, kindB = 0;                        // 0 none, 1 the light's table spectrum, 2 RGB illuminant
+                float4 rgbL = make_float4(0, 0, 0, 0), rgbB = rgbL;
+                if ((flags & RF_L) && wb.sh_slot[r] == SPT_MISS) {    // integrator.cpp:122-137
+                    cL = make_float2(c0.x, c0.y); sL = c1.z * inv;
+                    if (l.type == SPT_LIGHT_INFINITE) { rgbL = wb.laux[r]; kindL = 2; } else kindL = 1;
+                }
+                if (flags & RF_B) {                                   // integrator.cpp:139-163
+                    const float4 g0 = wb.g0[r], g2 = wb.g2[r];
+                    const uint32_t ms = wb.mis_slot[r];
+                    const v3 wi = V(g2.x, g2.y, g2.z);
+                    if (ms != SPT_MISS) {
+                        if (sc.prim_light[ms] == lightIdx) {
+                            Ray ray; ray.o = V(g0.x, g0.y, g0.z); ray.d = wi; ray.mint = g0.w; ray.maxt = SPT_INF;
+                            Hit hh;
+                            shape_record(sc, sc.prim_kind[ms], sc.prim_flags[ms], sc.prim_data[ms], ray, wb.mis_t[r], &hh);
+                            if (dot(hh.nn, vneg(wi)) > 0.f) kindB = 1;
+                        }
+                    } else if (l.type == SPT_LIGHT_INFINITE) {
+                        float rgb[3];
+                        infinite_le_rgb(sc, l, wi, rgb);
+                        rgbB = make_float4(rgb[0], rgb[1], rgb[2], 0.f); kindB = 2;
                     }
-                } else if (l.type == SPT_LIGHT_INFINITE) { infinite_le_rgb(sc, l, wi, rgbB); kindB = 2; }
+                    if (kindB) { cB = make_float2(c0.z, c0.w); sB = c1.w * inv; }
+                }
+                stage[lane][0] = make_float4(cL.x, cL.y, cB.x, cB.y);
+                stage[lane][1] = make_float4(sL, sB, __uint_as_float(flags | kindL << 12 | kindB << 14 | (uint32_t)lightIdx << 16), 0.f);
+                stage[lane][2] = rgbL;
+                stage[lane][3] = rgbB;
             }
-            if (!haveL && !kindB) continue;
-            if ((flags & RF_TEXKD) && j == 0) {                       // the image-mapped Kd is a property of the vertex
-                const float4 r4 = wb.rec4[r];
-                const float rgb[3] = { r4.x, r4.y, r4.z };
-                s0 = refl_band(tb, illum_coefs(rgb), lane);
+            __syncwarp();
+            // ---- phase B: lane = band
+            for (uint32_t hh = 0; hh < nh; ++hh) {
+                const uint32_t i = queue[h0 + hh];
+                const uint32_t r0 = i * sub;
+                const uint32_t bits1 = __float_as_uint(wb.rec2[r0].w);
+                const SptMaterial &m = sc.materials[bits1 & 0xffffu];
+                float s0 = __ldg(m.spec0 + lane);
+                const float s1 = __ldg(m.spec1 + lane);
+                float L = 0.f;
+                if (j0 == 0) { const uint32_t emit = bits1 >> 16; L = emit ? __ldg(sc.lights[emit - 1].spectrum + lane) : 0.f; }
+                const uint32_t jn = sub <= 32u ? sub : min(32u, sub - j0);
+                if (__float_as_uint(stage[sub <= 32u ? hh * sub : 0u][1].z) & RF_TEXKD) {      // the image-mapped Kd is a property of the vertex
+                    const float4 r4 = wb.rec4[r0];
+                    const float rgb[3] = { r4.x, r4.y, r4.z };
+                    s0 = refl_band(tb, illum_coefs(rgb), lane);
+                }
+                for (uint32_t jj = 0; jj < jn; ++jj) {
+                    const uint32_t sl = sub <= 32u ? hh * sub + jj : jj;
+                    const float4 cLB = stage[sl][0], sc4 = stage[sl][1];
+                    const uint32_t bits = __float_as_uint(sc4.z);
+                    const uint32_t kindL = (bits >> 12) & 3u, kindB = (bits >> 14) & 3u;
+                    if (!(kindL | kindB)) continue;
+                    const uint32_t r = r0 + (sub <= 32u ? jj : j0 + jj);
+                    float fL, fB;
+                    if (bits & RF_MEASURED) {
+                        const float *fr = wb.frow + (size_t)r * 3 * NB + lane;
+                        fL = cLB.x != 0.f ? fr[0] : 0.f;
+                        fB = cLB.z != 0.f ? fr[NB] : 0.f;
+                    } else if (bits & RF_SUBSTRATE) {
+                        const float4 e3 = wb.rec3[r];
+                        const float oms = 1.f - s1, dR = s0 * oms;
+                        fL = dR * cLB.x + (s1 + oms * e3.x) * cLB.y;
+                        fB = dR * cLB.z + (s1 + oms * e3.y) * cLB.w;
+                    } else if (bits & RF_METAL) {
+                        fL = cLB.x != 0.f ? cLB.x * fr_cond_fast(cLB.y, cLB.y * cLB.y, s0, s1) : 0.f;
+                        fB = cLB.z != 0.f ? cLB.z * fr_cond_fast(cLB.w, cLB.w * cLB.w, s0, s1) : 0.f;
+                    } else {
+                        fL = fmaf(s0, cLB.x, s1 * cLB.y);
+                        fB = fmaf(s0, cLB.z, s1 * cLB.w);
+                    }
+                    float LcL = 0.f, LcB = 0.f;
+                    if ((kindL | kindB) & 2u) {
+                        if (kindL == 2u) { const float4 q = stage[sl][2]; const float rgb[3] = { q.x, q.y, q.z }; LcL = illum_band(tb, illum_coefs(rgb), lane); }
+                        if (kindB == 2u) { const float4 q = stage[sl][3]; const float rgb[3] = { q.x, q.y, q.z }; LcB = illum_band(tb, illum_coefs(rgb), lane); }
+                    } else LcL = LcB = __ldg(sc.lights[bits >> 16].spectrum + lane);
+                    L += fL * LcL * sc4.x + fB * LcB * sc4.y;
+                }
+                if (sub <= 32u) wb.L[band_off(i, lane)] = L; else Lacc += L;
             }
-            const float2 cL = haveL ? make_float2(c0.x, c0.y) : make_float2(0.f, (flags & RF_METAL) ? 1.f : 0.f);
-            const float2 cB = kindB ? make_float2(c0.z, c0.w) : make_float2(0.f, (flags & RF_METAL) ? 1.f : 0.f);
-            float fL, fB;
-            if (flags & RF_MEASURED) {
-                const float *fr = wb.frow + (size_t)r * 3 * NB + lane;
-                fL = cL.x != 0.f ? fr[0] : 0.f;
-                fB = cB.x != 0.f ? fr[NB] : 0.f;
-            } else if (flags & RF_SUBSTRATE) {
-                const float4 e3 = wb.rec3[r];
-                const float oms = 1.f - s1, dR = s0 * oms;
-                fL = dR * cL.x + (s1 + oms * e3.x) * cL.y;
-                fB = dR * cB.x + (s1 + oms * e3.y) * cB.y;
-            } else if (flags & RF_METAL) {
-                fL = cL.x != 0.f ? cL.x * fr_cond_fast(cL.y, cL.y * cL.y, s0, s1) : 0.f;
-                fB = cB.x != 0.f ? cB.x * fr_cond_fast(cB.y, cB.y * cB.y, s0, s1) : 0.f;
-            } else {
-                fL = fmaf(s0, cL.x, s1 * cL.y);
-                fB = fmaf(s0, cB.x, s1 * cB.y);
-            }
-            // radiance arriving along the two directions: the light's table row, or an RGB illuminant (infinite light)
-            float LcL = 0.f, LcB = 0.f;
-            if (l.type == SPT_LIGHT_INFINITE) {
-                if (haveL) { const float4 la = wb.laux[r]; const float rgb[3] = { la.x, la.y, la.z }; LcL = illum_band(tb, illum_coefs(rgb), lane); }
-                if (kindB == 2) LcB = illum_band(tb, illum_coefs(rgbB), lane);
-            } else {
-                const float row = __ldg(l.spectrum + lane);
-                LcL = row; LcB = row;
-            }
-            Ld += fL * LcL * (haveL ? c1.z : 0.f) + fB * LcB * (kindB ? c1.w : 0.f);
+            __syncwarp();
         }
-        if (curLight >= 0) L += Ld / (float)sc.lights[curLight].n_samples;
-        wb.L[band_off(i, lane)] = L;
+        if (sub > 32u) wb.L[band_off(queue[h0], lane)] = Lacc;
     }
 }
 
