@@ -19,7 +19,7 @@ for r in rows[2:]:
     elif "k_accumulate" in name.split("(")[0]: cls = "accumulate"
     if not cls: continue
     b = float(r[ri]) * scale[units[ri]] + float(r[wi]) * scale[units[wi]]
-    if float(r[ti]) < 0.5 and cls.startswith("trace"): continue      # the near-empty MIS launches
+    if float(r[ti]) < 0.5: continue      # near-empty launches (MIS queues, the last bounce of the previous frame)
     acc.setdefault(cls, []).append(b)
 res = {k: sum(v) / len(v) for k, v in acc.items()}
 res["_source"] = os.path.basename(sys.argv[1]) + ": mean over the captured launches (bounces 0-1 of one frame), dram__bytes_read.sum + dram__bytes_write.sum"
