@@ -260,16 +260,32 @@ def main():
     e1 = torch.cuda.Event(enable_timing=True)
     render_ms = 0.0
     lanes_used = 1
+    # N > 1: two film buffers, so that the exchange of frame k (torch's stream: gather over NCCL + adds on rank 0) runs while
+    # frame k+1 renders (the library's streams). The next film is zeroed on torch's stream BEHIND the previous use of that
+    # buffer (the exchange of frame k-1) and the host waits for that one event only before it renders into it.
+    films_t = [film_t, torch.zeros_like(film_t)] if world > 1 else [film_t]
+    films = [film] + ([capi.Film(fd, films_t[1].data_ptr())] if world > 1 else [])
+    zeroed = torch.cuda.Event()
+    films_t[0].zero_()
+    barrier()
     e0.record()
-    for _ in range(args.steps):
-        film_t.zero_()
-        scene.render(film, rp)                       # blocks until the library's streams have drained
-        exchange.run(film_t, rank)                    # N > 1: the film is summed onto rank 0 over NVLink (NCCL)
+    for k in range(args.steps):
+        cur = k % len(films)
+        if world == 1:
+            films_t[0].zero_()
+        scene.render(films[cur], rp)                 # blocks until the library's streams have drained
+        if world > 1:
+            films_t[(k + 1) % 2].zero_()
+            zeroed.record()
+            exchange.run(films_t[cur], rank)         # the ranks' film pixels gathered onto rank 0 over NVLink (NCCL) and added there
+            zeroed.synchronize()
         st = scene.stats()
         render_ms += st["render_ms"]
         lanes_used = st["lanes_used"]
     e1.record()
     barrier()
+    for f in films[1:]:
+        f.close()
     if sampler:
         sampler.stop_flag = True
         sampler.join()
@@ -402,7 +418,8 @@ def main():
                 else "synthetic scene written as .pbrt text, parsed, BVH-built and lowered by the reference's own code (oracle/make_golden.py)",
         "config": {"workload": workload_desc, "camera_samples_per_step": n_samples_total,
                    "parallelism": "image tile sets (32x32, round-robin) x%d, scene replicated, film pixels of each rank's tiles gathered to rank 0 over NCCL and added" % world,
-                   "l2": "per-step wave state (>2 GB) and film are larger than L2; no explicit flush"},
+                   "l2": "per-step wave state (>2 GB) and film are larger than L2; no explicit flush",
+                   "pipelining": "N > 1: the film exchange of frame k overlaps the render of frame k+1 (two film buffers); all work completes inside the timed region"},
         "mrays_per_s": rays_total / prof_steps / (ms_per_step / 1e3) / 1e6 if world == 1 else None,
         "rays_per_sample": rays_total / prof_steps / (n_samples_total / world) if world else None,
         "rays_per_sample_reference": (rays_total + elided) / prof_steps / (n_samples_total / world) if world else None,
