@@ -296,6 +296,8 @@ void      spt_scene_destroy(SptScene *scene);
 int       spt_scene_set_lanes(SptScene *scene, int lanes);
 int       spt_scene_enable_counters(SptScene *scene, int on);
 int       spt_get_stats(SptScene *scene, SptStats *out);
+/* SptStats::render_ms of the last spt_render alone (spt_get_stats also folds ~80 per-launch event deltas into class_ms). */
+double    spt_last_render_ms(SptScene *scene);
 
 /* K1: PerspectiveCamera::GenerateRayDifferential (src/cameras/perspective.cpp:73-106).
  * samples: n x 5 floats {imageX, imageY, lensU, lensV, time}; out_rays: n x 8 {o, d, mint, maxt}. */

@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("SPT_LIB") or os.path.join(HERE, "libspt.so")   # SPT_
 # every symbol include/spt.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "spt_nbands", "spt_last_error", "spt_device_count", "spt_set_device", "spt_host_alloc", "spt_host_free", "spt_trim",
-    "spt_scene_create", "spt_scene_destroy", "spt_scene_enable_counters", "spt_scene_set_lanes", "spt_get_stats",
+    "spt_scene_create", "spt_scene_destroy", "spt_scene_enable_counters", "spt_scene_set_lanes", "spt_get_stats", "spt_last_render_ms",
     "spt_camera_rays", "spt_trace_closest", "spt_trace_any", "spt_trace_closest_dev", "spt_trace_any_dev",
     "spt_shade_samples",
     "spt_film_create", "spt_film_create_external", "spt_film_destroy", "spt_film_clear",
@@ -48,6 +48,8 @@ def lib():
         L.spt_scene_enable_counters.argtypes = [C.c_void_p, C.c_int]
         L.spt_scene_set_lanes.argtypes = [C.c_void_p, C.c_int]
         L.spt_get_stats.argtypes = [C.c_void_p, C.POINTER(D.SptStats)]
+        L.spt_last_render_ms.restype = C.c_double
+        L.spt_last_render_ms.argtypes = [C.c_void_p]
         L.spt_camera_rays.argtypes = [C.POINTER(D.SptCameraDesc), C.c_void_p, C.c_uint64, C.c_void_p]
         L.spt_trace_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.spt_trace_any.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
@@ -144,6 +146,10 @@ class Scene:
 
     def set_lanes(self, lanes):
         _check(lib().spt_scene_set_lanes(self.h, int(lanes)))
+
+    def render_ms(self):
+        """Device time of the last spt_render (first launch -> film final), without folding the per-kernel times."""
+        return float(lib().spt_last_render_ms(self.h))
 
     def stats(self):
         st = D.SptStats()

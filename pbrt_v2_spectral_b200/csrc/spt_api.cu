@@ -13,6 +13,8 @@
 #include <vector>
 #include "launch.h"
 
+struct SptScene;
+static void collect_class_times(SptScene *s);
 static thread_local std::string g_err;
 static int fail(int code, const std::string &msg) { g_err = msg; return code; }
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
@@ -119,6 +121,7 @@ struct SptScene {
     cudaStream_t stream = nullptr;   // = lane[0].stream
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     SptStats stats{};
+    bool class_times_pending = false;    // the per-launch event deltas of the last render are folded into stats.class_ms on demand
     uint64_t launches = 0;
     // per-launch timing: an event after every launch of a render, attributed to the launch's class;
     // deltas are taken between consecutive events of the same lane
@@ -396,6 +399,8 @@ int spt_scene_set_lanes(SptScene *s, int lanes) {
     return SPT_OK;
 }
 
+double spt_last_render_ms(SptScene *s) { return s ? s->stats.render_ms : 0.0; }
+
 int spt_get_stats(SptScene *s, SptStats *out) {
     if (!s || !out) return fail(SPT_ERR_ARG, "null argument");
     if (s->counters_on) {
@@ -404,6 +409,7 @@ int spt_get_stats(SptScene *s, SptStats *out) {
         s->stats.node_visits_closest = c[0]; s->stats.prim_tests_closest = c[1];
         s->stats.node_visits_any = c[2]; s->stats.prim_tests_any = c[3];
     }
+    if (s->class_times_pending) collect_class_times(s);
     s->stats.kernel_launches = s->launches;
     *out = s->stats;
     return SPT_OK;
@@ -510,6 +516,7 @@ static void run_wave(SptScene *s, const RenderCfg &cfg, const SampleSource &src,
 
 // after the stream has drained: fold the per-launch event deltas into stats.class_ms
 static void collect_class_times(SptScene *s) {
+    s->class_times_pending = false;
     cudaEvent_t last[SPT_MAX_LANES] = {};
     for (size_t k = 0; k < s->ev_used; ++k) {
         const SptScene::Mark &m = s->marks[k];
@@ -522,6 +529,7 @@ static void collect_class_times(SptScene *s) {
     s->ev_used = 0;
 }
 static void reset_class_stats(SptScene *s) {
+    s->class_times_pending = false;
     for (int k = 0; k < SPT_K_CLASSES; ++k) { s->stats.class_ms[k] = 0.; s->stats.class_launches[k] = 0; s->stats.class_rays[k] = 0; }
     s->stats.mis_rays_elided = 0; s->stats.first_vertices = 0;
     s->ev_used = 0;
@@ -697,7 +705,7 @@ int spt_shade_samples(SptScene *s, const SptCameraDesc *cam, int32_t integrator,
     if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
     m.release();
     if (e != cudaSuccess) return fail(SPT_ERR_CUDA, cudaGetErrorString(e));
-    collect_class_times(s);
+    s->class_times_pending = true;
     s->stats.camera_samples += n;
     add_ray_stats(s, hc, max_depth, 1);
     return SPT_OK;
@@ -899,7 +907,7 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
     float ms = 0.f;
     cudaEventElapsedTime(&ms, s->ev0, s->ev1);
     s->stats.render_ms = ms;
-    collect_class_times(s);
+    s->class_times_pending = true;          // ~80 cudaEventElapsedTime calls: only when spt_get_stats asks (not between frames)
     // sample slots of tiles that overhang the sample extent carry rays that cannot hit anything: not samples
     uint64_t slots = 0, valid_pixels = 0;
     for (size_t w = 0; w < n_waves; ++w) slots += hc[w * per_wave];
