@@ -17,16 +17,16 @@ void spt_launch_slot_to_flag(cudaStream_t st, const uint32_t *slot, uint32_t n, 
 
 void spt_launch_compact_hits(int grid, cudaStream_t st, const uint32_t *queue, const uint32_t *count, const uint32_t *hit_slot,
                              uint32_t *hit_queue, uint32_t *hit_count, uint32_t *miss_queue, uint32_t *miss_count, float *black_L);
-void spt_launch_miss_env(int grid, cudaStream_t st, const DevScene &sc, const WaveBuffers &wb, int bounce, const uint32_t *queue, const uint32_t *count, int sub);
+void spt_launch_miss_env(int grid, cudaStream_t st, const DevScene &sc, const WaveBuffers &wb, int bounce, const uint32_t *queue, const uint32_t *count);
 void spt_launch_shade(int grid, cudaStream_t st, const DevScene &sc, const RenderCfg &cfg, const SampleSource &src, const WaveBuffers &wb,
                       int bounce, const uint32_t *queue, const uint32_t *count, uint32_t *shadow_count, uint32_t *mis_count,
                       uint32_t *elided_count, uint32_t *mis_any_count);
 void spt_launch_accumulate(int grid, cudaStream_t st, const DevScene &sc, const RenderCfg &cfg, const WaveBuffers &wb, int bounce,
                            const uint32_t *queue, const uint32_t *count, uint32_t *next_queue, uint32_t *next_count);
 void spt_launch_film_add(int grid, cudaStream_t st, const FilmView &film, const SptSpectralTables *tables, const float2 *img_xy,
-                         const float *L, uint32_t cap, uint32_t n_samples, int spp, int sub);
+                         const float *L, uint32_t cap, uint32_t n_samples, int spp);
 void spt_launch_film_split(int grid, cudaStream_t st, const float *pix, size_t npix, float *c, float *w);
-void spt_launch_gather_L(cudaStream_t st, const float *L, uint32_t cap, uint32_t n, int sub, float *out);
+void spt_launch_gather_L(cudaStream_t st, const float *L, uint32_t cap, uint32_t n, float *out);
 void spt_launch_scatter_L(cudaStream_t st, const float *in, uint32_t cap, uint32_t n, float *L);
 
 // spt_build.cu: scene re-layout on the device

@@ -494,7 +494,7 @@ static void run_wave(SptScene *s, const RenderCfg &cfg, const SampleSource &src,
         s->mark(SPT_K_TRACE_PATH, li);
         spt_launch_compact_hits(gridC, st, q, row + 0, wb.hit_slot, wb.hitQ, row + 3, mq, row + 7, (b == 0 && !s->has_env) ? wb.L : nullptr);
         s->mark(SPT_K_SHADE, li);
-        if (mq) { spt_launch_miss_env(gridT, st, sc, wb, b, mq, row + 7, 1); s->mark(SPT_K_SHADE, li); }
+        if (mq) { spt_launch_miss_env(gridT, st, sc, wb, b, mq, row + 7); s->mark(SPT_K_SHADE, li); }
         spt_launch_shade(gridT, st, sc, cfg, src, wb, b, wb.hitQ, row + 3, row + 1, row + 2, row + 8, row + 9);
         s->mark(SPT_K_SHADE, li);
         if (sc.n_lights > 0) {
@@ -698,7 +698,7 @@ int spt_shade_samples(SptScene *s, const SptCameraDesc *cam, int32_t integrator,
     cudaMemsetAsync(s->counts, 0, nc * 4, s->stream);
     reset_class_stats(s);
     run_wave(s, cfg, src, s->counts);
-    spt_launch_gather_L(s->stream, s->lane[0].wb.L, s->lane[0].wb.cap, (uint32_t)n, 1, dout);
+    spt_launch_gather_L(s->stream, s->lane[0].wb.L, s->lane[0].wb.cap, (uint32_t)n, dout);
     std::vector<uint32_t> hc(nc);
     cudaMemcpyAsync(hc.data(), s->counts, nc * 4, cudaMemcpyDeviceToHost, s->stream);
     cudaError_t e = cudaMemcpyAsync(out_L, dout, n * NB * sizeof(float), cudaMemcpyDeviceToHost, s->stream);
@@ -808,7 +808,7 @@ int spt_film_add_samples(SptFilm *f, const SptSpectralTables *tables, const floa
     spt_launch_scatter_L(0, dl, (uint32_t)n, (uint32_t)n, soa);
     FilmView fv; fv.d = f->desc; fv.pix = f->pix; fv.table = f->table;
     unsigned gw = (unsigned)std::min<uint64_t>((n * 32 + 255) / 256, (uint64_t)num_sms() * 16);
-    spt_launch_film_add((int)gw, 0, fv, dt, dxy, soa, (uint32_t)n, (uint32_t)n, 1, 1);
+    spt_launch_film_add((int)gw, 0, fv, dt, dxy, soa, (uint32_t)n, (uint32_t)n, 1);
     cudaError_t e = cudaDeviceSynchronize();
     m.release();
     if (e != cudaSuccess) return fail(SPT_ERR_CUDA, cudaGetErrorString(e));
@@ -891,7 +891,7 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
         run_wave(s, cfg, src, s->counts + w * per_wave, li);
         unsigned gw = (unsigned)std::min<uint64_t>((np * 32 + 255) / 256, (uint64_t)num_sms() * 16);
         const WaveBuffers &wb = s->lane[li].wb;
-        spt_launch_film_add((int)gw, s->lane[li].stream, fv, s->dev.tables, wb.img_xy, wb.L, wb.cap, (uint32_t)(np * rp->spp), rp->spp, 1);
+        spt_launch_film_add((int)gw, s->lane[li].stream, fv, s->dev.tables, wb.img_xy, wb.L, wb.cap, (uint32_t)(np * rp->spp), rp->spp);
         s->mark(SPT_K_FILM, li);
     }
     for (int k = 1; k < n_lanes; ++k) {                                              // join

@@ -12,14 +12,13 @@ __global__ void __launch_bounds__(256) k_gen_camera(RenderCfg cfg, SampleSource 
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cfg.n_samples; i += gridDim.x * blockDim.x) {
         float ix, iy, lu, lv;
         bool valid = true;
-        const uint32_t cs = i;
         if (src.smp) {
-            const float *s = src.smp + (size_t)src.stride * cs;
+            const float *s = src.smp + (size_t)src.stride * i;
             ix = s[0]; iy = s[1]; lu = s[2]; lv = s[3];
         } else {
             int px, py;
-            uint32_t s = cs & ((uint32_t)cfg.spp - 1u);                      // spp is a power of two (LDSampler rounds up)
-            valid = wave_pixel(cfg, cfg.pixel_base + (cs >> cfg.spp_shift), &px, &py);
+            uint32_t s = i & ((uint32_t)cfg.spp - 1u);                       // spp is a power of two (LDSampler rounds up)
+            valid = wave_pixel(cfg, cfg.pixel_base + (i >> cfg.spp_shift), &px, &py);
             if (valid) {
                 uint32_t pk = pixel_key(src.seed, pix_key(px, py));
                 float t2[2];

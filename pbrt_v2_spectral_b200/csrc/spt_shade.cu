@@ -80,15 +80,11 @@ __global__ void __launch_bounds__(256) k_compact_hits(const uint32_t *__restrict
 // Camera rays that escape: SamplerRenderer::Li's miss branch (samplerrenderer.cpp:239-243), the sum of
 // Light::Le over all lights - only the infinite light is non-zero. Later bounces: the same sum times the
 // throughput, but only for a ray that left a specular bounce (path.cpp:106-108).
-__global__ void __launch_bounds__(128) k_miss_env(DevScene sc, WaveBuffers wb, int bounce, const uint32_t *queue, const uint32_t *count, int sub) {
+__global__ void __launch_bounds__(128) k_miss_env(DevScene sc, WaveBuffers wb, int bounce, const uint32_t *queue, const uint32_t *count) {
     uint32_t n = *count;
     for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
         uint32_t i = queue[q];
         if (bounce > 0 && !(wb.pflags[i] & 1u)) continue;
-        if (sub > 1 && (i % (uint32_t)sub)) {                       // directlighting: the first of a camera sample's slots carries Le
-            for (int c = 0; c < NB; ++c) wb.L[band_off(i, c)] = 0.f;
-            continue;
-        }
         float4 d4 = wb.ray_d[i];
         float Le[NB];
         for (int c = 0; c < NB; ++c) Le[c] = 0.f;
@@ -714,10 +710,8 @@ __global__ void __launch_bounds__(32 * ACCD_WARPS, 8) k_accumulate_direct(DevSce
 // exchanging over lane bits 4, 3, 2 each group of four lanes owns one sample, bits 1, 0 finish it).
 #define FILM_GROUP 8
 __device__ __forceinline__ int film_y_lane(int k) { return ((k & 1) << 4) | ((k & 2) << 2) | (k & 4); }   // a lane that ends up holding y of sample k
-// sub > 1 (directlighting): a camera sample's radiance is the sum of `sub` consecutive rows (its light samples), formed
-// before the guards as the reference guards the integrator's total.
 __global__ void __launch_bounds__(256) k_film_add(FilmView film, const SptSpectralTables *tables, const float2 *img_xy,
-                                                  const float *L, uint32_t cap, uint32_t n_samples, int spp, int sub) {
+                                                  const float *L, uint32_t cap, uint32_t n_samples, int spp) {
     const SptSpectralTables &tb = *tables;
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -731,23 +725,19 @@ __global__ void __launch_bounds__(256) k_film_add(FilmView film, const SptSpectr
         const uint32_t first = pixel * (uint32_t)spp;
         const uint32_t ns = min((uint32_t)spp, n_samples - first);
         // the pixel this warp accumulates for: the one the first sample of the group falls in
-        float2 xy0 = img_xy[(size_t)first * sub];
+        float2 xy0 = img_xy[first];
         const int mainx = (int)floorf(xy0.x), mainy = (int)floorf(xy0.y);
         const bool mainInside = mainx >= xs && mainx <= xe && mainy >= ys && mainy <= ye;
         float acc = 0.f, wsum = 0.f;
         for (uint32_t s0 = 0; s0 < ns; s0 += FILM_GROUP) {
             float Lv[FILM_GROUP];
 #pragma unroll
-            for (int k = 0; k < FILM_GROUP; ++k) {
-                const uint32_t row = (first + min(s0 + k, ns - 1)) * (uint32_t)sub;
-                Lv[k] = L[band_off(row, lane)];
-                for (int q = 1; q < sub; ++q) Lv[k] += L[band_off(row + q, lane)];
-            }
+            for (int k = 0; k < FILM_GROUP; ++k) Lv[k] = L[band_off(first + min(s0 + k, ns - 1), lane)];
             // ---- footprint of sample s0 + lane (lanes 0-7): 0 nothing to add, 1 exactly the warp's pixel, 2 anything else
             int kind = 0;
             float wt = 0.f;
             if (lane < FILM_GROUP && s0 + lane < ns) {
-                const float2 xy = img_xy[(size_t)(first + s0 + lane) * sub];
+                const float2 xy = img_xy[first + s0 + lane];
                 if (xy.x > -1e29f) {                                    // else: sample outside this rank's tile set
                     const float dimageX = xy.x - 0.5f, dimageY = xy.y - 0.5f;
                     int x0 = (int)ceilf(dimageX - fd.filter_xwidth), x1 = (int)floorf(dimageX + fd.filter_xwidth);
@@ -803,7 +793,7 @@ __global__ void __launch_bounds__(256) k_film_add(FilmView film, const SptSpectr
                 const float w = __shfl_sync(FULL, wt, k);
                 if ((fastMask >> k) & 1u) { acc += w * v; wsum += w; }
                 else if ((slowMask >> k) & 1u) {
-                    const float2 xy = img_xy[(size_t)(first + s0 + k) * sub];
+                    const float2 xy = img_xy[first + s0 + k];
                     const float dimageX = xy.x - 0.5f, dimageY = xy.y - 0.5f;
                     int x0 = (int)ceilf(dimageX - fd.filter_xwidth), x1 = (int)floorf(dimageX + fd.filter_xwidth);
                     int y0 = (int)ceilf(dimageY - fd.filter_ywidth), y1 = (int)floorf(dimageY + fd.filter_ywidth);
@@ -842,12 +832,10 @@ __global__ void k_film_split(const float *pix, size_t npix, float *c, float *w) 
     }
 }
 // SoA [NB][cap] -> AoS [n][NB] (spt_shade_samples output)
-__global__ void k_gather_L(const float *L, uint32_t cap, uint32_t n, int sub, float *out) {
+__global__ void k_gather_L(const float *L, uint32_t cap, uint32_t n, float *out) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n * NB; i += gridDim.x * blockDim.x) {
         uint32_t s = i / NB, c = i % NB;
-        float v = L[band_off(s * (uint32_t)sub, c)];
-        for (int q = 1; q < sub; ++q) v += L[band_off(s * (uint32_t)sub + q, c)];
-        out[i] = v;
+        out[i] = L[band_off(s, c)];
     }
 }
 // AoS [n][NB] -> SoA, for spt_film_add_samples
@@ -864,8 +852,8 @@ void spt_launch_compact_hits(int grid, cudaStream_t st, const uint32_t *queue, c
                              uint32_t *hit_queue, uint32_t *hit_count, uint32_t *miss_queue, uint32_t *miss_count, float *black_L) {
     k_compact_hits<<<grid, 256, 0, st>>>(queue, count, hit_slot, hit_queue, hit_count, miss_queue, miss_count, black_L);
 }
-void spt_launch_miss_env(int grid, cudaStream_t st, const DevScene &sc, const WaveBuffers &wb, int bounce, const uint32_t *queue, const uint32_t *count, int sub) {
-    k_miss_env<<<grid, 128, 0, st>>>(sc, wb, bounce, queue, count, sub);
+void spt_launch_miss_env(int grid, cudaStream_t st, const DevScene &sc, const WaveBuffers &wb, int bounce, const uint32_t *queue, const uint32_t *count) {
+    k_miss_env<<<grid, 128, 0, st>>>(sc, wb, bounce, queue, count);
 }
 void spt_launch_shade(int grid, cudaStream_t st, const DevScene &sc, const RenderCfg &cfg, const SampleSource &src, const WaveBuffers &wb,
                       int bounce, const uint32_t *queue, const uint32_t *count, uint32_t *shadow_count, uint32_t *mis_count,
@@ -882,14 +870,14 @@ void spt_launch_accumulate(int grid, cudaStream_t st, const DevScene &sc, const 
     else k_accumulate<false><<<grid, 128, 0, st>>>(sc, cfg, wb, bounce, queue, count, next_queue, next_count);
 }
 void spt_launch_film_add(int grid, cudaStream_t st, const FilmView &film, const SptSpectralTables *tables, const float2 *img_xy,
-                         const float *L, uint32_t cap, uint32_t n_samples, int spp, int sub) {
-    k_film_add<<<grid, 256, 0, st>>>(film, tables, img_xy, L, cap, n_samples, spp, sub);
+                         const float *L, uint32_t cap, uint32_t n_samples, int spp) {
+    k_film_add<<<grid, 256, 0, st>>>(film, tables, img_xy, L, cap, n_samples, spp);
 }
 void spt_launch_film_split(int grid, cudaStream_t st, const float *pix, size_t npix, float *c, float *w) {
     k_film_split<<<grid, 256, 0, st>>>(pix, npix, c, w);
 }
-void spt_launch_gather_L(cudaStream_t st, const float *L, uint32_t cap, uint32_t n, int sub, float *out) {
-    k_gather_L<<<grid1d((uint64_t)n * NB, 256, 65535), 256, 0, st>>>(L, cap, n, sub, out);
+void spt_launch_gather_L(cudaStream_t st, const float *L, uint32_t cap, uint32_t n, float *out) {
+    k_gather_L<<<grid1d((uint64_t)n * NB, 256, 65535), 256, 0, st>>>(L, cap, n, out);
 }
 void spt_launch_scatter_L(cudaStream_t st, const float *in, uint32_t cap, uint32_t n, float *L) {
     k_scatter_L<<<grid1d((uint64_t)n * NB, 256, 65535), 256, 0, st>>>(in, cap, n, L);
