@@ -231,7 +231,10 @@ typedef struct SptFilmDesc {
  *   DIRECT_ALL  DirectLightingIntegrator with strategy "all" (src/integrators/directlighting.cpp:70-105):
  *               emitted light + UniformSampleAllLights (src/core/integrator.cpp:39-71) at the camera ray's hit.
  *               Scenes with specular materials are not lowered under it (its SpecularReflect/Transmit recursion). */
-enum { SPT_INTEGRATOR_PATH = 0, SPT_INTEGRATOR_DIRECT_ALL = 1 };
+enum { SPT_INTEGRATOR_PATH = 0, SPT_INTEGRATOR_DIRECT_ALL = 1,
+       SPT_INTEGRATOR_DIRECT_ONE = 2   /* DirectLightingIntegrator, strategy "one": emitted light + UniformSampleOneLight
+                                          (src/core/integrator.cpp:72-107) at the camera ray's hit */
+};
 
 /* What SamplerRenderer + LDSampler + the surface integrator are configured with. */
 typedef struct SptRenderParams {
@@ -327,6 +330,8 @@ int spt_trace_any_dev(SptScene *scene, const float *rays_dev, uint64_t n, uint8_
  * order DirectLightingIntegrator::RequestSamples leaves them (directlighting.cpp:46-60, src/core/light.cpp:56-60,
  * src/core/reflection.cpp:494-498): {5 camera floats, per light [light component x n_i, bsdf component x n_i],
  * 2 floats of the volume integrator, per light [light position x 2 n_i, bsdf direction x 2 n_i]}; rng is unused.
+ * integrator = SPT_INTEGRATOR_DIRECT_ONE: n x 14 floats {5 camera floats, light component, light number, bsdf component,
+ * 2 floats of the volume integrator, light position x 2, bsdf direction x 2} (directlighting.cpp:61-68).
  * out_L: n x SPT_NBANDS radiance BEFORE the NaN/negative/inf guards of
  * src/renderers/samplerrenderer.cpp:119-133. */
 int spt_shade_samples(SptScene *scene, const SptCameraDesc *cam, int32_t integrator, int32_t max_depth, int32_t spp,

@@ -220,6 +220,13 @@ def killeroo_direct(w, h, spp, name, maxdepth=5):
     return set_filename(set_spp(set_res(s, w, h), spp), name)
 
 
+def killeroo_direct_one(w, h, spp, name, maxdepth=5):
+    """killeroo-simple.pbrt with the directlighting integrator's other strategy ("one": UniformSampleOneLight)."""
+    s = killeroo_direct(w, h, spp, name, maxdepth)
+    s = s.replace('SurfaceIntegrator "directlighting"', 'SurfaceIntegrator "directlighting" "string strategy" ["one"]')
+    return s
+
+
 def bunny_direct(w, h, spp, name, maxdepth=5):
     """bunny.pbrt as shipped (default directlighting integrator, point light + disk area light with nsamples 4) except
     its measured BRDF ("next"), for which plastic stands in."""
@@ -263,6 +270,7 @@ CONFIGS = {
     "killeroo_direct_small": (killeroo_direct, 176, 176, 4, 6000, 8, 1024),
     "bunny_direct_small":    (bunny_direct, 320, 240, 4, 6000, 8, 1024),
     "killeroo_direct":       (killeroo_direct, 700, 700, 64, 0, 0, 0),
+    "killeroo_direct_one_small": (killeroo_direct_one, 176, 176, 4, 3000, 8, 0),
     # the bunny with its shipped measured BRDF: under the path integrator (config 2) and as shipped (directlighting)
     "bunny_measured_small":  (bunny_measured, 320, 240, 4, 6000, 40, 4096),
     "bunny_shipped_small":   (bunny_shipped, 320, 240, 4, 6000, 8, 1024),

@@ -1566,8 +1566,45 @@ static void li_sample_direct(const SptSceneDesc *sc, const SptCameraDesc *cam, i
     memcpy(Lout, L, sizeof(L));
 }
 
+/* DirectLightingIntegrator::Li with strategy "one" (directlighting.cpp:70-105, UniformSampleOneLight core/integrator.cpp:72-107).
+ * Sample layout (directlighting.cpp:61-68): [5] light component, [6] light number, [7] bsdf component, [8],[9] volume
+ * integrator, [10],[11] light position, [12],[13] bsdf direction. */
+static void li_sample_direct_one(const SptSceneDesc *sc, const SptCameraDesc *cam, int spp, const float *smp, float *Lout) {
+    Ray ray;
+    RayDiff rd;
+    camera_ray_diff(cam, smp, spp, &ray, &rd);
+    float L[NB];
+    for (int c = 0; c < NB; ++c) L[c] = 0.f;
+    uint32_t slot; Hit isect;
+    if (!bvh_intersect(sc, &ray, 0, &slot, &isect, NULL, NULL)) {
+        for (uint32_t i = 0; i < sc->n_lights; ++i) {
+            float le[NB];
+            light_le(sc, sc->lights + i, ray.d, le);
+            for (int c = 0; c < NB; ++c) L[c] += le[c];
+        }
+        memcpy(Lout, L, sizeof(L));
+        return;
+    }
+    BSDF bsdf; v3 n;
+    make_bsdf(sc, slot, &isect, &rd, &bsdf, &n);
+    v3 p = isect.p, wo = vneg(ray.d);
+    float le[NB];
+    isect_le(sc, slot, &isect, wo, le);
+    for (int c = 0; c < NB; ++c) L[c] += le[c];
+    int nLights = (int)sc->n_lights;
+    if (nLights > 0) {
+        int lightNum = (int)floorf(smp[6] * nLights);
+        if (nLights - 1 < lightNum) lightNum = nLights - 1;
+        float ls[3] = { smp[10], smp[11], smp[5] }, bs[3] = { smp[12], smp[13], smp[7] };
+        float Ld[NB];
+        estimate_direct(sc, sc->lights + lightNum, lightNum, p, n, wo, isect.rayEpsilon, &bsdf, ls, bs, Ld);
+        for (int c = 0; c < NB; ++c) L[c] += Ld[c] * (float)nLights;
+    }
+    memcpy(Lout, L, sizeof(L));
+}
+
 int orc_sample_floats(const SptSceneDesc *sc, int32_t integrator) {
-    return integrator == SPT_INTEGRATOR_DIRECT_ALL ? direct_sample_floats(sc) : 37;
+    return integrator == SPT_INTEGRATOR_DIRECT_ALL ? direct_sample_floats(sc) : (integrator == SPT_INTEGRATOR_DIRECT_ONE ? 14 : 37);
 }
 
 void orc_shade_samples(const SptSceneDesc *sc, const SptCameraDesc *cam, int32_t integrator, int32_t max_depth, int32_t spp,
@@ -1576,6 +1613,7 @@ void orc_shade_samples(const SptSceneDesc *sc, const SptCameraDesc *cam, int32_t
 #pragma omp parallel for schedule(dynamic, 64)
     for (int64_t i = 0; i < (int64_t)n; ++i) {
         if (integrator == SPT_INTEGRATOR_DIRECT_ALL) li_sample_direct(sc, cam, spp, samples + (size_t)stride * i, out_L + (size_t)NB * i);
+        else if (integrator == SPT_INTEGRATOR_DIRECT_ONE) li_sample_direct_one(sc, cam, spp, samples + (size_t)stride * i, out_L + (size_t)NB * i);
         else li_sample(sc, cam, max_depth, spp, samples + 37 * i, rng ? rng + (size_t)n_rng * i : NULL, rng ? n_rng : 0,
                        out_L + (size_t)NB * i);
     }
@@ -1720,8 +1758,8 @@ static void gen_sample_direct(const SptSceneDesc *sc, uint64_t seed64, int32_t p
 
 void orc_render(const SptSceneDesc *sc, const SptCameraDesc *cam, const SptFilmDesc *fd, const SptRenderParams *rp,
                 float *c, float *weight) {
-    const int direct = rp->integrator == SPT_INTEGRATOR_DIRECT_ALL;
-    const int stride = orc_sample_floats(sc, rp->integrator);
+    const int direct = rp->integrator == SPT_INTEGRATOR_DIRECT_ALL, directOne = rp->integrator == SPT_INTEGRATOR_DIRECT_ONE;
+    const int stride = directOne ? 37 : orc_sample_floats(sc, rp->integrator);
     int nrng = 11 * (rp->max_depth > 2 ? rp->max_depth - 2 : 0) + 1;
     int x1 = rp->x_end, y1 = rp->y_end;
     if (rp->skip_border) {
@@ -1746,7 +1784,12 @@ void orc_render(const SptSceneDesc *sc, const SptCameraDesc *cam, const SptFilmD
                 } else {
                     orc_gen_sample(rp->seed, px, py, s, rp->spp, cam->shutter_open, cam->shutter_close, nrng,
                                    smp + 37 * s, rng + nrng * s);
-                    li_sample(sc, cam, rp->max_depth, rp->spp, smp + 37 * s, rng + nrng * s, nrng, L + NB * s);
+                    if (directOne) {
+                        /* the product draws strategy "one" from the path sampler's first-bounce dimensions */
+                        const float *q = smp + 37 * s;
+                        float o14[14] = { q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7], 0.f, 0.f, q[19], q[20], q[21], q[22] };
+                        li_sample_direct_one(sc, cam, rp->spp, o14, L + NB * s);
+                    } else li_sample(sc, cam, rp->max_depth, rp->spp, smp + 37 * s, rng + nrng * s, nrng, L + NB * s);
                 }
             }
 #pragma omp critical

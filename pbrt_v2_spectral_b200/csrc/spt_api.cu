@@ -671,14 +671,15 @@ int spt_shade_samples(SptScene *s, const SptCameraDesc *cam, int32_t integrator,
                       const float *rng, int32_t n_rng, uint64_t n, float *out_L) {
     if (!s || !cam || !samples || !out_L) return fail(SPT_ERR_ARG, "null argument");
     if (spp <= 0) return fail(SPT_ERR_ARG, "spp must be positive");
-    if (integrator != SPT_INTEGRATOR_PATH && integrator != SPT_INTEGRATOR_DIRECT_ALL) return fail(SPT_ERR_ARG, "unknown integrator");
-    const bool direct = integrator == SPT_INTEGRATOR_DIRECT_ALL;
-    if (direct && s->dev.has_specular) return fail(SPT_ERR_UNSUPP, "directlighting with specular materials is not supported");
+    if (integrator != SPT_INTEGRATOR_PATH && integrator != SPT_INTEGRATOR_DIRECT_ALL && integrator != SPT_INTEGRATOR_DIRECT_ONE)
+        return fail(SPT_ERR_ARG, "unknown integrator");
+    const bool direct = integrator == SPT_INTEGRATOR_DIRECT_ALL, directOne = integrator == SPT_INTEGRATOR_DIRECT_ONE;
+    if ((direct || directOne) && s->dev.has_specular) return fail(SPT_ERR_UNSUPP, "directlighting with specular materials is not supported");
     if (direct && s->dev.n_lights == 0) return fail(SPT_ERR_UNSUPP, "directlighting needs at least one light");
     if (n == 0) return SPT_OK;
     const int sub = direct ? s->direct_slots : 1;
-    const int stride = direct ? 7 + 6 * s->direct_slots : 37;
-    if (direct) max_depth = 0;
+    const int stride = direct ? 7 + 6 * s->direct_slots : (directOne ? 14 : 37);
+    if (direct || directOne) max_depth = 0;     // strategy "one" is the path integrator's first vertex: emitted light + UniformSampleOneLight
     if (n * (uint64_t)sub > (1u << 26)) return fail(SPT_ERR_ARG, "too many samples for one call");
     int rc = ensure_wave(s, 1, (uint32_t)n, max_depth, 1, (uint32_t)sub);
     if (rc != SPT_OK) return rc;
@@ -822,15 +823,16 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
     if (rp->max_depth < 0 || rp->max_depth > 64) return fail(SPT_ERR_ARG, "max_depth out of range");
     int nranks = rp->tile_nranks > 0 ? rp->tile_nranks : 1;
     if (rp->tile_rank < 0 || rp->tile_rank >= nranks) return fail(SPT_ERR_ARG, "tile_rank out of range");
-    if (rp->integrator != SPT_INTEGRATOR_PATH && rp->integrator != SPT_INTEGRATOR_DIRECT_ALL) return fail(SPT_ERR_ARG, "unknown integrator");
-    const bool direct = rp->integrator == SPT_INTEGRATOR_DIRECT_ALL;
-    if (direct && s->dev.has_specular) return fail(SPT_ERR_UNSUPP, "directlighting with specular materials is not supported");
+    if (rp->integrator != SPT_INTEGRATOR_PATH && rp->integrator != SPT_INTEGRATOR_DIRECT_ALL && rp->integrator != SPT_INTEGRATOR_DIRECT_ONE)
+        return fail(SPT_ERR_ARG, "unknown integrator");
+    const bool direct = rp->integrator == SPT_INTEGRATOR_DIRECT_ALL, directOne = rp->integrator == SPT_INTEGRATOR_DIRECT_ONE;
+    if ((direct || directOne) && s->dev.has_specular) return fail(SPT_ERR_UNSUPP, "directlighting with specular materials is not supported");
     if (direct && s->dev.n_lights == 0) return fail(SPT_ERR_UNSUPP, "directlighting needs at least one light");
     if (direct && !s->direct_pow2) return fail(SPT_ERR_ARG, "directlighting: every light's n_samples must be a power of two (Sampler::RoundSize)");
     const int sub = direct ? s->direct_slots : 1;                 // jobs per camera hit
     RenderCfg cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.cam = *cam; cfg.spp = rp->spp; cfg.max_depth = direct ? 0 : rp->max_depth;
+    cfg.cam = *cam; cfg.spp = rp->spp; cfg.max_depth = (direct || directOne) ? 0 : rp->max_depth;
     cfg.integrator = rp->integrator; cfg.sub = sub;
     cfg.diff_scale = 1.f / sqrtf((float)rp->spp);
     for (cfg.spp_shift = 0; (1 << cfg.spp_shift) < cfg.spp; ++cfg.spp_shift) {}

@@ -181,6 +181,13 @@ __global__ void __launch_bounds__(128, 4) k_shade(DevScene sc, RenderCfg cfg, Sa
                     for (int k = 0; k < 10; ++k) u[k] = 0.f;
                     rr = 0.f;
                     direct_dims(src, i, pk, s_idx, directLight, prefix, sc.lights[directLight].n_samples, jj, cfg.sub, u);
+                } else if (EXT && cfg.integrator == SPT_INTEGRATOR_DIRECT_ONE && src.smp) {
+                    // strategy "one" (directlighting.cpp:61-68): {light component, light number, bsdf component}, 2 volume floats,
+                    // {light position, bsdf direction}; generated samples take the path sampler's first-bounce dimensions
+                    const float *q = src.smp + (size_t)src.stride * i;
+                    for (int k = 0; k < 10; ++k) u[k] = 0.f;
+                    rr = 0.f;
+                    u[0] = q[6]; u[1] = q[10]; u[2] = q[11]; u[3] = q[5]; u[4] = q[12]; u[5] = q[13]; u[6] = q[7];
                 } else bounce_dims(src, i, pk, s_idx, bounce, sc.n_lights > 0, u, &rr);
 
                 float4 g1 = make_float4(0, 0, 0, 0), g2 = g1, g3 = g1, laux = g1;
@@ -212,7 +219,7 @@ __global__ void __launch_bounds__(128, 4) k_shade(DevScene sc, RenderCfg cfg, Sa
                 float specR = 0.f, specT = 0.f, specPdf = 0.f;
                 for (int d = 1; d <= 2; ++d) {
                     if (d == 1 && (!haveLights || lr.delta)) continue;
-                    if (d == 2 && direct) continue;                  // no continuation under directlighting
+                    if (d == 2 && (direct || (EXT && cfg.integrator == SPT_INTEGRATOR_DIRECT_ONE))) continue;   // no continuation under directlighting
                     if (specMat) {                                      // only d == 2 gets here
                         v3 wl;
                         have2 = specular_sample(bsdf, wo, u[9], &wl, &specR, &specT, &specPdf);

@@ -61,7 +61,7 @@ class SptRenderParams(C.Structure):
                 ("wave_pixels", C.c_int32), ("skip_border", C.c_int32), ("integrator", C.c_int32)]
 
 
-INTEGRATOR_PATH, INTEGRATOR_DIRECT_ALL = 0, 1
+INTEGRATOR_PATH, INTEGRATOR_DIRECT_ALL, INTEGRATOR_DIRECT_ONE = 0, 1, 2
 
 
 K_GEN, K_TRACE_PATH, K_SHADE, K_TRACE_SHADOW, K_TRACE_MIS, K_ACCUMULATE, K_FILM, K_CLASSES = 0, 1, 2, 3, 4, 5, 6, 8

@@ -643,13 +643,13 @@ struct Lowerer {
             out->params.integrator = SPT_INTEGRATOR_PATH;
             out->params.max_depth = pi->maxDepth;
         } else if (const DirectLightingIntegrator *dl = dynamic_cast<const DirectLightingIntegrator *>(surf)) {
-            // directlighting.cpp:70-105: strategy "all" (the default) = UniformSampleAllLights at the camera hit; its
+            // directlighting.cpp:70-105: UniformSampleAllLights (strategy "all", the default) or UniformSampleOneLight at the camera hit; its
             // SpecularReflect / SpecularTransmit recursion only does anything for specular BxDFs, which are not lowered under it
-            if (dl->strategy != SAMPLE_ALL_UNIFORM) return fail("directlighting with strategy \"one\" is not supported");
+
             for (size_t i = 0; i < out->materials.size(); ++i)
                 if (out->materials[i].type == SPT_MAT_MIRROR || out->materials[i].type == SPT_MAT_GLASS)
                     return fail("directlighting integrator with specular materials is not supported");
-            out->params.integrator = SPT_INTEGRATOR_DIRECT_ALL;
+            out->params.integrator = dl->strategy == SAMPLE_ALL_UNIFORM ? SPT_INTEGRATOR_DIRECT_ALL : SPT_INTEGRATOR_DIRECT_ONE;
             out->params.max_depth = dl->maxDepth;
         } else return fail("surface integrator is neither the path nor the directlighting integrator");
         out->params.x_start = ld->xPixelStart; out->params.x_end = ld->xPixelEnd;

@@ -112,7 +112,7 @@ def test_film_wide_filter():
 
 
 RENDER_CASES = [c for c in CASES if c[0] in ("tiny", "metal_shipped_small", "ssenv_shipped_small", "killeroo_direct_small",
-                                             "bunny_direct_small", "bunny_shipped_small")]
+                                             "bunny_direct_small", "bunny_shipped_small", "killeroo_direct_one_small")]
 
 
 @pytest.mark.parametrize("rcase", RENDER_CASES, ids=[c[0] for c in RENDER_CASES])
