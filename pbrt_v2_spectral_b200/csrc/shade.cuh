@@ -632,11 +632,48 @@ __device__ inline void measured_f(const DevScene &sc, const SptBrdfTable &t, v3 
     const SptKdNode *nodes = sc.brdf_nodes + t.node_first;
     const float *spectra = sc.brdf_spectra + (size_t)t.node_first * NB;
     const uint32_t NONE = 0xffffffffu;
+    // The reference repeats the search with maxDist2 = .001, .002, .004, ... until it finds more than two samples (or
+    // maxDist2 exceeds 1.5), i.e. it stops at the first radius^2 of that sequence above the THIRD-SMALLEST squared distance.
+    // That distance comes from one 3-nearest-neighbour descent (near child first, far child only if the split plane is
+    // closer than the third best so far: a far-side sample's rounded distance^2 is never below the plane's, so nothing
+    // that could enter the best three is skipped), and only the final search is run - same radius, same visiting order,
+    // same sums as the reference's last round.
+    float b0 = SPT_INF, b1 = SPT_INF, b2 = SPT_INF;
+    {
+        uint32_t stk[32];
+        float stkd[32];
+        int sp = 0;
+        stk[sp] = 0u; stkd[sp++] = 0.f;
+        while (sp) {
+            --sp;
+            const uint32_t n = stk[sp];
+            if (!(stkd[sp] < b2)) continue;
+            const SptKdNode nd = nodes[n];
+            const float dx = nd.p[0] - m.x, dy = nd.p[1] - m.y, dz = nd.p[2] - m.z;
+            const float d2 = dx * dx + dy * dy + dz * dz;
+            if (d2 < b2) {
+                if (d2 < b0) { b2 = b1; b1 = b0; b0 = d2; }
+                else if (d2 < b1) { b2 = b1; b1 = d2; }
+                else b2 = d2;
+            }
+            const int axis = (int)(nd.bits & 3u);
+            if (axis == 3) continue;
+            const bool hasLeft = (nd.bits >> 2) & 1u;
+            const uint32_t right = nd.bits >> 3;
+            const float pa = vcomp(m, axis);
+            const float pd = (pa - nd.split_pos) * (pa - nd.split_pos);
+            const bool leftFirst = pa <= nd.split_pos;
+            const uint32_t L = hasLeft ? n + 1 : NONE, R = right < t.n_nodes ? right : NONE;
+            const uint32_t nearC = leftFirst ? L : R, farC = leftFirst ? R : L;
+            if (farC != NONE && sp < 31) { stk[sp] = farC; stkd[sp++] = pd; }
+            if (nearC != NONE && sp < 31) { stk[sp] = nearC; stkd[sp++] = 0.f; }
+        }
+    }
     float maxD2 = .001f;
-    for (;;) {
+    while (!(b2 < maxD2) && !(maxD2 > 1.5f)) maxD2 *= 2.f;
+    {
         for (int c = 0; c < NB; ++c) v[c] = 0.f;
         float sumW = 0.f;
-        int nFound = 0;
         uint32_t stack[32];                                          // node << 2 | stage: 0 enter, 1 first child done, 2 both done
         int sp = 0;
         stack[sp++] = 0u;
@@ -669,14 +706,9 @@ __device__ inline void measured_f(const DevScene &sc, const SptBrdfTable &t, v3 
                 const float *sv = spectra + (size_t)n * NB;
                 for (int c = 0; c < NB; ++c) v[c] += __ldg(sv + c) * weight;
                 sumW += weight;
-                ++nFound;
             }
         }
-        if (nFound > 2 || maxD2 > 1.5f) {
-            for (int c = 0; c < NB; ++c) v[c] = clampf(v[c], 0.f, SPT_INF) / sumW;
-            return;
-        }
-        maxD2 *= 2.f;
+        for (int c = 0; c < NB; ++c) v[c] = clampf(v[c], 0.f, SPT_INF) / sumW;
     }
 }
 
