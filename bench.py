@@ -358,7 +358,7 @@ def main():
         first_vertices += st["first_vertices"]
         for k in range(D.K_CLASSES):
             class_ms[k] += st["class_ms"][k]; class_launches[k] += st["class_launches"][k]; class_rays[k] += st["class_rays"][k]
-    scene.set_lanes(int(os.environ.get("SPT_LANES", "2")))
+    scene.set_lanes(int(os.environ.get("SPT_LANES", "4")))
     film_t.zero_()
     scene.render(film, rp)
     exchange.run(film_t, rank)

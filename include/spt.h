@@ -293,7 +293,7 @@ void        spt_trim(void);
 /* Scene: uploads every table to HBM (replaces nothing in the reference; it is the hand-off). */
 SptScene *spt_scene_create(const SptSceneDesc *desc);
 void      spt_scene_destroy(SptScene *scene);
-/* Waves of a frame are dealt to several streams ("lanes", 1..4, default 2) so that the drain of one wave's
+/* Waves of a frame are dealt to several streams ("lanes", at most `lanes` of them: 1..4, default 4; a frame that fits two waves uses two) so that the drain of one wave's
  * persistent trace kernel overlaps the other waves' work; lanes = 1 keeps everything on one stream (exact
  * per-kernel times). */
 int       spt_scene_set_lanes(SptScene *scene, int lanes);

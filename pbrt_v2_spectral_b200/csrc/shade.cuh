@@ -105,7 +105,9 @@ __device__ inline TexLevel tex_level(const DevScene &sc, const SptTexture &t, in
 }
 // MIPMap::Texel, mipmap.h:177-201. C = channels per texel (3: RGB, 1: float)
 template <int C> __device__ inline void tex_texel(const SptTexture &t, const TexLevel &l, int s, int tt, float *out) {
-    if (t.wrap == SPT_WRAP_REPEAT) { s = imod(s, l.w); tt = imod(tt, l.h); }
+    // MIP levels are powers of two (the MIPMap constructor resamples, mipmap.h:124-170; checked by spt_scene_create), so
+    // Mod(s, w) - including its wrap of negative s - is a mask: no integer divisions in the EWA loops
+    if (t.wrap == SPT_WRAP_REPEAT) { s &= l.w - 1; tt &= l.h - 1; }
     else if (t.wrap == SPT_WRAP_CLAMP) { s = clampi(s, 0, l.w - 1); tt = clampi(tt, 0, l.h - 1); }
     else if (s < 0 || s >= l.w || tt < 0 || tt >= l.h) {
 #pragma unroll
@@ -729,10 +731,12 @@ __device__ inline void env_lookup(const DevScene &sc, float s, float t, float rg
     t = t * h - 0.5f;
     int s0 = (int)floorf(s), t0 = (int)floorf(t);
     float ds = s - s0, dt = t - t0;
-    const float *a = sc.env_rgb + 3 * ((size_t)imod(t0, h) * w + imod(s0, w));
-    const float *b = sc.env_rgb + 3 * ((size_t)imod(t0 + 1, h) * w + imod(s0, w));
-    const float *c = sc.env_rgb + 3 * ((size_t)imod(t0, h) * w + imod(s0 + 1, w));
-    const float *d = sc.env_rgb + 3 * ((size_t)imod(t0 + 1, h) * w + imod(s0 + 1, w));
+    // power-of-two map (spt_scene_create checks): Mod is a mask
+    const int sa = s0 & (w - 1), sb = (s0 + 1) & (w - 1), ta = t0 & (h - 1), tb = (t0 + 1) & (h - 1);
+    const float *a = sc.env_rgb + 3 * ((size_t)ta * w + sa);
+    const float *b = sc.env_rgb + 3 * ((size_t)tb * w + sa);
+    const float *c = sc.env_rgb + 3 * ((size_t)ta * w + sb);
+    const float *d = sc.env_rgb + 3 * ((size_t)tb * w + sb);
 #pragma unroll
     for (int k = 0; k < 3; ++k)
         rgb[k] = a[k] * ((1.f - ds) * (1.f - dt)) + b[k] * ((1.f - ds) * dt) + c[k] * (ds * (1.f - dt)) + d[k] * (ds * dt);

@@ -96,8 +96,9 @@ struct SptScene {
     bool counters_on = false;
     int trace_variant = 1;           // trace_kernels.cuh: 0 reference nodes, 1 pair nodes (default)
     uint32_t fetch_threshold = 14;
-    int max_lanes = 2;               // spt_scene_set_lanes: 1 = every wave on one stream (per-kernel timing is then exact); two lanes
-                                     // measured best at every job size (profiles/r01_rank_emulation.log)
+    int max_lanes = 4;               // spt_scene_set_lanes: the most streams a frame's waves are dealt to (1 = one stream: per-kernel
+                                     // timing is then exact). A frame that fits two waves uses two lanes - fewer, larger waves win
+                                     // (profiles/r01_rank_emulation.log) - a frame of many memory-capped waves uses all of them.
     cudaEvent_t evjoin[SPT_MAX_LANES] = {};
     bool has_env = false;            // an infinite light is present (escaped camera rays pick up Le)
     int direct_slots = 1;            // sum of the lights' n_samples: slots per camera sample under directlighting
@@ -315,6 +316,15 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
         if (mt.tex_kd >= (int32_t)d->n_textures || mt.tex_bump >= (int32_t)d->n_textures) { g_err = "material references a texture that is not in the scene"; delete s; return nullptr; }
         if (mt.tex_kd >= 0 && d->textures[mt.tex_kd].channels != 3) { g_err = "Kd texture is not an RGB image map"; delete s; return nullptr; }
         if (mt.tex_bump >= 0 && d->textures[mt.tex_bump].channels != 1) { g_err = "bump texture is not a float image map"; delete s; return nullptr; }
+    }
+    for (uint32_t t = 0; t < d->n_textures; ++t) {
+        const SptTexture &tx = d->textures[t];
+        if (tx.width <= 0 || tx.height <= 0 || (tx.width & (tx.width - 1)) || (tx.height & (tx.height - 1)) || tx.n_levels < 1) {
+            g_err = "image texture: level 0 must have power-of-two sides (MIPMap resamples to them)"; delete s; return nullptr;
+        }
+    }
+    if (d->env_w > 0 && ((d->env_w & (d->env_w - 1)) || (d->env_h & (d->env_h - 1)))) {
+        g_err = "environment map resolution must be a power of two"; delete s; return nullptr;
     }
     if (d->n_textures && !d->ewa_weight_lut) { g_err = "image textures need ewa_weight_lut"; delete s; return nullptr; }
     for (uint32_t p = 0; p < d->n_prims; ++p) {
@@ -861,6 +871,7 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
     const int depth = cfg.max_depth;
     const uint64_t local_samples = local_pixels * slots_pp;
     int want_lanes = s->max_lanes;
+    if (want_lanes > 2 && local_pixels * mem_pp <= (1ull << 25)) want_lanes = 2;
     while (want_lanes > 1 && local_samples < ((uint64_t)want_lanes << 19)) --want_lanes;
     const uint64_t lane_cap_pixels = std::max<uint64_t>(1, ((1u << 25) / (uint64_t)want_lanes) / mem_pp);
     uint64_t wave_pixels;

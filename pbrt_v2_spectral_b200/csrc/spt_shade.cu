@@ -118,7 +118,9 @@ __device__ __forceinline__ float2 dir_coef(int mtype, bool on, const DirTerms &t
 // specularBounce flag traffic, out of the kernel every other scene runs).
 // EXT: the scene has a substrate, an image-mapped Kd or a bump map (DevScene::has_ext): ray differentials at the
 // first vertex, filtered texture lookups, Material::Bump, FresnelBlend - again kept out of the common kernel.
-template <bool SPEC, bool EXT>
+// DIRECT: directlighting, strategy "all" - the per-direction part runs once per job of the vertex (a compile-time switch:
+// with a run-time job count the path integrator's kernels kept the vertex set-up live across a loop of one and lost 10 %).
+template <bool SPEC, bool EXT, bool DIRECT = false>
 __global__ void __launch_bounds__(128, 4) k_shade(DevScene sc, RenderCfg cfg, SampleSource src, WaveBuffers wb, int bounce,
                                                const uint32_t *queue, const uint32_t *count,
                                                uint32_t *shadow_count, uint32_t *mis_count, uint32_t *elided_count, uint32_t *mis_any_count) {
@@ -126,8 +128,8 @@ __global__ void __launch_bounds__(128, 4) k_shade(DevScene sc, RenderCfg cfg, Sa
     // directlighting (EXT kernels only): a vertex carries `sub` JOBS, one per (light, light sample) of UniformSampleAllLights
     // (integrator.cpp:39-71); the vertex is set up once and the per-direction part below runs per job, its records and
     // shadow / MIS rays indexed by r = vertex * sub + job. The path integrator has one job per vertex, r = vertex.
-    const bool direct = EXT && cfg.integrator == SPT_INTEGRATOR_DIRECT_ALL;
-    const uint32_t nj = direct ? (uint32_t)cfg.sub : 1u;
+    const bool direct = DIRECT;
+    const uint32_t nj = DIRECT ? (uint32_t)cfg.sub : 1u;
     for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < ((n + 31u) & ~31u); q += gridDim.x * blockDim.x) {
         bool active = q < n;
         uint32_t i = active ? queue[q] : 0;
@@ -866,7 +868,9 @@ void spt_launch_shade(int grid, cudaStream_t st, const DevScene &sc, const Rende
                       int bounce, const uint32_t *queue, const uint32_t *count, uint32_t *shadow_count, uint32_t *mis_count,
                       uint32_t *elided_count, uint32_t *mis_any_count) {
 #define SPT_SHADE(S, E) k_shade<S, E><<<grid, 128, 0, st>>>(sc, cfg, src, wb, bounce, queue, count, shadow_count, mis_count, elided_count, mis_any_count)
-    if (sc.has_ext || cfg.integrator != SPT_INTEGRATOR_PATH) { if (sc.has_specular) SPT_SHADE(true, true); else SPT_SHADE(false, true); }
+    if (cfg.integrator == SPT_INTEGRATOR_DIRECT_ALL)          // never with specular materials (spt_render refuses)
+        k_shade<false, true, true><<<grid, 128, 0, st>>>(sc, cfg, src, wb, bounce, queue, count, shadow_count, mis_count, elided_count, mis_any_count);
+    else if (sc.has_ext || cfg.integrator != SPT_INTEGRATOR_PATH) { if (sc.has_specular) SPT_SHADE(true, true); else SPT_SHADE(false, true); }
     else { if (sc.has_specular) SPT_SHADE(true, false); else SPT_SHADE(false, false); }
 #undef SPT_SHADE
 }
