@@ -120,7 +120,9 @@ __device__ __forceinline__ float2 dir_coef(int mtype, bool on, const DirTerms &t
 // first vertex, filtered texture lookups, Material::Bump, FresnelBlend - again kept out of the common kernel.
 // DIRECT: directlighting, strategy "all" - the per-direction part runs once per job of the vertex (a compile-time switch:
 // with a run-time job count the path integrator's kernels kept the vertex set-up live across a loop of one and lost 10 %).
-template <bool SPEC, bool EXT, bool DIRECT = false>
+// MEAS: the scene has a measured BRDF (DevScene::has_measured) - its kd-tree look-up (512 bytes of per-thread stacks and
+// sums) stays out of the kernels of the textured / substrate scenes, which lost 4-6 % to it.
+template <bool SPEC, bool EXT, bool DIRECT = false, bool MEAS = false>
 __global__ void __launch_bounds__(128, 4) k_shade(DevScene sc, RenderCfg cfg, SampleSource src, WaveBuffers wb, int bounce,
                                                const uint32_t *queue, const uint32_t *count,
                                                uint32_t *shadow_count, uint32_t *mis_count, uint32_t *elided_count, uint32_t *mis_any_count) {
@@ -297,7 +299,7 @@ __global__ void __launch_bounds__(128, 4) k_shade(DevScene sc, RenderCfg cfg, Sa
                     g3 = make_float4(wiW2.x, wiW2.y, wiW2.z, 0.f);
                 }
                 if (mtype == SPT_MAT_METAL) flags |= RF_METAL;
-                if (EXT && mtype == SPT_MAT_MEASURED) {
+                if (EXT && MEAS && mtype == SPT_MAT_MEASURED) {
                     // f of every direction that survived: a table look-up per direction, written as one 128-byte row
                     flags |= RF_MEASURED;
                     const SptBrdfTable tb = sc.brdfs[bsdf.brdf];
@@ -867,12 +869,15 @@ void spt_launch_miss_env(int grid, cudaStream_t st, const DevScene &sc, const Wa
 void spt_launch_shade(int grid, cudaStream_t st, const DevScene &sc, const RenderCfg &cfg, const SampleSource &src, const WaveBuffers &wb,
                       int bounce, const uint32_t *queue, const uint32_t *count, uint32_t *shadow_count, uint32_t *mis_count,
                       uint32_t *elided_count, uint32_t *mis_any_count) {
-#define SPT_SHADE(S, E) k_shade<S, E><<<grid, 128, 0, st>>>(sc, cfg, src, wb, bounce, queue, count, shadow_count, mis_count, elided_count, mis_any_count)
-    if (cfg.integrator == SPT_INTEGRATOR_DIRECT_ALL)          // never with specular materials (spt_render refuses)
-        k_shade<false, true, true><<<grid, 128, 0, st>>>(sc, cfg, src, wb, bounce, queue, count, shadow_count, mis_count, elided_count, mis_any_count);
+#define SPT_SHADE4(S, E, D, M) k_shade<S, E, D, M><<<grid, 128, 0, st>>>(sc, cfg, src, wb, bounce, queue, count, shadow_count, mis_count, elided_count, mis_any_count)
+#define SPT_SHADE(S, E) SPT_SHADE4(S, E, false, false)
+    if (cfg.integrator == SPT_INTEGRATOR_DIRECT_ALL) {        // never with specular materials (spt_render refuses)
+        if (sc.has_measured) SPT_SHADE4(false, true, true, true); else SPT_SHADE4(false, true, true, false);
+    } else if (sc.has_measured) { if (sc.has_specular) SPT_SHADE4(true, true, false, true); else SPT_SHADE4(false, true, false, true); }
     else if (sc.has_ext || cfg.integrator != SPT_INTEGRATOR_PATH) { if (sc.has_specular) SPT_SHADE(true, true); else SPT_SHADE(false, true); }
     else { if (sc.has_specular) SPT_SHADE(true, false); else SPT_SHADE(false, false); }
 #undef SPT_SHADE
+#undef SPT_SHADE4
 }
 void spt_launch_accumulate(int grid, cudaStream_t st, const DevScene &sc, const RenderCfg &cfg, const WaveBuffers &wb, int bounce,
                            const uint32_t *queue, const uint32_t *count, uint32_t *next_queue, uint32_t *next_count) {
