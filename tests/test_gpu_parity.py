@@ -161,3 +161,21 @@ def test_tile_sets_partition_the_image():
     film.close(); scene.close()
     assert np.array_equal(w1, w3)
     assert np.allclose(c1, c3, rtol=1e-5, atol=1e-6)
+
+
+def test_device_relayout_matches_host_relayout(monkeypatch):
+    """spt_scene_create builds the pair nodes, leaf flags and per-slot vertices on the device (csrc/spt_build.cu); the first,
+    host-side builder stays behind SPT_HOST_RELAYOUT: both must trace every golden ray to the same slot and distance."""
+    lowered, g = O.load_case(*[c for c in CASES if c[0] in ("killeroo_small", "tiny")][-1][1:])
+    dev_scene = capi.Scene(lowered)
+    a = dev_scene.trace_closest(g["rays"])
+    ha = dev_scene.trace_any(g["rays2"])
+    dev_scene.close()
+    monkeypatch.setenv("SPT_HOST_RELAYOUT", "1")
+    host_scene = capi.Scene(lowered)
+    b = host_scene.trace_closest(g["rays"])
+    hb = host_scene.trace_any(g["rays2"])
+    host_scene.close()
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert np.array_equal(a[2].view(np.uint32), b[2].view(np.uint32))
+    assert np.array_equal(ha, hb)

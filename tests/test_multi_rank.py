@@ -82,3 +82,28 @@ def test_tile_owner_matches_the_render_partition():
         for y, x in zip(ys[:200], xs[:200]):
             assert multi.tile_owner(x + fd.x_pixel_start, y + fd.y_pixel_start, rp.x_start, rp.y_start, n_tiles_x, world, tile) == r
     assert np.all(owner >= 0)
+
+
+def test_film_exchange_covers_a_wide_filter():
+    """FilmExchange sends the pixels a rank's tiles can reach: with a filter several pixels wide every pixel a rank's samples
+    touched must be in its list, and the lists must stay a small multiple of the film."""
+    import ctypes as C
+    import oracle_lib as O
+    from pbrt_v2_spectral_b200 import ctypes_defs as D, multi
+    lowered, _ = O.load_case(*O.golden_cases(big=False)[0][1:])
+    fd = D.SptFilmDesc.from_buffer_copy(bytes(lowered.film))
+    fd.filter_xwidth = fd.filter_ywidth = 2.0
+    fd.filter_inv_xwidth = fd.filter_inv_ywidth = 0.5
+    for k in range(256):
+        fd.filter_table[k] = 1.0
+    rp = D.SptRenderParams.from_buffer_copy(bytes(lowered.params))
+    rp.spp, rp.seed = 1, 5
+    world, tile = 3, 8
+    ex = multi.FilmExchange(fd, multi.rank_params(rp, 0, world, tile), world, torch.device("cpu"), tile=tile)
+    npix = fd.x_pixel_count * fd.y_pixel_count
+    for r in range(world):
+        _, w = O.render(lowered, multi.rank_params(rp, r, world, tile), film=fd)
+        touched = set(np.flatnonzero(w.reshape(-1)).tolist())
+        mine = set(ex.idx[r][:ex.counts[r]].tolist())
+        assert touched <= mine, "rank %d wrote %d pixels outside its exchange list" % (r, len(touched - mine))
+    assert sum(ex.counts) < 3 * npix
