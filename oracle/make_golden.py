@@ -297,8 +297,8 @@ def write_delta(path, name):
         return
     sys.path.insert(0, REPO)
     import numpy as np
-    from pbrt_v2_spectral_b200.scene_io import load_container, save_container
-    a, b = load_container(path), load_container(base_path)
+    from pbrt_v2_spectral_b200.scene_io import LoweredScene, load_container, save_container
+    a, b = load_container(path), LoweredScene.load_arrays(base_path)
     own = ("camera", "film", "params", "film_filename")
     if set(a) != set(b) or any(not np.array_equal(a[k], b[k]) for k in a if k not in own):
         return
@@ -347,6 +347,25 @@ def noise_floor(name, spp):
         name, spp, time.time() - t0, 100 * l1.max(), 100 * bias.max()), flush=True)
 
 
+def share_arrays(path, donor, keys=("tex_texels",)):
+    """Replace arrays of the container `path` that are byte-identical in `donor` by "<array>@" references to it (the loader
+    resolves them): the shipped-floor scenes carry the same 22 MB texel pool."""
+    if not (os.path.exists(path) and os.path.exists(donor)) or os.path.abspath(path) == os.path.abspath(donor):
+        return
+    sys.path.insert(0, REPO)
+    import numpy as np
+    from pbrt_v2_spectral_b200.scene_io import load_container, save_container
+    a, b = load_container(path), load_container(donor)
+    changed = False
+    for k in keys:
+        if k in a and k in b and a[k].size > (1 << 20) and np.array_equal(a[k], b[k]):
+            del a[k]
+            a[k + "@"] = np.frombuffer(os.path.relpath(donor, os.path.dirname(path)).encode(), np.uint8)
+            changed = True
+    if changed:
+        save_container(path, a)
+
+
 def with_gpupath(s):
     return s.replace("WorldBegin", 'Renderer "gpupath"\nWorldBegin', 1)
 
@@ -392,6 +411,8 @@ def main():
             dst = os.path.join(LOWERED, name + ".spt")
             shutil.move(prefix + ".spt", dst)
             write_delta(dst, name)
+        if name == "ssenv_shipped_small":
+            share_arrays(os.path.join(GOLDEN, name + ".spt"), os.path.join(GOLDEN, "metal_shipped_small.spt"))
         print("%-16s lowered + golden in %.1fs" % (name, time.time() - t0), flush=True)
         if name.startswith("synth"):                 # tens of MB of text per scene: regenerable, not shipped
             for f in (name + ".pbrt", name + ".gpu.pbrt"):

@@ -80,19 +80,28 @@ class LoweredScene:
         self.film_filename = a["film_filename"].tobytes().decode() if "film_filename" in a else ""
         self.desc = self._make_desc()
 
-    @classmethod
-    def load(cls, path):
-        """A container file, or a DELTA file: {"base_scene": file name next to / relative to this one, camera, film,
-        params, film_filename} - the full-size bench workloads share every scene table with their small golden
-        variant and differ in resolution and sample count only (oracle/make_golden.py writes them)."""
+    @staticmethod
+    def load_arrays(path):
+        """name -> array of a scene file with its references resolved (recursively):
+        "<array>@" = file name (relative to this file) of another container holding <array> - scenes that share a big table,
+        the shipped-floor scenes' 22 MB texel pool, keep one copy (oracle/make_golden.py share_arrays);
+        "base_scene" = a DELTA file {base_scene, camera, film, params, film_filename}: the full-size bench workloads share
+        every scene table with their small golden variant and differ in resolution and sample count only."""
         import os
+        here = os.path.dirname(os.path.abspath(path))
         a = load_container(path)
+        for key in [k for k in a if k.endswith("@")]:
+            other = os.path.normpath(os.path.join(here, a.pop(key).tobytes().decode()))
+            a[key[:-1]] = LoweredScene.load_arrays(other)[key[:-1]]
         if "base_scene" in a:
-            base = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(path)), a["base_scene"].tobytes().decode()))
-            full = load_container(base)
+            full = LoweredScene.load_arrays(os.path.normpath(os.path.join(here, a["base_scene"].tobytes().decode())))
             full.update({k: v for k, v in a.items() if k != "base_scene"})
             a = full
-        return cls(a)
+        return a
+
+    @classmethod
+    def load(cls, path):
+        return cls(LoweredScene.load_arrays(path))
 
     def _ptr(self, key):
         arr = self.a[key]
