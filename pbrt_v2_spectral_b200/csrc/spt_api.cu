@@ -224,7 +224,7 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
             for (uint32_t n = 0; n < d->n_nodes; ++n) {
                 if (rn[n].np) continue;
                 uint32_t c0 = n + 1, c1 = rn[n].off;
-                if (c0 >= d->n_nodes || c1 >= d->n_nodes) { g_err = "malformed BVH: child index out of range"; delete s; return nullptr; }
+                if (c0 >= d->n_nodes || c1 >= d->n_nodes) { g_err = "malformed BVH: child index out of range"; s->mem.release(); delete s; return nullptr; }
                 float4 *q = &pn[(size_t)pidx[n] * 4];
                 const float *a = rn[c0].b, *b = rn[c1].b;
                 q[0] = make_float4(a[0], a[1], a[2], a[3]);
@@ -311,26 +311,26 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
         if (mt.type == SPT_MAT_SUBSTRATE || mt.type == SPT_MAT_MEASURED || mt.tex_kd >= 0 || mt.tex_bump >= 0) v.has_ext = 1;
         if (mt.type == SPT_MAT_MEASURED) {
             v.has_measured = 1;
-            if (mt.brdf < 0 || mt.brdf >= (int32_t)d->n_brdfs) { g_err = "measured material references a BRDF table that is not in the scene"; delete s; return nullptr; }
+            if (mt.brdf < 0 || mt.brdf >= (int32_t)d->n_brdfs) { g_err = "measured material references a BRDF table that is not in the scene"; s->mem.release(); delete s; return nullptr; }
         }
-        if (mt.tex_kd >= (int32_t)d->n_textures || mt.tex_bump >= (int32_t)d->n_textures) { g_err = "material references a texture that is not in the scene"; delete s; return nullptr; }
-        if (mt.tex_kd >= 0 && d->textures[mt.tex_kd].channels != 3) { g_err = "Kd texture is not an RGB image map"; delete s; return nullptr; }
-        if (mt.tex_bump >= 0 && d->textures[mt.tex_bump].channels != 1) { g_err = "bump texture is not a float image map"; delete s; return nullptr; }
+        if (mt.tex_kd >= (int32_t)d->n_textures || mt.tex_bump >= (int32_t)d->n_textures) { g_err = "material references a texture that is not in the scene"; s->mem.release(); delete s; return nullptr; }
+        if (mt.tex_kd >= 0 && d->textures[mt.tex_kd].channels != 3) { g_err = "Kd texture is not an RGB image map"; s->mem.release(); delete s; return nullptr; }
+        if (mt.tex_bump >= 0 && d->textures[mt.tex_bump].channels != 1) { g_err = "bump texture is not a float image map"; s->mem.release(); delete s; return nullptr; }
     }
     for (uint32_t t = 0; t < d->n_textures; ++t) {
         const SptTexture &tx = d->textures[t];
         if (tx.width <= 0 || tx.height <= 0 || (tx.width & (tx.width - 1)) || (tx.height & (tx.height - 1)) || tx.n_levels < 1) {
-            g_err = "image texture: level 0 must have power-of-two sides (MIPMap resamples to them)"; delete s; return nullptr;
+            g_err = "image texture: level 0 must have power-of-two sides (MIPMap resamples to them)"; s->mem.release(); delete s; return nullptr;
         }
     }
     if (d->env_w > 0 && ((d->env_w & (d->env_w - 1)) || (d->env_h & (d->env_h - 1)))) {
-        g_err = "environment map resolution must be a power of two"; delete s; return nullptr;
+        g_err = "environment map resolution must be a power of two"; s->mem.release(); delete s; return nullptr;
     }
-    if (d->n_textures && !d->ewa_weight_lut) { g_err = "image textures need ewa_weight_lut"; delete s; return nullptr; }
+    if (d->n_textures && !d->ewa_weight_lut) { g_err = "image textures need ewa_weight_lut"; s->mem.release(); delete s; return nullptr; }
     for (uint32_t p = 0; p < d->n_prims; ++p) {
         const SptMaterial &mt = d->materials[d->prim_material[p]];
         if ((mt.tex_kd >= 0 || mt.tex_bump >= 0) && d->prim_kind[p] != SPT_PRIM_TRIANGLE) {
-            g_err = "textured materials are supported on triangles only"; delete s; return nullptr;
+            g_err = "textured materials are supported on triangles only"; s->mem.release(); delete s; return nullptr;
         }
     }
     UP(v.materials, mats.data(), d->n_materials); UP(v.lights, d->lights, d->n_lights);
@@ -338,7 +338,7 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
     UP(v.ewa_lut, d->ewa_weight_lut, d->ewa_weight_lut ? 128 : 0);
     for (uint32_t b = 0; b < d->n_brdfs; ++b)
         if ((uint64_t)d->brdfs[b].node_first + d->brdfs[b].n_nodes > d->n_brdf_nodes || d->brdfs[b].n_nodes == 0 || d->brdfs[b].n_nodes > (1u << 16)) {
-            g_err = "malformed BRDF table"; delete s; return nullptr;       // 2^16 nodes: the look-up's stack of 32 covers depth 16
+            g_err = "malformed BRDF table"; s->mem.release(); delete s; return nullptr;       // 2^16 nodes: the look-up's stack of 32 covers depth 16
         }
     UP(v.brdfs, d->brdfs, d->n_brdfs); UP(v.brdf_nodes, d->brdf_nodes, d->n_brdf_nodes);
     UP(v.brdf_spectra, d->brdf_spectra, (size_t)d->n_brdf_nodes * NB);
@@ -350,7 +350,7 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
         int N = 0;
         for (uint32_t li = 0; li < d->n_lights; ++li) {
             int ns = d->lights[li].n_samples;
-            if (ns < 1) { g_err = "light n_samples must be >= 1"; delete s; return nullptr; }
+            if (ns < 1) { g_err = "light n_samples must be >= 1"; s->mem.release(); delete s; return nullptr; }
             if (ns & (ns - 1)) s->direct_pow2 = false;
             N += ns;
         }
