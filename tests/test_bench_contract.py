@@ -1,0 +1,24 @@
+"""bench.py's reference arm (the unmodified reference binary on the host cores) runs without a GPU: its stdout must be
+exactly one JSON line with the keys the driver reads."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "bin", "pbrt")), reason="oracle/_ref/bin/pbrt not built")
+def test_reference_arm_prints_one_json_line():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stderr
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "Msamples/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
