@@ -238,6 +238,51 @@ def bunny_direct(w, h, spp, name, maxdepth=5):
     return set_filename(s, name)
 
 
+def tiny_pattern_pfm(dst):
+    """A small procedural image (24 x 20: not a power of two, so the reference's MIPMap resamples it) for the committed
+    texture fixture: own authoring, written on the spot - the lowered scene carries the MIP pyramid the reference built."""
+    import numpy as np
+    y, x = np.mgrid[0:20, 0:24]
+    r = 0.15 + 0.8 * (((x // 3) + (y // 4)) % 2)
+    g = 0.2 + 0.6 * np.abs(np.sin(0.7 * x)) * (y / 19.0)
+    b = 0.9 - 0.7 * ((x + 2 * y) % 5) / 4.0
+    rgb = np.stack([r, g, b], -1).astype("<f4")
+    os.makedirs(os.path.dirname(dst), exist_ok=True)
+    with open(dst, "wb") as f:
+        f.write(b"PF\n24 20\n-1.0\n")
+        f.write(rgb.tobytes())
+
+
+def tiny_tex(w, h, spp, name, maxdepth=5):
+    """Committed fixture for the extended materials: the tiny scene with a substrate floor whose Kd is an
+    EWA-filtered image map and whose bump map is the same image scaled by a constant, and with a trilinear-filtered image
+    map + bump map on the sphere that has per-vertex normals and uvs (dndu / dndv)."""
+    s = read(os.path.join(TESTS_GOLDEN, "tiny.pbrt"))
+    tex = ('Texture "tmap" "color" "imagemap" "string filename" "textures/tiny_pattern.pfm" "float uscale" 2 "float vscale" 2\n'
+           'Texture "tbump-tex" "float" "imagemap" "string filename" "textures/tiny_pattern.pfm" "float uscale" 2 "float vscale" 2\n'
+           'Texture "sbump" "float" "scale" "texture tex1" "tbump-tex" "float tex2" [-.05]\n'
+           'Texture "tri" "color" "imagemap" "string filename" "textures/tiny_pattern.pfm" "bool trilinear" ["true"] "float uscale" 3\n'
+           'Texture "tribump" "float" "imagemap" "string filename" "textures/tiny_pattern.pfm" "bool trilinear" ["true"] "float uscale" 3 "float scale" [.02]\n')
+    a = 'Material "matte" "color Kd" [.55 .5 .45]'
+    b = 'Material "plastic" "color Kd" [.45 .2 .15] "color Ks" [.5 .5 .5] "float roughness" [.04]'
+    assert a in s and b in s
+    s = s.replace(a, tex + 'Material "substrate" "texture Kd" "tmap" "color Ks" [.4 .4 .4] "float uroughness" [.05] "float vroughness" [.2] '
+                  '"texture bumpmap" "sbump"')
+    s = s.replace(b, 'Material "plastic" "texture Kd" "tri" "color Ks" [.5 .5 .5] "float roughness" [.04] "texture bumpmap" "tribump"')
+    return set_filename(set_spp(set_res(s, w, h), spp), name)
+
+
+def tiny_direct(w, h, spp, name, maxdepth=5):
+    """Committed fixture for the directlighting integrator: the tiny scene under strategy "all", its area
+    lights with 4, 2 and 1 samples, plus the point light."""
+    s = read(os.path.join(TESTS_GOLDEN, "tiny.pbrt"))
+    s = s.replace('SurfaceIntegrator "path" "integer maxdepth" [5]', 'SurfaceIntegrator "directlighting"')
+    s = s.replace('AreaLightSource "area" "color L" [40 36 30]', 'AreaLightSource "area" "color L" [40 36 30] "integer nsamples" [4]')
+    s = s.replace('AreaLightSource "area" "color L" [9 10 12]', 'AreaLightSource "area" "color L" [9 10 12] "integer nsamples" [2]')
+    assert "directlighting" in s and '"integer nsamples" [4]' in s
+    return set_filename(set_spp(set_res(s, w, h), spp), name)
+
+
 def tiny(w, h, spp, name, maxdepth=5):
     s = read(os.path.join(TESTS_GOLDEN, "tiny.pbrt"))
     return set_filename(set_spp(set_res(s, w, h), spp), name)
@@ -279,6 +324,9 @@ CONFIGS = {
     "synth_1m":        (lambda w, h, spp, name, maxdepth=5: synth(w, h, spp, name, maxdepth, ntris=1000000, chunks=10), 1024, 576, 16, 0, 0, 0),
     # small committed fixture
     "tiny":            (tiny, 48, 48, 4, 700, 40, 0),
+    # two more committed fixtures (tests/golden/): extended materials, directlighting
+    "tiny_tex":        (tiny_tex, 48, 48, 4, 300, 40, 0),
+    "tiny_direct":     (tiny_direct, 48, 48, 4, 300, 8, 0),
 }
 
 
@@ -393,12 +441,13 @@ def main():
             pfm = os.path.join(SCENES, "textures", tex + ".pfm")
             if not os.path.exists(pfm):
                 exr_to_pfm(os.path.join(REF, "scenes", "textures", tex + ".exr"), pfm)
+    tiny_pattern_pfm(os.path.join(SCENES, "textures", "tiny_pattern.pfm"))
     for name in names:
         build, w, h, spp, npix, nrng, img_spp = CONFIGS[name]
         s = build(w, h, spp, name)
         write(os.path.join(SCENES, name + ".pbrt"), s)
         write(os.path.join(SCENES, name + ".gpu.pbrt"), with_gpupath(s))
-        prefix = os.path.join(TESTS_GOLDEN if name == "tiny" else GOLDEN, name)
+        prefix = os.path.join(TESTS_GOLDEN if name.startswith("tiny") else GOLDEN, name)
         env = dict(os.environ, SPT_DUMP_PREFIX=prefix, SPT_DUMP_PIXELS=str(max(npix, 1)),
                    SPT_DUMP_NRNG=str(max(nrng, 1)), SPT_DUMP_LI="1" if npix else "0")
         t0 = time.time()

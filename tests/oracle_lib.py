@@ -127,7 +127,8 @@ def render(scene, params=None, film=None):
 
 def golden_cases(big=True):
     """[(name, scene path, golden path)] of every golden set present (the tiny one always is)."""
-    cases = [("tiny", os.path.join(GOLDEN_SMALL, "tiny.spt"), os.path.join(GOLDEN_SMALL, "tiny.golden"))]
+    cases = [(n, os.path.join(GOLDEN_SMALL, n + ".spt"), os.path.join(GOLDEN_SMALL, n + ".golden"))
+             for n in ("tiny", "tiny_tex", "tiny_direct") if os.path.exists(os.path.join(GOLDEN_SMALL, n + ".golden"))]
     if big and os.path.isdir(GOLDEN_BIG):
         for f in sorted(os.listdir(GOLDEN_BIG)):
             if f.endswith(".golden"):
