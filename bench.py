@@ -191,7 +191,8 @@ def main():
 
     scene_spt = os.path.join(ROOT, "assets", "_lowered", args.workload + ".spt")
     if not os.path.exists(scene_spt) and args.workload.startswith("synth") and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "bin", "oracle_dump")):
-        # synthetic workloads are generated on the spot (text -> the built reference's parser + BVH build -> lowered scene)
+        # synthetic workloads are generated on the spot: .pbrt text -> the built reference's own parser + BVH build (the host
+        # side of the boundary, which stays on the CPU by design) -> lowered scene. Scene preparation, outside every timed region.
         if rank == 0:
             subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "make_golden.py"), "--only", args.workload], check=True,
                            stdout=sys.stderr)

@@ -1,8 +1,8 @@
-"""GPU-box diagnostic: per-sample radiance of the CUDA path for the reference's own sample vectors, saved next to
+"""TEST INFRASTRUCTURE (uses the golden vectors through tests/oracle_lib.py). GPU-box diagnostic: per-sample radiance of the CUDA path for the reference's own sample vectors, saved next to
 the reference values so disagreements can be classified offline (which material, which bounce)."""
 import os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # tests/tools/ -> repo root
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import oracle_lib as O
 from pbrt_v2_spectral_b200 import capi
