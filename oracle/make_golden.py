@@ -330,17 +330,19 @@ CONFIGS = {
 }
 
 
-# full-size workload -> the small golden scene it shares every table with (same scene file, other resolution / spp)
-DELTA_BASE = {"killeroo_path": "killeroo_small", "bunny_path": "bunny_small", "metal_path": "metal_shipped_small",
-              "ssenv_path": "ssenv_shipped_small", "killeroo_direct": "killeroo_direct_small",
-              "bunny_shipped": "bunny_shipped_small"}
+# small golden scene -> the full-size bench workload (assets/_lowered/, product data) it shares every table with: same scene
+# file, other resolution / spp. The golden scene is stored as a delta of the workload, never the other way round: bench.py
+# reads nothing under oracle/.
+DELTA_BASE = {"killeroo_small": "killeroo_path", "bunny_small": "bunny_path", "metal_shipped_small": "metal_path",
+              "ssenv_shipped_small": "ssenv_path", "killeroo_direct_small": "killeroo_direct",
+              "bunny_shipped_small": "bunny_shipped"}
 
 
 def write_delta(path, name):
-    """Replace a full-size lowered scene by {base_scene, camera, film, params, film_filename} when every other array is
-    byte-identical to its small golden variant (checked): keeps the snapshot shipped to the GPU box small."""
+    """Replace a golden lowered scene by {base_scene, camera, film, params, film_filename} when every other array is
+    byte-identical to the full-size workload's (checked): keeps the snapshot shipped to the GPU box small."""
     base = DELTA_BASE.get(name)
-    base_path = os.path.join(GOLDEN, (base or "") + ".spt")
+    base_path = os.path.join(LOWERED, (base or "") + ".spt")
     if not base or not os.path.exists(base_path):
         return
     sys.path.insert(0, REPO)
@@ -424,7 +426,7 @@ def main():
     ap.add_argument("--only", default="", help="comma-separated config names")
     args = ap.parse_args()
     names = [n for n in CONFIGS if not args.only or n in args.only.split(",")]
-    names.sort(key=lambda n: n in DELTA_BASE)          # small golden variants first: the full-size workloads refer to them
+    names.sort(key=lambda n: (n in DELTA_BASE, n == "ssenv_path"))   # full-size workloads first (metal_path before ssenv_path): the golden variants refer to them
     # the synthetic scenes are written from scratch and lowered by the BUILT reference (oracle/_ref/bin/oracle_dump,
     # which travels with the repo): they can be generated where the reference source tree is absent (the GPU box)
     need_ref = any(not n.startswith("synth") for n in names)
@@ -459,9 +461,10 @@ def main():
             os.makedirs(LOWERED, exist_ok=True)
             dst = os.path.join(LOWERED, name + ".spt")
             shutil.move(prefix + ".spt", dst)
-            write_delta(dst, name)
-        if name == "ssenv_shipped_small":
-            share_arrays(os.path.join(GOLDEN, name + ".spt"), os.path.join(GOLDEN, "metal_shipped_small.spt"))
+            if name == "ssenv_path":
+                share_arrays(dst, os.path.join(LOWERED, "metal_path.spt"))
+        if npix and name in DELTA_BASE:
+            write_delta(prefix + ".spt", name)
         print("%-16s lowered + golden in %.1fs" % (name, time.time() - t0), flush=True)
         if name.startswith("synth"):                 # tens of MB of text per scene: regenerable, not shipped
             for f in (name + ".pbrt", name + ".gpu.pbrt"):
