@@ -77,7 +77,17 @@ public:
         SptFilm *gf = api.film_create(&ls.film);
         if (!gf) Severe("Renderer \"gpupath\": spt_film_create failed: %s", api.last_error());
         ls.params.seed = (uint64_t)seed;
-        if (api.render(gs, &ls.camera, gf, &ls.params) != SPT_OK)
+        int rc = api.render(gs, &ls.camera, gf, &ls.params);
+        if (rc == SPT_ERR_UNSUPP) {
+            // the library knows a combination it does not implement that the lowering let through (today: none): the
+            // reference's own renderer takes the scene, nothing is approximated. Any other failure is fatal - no CPU path.
+            Error("Renderer \"gpupath\": %s; rendering with the CPU SamplerRenderer instead.", api.last_error());
+            api.film_destroy(gf);
+            api.scene_destroy(gs);
+            cpu->Render(scene);
+            return;
+        }
+        if (rc != SPT_OK)
             Severe("Renderer \"gpupath\": spt_render failed: %s", api.last_error());
         SptStats st;
         if (api.get_stats(gs, &st) == SPT_OK)
