@@ -1799,4 +1799,45 @@ void orc_render(const SptSceneDesc *sc, const SptCameraDesc *cam, const SptFilmD
     }
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* Hooks on single functions of the restatement, for tests that compare them with the product's device code compiled
+ * for the host (tests/host_shim/, tests/test_device_code_on_host.py). Same arguments as the hd_* functions there. */
+void orc_measured_f(const SptSceneDesc *sc, int table, const float *wo, const float *wi, int n, float *out) {
+    for (int i = 0; i < n; ++i) {
+        float *o = out + (size_t)NB * i;
+        for (int c = 0; c < NB; ++c) o[c] = 0.f;
+        measured_f(sc, sc->brdfs + table, V(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]), V(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), o);
+    }
+}
+void orc_tex_evaluate(const SptSceneDesc *sc, int tex, const float *uvd, int n, float *out) {
+    const SptTexture *t = sc->textures + tex;
+    for (int i = 0; i < n; ++i) {
+        UVDiff df = { uvd[6 * i + 2], uvd[6 * i + 3], uvd[6 * i + 4], uvd[6 * i + 5] };
+        tex_evaluate(sc, t, uvd[6 * i], uvd[6 * i + 1], &df, out + (size_t)t->channels * i);
+    }
+}
+/* shading frame + image-mapped Kd (as RGB) at the first hit of camera samples known to hit BVH slot slot[i] */
+void orc_first_vertex_frame(const SptSceneDesc *sc, const SptCameraDesc *cam, int spp, const float *samples, const uint32_t *slot,
+                            const float *t, int n, float *out) {
+    (void)t;
+    for (int i = 0; i < n; ++i) {
+        Ray ray; RayDiff rd;
+        camera_ray_diff(cam, samples + 5 * (size_t)i, spp, &ray, &rd);
+        uint32_t s; Hit isect;
+        float *o = out + 12 * (size_t)i;
+        for (int k = 0; k < 12; ++k) o[k] = 0.f;
+        if (!bvh_intersect(sc, &ray, 0, &s, &isect, NULL, NULL) || s != slot[i]) continue;
+        BSDF b; v3 n_s;
+        make_bsdf(sc, s, &isect, &rd, &b, &n_s);
+        o[0] = b.nn.x; o[1] = b.nn.y; o[2] = b.nn.z; o[3] = b.sn.x; o[4] = b.sn.y; o[5] = b.sn.z;
+        o[6] = b.tn.x; o[7] = b.tn.y; o[8] = b.tn.z;
+        const SptMaterial *m = sc->materials + sc->prim_material[s];
+        if (m->tex_kd >= 0) {
+            UVDiff df;
+            compute_differentials(&isect, &rd, &df);
+            tex_evaluate(sc, sc->textures + m->tex_kd, isect.u, isect.v, &df, o + 9);
+        }
+    }
+}
+
 int orc_nbands(void) { return NB; }

@@ -33,6 +33,11 @@ void orc_gen_sample(uint64_t seed, int32_t px, int32_t py, int32_t s, int32_t sp
  * spt_render on small images. c: [y][x][NBANDS], weight: [y][x]. */
 void orc_render(const SptSceneDesc *scene, const SptCameraDesc *cam, const SptFilmDesc *film,
                 const SptRenderParams *params, float *c, float *weight);
+/* single functions of the restatement, for comparison with the product's device code compiled for the host (tests/host_shim/) */
+void orc_measured_f(const SptSceneDesc *scene, int table, const float *wo, const float *wi, int n, float *out);
+void orc_tex_evaluate(const SptSceneDesc *scene, int tex, const float *uvd, int n, float *out);
+void orc_first_vertex_frame(const SptSceneDesc *scene, const SptCameraDesc *cam, int spp, const float *samples,
+                            const uint32_t *slot, const float *t, int n, float *out);
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,100 @@
+"""The product's DEVICE functions (pbrt_v2_spectral_b200/csrc/shade.cuh) compiled for the host with g++ and compared with
+the oracle - which is pinned bit-exactly against the reference - on a machine without a GPU: the kd-tree look-up of the
+measured BRDF (with its 3-nearest-neighbour shortcut to the reference's final search radius), the image-texture filters
+(EWA, trilinear), and the first-vertex shading frame (ray differentials, bump map, image-mapped Kd). Same compiler flags
+and libm on both sides, so the comparison is bit for bit. The CUDA build of the same headers is what `-m gpu` tests."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SHIM_SRC = os.path.join(ROOT, "tests", "host_shim", "device_on_host.cpp")
+SHIM_SO = os.path.join(ROOT, "oracle", "_ref", "libdevhost.so")      # built artefact, next to the oracle's
+
+
+@pytest.fixture(scope="module")
+def shim():
+    deps = [SHIM_SRC, os.path.join(ROOT, "tests", "host_shim", "fake", "cuda_runtime.h"), os.path.join(ROOT, "include", "spt.h")]
+    csrc = os.path.join(ROOT, "pbrt_v2_spectral_b200", "csrc")
+    deps += [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cuh", ".h"))]
+    if not os.path.exists(SHIM_SO) or any(os.path.getmtime(SHIM_SO) < os.path.getmtime(d) for d in deps):
+        os.makedirs(os.path.dirname(SHIM_SO), exist_ok=True)
+        subprocess.run(["g++", "-O2", "-m64", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-std=c++17", "-w",
+                        "-I" + os.path.join(ROOT, "tests", "host_shim", "fake"), "-I" + os.path.join(ROOT, "include"), "-I" + csrc,
+                        "-o", SHIM_SO, SHIM_SRC, "-lm"], check=True)
+    return C.CDLL(SHIM_SO)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _unit(rng, n, upper=True):
+    v = rng.normal(size=(n, 3)).astype(np.float32)
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    if upper:
+        v[:, 2] = np.abs(v[:, 2])
+    return np.ascontiguousarray(v, np.float32)
+
+
+def _case(name):
+    sp, gp = os.path.join(O.GOLDEN_BIG, name + ".spt"), os.path.join(O.GOLDEN_BIG, name + ".golden")
+    if not os.path.exists(sp):
+        sp, gp = os.path.join(O.GOLDEN_SMALL, name + ".spt"), os.path.join(O.GOLDEN_SMALL, name + ".golden")
+    if not os.path.exists(sp):
+        pytest.skip("golden set %s not generated" % name)
+    return O.load_case(sp, gp)
+
+
+def test_measured_brdf_lookup_bit_exact(shim):
+    scene, _ = _case("bunny_measured_small")
+    rng = np.random.default_rng(3)
+    n = 4000
+    wo, wi = _unit(rng, n), _unit(rng, n, upper=False)
+    wi[:100] = wo[:100] * np.float32(-1.0)                     # degenerate pairs (wo + wi = 0 in the remap)
+    wi[100:200, 2] = 0.0                                       # grazing
+    a = np.empty((n, O.D.NBANDS), np.float32); b = np.empty_like(a)
+    shim.hd_measured_f(C.byref(scene.desc), 0, _p(wo), _p(wi), n, _p(a))
+    O.lib().orc_measured_f(C.byref(scene.desc), 0, _p(wo), _p(wi), n, _p(b))
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert np.isfinite(b).mean() > 0.9 and b[np.isfinite(b)].max() > 0
+
+
+@pytest.mark.parametrize("name", ["tiny_tex", "metal_shipped_small"])
+def test_image_texture_filters_bit_exact(shim, name):
+    scene, _ = _case(name)
+    rng = np.random.default_rng(5)
+    for tex in range(scene.desc.n_textures):
+        n = 3000
+        uvd = np.empty((n, 6), np.float32)
+        uvd[:, :2] = rng.uniform(-1.5, 2.5, (n, 2))
+        scale = 10.0 ** rng.uniform(-5, -0.5, (n, 1))          # footprints from far below a texel to many texels
+        uvd[:, 2:] = rng.normal(size=(n, 4)) * scale
+        uvd[:300, 2:] = 0.0                                    # no differentials: level-0 bilinear (later path vertices)
+        uvd[300:400, 4:] = 0.0                                 # degenerate minor axis
+        ch = int(np.frombuffer(scene.a["textures"].tobytes(), np.int32).reshape(-1, 16)[tex, 0])
+        a = np.empty((n, ch), np.float32); b = np.empty_like(a)
+        shim.hd_tex_evaluate(C.byref(scene.desc), tex, _p(uvd), n, _p(a))
+        O.lib().orc_tex_evaluate(C.byref(scene.desc), tex, _p(uvd), n, _p(b))
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), "texture %d of %s" % (tex, name)
+
+
+@pytest.mark.parametrize("name", ["tiny_tex", "metal_shipped_small", "killeroo_small"])
+def test_first_vertex_frame_bit_exact(shim, name):
+    """camera_ray_diff -> shape_record -> compute_differentials -> Material::Bump / Kd look-up -> BSDF frame."""
+    scene, g = _case(name)
+    slot, pid, t = O.trace_closest(scene, g["rays"])
+    hit = np.flatnonzero(slot != 0xffffffff)[:4000]
+    smp = np.ascontiguousarray(g["samples"][hit, :5], np.float32)
+    s = np.ascontiguousarray(slot[hit]); tt = np.ascontiguousarray(t[hit])
+    spp = int(g["meta"][0])
+    a = np.zeros((len(hit), 12), np.float32); b = np.zeros_like(a)
+    shim.hd_first_vertex_frame(C.byref(scene.desc), C.byref(scene.camera), spp, _p(smp), _p(s), _p(tt), len(hit), _p(a))
+    O.lib().orc_first_vertex_frame(C.byref(scene.desc), C.byref(scene.camera), spp, _p(smp), _p(s), _p(tt), len(hit), _p(b))
+    assert np.any(b != 0)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
