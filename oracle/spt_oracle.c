@@ -1840,4 +1840,18 @@ void orc_first_vertex_frame(const SptSceneDesc *sc, const SptCameraDesc *cam, in
     }
 }
 
+void orc_light_sample(const SptSceneDesc *sc, int light, const float *p, const float *u, int n, float *out) {
+    for (int i = 0; i < n; ++i) {
+        LightSampleResult lr;
+        light_sample(sc, sc->lights + light, V(p[3 * i], p[3 * i + 1], p[3 * i + 2]), 0.f, u[3 * i], u[3 * i + 1], u[3 * i + 2], &lr);
+        float *o = out + 9 * (size_t)i;
+        o[0] = lr.wi.x; o[1] = lr.wi.y; o[2] = lr.wi.z; o[3] = lr.pdf;
+        o[4] = lr.shadow.d.x; o[5] = lr.shadow.d.y; o[6] = lr.shadow.d.z; o[7] = lr.shadow.maxt; o[8] = is_black(lr.Li) ? 1.f : 0.f;
+    }
+}
+void orc_light_pdf(const SptSceneDesc *sc, int light, const float *p, const float *w, int n, float *out) {
+    for (int i = 0; i < n; ++i)
+        out[i] = light_pdf(sc, sc->lights + light, V(p[3 * i], p[3 * i + 1], p[3 * i + 2]), V(w[3 * i], w[3 * i + 1], w[3 * i + 2]));
+}
+
 int orc_nbands(void) { return NB; }

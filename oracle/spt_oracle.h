@@ -38,6 +38,8 @@ void orc_measured_f(const SptSceneDesc *scene, int table, const float *wo, const
 void orc_tex_evaluate(const SptSceneDesc *scene, int tex, const float *uvd, int n, float *out);
 void orc_first_vertex_frame(const SptSceneDesc *scene, const SptCameraDesc *cam, int spp, const float *samples,
                             const uint32_t *slot, const float *t, int n, float *out);
+void orc_light_sample(const SptSceneDesc *scene, int light, const float *p, const float *u, int n, float *out);
+void orc_light_pdf(const SptSceneDesc *scene, int light, const float *p, const float *w, int n, float *out);
 #ifdef __cplusplus
 }
 #endif

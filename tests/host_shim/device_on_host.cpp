@@ -4,8 +4,27 @@
 #include "shade.cuh"
 #include "camera.cuh"
 
+#include <vector>
+static std::vector<float> g_light_cdf;     // per-call scratch of the single-threaded tests
+
 static void dev_scene(const SptSceneDesc *d, DevScene *v) {
     memset(v, 0, sizeof(*v));
+    // Distribution1D of each area light's ShapeSet, as spt_scene_create builds it (csrc/spt_api.cu)
+    g_light_cdf.assign(d->n_light_shapes + d->n_lights + 1, 0.f);
+    for (uint32_t li = 0; li < d->n_lights; ++li) {
+        const SptLight &l = d->lights[li];
+        if (l.type != SPT_LIGHT_AREA) continue;
+        float *c = &g_light_cdf[l.shape_first + li];
+        int n = l.shape_count;
+        c[0] = 0.f;
+        for (int i = 1; i < n + 1; ++i) c[i] = c[i - 1] + d->light_shapes[l.shape_first + i - 1].area / n;
+        float funcInt = c[n];
+        if (funcInt == 0.f) for (int i = 1; i < n + 1; ++i) c[i] = float(i) / float(n);
+        else for (int i = 1; i < n + 1; ++i) c[i] /= funcInt;
+    }
+    v->light_cdf = g_light_cdf.data();
+    v->env_func = d->env_func; v->env_cdf = d->env_cdf; v->env_func_int = d->env_func_int;
+    v->env_marg_func = d->env_marg_func; v->env_marg_cdf = d->env_marg_cdf; v->env_marg_int = d->env_marg_int;
     v->n_nodes = d->n_nodes; v->n_prims = d->n_prims;
     v->prim_kind = d->prim_kind; v->prim_flags = d->prim_flags; v->prim_id = d->prim_id; v->prim_data = d->prim_data;
     v->prim_material = d->prim_material; v->prim_light = d->prim_light; v->prim_xform = d->prim_xform;
@@ -60,6 +79,25 @@ void hd_first_vertex_frame(const SptSceneDesc *d, const SptCameraDesc *cam, int 
         o[0] = b.nn.x; o[1] = b.nn.y; o[2] = b.nn.z; o[3] = b.sn.x; o[4] = b.sn.y; o[5] = b.sn.z;
         o[6] = b.tn.x; o[7] = b.tn.y; o[8] = b.tn.z; o[9] = b.kd_rgb[0]; o[10] = b.kd_rgb[1]; o[11] = b.kd_rgb[2];
     }
+}
+
+// Light::Sample_L (+ Light::Pdf of the sampled direction) for n points p and sample values {uPos0, uPos1, uComponent}:
+// out 9 floats {wi, pdf, shadow direction, shadow maxt, black}
+void hd_light_sample(const SptSceneDesc *d, int light, const float *p, const float *u, int n, float *out) {
+    DevScene sc; dev_scene(d, &sc);
+    for (int i = 0; i < n; ++i) {
+        LightSampleResult lr;
+        light_sample(sc, light, V(p[3 * i], p[3 * i + 1], p[3 * i + 2]), u[3 * i], u[3 * i + 1], u[3 * i + 2], &lr, false);
+        float *o = out + 9 * (size_t)i;
+        o[0] = lr.wi.x; o[1] = lr.wi.y; o[2] = lr.wi.z; o[3] = lr.pdf;
+        o[4] = lr.shadow_d.x; o[5] = lr.shadow_d.y; o[6] = lr.shadow_d.z; o[7] = lr.shadow_maxt; o[8] = lr.black ? 1.f : 0.f;
+    }
+}
+// Light::Pdf(p, w) for n points and directions
+void hd_light_pdf(const SptSceneDesc *d, int light, const float *p, const float *w, int n, float *out) {
+    DevScene sc; dev_scene(d, &sc);
+    for (int i = 0; i < n; ++i)
+        out[i] = light_pdf(sc, light, V(p[3 * i], p[3 * i + 1], p[3 * i + 2]), V(w[3 * i], w[3 * i + 1], w[3 * i + 2]));
 }
 
 }  // extern "C"
