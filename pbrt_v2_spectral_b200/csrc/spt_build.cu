@@ -2,7 +2,9 @@
 // reference's arrays AFTER they are in HBM, so the host does not spend 1.7 ms per scene (131 k nodes, 66 k primitives)
 // building it: leaf flags in the reference nodes, the pair-node array (one 64-byte node per interior node: both children's
 // bounds + child codes, see spt_device.cuh) and the triangle vertices pre-gathered per BVH slot.
+#ifndef SPT_HOST_SHIM                     // tests/host_shim compiles the kernels below for the host, without CUB and the launcher
 #include <cub/device/device_scan.cuh>
+#endif
 #include "launch.h"
 
 struct RefNodeD { float b[6]; uint32_t off; uint32_t meta; };     // LinearBVHNode: meta = nPrims | axis << 8 | pad << 16
@@ -50,6 +52,7 @@ __global__ void k_tri_gather(const uint8_t *prim_kind, const uint32_t *prim_data
     }
 }
 
+#ifndef SPT_HOST_SHIM
 size_t spt_relayout_scratch_bytes(uint32_t n_nodes) {
     size_t tmp = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp, (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n_nodes);
@@ -81,3 +84,4 @@ cudaError_t spt_launch_relayout(cudaStream_t st, void *nodes, uint32_t n_nodes, 
     if (e == cudaSuccess) e = cudaGetLastError();
     return e;
 }
+#endif

@@ -27,3 +27,29 @@ using std::isinf;
 using std::isnan;
 using std::max;
 using std::min;
+
+// ---- what the KERNELS need on top: a "warp" of one lane, a grid of one thread ----------------------------------------
+#define __launch_bounds__(...)
+#define __shared__ static
+#define __restrict__
+struct uint2 { uint32_t x, y; };
+static inline uint2 make_uint2(uint32_t x, uint32_t y) { uint2 r = { x, y }; return r; }
+struct HostDim3 { unsigned x, y, z; };
+static const HostDim3 threadIdx = { 0, 0, 0 }, blockIdx = { 0, 0, 0 }, blockDim = { 1, 1, 1 }, gridDim = { 1, 1, 1 };
+static inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
+static inline unsigned __activemask() { return 1u; }
+static inline bool __any_sync(unsigned, int p) { return p != 0; }
+static inline bool __all_sync(unsigned, int p) { return p != 0; }
+template <typename T> static inline T __shfl_sync(unsigned, T v, int, int = 32) { return v; }
+template <typename T> static inline T __shfl_up_sync(unsigned, T v, unsigned, int = 32) { return v; }
+template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int, int = 32) { return v; }
+static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+static inline int __ffs(int x) { return __builtin_ffs(x); }
+static inline void __syncwarp(unsigned = 0xffffffffu) {}
+static inline void __syncthreads() {}
+template <typename T> static inline T atomicAdd(T *p, T v) { T o = *p; *p += v; return o; }
+static inline unsigned atomicOr(unsigned *p, unsigned v) { unsigned o = *p; *p |= v; return o; }
+using std::isfinite;
+typedef void *cudaStream_t;
+typedef int cudaError_t;
+enum { cudaSuccess = 0 };

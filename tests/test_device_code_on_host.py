@@ -1,5 +1,6 @@
-"""The product's DEVICE functions (pbrt_v2_spectral_b200/csrc/shade.cuh) compiled for the host with g++ and compared with
-the oracle - which is pinned bit-exactly against the reference - on a machine without a GPU: the kd-tree look-up of the
+"""The product's DEVICE code (pbrt_v2_spectral_b200/csrc) compiled for the host with g++ and compared with the reference's
+golden vectors and with the oracle - which is pinned bit-exactly against the reference - on a machine without a GPU: the
+traversal kernel itself and the scene re-layout kernels (a warp of one lane), the kd-tree look-up of the
 measured BRDF (with its 3-nearest-neighbour shortcut to the reference's final search radius), the image-texture filters
 (EWA, trilinear), and the first-vertex shading frame (ray differentials, bump map, image-mapped Kd). Same compiler flags
 and libm on both sides, so the comparison is bit for bit. The CUDA build of the same headers is what `-m gpu` tests."""
@@ -17,17 +18,55 @@ SHIM_SRC = os.path.join(ROOT, "tests", "host_shim", "device_on_host.cpp")
 SHIM_SO = os.path.join(ROOT, "oracle", "_ref", "libdevhost.so")      # built artefact, next to the oracle's
 
 
-@pytest.fixture(scope="module")
-def shim():
-    deps = [SHIM_SRC, os.path.join(ROOT, "tests", "host_shim", "fake", "cuda_runtime.h"), os.path.join(ROOT, "include", "spt.h")]
+def _build(so, src):
+    deps = [src, os.path.join(ROOT, "tests", "host_shim", "fake", "cuda_runtime.h"), os.path.join(ROOT, "include", "spt.h")]
     csrc = os.path.join(ROOT, "pbrt_v2_spectral_b200", "csrc")
-    deps += [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cuh", ".h"))]
-    if not os.path.exists(SHIM_SO) or any(os.path.getmtime(SHIM_SO) < os.path.getmtime(d) for d in deps):
-        os.makedirs(os.path.dirname(SHIM_SO), exist_ok=True)
+    deps += [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cuh", ".h", "spt_build.cu"))]
+    if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(d) for d in deps):
+        os.makedirs(os.path.dirname(so), exist_ok=True)
         subprocess.run(["g++", "-O2", "-m64", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-std=c++17", "-w",
                         "-I" + os.path.join(ROOT, "tests", "host_shim", "fake"), "-I" + os.path.join(ROOT, "include"), "-I" + csrc,
-                        "-o", SHIM_SO, SHIM_SRC, "-lm"], check=True)
-    return C.CDLL(SHIM_SO)
+                        "-o", so, src, "-lm"], check=True)
+    return C.CDLL(so)
+
+
+@pytest.fixture(scope="module")
+def trace_shim():
+    return _build(os.path.join(ROOT, "oracle", "_ref", "libtracehost.so"), os.path.join(ROOT, "tests", "host_shim", "trace_on_host.cpp"))
+
+
+ALL_CASES = O.golden_cases()
+
+
+@pytest.mark.parametrize("case", ALL_CASES, ids=[c[0] for c in ALL_CASES])
+def test_traversal_kernel_and_relayout_bit_exact(trace_shim, case):
+    """The traversal KERNEL source (k_trace_v1: pair-node walk, min/max slab form, leaf tests) and the re-layout kernels
+    (leaf flags, pair nodes, vertex pre-gather), compiled for the host as a warp of one lane, against the reference's golden
+    vectors: first-hit primitive ids and distances of camera and secondary rays bit for bit, any-hit verdicts."""
+    name, sp, gp = case
+    scene, g = O.load_case(sp, gp)
+    rays = np.ascontiguousarray(g["rays"], np.float32)
+    slot = np.empty(len(rays), np.uint32); t = np.empty(len(rays), np.float32)
+    assert trace_shim.hd_trace(C.byref(scene.desc), _p(rays), len(rays), 0, _p(slot), _p(t)) == 0
+    pid = np.where(slot == 0xffffffff, 0, scene.a["prim_id"][np.minimum(slot, len(scene.a["prim_id"]) - 1)])
+    assert np.array_equal(pid, g["prim_id"])
+    assert np.array_equal(t.view(np.uint32), g["t_hit"].view(np.uint32))
+    m = g["prim_id"] != 0
+    unbounded = np.ascontiguousarray(g["rays2"][m]); unbounded[:, 7] = np.inf
+    s2 = np.empty(len(unbounded), np.uint32); t2 = np.empty(len(unbounded), np.float32)
+    trace_shim.hd_trace(C.byref(scene.desc), _p(unbounded), len(unbounded), 0, _p(s2), _p(t2))
+    pid2 = np.where(s2 == 0xffffffff, 0, scene.a["prim_id"][np.minimum(s2, len(scene.a["prim_id"]) - 1)])
+    assert np.array_equal(pid2, g["prim_id2"][m])
+    assert np.array_equal(t2.view(np.uint32), g["t_hit2"][m].view(np.uint32))
+    seg = np.ascontiguousarray(g["rays2"][m])
+    s3 = np.empty(len(seg), np.uint32)
+    trace_shim.hd_trace(C.byref(scene.desc), _p(seg), len(seg), 1, _p(s3), None)
+    assert np.array_equal((s3 != 0xffffffff).astype(np.uint8), g["any2"][m])
+
+
+@pytest.fixture(scope="module")
+def shim():
+    return _build(SHIM_SO, SHIM_SRC)
 
 
 def _p(a):
