@@ -44,6 +44,13 @@ template <typename T> static inline T __shfl_sync(unsigned, T v, int, int = 32) 
 template <typename T> static inline T __shfl_up_sync(unsigned, T v, unsigned, int = 32) { return v; }
 template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int, int = 32) { return v; }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+static inline unsigned __brev(unsigned n) {
+    n = (n << 16) | (n >> 16);
+    n = ((n & 0x00ff00ffu) << 8) | ((n & 0xff00ff00u) >> 8);
+    n = ((n & 0x0f0f0f0fu) << 4) | ((n & 0xf0f0f0f0u) >> 4);
+    n = ((n & 0x33333333u) << 2) | ((n & 0xccccccccu) >> 2);
+    return ((n & 0x55555555u) << 1) | ((n & 0xaaaaaaaau) >> 1);
+}
 static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline void __syncwarp(unsigned = 0xffffffffu) {}
 static inline void __syncthreads() {}

@@ -5,7 +5,30 @@
 #define SPT_HOST_SHIM 1
 #include "trace_kernels.cuh"
 #include "../../pbrt_v2_spectral_b200/csrc/spt_build.cu"
+#include "camera.cuh"
+#include "sampler.cuh"
 #include <vector>
+
+// K1 of csrc/spt_exact.cu is a __global__ in a .cu with launchers; its body is repeated here around the same device
+// functions (wave_pixel, pixel_key, ld2, camera_ray) so that the sample -> film position -> camera ray chain runs on the host.
+static void gen_camera_host(const RenderCfg &cfg, const SampleSource &src, float4 *ray_o, float4 *ray_d, float2 *img_xy) {
+    for (uint32_t i = 0; i < cfg.n_samples; ++i) {
+        int px, py;
+        uint32_t s = i & ((uint32_t)cfg.spp - 1u);
+        bool valid = wave_pixel(cfg, cfg.pixel_base + (i >> cfg.spp_shift), &px, &py);
+        if (!valid) { ray_o[i] = make_float4(0.f, 0.f, 0.f, 1.f); ray_d[i] = make_float4(0.f, 0.f, 1.f, -1.f); img_xy[i] = make_float2(-1e30f, -1e30f); continue; }
+        uint32_t pk = pixel_key(src.seed, pix_key(px, py));
+        float t2[2];
+        ld2(pk, 0, s, src.spp, t2);
+        float ix = px + t2[0], iy = py + t2[1];
+        ld2(pk, 1, s, src.spp, t2);
+        Ray ray;
+        camera_ray(cfg.cam, ix, iy, t2[0], t2[1], &ray);
+        ray_o[i] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.mint);
+        ray_d[i] = make_float4(ray.d.x, ray.d.y, ray.d.z, ray.maxt);
+        img_xy[i] = make_float2(ix, iy);
+    }
+}
 
 extern "C" {
 
@@ -43,6 +66,34 @@ int hd_trace(const SptSceneDesc *d, const float *rays, uint32_t n, int any, uint
     a.out_slot = out_slot; a.out_t = out_t; a.fetch_threshold = 14;
     if (any) k_trace_v1<true, false>(sc, a); else k_trace_v1<false, false>(sc, a);
     return 0;
+}
+
+// One 8x8-pixel tile at (x0, y0) of the product's generated samples: film positions and camera rays per slot
+// (n = 64 * spp slots; out_xy n x 2, out_rays n x 8), and for slot order see wave_pixel (csrc/wave.cuh).
+void hd_gen_tile(const SptCameraDesc *cam, uint64_t seed64, int x0, int y0, int spp, float *out_xy, float *out_rays) {
+    RenderCfg cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.cam = *cam; cfg.spp = spp;
+    for (cfg.spp_shift = 0; (1 << cfg.spp_shift) < spp; ++cfg.spp_shift) {}
+    cfg.x0 = x0; cfg.y0 = y0; cfg.x1 = x0 + 8; cfg.y1 = y0 + 8; cfg.tile = 8; cfg.tile_shift = 3; cfg.tilesX = 1; cfg.tilesY = 1;
+    cfg.rank = 0; cfg.nranks = 1; cfg.seed = (uint32_t)(seed64 ^ (seed64 >> 32)); cfg.pixel_base = 0; cfg.n_samples = 64u * (uint32_t)spp;
+    cfg.sub = 1;
+    SampleSource src; src.smp = nullptr; src.stride = 0; src.rng = nullptr; src.n_rng = 0; src.seed = cfg.seed; src.spp = (uint32_t)spp;
+    std::vector<float4> ro(cfg.n_samples), rd(cfg.n_samples);
+    std::vector<float2> xy(cfg.n_samples);
+    gen_camera_host(cfg, src, ro.data(), rd.data(), xy.data());
+    for (uint32_t i = 0; i < cfg.n_samples; ++i) {
+        out_xy[2 * i] = xy[i].x; out_xy[2 * i + 1] = xy[i].y;
+        float *r = out_rays + 8 * (size_t)i;
+        r[0] = ro[i].x; r[1] = ro[i].y; r[2] = ro[i].z; r[3] = rd[i].x; r[4] = rd[i].y; r[5] = rd[i].z; r[6] = ro[i].w; r[7] = rd[i].w;
+    }
+}
+// The ten values + Russian-roulette draw bounce b of sample s of pixel (px, py) consumes (bounce_dims, csrc/sampler.cuh)
+void hd_bounce_dims(uint64_t seed64, int px, int py, int s, int spp, int b, int have_lights, float *u11) {
+    SampleSource src; src.smp = nullptr; src.stride = 0; src.rng = nullptr; src.n_rng = 0;
+    src.seed = (uint32_t)(seed64 ^ (seed64 >> 32)); src.spp = (uint32_t)spp;
+    uint32_t pk = pixel_key(src.seed, pix_key(px, py));
+    bounce_dims(src, 0, pk, (uint32_t)s, b, have_lights != 0, u11, u11 + 10);
 }
 
 }  // extern "C"

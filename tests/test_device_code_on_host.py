@@ -177,3 +177,33 @@ def test_light_sampling_bit_exact(shim, name):
             shim.hd_light_pdf(C.byref(scene.desc), light, _p(p), _p(dirs), len(hit), _p(pa))
             O.lib().orc_light_pdf(C.byref(scene.desc), light, _p(p), _p(dirs), len(hit), _p(pb))
             assert np.array_equal(pa.view(np.uint32), pb.view(np.uint32)), "Pdf of light %d of %s" % (light, name)
+
+
+def test_generated_samples_match_the_restated_sampler(trace_shim):
+    """The product's own sampler (hashed (0,2)-sequences, csrc/sampler.cuh) and K1's sample -> film position -> camera ray
+    chain, run on the host, against the oracle's restatement of it (orc_gen_sample): the whole-render tests on the GPU
+    compare images made by the two and rely on the samples being the same numbers."""
+    scene, _ = _case("tiny")
+    spp, seed = 8, 1234567
+    n = 64 * spp
+    xy = np.empty((n, 2), np.float32); rays = np.empty((n, 8), np.float32)
+    trace_shim.hd_gen_tile(C.byref(scene.camera), C.c_uint64(seed), 16, 8, spp, _p(xy), _p(rays))
+    px, py = np.floor(xy[:, 0]).astype(int), np.floor(xy[:, 1]).astype(int)
+    assert px.min() == 16 and px.max() == 23 and py.min() == 8 and py.max() == 15
+    u11 = np.empty(11, np.float32)
+    for i in range(0, n, 7):
+        s = i & (spp - 1)
+        smp, rng = O.gen_samples(seed, int(px[i]), int(py[i]), spp, shutter=(scene.camera.shutter_open, scene.camera.shutter_close), n_rng=34)
+        assert np.array_equal(smp[s, :2].view(np.uint32), xy[i].view(np.uint32))
+        ref_ray = O.camera_rays(scene, smp[s:s + 1, :5])[0]
+        assert np.array_equal(ref_ray.view(np.uint32), rays[i].view(np.uint32))
+        for b in range(6):
+            trace_shim.hd_bounce_dims(C.c_uint64(seed), int(px[i]), int(py[i]), s, spp, b, 1, _p(u11))
+            if b < 3:
+                one, two = smp[s, 5 + 4 * b:9 + 4 * b], smp[s, 19 + 6 * b:25 + 6 * b]
+                want = np.array([one[1], two[0], two[1], one[0], two[2], two[3], one[2], two[4], two[5], one[3]], np.float32)
+                assert np.array_equal(u11[:10].view(np.uint32), want.view(np.uint32))
+            else:
+                k = (b - 3) * 10 + (b - 4 if b > 4 else 0)          # RNG draws consumed before bounce b (path.cpp:82,97)
+                assert np.array_equal(u11[:10].view(np.uint32), rng[s, k:k + 10].view(np.uint32))
+                assert u11[10].view(np.uint32) == rng[s, k + 10].view(np.uint32)
