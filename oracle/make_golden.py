@@ -322,6 +322,13 @@ CONFIGS = {
     "bunny_shipped":         (bunny_shipped, 640, 480, 256, 0, 0, 0),
     # config 5 recipe at 1 M triangles (BVH + pair nodes + vertices = 176 MB, larger than L2): optional bench workload
     "synth_1m":        (lambda w, h, spp, name, maxdepth=5: synth(w, h, spp, name, maxdepth, ntris=1000000, chunks=10), 1024, 576, 16, 0, 0, 0),
+    # first hits at BASELINE resolution (configs 1 and 2): 262 144 random pixels x 4 spp = 1 048 576 camera rays each, compact
+    # records (COMPACT below); the _mid variants (16 384 x 4 = 65 536 rays) are committed under tests/golden/ with the lowered
+    # scene xz-compressed, so that a fresh clone checks first hits on the real scenes, not only on the tiny fixtures
+    "killeroo_rays":     (killeroo, 700, 700, 4, 262144, 0, 0),
+    "bunny_rays":        (bunny, 640, 480, 4, 262144, 0, 0),
+    "killeroo_rays_mid": (killeroo, 700, 700, 4, 16384, 0, 0),
+    "bunny_rays_mid":    (bunny, 640, 480, 4, 16384, 0, 0),
     # small committed fixture
     "tiny":            (tiny, 48, 48, 4, 700, 40, 0),
     # two more committed fixtures (tests/golden/): extended materials, directlighting
@@ -333,7 +340,9 @@ CONFIGS = {
 # small golden scene -> the full-size bench workload (assets/_lowered/, product data) it shares every table with: same scene
 # file, other resolution / spp. The golden scene is stored as a delta of the workload, never the other way round: bench.py
 # reads nothing under oracle/.
-DELTA_BASE = {"killeroo_small": "killeroo_path", "bunny_small": "bunny_path", "metal_shipped_small": "metal_path",
+COMPACT = {"killeroo_rays", "bunny_rays", "killeroo_rays_mid", "bunny_rays_mid"}
+COMMITTED = {"killeroo_rays_mid", "bunny_rays_mid"}
+DELTA_BASE = {"killeroo_rays": "killeroo_path", "bunny_rays": "bunny_path", "killeroo_small": "killeroo_path", "bunny_small": "bunny_path", "metal_shipped_small": "metal_path",
               "ssenv_shipped_small": "ssenv_path", "killeroo_direct_small": "killeroo_direct",
               "bunny_shipped_small": "bunny_shipped"}
 
@@ -449,9 +458,10 @@ def main():
         s = build(w, h, spp, name)
         write(os.path.join(SCENES, name + ".pbrt"), s)
         write(os.path.join(SCENES, name + ".gpu.pbrt"), with_gpupath(s))
-        prefix = os.path.join(TESTS_GOLDEN if name.startswith("tiny") else GOLDEN, name)
+        prefix = os.path.join(TESTS_GOLDEN if name.startswith("tiny") or name in COMMITTED else GOLDEN, name)
         env = dict(os.environ, SPT_DUMP_PREFIX=prefix, SPT_DUMP_PIXELS=str(max(npix, 1)),
-                   SPT_DUMP_NRNG=str(max(nrng, 1)), SPT_DUMP_LI="1" if npix else "0")
+                   SPT_DUMP_NRNG=str(max(nrng, 1)), SPT_DUMP_LI="1" if npix else "0",
+                   SPT_DUMP_COMPACT="1" if name in COMPACT else "0")
         t0 = time.time()
         subprocess.run([os.path.join(OUT, "bin/oracle_dump"), "--quiet", name + ".gpu.pbrt"],
                        cwd=SCENES, env=env, check=True, stdout=subprocess.DEVNULL)
@@ -465,6 +475,15 @@ def main():
                 share_arrays(dst, os.path.join(LOWERED, "metal_path.spt"))
         if npix and name in DELTA_BASE:
             write_delta(prefix + ".spt", name)
+        if name in COMMITTED:
+            # committed fixtures: xz-compressed containers (the loader opens .xz transparently)
+            import lzma
+            for ext in (".spt", ".golden"):
+                with open(prefix + ext, "rb") as f:
+                    raw = f.read()
+                with open(prefix + ext + ".xz", "wb") as f:
+                    f.write(lzma.compress(raw, preset=9 | lzma.PRESET_EXTREME))
+                os.remove(prefix + ext)
         print("%-16s lowered + golden in %.1fs" % (name, time.time() - t0), flush=True)
         if name.startswith("synth"):                 # tens of MB of text per scene: regenerable, not shipped
             for f in (name + ".pbrt", name + ".gpu.pbrt"):

@@ -11,7 +11,9 @@
 //                    radiance SamplerRenderer::Li returns (src/renderers/samplerrenderer.cpp:225-247)
 //                    together with the RNG floats it consumed.
 // Environment: SPT_DUMP_PREFIX (required), SPT_DUMP_PIXELS (default 2000), SPT_DUMP_NRNG (64),
-//              SPT_DUMP_LI (1: also record radiance; 0: rays only).
+//              SPT_DUMP_LI (1: also record radiance; 0: rays only),
+//              SPT_DUMP_COMPACT (1: first hits only, 16 bytes per camera ray - {imageX, imageY}, primitive id, t - for the
+//              parity tests at BASELINE resolution: a million rays per config; pinhole cameras only).
 #include <algorithm>
 #include <stdio.h>
 #include <stdlib.h>
@@ -46,6 +48,8 @@ public:
         int nPixelsWanted = getenv("SPT_DUMP_PIXELS") ? atoi(getenv("SPT_DUMP_PIXELS")) : 2000;
         int nRng = getenv("SPT_DUMP_NRNG") ? atoi(getenv("SPT_DUMP_NRNG")) : 64;
         bool doLi = getenv("SPT_DUMP_LI") ? atoi(getenv("SPT_DUMP_LI")) != 0 : true;
+        bool compact = getenv("SPT_DUMP_COMPACT") ? atoi(getenv("SPT_DUMP_COMPACT")) != 0 : false;
+        if (compact) doLi = false;
 
         LoweredScene ls;
         std::string why;
@@ -68,7 +72,7 @@ public:
         long long extent = (long long)(x1 - x0) * (y1 - y0);
         int nPix = (int)std::min<long long>(nPixelsWanted, extent);
 
-        std::vector<float> outSamples, outRays, outT, outL, outRng, outRays2, outT2;
+        std::vector<float> outSamples, outRays, outT, outL, outRng, outRays2, outT2, outXY;
         std::vector<uint32_t> outId, outId2, outPixel;
         std::vector<uint8_t> outAny;
         MemoryArena arena;
@@ -84,6 +88,18 @@ public:
             LDPixelSample(px, py, sampler->shutterOpen, sampler->shutterClose, spp, samples, &buf[0], pixRng);
             for (int i = 0; i < spp; ++i) {
                 Sample &s = samples[i];
+                if (compact) {
+                    // first hit of the camera ray only, by the reference's own camera and BVH
+                    RayDifferential cray;
+                    camera->GenerateRayDifferential(s, &cray);
+                    Ray probe(cray);
+                    Intersection isect;
+                    bool hit = scene->Intersect(probe, &isect);
+                    outXY.push_back(s.imageX); outXY.push_back(s.imageY);
+                    outId.push_back(hit ? isect.primitiveId : 0u);
+                    outT.push_back(probe.maxt);
+                    continue;
+                }
                 outPixel.push_back((uint32_t)px); outPixel.push_back((uint32_t)py);
                 outSamples.push_back(s.imageX); outSamples.push_back(s.imageY);
                 outSamples.push_back(s.lensU); outSamples.push_back(s.lensV); outSamples.push_back(s.time);
@@ -150,6 +166,16 @@ public:
         if (!w.begin(std::string(prefix) + ".golden")) Severe("oracle_dump: cannot write golden file");
         int32_t meta[4] = { spp, nSampleFloats, nRng, nSpectralSamples };
         w.put("meta", 1, meta, sizeof(meta), 4);
+        if (compact) {
+            if (ls.camera.lens_radius != 0.f) Severe("oracle_dump: SPT_DUMP_COMPACT needs a pinhole camera");
+            w.vec("image_xy", 3, outXY, 2);
+            w.vec("prim_id", 2, outId);
+            w.vec("t_hit", 3, outT);
+            w.end();
+            fprintf(stderr, "oracle_dump: wrote %s.spt and %s.golden (compact: %d pixels x %d spp first hits)\n", prefix, prefix, nPix, spp);
+            delete origSample;
+            return;
+        }
         w.vec("pixel", 2, outPixel, 2);
         w.vec("samples", 3, outSamples, nSampleFloats);
         w.vec("rays", 3, outRays, 8);

@@ -40,8 +40,12 @@ def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     extra = ["-Xptxas", "-v"] if verbose else []
     objs = [os.path.join(OBJ, u[:-3] + ".o") for u, _ in UNITS]
-    cmds = [["nvcc", *COMMON, *flags, *extra, "-c", os.path.join(CSRC, u), "-o", o] for (u, flags), o in zip(UNITS, objs)]
-    with ThreadPoolExecutor(len(cmds)) as ex:
+    # a unit is recompiled when its own source or any header is newer than its object
+    headers = [d for d in DEPS if not d.endswith(".cu")]
+    def stale(u, o):
+        return force or not os.path.exists(o) or any(os.path.getmtime(o) < os.path.getmtime(d) for d in headers + [os.path.join(CSRC, u)])
+    cmds = [["nvcc", *COMMON, *flags, *extra, "-c", os.path.join(CSRC, u), "-o", o] for (u, flags), o in zip(UNITS, objs) if stale(u, o)]
+    with ThreadPoolExecutor(max(len(cmds), 1)) as ex:
         list(ex.map(lambda c: _run(c, verbose), cmds))
     _run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-o", OUT, *objs], verbose)
     return OUT

@@ -32,8 +32,8 @@ namespace {
 struct BlockCache {
     std::mutex mu;
     std::multimap<std::pair<int, size_t>, void *> free_blocks;
-    void *get(size_t bytes) {
-        int dev = 0; cudaGetDevice(&dev);
+    // dev: the device the block lives on (the caller's current device at allocation time; DevMem records it)
+    void *get(size_t bytes, int dev) {
         {
             std::lock_guard<std::mutex> lk(mu);
             auto it = free_blocks.find({dev, bytes});
@@ -47,25 +47,36 @@ struct BlockCache {
         }
         return p;
     }
-    void put(void *p, size_t bytes) {
-        int dev = 0; cudaGetDevice(&dev);
+    void put(void *p, size_t bytes, int dev) {
         std::lock_guard<std::mutex> lk(mu);
         free_blocks.insert({{dev, bytes}, p});
     }
     void trim() {
         std::lock_guard<std::mutex> lk(mu);
-        for (auto &kv : free_blocks) cudaFree(kv.second);
+        int cur = 0; cudaGetDevice(&cur);
+        for (auto &kv : free_blocks) { cudaSetDevice(kv.first.first); cudaFree(kv.second); }
+        cudaSetDevice(cur);
         free_blocks.clear();
     }
 };
 BlockCache g_blocks;
 
+// RAII over the current device: handles remember the device they were created on (spt_set_device supports several
+// devices per process) and every entry point that touches a handle's memory switches to it first.
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { if (dev >= 0 && cudaGetDevice(&prev) == cudaSuccess && prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 struct DevMem {
     std::vector<std::pair<void *, size_t>> ptrs;
+    int dev = -1;                // the device every block of this holder lives on (set by the first allocation)
     template <typename T> T *alloc(size_t n) {
         if (n == 0) n = 1;
         size_t bytes = (n * sizeof(T) + 255) & ~(size_t)255;
-        void *p = g_blocks.get(bytes);
+        if (dev < 0) { dev = 0; cudaGetDevice(&dev); }
+        void *p = g_blocks.get(bytes, dev);
         if (!p) return nullptr;
         ptrs.push_back({p, bytes});
         return (T *)p;
@@ -76,7 +87,7 @@ struct DevMem {
         return d;
     }
     // callers synchronise the device (or the stream that last touched the blocks) before releasing
-    void release() { for (auto &p : ptrs) g_blocks.put(p.first, p.second); ptrs.clear(); }
+    void release() { for (auto &p : ptrs) g_blocks.put(p.first, p.second, dev); ptrs.clear(); }
 };
 
 int num_sms() {
@@ -89,7 +100,12 @@ int num_sms() {
 
 #define SPT_MAX_LANES 4
 struct SptScene {
+    int device = 0;                  // the device the scene lives on: every entry point switches to it (DeviceGuard)
     DevMem mem;
+    DevMem trace_scratch;            // spt_trace_*_dev: split rays + counters, grown on demand, released with the scene
+    uint64_t trace_scratch_n = 0;
+    float4 *ts_ro = nullptr, *ts_rd = nullptr;
+    uint32_t *ts_cnt = nullptr, *ts_slot = nullptr;
     DevScene dev;
     std::vector<uint32_t> prim_id_host;
     uint32_t *prim_id_dev = nullptr;
@@ -137,14 +153,21 @@ struct SptScene {
     }
 };
 
+static void destroy_lanes(SptScene *s) {
+    for (int k = 0; k < SPT_MAX_LANES; ++k) {
+        if (s->lane[k].stream) { cudaStreamDestroy(s->lane[k].stream); s->lane[k].stream = nullptr; }
+        if (s->evjoin[k]) { cudaEventDestroy(s->evjoin[k]); s->evjoin[k] = nullptr; }
+    }
+}
 static bool make_lanes(SptScene *s) {
     for (int k = 0; k < SPT_MAX_LANES; ++k)
         if (cudaStreamCreateWithFlags(&s->lane[k].stream, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaEventCreateWithFlags(&s->evjoin[k], cudaEventDisableTiming) != cudaSuccess) return false;
+            cudaEventCreateWithFlags(&s->evjoin[k], cudaEventDisableTiming) != cudaSuccess) { destroy_lanes(s); return false; }
     return true;
 }
 
 struct SptFilm {
+    int device = 0;
     SptFilmDesc desc;
     float *pix = nullptr;           // [y][x][NB+1]
     bool owned = true;
@@ -181,7 +204,37 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
     if (d->nbands != NB) { g_err = "scene band count does not match the library's SPT_NBANDS"; return nullptr; }
     if (spt_device_count() <= 0) { g_err = "no CUDA device: this library has no CPU path"; return nullptr; }
     if (d->n_materials > 0xffffu || d->n_lights > 0xfffeu) { g_err = "more than 65535 materials or 65534 lights"; return nullptr; }
+    // indices the host and the kernels dereference: checked here once, so that a malformed table is an error, not a fault
+    {
+        auto bad = [&](const char *what) { g_err = std::string("scene tables: ") + what; return (SptScene *)nullptr; };
+        if (d->n_prims && (!d->prim_kind || !d->prim_flags || !d->prim_id || !d->prim_data || !d->prim_material || !d->prim_light || !d->prim_xform))
+            return bad("a per-slot array is NULL");
+        for (uint32_t p = 0; p < d->n_prims; ++p) {
+            if (d->prim_material[p] < 0 || (uint32_t)d->prim_material[p] >= d->n_materials) return bad("prim_material out of range");
+            if (d->prim_light[p] < -1 || d->prim_light[p] >= (int32_t)d->n_lights) return bad("prim_light out of range");
+            if (d->prim_kind[p] == SPT_PRIM_TRIANGLE) { if (d->prim_data[p] >= d->n_tris) return bad("prim_data: triangle number out of range"); }
+            else if (d->prim_kind[p] == SPT_PRIM_SPHERE || d->prim_kind[p] == SPT_PRIM_DISK) { if (d->prim_data[p] >= d->n_quadrics) return bad("prim_data: quadric row out of range"); }
+            else return bad("unknown primitive kind");
+            if (d->prim_xform[p] < 0 || (d->n_xforms && (uint32_t)d->prim_xform[p] >= d->n_xforms)) return bad("prim_xform out of range");
+        }
+        for (size_t k = 0; k < (size_t)d->n_tris * 3; ++k)
+            if (d->tri_vidx[k] < 0 || (uint32_t)d->tri_vidx[k] >= d->n_verts) return bad("tri_vidx out of range");
+        for (uint32_t q = 0; q < d->n_quadrics; ++q)
+            if (d->quadrics[q].xform < 0 || (uint32_t)d->quadrics[q].xform >= d->n_xforms) return bad("quadric xform out of range");
+        for (uint32_t li = 0; li < d->n_lights; ++li) {
+            const SptLight &l = d->lights[li];
+            if (l.type == SPT_LIGHT_AREA && (l.shape_first < 0 || l.shape_count < 0 || (uint64_t)l.shape_first + (uint64_t)l.shape_count > d->n_light_shapes))
+                return bad("light shape range out of bounds");
+            if (l.type == SPT_LIGHT_INFINITE && (l.xform < 0 || (uint32_t)l.xform >= d->n_xforms)) return bad("infinite light xform out of range");
+        }
+        for (uint32_t k = 0; k < d->n_light_shapes; ++k) {
+            const SptLightShape &ls = d->light_shapes[k];
+            if (ls.kind == SPT_PRIM_TRIANGLE ? (ls.data < 0 || (uint32_t)ls.data >= d->n_tris) : (ls.data < 0 || (uint32_t)ls.data >= d->n_quadrics))
+                return bad("light shape data out of range");
+        }
+    }
     SptScene *s = new SptScene();
+    cudaGetDevice(&s->device);
     if (const char *e = getenv("SPT_TRACE_VARIANT")) s->trace_variant = atoi(e);
     if (const char *e = getenv("SPT_FETCH_THRESHOLD")) s->fetch_threshold = (uint32_t)atoi(e);
     if (const char *e = getenv("SPT_LANES")) s->max_lanes = std::min(std::max(atoi(e), 1), SPT_MAX_LANES);
@@ -292,7 +345,7 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
                                                      pn_dev, tv_dev, sc_dev, status) : cudaErrorMemoryAllocation;
         scratch.release();
         if (e != cudaSuccess) { g_err = std::string("scene re-layout failed: ") + cudaGetErrorString(e); m.release(); delete s; return nullptr; }
-        if ((status[0] & 1u) && pairs_ok && !(status[0] & 2u)) { g_err = "malformed BVH: child index out of range"; m.release(); delete s; return nullptr; }
+        if (status[0] & 1u) { g_err = "malformed BVH: child index out of range"; m.release(); delete s; return nullptr; }     // whatever the variant
         if (status[0] & 2u) pairs_ok = false;
         if (pairs_ok) root_code = d->n_nodes ? status[1] : 0xffffffffu; else s->trace_variant = 0;
     }
@@ -370,6 +423,9 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
         !make_lanes(s) ||
         cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess) {
         g_err = std::string("scene upload failed: ") + cudaGetErrorString(cudaGetLastError());
+        destroy_lanes(s);
+        if (s->ev0) cudaEventDestroy(s->ev0);
+        if (s->ev1) cudaEventDestroy(s->ev1);
         m.release();
         delete s;
         return nullptr;
@@ -382,8 +438,10 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
 
 void spt_scene_destroy(SptScene *s) {
     if (!s) return;
+    DeviceGuard dg(s->device);
     cudaDeviceSynchronize();
     s->mem.release();
+    s->trace_scratch.release();
     s->counts_mem.release();
     for (auto &ln : s->lane) { ln.mem.release(); if (ln.stream) cudaStreamDestroy(ln.stream); }
     if (s->ev0) cudaEventDestroy(s->ev0);
@@ -395,6 +453,7 @@ void spt_scene_destroy(SptScene *s) {
 
 int spt_scene_enable_counters(SptScene *s, int on) {
     if (!s) return fail(SPT_ERR_ARG, "null scene");
+    DeviceGuard dg(s->device);
     s->counters_on = on != 0;
     s->dev.counters = on ? s->counters : nullptr;
     CU(cudaMemset(s->counters, 0, 32));
@@ -413,6 +472,7 @@ double spt_last_render_ms(SptScene *s) { return s ? s->stats.render_ms : 0.0; }
 
 int spt_get_stats(SptScene *s, SptStats *out) {
     if (!s || !out) return fail(SPT_ERR_ARG, "null argument");
+    DeviceGuard dg(s->device);
     if (s->counters_on) {
         unsigned long long c[4];
         CU(cudaMemcpy(c, s->counters, 32, cudaMemcpyDeviceToHost));
@@ -435,6 +495,7 @@ int spt_get_stats(SptScene *s, SptStats *out) {
 static int ensure_wave(SptScene *s, int n_lanes, uint32_t cap, int max_depth, size_t n_waves, uint32_t sub = 1) {
     cap = (cap + 31u) & ~31u;
     const size_t jcap = (size_t)cap * sub;
+    if (jcap > 0xffffffffull) return fail(SPT_ERR_ARG, "wave too large: paths x jobs per path exceeds 2^32 (lower wave_pixels)");
     size_t need_counts = n_waves * (size_t)(max_depth + 2) * SPT_ROW;
     for (int li = 0; li < n_lanes; ++li) {
         SptScene::Lane &ln = s->lane[li];
@@ -602,6 +663,7 @@ static int trace_host(SptScene *s, bool any, const float *rays, uint64_t n, uint
     if (!s || !rays) return fail(SPT_ERR_ARG, "null argument");
     if (n == 0) return SPT_OK;
     if (n > 0x7fffffffull) return fail(SPT_ERR_ARG, "too many rays for one call");
+    DeviceGuard dg(s->device);
     DevMem m;
     float *dr = m.upload(rays, n * 8);
     float4 *ro = m.alloc<float4>(n), *rd = m.alloc<float4>(n);
@@ -612,7 +674,6 @@ static int trace_host(SptScene *s, bool any, const float *rays, uint64_t n, uint
     uint32_t n32 = (uint32_t)n;
     uint32_t cw[2] = { n32, 0 };
     cudaMemcpyAsync(cnt, cw, 8, cudaMemcpyHostToDevice, s->stream);
-    unsigned g = (unsigned)std::min<uint64_t>((n + 255) / 256, 65535);
     spt_launch_split_rays(s->stream, dr, n32, ro, rd);
     int rc = trace_dev(s, any, ro, rd, n, slot, t, cnt);
     if (rc == SPT_OK) {
@@ -645,12 +706,15 @@ static int trace_resident(SptScene *s, bool any, const float *rays_dev, uint64_t
                           uint8_t *hit_dev) {
     if (!s || !rays_dev) return fail(SPT_ERR_ARG, "null argument");
     if (n == 0) return SPT_OK;
-    // scratch (split rays + count) is cached in the wave allocator's lifetime
-    static thread_local DevMem scratch;
-    static thread_local uint64_t scratch_n = 0;
-    static thread_local float4 *ro = nullptr, *rd = nullptr;
-    static thread_local uint32_t *cnt = nullptr, *slot_tmp = nullptr;
+    if (n > 0x7fffffffull) return fail(SPT_ERR_ARG, "too many rays for one call");
+    DeviceGuard dg(s->device);
+    // scratch (split rays + count) belongs to the scene: same device, released by spt_scene_destroy
+    DevMem &scratch = s->trace_scratch;
+    uint64_t &scratch_n = s->trace_scratch_n;
+    float4 *&ro = s->ts_ro, *&rd = s->ts_rd;
+    uint32_t *&cnt = s->ts_cnt, *&slot_tmp = s->ts_slot;
     if (scratch_n < n) {
+        cudaStreamSynchronize(s->stream);
         scratch.release();
         ro = scratch.alloc<float4>(n); rd = scratch.alloc<float4>(n); cnt = scratch.alloc<uint32_t>(2);
         slot_tmp = scratch.alloc<uint32_t>(n);
@@ -658,10 +722,9 @@ static int trace_resident(SptScene *s, bool any, const float *rays_dev, uint64_t
         scratch_n = n;
     }
     uint32_t n32 = (uint32_t)n;
-    static thread_local uint32_t cw[2];
-    cw[0] = n32; cw[1] = 0;
-    cudaMemcpyAsync(cnt, cw, 8, cudaMemcpyHostToDevice, s->stream);
-    unsigned g = (unsigned)std::min<uint64_t>((n + 255) / 256, 65535);
+    uint32_t cw[2] = { n32, 0 };
+    CU(cudaMemcpyAsync(cnt, cw, 8, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaStreamSynchronize(s->stream));        // cw is on this frame's stack
     spt_launch_split_rays(s->stream, rays_dev, n32, ro, rd);
     uint32_t *slot = any ? slot_tmp : (slot_dev ? slot_dev : slot_tmp);
     int rc = trace_dev(s, any, ro, rd, n, slot, t_dev, cnt);
@@ -691,6 +754,7 @@ int spt_shade_samples(SptScene *s, const SptCameraDesc *cam, int32_t integrator,
     const int stride = direct ? 7 + 6 * s->direct_slots : (directOne ? 14 : 37);
     if (direct || directOne) max_depth = 0;     // strategy "one" is the path integrator's first vertex: emitted light + UniformSampleOneLight
     if (n * (uint64_t)sub > (1u << 26)) return fail(SPT_ERR_ARG, "too many samples for one call");
+    DeviceGuard dg(s->device);
     int rc = ensure_wave(s, 1, (uint32_t)n, max_depth, 1, (uint32_t)sub);
     if (rc != SPT_OK) return rc;
     DevMem m;
@@ -728,13 +792,15 @@ static SptFilm *film_new(const SptFilmDesc *d, float *ext) {
     if (d->x_pixel_count <= 0 || d->y_pixel_count <= 0) { g_err = "empty film"; return nullptr; }
     if (spt_device_count() <= 0) { g_err = "no CUDA device: this library has no CPU path"; return nullptr; }
     SptFilm *f = new SptFilm();
+    cudaGetDevice(&f->device);
     f->desc = *d;
     f->owned = ext == nullptr;
     f->pix = ext;
     size_t bytes = f->npix() * (NB + 1) * sizeof(float);
     if (!ext) {
         f->pix = f->mem.alloc<float>(bytes / sizeof(float));
-        if (!f->pix || cudaMemset(f->pix, 0, bytes) != cudaSuccess) {
+        // the lanes are non-blocking streams: the zeroing must have FINISHED before a render may add to the film
+        if (!f->pix || cudaMemset(f->pix, 0, bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
             g_err = std::string("film allocation failed: ") + cudaGetErrorString(cudaGetLastError());
             f->mem.release(); delete f; return nullptr;
         }
@@ -753,19 +819,25 @@ SptFilm *spt_film_create_external(const SptFilmDesc *d, float *pixels_dev) {
 }
 void spt_film_destroy(SptFilm *f) {
     if (!f) return;
+    DeviceGuard dg(f->device);
     cudaDeviceSynchronize();
     f->mem.release();
     delete f;
 }
 int spt_film_clear(SptFilm *f) {
     if (!f) return fail(SPT_ERR_ARG, "null film");
+    DeviceGuard dg(f->device);
+    // ordered against every stream of the device on both sides (the render lanes do not synchronise with the legacy stream)
+    CU(cudaDeviceSynchronize());
     CU(cudaMemset(f->pix, 0, f->npix() * (NB + 1) * sizeof(float)));
+    CU(cudaDeviceSynchronize());
     return SPT_OK;
 }
 float *spt_film_device_ptr(SptFilm *f) { return f ? f->pix : nullptr; }
 
 int spt_film_download(SptFilm *f, float *c, float *weight) {
     if (!f) return fail(SPT_ERR_ARG, "null film");
+    DeviceGuard dg(f->device);
     size_t np = f->npix();
     if (!f->split) f->split = f->mem.alloc<float>(np * (NB + 1));
     if (!f->split) return fail(SPT_ERR_CUDA, "out of device memory for the film staging buffer");
@@ -810,12 +882,13 @@ int spt_film_write_dat(SptFilm *f, const char *path) {
 int spt_film_add_samples(SptFilm *f, const SptSpectralTables *tables, const float *image_xy, const float *L, uint64_t n) {
     if (!f || !tables || !image_xy || !L) return fail(SPT_ERR_ARG, "null argument");
     if (n == 0) return SPT_OK;
+    if (n > 0x7fffffffull) return fail(SPT_ERR_ARG, "too many samples for one call");
+    DeviceGuard dg(f->device);
     DevMem m;
     SptSpectralTables *dt = m.upload(tables, 1);
     float2 *dxy = (float2 *)m.upload(image_xy, n * 2);
     float *dl = m.upload(L, n * NB), *soa = m.alloc<float>(((n + 31) / 32 * 32) * NB);
     if (!dt || !dxy || !dl || !soa) { m.release(); return fail(SPT_ERR_CUDA, "device allocation failed"); }
-    unsigned g = (unsigned)std::min<uint64_t>((n * NB + 255) / 256, 65535);
     spt_launch_scatter_L(0, dl, (uint32_t)n, (uint32_t)n, soa);
     FilmView fv; fv.d = f->desc; fv.pix = f->pix; fv.table = f->table;
     unsigned gw = (unsigned)std::min<uint64_t>((n * 32 + 255) / 256, (uint64_t)num_sms() * 16);
@@ -829,6 +902,8 @@ int spt_film_add_samples(SptFilm *f, const SptSpectralTables *tables, const floa
 // ---- the whole job -------------------------------------------------------------------------------
 int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRenderParams *rp) {
     if (!s || !cam || !film || !rp) return fail(SPT_ERR_ARG, "null argument");
+    if (film->device != s->device) return fail(SPT_ERR_ARG, "scene and film live on different devices");
+    DeviceGuard dg(s->device);
     if (rp->spp <= 0 || (rp->spp & (rp->spp - 1))) return fail(SPT_ERR_ARG, "spp must be a power of two (LDSampler rounds up)");
     if (rp->max_depth < 0 || rp->max_depth > 64) return fail(SPT_ERR_ARG, "max_depth out of range");
     int nranks = rp->tile_nranks > 0 ? rp->tile_nranks : 1;
@@ -854,7 +929,7 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
     }
     if (cfg.x1 <= cfg.x0 || cfg.y1 <= cfg.y0) return fail(SPT_ERR_ARG, "empty sample extent");
     cfg.tile = rp->tile_size > 0 ? rp->tile_size : 32;
-    if (cfg.tile & (cfg.tile - 1)) return fail(SPT_ERR_ARG, "tile_size must be a power of two");
+    if ((cfg.tile & (cfg.tile - 1)) || cfg.tile > 4096) return fail(SPT_ERR_ARG, "tile_size must be a power of two, at most 4096");
     for (cfg.tile_shift = 0; (1 << cfg.tile_shift) < cfg.tile; ++cfg.tile_shift) {}
     cfg.tilesX = (cfg.x1 - cfg.x0 + cfg.tile - 1) / cfg.tile;
     cfg.tilesY = (cfg.y1 - cfg.y0 + cfg.tile - 1) / cfg.tile;
@@ -863,6 +938,11 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
     uint64_t ntiles = (uint64_t)cfg.tilesX * cfg.tilesY;
     uint64_t local_tiles = ntiles > (uint64_t)cfg.rank ? (ntiles - cfg.rank + nranks - 1) / nranks : 0;
     uint64_t local_pixels = local_tiles * (uint64_t)cfg.tile * cfg.tile;
+    if (local_pixels == 0) {            // a rank that owns no tile (more ranks than tiles): nothing to render
+        reset_class_stats(s);
+        s->stats.render_ms = 0.; s->stats.lanes_used = 0;
+        return SPT_OK;
+    }
     // Waves: by default the rank's pixels are cut into a multiple of max_lanes waves, each at most
     // 2^25 / max_lanes paths (17 GB of state over all lanes), dealt to the lanes in turn; small jobs
     // (< 2^19 paths per wave) use fewer lanes, down to one wave on one lane.
@@ -881,11 +961,22 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
         nw = (nw + want_lanes - 1) / want_lanes * want_lanes;
         wave_pixels = (local_pixels + nw - 1) / nw;
     }
-    wave_pixels = std::min<uint64_t>(wave_pixels, std::max<uint64_t>(local_pixels, 1));
+    wave_pixels = std::max<uint64_t>(1, std::min<uint64_t>(wave_pixels, local_pixels));
     if (wave_pixels * slots_pp > (1ull << 27)) wave_pixels = std::max<uint64_t>(1, (1ull << 27) / slots_pp);
-    size_t n_waves = (size_t)((local_pixels + wave_pixels - 1) / wave_pixels);
-    const int n_lanes = (int)std::min<size_t>((size_t)s->max_lanes, std::max<size_t>(n_waves, 1));
-    int rc = ensure_wave(s, n_lanes, (uint32_t)(wave_pixels * slots_pp), depth, std::max<size_t>(n_waves, 1), (uint32_t)sub);
+    if (wave_pixels * slots_pp * (uint64_t)sub > 0xffffffffull) wave_pixels = std::max<uint64_t>(1, 0xffffffffull / (slots_pp * (uint64_t)sub));
+    size_t n_waves;
+    int n_lanes, rc;
+    for (;;) {
+        n_waves = (size_t)((local_pixels + wave_pixels - 1) / wave_pixels);
+        n_lanes = (int)std::min<size_t>((size_t)s->max_lanes, std::max<size_t>(n_waves, 1));
+        rc = ensure_wave(s, n_lanes, (uint32_t)(wave_pixels * slots_pp), depth, std::max<size_t>(n_waves, 1), (uint32_t)sub);
+        // a part with less free memory than the default sizing assumes: smaller waves instead of an error
+        if (rc != SPT_ERR_CUDA || wave_pixels * slots_pp <= (1u << 16)) break;
+        cudaDeviceSynchronize();
+        for (auto &ln : s->lane) { ln.mem.release(); ln.wb.cap = 0; ln.wb.jcap = 0; }
+        g_blocks.trim();
+        wave_pixels = (wave_pixels + 1) / 2;
+    }
     if (rc != SPT_OK) return rc;
     size_t per_wave = (size_t)(depth + 2) * SPT_ROW;
     cudaStream_t st = s->stream;

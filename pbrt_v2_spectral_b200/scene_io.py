@@ -15,6 +15,9 @@ def load_container(path):
     """name -> numpy array, for a file written by SptContainerWriter."""
     with open(path, "rb") as f:
         buf = f.read()
+    if path.endswith(".xz"):
+        import lzma
+        buf = lzma.decompress(buf)
     if buf[:8] != b"SPTSCN01":
         raise ValueError("%s: not an SPTSCN01 container" % path)
     (count,) = struct.unpack_from("<I", buf, 8)

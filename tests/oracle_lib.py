@@ -131,10 +131,29 @@ def golden_cases(big=True):
              for n in ("tiny", "tiny_tex", "tiny_direct") if os.path.exists(os.path.join(GOLDEN_SMALL, n + ".golden"))]
     if big and os.path.isdir(GOLDEN_BIG):
         for f in sorted(os.listdir(GOLDEN_BIG)):
-            if f.endswith(".golden"):
+            if f.endswith(".golden") and not f.endswith("_rays.golden"):
                 name = f[:-7]
                 cases.append((name, os.path.join(GOLDEN_BIG, name + ".spt"), os.path.join(GOLDEN_BIG, f)))
     return cases
+
+
+def ray_cases(big=True):
+    """[(name, scene path, golden path)] of the compact first-hit sets ({image_xy, prim_id, t_hit}, oracle_dump's
+    SPT_DUMP_COMPACT): the committed mid-size ones (65 536 camera rays of BASELINE configs 1 and 2 at full resolution, xz
+    containers) and, where oracle/_ref/golden is present, the 1 048 576-ray ones."""
+    cases = [(n, os.path.join(GOLDEN_SMALL, n + ".spt.xz"), os.path.join(GOLDEN_SMALL, n + ".golden.xz"))
+             for n in ("killeroo_rays_mid", "bunny_rays_mid") if os.path.exists(os.path.join(GOLDEN_SMALL, n + ".golden.xz"))]
+    if big:
+        cases += [(n, os.path.join(GOLDEN_BIG, n + ".spt"), os.path.join(GOLDEN_BIG, n + ".golden"))
+                  for n in ("killeroo_rays", "bunny_rays") if os.path.exists(os.path.join(GOLDEN_BIG, n + ".golden"))]
+    return cases
+
+
+def compact_samples(g):
+    """n x 5 camera sample floats of a compact set: {imageX, imageY, 0, 0, 0} (pinhole camera, static scene)."""
+    s = np.zeros((len(g["image_xy"]), 5), np.float32)
+    s[:, :2] = g["image_xy"]
+    return s
 
 
 def load_case(scene_path, golden_path):

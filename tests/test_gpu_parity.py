@@ -38,6 +38,29 @@ def test_first_hit_ids_bit_exact_t_1e5(case):
     assert np.array_equal(t.view(np.uint32), g["t_hit"].view(np.uint32))
 
 
+RAY_CASES = O.ray_cases()
+
+
+@pytest.mark.parametrize("rcase", RAY_CASES, ids=[c[0] for c in RAY_CASES])
+def test_first_hits_at_baseline_resolution(rcase):
+    """north_star / SURVEY 8(d): camera-ray first hits of BASELINE configs 1 (killeroo, 700x700) and 2 (bunny, 640x480) at
+    full resolution - 1 048 576 rays each (65 536 in the committed sets) dumped by the reference's own camera and
+    BVHAccel::Intersect (src/accelerators/bvh.cpp:380-432): ids and t bit for bit through the C ABI."""
+    name, sp, gp = rcase
+    lowered, g = O.load_case(sp, gp)
+    assert lowered.camera.lens_radius == 0.0
+    scene = capi.Scene(lowered)
+    rays = capi.camera_rays(lowered.camera, O.compact_samples(g))
+    slot, pid, t = scene.trace_closest(rays)
+    scene.close()
+    assert len(pid) >= (1 << 20 if not name.endswith("_mid") else 1 << 16)
+    assert np.array_equal(pid, g["prim_id"]), "%d of %d ids differ" % ((pid != g["prim_id"]).sum(), len(pid))
+    hit = pid != 0
+    rel = np.abs(t[hit] - g["t_hit"][hit]) / g["t_hit"][hit]
+    assert rel.max() <= 1e-5
+    assert np.array_equal(t.view(np.uint32), g["t_hit"].view(np.uint32))
+
+
 def test_secondary_rays(case):
     _, _, scene, g = case
     m = g["prim_id"] != 0

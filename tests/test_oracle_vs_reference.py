@@ -52,3 +52,21 @@ def test_path_radiance(case):
     # same libm, same fp32 operation order as the reference build: bit-exact radiance
     assert np.array_equal(L.view(np.uint32), ref.view(np.uint32)), "%s: %d of %d samples differ" % (
         name, (L != ref).any(axis=1).sum(), len(L))
+
+
+RAY_CASES = O.ray_cases()
+
+
+@pytest.mark.parametrize("rcase", RAY_CASES, ids=[c[0] for c in RAY_CASES])
+def test_first_hits_at_baseline_resolution(rcase):
+    """BASELINE configs 1 (700x700) and 2 (640x480) at full resolution: the reference's own first hits of 65 536 (committed)
+    and 1 048 576 camera rays - ids and distances bit for bit."""
+    name, sp, gp = rcase
+    scene, g = O.load_case(sp, gp)
+    assert scene.camera.lens_radius == 0.0
+    rays = O.camera_rays(scene, O.compact_samples(g))
+    slot, pid, t = O.trace_closest(scene, rays)
+    assert len(pid) >= (1 << 20 if not name.endswith("_mid") else 1 << 16)
+    assert np.array_equal(pid, g["prim_id"])
+    assert np.array_equal(t.view(np.uint32), g["t_hit"].view(np.uint32))
+    assert (pid != 0).mean() > 0.2          # not a set of misses
