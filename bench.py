@@ -33,7 +33,9 @@ WORKLOAD_DESC = "scenes/killeroo-simple.pbrt, path integrator maxdepth 5, Sample
 SCENE_SPT = os.path.join(ROOT, "assets", "_lowered", WORKLOAD + ".spt")
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "bin", "pbrt")
 REF_SCENES = os.path.join(ROOT, "oracle", "_ref", "scenes")
-CPU_SAMPLE_SPP = 16          # bounded sample of the workload for the CPU arm: same frame, 16 of the 64 spp
+CPU_SAMPLE_SPP = 16          # bounded sample of the workload for the in-line cpu_baseline leg: same frame, 16 of the 64 spp
+REF_ARM_SPP = int(os.environ.get("SPT_REF_ARM_SPP", "64"))     # (the CPU test of this arm's output format lowers it)
+# --impl reference renders the whole configuration (64 spp): ~9 s per step on 16 cores
 # workloads that have a scene file the reference binary can run for the CPU leg: (xres, yres, spp, bounded-sample spp)
 CPU_WORKLOADS = {"killeroo_path": (700, 700, 64, CPU_SAMPLE_SPP), "killeroo_direct": (700, 700, 64, CPU_SAMPLE_SPP),
                  "bunny_shipped": (640, 480, 256, 8), "metal_path": (400, 400, 512, 16), "ssenv_path": (1920, 1080, 1024, 8)}
@@ -128,13 +130,13 @@ def run_reference_arm(args):
     setup = min(reference_run(reference_scene(1, 8), ncores) for _ in range(2))
     times = []
     for i in range(args.warmup + args.steps):
-        t = reference_run(reference_scene(CPU_SAMPLE_SPP), ncores)
+        t = reference_run(reference_scene(REF_ARM_SPP), ncores)
         if i >= args.warmup:
             times.append(max(t - setup, 1e-6))
-    n_samples = 701 * 701 * CPU_SAMPLE_SPP
+    n_samples = 701 * 701 * REF_ARM_SPP
     ms = 1e3 * sum(times) / len(times)
     value = n_samples / (ms / 1e3) / 1e6
-    sample = "same frame (700x700, sample extent 701x701) at %d of the 64 spp per step; parse+BVH build (%.2fs, 8x8 1spp run) subtracted" % (CPU_SAMPLE_SPP, setup)
+    sample = "the whole configuration per step: 700x700 (sample extent 701x701) at all %d spp; parse+BVH build (%.2fs, 8x8 1spp run) subtracted" % (REF_ARM_SPP, setup)
     print_json({
         "impl": "reference", "metric": "Msamples/sec (32-band spectral path trace)", "value": value, "unit": "Msamples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -221,37 +223,61 @@ def main():
     n_samples_total = (rp.x_end - rp.x_start) * (rp.y_end - rp.y_start) * rp.spp
 
     scene = capi.Scene(lowered)
-    film_t = torch.zeros((fd.y_pixel_count, fd.x_pixel_count, D.NBANDS + 1), dtype=torch.float32, device=dev)
-    film = capi.Film(fd, film_t.data_ptr())
-
-    # N > 1: the one exchange of the job - every rank's possibly non-zero film pixels (its tiles grown by the filter's reach)
-    # gathered onto rank 0 over NVLink (NCCL) and added there; same sum as a full-film reduction, 1/N of the bytes
-    exchange = multi.FilmExchange(fd, rp, world, dev)
+    # N = 1: the film is the library's. N > 1: ONE film per frame buffer lives on rank 0 (spt_film_create there, exported with
+    # spt_film_ipc_export); the other ranks open it (spt_film_open_ipc) and their film kernel adds their tile sets' samples
+    # straight into it over NVLink - the "gather" is fused into K7, what is left of it is a barrier at the end of the frame.
+    n_buf = 2 if world > 1 else 1
+    if world == 1:
+        films = [capi.Film(fd)]
+    else:
+        handles = [None] * n_buf
+        if rank == 0:
+            films = [capi.Film(fd) for _ in range(n_buf)]
+            handles = [f.ipc_export() for f in films]
+        dist.broadcast_object_list(handles, src=0)
+        if rank != 0:
+            films = [capi.Film(fd, ipc_handle=h) for h in handles]
+    film = films[0]
+    sync_t = torch.zeros(1, device=dev)
 
     def barrier():
         torch.cuda.synchronize()
         if dist is not None:
-            dist.barrier()
+            dist.all_reduce(sync_t)
         torch.cuda.synchronize()
+
+    def frame(k, params=None):
+        """One whole frame of the job on N GPUs: every rank renders its tile set into film buffer k % n_buf (rank 0's memory),
+        the end-of-frame barrier makes the film complete, and rank 0 clears it for the frame after next."""
+        f = films[k % n_buf]
+        scene.render(f, params if params is not None else rp)        # blocks until this rank's streams have drained
+        if dist is not None:
+            dist.all_reduce(sync_t)
+            torch.cuda.current_stream().synchronize()
+        return f
 
     # ---- untimed counted pass: BVH nodes visited / primitives tested per ray class (roofline's algorithmic bytes)
     scene.enable_counters(True)
     scene.render(film, rp)
     cst = scene.stats()
     scene.enable_counters(False)
-    rays_path = max(cst["class_rays"][D.K_TRACE_PATH], 1)
-    rays_mis = cst["class_rays"][D.K_TRACE_MIS]
-    rays_sh = max(cst["class_rays"][D.K_TRACE_SHADOW], 1)
-    nodes_per_closest = cst["node_visits_closest"] / max(rays_path + rays_mis, 1)
-    prims_per_closest = cst["prim_tests_closest"] / max(rays_path + rays_mis, 1)
-    nodes_per_any = cst["node_visits_any"] / rays_sh
-    prims_per_any = cst["prim_tests_any"] / rays_sh
+    # the kernel counts per ray CLASS (closest-hit / any-hit query), whatever queue the ray came from
+    n_closest, n_any = max(cst["closest_rays"], 1), max(cst["any_rays"], 1)
+    nodes_per_closest = cst["node_visits_closest"] / n_closest
+    prims_per_closest = cst["prim_tests_closest"] / n_closest
+    nodes_per_any = cst["node_visits_any"] / n_any
+    prims_per_any = cst["prim_tests_any"] / n_any
+    # MIS rays traced as closest-hit queries (the others - towards an infinite light - are any-hit queries)
+    mis_closest_frac = (cst["closest_rays"] - cst["class_rays"][D.K_TRACE_PATH]) / max(cst["class_rays"][D.K_TRACE_MIS], 1)
 
     # ---- warm-up, then the timed steps
-    for _ in range(max(args.warmup, 3)):
-        film_t.zero_()
-        scene.render(film, rp)
-        exchange.run(film_t, rank)
+    if rank == 0:
+        film.clear()
+    barrier()
+    for k in range(max(args.warmup, 3)):
+        f = frame(k)
+        if rank == 0:
+            f.clear()
     barrier()
     launches0 = scene.stats()["kernel_launches"]
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -261,79 +287,16 @@ def main():
     e1 = torch.cuda.Event(enable_timing=True)
     render_ms = 0.0
     lanes_used = 1
-    # N > 1: two film buffers, so that the exchange of frame k (torch's stream: gather over NCCL + adds on rank 0) runs while
-    # frame k+1 renders (the library's streams). The next film is zeroed on torch's stream BEHIND the previous use of that
-    # buffer (the exchange of frame k-1) and the host waits for that one event only before it renders into it.
-    # A worker thread owns the exchange (its own CUDA stream): the host-side enqueueing of the gather and adds costs ~0.2 ms
-    # per frame, which would otherwise sit between two renders; spt_render releases the GIL while it blocks.
-    films_t = [film_t, torch.zeros_like(film_t)] if world > 1 else [film_t]
-    films = [film] + ([capi.Film(fd, films_t[1].data_ptr())] if world > 1 else [])
-    worker = None
-    if world > 1:
-        import queue
-
-        class ExchangeWorker(threading.Thread):
-            def __init__(self):
-                super().__init__(daemon=True)
-                self.q = queue.Queue()
-                self.ready = [threading.Event(), threading.Event()]     # buffer b may be rendered into (its zeroing is enqueued)
-                self.zeroed = [None, None]                               # CUDA event behind that zeroing
-                self.stream = torch.cuda.Stream(dev)
-                self.error = None
-                for e in self.ready:
-                    e.set()
-
-            def run(self):
-                try:
-                    torch.cuda.set_device(dev)
-                    with torch.cuda.stream(self.stream):
-                        while True:
-                            k = self.q.get()
-                            if k is None:
-                                return
-                            b = k % 2
-                            exchange.run(films_t[b], rank)       # the ranks' film pixels gathered onto rank 0 over NVLink (NCCL) and added there
-                            films_t[b].zero_()                   # for frame k + 2
-                            ev = torch.cuda.Event()
-                            ev.record(self.stream)
-                            self.zeroed[b] = ev
-                            self.ready[b].set()
-                except Exception as exc:                         # surfaced by the main thread
-                    self.error = exc
-                    for e in self.ready:
-                        e.set()
-
-        worker = ExchangeWorker()
-        films_t[0].zero_(); films_t[1].zero_()
     barrier()
-    if worker:
-        worker.start()
     e0.record()
     for k in range(args.steps):
-        b = k % len(films)
-        if worker:
-            worker.ready[b].wait(); worker.ready[b].clear()
-            if worker.error:
-                raise worker.error
-            if worker.zeroed[b] is not None:
-                worker.zeroed[b].synchronize()
-        else:
-            films_t[0].zero_()
-        scene.render(films[b], rp)                   # blocks until the library's streams have drained
-        if worker:
-            worker.q.put(k)
+        f = frame(k)
         render_ms += scene.render_ms()
-    if worker:
-        worker.q.put(None)
-        worker.join()
-        if worker.error:
-            raise worker.error
-        torch.cuda.current_stream().wait_stream(worker.stream)
+        if rank == 0:
+            f.clear()                                    # N > 1: frame k + 1 goes to the other buffer; k + 2 starts behind the next barrier
     e1.record()
     barrier()
     lanes_used = scene.stats()["lanes_used"]
-    for f in films[1:]:
-        f.close()
     if sampler:
         sampler.stop_flag = True
         sampler.join()
@@ -351,7 +314,6 @@ def main():
     scene.set_lanes(1)
     scene.render(film, rp)
     for _ in range(prof_steps):
-        film_t.zero_()
         scene.render(film, rp)
         st = scene.stats()
         serial_ms += st["render_ms"]
@@ -360,9 +322,32 @@ def main():
         for k in range(D.K_CLASSES):
             class_ms[k] += st["class_ms"][k]; class_launches[k] += st["class_launches"][k]; class_rays[k] += st["class_rays"][k]
     scene.set_lanes(int(os.environ.get("SPT_LANES", "4")))
-    film_t.zero_()
-    scene.render(film, rp)
-    exchange.run(film_t, rank)
+    barrier()
+    # ---- the complete film of one more frame (N > 1: assembled on rank 0 over NVLink), and for N > 1 its check against a
+    # one-GPU render of the same seed on rank 0
+    if rank == 0:
+        film.clear()
+    barrier()
+    frame(0)
+    barrier()
+    image_sum = 0.0
+    film_check = None
+    if rank == 0:
+        c_all, w_all = film.download()
+        image_sum = float(c_all.sum(dtype=np.float64))
+        if world > 1:
+            rp1 = multi.rank_params(rp, 0, 1)
+            f1 = capi.Film(fd)
+            scene.render(f1, rp1)
+            c_one, w_one = f1.download()
+            f1.close()
+            scale = np.maximum(np.abs(c_one).max(axis=2, keepdims=True), 1e-20)
+            rel = float((np.abs(c_all - c_one) / scale).max())
+            film_check = {"max_rel_err_vs_1gpu_render": rel, "weights_equal": bool(np.array_equal(w_all, w_one)), "tolerance": 1e-5,
+                          "ok": bool(rel <= 1e-5 and np.array_equal(w_all, w_one))}
+            if not film_check["ok"]:
+                raise SystemExit("N-GPU film differs from the 1-GPU render of the same seed: %r" % film_check)
+        c_all = w_all = None
     barrier()
     step_ms = e0.elapsed_time(e1) / args.steps
     sys.stderr.write("[rank %d] render %.3f ms/step (library events), step incl. film zero + reduce %.3f ms, serialized kernels %.3f ms\n" % (rank, render_ms / args.steps, step_ms, serial_ms / prof_steps))
@@ -378,7 +363,6 @@ def main():
     # N=1: the job is spt_render itself (library events); N>1: render + NCCL reduce (max over ranks)
     ms_per_step = render_only_ms if world == 1 else step_ms
     value = n_samples_total / (ms_per_step / 1e3) / 1e6
-    image_sum = float(film_t[..., :D.NBANDS].sum()) if rank == 0 else 0.0
 
     # ---- e2e through the C ABI with host buffers (rank-local: each rank uploads, renders its tiles, downloads)
     scene_bytes = int(sum(v.nbytes for k, v in lowered.a.items() if k not in ("camera", "film", "params", "film_filename")))
@@ -391,12 +375,23 @@ def main():
     for i in range(1 + args.steps):
         barrier()
         t0 = time.perf_counter()
-        sc2 = capi.Scene(lowered)                    # H2D: every scene table from host memory
-        f2 = capi.Film(fd)
+        sc2 = capi.Scene(lowered)                    # H2D: every scene table from host memory (every rank)
+        if world == 1:
+            f2 = capi.Film(fd)
+        else:
+            f2 = films[0]                            # the shared film on rank 0 (cleared below, inside the timed region)
+            if rank == 0:
+                f2.clear()
+            dist.all_reduce(sync_t); torch.cuda.current_stream().synchronize()
         sc2.render(f2, rp)
-        f2.download((c_host, w_host))                # D2H: the film
+        if world > 1:
+            dist.all_reduce(sync_t); torch.cuda.current_stream().synchronize()      # end of frame: the film is complete on rank 0
+        if rank == 0:
+            f2.download((c_host, w_host))            # D2H: the COMPLETE film
         t1 = time.perf_counter()
-        f2.close(); sc2.close()
+        if world == 1:
+            f2.close()
+        sc2.close()
         if i > 0:
             e2e_times.append(t1 - t0)
     e2e_s = sum(e2e_times) / len(e2e_times)
@@ -410,9 +405,14 @@ def main():
     e2e_value = n_samples_total / e2e_s / 1e6
 
     if rank != 0:
+        barrier()
+        for f in films:
+            f.close()
+        scene.close()
         if dist is not None:
             dist.destroy_process_group()
         return
+    barrier()
 
     # ---- rooflines (algorithmic bytes per unit: SURVEY.md 8d for rays, DESIGN.md 3 for the other kernels)
     peak, peak_src = read_peaks()
@@ -426,24 +426,30 @@ def main():
     closest_bytes = 32.0 * nodes_per_closest + 48.0 * prims_per_closest + 40.0
     any_bytes = 32.0 * nodes_per_any + 48.0 * prims_per_any + 40.0
     v_all, v_first = class_rays[D.K_ACCUMULATE], first_vertices
-    unit_bytes = {                                   # class -> (unit, algorithmic bytes moved by the class over the timed steps)
-        D.K_GEN: ("camera sample", 44.0 * class_rays[D.K_GEN]),
-        D.K_TRACE_PATH: ("ray", closest_bytes * class_rays[D.K_TRACE_PATH]),
-        D.K_TRACE_MIS: ("ray", closest_bytes * class_rays[D.K_TRACE_MIS]),
-        D.K_TRACE_SHADOW: ("ray", any_bytes * class_rays[D.K_TRACE_SHADOW]),
-        D.K_SHADE: ("path vertex", 250.0 * class_rays[D.K_SHADE]),
-        D.K_ACCUMULATE: ("path vertex", 380.0 * v_first + 636.0 * max(v_all - v_first, 0)),
-        D.K_FILM: ("camera sample", 136.0 * class_rays[D.K_FILM] + 132.0 * class_rays[D.K_FILM] / max(rp.spp, 1)),
+    v_adv = class_rays[D.K_ADVANCE]
+    rays_mis_closest_steps = mis_closest_frac * class_rays[D.K_TRACE_MIS]
+    rays_closest = class_rays[D.K_TRACE_PATH] + rays_mis_closest_steps
+    rays_any = class_rays[D.K_TRACE_SHADOW] + (class_rays[D.K_TRACE_MIS] - rays_mis_closest_steps)
+    unit_bytes = {                                   # class -> (unit, algorithmic bytes moved by the class over the profiled steps, units)
+        D.K_GEN: ("camera sample", 44.0 * class_rays[D.K_GEN], class_rays[D.K_GEN]),
+        # ONE traversal launch per bounce: its path rays + the previous bounce's shadow / MIS rays
+        D.K_TRACE_PATH: ("ray", closest_bytes * rays_closest + any_bytes * rays_any, rays_closest + rays_any),
+        D.K_SHADE: ("path vertex", 250.0 * class_rays[D.K_SHADE], class_rays[D.K_SHADE]),
+        # k_addlight: records 48 + verdicts 8 + (T 128 + L 256 | first vertex: L 128 written)
+        D.K_ACCUMULATE: ("path vertex", (56.0 + 128.0) * v_first + (56.0 + 384.0) * max(v_all - v_first, 0), v_all),
+        # k_advance: records 32 + g0/g3 32 + next ray 32 + queue 8 + (T 256 | first vertex: T 128 written)
+        D.K_ADVANCE: ("path vertex", 104.0 * v_adv + 128.0 * min(v_first, v_adv) + 256.0 * max(v_adv - v_first, 0), v_adv),
+        D.K_FILM: ("camera sample", 136.0 * class_rays[D.K_FILM] + 132.0 * class_rays[D.K_FILM] / max(rp.spp, 1), class_rays[D.K_FILM]),
     }
     total_class = sum(class_ms)
     def roof(k):
         ms = class_ms[k]
-        unit, nbytes = unit_bytes[k]
+        unit, nbytes, units = unit_bytes[k]
         ach = nbytes / (ms / 1e3) / 1e9 if ms > 0 else 0.0
         return {"bound": "hbm", "kernel": D.K_KERNELS[k] + " (" + D.K_NAMES[k] + ")", "achieved": ach, "peak": peak, "unit": "GB/s",
                 "frac": ach / peak, "traffic": traffic_all.get(D.K_NAMES[k]), "peak_source": peak_src,
-                "bytes_per_unit": nbytes / max(class_rays[k], 1), "unit_of_work": unit,
-                "units_per_launch": class_rays[k] / max(class_launches[k], 1),
+                "bytes_per_unit": nbytes / max(units, 1), "unit_of_work": unit,
+                "units_per_launch": units / max(class_launches[k], 1),
                 "avg_launch_ms": ms / max(class_launches[k], 1), "share_of_step": ms / total_class if total_class else None}
     dom = max((k for k in unit_bytes if class_launches[k]), key=lambda k: class_ms[k])
     roofline = roof(dom)
@@ -457,6 +463,7 @@ def main():
                 "algorithmic bytes per unit as for config 1 (DESIGN.md 3); traffic figures in profiles/traffic.json were captured on config 1"})
     roofline_by_kernel = {D.K_NAMES[k]: roof(k) for k in unit_bytes if class_launches[k]}
     rays_total = class_rays[D.K_TRACE_PATH] + class_rays[D.K_TRACE_MIS] + class_rays[D.K_TRACE_SHADOW]
+    kernel_launch_counts = {D.K_NAMES[k]: class_launches[k] / prof_steps for k in range(D.K_CLASSES) if class_launches[k]}
     out = {
         "metric": "Msamples/sec (32-band spectral path trace)", "value": value, "unit": "Msamples/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
@@ -465,9 +472,11 @@ def main():
                 else "reference scene file lowered by the host side (substitutions listed in config.workload)" if not args.workload.startswith("synth")
                 else "synthetic scene written as .pbrt text, parsed, BVH-built and lowered by the reference's own code (oracle/make_golden.py)",
         "config": {"workload": workload_desc, "camera_samples_per_step": n_samples_total,
-                   "parallelism": "image tile sets (32x32, round-robin) x%d, scene replicated, film pixels of each rank's tiles gathered to rank 0 over NCCL and added" % world,
+                   "parallelism": "image tile sets (32x32, round-robin) x%d, scene replicated; every rank's film kernel adds its samples straight into ONE film "
+                                  "on rank 0 through a peer mapping (NVLink), a NCCL barrier ends the frame" % world,
                    "l2": "per-step wave state (>2 GB) and film are larger than L2; no explicit flush",
-                   "pipelining": "N > 1: the film exchange of frame k (a worker thread on its own stream) overlaps the render of frame k+1 (two film buffers); all work completes inside the timed region"},
+                   "pipelining": "N > 1: two film buffers alternate, rank 0 clears buffer k behind the barrier of frame k while frame k+1 fills the other; "
+                                 "every frame's film is complete on rank 0 inside the timed region"},
         "mrays_per_s": rays_total / prof_steps / (ms_per_step / 1e3) / 1e6 if world == 1 else None,
         "rays_per_sample": rays_total / prof_steps / (n_samples_total / world) if world else None,
         "rays_per_sample_reference": (rays_total + elided) / prof_steps / (n_samples_total / world) if world else None,
@@ -476,8 +485,11 @@ def main():
         "kernel_ms_per_step": {D.K_NAMES[k]: class_ms[k] / prof_steps for k in range(D.K_CLASSES) if class_launches[k]},
         "kernel_ms_note": "timed region: the frame's waves overlap on %d streams (ms_per_step); per-kernel times, rooflines and ray counts come "
                           "from %d more frames rendered with every wave on one stream (%.2f ms per frame), each kernel between its own CUDA events" % (lanes_used, prof_steps, serial_ms / prof_steps),
-        "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": scene_bytes, "d2h_bytes_per_step": film_bytes,
-                "ms_per_step": e2e_s * 1e3, "path": "spt_scene_create+spt_film_create+spt_render+spt_film_download, host buffers (film read into page-locked host memory)",
+        "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": scene_bytes * world, "d2h_bytes_per_step": film_bytes,
+                "ms_per_step": e2e_s * 1e3,
+                "path": "spt_scene_create+spt_film_create+spt_render+spt_film_download, host buffers (film read into page-locked host memory)" if world == 1 else
+                        "per rank spt_scene_create from host buffers + spt_render of its tile set into rank 0's film (cleared inside the timed region), "
+                        "end-of-frame barrier, rank 0 spt_film_download of the COMPLETE film into page-locked host memory; max over ranks",
                 "image_checksum": e2e_checksum},
         "gpu_launches": launches,
         "render_ms_max_rank": render_only_ms, "step_ms_max_rank": step_ms,
@@ -485,6 +497,8 @@ def main():
         "roofline_by_kernel": roofline_by_kernel,
         "clocks": sampler.summary() if sampler else None,
         "image_checksum": image_sum,
+        "film_check": film_check,
+        "kernel_launches_per_step": kernel_launch_counts,
     }
     if world == 1 and not args.no_cpu_baseline and os.path.exists(REF_BIN) and args.workload in CPU_WORKLOADS and \
             os.path.exists(os.path.join(REF_SCENES, args.workload + ".pbrt")):
@@ -495,7 +509,9 @@ def main():
     else:
         out["cpu_baseline"] = None
     print_json(out)
-    film.close(); scene.close()
+    for f in films:
+        f.close()
+    scene.close()
     if dist is not None:
         dist.destroy_process_group()
 

@@ -250,9 +250,12 @@ typedef struct SptRenderParams {
     int32_t integrator;             /* SPT_INTEGRATOR_* */
 } SptRenderParams;
 
-/* kernel classes of the wavefront, for per-class device time (CUDA events on the launching stream) */
+/* kernel classes of the wavefront, for per-class device time (CUDA events on the launching stream).
+ * SPT_K_TRACE_PATH times the ONE traversal launch of a bounce, which carries the bounce's path rays together with the
+ * previous bounce's shadow and MIS rays (class_ms of SPT_K_TRACE_SHADOW / _MIS stay 0; their class_rays are counted);
+ * SPT_K_ACCUMULATE = k_addlight (L += T (Le + Ld)), SPT_K_ADVANCE = k_advance (throughput, Russian roulette, next ray). */
 enum { SPT_K_GEN = 0, SPT_K_TRACE_PATH = 1, SPT_K_SHADE = 2, SPT_K_TRACE_SHADOW = 3, SPT_K_TRACE_MIS = 4,
-       SPT_K_ACCUMULATE = 5, SPT_K_FILM = 6, SPT_K_CLASSES = 8 };
+       SPT_K_ACCUMULATE = 5, SPT_K_FILM = 6, SPT_K_ADVANCE = 7, SPT_K_CLASSES = 8 };
 
 typedef struct SptStats {
     uint64_t camera_samples;        /* samples traced (cumulative) */
@@ -359,6 +362,32 @@ int      spt_film_write_dat(SptFilm *film, const char *path);
 /* The whole job: SamplerRenderer::Render without the final WriteImage
  * (src/renderers/samplerrenderer.cpp:188-222). Accumulates into film. */
 int spt_render(SptScene *scene, const SptCameraDesc *cam, SptFilm *film, const SptRenderParams *params);
+
+/* ---- several GPUs: the scene is replicated, the image is cut into square tiles dealt round-robin to the GPUs
+ * (SptRenderParams::tile_rank / tile_nranks, all samples of a pixel on one GPU), and K7 of every GPU adds its samples STRAIGHT
+ * INTO ONE film that lives on the first GPU - peer stores / reductions over NVLink issued by the film kernel itself, no
+ * separate exchange step, no staging copy. What is left of the "gather" is a barrier at the end of the frame. This replaces
+ * the reference's own partition of the image into independent tasks (src/renderers/samplerrenderer.cpp:203-214).
+ *
+ * One process, N devices: spt_multi_* below (one host thread per device inside the library).
+ * One process per GPU (torchrun): the process that owns the film exports it (spt_film_ipc_export), the others open it
+ * (spt_film_open_ipc) and render their tile sets into it with spt_render; the host barriers (e.g. over NCCL) at frame end. */
+#define SPT_IPC_HANDLE_BYTES 64
+int      spt_film_ipc_export(SptFilm *film, uint8_t handle[SPT_IPC_HANDLE_BYTES]);   /* library-allocated films only */
+SptFilm *spt_film_open_ipc(const SptFilmDesc *desc, const uint8_t handle[SPT_IPC_HANDLE_BYTES]);
+
+typedef struct SptMulti SptMulti;
+/* devices: n_devices CUDA ordinals, or NULL for 0 .. n_devices-1; n_devices <= 0: every visible device. The film lives on
+ * devices[0]; every other device must be able to reach it (cudaDeviceCanAccessPeer), else NULL / SPT_ERR_UNSUPP. */
+SptMulti *spt_multi_create(const SptSceneDesc *scene, const SptFilmDesc *film, int n_devices, const int *devices);
+void      spt_multi_destroy(SptMulti *m);
+int       spt_multi_device_count(SptMulti *m);
+/* The whole job on all devices: tile_rank / tile_nranks of params are set per device (a tile_size of 0 means 32).
+ * Accumulates into the shared film; returns when every device has finished. */
+int       spt_multi_render(SptMulti *m, const SptCameraDesc *cam, const SptRenderParams *params);
+SptFilm  *spt_multi_film(SptMulti *m);                        /* the complete film (download / clear / write_dat as usual) */
+int       spt_multi_get_stats(SptMulti *m, int index, SptStats *out);      /* per device, index 0 .. count-1 */
+double    spt_multi_last_render_ms(SptMulti *m);              /* slowest device's SptStats::render_ms of the last frame */
 
 #ifdef __cplusplus
 }

@@ -374,6 +374,57 @@ HEAVY_TAILED = {"metal_shipped_small", "bunny_measured_small"}     # the measure
 IMAGE_SEED = 2024
 
 
+# The reference's SpectralImageFilm::WriteImage adds `splatScale * splatC[nSpectralSamples]` to every band of a pixel
+# (src/film/spectralImage.cpp:307-313): one float PAST the splat array, i.e. Pixel::pad, which Pixel() never initialises
+# (src/film/spectralImage.h:74-84). The film is allocated at WorldEnd, after the scene's textures were read and their
+# temporary buffers freed, so on scenes with an environment map `pad` holds stale texels: a constant, band-independent,
+# spp-independent offset per pixel (0.36 per pixel on the grace-map scenes here = 65 samples' worth of radiance at 64 spp,
+# 0.4 % of the image at 8192 spp - found as a "bias" that two reference renders shared and eight GPU seeds did not).
+# Undefined behaviour is not a parity target: every reference IMAGE is rendered with glibc's MALLOC_PERTURB_=255, which
+# hands out zero-filled allocations, so the term reads as zero; the binary itself stays unmodified.
+REF_RENDER_ENV = dict(os.environ, MALLOC_PERTURB_="255")
+
+
+def pad_garbage(name, spp_tag):
+    """What the uninitialised Pixel::pad added to an EXISTING reference image of config `name`: the difference of two 1-spp
+    renders of the same scene (same samples, one task) without and with zero-filled allocations. The film is allocated
+    before any sampler or thread exists, so the garbage does not depend on spp or --ncores."""
+    sys.path.insert(0, REPO)
+    import numpy as np
+    from pbrt_v2_spectral_b200 import capi
+    build, w, h, _spp, _npix, _nrng, _img = CONFIGS[name]
+    out = []
+    for tag, env in (("g", dict(os.environ)), ("z", REF_RENDER_ENV)):
+        iname = "%s_pad%s" % (name, tag)
+        write(os.path.join(SCENES, iname + ".pbrt"), build(w, h, 1, iname))
+        subprocess.run([os.path.join(OUT, "bin/pbrt"), "--quiet", "--ncores", "1", iname + ".pbrt"], cwd=SCENES, env=env, check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        out.append(capi.read_dat(os.path.join(SCENES, iname + ".dat")))
+        os.remove(os.path.join(SCENES, iname + ".dat")); os.remove(os.path.join(SCENES, iname + ".pbrt"))
+    return out[0] - out[1]
+
+
+def fix_pad():
+    """Subtract the pad garbage from the reference images rendered before REF_RENDER_ENV existed (once: a marker is kept)."""
+    import json
+    import numpy as np
+    for f in sorted(os.listdir(GOLDEN)):
+        m = re.match(r"(.+)_(\d+)spp\.(ref2?)\.npy$", f)
+        if not m or m.group(1) not in CONFIGS:
+            continue
+        marker = os.path.join(GOLDEN, f[:-4] + ".padfix.json")
+        if os.path.exists(marker):
+            continue
+        E = pad_garbage(m.group(1), m.group(2))
+        img = np.load(os.path.join(GOLDEN, f))
+        if E.max() > 0:
+            np.save(os.path.join(GOLDEN, f), (img.astype(np.float64) - E).astype(np.float32))
+        with open(marker, "w") as fp:
+            json.dump({"pad_mean": float(E.mean()), "pad_max": float(E.max()), "share_of_image": float(E.sum() / max(img.sum(), 1e-30)),
+                       "how": "oracle/make_golden.py --fix-pad: 1-spp reference renders without / with MALLOC_PERTURB_=255"}, fp)
+        print("%-40s pad garbage: mean %.4g per pixel and band, %.3f %% of the image" % (f, E.mean(), 100 * E.sum() / max(img.sum(), 1e-30)), flush=True)
+
+
 def dat_to_npy(dat, npy):
     """The reference's .dat ([band][x][y] float64 sums, spectralImage.cpp:319-369) kept as [y][x][band] float32: half the
     bytes in the snapshot shipped to the GPU box; the 2^-24 relative rounding is far below the images' Monte-Carlo noise."""
@@ -406,6 +457,48 @@ def noise_floor(name, spp):
         name, spp, time.time() - t0, 100 * l1.max(), 100 * bias.max()), flush=True)
 
 
+# Reference-vs-reference floor of the converged-image check for the heavy-tailed scenes: a SECOND, independent render by the
+# unmodified reference (another --ncores gives another task split, hence other per-task RNG seeds and sample scrambles:
+# src/renderers/samplerrenderer.cpp:203-214,66-71) at the same spp. Their mutual per-band L1 / band-mean bias is what the
+# metric reads when both images are correct; tests/test_image_parity.py compares the GPU image with the mean of the two
+# renders against max(1 %, 1.2 x floor). The numbers are committed (tests/golden/image_floor.json), the images travel in
+# oracle/_ref/golden.
+FLOOR_NCORES = {"metal_shipped_small": 16, "bunny_measured_small": 32}
+
+
+def reference_floor(name, spp):
+    import json
+    import numpy as np
+    build, w, h, _spp, _npix, _nrng, img_spp = CONFIGS[name]
+    assert spp == img_spp
+    iname = "%s_%dspp" % (name, spp)
+    ref1 = os.path.join(GOLDEN, iname + ".ref.npy")
+    ref2 = os.path.join(GOLDEN, iname + ".ref2.npy")
+    n2 = FLOOR_NCORES[name]
+    if not os.path.exists(ref2):
+        i2 = iname + "_b"
+        write(os.path.join(SCENES, i2 + ".pbrt"), build(w, h, spp, i2))
+        t0 = time.time()
+        subprocess.run([os.path.join(OUT, "bin/pbrt"), "--quiet", "--ncores", str(n2), i2 + ".pbrt"],
+                       cwd=SCENES, env=REF_RENDER_ENV, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        dat_to_npy(os.path.join(SCENES, i2 + ".dat"), ref2)
+        os.remove(os.path.join(SCENES, i2 + ".pbrt"))
+        print("%-16s second reference render (--ncores %d) in %.1fs" % (name, n2, time.time() - t0), flush=True)
+    a = np.load(ref1).astype(np.float64) / spp
+    b = np.load(ref2).astype(np.float64) / spp
+    assert not np.array_equal(a, b), "the two reference renders are identical: same task split"
+    l1 = np.abs(a - b).sum((0, 1)) / (0.5 * (a + b)).sum((0, 1))
+    bias = np.abs(a.mean((0, 1)) - b.mean((0, 1))) / (0.5 * (a + b)).mean((0, 1))
+    fp = os.path.join(TESTS_GOLDEN, "image_floor.json")
+    floor = json.load(open(fp)) if os.path.exists(fp) else {}
+    floor[name] = {"spp": spp, "l1_max": float(l1.max()), "bias_max": float(bias.max()),
+                   "how": "two renders of oracle/_ref/bin/pbrt (unmodified reference), --ncores %s vs %d: per-band "
+                          "sum|a-b| / sum mean(a,b) and |mean a - mean b| / mean" % (read(os.path.join(GOLDEN, iname + ".txt")).split()[0].split("=")[1], n2)}
+    with open(fp, "w") as f:
+        json.dump(floor, f, indent=1, sort_keys=True)
+    print("%-16s reference vs reference at %d spp: L1 %.3f%%, bias %.3f%%" % (name, spp, 100 * l1.max(), 100 * bias.max()), flush=True)
+
+
 def share_arrays(path, donor, keys=("tex_texels",)):
     """Replace arrays of the container `path` that are byte-identical in `donor` by "<array>@" references to it (the loader
     resolves them): the shipped-floor scenes carry the same 22 MB texel pool."""
@@ -433,7 +526,17 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--images", action="store_true", help="also render reference .dat images")
     ap.add_argument("--only", default="", help="comma-separated config names")
+    ap.add_argument("--fix-pad", action="store_true", help="only: subtract the uninitialised Pixel::pad term from existing reference images")
+    ap.add_argument("--floor", action="store_true", help="only: second reference render + reference-vs-reference floor of the heavy-tailed scenes")
     args = ap.parse_args()
+    if args.fix_pad:
+        fix_pad()
+        return
+    if args.floor:
+        for name in sorted(HEAVY_TAILED):
+            if not args.only or name in args.only.split(","):
+                reference_floor(name, CONFIGS[name][6])
+        return
     names = [n for n in CONFIGS if not args.only or n in args.only.split(",")]
     names.sort(key=lambda n: (n in DELTA_BASE, n == "ssenv_path"))   # full-size workloads first (metal_path before ssenv_path): the golden variants refer to them
     # the synthetic scenes are written from scratch and lowered by the BUILT reference (oracle/_ref/bin/oracle_dump,
@@ -495,7 +598,9 @@ def main():
             t0 = time.time()
             ncores = os.cpu_count()
             subprocess.run([os.path.join(OUT, "bin/pbrt"), "--quiet", "--ncores", str(ncores), iname + ".pbrt"],
-                           cwd=SCENES, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                           cwd=SCENES, env=REF_RENDER_ENV, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            with open(os.path.join(GOLDEN, iname + ".ref.padfix.json"), "w") as fp:
+                fp.write('{"how": "rendered with MALLOC_PERTURB_=255: Pixel::pad reads as zero"}')
             dat_to_npy(os.path.join(SCENES, iname + ".dat"), os.path.join(GOLDEN, iname + ".ref.npy"))
             if name.startswith("synth"):
                 for f in (name + ".pbrt", iname + ".pbrt"):

@@ -216,3 +216,4 @@ Renderer *CreateGpuPathRenderer(const ParamSet &params, Sampler *sampler, Camera
                                 SurfaceIntegrator *surf, VolumeIntegrator *vol, bool visIds) {
     return new DumpRenderer(sampler, camera, surf, vol, visIds);
 }
+void GpuPathTouchParams(const ParamSet &) {}

@@ -21,7 +21,11 @@ SYMBOLS = [
     "spt_film_create", "spt_film_create_external", "spt_film_destroy", "spt_film_clear",
     "spt_film_add_samples", "spt_film_download", "spt_film_device_ptr", "spt_film_write_dat",
     "spt_render",
+    "spt_film_ipc_export", "spt_film_open_ipc",
+    "spt_multi_create", "spt_multi_destroy", "spt_multi_device_count", "spt_multi_render", "spt_multi_film", "spt_multi_get_stats",
+    "spt_multi_last_render_ms",
 ]
+IPC_HANDLE_BYTES = 64
 
 
 class SptError(RuntimeError):
@@ -69,6 +73,20 @@ def lib():
         L.spt_film_device_ptr.argtypes = [C.c_void_p]
         L.spt_film_write_dat.argtypes = [C.c_void_p, C.c_char_p]
         L.spt_render.argtypes = [C.c_void_p, C.POINTER(D.SptCameraDesc), C.c_void_p, C.POINTER(D.SptRenderParams)]
+        L.spt_film_ipc_export.argtypes = [C.c_void_p, C.c_void_p]
+        L.spt_film_open_ipc.restype = C.c_void_p
+        L.spt_film_open_ipc.argtypes = [C.POINTER(D.SptFilmDesc), C.c_void_p]
+        L.spt_multi_create.restype = C.c_void_p
+        L.spt_multi_create.argtypes = [C.POINTER(D.SptSceneDesc), C.POINTER(D.SptFilmDesc), C.c_int, C.c_void_p]
+        L.spt_multi_destroy.argtypes = [C.c_void_p]
+        L.spt_multi_destroy.restype = None
+        L.spt_multi_device_count.argtypes = [C.c_void_p]
+        L.spt_multi_render.argtypes = [C.c_void_p, C.POINTER(D.SptCameraDesc), C.POINTER(D.SptRenderParams)]
+        L.spt_multi_film.restype = C.c_void_p
+        L.spt_multi_film.argtypes = [C.c_void_p]
+        L.spt_multi_get_stats.argtypes = [C.c_void_p, C.c_int, C.POINTER(D.SptStats)]
+        L.spt_multi_last_render_ms.restype = C.c_double
+        L.spt_multi_last_render_ms.argtypes = [C.c_void_p]
         if L.spt_nbands() != D.NBANDS:
             raise SptError("libspt.so was built for %d bands, the Python side expects %d" % (L.spt_nbands(), D.NBANDS))
         _lib = L
@@ -200,18 +218,33 @@ class Scene:
 class Film:
     """SpectralImageFilm accumulator on the device (spt_film_create[_external])."""
 
-    def __init__(self, desc, device_ptr=None):
+    def __init__(self, desc, device_ptr=None, ipc_handle=None, borrowed=None):
+        """device_ptr: accumulate into caller-provided device memory; ipc_handle: the 64 bytes another process's
+        Film.ipc_export() returned - this film then adds into THAT film's pixels over NVLink (spt_film_open_ipc);
+        borrowed: an SptFilm* owned by someone else (MultiRenderer.film)."""
         self.desc = desc
-        if device_ptr is None:
+        self.owner = borrowed is None
+        if borrowed is not None:
+            self.h = borrowed
+        elif ipc_handle is not None:
+            hb = (C.c_uint8 * IPC_HANDLE_BYTES).from_buffer_copy(bytes(ipc_handle))
+            self.h = lib().spt_film_open_ipc(C.byref(desc), hb)
+        elif device_ptr is None:
             self.h = lib().spt_film_create(C.byref(desc))
         else:
             self.h = lib().spt_film_create_external(C.byref(desc), C.c_void_p(device_ptr))
         if not self.h:
             raise SptError("spt_film_create: " + (lib().spt_last_error() or b"").decode())
 
+    def ipc_export(self):
+        hb = (C.c_uint8 * IPC_HANDLE_BYTES)()
+        _check(lib().spt_film_ipc_export(self.h, hb))
+        return bytes(hb)
+
     def close(self):
         if self.h:
-            lib().spt_film_destroy(self.h)
+            if self.owner:
+                lib().spt_film_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -245,6 +278,54 @@ class Film:
 
     def write_dat(self, path):
         _check(lib().spt_film_write_dat(self.h, path.encode()))
+
+
+def _stats_dict(st):
+    d = {k: getattr(st, k) for k, _ in D.SptStats._fields_ if k not in ("class_ms", "class_launches", "class_rays", "pad_")}
+    d["class_ms"] = list(st.class_ms); d["class_launches"] = list(st.class_launches); d["class_rays"] = list(st.class_rays)
+    return d
+
+
+class MultiRenderer:
+    """The whole job on several GPUs of this process (spt_multi_*): scene replicated, image tile sets dealt round-robin, every
+    GPU's film kernel adding straight into ONE film on the first device over NVLink."""
+
+    def __init__(self, lowered, n_devices=0, devices=None):
+        self.lowered = lowered
+        arr = (C.c_int * len(devices))(*devices) if devices else None
+        self.h = lib().spt_multi_create(C.byref(lowered.desc), C.byref(lowered.film), len(devices) if devices else int(n_devices), arr)
+        if not self.h:
+            raise SptError("spt_multi_create: " + (lib().spt_last_error() or b"").decode())
+        self.film = Film(lowered.film, borrowed=lib().spt_multi_film(self.h))
+
+    @property
+    def device_count(self):
+        return lib().spt_multi_device_count(self.h)
+
+    def render(self, params=None, camera=None):
+        rp = params if params is not None else self.lowered.params
+        cam = camera if camera is not None else self.lowered.camera
+        _check(lib().spt_multi_render(self.h, C.byref(cam), C.byref(rp)))
+
+    def stats(self, index=0):
+        st = D.SptStats()
+        _check(lib().spt_multi_get_stats(self.h, index, C.byref(st)))
+        return _stats_dict(st)
+
+    def render_ms(self):
+        return lib().spt_multi_last_render_ms(self.h)
+
+    def close(self):
+        if self.h:
+            self.film.close()
+            lib().spt_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def read_dat(path):

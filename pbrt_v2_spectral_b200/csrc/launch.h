@@ -9,7 +9,9 @@
 #include "trace_args.h"
 
 void spt_launch_gen_camera(int grid, cudaStream_t st, const RenderCfg &cfg, const SampleSource &src, const WaveBuffers &wb, uint32_t *count_out);
-void spt_launch_trace(bool any, int variant, bool count, int grid, cudaStream_t st, const DevScene &sc, const TraceArgs &a);
+// variant 1: ONE launch of the pair-node kernel over all segments (merge) or one per segment; variant 0 (trees that do not pack):
+// the reference-layout kernel, one launch per segment. a.work points at TRACE_MAX_SEG zeroed words.
+void spt_launch_trace_multi(int variant, bool merge, bool count, int grid, cudaStream_t st, const DevScene &sc, const TraceMultiArgs &a);
 void spt_launch_camera_rays(cudaStream_t st, const SptCameraDesc &cam, const float *samples, uint32_t n, float *out);
 void spt_launch_split_rays(cudaStream_t st, const float *rays, uint32_t n, float4 *ro, float4 *rd);
 void spt_launch_slot_to_id(cudaStream_t st, const uint32_t *slot, const uint32_t *prim_id, uint32_t n, uint32_t *out);
@@ -21,8 +23,10 @@ void spt_launch_miss_env(int grid, cudaStream_t st, const DevScene &sc, const Wa
 void spt_launch_shade(int grid, cudaStream_t st, const DevScene &sc, const RenderCfg &cfg, const SampleSource &src, const WaveBuffers &wb,
                       int bounce, const uint32_t *queue, const uint32_t *count, uint32_t *shadow_count, uint32_t *mis_count,
                       uint32_t *elided_count, uint32_t *mis_any_count);
-void spt_launch_accumulate(int grid, cudaStream_t st, const DevScene &sc, const RenderCfg &cfg, const WaveBuffers &wb, int bounce,
-                           const uint32_t *queue, const uint32_t *count, uint32_t *next_queue, uint32_t *next_count);
+void spt_launch_advance(int grid, cudaStream_t st, const DevScene &sc, const RenderCfg &cfg, const WaveBuffers &wb, int bounce,
+                        const uint32_t *queue, const uint32_t *count, uint32_t *next_queue, uint32_t *next_count);
+void spt_launch_addlight(int grid, cudaStream_t st, const DevScene &sc, const RenderCfg &cfg, const WaveBuffers &wb, int bounce,
+                         const uint32_t *queue, const uint32_t *count);
 void spt_launch_film_add(int grid, cudaStream_t st, const FilmView &film, const SptSpectralTables *tables, const float2 *img_xy,
                          const float *L, uint32_t cap, uint32_t n_samples, int spp);
 void spt_launch_film_split(int grid, cudaStream_t st, const float *pix, size_t npix, float *c, float *w);

@@ -10,6 +10,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 #include "launch.h"
 
@@ -112,6 +113,7 @@ struct SptScene {
     bool counters_on = false;
     int trace_variant = 1;           // trace_kernels.cuh: 0 reference nodes, 1 pair nodes (default)
     uint32_t fetch_threshold = 14;
+    bool merge_trace = true;         // one persistent trace launch per bounce over all its ray queues (SPT_MERGE_TRACE=0: one per queue)
     int max_lanes = 4;               // spt_scene_set_lanes: the most streams a frame's waves are dealt to (1 = one stream: per-kernel
                                      // timing is then exact). A frame that fits two waves uses two lanes - fewer, larger waves win
                                      // (profiles/r01_rank_emulation.log) - a frame of many memory-capped waves uses all of them.
@@ -172,6 +174,7 @@ struct SptFilm {
     float *pix = nullptr;           // [y][x][NB+1]
     bool owned = true;
     float *table = nullptr;
+    void *ipc_base = nullptr;       // pixels opened from another process's film (spt_film_open_ipc): closed on destroy
     float *split = nullptr;         // download staging: [y][x][NB] followed by [y][x] weights
     DevMem mem;                     // owned device blocks (pixels unless external, filter table, staging)
     size_t npix() const { return (size_t)desc.x_pixel_count * desc.y_pixel_count; }
@@ -237,6 +240,7 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
     cudaGetDevice(&s->device);
     if (const char *e = getenv("SPT_TRACE_VARIANT")) s->trace_variant = atoi(e);
     if (const char *e = getenv("SPT_FETCH_THRESHOLD")) s->fetch_threshold = (uint32_t)atoi(e);
+    if (const char *e = getenv("SPT_MERGE_TRACE")) s->merge_trace = atoi(e) != 0;
     if (const char *e = getenv("SPT_LANES")) s->max_lanes = std::min(std::max(atoi(e), 1), SPT_MAX_LANES);
     DevScene &v = s->dev;
     memset(&v, 0, sizeof(v));
@@ -488,15 +492,13 @@ int spt_get_stats(SptScene *s, SptStats *out) {
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------------
-// Device-side counters of one bounce: {path rays, shadow rays, MIS rays traced, hits, 3 x trace work
-// cursors, escaped camera rays, MIS rays elided (could not reach the light), MIS rays traced as any-hit + their cursor}
 #define SPT_ROW 16
 
 static int ensure_wave(SptScene *s, int n_lanes, uint32_t cap, int max_depth, size_t n_waves, uint32_t sub = 1) {
     cap = (cap + 31u) & ~31u;
     const size_t jcap = (size_t)cap * sub;
     if (jcap > 0xffffffffull) return fail(SPT_ERR_ARG, "wave too large: paths x jobs per path exceeds 2^32 (lower wave_pixels)");
-    size_t need_counts = n_waves * (size_t)(max_depth + 2) * SPT_ROW;
+    size_t need_counts = n_waves * (size_t)(max_depth + 3) * SPT_ROW;
     for (int li = 0; li < n_lanes; ++li) {
         SptScene::Lane &ln = s->lane[li];
         if (ln.wb.cap >= cap && ln.wb.jcap >= jcap) continue;
@@ -514,7 +516,7 @@ static int ensure_wave(SptScene *s, int n_lanes, uint32_t cap, int max_depth, si
         AL(w.rec3, float4, s->dev.has_ext ? jcap : 1); AL(w.rec4, float4, s->dev.has_ext ? jcap : 1);
         AL(w.frow, float, s->dev.has_measured ? jcap * 3 * NB : 1);
         AL(w.img_xy, float2, cap);
-        AL(w.T, float, (size_t)cap * NB); AL(w.L, float, (size_t)cap * NB);
+        AL(w.T[0], float, (size_t)cap * NB); AL(w.T[1], float, (size_t)cap * NB); AL(w.L, float, (size_t)cap * NB);
         AL(w.pathQ[0], uint32_t, cap); AL(w.pathQ[1], uint32_t, cap); AL(w.shadowQ, uint32_t, jcap); AL(w.misQ, uint32_t, jcap);
         AL(w.hitQ, uint32_t, cap); AL(w.missQ, uint32_t, cap); AL(w.misAnyQ, uint32_t, jcap);
 #undef AL
@@ -529,17 +531,32 @@ static int ensure_wave(SptScene *s, int n_lanes, uint32_t cap, int max_depth, si
     return SPT_OK;
 }
 
-// One launch of the traversal kernel (variant chosen per scene; SPT_TRACE_VARIANT overrides for experiments).
-template <bool ANY>
-static void launch_trace(SptScene *s, cudaStream_t st, int grid, const uint32_t *queue, const uint32_t *count, uint32_t *work,
-                         const float4 *ro, const float4 *rd, uint32_t *out_slot, float *out_t) {
-    TraceArgs a; a.queue = queue; a.count = count; a.work = work; a.ro = ro; a.rd = rd; a.out_slot = out_slot; a.out_t = out_t;
-    a.fetch_threshold = s->fetch_threshold;
-    spt_launch_trace(ANY, s->trace_variant, s->counters_on, grid, st, s->dev, a);
+// Row of device counters of bounce b (SPT_ROW words, zeroed per frame):
+//   0 path rays into the bounce, 1 shadow rays, 2 MIS rays traced as closest-hit queries, 3 hits, 4..7 work cursors of the
+//   trace launch that carries the bounce's path rays, 8 MIS rays elided (could not reach the light), 9 MIS rays traced as
+//   any-hit queries (towards an infinite light), 10 escaped rays
+// One trace launch over up to four ray queues (variant chosen per scene; SPT_TRACE_VARIANT / SPT_MERGE_TRACE override).
+struct SegList {
+    TraceMultiArgs a;
+    SegList() { memset(&a, 0, sizeof(a)); }
+    void add(bool any, const uint32_t *queue, const uint32_t *count, const float4 *ro, const float4 *rd, uint32_t *out_slot, float *out_t) {
+        TraceSeg &g = a.seg[a.nseg++];
+        g.queue = queue; g.count = count; g.ro = ro; g.rd = rd; g.out_slot = out_slot; g.out_t = out_t; g.any = any ? 1u : 0u;
+    }
+};
+static void launch_trace(SptScene *s, cudaStream_t st, int grid, SegList &sl, uint32_t *work) {
+    sl.a.work = work;
+    sl.a.fetch_threshold = s->fetch_threshold;
+    spt_launch_trace_multi(s->trace_variant, s->merge_trace, s->counters_on, grid, st, s->dev, sl.a);
 }
 
-// Runs one wave: K1, then (K2, K5, K3, K2, K6) per bounce. counts: (max_depth+2) x 4 device words,
-// zeroed; row b = {path rays into bounce b, shadow rays of bounce b, MIS rays of bounce b, -}.
+// Runs one wave: K1, then per bounce b
+//   trace   { path rays of b | shadow, MIS, MIS-any rays of b-1 }     one persistent launch
+//   K6b     k_addlight(b-1): L += T (Le + Ld)                          (needs the shadow / MIS verdicts just traced)
+//   compact hits of b, [escaped rays -> environment light]
+//   K5      k_shade(b): records + shadow / MIS rays of b
+//   K6a     k_advance(b): T' = T f|cos|/pdf, Russian roulette, path rays of b+1      (not at the last bounce)
+// and a last trace { shadow, MIS, MIS-any of max_depth } + k_addlight(max_depth).
 static void run_wave(SptScene *s, const RenderCfg &cfg, const SampleSource &src, uint32_t *counts, int li = 0) {
     cudaStream_t st = s->lane[li].stream;
     const WaveBuffers &wb = s->lane[li].wb;
@@ -551,37 +568,48 @@ static void run_wave(SptScene *s, const RenderCfg &cfg, const SampleSource &src,
     s->mark(-1, li);
     spt_launch_gen_camera(gridN, st, cfg, src, wb, counts + 0);
     s->mark(SPT_K_GEN, li);
+    const uint64_t nj = (uint64_t)n * (uint64_t)std::max(cfg.sub, 1);
     int gridT = (int)std::min<uint64_t>(((uint64_t)n + 127) / 128, (uint64_t)sms * 16);
     if (gridT < 1) gridT = 1;
-    int gridP = std::min(gridT, sms * 8);      // persistent trace kernels: resident blocks only
+    int gridP = (int)std::min<uint64_t>((nj + 127) / 128, (uint64_t)sms * 8);      // persistent trace kernels: resident blocks only
+    if (gridP < 1) gridP = 1;
     int gridC = (int)std::min<uint64_t>(((uint64_t)n + 2047) / 2048, (uint64_t)sms * 8);
     if (gridC < 1) gridC = 1;
-    for (int b = 0; b <= cfg.max_depth; ++b) {
-        uint32_t *row = counts + SPT_ROW * b, *next = counts + SPT_ROW * (b + 1);
-        uint32_t *q = b == 0 ? nullptr : wb.pathQ[b & 1], *qn = wb.pathQ[(b + 1) & 1];     // camera rays: sample order, no queue
+    const bool lights = sc.n_lights > 0;
+    for (int b = 0; b <= cfg.max_depth + 1; ++b) {
+        uint32_t *row = counts + SPT_ROW * b, *prev = b > 0 ? counts + SPT_ROW * (b - 1) : nullptr, *next = counts + SPT_ROW * (b + 1);
+        const bool last = b == cfg.max_depth + 1;                                            // only the light rays of max_depth are left
+        uint32_t *q = b == 0 ? nullptr : wb.pathQ[b & 1], *qn = wb.pathQ[(b + 1) & 1];      // camera rays: sample order, no queue
+        SegList sl;
+        if (!last) sl.add(false, q, row + 0, wb.ray_o, wb.ray_d, wb.hit_slot, wb.hit_t);
+        if (prev && lights) {
+            sl.add(true, wb.shadowQ, prev + 1, wb.g0, wb.g1, wb.sh_slot, nullptr);
+            sl.add(false, wb.misQ, prev + 2, wb.g0, wb.g2, wb.mis_slot, wb.mis_t);
+            // EstimateDirect's BSDF-sampled ray towards an INFINITE light contributes Le iff it escapes
+            // (integrator.cpp:151-158: a hit primitive never is that light): an any-hit query
+            if (s->has_env) sl.add(true, wb.misAnyQ, prev + 9, wb.g0, wb.g2, wb.mis_slot, nullptr);
+        }
+        if (sl.a.nseg) {
+            launch_trace(s, st, gridP, sl, row + 4);
+            s->mark(SPT_K_TRACE_PATH, li);
+            if (!s->merge_trace || s->trace_variant == 0) s->launches += sl.a.nseg - 1;
+        }
+        if (prev) {
+            spt_launch_addlight(gridT, st, sc, cfg, wb, b - 1, wb.hitQ, prev + 3);
+            s->mark(SPT_K_ACCUMULATE, li);
+        }
+        if (last) break;
         // camera rays that escape pick up the environment light (samplerrenderer.cpp:239-243)
         uint32_t *mq = (s->has_env && (b == 0 || sc.has_specular)) ? wb.missQ : nullptr;
-        launch_trace<false>(s, st, gridP, q, row + 0, row + 4, wb.ray_o, wb.ray_d, wb.hit_slot, wb.hit_t);
-        s->mark(SPT_K_TRACE_PATH, li);
-        spt_launch_compact_hits(gridC, st, q, row + 0, wb.hit_slot, wb.hitQ, row + 3, mq, row + 7, (b == 0 && !s->has_env) ? wb.L : nullptr);
+        spt_launch_compact_hits(gridC, st, q, row + 0, wb.hit_slot, wb.hitQ, row + 3, mq, row + 10, (b == 0 && !s->has_env) ? wb.L : nullptr);
         s->mark(SPT_K_SHADE, li);
-        if (mq) { spt_launch_miss_env(gridT, st, sc, wb, b, mq, row + 7); s->mark(SPT_K_SHADE, li); }
+        if (mq) { spt_launch_miss_env(gridT, st, sc, wb, b, mq, row + 10); s->mark(SPT_K_SHADE, li); }
         spt_launch_shade(gridT, st, sc, cfg, src, wb, b, wb.hitQ, row + 3, row + 1, row + 2, row + 8, row + 9);
         s->mark(SPT_K_SHADE, li);
-        if (sc.n_lights > 0) {
-            launch_trace<true>(s, st, gridP, wb.shadowQ, row + 1, row + 5, wb.g0, wb.g1, wb.sh_slot, nullptr);
-            s->mark(SPT_K_TRACE_SHADOW, li);
-            launch_trace<false>(s, st, gridP, wb.misQ, row + 2, row + 6, wb.g0, wb.g2, wb.mis_slot, wb.mis_t);
-            s->mark(SPT_K_TRACE_MIS, li);
-            if (s->has_env) {
-                // EstimateDirect's BSDF-sampled ray towards an INFINITE light contributes Le iff it escapes
-                // (integrator.cpp:151-158: a hit primitive never is that light): an any-hit query
-                launch_trace<true>(s, st, gridP, wb.misAnyQ, row + 9, row + 10, wb.g0, wb.g2, wb.mis_slot, nullptr);
-                s->mark(SPT_K_TRACE_MIS, li);
-            }
+        if (b < cfg.max_depth) {
+            spt_launch_advance(gridT, st, sc, cfg, wb, b, wb.hitQ, row + 3, qn, next + 0);
+            s->mark(SPT_K_ADVANCE, li);
         }
-        spt_launch_accumulate(gridT, st, sc, cfg, wb, b, wb.hitQ, row + 3, qn, next + 0);
-        s->mark(SPT_K_ACCUMULATE, li);
     }
 }
 
@@ -609,12 +637,13 @@ static void reset_class_stats(SptScene *s) {
 static void add_ray_stats(SptScene *s, const std::vector<uint32_t> &counts, int max_depth, size_t n_waves) {
     for (size_t w = 0; w < n_waves; ++w)
         for (int b = 0; b <= max_depth; ++b) {
-            const uint32_t *row = &counts[(w * (size_t)(max_depth + 2) + b) * SPT_ROW];
+            const uint32_t *row = &counts[(w * (size_t)(max_depth + 3) + b) * SPT_ROW];
             s->stats.closest_rays += row[0] + row[2];
             s->stats.any_rays += row[1];
             s->stats.class_rays[SPT_K_TRACE_PATH] += row[0];
             s->stats.class_rays[SPT_K_SHADE] += row[3];
             s->stats.class_rays[SPT_K_ACCUMULATE] += row[3];
+            if (b < max_depth) s->stats.class_rays[SPT_K_ADVANCE] += row[3];
             s->stats.class_rays[SPT_K_TRACE_SHADOW] += row[1];
             s->stats.class_rays[SPT_K_TRACE_MIS] += row[2] + row[9];
             s->stats.any_rays += row[9];
@@ -646,8 +675,9 @@ static int trace_dev(SptScene *s, bool any, const float4 *ro, const float4 *rd, 
     if (grid < 1) grid = 1;
     cudaStream_t st = s->stream;
     cudaEventRecord(s->ev0, st);
-    if (any) launch_trace<true>(s, st, grid, nullptr, count_dev, count_dev + 1, ro, rd, slot, t);
-    else launch_trace<false>(s, st, grid, nullptr, count_dev, count_dev + 1, ro, rd, slot, t);
+    SegList sl;
+    sl.add(any, nullptr, count_dev, ro, rd, slot, t);
+    launch_trace(s, st, grid, sl, count_dev + 1);
     cudaEventRecord(s->ev1, st);
     s->launches += 1;
     CU(cudaStreamSynchronize(st));
@@ -769,7 +799,7 @@ int spt_shade_samples(SptScene *s, const SptCameraDesc *cam, int32_t integrator,
     cfg.tile = 1; cfg.tile_shift = 0; cfg.tilesX = 1; cfg.tilesY = 1; cfg.nranks = 1;
     cfg.diff_scale = 1.f / sqrtf((float)spp);
     SampleSource src; src.smp = dsmp; src.stride = stride; src.rng = drng; src.n_rng = drng ? n_rng : 0; src.seed = 0; src.spp = 1;
-    size_t nc = (size_t)(max_depth + 2) * SPT_ROW;
+    size_t nc = (size_t)(max_depth + 3) * SPT_ROW;
     cudaMemsetAsync(s->counts, 0, nc * 4, s->stream);
     reset_class_stats(s);
     run_wave(s, cfg, src, s->counts);
@@ -822,6 +852,7 @@ void spt_film_destroy(SptFilm *f) {
     DeviceGuard dg(f->device);
     cudaDeviceSynchronize();
     f->mem.release();
+    if (f->ipc_base) cudaIpcCloseMemHandle(f->ipc_base);
     delete f;
 }
 int spt_film_clear(SptFilm *f) {
@@ -978,7 +1009,7 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
         wave_pixels = (wave_pixels + 1) / 2;
     }
     if (rc != SPT_OK) return rc;
-    size_t per_wave = (size_t)(depth + 2) * SPT_ROW;
+    size_t per_wave = (size_t)(depth + 3) * SPT_ROW;
     cudaStream_t st = s->stream;
     CU(cudaMemsetAsync(s->counts, 0, std::max<size_t>(n_waves, 1) * per_wave * 4, st));
     SampleSource src; src.smp = nullptr; src.stride = 0; src.rng = nullptr; src.n_rng = 0; src.seed = cfg.seed; src.spp = (uint32_t)rp->spp;
@@ -1029,6 +1060,141 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
     s->stats.closest_rays -= overhang;
     s->stats.class_rays[SPT_K_TRACE_PATH] -= overhang;
     return SPT_OK;
+}
+
+
+// ---- several GPUs ------------------------------------------------------------------------------------
+int spt_film_ipc_export(SptFilm *f, uint8_t handle[SPT_IPC_HANDLE_BYTES]) {
+    if (!f || !handle) return fail(SPT_ERR_ARG, "null argument");
+    if (!f->owned) return fail(SPT_ERR_ARG, "only films allocated by the library can be exported");
+    static_assert(sizeof(cudaIpcMemHandle_t) == SPT_IPC_HANDLE_BYTES, "IPC handle size");
+    DeviceGuard dg(f->device);
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, f->pix));
+    memcpy(handle, &h, sizeof(h));
+    return SPT_OK;
+}
+SptFilm *spt_film_open_ipc(const SptFilmDesc *d, const uint8_t handle[SPT_IPC_HANDLE_BYTES]) {
+    if (!d || !handle) { g_err = "null argument"; return nullptr; }
+    if (spt_device_count() <= 0) { g_err = "no CUDA device: this library has no CPU path"; return nullptr; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void *p = nullptr;
+    CUP(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    SptFilm *f = film_new(d, (float *)p);
+    if (!f) { cudaIpcCloseMemHandle(p); return nullptr; }
+    f->ipc_base = p;
+    return f;
+}
+
+}  // extern "C"
+
+struct SptMulti {
+    std::vector<int> devices;
+    std::vector<SptScene *> scenes;
+    std::vector<SptFilm *> films;        // films[0] owns the pixels (devices[0]); the others alias them through peer access
+    std::vector<int> rc;
+    std::vector<std::string> err;
+};
+
+// runs fn(k) on one host thread per device, with that device current; gathers status + message per device
+template <typename F> static int multi_run(SptMulti *m, F fn) {
+    const size_t n = m->devices.size();
+    std::vector<std::thread> th;
+    for (size_t k = 0; k < n; ++k)
+        th.emplace_back([m, k, &fn]() {
+            m->rc[k] = SPT_OK; m->err[k].clear();
+            if (cudaSetDevice(m->devices[k]) != cudaSuccess) { m->rc[k] = SPT_ERR_CUDA; m->err[k] = "cudaSetDevice failed"; cudaGetLastError(); return; }
+            m->rc[k] = fn(k);
+            if (m->rc[k] != SPT_OK) m->err[k] = g_err;
+        });
+    for (auto &t : th) t.join();
+    for (size_t k = 0; k < n; ++k)
+        if (m->rc[k] != SPT_OK) { g_err = "device " + std::to_string(m->devices[k]) + ": " + m->err[k]; return m->rc[k]; }
+    return SPT_OK;
+}
+
+extern "C" {
+
+void spt_multi_destroy(SptMulti *m) {
+    if (!m) return;
+    multi_run(m, [m](size_t k) {
+        if (k > 0 && k < m->films.size() && m->films[k]) spt_film_destroy(m->films[k]);
+        if (k < m->scenes.size() && m->scenes[k]) spt_scene_destroy(m->scenes[k]);
+        return SPT_OK;
+    });
+    if (!m->films.empty() && m->films[0]) spt_film_destroy(m->films[0]);
+    delete m;
+}
+
+SptMulti *spt_multi_create(const SptSceneDesc *scene, const SptFilmDesc *film, int n_devices, const int *devices) {
+    if (!scene || !film) { g_err = "null argument"; return nullptr; }
+    const int visible = spt_device_count();
+    if (visible <= 0) { g_err = "no CUDA device: this library has no CPU path"; return nullptr; }
+    if (n_devices <= 0) { n_devices = visible; devices = nullptr; }
+    SptMulti *m = new SptMulti();
+    for (int k = 0; k < n_devices; ++k) {
+        const int d = devices ? devices[k] : k;
+        if (d < 0 || d >= visible) { g_err = "device ordinal out of range"; delete m; return nullptr; }
+        for (int dd : m->devices) if (dd == d) { g_err = "a device is listed twice"; delete m; return nullptr; }
+        m->devices.push_back(d);
+    }
+    const size_t n = m->devices.size();
+    m->scenes.assign(n, nullptr); m->films.assign(n, nullptr); m->rc.assign(n, SPT_OK); m->err.assign(n, "");
+    int prev = 0; cudaGetDevice(&prev);
+    // the film: on the first device; every other device reaches it through peer access (NVLink / NVSwitch)
+    for (size_t k = 1; k < n; ++k) {
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, m->devices[k], m->devices[0]) != cudaSuccess || !can) {
+            g_err = "device " + std::to_string(m->devices[k]) + " cannot access the film's device " + std::to_string(m->devices[0]) + " (no peer access)";
+            cudaGetLastError(); delete m; return nullptr;
+        }
+    }
+    cudaSetDevice(m->devices[0]);
+    m->films[0] = spt_film_create(film);
+    cudaSetDevice(prev);
+    if (!m->films[0]) { delete m; return nullptr; }
+    float *pix0 = m->films[0]->pix;
+    int rc = multi_run(m, [m, scene, film, pix0](size_t k) {
+        if (k > 0) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(m->devices[0], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { g_err = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e); cudaGetLastError(); return SPT_ERR_CUDA; }
+            cudaGetLastError();
+            m->films[k] = spt_film_create_external(film, pix0);
+            if (!m->films[k]) return SPT_ERR_CUDA;
+        }
+        m->scenes[k] = spt_scene_create(scene);
+        return m->scenes[k] ? SPT_OK : SPT_ERR_CUDA;
+    });
+    cudaSetDevice(prev);
+    if (rc != SPT_OK) { std::string keep = g_err; spt_multi_destroy(m); g_err = keep; return nullptr; }
+    return m;
+}
+
+int spt_multi_device_count(SptMulti *m) { return m ? (int)m->devices.size() : 0; }
+SptFilm *spt_multi_film(SptMulti *m) { return m ? m->films[0] : nullptr; }
+
+int spt_multi_render(SptMulti *m, const SptCameraDesc *cam, const SptRenderParams *rp) {
+    if (!m || !cam || !rp) return fail(SPT_ERR_ARG, "null argument");
+    const int n = (int)m->devices.size();
+    // every device renders its tile set into the one film and returns when its streams have drained: the join below is
+    // the end-of-frame barrier
+    return multi_run(m, [m, cam, rp, n](size_t k) {
+        SptRenderParams p = *rp;
+        p.tile_rank = (int)k; p.tile_nranks = n;
+        if (p.tile_size <= 0) p.tile_size = 32;
+        return spt_render(m->scenes[k], cam, m->films[k], &p);
+    });
+}
+
+int spt_multi_get_stats(SptMulti *m, int index, SptStats *out) {
+    if (!m || index < 0 || index >= (int)m->devices.size()) return fail(SPT_ERR_ARG, "device index out of range");
+    return spt_get_stats(m->scenes[index], out);
+}
+double spt_multi_last_render_ms(SptMulti *m) {
+    double t = 0.;
+    if (m) for (SptScene *s : m->scenes) if (s) t = std::max(t, s->stats.render_ms);
+    return t;
 }
 
 }  // extern "C"

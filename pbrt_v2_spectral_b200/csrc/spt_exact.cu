@@ -80,13 +80,23 @@ void spt_launch_gen_camera(int grid, cudaStream_t st, const RenderCfg &cfg, cons
                            uint32_t *count_out) {
     k_gen_camera<<<grid, 256, 0, st>>>(cfg, src, wb, count_out);
 }
-void spt_launch_trace(bool any, int variant, bool count, int grid, cudaStream_t st, const DevScene &sc, const TraceArgs &a) {
-#define SPT_T(K) do { \
-        if (any) { if (count) K<true, true><<<grid, 128, 0, st>>>(sc, a); else K<true, false><<<grid, 128, 0, st>>>(sc, a); } \
-        else { if (count) K<false, true><<<grid, 128, 0, st>>>(sc, a); else K<false, false><<<grid, 128, 0, st>>>(sc, a); } } while (0)
-    if (variant == 0) SPT_T(k_trace_v0);
-    else SPT_T(k_trace_v1);
-#undef SPT_T
+static void launch_multi(bool count, int grid, cudaStream_t st, const DevScene &sc, const TraceMultiArgs &a) {
+    if (count) k_trace_multi<true><<<grid, 128, 0, st>>>(sc, a); else k_trace_multi<false><<<grid, 128, 0, st>>>(sc, a);
+}
+void spt_launch_trace_multi(int variant, bool merge, bool count, int grid, cudaStream_t st, const DevScene &sc, const TraceMultiArgs &a) {
+    if (variant != 0 && merge) { launch_multi(count, grid, st, sc, a); return; }
+    for (uint32_t k = 0; k < a.nseg; ++k) {
+        if (variant != 0) {
+            TraceMultiArgs one = a;
+            one.seg[0] = a.seg[k]; one.nseg = 1; one.work = a.work + k;
+            launch_multi(count, grid, st, sc, one);
+        } else {
+            TraceArgs t; t.queue = a.seg[k].queue; t.count = a.seg[k].count; t.work = a.work + k; t.ro = a.seg[k].ro; t.rd = a.seg[k].rd;
+            t.out_slot = a.seg[k].out_slot; t.out_t = a.seg[k].out_t; t.fetch_threshold = a.fetch_threshold;
+            if (a.seg[k].any) { if (count) k_trace_v0<true, true><<<grid, 128, 0, st>>>(sc, t); else k_trace_v0<true, false><<<grid, 128, 0, st>>>(sc, t); }
+            else { if (count) k_trace_v0<false, true><<<grid, 128, 0, st>>>(sc, t); else k_trace_v0<false, false><<<grid, 128, 0, st>>>(sc, t); }
+        }
+    }
 }
 void spt_launch_camera_rays(cudaStream_t st, const SptCameraDesc &cam, const float *samples, uint32_t n, float *out) {
     k_camera_rays<<<grid256(n), 256, 0, st>>>(cam, samples, n, out);

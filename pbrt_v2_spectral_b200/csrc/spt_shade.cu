@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(128) k_miss_env(DevScene sc, WaveBuffers wb, i
                 for (int c = 0; c < NB; ++c) Le[c] += illum_band(*sc.tables, k, c);
             }
         if (bounce == 0) { for (int c = 0; c < NB; ++c) wb.L[band_off(i, c)] = Le[c]; }
-        else for (int c = 0; c < NB; ++c) wb.L[band_off(i, c)] += wb.T[band_off(i, c)] * Le[c];
+        else for (int c = 0; c < NB; ++c) wb.L[band_off(i, c)] += wb.T[bounce & 1][band_off(i, c)] * Le[c];
     }
 }
 
@@ -122,8 +122,11 @@ __device__ __forceinline__ float2 dir_coef(int mtype, bool on, const DirTerms &t
 // with a run-time job count the path integrator's kernels kept the vertex set-up live across a loop of one and lost 10 %).
 // MEAS: the scene has a measured BRDF (DevScene::has_measured) - its kd-tree look-up (512 bytes of per-thread stacks and
 // sums) stays out of the kernels of the textured / substrate scenes, which lost 4-6 % to it.
+#ifndef SPT_SHADE_MINBLOCKS
+#define SPT_SHADE_MINBLOCKS 4          // A/B builds: profiles/tools/build_variants.py
+#endif
 template <bool SPEC, bool EXT, bool DIRECT = false, bool MEAS = false>
-__global__ void __launch_bounds__(128, 4) k_shade(DevScene sc, RenderCfg cfg, SampleSource src, WaveBuffers wb, int bounce,
+__global__ void __launch_bounds__(128, SPT_SHADE_MINBLOCKS) k_shade(DevScene sc, RenderCfg cfg, SampleSource src, WaveBuffers wb, int bounce,
                                                const uint32_t *queue, const uint32_t *count,
                                                uint32_t *shadow_count, uint32_t *mis_count, uint32_t *elided_count, uint32_t *mis_any_count) {
     uint32_t n = *count;
@@ -362,51 +365,198 @@ __device__ __forceinline__ float fr_cond_fast(float cosi, float c2, float eta, f
 // (three basis spectra, coefficients k0..k2)
 struct LightBand { int kind; IllumCoefs k; };
 
-// Two phases per batch of 32 path vertices, one batch per warp:
-//   A  lane = vertex: everything wavelength-independent (which terms survive the shadow / MIS rays,
-//      the folded scalar factors), staged in shared memory as 6 x float4 per vertex;
-//   B  lane = band: for each vertex of the batch the warp reads the staged scalars (broadcast),
-//      the material row, the light spectrum and the path's T and L rows - every access a
-//      coalesced 128-byte line - and updates L += T*Ld, T *= f|cos|/pdf. y(T) is a warp sum, the
-//      Russian-roulette decision and the 1/q scaling are warp-uniform, so T is written once.
-//   C  lane = vertex again: surviving paths write their next ray and join the next path queue.
-static_assert(NB == 32, "k_accumulate and k_film_add map one band to one lane");
+// K6 is two kernels, because the continuation ray of a vertex does not depend on that vertex's shadow / MIS rays:
+//   k_advance   straight after K5: T' = T * f|cos|/pdf of the continuation, Russian roulette, the next ray, the next
+//               path queue (path.cpp:88-104). T is double-buffered by bounce parity: T[b & 1] is the throughput ARRIVING at
+//               the vertex of bounce b, so the old value survives until the light terms are added.
+//   k_addlight  after the trace launch that carried this bounce's shadow / MIS rays (the same launch that traced the NEXT
+//               bounce's path rays): L += T * (Le + Ld * nLights) (path.cpp:55-56, integrator.cpp:122-163).
+// The dependent chain of a bounce is therefore trace -> compact -> K5 -> k_advance -> trace, with ONE persistent trace
+// launch per bounce (a persistent kernel ends in the drain of its longest rays: at 1/8 of a frame per GPU those drains,
+// three or four per bounce before, were the scaling loss).
+//
+// Both kernels: a warp takes 32 vertices. Phase A, lane = vertex: everything wavelength-independent, staged in shared
+// memory. Phase B, lane = (vertex of a group of four, four bands): 8 lanes x float4 cover a vertex's 128-byte row, so one
+// LDG.128 / STG.128 per lane moves four rows per warp instruction (the one-float-per-lane form was issue-bound at 0.49 of
+// the HBM rate); y(T) is a sum over the 8 lanes of a vertex. Phase C (k_advance), lane = vertex: next ray + queue push.
+static_assert(NB == 32, "k_advance / k_addlight / k_film_add assume 128-byte rows");
 #define ACC_WARPS 4
-#define ACC_GROUP 4          // vertices whose T/L rows are in flight together in phase B
-// EXT (DevScene::has_ext): two more staged float4 per vertex - the substrate's third coefficients and the
-// reflectance coefficients of an image-mapped Kd - and the FresnelBlend form of f[c].
+struct F4 { float v[4]; };
+__device__ __forceinline__ F4 ld4(const float *row, int bg) { float4 q = __ldg((const float4 *)row + bg); F4 r; r.v[0] = q.x; r.v[1] = q.y; r.v[2] = q.z; r.v[3] = q.w; return r; }
+__device__ __forceinline__ F4 ld4g(const float *row, int bg) { float4 q = *((const float4 *)row + bg); F4 r; r.v[0] = q.x; r.v[1] = q.y; r.v[2] = q.z; r.v[3] = q.w; return r; }
+__device__ __forceinline__ void st4(float *row, int bg, const F4 &r) { *((float4 *)row + bg) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]); }
+__device__ __forceinline__ F4 splat4(float x) { F4 r; r.v[0] = r.v[1] = r.v[2] = r.v[3] = x; return r; }
+// Kd from an image map: FromRGB(rgb, SPECTRUM_REFLECTANCE), four bands
+__device__ __forceinline__ F4 refl4(const SptSpectralTables &tb, const float4 &e4, uint32_t bits, int bg) {
+    IllumCoefs kk; kk.k0 = e4.x; kk.k1 = e4.y; kk.k2 = e4.z; kk.b1 = bits & 15; kk.b2 = (bits >> 4) & 15;
+    F4 r;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) r.v[c] = refl_band(tb, kk, 4 * bg + c);
+    return r;
+}
+__device__ __forceinline__ F4 illum4(const SptSpectralTables &tb, const float4 &l4, int bg) {
+    const uint32_t kb = __float_as_uint(l4.w);
+    IllumCoefs kk; kk.k0 = l4.x; kk.k1 = l4.y; kk.k2 = l4.z; kk.b1 = (kb >> 4) & 15; kk.b2 = (kb >> 8) & 15;
+    F4 r;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) r.v[c] = illum_band(tb, kk, 4 * bg + c);
+    return r;
+}
+// f of one direction, four bands, from its two folded coefficients {a, b} (see WaveBuffers::rec0) and the material rows.
+// kind: 0 matte / plastic (f = spec0 a + spec1 b), 1 metal (f = a FrCond(b, eta, k)), 2 substrate (FresnelBlend with the
+// Schlick weight c3: Kd (1 - Ks) a + (Ks + (1 - Ks) c3) b)
+__device__ __forceinline__ F4 fold_f(int kind, const F4 &s0, const F4 &s1, float a, float b, float c3) {
+    F4 r;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        if (kind == 1) r.v[c] = a != 0.f ? a * fr_cond_fast(b, b * b, s0.v[c], s1.v[c]) : 0.f;
+        else if (kind == 2) { const float oms = 1.f - s1.v[c]; r.v[c] = s0.v[c] * oms * a + (s1.v[c] + oms * c3) * b; }
+        else r.v[c] = fmaf(s0.v[c], a, s1.v[c] * b);
+    }
+    return r;
+}
+
+// EXT (DevScene::has_ext): the substrate's third coefficients, the reflectance coefficients of an image-mapped Kd and the
+// measured-BRDF rows.
 template <bool EXT>
-__global__ void __launch_bounds__(32 * ACC_WARPS, 8) k_accumulate(DevScene sc, RenderCfg cfg, WaveBuffers wb, int bounce,
-                                                               const uint32_t *__restrict__ queue, const uint32_t *__restrict__ count,
-                                                               uint32_t *__restrict__ next_queue, uint32_t *__restrict__ next_count) {
-    constexpr int STAGE = EXT ? 8 : 6;
+__global__ void __launch_bounds__(32 * ACC_WARPS, 8) k_advance(DevScene sc, RenderCfg cfg, WaveBuffers wb, int bounce,
+                                                            const uint32_t *__restrict__ queue, const uint32_t *__restrict__ count,
+                                                            uint32_t *__restrict__ next_queue, uint32_t *__restrict__ next_count) {
+    constexpr int STAGE = EXT ? 3 : 2;
     __shared__ float4 stage_all[ACC_WARPS][32][STAGE];
     const uint32_t n = *count;
     const SptSpectralTables &tb = *sc.tables;
-    float *__restrict__ Tg = wb.T;
-    float *__restrict__ Lg = wb.L;
+    const float *__restrict__ Tin = wb.T[bounce & 1];
+    float *__restrict__ Tout = wb.T[(bounce + 1) & 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grp = lane >> 3, bg = lane & 7;
     float4 (*stage)[STAGE] = stage_all[warp];
     const unsigned FULL = 0xffffffffu;
-    const float cieY = tb.cie_y[lane];
-    const float nL = (float)sc.n_lights;
-    const float light0 = sc.n_lights ? sc.lights[0].spectrum[lane] : 0.f;    // most scenes: the one light's row, read once
+    const F4 cieY = ld4(tb.cie_y, bg);
+    const float yint = tb.yint;
     const uint32_t nwarps = gridDim.x * ACC_WARPS;
     for (uint32_t base = (blockIdx.x * ACC_WARPS + warp) * 32u; base < n; base += nwarps * 32u) {
-        // ---- phase A
+        // ---- phase A: lane = vertex
         const uint32_t q = base + lane;
         const bool active = q < n;
         const uint32_t i = active ? queue[q] : 0;
-        float4 g0 = make_float4(0, 0, 0, 0);
         bool specBounce = false;
         if (active) {
+            const float4 c1 = wb.rec1[i], c2 = wb.rec2[i];
+            const uint32_t bits0 = __float_as_uint(c2.z), bits1 = __float_as_uint(c2.w);
+            const uint32_t flags = bits0 & 0xfffu;
+            const bool haveP = (flags & RF_P) != 0;
+            specBounce = (flags & RF_P_SPEC) != 0;
+            uint32_t kind = (flags & RF_METAL) ? 1u : 0u;
+            float c3 = 0.f;
+            float4 e4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            uint32_t ebits = 0;
+            if (EXT) {
+                if (flags & RF_SUBSTRATE) { kind = 2u; c3 = wb.rec3[i].z; }
+                if (flags & RF_MEASURED) kind = 3u;
+                if (flags & RF_TEXKD) {
+                    const float4 r4 = wb.rec4[i];
+                    const float rgb[3] = { r4.x, r4.y, r4.z };
+                    const IllumCoefs kk = illum_coefs(rgb);           // same basis choice for the reflectance tables
+                    e4 = make_float4(kk.k0, kk.k1, kk.k2, 0.f);
+                    ebits = 1u | (uint32_t)kk.b1 << 4 | (uint32_t)kk.b2 << 8;
+                }
+            }
+            stage[lane][0] = make_float4(c1.x, c1.y, haveP ? c2.x : 0.f, c2.y);           // {a, b, sP, Russian-roulette draw}
+            stage[lane][1] = make_float4(__uint_as_float(i), __uint_as_float((haveP ? 1u : 0u) | kind << 1 | ebits << 4),
+                                         __uint_as_float(bits1 & 0xffffu), c3);
+            if (EXT) stage[lane][2] = e4;
+        }
+        __syncwarp();
+        // ---- phase B: lane = (vertex grp of a group of four, bands 4 bg .. 4 bg + 3)
+        const uint32_t cnt = min(32u, n - base);
+        uint32_t aliveMask = 0;
+        for (uint32_t v0 = 0; v0 < cnt; v0 += 4u) {
+            const uint32_t v = v0 + (uint32_t)grp;
+            const bool valid = v < cnt;
+            const uint32_t vv = valid ? v : cnt - 1u;
+            const float4 cP = stage[vv][0], m4 = stage[vv][1];
+            const uint32_t vi = __float_as_uint(m4.x), misc = __float_as_uint(m4.y);
+            const bool haveP = valid && (misc & 1u);
+            const uint32_t kind = (misc >> 1) & 7u;
+            F4 Tn = splat4(0.f), fP = splat4(0.f);
+            if (haveP) {
+                const F4 Tv = bounce == 0 ? splat4(1.f) : ld4g(Tin + (size_t)vi * NB, bg);
+                if (EXT && kind == 3u) {
+                    // measured BRDF: the value is a row K5 wrote (coefficient 1 = the direction has a value)
+                    if (cP.x != 0.f) fP = ld4g(wb.frow + ((size_t)vi * 3 + 2) * NB, bg);
+                } else {
+                    const SptMaterial &m = sc.materials[__float_as_uint(m4.z)];
+                    F4 s0 = ld4(m.spec0, bg);
+                    const F4 s1 = ld4(m.spec1, bg);
+                    if (EXT && ((misc >> 4) & 1u)) s0 = refl4(tb, stage[vv][2], misc >> 8, bg);
+                    fP = fold_f((int)kind, s0, s1, cP.x, cP.y, m4.w);
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) Tn.v[c] = Tv.v[c] * (fP.v[c] * cP.z);
+            }
+            // path.cpp:88-104: the path ends on a black BSDF value; Russian roulette from the fourth bounce on
+            const unsigned nz = __ballot_sync(FULL, fP.v[0] != 0.f || fP.v[1] != 0.f || fP.v[2] != 0.f || fP.v[3] != 0.f);
+            bool alive = haveP && ((nz >> (grp * 8)) & 0xffu) != 0u;
+            if (bounce > 3) {
+                float yy = cieY.v[0] * Tn.v[0] + cieY.v[1] * Tn.v[1] + cieY.v[2] * Tn.v[2] + cieY.v[3] * Tn.v[3];
+                yy += __shfl_xor_sync(FULL, yy, 4);
+                yy += __shfl_xor_sync(FULL, yy, 2);
+                yy += __shfl_xor_sync(FULL, yy, 1);
+                const float continueProbability = stdminf(.5f, yy / yint);
+                if (cP.w > continueProbability) alive = false;
+                else {
+                    const float inv = 1.f / continueProbability;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) Tn.v[c] *= inv;
+                }
+            }
+            if (alive) st4(Tout + (size_t)vi * NB, bg, Tn);
+            // the four vertices of this pass: their verdicts sit at lanes 0, 8, 16, 24 of the ballot -> bits v0 .. v0 + 3
+            const unsigned b4 = __ballot_sync(FULL, alive && bg == 0);
+            aliveMask |= ((b4 & 1u) | ((b4 >> 7) & 2u) | ((b4 >> 14) & 4u) | ((b4 >> 21) & 8u)) << v0;
+        }
+        // ---- phase C: lane = vertex
+        const bool alive = active && ((aliveMask >> lane) & 1u);
+        if (alive) {
+            const float4 g3 = wb.g3[i], g0 = wb.g0[i];
+            wb.ray_o[i] = g0;
+            wb.ray_d[i] = make_float4(g3.x, g3.y, g3.z, SPT_INF);
+            if (sc.has_specular) wb.pflags[i] = specBounce ? 1u : 0u;
+        }
+        queue_push(next_queue, next_count, alive, i);
+        __syncwarp();
+    }
+}
+
+template <bool EXT>
+__global__ void __launch_bounds__(32 * ACC_WARPS, 8) k_addlight(DevScene sc, RenderCfg cfg, WaveBuffers wb, int bounce,
+                                                             const uint32_t *__restrict__ queue, const uint32_t *__restrict__ count) {
+    constexpr int STAGE = EXT ? 7 : 5;
+    __shared__ float4 stage_all[ACC_WARPS][32][STAGE];
+    const uint32_t n = *count;
+    const SptSpectralTables &tb = *sc.tables;
+    const float *__restrict__ Tin = wb.T[bounce & 1];        // the throughput that ARRIVED at this bounce's vertices
+    float *__restrict__ Lg = wb.L;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grp = lane >> 3, bg = lane & 7;
+    float4 (*stage)[STAGE] = stage_all[warp];
+    const float nL = (float)sc.n_lights;
+    const F4 light0 = sc.n_lights ? ld4(sc.lights[0].spectrum, bg) : splat4(0.f);    // most scenes: the one light's row, read once
+    const uint32_t nwarps = gridDim.x * ACC_WARPS;
+    for (uint32_t base = (blockIdx.x * ACC_WARPS + warp) * 32u; base < n; base += nwarps * 32u) {
+        // ---- phase A: lane = vertex - which terms survived the shadow / MIS rays
+        const uint32_t q = base + lane;
+        const bool active = q < n;
+        if (active) {
+            const uint32_t i = queue[q];
             const float4 c0 = wb.rec0[i], c1 = wb.rec1[i], c2 = wb.rec2[i];
             const uint32_t bits0 = __float_as_uint(c2.z), bits1 = __float_as_uint(c2.w);
             const uint32_t flags = bits0 & 0xfffu;
             const int lightIdx = (int)(bits0 >> 12);
             const bool metal = (flags & RF_METAL) != 0;
             const float2 none = make_float2(0.f, metal ? 1.f : 0.f);
-            float2 cL = none, cB = none, cP = make_float2(c1.x, c1.y);
+            float2 cL = none, cB = none;
             LightBand lbL, lbB; lbL.kind = 0; lbB.kind = 0;
             lbL.k.k0 = lbL.k.k1 = lbL.k.k2 = 0.f; lbL.k.b1 = lbL.k.b2 = 0; lbB.k = lbL.k;
             float sL = 0.f, sB = 0.f;
@@ -422,8 +572,7 @@ __global__ void __launch_bounds__(32 * ACC_WARPS, 8) k_accumulate(DevScene sc, R
             }
             // --- BSDF-sample term (integrator.cpp:139-163): radiance from what the MIS ray found
             if (flags & RF_B) {
-                g0 = wb.g0[i];
-                float4 g2 = wb.g2[i];
+                const float4 g0 = wb.g0[i], g2 = wb.g2[i];
                 uint32_t ms = wb.mis_slot[i];
                 const SptLight &l = sc.lights[lightIdx];
                 v3 wi = V(g2.x, g2.y, g2.z);
@@ -441,147 +590,100 @@ __global__ void __launch_bounds__(32 * ACC_WARPS, 8) k_accumulate(DevScene sc, R
                 }
                 if (lbB.kind) { cB = make_float2(c0.z, c0.w); sB = c1.w; }
             }
-            const bool haveP = (flags & RF_P) != 0;
-            specBounce = (flags & RF_P_SPEC) != 0;
-            // UniformSampleOneLight scales by the light count (integrator.cpp:105)
-            sL *= nL; sB *= nL;
-            stage[lane][0] = make_float4(cL.x, cL.y, cB.x, cB.y);
-            stage[lane][1] = make_float4(cP.x, cP.y, sL, sB);
-            stage[lane][2] = make_float4(haveP ? c2.x : 0.f, c2.y, __uint_as_float(i),
-                                         __uint_as_float((haveP ? 1u : 0u) | (metal ? 2u : 0u) | (lbL.kind == 2 ? 4u : 0u) |
-                                                         (lbB.kind == 2 ? 8u : 0u) | (uint32_t)lightIdx << 4));
-            stage[lane][3] = make_float4(lbL.k.k0, lbL.k.k1, lbL.k.k2, __uint_as_float((uint32_t)lbL.kind | (uint32_t)lbL.k.b1 << 4 | (uint32_t)lbL.k.b2 << 8));
-            stage[lane][4] = make_float4(lbB.k.k0, lbB.k.k1, lbB.k.k2, __uint_as_float((uint32_t)lbB.kind | (uint32_t)lbB.k.b1 << 4 | (uint32_t)lbB.k.b2 << 8));
-            stage[lane][5] = make_float4(__uint_as_float(bits1 & 0xffffu), __uint_as_float(bits1 >> 16), 0.f, 0.f);
+            const uint32_t emit = bits1 >> 16;
+            // rows are first written at bounce 0 (every vertex); afterwards only vertices that add something touch theirs
+            const bool need = bounce == 0 || emit != 0u || lbL.kind != 0 || lbB.kind != 0;
+            uint32_t kind = metal ? 1u : 0u;
+            float4 e3 = make_float4(0.f, 0.f, 0.f, 0.f), e4 = e3;
+            uint32_t ebits = 0;
             if (EXT) {
-                float4 e3 = make_float4(0.f, 0.f, 0.f, 0.f), e4 = e3;
-                uint32_t ebits = 0;
-                if (flags & RF_SUBSTRATE) { e3 = wb.rec3[i]; ebits |= 1u; }
-                if (flags & RF_MEASURED) ebits |= 4u;
+                if (flags & RF_SUBSTRATE) { kind = 2u; e3 = wb.rec3[i]; }
+                if (flags & RF_MEASURED) kind = 3u;
                 if (flags & RF_TEXKD) {
                     const float4 r4 = wb.rec4[i];
                     const float rgb[3] = { r4.x, r4.y, r4.z };
-                    const IllumCoefs kk = illum_coefs(rgb);           // same basis choice for the reflectance tables
+                    const IllumCoefs kk = illum_coefs(rgb);
                     e4 = make_float4(kk.k0, kk.k1, kk.k2, 0.f);
-                    ebits |= 2u | (uint32_t)kk.b1 << 4 | (uint32_t)kk.b2 << 8;
+                    ebits = 1u | (uint32_t)kk.b1 << 4 | (uint32_t)kk.b2 << 8;
                 }
-                e3.w = __uint_as_float(ebits);
-                stage[lane][6] = e3; stage[lane][7] = e4;
             }
+            // UniformSampleOneLight scales by the light count (integrator.cpp:105)
+            stage[lane][0] = make_float4(cL.x, cL.y, cB.x, cB.y);
+            stage[lane][1] = make_float4(sL * nL, sB * nL, __uint_as_float(i),
+                                         __uint_as_float((need ? 1u : 0u) | kind << 1 | (lbL.kind == 2 ? 16u : 0u) | (lbB.kind == 2 ? 32u : 0u) |
+                                                         (uint32_t)lightIdx << 8));
+            stage[lane][2] = make_float4(lbL.k.k0, lbL.k.k1, lbL.k.k2, __uint_as_float((uint32_t)lbL.kind | (uint32_t)lbL.k.b1 << 4 | (uint32_t)lbL.k.b2 << 8));
+            stage[lane][3] = make_float4(lbB.k.k0, lbB.k.k1, lbB.k.k2, __uint_as_float((uint32_t)lbB.kind | (uint32_t)lbB.k.b1 << 4 | (uint32_t)lbB.k.b2 << 8));
+            stage[lane][4] = make_float4(__uint_as_float(bits1 & 0xffffu), __uint_as_float(emit), __uint_as_float(ebits), 0.f);
+            if (EXT) { stage[lane][5] = e3; stage[lane][6] = e4; }
         }
         __syncwarp();
-        // ---- phase B
+        // ---- phase B: lane = (vertex grp of a group of four, bands 4 bg .. 4 bg + 3)
         const uint32_t cnt = min(32u, n - base);
-        uint32_t aliveMask = 0;
-        for (uint32_t v0 = 0; v0 < cnt; v0 += ACC_GROUP) {
-            float Tv[ACC_GROUP], Lv[ACC_GROUP];
-            uint32_t iv[ACC_GROUP];
+        for (uint32_t v0 = 0; v0 < cnt; v0 += 4u) {
+            const uint32_t v = v0 + (uint32_t)grp;
+            if (v >= cnt) continue;
+            const float4 cLB = stage[v][0], m4 = stage[v][1];
+            const uint32_t misc = __float_as_uint(m4.w);
+            if (!(misc & 1u)) continue;
+            const uint32_t vi = __float_as_uint(m4.z);
+            const uint32_t kind = (misc >> 1) & 7u, lightIdx = misc >> 8;
+            const float4 x4 = stage[v][4];
+            const uint32_t emit = __float_as_uint(x4.y);
+            float *Lrow = Lg + (size_t)vi * NB;
+            F4 Tv, Lv;
+            if (bounce == 0) {
+                // the path starts here: T = 1, L = what the first vertex emits towards the camera (path.cpp:55-56)
+                Tv = splat4(1.f);
+                Lv = emit == 0 ? splat4(0.f) : (emit == 1 ? light0 : ld4(sc.lights[emit - 1].spectrum, bg));
+            } else {
+                Tv = ld4g(Tin + (size_t)vi * NB, bg);
+                Lv = ld4g(Lrow, bg);
+                // a vertex reached through a specular bounce adds what it emits (path.cpp:55-56)
+                if (emit) {
+                    const F4 Le = emit == 1 ? light0 : ld4(sc.lights[emit - 1].spectrum, bg);
 #pragma unroll
-            for (int k = 0; k < ACC_GROUP; ++k) {
-                uint32_t v = min(v0 + k, cnt - 1);                       // clamped: tail entries repeat the last vertex (not stored)
-                iv[k] = __float_as_uint(stage[v][2].z);
-                size_t off = band_off(iv[k], lane);
-                if (bounce == 0) {
-                    // the path starts here: T = 1, L = what the first vertex emits towards the camera (path.cpp:55-56)
-                    uint32_t emit = __float_as_uint(stage[v][5].y);
-                    Tv[k] = 1.f;
-                    Lv[k] = emit == 0 ? 0.f : (emit == 1 ? light0 : __ldg(sc.lights[emit - 1].spectrum + lane));
-                } else {
-                    Tv[k] = Tg[off]; Lv[k] = Lg[off];
-                    // a vertex reached through a specular bounce adds what it emits (path.cpp:55-56)
-                    uint32_t emit = __float_as_uint(stage[v][5].y);
-                    if (emit) Lv[k] = Lv[k] + Tv[k] * (emit == 1 ? light0 : __ldg(sc.lights[emit - 1].spectrum + lane));
+                    for (int c = 0; c < 4; ++c) Lv.v[c] = Lv.v[c] + Tv.v[c] * Le.v[c];
                 }
             }
-#pragma unroll
-            for (int k = 0; k < ACC_GROUP; ++k) {
-                const uint32_t v = v0 + k;
-                if (v >= cnt) break;
-                const float4 cLB = stage[v][0], cPs = stage[v][1], m4 = stage[v][2];
-                const uint32_t misc = __float_as_uint(m4.w);
-                const uint32_t lightIdx = misc >> 4;
-                const SptMaterial &m = sc.materials[__float_as_uint(stage[v][5].x)];
-                const bool haveP = misc & 1u, metal = (misc & 2u) != 0;
-                float s0 = __ldg(m.spec0 + lane);
-                const float s1 = __ldg(m.spec1 + lane);
-                float fL, fB, fP;
-                uint32_t ebits = 0;
-                float4 e3 = make_float4(0.f, 0.f, 0.f, 0.f);
+            F4 fL = splat4(0.f), fB = splat4(0.f);
+            if (EXT && kind == 3u) {
+                // measured BRDF: the values are rows K5 wrote (coefficient 1 = the direction has a value)
+                if (cLB.x != 0.f) fL = ld4g(wb.frow + ((size_t)vi * 3 + 0) * NB, bg);
+                if (cLB.z != 0.f) fB = ld4g(wb.frow + ((size_t)vi * 3 + 1) * NB, bg);
+            } else {
+                const SptMaterial &m = sc.materials[__float_as_uint(x4.x)];
+                F4 s0 = ld4(m.spec0, bg);
+                const F4 s1 = ld4(m.spec1, bg);
+                float c3L = 0.f, c3B = 0.f;
                 if (EXT) {
-                    e3 = stage[v][6];
-                    ebits = __float_as_uint(e3.w);
-                    if (ebits & 2u) {                                // Kd from the image map: FromRGB(rgb, SPECTRUM_REFLECTANCE)
-                        const float4 e4 = stage[v][7];
-                        IllumCoefs kk; kk.k0 = e4.x; kk.k1 = e4.y; kk.k2 = e4.z; kk.b1 = (ebits >> 4) & 15; kk.b2 = (ebits >> 8) & 15;
-                        s0 = refl_band(tb, kk, lane);
-                    }
+                    const uint32_t ebits = __float_as_uint(x4.z);
+                    if (ebits & 1u) s0 = refl4(tb, stage[v][6], ebits >> 4, bg);
+                    const float4 e3 = stage[v][5];
+                    c3L = e3.x; c3B = e3.y;
                 }
-                if (EXT && (ebits & 4u)) {
-                    // measured BRDF: the three values are rows K5 wrote (coefficient 1 = the direction has a value)
-                    const float *fr = wb.frow + (size_t)iv[k] * 3 * NB + lane;
-                    fL = cLB.x != 0.f ? fr[0] : 0.f;
-                    fB = cLB.z != 0.f ? fr[NB] : 0.f;
-                    fP = cPs.x != 0.f ? fr[2 * NB] : 0.f;
-                } else if (EXT && (ebits & 1u)) {
-                    // FresnelBlend (reflection.cpp:224-236): Kd (1 - Ks) x diffuse scalar + (Ks + (1 - Ks) (1 - wi.wh)^5) x D-term
-                    const float oms = 1.f - s1, dR = s0 * oms;
-                    fL = dR * cLB.x + (s1 + oms * e3.x) * cLB.y;
-                    fB = dR * cLB.z + (s1 + oms * e3.y) * cLB.w;
-                    fP = dR * cPs.x + (s1 + oms * e3.z) * cPs.y;
-                } else if (metal) {
-                    fL = cLB.x != 0.f ? cLB.x * fr_cond_fast(cLB.y, cLB.y * cLB.y, s0, s1) : 0.f;
-                    fB = cLB.z != 0.f ? cLB.z * fr_cond_fast(cLB.w, cLB.w * cLB.w, s0, s1) : 0.f;
-                    fP = cPs.x != 0.f ? cPs.x * fr_cond_fast(cPs.y, cPs.y * cPs.y, s0, s1) : 0.f;
-                } else {
-                    fL = fmaf(s0, cLB.x, s1 * cLB.y);
-                    fB = fmaf(s0, cLB.z, s1 * cLB.w);
-                    fP = fmaf(s0, cPs.x, s1 * cPs.y);
-                }
-                // radiance arriving along the light / MIS direction: the light's table row, or (misc bits 2,3:
-                // infinite light) an RGB illuminant rebuilt from the staged coefficients
-                float LcL = 0.f, LcB = 0.f;
-                if (misc & 12u) {
-                    const float4 lL4 = stage[v][3], lB4 = stage[v][4];
-                    const uint32_t kL = __float_as_uint(lL4.w), kB = __float_as_uint(lB4.w);
-                    if ((kL & 15u) == 2u) { IllumCoefs kk; kk.k0 = lL4.x; kk.k1 = lL4.y; kk.k2 = lL4.z; kk.b1 = (kL >> 4) & 15; kk.b2 = (kL >> 8) & 15; LcL = illum_band(tb, kk, lane); }
-                    if ((kB & 15u) == 2u) { IllumCoefs kk; kk.k0 = lB4.x; kk.k1 = lB4.y; kk.k2 = lB4.z; kk.b1 = (kB >> 4) & 15; kk.b2 = (kB >> 8) & 15; LcB = illum_band(tb, kk, lane); }
-                } else {
-                    // a direction without a light term has zero coefficients / scale, so the row can be applied unconditionally
-                    LcL = LcB = lightIdx == 0 ? light0 : __ldg(sc.lights[lightIdx].spectrum + lane);
-                }
-                // L += T * Ld * nLights ; T *= f |cos| / pdf   (integrator.cpp:122-163, path.cpp:88-90)
-                const float Ld = fL * LcL * cPs.z + fB * LcB * cPs.w;
-                const size_t off = band_off(iv[k], lane);
-                Lg[off] = fmaf(Tv[k], Ld, Lv[k]);
-                float Tn = Tv[k] * (fP * m4.x);
-                const bool fBlack = !__any_sync(FULL, fP != 0.f);
-                // path.cpp:88-104
-                bool alive = false;
-                if (haveP && !fBlack) {
-                    alive = true;
-                    if (bounce > 3) {
-                        float yy = cieY * Tn;
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) yy += __shfl_xor_sync(FULL, yy, o);
-                        float continueProbability = stdminf(.5f, yy / tb.yint);
-                        if (m4.y > continueProbability) alive = false;
-                        else if (bounce != cfg.max_depth) Tn *= 1.f / continueProbability;
-                    }
-                    if (bounce == cfg.max_depth) alive = false;
-                }
-                if (alive) { Tg[off] = Tn; aliveMask |= 1u << v; }
+                fL = fold_f((int)kind, s0, s1, cLB.x, cLB.y, c3L);
+                fB = fold_f((int)kind, s0, s1, cLB.z, cLB.w, c3B);
             }
+            // radiance arriving along the light / MIS direction: the light's table row, or (infinite light) an RGB
+            // illuminant rebuilt from the staged coefficients
+            F4 LcL, LcB;
+            if (misc & 48u) {
+                LcL = (misc & 16u) ? illum4(tb, stage[v][2], bg) : splat4(0.f);
+                LcB = (misc & 32u) ? illum4(tb, stage[v][3], bg) : splat4(0.f);
+            } else {
+                // a direction without a light term has zero coefficients / scale, so the row can be applied unconditionally
+                LcL = LcB = lightIdx == 0 ? light0 : ld4(sc.lights[lightIdx].spectrum, bg);
+            }
+            // L += T * Ld * nLights (integrator.cpp:122-163, path.cpp:69-72)
+            F4 Lo;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float Ld = fL.v[c] * LcL.v[c] * m4.x + fB.v[c] * LcB.v[c] * m4.y;
+                Lo.v[c] = fmaf(Tv.v[c], Ld, Lv.v[c]);
+            }
+            st4(Lrow, bg, Lo);
         }
-        // ---- phase C
-        bool alive = active && ((aliveMask >> lane) & 1u);
-        if (alive) {
-            float4 g3 = wb.g3[i];
-            g0 = wb.g0[i];
-            wb.ray_o[i] = g0;
-            wb.ray_d[i] = make_float4(g3.x, g3.y, g3.z, SPT_INF);
-            if (sc.has_specular) wb.pflags[i] = specBounce ? 1u : 0u;
-        }
-        queue_push(next_queue, next_count, alive, i);
         __syncwarp();
     }
 }
@@ -879,11 +981,16 @@ void spt_launch_shade(int grid, cudaStream_t st, const DevScene &sc, const Rende
 #undef SPT_SHADE
 #undef SPT_SHADE4
 }
-void spt_launch_accumulate(int grid, cudaStream_t st, const DevScene &sc, const RenderCfg &cfg, const WaveBuffers &wb, int bounce,
-                           const uint32_t *queue, const uint32_t *count, uint32_t *next_queue, uint32_t *next_count) {
+void spt_launch_advance(int grid, cudaStream_t st, const DevScene &sc, const RenderCfg &cfg, const WaveBuffers &wb, int bounce,
+                        const uint32_t *queue, const uint32_t *count, uint32_t *next_queue, uint32_t *next_count) {
+    if (sc.has_ext) k_advance<true><<<grid, 128, 0, st>>>(sc, cfg, wb, bounce, queue, count, next_queue, next_count);
+    else k_advance<false><<<grid, 128, 0, st>>>(sc, cfg, wb, bounce, queue, count, next_queue, next_count);
+}
+void spt_launch_addlight(int grid, cudaStream_t st, const DevScene &sc, const RenderCfg &cfg, const WaveBuffers &wb, int bounce,
+                         const uint32_t *queue, const uint32_t *count) {
     if (cfg.integrator == SPT_INTEGRATOR_DIRECT_ALL) k_accumulate_direct<<<grid, 128, 0, st>>>(sc, cfg, wb, queue, count);
-    else if (sc.has_ext) k_accumulate<true><<<grid, 128, 0, st>>>(sc, cfg, wb, bounce, queue, count, next_queue, next_count);
-    else k_accumulate<false><<<grid, 128, 0, st>>>(sc, cfg, wb, bounce, queue, count, next_queue, next_count);
+    else if (sc.has_ext) k_addlight<true><<<grid, 128, 0, st>>>(sc, cfg, wb, bounce, queue, count);
+    else k_addlight<false><<<grid, 128, 0, st>>>(sc, cfg, wb, bounce, queue, count);
 }
 void spt_launch_film_add(int grid, cudaStream_t st, const FilmView &film, const SptSpectralTables *tables, const float2 *img_xy,
                          const float *L, uint32_t cap, uint32_t n_samples, int spp) {

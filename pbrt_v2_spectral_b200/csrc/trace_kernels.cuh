@@ -168,97 +168,166 @@ __device__ __forceinline__ bool slab6_finite(float x0, float x1, float y0, float
     return (tmin <= tmax) && (tmin < ray.maxt) && (tmax > ray.mint);
 }
 
-// ---- variant 1: pair nodes ------------------------------------------------------------------------
-// One 64-byte record per INTERIOR node holds the bounds of both children (built in
-// spt_scene_create): one step fetches four 16-byte words, slab-tests both children and descends.
-// A child is one 32-bit code: a pair index, or PN_LEAF | hasQuadric << 30 | (nPrims-1) << 27 | first slot.
+// ---- variant 1: pair nodes, several ray queues per launch ------------------------------------------------------------
+// One 64-byte record per INTERIOR node holds the bounds of both children (built in spt_scene_create): one step fetches
+// four 16-byte words, slab-tests both children and descends. A child is one 32-bit code: a pair index, or
+// PN_LEAF | hasQuadric << 30 | (nPrims-1) << 27 | first slot.
 //
-// Closest hit: the reference pushes the far child unconditionally and slab-tests it when popped,
-// against the maxt current THEN; of that test only `tmin < maxt` depends on maxt, so the far child
-// is tested at push time, dropped if it already fails, and its tmin is kept on the stack and
-// re-compared with the (possibly shrunk) maxt at pop time - the same decision, bit for bit.
-// Any hit: maxt never changes during IntersectP, the answer is the OR over the same set of leaves
-// whatever their order, so the stack holds bare codes.
+// Closest hit: the reference pushes the far child unconditionally and slab-tests it when popped, against the maxt current
+// THEN; of that test only `tmin < maxt` depends on maxt, so the far child is tested at push time, dropped if it already
+// fails, and its tmin is kept on the stack and re-compared with the (possibly shrunk) maxt at pop time - the same decision,
+// bit for bit. Any hit: maxt never changes during IntersectP, so the pop-time comparison always holds and the answer is the
+// OR over the same set of leaves whatever their order. Whether a lane's ray is a closest-hit or an any-hit query is a
+// run-time property of the QUEUE it came from: one launch drains up to four queues (a bounce's path rays together with the
+// previous bounce's shadow and MIS rays), so a wavefront bounce pays for ONE persistent kernel's drain instead of three or four.
+//
 #define PN_LEAF 0x80000000u
-template <bool ANY, bool COUNT>
-__global__ void __launch_bounds__(128) k_trace_v1(DevScene sc, TraceArgs a) {
-    const uint32_t n = *a.count;
+template <typename T> __device__ __forceinline__ T seg_sel(uint32_t k, T a, T b, T c, T d) { return k == 0 ? a : (k == 1 ? b : (k == 2 ? c : d)); }
+
+// Warp organisation: one loop - every iteration a lane pops if it must, takes one pair step if it holds an interior node,
+// then tests the leaf it may have reached; idle lanes wait for the refill. Two alternatives were built and measured on the
+// B200 (profiles/r02_trace_modes.log, whole killeroo frame): while-while (every lane walks to its next leaf, the warp
+// reconverges, leaves are tested together) 43.8 ms against 40.9 ms, batched leaves (a leaf phase once 4-16 lanes hold a leaf)
+// 41.8-45.1 ms; keeping the first 8 or 16 stack entries of a lane in shared memory ([entry][thread], conflict-free) instead
+// of local memory: 45.7 against 44.3 ms. The L1-served local stack and the plain loop won, so they are what is left.
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_trace_multi(DevScene sc, TraceMultiArgs a) {
+    uint2 stk[64];                  // the 64-entry todo stack (bvh.cpp:384): {child code, tmin of its slab test at push time}
+    const uint32_t e0 = *a.seg[0].count;
+    const uint32_t e1 = e0 + (a.nseg > 1 ? *a.seg[1].count : 0u);
+    const uint32_t e2 = e1 + (a.nseg > 2 ? *a.seg[2].count : 0u);
+    const uint32_t total = e2 + (a.nseg > 3 ? *a.seg[3].count : 0u);
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
-    uint2 stk[ANY ? 1 : 64];         // closest: {child code, tmin of the child's slab test at push time}
-    uint32_t stk1[ANY ? 64 : 1];     // any hit: child code
-    uint32_t sp = 0, cur = PN_NONE, negMask = 0;
-    LaneRay L; L.ray.o = V(0, 0, 0); L.ray.d = V(0, 0, 1); L.ray.mint = 0.f; L.ray.maxt = 0.f; L.invDir = V(0, 0, 0);
-    L.negx = L.negy = L.negz = false; L.exact = false; L.i = 0; L.best = SPT_MISS;
-    bool active = false, exhausted = (n == 0);
-    unsigned long long cn = 0, cp = 0;
+    uint32_t sp = 0, cur = PN_NONE, negMask = 0, seg = 0;
+    Ray ray; ray.o = V(0, 0, 0); ray.d = V(0, 0, 1); ray.mint = 0.f; ray.maxt = 0.f;
+    v3 invDir = V(0, 0, 0);
+    bool exact = false, isAny = false;
+    uint32_t ri = 0, best = SPT_MISS;
+    bool active = false, exhausted = (total == 0);
+    unsigned long long cn = 0, cp = 0, cnA = 0, cpA = 0;
+    // pop: the next stack entry whose slab test still holds with the current maxt; true when the stack ran empty
+    auto pop = [&]() -> bool {
+        for (;;) {
+            if (sp == 0) return true;
+            const uint2 e = stk[--sp];
+            // the far child's slab test completes here with the current maxt
+            if (__uint_as_float(e.y) < ray.maxt) { cur = e.x; return false; }
+        }
+    };
+    // one pair step from the interior node `cur`: both children slab-tested, the far one pushed, the near one entered
+    auto node_step = [&]() {
+        const float4 *pn = sc.pnodes + 4 * (size_t)cur;
+        const float4 q0 = __ldg(pn), q1 = __ldg(pn + 1), q2 = __ldg(pn + 2), q3 = __ldg(pn + 3);
+        if (COUNT) { if (isAny) cnA += 2; else cn += 2; }
+        // child 0: min (q0.x,q0.y,q0.z) max (q0.w,q1.x,q1.y); child 1: min (q1.z,q1.w,q2.x) max (q2.y,q2.z,q2.w)
+        float t0, t1;
+        bool h0, h1;
+        if (!exact) {
+            h0 = slab6_finite(q0.x, q0.w, q0.y, q1.x, q0.z, q1.y, ray, invDir, &t0);
+            h1 = slab6_finite(q1.z, q2.y, q1.w, q2.z, q2.x, q2.w, ray, invDir, &t1);
+        } else {
+            const bool negx = negMask & 1u, negy = negMask & 2u, negz = negMask & 4u;
+            h0 = slab6(negx ? q0.w : q0.x, negx ? q0.x : q0.w, negy ? q1.x : q0.y, negy ? q0.y : q1.x,
+                       negz ? q1.y : q0.z, negz ? q0.z : q1.y, ray, invDir, &t0);
+            h1 = slab6(negx ? q2.y : q1.z, negx ? q1.z : q2.y, negy ? q2.z : q1.w, negy ? q1.w : q2.z,
+                       negz ? q2.w : q2.x, negz ? q2.x : q2.w, ray, invDir, &t1);
+        }
+        const uint32_t c0 = __float_as_uint(q3.x), c1 = __float_as_uint(q3.y), axis = __float_as_uint(q3.z);
+        // reference: dirIsNeg[axis] ? second child first : first child first
+        const bool swap = (negMask >> axis) & 1u;
+        const uint32_t nearC = swap ? c1 : c0, farC = swap ? c0 : c1;
+        const bool nearHit = swap ? h1 : h0, farHit = swap ? h0 : h1;
+        if (farHit) stk[sp++] = make_uint2(farC, __float_as_uint(swap ? t0 : t1));
+        cur = nearHit ? nearC : PN_NONE;
+    };
+    // the primitives of the leaf `cur`, in slot order; true when an any-hit ray is finished
+    auto leaf_step = [&]() -> bool {
+        const uint32_t offset = cur & 0x07ffffffu, nPrims = ((cur >> 27) & 7u) + 1u;
+        const bool hasQuadric = (cur >> 30) & 1u;
+        cur = PN_NONE;
+        for (uint32_t k = 0; k < nPrims; ++k) {
+            const uint32_t s = offset + k;
+            if (COUNT) { if (isAny) ++cpA; else ++cp; }
+            float t;
+            bool h;
+            if (!hasQuadric || sc.prim_kind[s] == SPT_PRIM_TRIANGLE) {
+                const float4 va = __ldg(&sc.tri_verts[3 * (size_t)s]);
+                const float4 vb = __ldg(&sc.tri_verts[3 * (size_t)s + 1]);
+                const float4 vc = __ldg(&sc.tri_verts[3 * (size_t)s + 2]);
+                float b1, b2;
+                h = tri_test(V(va.x, va.y, va.z), V(vb.x, vb.y, vb.z), V(vc.x, vc.y, vc.z), ray, &t, &b1, &b2);
+            } else if (sc.prim_kind[s] == SPT_PRIM_SPHERE) {
+                h = sphere_intersect(sc, sc.quadrics[sc.prim_data[s]], 0, ray, &t, nullptr);
+            } else {
+                h = disk_intersect(sc, sc.quadrics[sc.prim_data[s]], 0, ray, &t, nullptr);
+            }
+            if (h) {
+                best = s;
+                if (isAny) return true;                  // IntersectP returns at the first accepted primitive
+                ray.maxt = t;
+            }
+        }
+        return false;
+    };
+    auto finish = [&]() {
+        uint32_t *out_slot = seg_sel(seg, a.seg[0].out_slot, a.seg[1].out_slot, a.seg[2].out_slot, a.seg[3].out_slot);
+        out_slot[ri] = best;
+        if (!isAny) {
+            float *out_t = seg_sel(seg, a.seg[0].out_t, a.seg[1].out_t, a.seg[2].out_t, a.seg[3].out_t);
+            out_t[ri] = ray.maxt;
+        }
+        active = false;
+    };
     for (;;) {
-        if (lane_fetch(a, n, lane, active, exhausted, L)) {
-            sp = 0; cur = PN_NONE; active = true;
-            negMask = (L.negx ? 1u : 0u) | (L.negy ? 2u : 0u) | (L.negz ? 4u : 0u);
-            // the root: the one node whose own box is tested from the reference array
-            if (sc.n_nodes) {
-                float4 n0 = __ldg(&sc.nodes[0]), n1 = __ldg(&sc.nodes[1]);
-                if (COUNT) ++cn;
-                if (slab(n0, n1, L.ray, L.invDir, L.negx, L.negy, L.negz)) cur = sc.root_code;
+        // ---- refill: idle lanes claim the next entries of the concatenated queues with one warp-aggregated atomic
+        {
+            const unsigned idle = __ballot_sync(FULL, !active);
+            if (!exhausted && idle) {
+                uint32_t base = 0;
+                const int leader = __ffs(idle) - 1;
+                if (lane == leader) base = atomicAdd(a.work, (uint32_t)__popc(idle));
+                base = __shfl_sync(FULL, base, leader);
+                if (!active) {
+                    const uint32_t q = base + __popc(idle & ((1u << lane) - 1));
+                    if (q < total) {
+                        seg = (q >= e0 ? 1u : 0u) + (q >= e1 ? 1u : 0u) + (q >= e2 ? 1u : 0u);
+                        const uint32_t ql = q - (seg == 0 ? 0u : (seg == 1 ? e0 : (seg == 2 ? e1 : e2)));
+                        const uint32_t *queue = seg_sel(seg, a.seg[0].queue, a.seg[1].queue, a.seg[2].queue, a.seg[3].queue);
+                        const float4 *ro = seg_sel(seg, a.seg[0].ro, a.seg[1].ro, a.seg[2].ro, a.seg[3].ro);
+                        const float4 *rd = seg_sel(seg, a.seg[0].rd, a.seg[1].rd, a.seg[2].rd, a.seg[3].rd);
+                        isAny = seg_sel(seg, a.seg[0].any, a.seg[1].any, a.seg[2].any, a.seg[3].any) != 0u;
+                        ri = queue ? queue[ql] : ql;
+                        const float4 o = ro[ri], d = rd[ri];
+                        ray.o = V(o.x, o.y, o.z); ray.d = V(d.x, d.y, d.z); ray.mint = o.w; ray.maxt = d.w;
+                        invDir = V(1.f / ray.d.x, 1.f / ray.d.y, 1.f / ray.d.z);
+                        const bool negx = invDir.x < 0, negy = invDir.y < 0, negz = invDir.z < 0;
+                        negMask = (negx ? 1u : 0u) | (negy ? 2u : 0u) | (negz ? 4u : 0u);
+                        exact = !(isfinite(invDir.x) && isfinite(invDir.y) && isfinite(invDir.z));
+                        best = SPT_MISS; sp = 0; cur = PN_NONE; active = true;
+                        // the root: the one node whose own box is tested from the reference array
+                        if (sc.n_nodes) {
+                            const float4 n0 = __ldg(&sc.nodes[0]), n1 = __ldg(&sc.nodes[1]);
+                            if (COUNT) { if (isAny) ++cnA; else ++cn; }
+                            if (slab(n0, n1, ray, invDir, negx, negy, negz)) cur = sc.root_code;
+                        }
+                    }
+                }
+                if (base + (uint32_t)__popc(idle) >= total) exhausted = true;
             }
         }
         if (!__any_sync(FULL, active)) break;
         while (active) {
             bool done = false;
-            if (cur == PN_NONE) {                                      // pop
-                if (ANY) {
-                    if (sp == 0) done = true; else cur = stk1[--sp];
-                } else {
-                    for (;;) {
-                        if (sp == 0) { done = true; break; }
-                        uint2 e = stk[--sp];
-                        // the far child's slab test completes here with the current maxt
-                        if (__uint_as_float(e.y) < L.ray.maxt) { cur = e.x; break; }
-                    }
-                }
-            }
-            if (cur < PN_LEAF) {                                        // interior: one pair step
-                const float4 *pn = sc.pnodes + 4 * (size_t)cur;
-                float4 q0 = __ldg(pn), q1 = __ldg(pn + 1), q2 = __ldg(pn + 2), q3 = __ldg(pn + 3);
-                if (COUNT) cn += 2;
-                // child 0: min (q0.x,q0.y,q0.z) max (q0.w,q1.x,q1.y); child 1: min (q1.z,q1.w,q2.x) max (q2.y,q2.z,q2.w)
-                float t0, t1;
-                bool h0, h1;
-                if (!L.exact) {
-                    h0 = slab6_finite(q0.x, q0.w, q0.y, q1.x, q0.z, q1.y, L.ray, L.invDir, &t0);
-                    h1 = slab6_finite(q1.z, q2.y, q1.w, q2.z, q2.x, q2.w, L.ray, L.invDir, &t1);
-                } else {
-                    h0 = slab6(L.negx ? q0.w : q0.x, L.negx ? q0.x : q0.w, L.negy ? q1.x : q0.y, L.negy ? q0.y : q1.x,
-                               L.negz ? q1.y : q0.z, L.negz ? q0.z : q1.y, L.ray, L.invDir, &t0);
-                    h1 = slab6(L.negx ? q2.y : q1.z, L.negx ? q1.z : q2.y, L.negy ? q2.z : q1.w, L.negy ? q1.w : q2.z,
-                               L.negz ? q2.w : q2.x, L.negz ? q2.x : q2.w, L.ray, L.invDir, &t1);
-                }
-                const uint32_t c0 = __float_as_uint(q3.x), c1 = __float_as_uint(q3.y), axis = __float_as_uint(q3.z);
-                // reference: dirIsNeg[axis] ? second child first : first child first
-                const bool swap = (negMask >> axis) & 1u;
-                const uint32_t nearC = swap ? c1 : c0, farC = swap ? c0 : c1;
-                const bool nearHit = swap ? h1 : h0, farHit = swap ? h0 : h1;
-                if (farHit) {
-                    if (ANY) stk1[sp++] = farC;
-                    else stk[sp++] = make_uint2(farC, __float_as_uint(swap ? t0 : t1));
-                }
-                cur = nearHit ? nearC : PN_NONE;
-            }
-            if (cur >= PN_LEAF && cur != PN_NONE) {                     // leaf: its primitives in slot order
-                if (leaf_test<ANY, COUNT>(sc, cur & 0x07ffffffu, ((cur >> 27) & 7u) + 1u, (cur >> 30) & 1u, L, cp)) done = true;
-                cur = PN_NONE;
-            }
-            if (done) {
-                a.out_slot[L.i] = L.best;
-                if (!ANY) a.out_t[L.i] = L.ray.maxt;
-                active = false;
-            }
+            if (cur == PN_NONE) done = pop();
+            if (!done && cur < PN_LEAF) node_step();
+            if (!done && cur >= PN_LEAF && cur != PN_NONE) done = leaf_step();
+            if (done) finish();
             if (active && !exhausted && (uint32_t)__popc(__activemask()) < a.fetch_threshold) break;
         }
     }
-    if (COUNT && sc.counters && (cn | cp)) {
-        atomicAdd(&sc.counters[ANY ? 2 : 0], cn);
-        atomicAdd(&sc.counters[ANY ? 3 : 1], cp);
+    if (COUNT && sc.counters) {
+        if (cn | cp) { atomicAdd(&sc.counters[0], cn); atomicAdd(&sc.counters[1], cp); }
+        if (cnA | cpA) { atomicAdd(&sc.counters[2], cnA); atomicAdd(&sc.counters[3], cpA); }
     }
 }

@@ -41,7 +41,8 @@ struct WaveBuffers {
     float4 *laux;                     // infinite light only: RGB radiance of the sampled direction
     uint32_t *pflags;                 // scenes with specular materials: bit 0 = the ray of this path left a specular bounce
     float2 *img_xy;
-    float *T, *L;                     // [cap][NB]: band_off()
+    float *T[2], *L;                  // [cap][NB]: band_off(). T[b & 1] = the throughput ARRIVING at the vertex of bounce b (k_advance of
+                                      // bounce b writes the other buffer; k_addlight of bounce b still reads this one)
     uint32_t *pathQ[2], *shadowQ, *misQ;
     uint32_t *misAnyQ;                // MIS rays towards an infinite light: only hit-or-escape matters, traced as any-hit rays
     uint32_t *hitQ, *missQ;           // path rays of the bounce that found a surface / escaped (bounce 0, env light)

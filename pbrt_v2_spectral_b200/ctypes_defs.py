@@ -64,9 +64,11 @@ class SptRenderParams(C.Structure):
 INTEGRATOR_PATH, INTEGRATOR_DIRECT_ALL, INTEGRATOR_DIRECT_ONE = 0, 1, 2
 
 
-K_GEN, K_TRACE_PATH, K_SHADE, K_TRACE_SHADOW, K_TRACE_MIS, K_ACCUMULATE, K_FILM, K_CLASSES = 0, 1, 2, 3, 4, 5, 6, 8
-K_KERNELS = ["k_gen_camera", "k_trace_v1<closest>", "k_compact_hits + k_shade", "k_trace_v1<any>", "k_trace_v1<closest>", "k_accumulate", "k_film_add", "-"]
-K_NAMES = ["gen_camera", "trace_closest_path", "shade", "trace_any_shadow", "trace_closest_mis", "accumulate", "film_add", "-"]
+# K_TRACE_PATH times the one traversal launch of a bounce (its path rays + the previous bounce's shadow / MIS rays); the
+# shadow / MIS classes only count rays
+K_GEN, K_TRACE_PATH, K_SHADE, K_TRACE_SHADOW, K_TRACE_MIS, K_ACCUMULATE, K_FILM, K_ADVANCE, K_CLASSES = 0, 1, 2, 3, 4, 5, 6, 7, 8
+K_KERNELS = ["k_gen_camera", "k_trace_multi", "k_compact_hits + k_shade", "k_trace_multi", "k_trace_multi", "k_addlight", "k_film_add", "k_advance"]
+K_NAMES = ["gen_camera", "trace", "shade", "trace_any_shadow", "trace_closest_mis", "addlight", "film_add", "advance"]
 
 
 class SptStats(C.Structure):

@@ -9,4 +9,7 @@
 class ParamSet;
 Renderer *CreateGpuPathRenderer(const ParamSet &params, Sampler *sampler, Camera *camera,
                                 SurfaceIntegrator *surf, VolumeIntegrator *vol, bool visIds);
+// looks the renderer's parameters up ("integer seed", "integer gpus") so that ReportUnused(), which MakeRenderer calls before
+// the renderer exists (src/core/api.cpp:1381), does not warn about them
+void GpuPathTouchParams(const ParamSet &params);
 #endif

@@ -1,4 +1,4 @@
-// TEST INFRASTRUCTURE (not part of the product): the traversal KERNEL (csrc/trace_kernels.cuh: k_trace_v1, the pair-node
+// TEST INFRASTRUCTURE (not part of the product): the traversal KERNEL (csrc/trace_kernels.cuh: k_trace_multi, the pair-node
 // walk) and the scene re-layout kernels (csrc/spt_build.cu) compiled for the host as a warp of one lane / a grid of one
 // thread (fake/cuda_runtime.h), so that first-hit ids and distances of the very kernel source can be compared with the
 // reference's golden vectors on a machine without a GPU.
@@ -60,11 +60,16 @@ int hd_trace(const SptSceneDesc *d, const float *rays, uint32_t n, int any, uint
         const float *r = rays + 8 * (size_t)i;
         ro[i] = make_float4(r[0], r[1], r[2], r[6]); rd[i] = make_float4(r[3], r[4], r[5], r[7]);
     }
-    uint32_t count = n, work = 0;
-    TraceArgs a;
-    a.queue = nullptr; a.count = &count; a.work = &work; a.ro = ro.data(); a.rd = rd.data();
-    a.out_slot = out_slot; a.out_t = out_t; a.fetch_threshold = 14;
-    if (any) k_trace_v1<true, false>(sc, a); else k_trace_v1<false, false>(sc, a);
+    // one launch over two queues, as the wavefront issues it: the first half of the rays, then the second half through an index queue
+    uint32_t n0 = n / 2, n1 = n - n0, work = 0;
+    std::vector<uint32_t> q1(n1);
+    for (uint32_t k = 0; k < n1; ++k) q1[k] = n0 + k;
+    TraceMultiArgs a;
+    memset(&a, 0, sizeof(a));
+    a.nseg = 2; a.work = &work; a.fetch_threshold = 14;
+    a.seg[0].queue = nullptr; a.seg[0].count = &n0; a.seg[1].queue = q1.data(); a.seg[1].count = &n1;
+    for (int k = 0; k < 2; ++k) { a.seg[k].ro = ro.data(); a.seg[k].rd = rd.data(); a.seg[k].out_slot = out_slot; a.seg[k].out_t = out_t; a.seg[k].any = any ? 1u : 0u; }
+    k_trace_multi<false>(sc, a);
     return 0;
 }
 

@@ -40,7 +40,7 @@ ALL_CASES = O.golden_cases()
 
 @pytest.mark.parametrize("case", ALL_CASES, ids=[c[0] for c in ALL_CASES])
 def test_traversal_kernel_and_relayout_bit_exact(trace_shim, case):
-    """The traversal KERNEL source (k_trace_v1: pair-node walk, min/max slab form, leaf tests) and the re-layout kernels
+    """The traversal KERNEL source (k_trace_multi: pair-node walk, min/max slab form, leaf tests) and the re-layout kernels
     (leaf flags, pair nodes, vertex pre-gather), compiled for the host as a warp of one lane, against the reference's golden
     vectors: first-hit primitive ids and distances of camera and secondary rays bit for bit, any-hit verdicts."""
     name, sp, gp = case

@@ -52,12 +52,21 @@ def test_unsupported_scene_falls_back_to_the_reference_renderer(tmp_path):
 
 @needs_bins
 @pytest.mark.gpu
-def test_gpupath_binary_renders_what_spt_render_renders(tmp_path):
-    s = open(TINY).read().replace("WorldBegin", 'Renderer "gpupath" "integer seed" [5]\nWorldBegin', 1)
+@pytest.mark.parametrize("gpus", [None, 1, 2, 0])
+def test_gpupath_binary_renders_what_spt_render_renders(tmp_path, gpus):
+    """`Renderer "gpupath"` alone renders on one GPU through spt_render; `"integer gpus" [N]` (0 = every visible GPU) goes
+    through spt_multi_* - the same image either way. The parameters are read like any renderer's (src/core/api.cpp:1374-1379)
+    and raise no unused-parameter warning."""
+    if gpus == 2 and capi.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    extra = "" if gpus is None else ' "integer gpus" [%d]' % gpus
+    s = open(TINY).read().replace("WorldBegin", 'Renderer "gpupath" "integer seed" [5]%s\nWorldBegin' % extra, 1)
     cwd = str(tmp_path)
     r = _run("pbrt_gpupath", s, cwd, "drop")
     assert r.returncode == 0, r.stderr
-    assert "CPU SamplerRenderer instead" not in re.sub(r"\s+", " ", r.stderr + r.stdout)
+    log = re.sub(r"\s+", " ", r.stderr + r.stdout)
+    assert "CPU SamplerRenderer instead" not in log
+    assert "not used" not in log and "unused" not in log.lower(), log
     got = capi.read_dat(os.path.join(cwd, "drop.dat"))
     lowered, _ = O.load_case(*O.golden_cases(big=False)[0][1:])
     scene = capi.Scene(lowered)
