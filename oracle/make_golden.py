@@ -510,7 +510,7 @@ def share_arrays(path, donor, keys=("tex_texels",)):
     a, b = load_container(path), load_container(donor)
     changed = False
     for k in keys:
-        if k in a and k in b and a[k].size > (1 << 20) and np.array_equal(a[k], b[k]):
+        if k in a and k in b and a[k].size > (1 << 18) and np.array_equal(a[k], b[k]):
             del a[k]
             a[k + "@"] = np.frombuffer(os.path.relpath(donor, os.path.dirname(path)).encode(), np.uint8)
             changed = True
@@ -578,6 +578,8 @@ def main():
                 share_arrays(dst, os.path.join(LOWERED, "metal_path.spt"))
         if npix and name in DELTA_BASE:
             write_delta(prefix + ".spt", name)
+        if name in ("envmap_small", "ssenv_small"):       # the grace map's tables (10 MB) are those of the config-4 workload
+            share_arrays(prefix + ".spt", os.path.join(LOWERED, "ssenv_path.spt"), keys=("env_rgb", "env_cdf", "env_func"))
         if name in COMMITTED:
             # committed fixtures: xz-compressed containers (the loader opens .xz transparently)
             import lzma
