@@ -37,6 +37,8 @@ CPU_SAMPLE_SPP = 16          # bounded sample of the workload for the in-line cp
 REF_ARM_SPP = int(os.environ.get("SPT_REF_ARM_SPP", "64"))     # (the CPU test of this arm's output format lowers it)
 # --impl reference renders the whole configuration (64 spp): ~9 s per step on 16 cores
 # workloads that have a scene file the reference binary can run for the CPU leg: (xres, yres, spp, bounded-sample spp)
+# synthetic workloads built through the reference's API (oracle/synth_scene.cpp): (triangles, xres, yres, spp)
+SYNTH_API = {"synth_10m": (10000000, 3840, 2160, 1024), "synth_10m_1080p64": (10000000, 1920, 1080, 64)}
 CPU_WORKLOADS = {"killeroo_path": (700, 700, 64, CPU_SAMPLE_SPP), "killeroo_direct": (700, 700, 64, CPU_SAMPLE_SPP),
                  "bunny_shipped": (640, 480, 256, 8), "metal_path": (400, 400, 512, 16), "ssenv_path": (1920, 1080, 1024, 8)}
 
@@ -138,10 +140,11 @@ def run_reference_arm(args):
     value = n_samples / (ms / 1e3) / 1e6
     sample = "the whole configuration per step: 700x700 (sample extent 701x701) at all %d spp; parse+BVH build (%.2fs, 8x8 1spp run) subtracted" % (REF_ARM_SPP, setup)
     print_json({
-        "impl": "reference", "metric": "Msamples/sec (32-band spectral path trace)", "value": value, "unit": "Msamples/s",
+        "impl": "reference", "metric": "Msamples/sec (%d-band spectral path trace)" % args.bands, "value": value, "unit": "Msamples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "reference scene file (killeroo-simple) derived per SURVEY.md F9",
-        "config": {"workload": WORKLOAD_DESC, "reference_binary": "oracle/_ref/bin/pbrt (unmodified reference, g++ -O2 -m64)"},
+        "config": {"workload": WORKLOAD_DESC, "reference_binary": "oracle/_ref/bin/pbrt (unmodified reference, g++ -O2 -m64)" if args.bands == 32 else
+                   "oracle/_ref/bin30/pbrt (the reference with the one line nSpectralSamples = 32 -> 30 of src/core/spectrum.h patched, g++ -O2 -m64)"},
         "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": ncores, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
@@ -156,9 +159,20 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--wave-pixels", type=int, default=0)
-    ap.add_argument("--workload", default=WORKLOAD, help="lowered scene under assets/_lowered (default: BASELINE config 1); "
+    ap.add_argument("--bands", type=int, default=32, choices=[32, 30], help="32: SampledSpectrum as the reference ships it (default); 30: the 30-band "
+                    "variant BASELINE.json's metric names - libspt30.so against the reference built with nSpectralSamples = 30 (oracle/_ref/bin30)")
+    ap.add_argument("--workload", default=None, help="lowered scene under assets/_lowered (default: BASELINE config 1); "
                     "synth_1m = config 5's recipe at 1 M triangles, BVH larger than L2 (no CPU arm)")
     args = ap.parse_args()
+    global REF_BIN, WORKLOAD, WORKLOAD_DESC
+    if args.bands == 30:
+        os.environ["SPT_NBANDS"] = "30"                  # read by pbrt_v2_spectral_b200.ctypes_defs at import
+        REF_BIN = os.path.join(ROOT, "oracle", "_ref", "bin30", "pbrt")
+        WORKLOAD = "killeroo_path30"
+        WORKLOAD_DESC = WORKLOAD_DESC.replace("SampledSpectrum 32 bands (as shipped)", "SampledSpectrum 30 bands (nSpectralSamples = 30, src/core/spectrum.h:43)")
+        CPU_WORKLOADS[WORKLOAD] = CPU_WORKLOADS["killeroo_path"]
+    if args.workload is None:
+        args.workload = WORKLOAD
     # stdout carries exactly ONE JSON line: everything else written to file descriptor 1 by this process or by libraries
     # under it (NCCL's version banner, which it prints itself whatever torch's logging is set to) goes to stderr
     sys.stdout.flush()
@@ -192,6 +206,20 @@ def main():
     dev = torch.device("cuda", local_rank)
 
     scene_spt = os.path.join(ROOT, "assets", "_lowered", args.workload + ".spt")
+    synth_tool = os.path.join(ROOT, "oracle", "_ref", "bin", "synth_scene")
+    if not os.path.exists(scene_spt) and args.workload in SYNTH_API and os.path.exists(synth_tool):
+        # BASELINE config 5 at full size: the scene is built through the reference's own API (oracle/synth_scene.cpp: its
+        # Shape classes, its BVHAccel build) and lowered - scene preparation on the host, outside every timed region
+        if rank == 0:
+            ntris, xr, yr, spp_w = SYNTH_API[args.workload]
+            os.makedirs(os.path.dirname(scene_spt), exist_ok=True)
+            t_gen = time.perf_counter()
+            subprocess.run([synth_tool, str(ntris), str(xr), str(yr), str(spp_w)], check=True, stdout=sys.stderr, cwd=os.path.dirname(scene_spt),
+                           env=dict(os.environ, SPT_DUMP_PREFIX=scene_spt[:-4], SPT_DUMP_PIXELS="1", SPT_DUMP_LI="0", SPT_DUMP_NRNG="1"))
+            os.remove(scene_spt[:-4] + ".golden")
+            sys.stderr.write("[bench] %s built by the reference's API + BVHAccel and lowered in %.1f s\n" % (args.workload, time.perf_counter() - t_gen))
+        if dist is not None:
+            dist.barrier()
     if not os.path.exists(scene_spt) and args.workload.startswith("synth") and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "bin", "oracle_dump")):
         # synthetic workloads are generated on the spot: .pbrt text -> the built reference's own parser + BVH build (the host
         # side of the boundary, which stays on the CPU by design) -> lowered scene. Scene preparation, outside every timed region.
@@ -213,6 +241,9 @@ def main():
                       "400x400, LD 512 spp, box filter",
         "ssenv_path": "scenes/ss-envmap.pbrt (BASELINE config 4) as shipped except the path integrator: subsurface teapot, substrate floor with "
                       "image-mapped Kd and bump map, grace environment map importance sampled, path maxdepth 5, 1920x1080, LD 1024 spp, box filter",
+        "synth_10m": "BASELINE config 5 at full size: synthetic random-triangle scene, 10 000 000 triangles (BVH + vertices 1.9 GB in HBM), half matte / "
+                     "half plastic, sphere area light + constant infinite light, path maxdepth 5, 3840x2160, LD 1024 spp, box filter; built "
+                     "through the reference's API and BVHAccel (oracle/synth_scene.cpp)",
         "synth_1m": "synthetic random-triangle scene (BASELINE config 5 recipe, SURVEY 8d) at 1 000 000 triangles, matte + plastic, sphere area light + "
                     "constant infinite light, path maxdepth 5, 1024x576, LD 16 spp, box filter"}.get(args.workload, args.workload)
     rp = D.SptRenderParams.from_buffer_copy(bytes(lowered.params))
@@ -310,7 +341,7 @@ def main():
     elided = 0
     first_vertices = 0
     serial_ms = 0.0
-    prof_steps = max(1, min(args.steps, 5))
+    prof_steps = max(1, min(args.steps, 5 if not args.workload.startswith("synth_10m") else 1))
     scene.set_lanes(1)
     scene.render(film, rp)
     for _ in range(prof_steps):
@@ -372,7 +403,7 @@ def main():
     w_pin = capi.HostBuffer((fd.y_pixel_count, fd.x_pixel_count))
     c_host, w_host = c_pin.array, w_pin.array
     e2e_times = []
-    for i in range(1 + args.steps):
+    for i in range(1 + (args.steps if not args.workload.startswith("synth_10m") else 1)):
         barrier()
         t0 = time.perf_counter()
         sc2 = capi.Scene(lowered)                    # H2D: every scene table from host memory (every rank)
@@ -465,7 +496,7 @@ def main():
     rays_total = class_rays[D.K_TRACE_PATH] + class_rays[D.K_TRACE_MIS] + class_rays[D.K_TRACE_SHADOW]
     kernel_launch_counts = {D.K_NAMES[k]: class_launches[k] / prof_steps for k in range(D.K_CLASSES) if class_launches[k]}
     out = {
-        "metric": "Msamples/sec (32-band spectral path trace)", "value": value, "unit": "Msamples/s",
+        "metric": "Msamples/sec (%d-band spectral path trace)" % args.bands, "value": value, "unit": "Msamples/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "reference scene file (killeroo-simple) lowered by the host side; no synthetic substitution" if args.workload == WORKLOAD

@@ -16,8 +16,8 @@
  * (not thread-safe) per handle. There is NO CPU fallback: every entry point that computes needs a
  * CUDA device and fails with SPT_ERR_CUDA otherwise.
  *
- * Spectra: SPT_NBANDS floats per spectrum, the reference's SampledSpectrum
- * (src/core/spectrum.h:41-43, 269-450: 32 bands 395-715 nm as shipped; 30 is a build option).
+ * Spectra: SPT_NBANDS samples per spectrum, the reference's SampledSpectrum
+ * (src/core/spectrum.h:41-43, 269-450: 32 bands 395-715 nm as shipped; 30 is a build option), in rows of SPT_BAND_PITCH floats.
  */
 #ifndef SPT_H
 #define SPT_H
@@ -28,6 +28,14 @@ extern "C" {
 
 #ifndef SPT_NBANDS
 #define SPT_NBANDS 32
+#endif
+/* Every spectrum crossing this boundary is stored as a ROW of SPT_BAND_PITCH floats - one 128-byte line, which the device reads
+ * and writes with one coalesced access: entries 0 .. SPT_NBANDS-1 are the reference's SampledSpectrum samples, the rest is
+ * padding and MUST BE ZERO. The library is built once per band count (libspt.so: 32 as the reference ships; libspt30.so:
+ * the 30-band variant BASELINE.json names, nSpectralSamples = 30 in src/core/spectrum.h:41-43); SptSceneDesc::nbands must match. */
+#define SPT_BAND_PITCH 32
+#if SPT_NBANDS > SPT_BAND_PITCH || SPT_NBANDS < 1
+#error "SPT_NBANDS must be 1..32"
 #endif
 
 #define SPT_OK            0
@@ -87,8 +95,8 @@ enum { SPT_MAT_MATTE = 0, SPT_MAT_PLASTIC = 1, SPT_MAT_METAL = 2, SPT_MAT_MIRROR
 typedef struct SptMaterial {
     int32_t type;
     float p0, p1, p2;
-    float spec0[SPT_NBANDS];
-    float spec1[SPT_NBANDS];
+    float spec0[SPT_BAND_PITCH];
+    float spec1[SPT_BAND_PITCH];
     int32_t tex_kd, tex_bump;
     int32_t brdf;                   /* MEASURED: row of brdfs[]; -1 otherwise */
     int32_t pad_;
@@ -96,7 +104,7 @@ typedef struct SptMaterial {
 
 /* Measured isotropic BRDF (theta-phi .brdf file): the kd-tree the reference built over the samples' BRDFRemap
  * coordinates (src/core/kdtree.h:91-140), node for node, so that a radius search visits and sums the samples in the
- * reference's order. Node k's sample spectrum is brdf_spectra[(node_first + k) * SPT_NBANDS ...]. */
+ * reference's order. Node k's sample spectrum is the row brdf_spectra[(node_first + k) * SPT_BAND_PITCH ...]. */
 typedef struct SptKdNode {
     float split_pos;
     uint32_t bits;                  /* splitAxis (3 = leaf) | hasLeftChild << 2 | rightChild << 3; the left child is node k+1 */
@@ -140,7 +148,7 @@ typedef struct SptLight {
     int32_t xform;
     float pos[3];
     float sum_area;                 /* ShapeSet::sumArea as the reference accumulated it */
-    float spectrum[SPT_NBANDS];
+    float spectrum[SPT_BAND_PITCH];
     int32_t n_samples;              /* Sampler::RoundSize(Light::nSamples): samples per camera hit under the
                                        directlighting integrator (src/integrators/directlighting.cpp:53-58); >= 1 */
     int32_t pad_[3];
@@ -157,10 +165,10 @@ typedef struct SptLightShape {
 /* Tables of SampledSpectrum statics the path needs (src/core/spectrum.h:297-351,417-422;
  * src/core/spectrum.cpp:136-176). Order of rgb_illum: White,Cyan,Magenta,Yellow,Red,Green,Blue. */
 typedef struct SptSpectralTables {
-    float cie_y[SPT_NBANDS];
+    float cie_y[SPT_BAND_PITCH];
     float yint;
-    float rgb_illum[7][SPT_NBANDS];
-    float rgb_refl[7][SPT_NBANDS];  /* rgbRefl2Spect*, same order: FromRGB(rgb, SPECTRUM_REFLECTANCE) of image textures */
+    float rgb_illum[7][SPT_BAND_PITCH];
+    float rgb_refl[7][SPT_BAND_PITCH];  /* rgbRefl2Spect*, same order: FromRGB(rgb, SPECTRUM_REFLECTANCE) of image textures */
 } SptSpectralTables;
 
 typedef struct SptSceneDesc {
@@ -205,7 +213,7 @@ typedef struct SptSceneDesc {
     /* measured BRDFs */
     uint32_t n_brdfs;      const SptBrdfTable *brdfs;
     uint32_t n_brdf_nodes; const SptKdNode *brdf_nodes;
-    const float *brdf_spectra;      /* n_brdf_nodes x SPT_NBANDS */
+    const float *brdf_spectra;      /* n_brdf_nodes rows of SPT_BAND_PITCH */
 } SptSceneDesc;
 
 /* PerspectiveCamera (src/cameras/perspective.cpp:33-106, src/core/camera.cpp:84-103). */

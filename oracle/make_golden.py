@@ -329,6 +329,10 @@ CONFIGS = {
     "bunny_rays":        (bunny, 640, 480, 4, 262144, 0, 0),
     "killeroo_rays_mid": (killeroo, 700, 700, 4, 16384, 0, 0),
     "bunny_rays_mid":    (bunny, 640, 480, 4, 16384, 0, 0),
+    # the 30-band variant (BASELINE.json's metric: "30-band spectral path trace"): the same scene through the reference built
+    # with nSpectralSamples = 30 (oracle/Makefile ref30 -> oracle/_ref/bin30); BANDS30 below routes these to that build
+    "killeroo_path30":  (killeroo, 700, 700, 64, 0, 0, 0),
+    "killeroo_small30": (killeroo, 176, 176, 4, 6000, 40, 1024),
     # small committed fixture
     "tiny":            (tiny, 48, 48, 4, 700, 40, 0),
     # two more committed fixtures (tests/golden/): extended materials, directlighting
@@ -340,9 +344,10 @@ CONFIGS = {
 # small golden scene -> the full-size bench workload (assets/_lowered/, product data) it shares every table with: same scene
 # file, other resolution / spp. The golden scene is stored as a delta of the workload, never the other way round: bench.py
 # reads nothing under oracle/.
+BANDS30 = {"killeroo_path30", "killeroo_small30"}
 COMPACT = {"killeroo_rays", "bunny_rays", "killeroo_rays_mid", "bunny_rays_mid"}
 COMMITTED = {"killeroo_rays_mid", "bunny_rays_mid"}
-DELTA_BASE = {"killeroo_rays": "killeroo_path", "bunny_rays": "bunny_path", "killeroo_small": "killeroo_path", "bunny_small": "bunny_path", "metal_shipped_small": "metal_path",
+DELTA_BASE = {"killeroo_small30": "killeroo_path30", "killeroo_rays": "killeroo_path", "bunny_rays": "bunny_path", "killeroo_small": "killeroo_path", "bunny_small": "bunny_path", "metal_shipped_small": "metal_path",
               "ssenv_shipped_small": "ssenv_path", "killeroo_direct_small": "killeroo_direct",
               "bunny_shipped_small": "bunny_shipped"}
 
@@ -566,7 +571,8 @@ def main():
                    SPT_DUMP_NRNG=str(max(nrng, 1)), SPT_DUMP_LI="1" if npix else "0",
                    SPT_DUMP_COMPACT="1" if name in COMPACT else "0")
         t0 = time.time()
-        subprocess.run([os.path.join(OUT, "bin/oracle_dump"), "--quiet", name + ".gpu.pbrt"],
+        bindir = "bin30" if name in BANDS30 else "bin"
+        subprocess.run([os.path.join(OUT, bindir, "oracle_dump"), "--quiet", name + ".gpu.pbrt"],
                        cwd=SCENES, env=env, check=True, stdout=subprocess.DEVNULL)
         if not npix:
             # full-size workloads: only the lowered scene is kept, where bench.py looks for it
@@ -599,7 +605,7 @@ def main():
             write(os.path.join(SCENES, iname + ".pbrt"), build(w, h, img_spp, iname))
             t0 = time.time()
             ncores = os.cpu_count()
-            subprocess.run([os.path.join(OUT, "bin/pbrt"), "--quiet", "--ncores", str(ncores), iname + ".pbrt"],
+            subprocess.run([os.path.join(OUT, bindir, "pbrt"), "--quiet", "--ncores", str(ncores), iname + ".pbrt"],
                            cwd=SCENES, env=REF_RENDER_ENV, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
             with open(os.path.join(GOLDEN, iname + ".ref.padfix.json"), "w") as fp:
                 fp.write('{"how": "rendered with MALLOC_PERTURB_=255: Pixel::pad reads as zero"}')

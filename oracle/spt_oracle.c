@@ -862,7 +862,7 @@ static void kd_lookup(const SptKdNode *nodes, const float *spectra, uint32_t nNo
     float d2 = dx * dx + dy * dy + dz * dz;                   /* DistanceSquared -> Vector::LengthSquared, geometry.h */
     if (d2 < maxDistSquared) {
         float weight = expf(-100.f * d2);
-        const float *sv = spectra + (size_t)nodeNum * NB;
+        const float *sv = spectra + (size_t)nodeNum * SPT_BAND_PITCH;
         for (int c = 0; c < NB; ++c) proc->v[c] += sv[c] * weight;
         proc->sumWeights += weight;
         ++proc->nFound;
@@ -884,7 +884,7 @@ static void measured_f(const SptSceneDesc *sc, const SptBrdfTable *t, v3 wo, v3 
         IrregIsoProc proc;
         for (int c = 0; c < NB; ++c) proc.v[c] = 0.f;
         proc.sumWeights = 0.f; proc.nFound = 0;
-        kd_lookup(sc->brdf_nodes + t->node_first, sc->brdf_spectra + (size_t)t->node_first * NB, t->n_nodes, 0, m, &proc, lastMaxDist2);
+        kd_lookup(sc->brdf_nodes + t->node_first, sc->brdf_spectra + (size_t)t->node_first * SPT_BAND_PITCH, t->n_nodes, 0, m, &proc, lastMaxDist2);
         if (proc.nFound > 2 || lastMaxDist2 > 1.5f) {
             for (int c = 0; c < NB; ++c) out[c] += clampf(proc.v[c], 0.f, INFINITY) / proc.sumWeights;
             return;

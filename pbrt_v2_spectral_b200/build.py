@@ -14,6 +14,8 @@ import subprocess
 import sys
 from concurrent.futures import ThreadPoolExecutor
 
+# Two libraries from the same sources: libspt.so (SPT_NBANDS = 32, the reference as shipped) and libspt30.so (-DSPT_NBANDS=30,
+# the 30-band SampledSpectrum BASELINE.json's metric names: src/core/spectrum.h:41-43 with nSpectralSamples = 30).
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
@@ -34,11 +36,23 @@ def _run(cmd, verbose):
         raise RuntimeError("nvcc failed: " + " ".join(cmd))
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, nbands=None):
+    """nbands None: both libraries; 32 / 30: that one. Returns the path of the 32-band library (or of the one asked for)."""
+    if nbands is None:
+        with ThreadPoolExecutor(2) as ex:
+            outs = list(ex.map(lambda nb: build(force, verbose, nb), (32, 30)))
+        return outs[0]
+    out_so = OUT if nbands == 32 else os.path.join(HERE, "libspt%d.so" % nbands)
+    obj_dir = OBJ if nbands == 32 else os.path.join(OBJ, "nb%d" % nbands)
+    band_flags = [] if nbands == 32 else ["-DSPT_NBANDS=%d" % nbands]
+    return _build_one(force, verbose, out_so, obj_dir, band_flags)
+
+
+def _build_one(force, verbose, OUT, OBJ, band_flags):
     if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in DEPS):
         return OUT
     os.makedirs(OBJ, exist_ok=True)
-    extra = ["-Xptxas", "-v"] if verbose else []
+    extra = (["-Xptxas", "-v"] if verbose else []) + band_flags
     objs = [os.path.join(OBJ, u[:-3] + ".o") for u, _ in UNITS]
     # a unit is recompiled when its own source or any header is newer than its object
     headers = [d for d in DEPS if not d.endswith(".cu")]

@@ -10,7 +10,9 @@ import numpy as np
 from . import ctypes_defs as D
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("SPT_LIB") or os.path.join(HERE, "libspt.so")   # SPT_LIB: A/B builds of the same ABI (profiles/tools)
+# libspt.so: 32 bands, the reference as shipped; libspt30.so: the 30-band variant (SPT_NBANDS=30 in the environment selects it
+# and sizes the Python-side arrays). SPT_LIB: A/B builds of the same ABI (profiles/tools)
+LIB_PATH = os.environ.get("SPT_LIB") or os.path.join(HERE, "libspt.so" if D.NBANDS == 32 else "libspt%d.so" % D.NBANDS)
 
 # every symbol include/spt.h declares (checked by tests/test_abi.py)
 SYMBOLS = [

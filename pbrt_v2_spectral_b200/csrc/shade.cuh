@@ -632,7 +632,7 @@ __device__ inline void measured_f(const DevScene &sc, const SptBrdfTable &t, v3 
     if (dphi > PI_F) dphi = 2.f * PI_F - dphi;
     const v3 m = V(sini * sino, dphi / PI_F, cosi * coso);
     const SptKdNode *nodes = sc.brdf_nodes + t.node_first;
-    const float *spectra = sc.brdf_spectra + (size_t)t.node_first * NB;
+    const float *spectra = sc.brdf_spectra + (size_t)t.node_first * NBP;
     const uint32_t NONE = 0xffffffffu;
     // The reference repeats the search with maxDist2 = .001, .002, .004, ... until it finds more than two samples (or
     // maxDist2 exceeds 1.5), i.e. it stops at the first radius^2 of that sequence above the THIRD-SMALLEST squared distance.
@@ -705,7 +705,7 @@ __device__ inline void measured_f(const DevScene &sc, const SptBrdfTable &t, v3 
             const float d2 = dx * dx + dy * dy + dz * dz;
             if (d2 < maxD2) {
                 const float weight = expf(-100.f * d2);
-                const float *sv = spectra + (size_t)n * NB;
+                const float *sv = spectra + (size_t)n * NBP;
                 for (int c = 0; c < NB; ++c) v[c] += __ldg(sv + c) * weight;
                 sumW += weight;
             }

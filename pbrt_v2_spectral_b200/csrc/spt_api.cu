@@ -236,6 +236,16 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
                 return bad("light shape data out of range");
         }
     }
+    if (NB < NBP) {
+        // rows are SPT_BAND_PITCH wide; what lies beyond the valid bands must be zero (the lane-per-band kernels read whole rows)
+        auto padded = [](const float *row) { for (int c = NB; c < NBP; ++c) if (row[c] != 0.f) return false; return true; };
+        bool ok = padded(d->tables.cie_y);
+        for (int k = 0; k < 7; ++k) ok = ok && padded(d->tables.rgb_illum[k]) && padded(d->tables.rgb_refl[k]);
+        for (uint32_t k = 0; k < d->n_materials; ++k) ok = ok && padded(d->materials[k].spec0) && padded(d->materials[k].spec1);
+        for (uint32_t k = 0; k < d->n_lights; ++k) ok = ok && padded(d->lights[k].spectrum);
+        for (uint32_t k = 0; k < d->n_brdf_nodes; ++k) ok = ok && padded(d->brdf_spectra + (size_t)k * NBP);
+        if (!ok) { g_err = "a spectrum row has non-zero padding beyond SPT_NBANDS"; return nullptr; }
+    }
     SptScene *s = new SptScene();
     cudaGetDevice(&s->device);
     if (const char *e = getenv("SPT_TRACE_VARIANT")) s->trace_variant = atoi(e);
@@ -398,7 +408,7 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
             g_err = "malformed BRDF table"; s->mem.release(); delete s; return nullptr;       // 2^16 nodes: the look-up's stack of 32 covers depth 16
         }
     UP(v.brdfs, d->brdfs, d->n_brdfs); UP(v.brdf_nodes, d->brdf_nodes, d->n_brdf_nodes);
-    UP(v.brdf_spectra, d->brdf_spectra, (size_t)d->n_brdf_nodes * NB);
+    UP(v.brdf_spectra, d->brdf_spectra, (size_t)d->n_brdf_nodes * NBP);
     UP(v.light_shapes, d->light_shapes, d->n_light_shapes);
     UP(v.light_cdf, cdf.data(), cdf.size());
     v.n_lights = d->n_lights;
@@ -514,9 +524,9 @@ static int ensure_wave(SptScene *s, int n_lanes, uint32_t cap, int max_depth, si
         AL(w.rec0, float4, jcap); AL(w.rec1, float4, jcap); AL(w.rec2, float4, jcap);
         AL(w.laux, float4, jcap); AL(w.pflags, uint32_t, cap);
         AL(w.rec3, float4, s->dev.has_ext ? jcap : 1); AL(w.rec4, float4, s->dev.has_ext ? jcap : 1);
-        AL(w.frow, float, s->dev.has_measured ? jcap * 3 * NB : 1);
+        AL(w.frow, float, s->dev.has_measured ? jcap * 3 * NBP : 1);
         AL(w.img_xy, float2, cap);
-        AL(w.T[0], float, (size_t)cap * NB); AL(w.T[1], float, (size_t)cap * NB); AL(w.L, float, (size_t)cap * NB);
+        AL(w.T[0], float, (size_t)cap * NBP); AL(w.T[1], float, (size_t)cap * NBP); AL(w.L, float, (size_t)cap * NBP);
         AL(w.pathQ[0], uint32_t, cap); AL(w.pathQ[1], uint32_t, cap); AL(w.shadowQ, uint32_t, jcap); AL(w.misQ, uint32_t, jcap);
         AL(w.hitQ, uint32_t, cap); AL(w.missQ, uint32_t, cap); AL(w.misAnyQ, uint32_t, jcap);
 #undef AL
@@ -918,7 +928,7 @@ int spt_film_add_samples(SptFilm *f, const SptSpectralTables *tables, const floa
     DevMem m;
     SptSpectralTables *dt = m.upload(tables, 1);
     float2 *dxy = (float2 *)m.upload(image_xy, n * 2);
-    float *dl = m.upload(L, n * NB), *soa = m.alloc<float>(((n + 31) / 32 * 32) * NB);
+    float *dl = m.upload(L, n * NB), *soa = m.alloc<float>(((n + 31) / 32 * 32) * NBP);
     if (!dt || !dxy || !dl || !soa) { m.release(); return fail(SPT_ERR_CUDA, "device allocation failed"); }
     spt_launch_scatter_L(0, dl, (uint32_t)n, (uint32_t)n, soa);
     FilmView fv; fv.d = f->desc; fv.pix = f->pix; fv.table = f->table;

@@ -11,7 +11,8 @@
 #include <stdint.h>
 #include "spt.h"
 
-#define NB SPT_NBANDS
+#define NB SPT_NBANDS            // valid bands
+#define NBP SPT_BAND_PITCH       // floats per spectrum row in memory (bands NB.. are zero padding)
 #define SPT_MISS 0xffffffffu
 #define PI_F 3.14159265358979323846f
 #define INV_PI_F 0.31830988618379067154f

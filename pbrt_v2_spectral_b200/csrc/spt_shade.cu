@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(256) k_compact_hits(const uint32_t *__restrict
                 if (black_L) {
                     float4 *row = (float4 *)(black_L + band_off(idx[k], 0));
 #pragma unroll
-                    for (int c = 0; c < NB / 4; ++c) row[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int c = 0; c < NBP / 4; ++c) row[c] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
         }
@@ -310,11 +310,12 @@ __global__ void __launch_bounds__(128, SPT_SHADE_MINBLOCKS) k_shade(DevScene sc,
                     for (int d = 0; d < 3; ++d) {
                         const bool need = d == 0 ? (flags & RF_L) != 0 : (d == 1 ? (flags & RF_B) != 0 : ((flags & RF_P) != 0 && t2.mf));
                         if (!need) continue;
-                        float fv[NB];
+                        float fv[NBP];
+                        for (int c = NB; c < NBP; ++c) fv[c] = 0.f;
                         measured_f(sc, tb, wo, d == 0 ? wl0 : (d == 1 ? wl1 : wl2), fv);
-                        float4 *row = (float4 *)(wb.frow + ((size_t)r * 3 + d) * NB);
+                        float4 *row = (float4 *)(wb.frow + ((size_t)r * 3 + d) * NBP);
 #pragma unroll
-                        for (int c = 0; c < NB / 4; ++c) row[c] = make_float4(fv[4 * c], fv[4 * c + 1], fv[4 * c + 2], fv[4 * c + 3]);
+                        for (int c = 0; c < NBP / 4; ++c) row[c] = make_float4(fv[4 * c], fv[4 * c + 1], fv[4 * c + 2], fv[4 * c + 3]);
                     }
                 }
                 if (EXT) {
@@ -379,7 +380,7 @@ struct LightBand { int kind; IllumCoefs k; };
 // memory. Phase B, lane = (vertex of a group of four, four bands): 8 lanes x float4 cover a vertex's 128-byte row, so one
 // LDG.128 / STG.128 per lane moves four rows per warp instruction (the one-float-per-lane form was issue-bound at 0.49 of
 // the HBM rate); y(T) is a sum over the 8 lanes of a vertex. Phase C (k_advance), lane = vertex: next ray + queue push.
-static_assert(NB == 32, "k_advance / k_addlight / k_film_add assume 128-byte rows");
+static_assert(NBP == 32, "k_advance / k_addlight / k_film_add assume 128-byte rows (lane = band, or 8 lanes x float4)");
 #define ACC_WARPS 4
 struct F4 { float v[4]; };
 __device__ __forceinline__ F4 ld4(const float *row, int bg) { float4 q = __ldg((const float4 *)row + bg); F4 r; r.v[0] = q.x; r.v[1] = q.y; r.v[2] = q.z; r.v[3] = q.w; return r; }
@@ -481,10 +482,10 @@ __global__ void __launch_bounds__(32 * ACC_WARPS, 8) k_advance(DevScene sc, Rend
             const uint32_t kind = (misc >> 1) & 7u;
             F4 Tn = splat4(0.f), fP = splat4(0.f);
             if (haveP) {
-                const F4 Tv = bounce == 0 ? splat4(1.f) : ld4g(Tin + (size_t)vi * NB, bg);
+                const F4 Tv = bounce == 0 ? splat4(1.f) : ld4g(Tin + (size_t)vi * NBP, bg);
                 if (EXT && kind == 3u) {
                     // measured BRDF: the value is a row K5 wrote (coefficient 1 = the direction has a value)
-                    if (cP.x != 0.f) fP = ld4g(wb.frow + ((size_t)vi * 3 + 2) * NB, bg);
+                    if (cP.x != 0.f) fP = ld4g(wb.frow + ((size_t)vi * 3 + 2) * NBP, bg);
                 } else {
                     const SptMaterial &m = sc.materials[__float_as_uint(m4.z)];
                     F4 s0 = ld4(m.spec0, bg);
@@ -511,7 +512,7 @@ __global__ void __launch_bounds__(32 * ACC_WARPS, 8) k_advance(DevScene sc, Rend
                     for (int c = 0; c < 4; ++c) Tn.v[c] *= inv;
                 }
             }
-            if (alive) st4(Tout + (size_t)vi * NB, bg, Tn);
+            if (alive) st4(Tout + (size_t)vi * NBP, bg, Tn);
             // the four vertices of this pass: their verdicts sit at lanes 0, 8, 16, 24 of the ballot -> bits v0 .. v0 + 3
             const unsigned b4 = __ballot_sync(FULL, alive && bg == 0);
             aliveMask |= ((b4 & 1u) | ((b4 >> 7) & 2u) | ((b4 >> 14) & 4u) | ((b4 >> 21) & 8u)) << v0;
@@ -630,14 +631,14 @@ __global__ void __launch_bounds__(32 * ACC_WARPS, 8) k_addlight(DevScene sc, Ren
             const uint32_t kind = (misc >> 1) & 7u, lightIdx = misc >> 8;
             const float4 x4 = stage[v][4];
             const uint32_t emit = __float_as_uint(x4.y);
-            float *Lrow = Lg + (size_t)vi * NB;
+            float *Lrow = Lg + (size_t)vi * NBP;
             F4 Tv, Lv;
             if (bounce == 0) {
                 // the path starts here: T = 1, L = what the first vertex emits towards the camera (path.cpp:55-56)
                 Tv = splat4(1.f);
                 Lv = emit == 0 ? splat4(0.f) : (emit == 1 ? light0 : ld4(sc.lights[emit - 1].spectrum, bg));
             } else {
-                Tv = ld4g(Tin + (size_t)vi * NB, bg);
+                Tv = ld4g(Tin + (size_t)vi * NBP, bg);
                 Lv = ld4g(Lrow, bg);
                 // a vertex reached through a specular bounce adds what it emits (path.cpp:55-56)
                 if (emit) {
@@ -649,8 +650,8 @@ __global__ void __launch_bounds__(32 * ACC_WARPS, 8) k_addlight(DevScene sc, Ren
             F4 fL = splat4(0.f), fB = splat4(0.f);
             if (EXT && kind == 3u) {
                 // measured BRDF: the values are rows K5 wrote (coefficient 1 = the direction has a value)
-                if (cLB.x != 0.f) fL = ld4g(wb.frow + ((size_t)vi * 3 + 0) * NB, bg);
-                if (cLB.z != 0.f) fB = ld4g(wb.frow + ((size_t)vi * 3 + 1) * NB, bg);
+                if (cLB.x != 0.f) fL = ld4g(wb.frow + ((size_t)vi * 3 + 0) * NBP, bg);
+                if (cLB.z != 0.f) fB = ld4g(wb.frow + ((size_t)vi * 3 + 1) * NBP, bg);
             } else {
                 const SptMaterial &m = sc.materials[__float_as_uint(x4.x)];
                 F4 s0 = ld4(m.spec0, bg);
@@ -781,9 +782,9 @@ __global__ void __launch_bounds__(32 * ACCD_WARPS, 8) k_accumulate_direct(DevSce
                     const uint32_t r = r0 + (sub <= 32u ? jj : j0 + jj);
                     float fL, fB;
                     if (bits & RF_MEASURED) {
-                        const float *fr = wb.frow + (size_t)r * 3 * NB + lane;
+                        const float *fr = wb.frow + (size_t)r * 3 * NBP + lane;
                         fL = cLB.x != 0.f ? fr[0] : 0.f;
-                        fB = cLB.z != 0.f ? fr[NB] : 0.f;
+                        fB = cLB.z != 0.f ? fr[NBP] : 0.f;
                     } else if (bits & RF_SUBSTRATE) {
                         const float4 e3 = wb.rec3[r];
                         const float oms = 1.f - s1, dR = s0 * oms;
@@ -919,7 +920,7 @@ __global__ void __launch_bounds__(256) k_film_add(FilmView film, const SptSpectr
                             int ix = min((int)floorf(fx), 15);
                             float wpx = film.table[iy * 16 + ix];
                             float *dst = film.pix + ((size_t)(py - ys) * fd.x_pixel_count + (px - xs)) * (NB + 1);
-                            atomicAdd(dst + lane, wpx * v);
+                            if (lane < NB) atomicAdd(dst + lane, wpx * v);
                             if (lane == 0) atomicAdd(dst + NB, wpx);
                         }
                     }
@@ -928,7 +929,7 @@ __global__ void __launch_bounds__(256) k_film_add(FilmView film, const SptSpectr
         }
         if (mainInside && wsum != 0.f) {
             float *dst = film.pix + ((size_t)(mainy - ys) * fd.x_pixel_count + (mainx - xs)) * (NB + 1);
-            atomicAdd(dst + lane, acc);
+            if (lane < NB) atomicAdd(dst + lane, acc);
             if (lane == 0) atomicAdd(dst + NB, wsum);
         }
     }
@@ -944,18 +945,19 @@ __global__ void k_film_split(const float *pix, size_t npix, float *c, float *w) 
         if (b < NB) c[p * NB + b] = v; else w[p] = v;
     }
 }
-// SoA [NB][cap] -> AoS [n][NB] (spt_shade_samples output)
+// rows of NBP floats -> [n][NB] (spt_shade_samples output)
 __global__ void k_gather_L(const float *L, uint32_t cap, uint32_t n, float *out) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n * NB; i += gridDim.x * blockDim.x) {
         uint32_t s = i / NB, c = i % NB;
         out[i] = L[band_off(s, c)];
     }
 }
-// AoS [n][NB] -> SoA, for spt_film_add_samples
+// [n][NB] -> rows of NBP floats (zero padding), for spt_film_add_samples
 __global__ void k_scatter_L(const float *in, uint32_t cap, uint32_t n, float *L) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n * NB; i += gridDim.x * blockDim.x) {
         uint32_t s = i / NB, c = i % NB;
         L[band_off(s, c)] = in[i];
+        if (NB < NBP && c == 0) for (int k = NB; k < NBP; ++k) L[band_off(s, k)] = 0.f;
     }
 }
 

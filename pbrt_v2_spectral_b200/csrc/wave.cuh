@@ -36,12 +36,12 @@ struct WaveBuffers {
     // directions and the RGB an image-mapped Kd evaluated to at this vertex
     float4 *rec3;                     // {light dir c, MIS dir c, continuation c, -}: Schlick weight (1 - wi.wh)^5
     float4 *rec4;                     // {r, g, b, -}
-    float *frow;                      // measured BRDFs only: [cap][3][NB] - f(wo,wi) of the light / MIS / continuation direction, one
+    float *frow;                      // measured BRDFs only: [cap][3][NBP] - f(wo,wi) of the light / MIS / continuation direction, one
                                       // 128-byte row each (a table look-up has no wavelength-independent factorisation)
     float4 *laux;                     // infinite light only: RGB radiance of the sampled direction
     uint32_t *pflags;                 // scenes with specular materials: bit 0 = the ray of this path left a specular bounce
     float2 *img_xy;
-    float *T[2], *L;                  // [cap][NB]: band_off(). T[b & 1] = the throughput ARRIVING at the vertex of bounce b (k_advance of
+    float *T[2], *L;                  // [cap][NBP]: band_off(). T[b & 1] = the throughput ARRIVING at the vertex of bounce b (k_advance of
                                       // bounce b writes the other buffer; k_addlight of bounce b still reads this one)
     uint32_t *pathQ[2], *shadowQ, *misQ;
     uint32_t *misAnyQ;                // MIS rays towards an infinite light: only hit-or-escape matters, traced as any-hit rays
@@ -52,7 +52,7 @@ struct WaveBuffers {
 // work lane-per-band, so every access is one coalesced line whatever the order of the paths in the
 // queues, and all bands of a path sit in one page (a [NB][cap] array strides by the wave capacity
 // - tens of MB - between bands and thrashes the TLB).
-__device__ __forceinline__ size_t band_off(uint32_t i, int c) { return (size_t)i * NB + (uint32_t)c; }
+__device__ __forceinline__ size_t band_off(uint32_t i, int c) { return (size_t)i * NBP + (uint32_t)c; }
 
 struct RenderCfg {
     SptCameraDesc cam;

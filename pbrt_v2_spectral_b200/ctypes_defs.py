@@ -1,12 +1,16 @@
 """ctypes mirrors of the plain-C structs in include/spt.h (kept field-for-field in the same order)."""
 import ctypes as C
+import os
 
-NBANDS = 32
+# valid bands of the library in use (libspt.so: 32 as the reference ships; SPT_NBANDS=30 selects libspt30.so) and the row
+# pitch of every spectrum crossing the boundary (include/spt.h: SPT_BAND_PITCH; entries beyond NBANDS are zero)
+NBANDS = int(os.environ.get("SPT_NBANDS", "32"))
+BAND_PITCH = 32
 
 
 class SptSpectralTables(C.Structure):
-    _fields_ = [("cie_y", C.c_float * NBANDS), ("yint", C.c_float), ("rgb_illum", (C.c_float * NBANDS) * 7),
-                ("rgb_refl", (C.c_float * NBANDS) * 7)]
+    _fields_ = [("cie_y", C.c_float * BAND_PITCH), ("yint", C.c_float), ("rgb_illum", (C.c_float * BAND_PITCH) * 7),
+                ("rgb_refl", (C.c_float * BAND_PITCH) * 7)]
 
 
 class SptSceneDesc(C.Structure):
@@ -85,9 +89,9 @@ class SptStats(C.Structure):
 # row sizes of the table structs (bytes), for sanity checks against the container file
 SIZEOF_QUADRIC = 32
 SIZEOF_XFORM = 128
-SIZEOF_MATERIAL = 16 + 2 * 4 * NBANDS + 16
+SIZEOF_MATERIAL = 16 + 2 * 4 * BAND_PITCH + 16
 SIZEOF_TEXTURE = 64
 SIZEOF_BRDF_TABLE = 8
 SIZEOF_KD_NODE = 32
-SIZEOF_LIGHT = 32 + 4 * NBANDS + 16
+SIZEOF_LIGHT = 32 + 4 * BAND_PITCH + 16
 SIZEOF_LIGHT_SHAPE = 16

@@ -386,7 +386,9 @@ struct Lowerer {
         }
     }
 
+    // rows of SPT_BAND_PITCH floats: the caller zero-fills them, the reference's nSpectralSamples samples go first
     static void CopySpectrum(const Spectrum &s, float *dst) {
+        static_assert(nSpectralSamples == SPT_NBANDS, "build the host side with -DSPT_NBANDS equal to the reference's nSpectralSamples");
         for (int i = 0; i < nSpectralSamples; ++i) dst[i] = s.c[i];
     }
 
@@ -411,9 +413,9 @@ struct Lowerer {
                     n.bits = (uint32_t)kd->nodes[k].splitAxis | (uint32_t)kd->nodes[k].hasLeftChild << 2 | (uint32_t)kd->nodes[k].rightChild << 3;
                     n.p[0] = kd->nodeData[k].p.x; n.p[1] = kd->nodeData[k].p.y; n.p[2] = kd->nodeData[k].p.z;
                     out->brdf_nodes.push_back(n);
-                    float v[nSpectralSamples];
+                    float v[SPT_BAND_PITCH] = { 0.f };       // one row per spectrum, zero beyond the valid bands
                     CopySpectrum(kd->nodeData[k].v, v);
-                    out->brdf_spectra.insert(out->brdf_spectra.end(), v, v + nSpectralSamples);
+                    out->brdf_spectra.insert(out->brdf_spectra.end(), v, v + SPT_BAND_PITCH);
                 }
                 out->brdfs.push_back(t);
                 brdfIdx[(const void *)kd] = (int)out->brdfs.size() - 1;

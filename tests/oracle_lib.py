@@ -10,7 +10,7 @@ from pbrt_v2_spectral_b200 import ctypes_defs as D
 from pbrt_v2_spectral_b200.scene_io import LoweredScene, load_container
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-ORACLE_SO = os.path.join(ROOT, "oracle", "_ref", "liboracle.so")
+ORACLE_SO = os.path.join(ROOT, "oracle", "_ref", "liboracle.so" if D.NBANDS == 32 else "liboracle%d.so" % D.NBANDS)
 GOLDEN_SMALL = os.path.join(ROOT, "tests", "golden")
 GOLDEN_BIG = os.path.join(ROOT, "oracle", "_ref", "golden")
 
@@ -127,11 +127,16 @@ def render(scene, params=None, film=None):
 
 def golden_cases(big=True):
     """[(name, scene path, golden path)] of every golden set present (the tiny one always is)."""
+    if D.NBANDS != 32:
+        # the 30-band variant (SPT_NBANDS=30 in the environment): its own golden sets, made by the reference built with
+        # nSpectralSamples = 30 (oracle/Makefile ref30); names end in the band count
+        return [(f[:-7], os.path.join(GOLDEN_BIG, f[:-7] + ".spt"), os.path.join(GOLDEN_BIG, f))
+                for f in (sorted(os.listdir(GOLDEN_BIG)) if os.path.isdir(GOLDEN_BIG) else []) if f.endswith("_small%d.golden" % D.NBANDS)]
     cases = [(n, os.path.join(GOLDEN_SMALL, n + ".spt"), os.path.join(GOLDEN_SMALL, n + ".golden"))
              for n in ("tiny", "tiny_tex", "tiny_direct") if os.path.exists(os.path.join(GOLDEN_SMALL, n + ".golden"))]
     if big and os.path.isdir(GOLDEN_BIG):
         for f in sorted(os.listdir(GOLDEN_BIG)):
-            if f.endswith(".golden") and not f.endswith("_rays.golden"):
+            if f.endswith(".golden") and not f.endswith("_rays.golden") and not f[:-7].endswith("30"):
                 name = f[:-7]
                 cases.append((name, os.path.join(GOLDEN_BIG, name + ".spt"), os.path.join(GOLDEN_BIG, f)))
     return cases
@@ -141,6 +146,8 @@ def ray_cases(big=True):
     """[(name, scene path, golden path)] of the compact first-hit sets ({image_xy, prim_id, t_hit}, oracle_dump's
     SPT_DUMP_COMPACT): the committed mid-size ones (65 536 camera rays of BASELINE configs 1 and 2 at full resolution, xz
     containers) and, where oracle/_ref/golden is present, the 1 048 576-ray ones."""
+    if D.NBANDS != 32:
+        return []
     cases = [(n, os.path.join(GOLDEN_SMALL, n + ".spt.xz"), os.path.join(GOLDEN_SMALL, n + ".golden.xz"))
              for n in ("killeroo_rays_mid", "bunny_rays_mid") if os.path.exists(os.path.join(GOLDEN_SMALL, n + ".golden.xz"))]
     if big:

@@ -25,6 +25,8 @@ IMAGES = [("killeroo_small", 1024), ("bunny_small", 4096), ("metal_small", 512),
           ("killeroo_direct_small", 1024), ("bunny_direct_small", 1024),
           # the bunny's shipped measured BRDF: under the path integrator (config 2), and bunny.pbrt exactly as shipped
           ("bunny_measured_small", 4096), ("bunny_shipped_small", 1024)]
+if D.NBANDS == 30:      # the 30-band library (SPT_NBANDS=30): the image the reference built with nSpectralSamples = 30 rendered
+    IMAGES = [("killeroo_small30", 1024)]
 
 
 FLOOR_PATH = os.path.join(O.GOLDEN_SMALL, "image_floor.json")
