@@ -89,8 +89,9 @@ typedef struct SptXform { float m[16]; float minv[16]; } SptXform;
  */
 enum { SPT_MAT_MATTE = 0, SPT_MAT_PLASTIC = 1, SPT_MAT_METAL = 2, SPT_MAT_MIRROR = 3, SPT_MAT_GLASS = 4,
        SPT_MAT_SUBSTRATE = 5,
-       SPT_MAT_MEASURED = 6    /* IrregIsotropicBRDF over the table brdfs[brdf] (src/materials/measured.cpp:77-120,185-205,
-                                  src/core/reflection.cpp:239-263); spectra unused */
+       SPT_MAT_MEASURED = 6    /* measured BRDF brdfs[brdf]: IrregIsotropicBRDF (theta-phi .brdf data, src/materials/measured.cpp:77-120,
+                                  185-205, src/core/reflection.cpp:239-263) or RegularHalfangleBRDF (MERL .binary data,
+                                  measured.cpp:122-170, reflection.cpp:267-300); spectra unused */
 };
 typedef struct SptMaterial {
     int32_t type;
@@ -111,7 +112,16 @@ typedef struct SptKdNode {
     float p[3];                     /* IrregIsotropicBRDFSample::p */
     float pad_[3];
 } SptKdNode;
-typedef struct SptBrdfTable { uint32_t node_first, n_nodes; } SptBrdfTable;
+/* One measured BRDF. Theta-phi data (IrregIsotropicBRDF): kd-tree nodes [node_first, node_first + n_nodes), n_nodes > 0.
+ * Half-angle data (MERL .binary -> RegularHalfangleBRDF, src/core/reflection.cpp:267-300, src/materials/measured.cpp:122-170):
+ * n_nodes == 0 and the table of n_theta_h x n_theta_d x n_phi_d RGB triples the reference loaded (already scaled and clamped
+ * at zero, :147-161) starts at merl_rgb[rgb_offset]; entry index = phiD + n_phi_d * (thetaD + thetaH * n_theta_d). */
+typedef struct SptBrdfTable {
+    uint32_t node_first, n_nodes;
+    uint32_t n_theta_h, n_theta_d, n_phi_d;
+    uint32_t pad_;
+    uint64_t rgb_offset;
+} SptBrdfTable;
 
 /* Image texture = ImageTexture<RGBSpectrum,Spectrum> / ImageTexture<float,float> over a UVMapping2D
  * (src/textures/imagemap.h:60-100, src/core/texture.cpp:80-90) with the MIPMap pyramid the reference built
@@ -214,6 +224,7 @@ typedef struct SptSceneDesc {
     uint32_t n_brdfs;      const SptBrdfTable *brdfs;
     uint32_t n_brdf_nodes; const SptKdNode *brdf_nodes;
     const float *brdf_spectra;      /* n_brdf_nodes rows of SPT_BAND_PITCH */
+    uint64_t n_merl_floats; const float *merl_rgb;      /* half-angle tables, 3 floats per entry (SptBrdfTable::rgb_offset) */
 } SptSceneDesc;
 
 /* PerspectiveCamera (src/cameras/perspective.cpp:33-106, src/core/camera.cpp:84-103). */
@@ -284,6 +295,10 @@ typedef struct SptStats {
     int32_t  lanes_used;            /* last spt_render: streams the waves were dealt to; with more than one, kernels of the
                                        lanes overlap and class_ms sums per-lane event deltas (can exceed render_ms) */
     int32_t  pad_;
+    /* last spt_render: the FIRST launch of each class (the first wave's bounce 0: camera rays, first vertices) - one well-defined
+     * launch per kernel for roofline figures: its device time and the units (rays / vertices / samples) it processed */
+    double   first_launch_ms[SPT_K_CLASSES];
+    uint64_t first_launch_units[SPT_K_CLASSES];
 } SptStats;
 
 typedef struct SptScene SptScene;
@@ -308,6 +323,13 @@ void      spt_scene_destroy(SptScene *scene);
  * persistent trace kernel overlaps the other waves' work; lanes = 1 keeps everything on one stream (exact
  * per-kernel times). */
 int       spt_scene_set_lanes(SptScene *scene, int lanes);
+/* Traversal layout. EXACT (default): the reference's node order, slab and leaf arithmetic - first-hit ids
+ * and distances bit-identical to BVHAccel::Intersect/IntersectP. FAST: a 4-wide BVH collapsed from the same flattened tree
+ * (src/accelerators/bvh.cpp:354-372), children entered nearest first: the same primitive and the bit-identical distance
+ * wherever the closest hit is unique; ties between primitives at exactly equal distance and rays grazing a box edge may
+ * resolve differently. Built on the first switch to FAST (host side, from the nodes already in HBM). */
+enum { SPT_TRAVERSAL_EXACT = 0, SPT_TRAVERSAL_FAST = 1 };
+int       spt_scene_set_traversal(SptScene *scene, int mode);
 int       spt_scene_enable_counters(SptScene *scene, int on);
 int       spt_get_stats(SptScene *scene, SptStats *out);
 /* SptStats::render_ms of the last spt_render alone (spt_get_stats also folds ~80 per-launch event deltas into class_ms). */

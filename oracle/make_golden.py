@@ -283,6 +283,38 @@ def tiny_direct(w, h, spp, name, maxdepth=5):
     return set_filename(set_spp(set_res(s, w, h), spp), name)
 
 
+def synth_merl(dst):
+    """A MERL-format half-angle table (measured.cpp:122-170 reads: int dims[3] = 90, 90, 180, then per colour channel
+    90*90*180 doubles, which it scales by 1/1500, 1.15/1500, 1.66/1500): no such file ships with the reference, so an
+    analytic glossy lobe over a coloured diffuse base is written on the spot (own authoring). theta_h is sampled on the
+    format's square-root scale."""
+    import numpy as np
+    if os.path.exists(dst):
+        return
+    ih, idd, ip = np.meshgrid(np.arange(90), np.arange(90), np.arange(180), indexing="ij")
+    theta_h = ((ih + 0.5) / 90.0) ** 2 * (np.pi / 2)
+    theta_d = (idd + 0.5) / 90.0 * (np.pi / 2)
+    phi_d = (ip + 0.5) / 180.0 * np.pi
+    lobe = 6.0 * np.exp(-(theta_h / 0.12) ** 2) * (1.0 + 2.0 * (theta_d / (np.pi / 2)) ** 4)
+    aniso = 1.0 + 0.15 * np.cos(2 * phi_d)
+    os.makedirs(os.path.dirname(dst), exist_ok=True)
+    with open(dst, "wb") as f:
+        f.write(np.array([90, 90, 180], np.int32).tobytes())
+        for base, scale in ((0.55, 1.0 / 1500), (0.30, 1.15 / 1500), (0.18, 1.66 / 1500)):
+            brdf = base / np.pi + lobe * aniso
+            f.write((brdf / scale).astype(np.float64).tobytes())
+
+
+def tiny_merl(w, h, spp, name, maxdepth=5):
+    """Fixture for the half-angle (MERL) measured BRDF: the tiny scene with RegularHalfangleBRDF on the
+    plastic sphere."""
+    s = read(os.path.join(TESTS_GOLDEN, "tiny.pbrt"))
+    b = 'Material "plastic" "color Kd" [.45 .2 .15] "color Ks" [.5 .5 .5] "float roughness" [.04]'
+    assert b in s
+    s = s.replace(b, 'Material "measured" "string filename" "brdfs/synth_merl.binary"')
+    return set_filename(set_spp(set_res(s, w, h), spp), name)
+
+
 def tiny(w, h, spp, name, maxdepth=5):
     s = read(os.path.join(TESTS_GOLDEN, "tiny.pbrt"))
     return set_filename(set_spp(set_res(s, w, h), spp), name)
@@ -333,6 +365,8 @@ CONFIGS = {
     # with nSpectralSamples = 30 (oracle/Makefile ref30 -> oracle/_ref/bin30); BANDS30 below routes these to that build
     "killeroo_path30":  (killeroo, 700, 700, 64, 0, 0, 0),
     "killeroo_small30": (killeroo, 176, 176, 4, 6000, 40, 1024),
+    # the half-angle (MERL) measured BRDF on the tiny scene; the 17 MB table keeps it out of tests/golden
+    "tiny_merl_small": (tiny_merl, 64, 64, 4, 1500, 40, 32768),
     # small committed fixture
     "tiny":            (tiny, 48, 48, 4, 700, 40, 0),
     # two more committed fixtures (tests/golden/): extended materials, directlighting
@@ -523,6 +557,31 @@ def share_arrays(path, donor, keys=("tex_texels",)):
         save_container(path, a)
 
 
+# scene files that repeat the geometry of a bench workload (other materials / integrator): every array over 256 KB that is
+# byte-identical in the donor becomes a "<array>@" reference - the snapshot shipped to the GPU box is capped at 512 MiB
+SHARE_DONOR = {"bunny_direct_small": "bunny_path", "bunny_measured_small": "bunny_path", "killeroo_direct_one_small": "killeroo_path",
+               "specular_small": "killeroo_path", "bunny_shipped": "bunny_path", "killeroo_direct": "killeroo_path", "killeroo_path30": "killeroo_path"}
+
+
+def share_all(path, donor):
+    if not (os.path.exists(path) and os.path.exists(donor)):
+        return
+    sys.path.insert(0, REPO)
+    import numpy as np
+    from pbrt_v2_spectral_b200.scene_io import load_container, save_container
+    a, b = load_container(path), load_container(donor)
+    if "base_scene" in a or "base_scene" in b:
+        return
+    changed = False
+    for k in list(a):
+        if not k.endswith("@") and k in b and a[k].nbytes > (1 << 18) and a[k].dtype == b[k].dtype and a[k].shape == b[k].shape and np.array_equal(a[k], b[k]):
+            del a[k]
+            a[k + "@"] = np.frombuffer(os.path.relpath(donor, os.path.dirname(path)).encode(), np.uint8)
+            changed = True
+    if changed:
+        save_container(path, a)
+
+
 def with_gpupath(s):
     return s.replace("WorldBegin", 'Renderer "gpupath"\nWorldBegin', 1)
 
@@ -561,12 +620,14 @@ def main():
             if not os.path.exists(pfm):
                 exr_to_pfm(os.path.join(REF, "scenes", "textures", tex + ".exr"), pfm)
     tiny_pattern_pfm(os.path.join(SCENES, "textures", "tiny_pattern.pfm"))
+    if any(n.startswith("tiny_merl") for n in names):
+        synth_merl(os.path.join(SCENES, "brdfs", "synth_merl.binary"))
     for name in names:
         build, w, h, spp, npix, nrng, img_spp = CONFIGS[name]
         s = build(w, h, spp, name)
         write(os.path.join(SCENES, name + ".pbrt"), s)
         write(os.path.join(SCENES, name + ".gpu.pbrt"), with_gpupath(s))
-        prefix = os.path.join(TESTS_GOLDEN if name.startswith("tiny") or name in COMMITTED else GOLDEN, name)
+        prefix = os.path.join(TESTS_GOLDEN if (name.startswith("tiny") and not name.endswith("_small")) or name in COMMITTED else GOLDEN, name)
         env = dict(os.environ, SPT_DUMP_PREFIX=prefix, SPT_DUMP_PIXELS=str(max(npix, 1)),
                    SPT_DUMP_NRNG=str(max(nrng, 1)), SPT_DUMP_LI="1" if npix else "0",
                    SPT_DUMP_COMPACT="1" if name in COMPACT else "0")
@@ -595,6 +656,8 @@ def main():
                 with open(prefix + ext + ".xz", "wb") as f:
                     f.write(lzma.compress(raw, preset=9 | lzma.PRESET_EXTREME))
                 os.remove(prefix + ext)
+        if name in SHARE_DONOR:
+            share_all(os.path.join(LOWERED if not npix else GOLDEN, name + ".spt"), os.path.join(LOWERED, SHARE_DONOR[name] + ".spt"))
         print("%-16s lowered + golden in %.1fs" % (name, time.time() - t0), flush=True)
         if name.startswith("synth"):                 # tens of MB of text per scene: regenerable, not shipped
             for f in (name + ".pbrt", name + ".gpu.pbrt"):

@@ -869,8 +869,35 @@ static void kd_lookup(const SptKdNode *nodes, const float *spectra, uint32_t nNo
     }
 }
 static float spherical_phi(v3 v);
+static void from_rgb_refl(const SptSpectralTables *t, const float rgb[3], float *r);
+/* RegularHalfangleBRDF::f (reflection.cpp:267-300), added into out[NB]: M_PI is the float constant of pbrt.h */
+static void halfangle_f(const SptSceneDesc *sc, const SptBrdfTable *t, v3 wo, v3 wi, float *out) {
+    v3 wh = vadd(wo, wi);
+    if (wh.z < 0.f) { wo = vneg(wo); wi = vneg(wi); wh = vneg(wh); }
+    if (wh.x == 0.f && wh.y == 0.f && wh.z == 0.f) return;
+    wh = normalize(wh);
+    float whTheta = acosf(clampf(wh.z, -1.f, 1.f));
+    float whCosPhi = cos_phi(wh), whSinPhi = sin_phi(wh);
+    float whCosTheta = wh.z, whSinTheta = sin_theta(wh);
+    v3 whx = V(whCosPhi * whCosTheta, whSinPhi * whCosTheta, -whSinTheta);
+    v3 why = V(-whSinPhi, whCosPhi, 0.f);
+    v3 wd = V(dot(wi, whx), dot(wi, why), dot(wi, wh));
+    float wdTheta = acosf(clampf(wd.z, -1.f, 1.f)), wdPhi = spherical_phi(wd);
+    if (wdPhi > PI_F) wdPhi -= PI_F;
+    int nH = (int)t->n_theta_h, nD = (int)t->n_theta_d, nP = (int)t->n_phi_d;
+#define REMAP(V_, MAX_, COUNT_) clampi((int)((V_) / (MAX_) * (COUNT_)), 0, (COUNT_) - 1)
+    int ih = REMAP(sqrtf(stdmaxf(0.f, whTheta / (PI_F / 2.f))), 1.f, nH);
+    int id = REMAP(wdTheta, PI_F / 2.f, nD);
+    int ip = REMAP(wdPhi, PI_F, nP);
+#undef REMAP
+    const float *e = sc->merl_rgb + t->rgb_offset + 3 * (size_t)(ip + nP * (id + ih * nD));
+    float s[NB];
+    from_rgb_refl(&sc->tables, e, s);
+    for (int c = 0; c < NB; ++c) out[c] += s[c];
+}
 /* IrregIsotropicBRDF::f (reflection.cpp:251-263) over BRDFRemap (:239-248), added into out[NB] */
 static void measured_f(const SptSceneDesc *sc, const SptBrdfTable *t, v3 wo, v3 wi, float *out) {
+    if (t->n_nodes == 0) { halfangle_f(sc, t, wo, wi, out); return; }
     float cosi = wi.z, coso = wo.z;
     float sini = sqrtf(stdmaxf(0.f, 1.f - wi.z * wi.z)), sino = sqrtf(stdmaxf(0.f, 1.f - wo.z * wo.z));
     float phii = spherical_phi(wi), phio = spherical_phi(wo);

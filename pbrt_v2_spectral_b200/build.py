@@ -8,7 +8,8 @@ Three translation units, two floating-point regimes:
                  in places (1 - cos of a small cone angle in the sphere-light pdf), so radiance only tracks the
                  reference to 2e-4 per sample when the rounding sequence is the same; FMA bought 5 % of one kernel.
   spt_api.cu     host side of the C ABI (no kernels).
-  spt_build.cu   scene re-layout kernels run once per spt_scene_create (pair nodes, leaf flags, vertex pre-gather)."""
+  spt_build.cu   scene re-layout kernels run once per spt_scene_create (pair nodes, leaf flags, vertex pre-gather).
+  spt_wide.cu    host-side builder of the fast (4-wide) traversal layout, no kernels."""
 import os
 import subprocess
 import sys
@@ -22,7 +23,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libspt.so")
 OBJ = os.path.join(HERE, "build")
 UNITS = [("spt_exact.cu", ["-fmad=false"]), ("spt_shade.cu", ["-fmad=false"]), ("spt_api.cu", ["-fmad=false"]),
-         ("spt_build.cu", ["-fmad=false"])]
+         ("spt_build.cu", ["-fmad=false"]), ("spt_wide.cu", [])]
 DEPS = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "spt.h")]
 COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
           "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]

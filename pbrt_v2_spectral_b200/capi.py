@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("SPT_LIB") or os.path.join(HERE, "libspt.so" if D.NBAN
 # every symbol include/spt.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "spt_nbands", "spt_last_error", "spt_device_count", "spt_set_device", "spt_host_alloc", "spt_host_free", "spt_trim",
-    "spt_scene_create", "spt_scene_destroy", "spt_scene_enable_counters", "spt_scene_set_lanes", "spt_get_stats", "spt_last_render_ms",
+    "spt_scene_create", "spt_scene_destroy", "spt_scene_set_traversal", "spt_scene_enable_counters", "spt_scene_set_lanes", "spt_get_stats", "spt_last_render_ms",
     "spt_camera_rays", "spt_trace_closest", "spt_trace_any", "spt_trace_closest_dev", "spt_trace_any_dev",
     "spt_shade_samples",
     "spt_film_create", "spt_film_create_external", "spt_film_destroy", "spt_film_clear",
@@ -52,6 +52,7 @@ def lib():
         L.spt_scene_create.argtypes = [C.POINTER(D.SptSceneDesc)]
         L.spt_scene_destroy.argtypes = [C.c_void_p]
         L.spt_scene_enable_counters.argtypes = [C.c_void_p, C.c_int]
+        L.spt_scene_set_traversal.argtypes = [C.c_void_p, C.c_int]
         L.spt_scene_set_lanes.argtypes = [C.c_void_p, C.c_int]
         L.spt_get_stats.argtypes = [C.c_void_p, C.POINTER(D.SptStats)]
         L.spt_last_render_ms.restype = C.c_double
@@ -179,6 +180,10 @@ class Scene:
             v = getattr(st, k)
             out[k] = list(v) if hasattr(v, "__len__") else v
         return out
+
+    def set_traversal(self, fast):
+        """fast = False: the bit-exact pair-node walk (default); True: the 4-wide fast layout (include/spt.h)."""
+        _check(lib().spt_scene_set_traversal(self.h, 1 if fast else 0))
 
     def trace_closest(self, rays):
         r = np.ascontiguousarray(rays, np.float32)

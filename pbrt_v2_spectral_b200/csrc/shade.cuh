@@ -622,7 +622,34 @@ __device__ __forceinline__ float spherical_phi(v3 v) { float p = atan2f(v.y, v.x
 // IrregIsotropicBRDF::f (reflection.cpp:251-263): radius search around BRDFRemap(wo, wi) (:239-248) in the reference's
 // kd-tree (kdtree.h:143-168: children first, then the node - the same order, so the same sums up to the rounding of expf),
 // the radius doubling until three samples are found; v = sum of weight * sample spectrum, clamped, over the sum of weights.
+__device__ __forceinline__ float refl_band(const SptSpectralTables &t, const IllumCoefs &k, int c);
+// RegularHalfangleBRDF::f (reflection.cpp:267-300): the entry of the theta_h / theta_d / phi_d table the half-angle
+// parameterisation of (wo, wi) falls in, an RGB triple turned into a spectrum by FromRGB(.., SPECTRUM_REFLECTANCE)
+__device__ inline void halfangle_f(const DevScene &sc, const SptBrdfTable &t, v3 wo, v3 wi, float *v) {
+    v3 wh = vadd(wo, wi);
+    if (wh.z < 0.f) { wo = vneg(wo); wi = vneg(wi); wh = vneg(wh); }
+    if (wh.x == 0.f && wh.y == 0.f && wh.z == 0.f) { for (int c = 0; c < NB; ++c) v[c] = 0.f; return; }
+    wh = normalize(wh);
+    const float whTheta = spherical_theta(wh);
+    const float whCosPhi = cos_phi(wh), whSinPhi = sin_phi(wh);
+    const float whCosTheta = wh.z, whSinTheta = sin_theta(wh);
+    const v3 whx = V(whCosPhi * whCosTheta, whSinPhi * whCosTheta, -whSinTheta);
+    const v3 why = V(-whSinPhi, whCosPhi, 0.f);
+    const v3 wd = V(dot(wi, whx), dot(wi, why), dot(wi, wh));
+    const float wdTheta = spherical_theta(wd);
+    float wdPhi = spherical_phi(wd);
+    if (wdPhi > PI_F) wdPhi -= PI_F;
+    const int nH = (int)t.n_theta_h, nD = (int)t.n_theta_d, nP = (int)t.n_phi_d;
+    const int ih = clampi((int)(sqrtf(stdmaxf(0.f, whTheta / (PI_F / 2.f))) / 1.f * nH), 0, nH - 1);
+    const int id = clampi((int)(wdTheta / (PI_F / 2.f) * nD), 0, nD - 1);
+    const int ip = clampi((int)(wdPhi / PI_F * nP), 0, nP - 1);
+    const float *e = sc.merl_rgb + t.rgb_offset + 3 * (size_t)(ip + nP * (id + ih * nD));
+    const float rgb[3] = { __ldg(e), __ldg(e + 1), __ldg(e + 2) };
+    const IllumCoefs k = illum_coefs(rgb);
+    for (int c = 0; c < NB; ++c) v[c] = refl_band(*sc.tables, k, c);
+}
 __device__ inline void measured_f(const DevScene &sc, const SptBrdfTable &t, v3 wo, v3 wi, float *v) {
+    if (t.n_nodes == 0) { halfangle_f(sc, t, wo, wi, v); return; }
     const float cosi = wi.z, coso = wo.z;
     const float sini = sin_theta(wi), sino = sin_theta(wo);
     const float phii = spherical_phi(wi), phio = spherical_phi(wo);

@@ -13,6 +13,7 @@
 #include <thread>
 #include <vector>
 #include "launch.h"
+#include "wide.h"
 
 struct SptScene;
 static void collect_class_times(SptScene *s);
@@ -110,6 +111,9 @@ struct SptScene {
     DevScene dev;
     std::vector<uint32_t> prim_id_host;
     uint32_t *prim_id_dev = nullptr;
+    DevMem wide_mem;                 // fast traversal layout (wide.h), built on the first spt_scene_set_traversal(FAST)
+    float4 *wnodes = nullptr;
+    uint32_t wroot = 0xffffffffu;
     bool counters_on = false;
     int trace_variant = 1;           // trace_kernels.cuh: 0 reference nodes, 1 pair nodes (default)
     uint32_t fetch_threshold = 14;
@@ -404,11 +408,18 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
     UP(v.textures, d->textures, d->n_textures); UP(v.tex_texels, d->tex_texels, d->n_texels);
     UP(v.ewa_lut, d->ewa_weight_lut, d->ewa_weight_lut ? 128 : 0);
     for (uint32_t b = 0; b < d->n_brdfs; ++b)
-        if ((uint64_t)d->brdfs[b].node_first + d->brdfs[b].n_nodes > d->n_brdf_nodes || d->brdfs[b].n_nodes == 0 || d->brdfs[b].n_nodes > (1u << 16)) {
+        if (d->brdfs[b].n_nodes == 0) {      // half-angle table
+            const SptBrdfTable &t = d->brdfs[b];
+            const uint64_t n = (uint64_t)t.n_theta_h * t.n_theta_d * t.n_phi_d;
+            if (n == 0 || t.n_theta_h > 4096 || t.n_theta_d > 4096 || t.n_phi_d > 4096 || t.rgb_offset + 3 * n > d->n_merl_floats || !d->merl_rgb) {
+                g_err = "malformed half-angle BRDF table"; s->mem.release(); delete s; return nullptr;
+            }
+        } else if ((uint64_t)d->brdfs[b].node_first + d->brdfs[b].n_nodes > d->n_brdf_nodes || d->brdfs[b].n_nodes > (1u << 16)) {
             g_err = "malformed BRDF table"; s->mem.release(); delete s; return nullptr;       // 2^16 nodes: the look-up's stack of 32 covers depth 16
         }
     UP(v.brdfs, d->brdfs, d->n_brdfs); UP(v.brdf_nodes, d->brdf_nodes, d->n_brdf_nodes);
     UP(v.brdf_spectra, d->brdf_spectra, (size_t)d->n_brdf_nodes * NBP);
+    UP(v.merl_rgb, d->merl_rgb, (size_t)d->n_merl_floats);
     UP(v.light_shapes, d->light_shapes, d->n_light_shapes);
     UP(v.light_cdf, cdf.data(), cdf.size());
     v.n_lights = d->n_lights;
@@ -455,6 +466,7 @@ void spt_scene_destroy(SptScene *s) {
     DeviceGuard dg(s->device);
     cudaDeviceSynchronize();
     s->mem.release();
+    s->wide_mem.release();
     s->trace_scratch.release();
     s->counts_mem.release();
     for (auto &ln : s->lane) { ln.mem.release(); if (ln.stream) cudaStreamDestroy(ln.stream); }
@@ -473,6 +485,26 @@ int spt_scene_enable_counters(SptScene *s, int on) {
     CU(cudaMemset(s->counters, 0, 32));
     s->stats.node_visits_closest = s->stats.prim_tests_closest = 0;
     s->stats.node_visits_any = s->stats.prim_tests_any = 0;
+    return SPT_OK;
+}
+
+int spt_scene_set_traversal(SptScene *s, int mode) {
+    if (!s || (mode != SPT_TRAVERSAL_EXACT && mode != SPT_TRAVERSAL_FAST)) return fail(SPT_ERR_ARG, "unknown traversal mode");
+    DeviceGuard dg(s->device);
+    CU(cudaDeviceSynchronize());
+    if (mode == SPT_TRAVERSAL_EXACT) { s->dev.wnodes = nullptr; return SPT_OK; }
+    if (s->trace_variant == 0) return fail(SPT_ERR_UNSUPP, "this tree does not pack into child codes (leaves of more than 8 primitives): exact traversal only");
+    if (!s->wnodes) {
+        // collapse the reference's binary tree (already in HBM, leaf flags set by the re-layout) into 4-wide nodes on the host
+        std::vector<uint8_t> ref((size_t)s->dev.n_nodes * 32);
+        CU(cudaMemcpy(ref.data(), s->dev.nodes, ref.size(), cudaMemcpyDeviceToHost));
+        std::vector<W4Node> wide;
+        if (!spt_build_w4(ref.data(), s->dev.n_nodes, &wide, &s->wroot)) return fail(SPT_ERR_UNSUPP, "the BVH does not collapse into the wide layout");
+        static_assert(sizeof(W4Node) == 128, "W4Node is 8 x float4");
+        s->wnodes = s->wide_mem.upload((const float4 *)wide.data(), wide.size() * 8);
+        if (!s->wnodes) return fail(SPT_ERR_CUDA, "out of device memory for the wide BVH");
+    }
+    s->dev.wnodes = s->wnodes; s->dev.wroot = s->wroot;
     return SPT_OK;
 }
 
@@ -627,11 +659,17 @@ static void run_wave(SptScene *s, const RenderCfg &cfg, const SampleSource &src,
 static void collect_class_times(SptScene *s) {
     s->class_times_pending = false;
     cudaEvent_t last[SPT_MAX_LANES] = {};
+    bool seen[SPT_K_CLASSES] = {};
     for (size_t k = 0; k < s->ev_used; ++k) {
         const SptScene::Mark &m = s->marks[k];
         if (m.cls >= 0 && last[m.lane]) {
             float ms = 0.f;
-            if (cudaEventElapsedTime(&ms, last[m.lane], m.e) == cudaSuccess) s->stats.class_ms[m.cls] += ms;
+            if (cudaEventElapsedTime(&ms, last[m.lane], m.e) == cudaSuccess) {
+                s->stats.class_ms[m.cls] += ms;
+                // SPT_K_SHADE's first mark is the hit compaction; the kernel itself is the class's longest launch of bounce 0
+                if (!seen[m.cls] || (m.cls == SPT_K_SHADE && m.lane == 0 && k < 8 && ms > s->stats.first_launch_ms[m.cls])) s->stats.first_launch_ms[m.cls] = ms;
+                seen[m.cls] = true;
+            }
         }
         last[m.lane] = m.e;
     }
@@ -639,7 +677,10 @@ static void collect_class_times(SptScene *s) {
 }
 static void reset_class_stats(SptScene *s) {
     s->class_times_pending = false;
-    for (int k = 0; k < SPT_K_CLASSES; ++k) { s->stats.class_ms[k] = 0.; s->stats.class_launches[k] = 0; s->stats.class_rays[k] = 0; }
+    for (int k = 0; k < SPT_K_CLASSES; ++k) {
+        s->stats.class_ms[k] = 0.; s->stats.class_launches[k] = 0; s->stats.class_rays[k] = 0;
+        s->stats.first_launch_ms[k] = 0.; s->stats.first_launch_units[k] = 0;
+    }
     s->stats.mis_rays_elided = 0; s->stats.first_vertices = 0;
     s->ev_used = 0;
 }
@@ -1066,6 +1107,11 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
     s->stats.class_rays[SPT_K_GEN] = samples; s->stats.class_rays[SPT_K_FILM] = samples;
     s->stats.camera_samples += samples;
     add_ray_stats(s, hc, depth, n_waves);
+    {   // the first wave's bounce 0: what the first launch of each class worked on (sample slots incl. the few that overhang the extent)
+        uint64_t *u = s->stats.first_launch_units;
+        u[SPT_K_GEN] = hc[0]; u[SPT_K_FILM] = hc[0]; u[SPT_K_TRACE_PATH] = hc[0];
+        u[SPT_K_SHADE] = hc[3]; u[SPT_K_ACCUMULATE] = hc[3]; u[SPT_K_ADVANCE] = hc[3];
+    }
     const uint64_t overhang = slots > samples ? slots - samples : 0;
     s->stats.closest_rays -= overhang;
     s->stats.class_rays[SPT_K_TRACE_PATH] -= overhang;

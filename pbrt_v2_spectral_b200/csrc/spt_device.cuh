@@ -92,6 +92,8 @@ struct DevScene {
     const float4 *nodes;
     const float4 *pnodes;            // pair nodes: 4 x float4 per interior node (both children's bounds + codes)
     uint32_t root_code;              // child code of the root
+    const float4 *wnodes;            // fast mode (wide.h): 8 x float4 per 4-wide node; NULL until spt_scene_set_traversal(FAST)
+    uint32_t wroot;                  // its root's child code
     const float4 *tri_verts;
     uint32_t n_nodes, n_prims;
     const uint8_t *prim_kind, *prim_flags;
@@ -121,6 +123,7 @@ struct DevScene {
     const SptBrdfTable *brdfs;
     const SptKdNode *brdf_nodes;
     const float *brdf_spectra;
+    const float *merl_rgb;           // half-angle (MERL) tables: RGB triples
     int has_measured;
     unsigned long long *counters;    // closest: [0] nodes, [1] prim tests; any-hit: [2], [3] (NULL when disabled)
 };

@@ -81,7 +81,11 @@ void spt_launch_gen_camera(int grid, cudaStream_t st, const RenderCfg &cfg, cons
     k_gen_camera<<<grid, 256, 0, st>>>(cfg, src, wb, count_out);
 }
 static void launch_multi(bool count, int grid, cudaStream_t st, const DevScene &sc, const TraceMultiArgs &a) {
-    if (count) k_trace_multi<true><<<grid, 128, 0, st>>>(sc, a); else k_trace_multi<false><<<grid, 128, 0, st>>>(sc, a);
+    if (sc.wnodes) {        // fast mode (wide.h): the scene opted in with spt_scene_set_traversal
+        if (count) k_trace_multi<true, true><<<grid, 128, 0, st>>>(sc, a); else k_trace_multi<false, true><<<grid, 128, 0, st>>>(sc, a);
+    } else {
+        if (count) k_trace_multi<true, false><<<grid, 128, 0, st>>>(sc, a); else k_trace_multi<false, false><<<grid, 128, 0, st>>>(sc, a);
+    }
 }
 void spt_launch_trace_multi(int variant, bool merge, bool count, int grid, cudaStream_t st, const DevScene &sc, const TraceMultiArgs &a) {
     if (variant != 0 && merge) { launch_multi(count, grid, st, sc, a); return; }

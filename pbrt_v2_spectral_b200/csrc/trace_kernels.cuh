@@ -182,6 +182,7 @@ __device__ __forceinline__ bool slab6_finite(float x0, float x1, float y0, float
 // previous bounce's shadow and MIS rays), so a wavefront bounce pays for ONE persistent kernel's drain instead of three or four.
 //
 #define PN_LEAF 0x80000000u
+#define W4_EMPTY_CODE 0xffffffffu
 template <typename T> __device__ __forceinline__ T seg_sel(uint32_t k, T a, T b, T c, T d) { return k == 0 ? a : (k == 1 ? b : (k == 2 ? c : d)); }
 
 // Warp organisation: one loop - every iteration a lane pops if it must, takes one pair step if it holds an interior node,
@@ -190,7 +191,8 @@ template <typename T> __device__ __forceinline__ T seg_sel(uint32_t k, T a, T b,
 // reconverges, leaves are tested together) 43.8 ms against 40.9 ms, batched leaves (a leaf phase once 4-16 lanes hold a leaf)
 // 41.8-45.1 ms; keeping the first 8 or 16 stack entries of a lane in shared memory ([entry][thread], conflict-free) instead
 // of local memory: 45.7 against 44.3 ms. The L1-served local stack and the plain loop won, so they are what is left.
-template <bool COUNT>
+// WIDE: the fast layout of wide.h instead of the pair nodes - four children per step, nearest first; NOT the parity path.
+template <bool COUNT, bool WIDE>
 __global__ void __launch_bounds__(128) k_trace_multi(DevScene sc, TraceMultiArgs a) {
     uint2 stk[64];                  // the 64-entry todo stack (bvh.cpp:384): {child code, tmin of its slab test at push time}
     const uint32_t e0 = *a.seg[0].count;
@@ -240,6 +242,43 @@ __global__ void __launch_bounds__(128) k_trace_multi(DevScene sc, TraceMultiArgs
         const bool nearHit = swap ? h1 : h0, farHit = swap ? h0 : h1;
         if (farHit) stk[sp++] = make_uint2(farC, __float_as_uint(swap ? t0 : t1));
         cur = nearHit ? nearC : PN_NONE;
+    };
+    // fast layout: one step tests the four children of the wide node `cur` (a slab plane is one fused multiply-add:
+    // b * invDir - o * invDir), enters the nearest one and pushes the others farthest first
+    v3 noid = V(0, 0, 0);            // -o * invDir
+    auto wide_step = [&]() {
+        const float4 *wn = sc.wnodes + 8 * (size_t)cur;
+        const float4 lx = __ldg(wn), ly = __ldg(wn + 1), lz = __ldg(wn + 2), hx = __ldg(wn + 3), hy = __ldg(wn + 4), hz = __ldg(wn + 5);
+        const float4 cc = __ldg(wn + 6);
+        if (COUNT) { if (isAny) cnA += 4; else cn += 4; }
+        float tn[4]; uint32_t cd[4];
+#define W4_CHILD(i, LX, HX, LY, HY, LZ, HZ, C) do { \
+            const float ax = fmaf(LX, invDir.x, noid.x), bx = fmaf(HX, invDir.x, noid.x); \
+            const float ay = fmaf(LY, invDir.y, noid.y), by = fmaf(HY, invDir.y, noid.y); \
+            const float az = fmaf(LZ, invDir.z, noid.z), bz = fmaf(HZ, invDir.z, noid.z); \
+            const float tnear = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), ray.mint)); \
+            const float tfar = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), ray.maxt)); \
+            cd[i] = __float_as_uint(C); tn[i] = (tnear <= tfar && cd[i] != W4_EMPTY_CODE) ? tnear : SPT_INF; } while (0)
+        W4_CHILD(0, lx.x, hx.x, ly.x, hy.x, lz.x, hz.x, cc.x);
+        W4_CHILD(1, lx.y, hx.y, ly.y, hy.y, lz.y, hz.y, cc.y);
+        W4_CHILD(2, lx.z, hx.z, ly.z, hy.z, lz.z, hz.z, cc.z);
+        W4_CHILD(3, lx.w, hx.w, ly.w, hy.w, lz.w, hz.w, cc.w);
+#undef W4_CHILD
+        if (!isAny) {
+            // sorting network on (entry distance, code): nearest first; a miss carries +inf and sinks to the end
+#define W4_SWAP(i, j) do { if (tn[j] < tn[i]) { const float t_ = tn[i]; tn[i] = tn[j]; tn[j] = t_; const uint32_t c_ = cd[i]; cd[i] = cd[j]; cd[j] = c_; } } while (0)
+            W4_SWAP(0, 1); W4_SWAP(2, 3); W4_SWAP(0, 2); W4_SWAP(1, 3); W4_SWAP(1, 2);
+#undef W4_SWAP
+        }
+        // enter the first (nearest) child that was hit, push the others so that the nearer ones come off the stack first
+        cur = PN_NONE;
+        float tcur = 0.f;
+#pragma unroll
+        for (int i = 3; i >= 0; --i) {
+            if (tn[i] == SPT_INF) continue;
+            if (cur != PN_NONE) stk[sp++] = make_uint2(cur, __float_as_uint(tcur));
+            cur = cd[i]; tcur = tn[i];
+        }
     };
     // the primitives of the leaf `cur`, in slot order; true when an any-hit ray is finished
     auto leaf_step = [&]() -> bool {
@@ -305,6 +344,17 @@ __global__ void __launch_bounds__(128) k_trace_multi(DevScene sc, TraceMultiArgs
                         negMask = (negx ? 1u : 0u) | (negy ? 2u : 0u) | (negz ? 4u : 0u);
                         exact = !(isfinite(invDir.x) && isfinite(invDir.y) && isfinite(invDir.z));
                         best = SPT_MISS; sp = 0; cur = PN_NONE; active = true;
+                        if (WIDE) {
+                            // a direction component of (almost) zero: a huge finite reciprocal keeps b * invDir - o * invDir free of
+                            // inf - inf; the slab of that axis then only excludes boxes the origin lies outside of
+                            const float tiny = 1e-18f;
+                            if (fabsf(ray.d.x) < tiny) invDir.x = copysignf(1.f / tiny, ray.d.x);
+                            if (fabsf(ray.d.y) < tiny) invDir.y = copysignf(1.f / tiny, ray.d.y);
+                            if (fabsf(ray.d.z) < tiny) invDir.z = copysignf(1.f / tiny, ray.d.z);
+                            noid = V(-ray.o.x * invDir.x, -ray.o.y * invDir.y, -ray.o.z * invDir.z);
+                            cur = sc.wroot == W4_EMPTY_CODE ? PN_NONE : sc.wroot;
+                            if (COUNT) { if (isAny) ++cnA; else ++cn; }
+                        } else
                         // the root: the one node whose own box is tested from the reference array
                         if (sc.n_nodes) {
                             const float4 n0 = __ldg(&sc.nodes[0]), n1 = __ldg(&sc.nodes[1]);
@@ -320,7 +370,7 @@ __global__ void __launch_bounds__(128) k_trace_multi(DevScene sc, TraceMultiArgs
         while (active) {
             bool done = false;
             if (cur == PN_NONE) done = pop();
-            if (!done && cur < PN_LEAF) node_step();
+            if (!done && cur < PN_LEAF) { if (WIDE) wide_step(); else node_step(); }
             if (!done && cur >= PN_LEAF && cur != PN_NONE) done = leaf_step();
             if (done) finish();
             if (active && !exhausted && (uint32_t)__popc(__activemask()) < a.fetch_threshold) break;

@@ -38,6 +38,7 @@ class SptSceneDesc(C.Structure):
         ("ewa_weight_lut", C.c_void_p),
         ("n_brdfs", C.c_uint32), ("brdfs", C.c_void_p),
         ("n_brdf_nodes", C.c_uint32), ("brdf_nodes", C.c_void_p), ("brdf_spectra", C.c_void_p),
+        ("n_merl_floats", C.c_uint64), ("merl_rgb", C.c_void_p),
     ]
 
 
@@ -83,7 +84,8 @@ class SptStats(C.Structure):
                 ("render_ms", C.c_double), ("trace_ms", C.c_double),
                 ("class_ms", C.c_double * K_CLASSES), ("class_launches", C.c_uint64 * K_CLASSES),
                 ("class_rays", C.c_uint64 * K_CLASSES), ("mis_rays_elided", C.c_uint64), ("first_vertices", C.c_uint64),
-                ("lanes_used", C.c_int32), ("pad_", C.c_int32)]
+                ("lanes_used", C.c_int32), ("pad_", C.c_int32),
+                ("first_launch_ms", C.c_double * K_CLASSES), ("first_launch_units", C.c_uint64 * K_CLASSES)]
 
 
 # row sizes of the table structs (bytes), for sanity checks against the container file
@@ -91,7 +93,7 @@ SIZEOF_QUADRIC = 32
 SIZEOF_XFORM = 128
 SIZEOF_MATERIAL = 16 + 2 * 4 * BAND_PITCH + 16
 SIZEOF_TEXTURE = 64
-SIZEOF_BRDF_TABLE = 8
+SIZEOF_BRDF_TABLE = 32
 SIZEOF_KD_NODE = 32
 SIZEOF_LIGHT = 32 + 4 * BAND_PITCH + 16
 SIZEOF_LIGHT_SHAPE = 16

@@ -138,6 +138,7 @@ SptSceneDesc LoweredScene::Desc() const {
     d.n_brdf_nodes = (uint32_t)brdf_nodes.size();
     d.brdf_nodes = ptr_or_null(brdf_nodes);
     d.brdf_spectra = ptr_or_null(brdf_spectra);
+    d.n_merl_floats = merl_rgb.size(); d.merl_rgb = ptr_or_null(merl_rgb);
     return d;
 }
 
@@ -179,6 +180,7 @@ bool LoweredScene::Save(const std::string &path, std::string *err) const {
     w.pod("brdfs", brdfs);
     w.pod("brdf_nodes", brdf_nodes);
     w.vec("brdf_spectra", 3, brdf_spectra);
+    w.vec("merl_rgb", 3, merl_rgb);
     w.put("camera", 0, &camera, sizeof(camera), 1, sizeof(camera));
     w.put("film", 0, &film, sizeof(film), 1, sizeof(film));
     w.put("params", 0, &params, sizeof(params), 1, sizeof(params));
@@ -399,12 +401,30 @@ struct Lowerer {
         if (const MeasuredMaterial *ms = dynamic_cast<const MeasuredMaterial *>(m)) {
             // measured.cpp:185-205: IrregIsotropicBRDF over the kd-tree of a theta-phi (.brdf) file
             if (!BumpParam(ms->bumpMap, ms->normalMap, &row.tex_bump)) return false;
-            if (ms->regularHalfangleData || !ms->thetaPhiData) return fail("measured material: only theta-phi (.brdf) data is supported");
             row.type = SPT_MAT_MEASURED;
+            if (ms->regularHalfangleData) {
+                // measured.cpp:122-170: the MERL table as the reference loaded it (scaled, clamped at zero), entry for entry
+                const void *key = (const void *)ms->regularHalfangleData;
+                std::map<const void *, int>::iterator hit = brdfIdx.find(key);
+                if (hit == brdfIdx.end()) {
+                    SptBrdfTable t;
+                    memset(&t, 0, sizeof(t));
+                    t.n_theta_h = ms->nThetaH; t.n_theta_d = ms->nThetaD; t.n_phi_d = ms->nPhiD;
+                    t.rgb_offset = out->merl_rgb.size();
+                    const size_t n = 3 * (size_t)ms->nThetaH * ms->nThetaD * ms->nPhiD;
+                    out->merl_rgb.insert(out->merl_rgb.end(), ms->regularHalfangleData, ms->regularHalfangleData + n);
+                    out->brdfs.push_back(t);
+                    brdfIdx[key] = (int)out->brdfs.size() - 1;
+                    hit = brdfIdx.find(key);
+                }
+                row.brdf = hit->second;
+            } else {
+            if (!ms->thetaPhiData) return fail("measured material without BRDF data");
             const KdTree<IrregIsotropicBRDFSample> *kd = ms->thetaPhiData;
             std::map<const void *, int>::iterator it = brdfIdx.find((const void *)kd);
             if (it == brdfIdx.end()) {
                 SptBrdfTable t;
+                memset(&t, 0, sizeof(t));
                 t.node_first = (uint32_t)out->brdf_nodes.size(); t.n_nodes = kd->nNodes;
                 for (uint32_t k = 0; k < kd->nNodes; ++k) {
                     SptKdNode n;
@@ -422,6 +442,7 @@ struct Lowerer {
                 it = brdfIdx.find((const void *)kd);
             }
             row.brdf = it->second;
+            }
         } else if (const MatteMaterial *mm = dynamic_cast<const MatteMaterial *>(m)) {
             float sig;
             if (!BumpParam(mm->bumpMap, mm->normalMap, &row.tex_bump) || !SpectrumParam(mm->Kd, row.spec0, &row.tex_kd, "Kd") ||

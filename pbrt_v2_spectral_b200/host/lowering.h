@@ -88,6 +88,7 @@ struct LoweredScene {
     std::vector<SptBrdfTable> brdfs;
     std::vector<SptKdNode> brdf_nodes;
     std::vector<float> brdf_spectra;
+    std::vector<float> merl_rgb;
 
     SptCameraDesc camera;
     SptFilmDesc film;

@@ -68,7 +68,7 @@ class LoweredScene:
         self.a = {k: np.ascontiguousarray(v) for k, v in arrays.items()}
         a = self.a
         for key, dt in (("textures", np.uint8), ("tex_texels", np.float32), ("ewa_weight_lut", np.float32),
-                        ("brdfs", np.uint8), ("brdf_nodes", np.uint8), ("brdf_spectra", np.float32)):
+                        ("brdfs", np.uint8), ("brdf_nodes", np.uint8), ("brdf_spectra", np.float32), ("merl_rgb", np.float32)):
             a.setdefault(key, np.zeros(0, dt))
         if int(a["nbands"][0]) != D.NBANDS:
             raise ValueError("scene has %d bands, library expects %d" % (int(a["nbands"][0]), D.NBANDS))
@@ -120,7 +120,7 @@ class LoweredScene:
         for k in ("prim_kind", "prim_flags", "prim_id", "prim_data", "prim_material", "prim_light", "prim_xform",
                   "tri_vidx", "P", "N", "UV", "quadrics", "xforms", "materials", "lights", "light_shapes",
                   "env_rgb", "env_func", "env_cdf", "env_func_int", "env_marg_func", "env_marg_cdf",
-                  "textures", "tex_texels", "ewa_weight_lut", "brdfs", "brdf_nodes", "brdf_spectra"):
+                  "textures", "tex_texels", "ewa_weight_lut", "brdfs", "brdf_nodes", "brdf_spectra", "merl_rgb"):
             setattr(d, k, self._ptr(k))
         d.n_tris = a["tri_vidx"].size // 3
         d.n_verts = a["P"].size // 3
@@ -136,6 +136,7 @@ class LoweredScene:
         d.n_texels = a["tex_texels"].size
         d.n_brdfs = a["brdfs"].size // D.SIZEOF_BRDF_TABLE
         d.n_brdf_nodes = a["brdf_nodes"].size // D.SIZEOF_KD_NODE
+        d.n_merl_floats = a["merl_rgb"].size
         return d
 
     @property

@@ -5,6 +5,7 @@
 #define SPT_HOST_SHIM 1
 #include "trace_kernels.cuh"
 #include "../../pbrt_v2_spectral_b200/csrc/spt_build.cu"
+#include "../../pbrt_v2_spectral_b200/csrc/spt_wide.cu"
 #include "camera.cuh"
 #include "sampler.cuh"
 #include <vector>
@@ -34,7 +35,7 @@ extern "C" {
 
 // rays: n x 8 {o, d, mint, maxt}; any = 0: closest hit (out_slot, out_t), 1: any hit (out_slot = SPT_MISS or a slot).
 // Returns 0, or -1 when the tree does not pack into pair nodes (the product then walks the reference layout).
-int hd_trace(const SptSceneDesc *d, const float *rays, uint32_t n, int any, uint32_t *out_slot, float *out_t) {
+int hd_trace(const SptSceneDesc *d, const float *rays, uint32_t n, int any, uint32_t *out_slot, float *out_t, int wide) {
     // ---- scene re-layout with the product's kernels: leaf flags, exclusive scan of the interior flags, pair nodes, vertices
     std::vector<RefNodeD> nodes(d->n_nodes);
     memcpy(nodes.data(), d->bvh_nodes, (size_t)d->n_nodes * 32);
@@ -54,6 +55,13 @@ int hd_trace(const SptSceneDesc *d, const float *rays, uint32_t n, int any, uint
     sc.prim_kind = d->prim_kind; sc.prim_flags = d->prim_flags; sc.prim_id = d->prim_id; sc.prim_data = d->prim_data;
     sc.prim_material = d->prim_material; sc.prim_light = d->prim_light; sc.prim_xform = d->prim_xform;
     sc.tri_vidx = d->tri_vidx; sc.P = d->P; sc.N = d->N; sc.UV = d->UV; sc.quadrics = d->quadrics; sc.xforms = d->xforms;
+    // wide != 0: the fast layout (csrc/wide.h), collapsed by the product's builder from the flagged reference nodes
+    std::vector<W4Node> wnodes;
+    if (wide) {
+        if (!spt_build_w4(nodes.data(), d->n_nodes, &wnodes, &sc.wroot)) return -2;
+        wnodes.push_back(W4Node());
+        sc.wnodes = (const float4 *)wnodes.data();
+    }
     // ---- the kernel itself, one lane
     std::vector<float4> ro(n), rd(n);
     for (uint32_t i = 0; i < n; ++i) {
@@ -69,7 +77,7 @@ int hd_trace(const SptSceneDesc *d, const float *rays, uint32_t n, int any, uint
     a.nseg = 2; a.work = &work; a.fetch_threshold = 14;
     a.seg[0].queue = nullptr; a.seg[0].count = &n0; a.seg[1].queue = q1.data(); a.seg[1].count = &n1;
     for (int k = 0; k < 2; ++k) { a.seg[k].ro = ro.data(); a.seg[k].rd = rd.data(); a.seg[k].out_slot = out_slot; a.seg[k].out_t = out_t; a.seg[k].any = any ? 1u : 0u; }
-    k_trace_multi<false>(sc, a);
+    if (wide) k_trace_multi<false, true>(sc, a); else k_trace_multi<false, false>(sc, a);
     return 0;
 }
 

@@ -61,6 +61,33 @@ def test_first_hits_at_baseline_resolution(rcase):
     assert np.array_equal(t.view(np.uint32), g["t_hit"].view(np.uint32))
 
 
+@pytest.mark.parametrize("rcase", RAY_CASES, ids=[c[0] for c in RAY_CASES])
+def test_fast_traversal_differs_only_on_ties(rcase):
+    """SURVEY 8f N1, the FAST traversal layout (include/spt.h: spt_scene_set_traversal): the 4-wide BVH collapsed from the
+    reference's flattened tree, on the camera rays of BASELINE configs 1 and 2 at full resolution. Where the closest hit is
+    unique it is the reference's primitive at the bit-identical distance; a difference must be a tie (another primitive at
+    the same distance to 1e-5) or a hit the reference's own box test dropped - none may be lost."""
+    name, sp, gp = rcase
+    lowered, g = O.load_case(sp, gp)
+    scene = capi.Scene(lowered)
+    rays = capi.camera_rays(lowered.camera, O.compact_samples(g))
+    scene.set_traversal(True)
+    slot, pid, t = scene.trace_closest(rays)
+    scene.set_traversal(False)
+    slot2, pid2, t2 = scene.trace_closest(rays[:65536])          # and back: the exact walk again
+    scene.close()
+    assert np.array_equal(pid2, g["prim_id"][:65536]) and np.array_equal(t2.view(np.uint32), g["t_hit"][:65536].view(np.uint32))
+    want_id, want_t = g["prim_id"], g["t_hit"]
+    diff = ~((pid == want_id) & (t.view(np.uint32) == want_t.view(np.uint32)))
+    with np.errstate(invalid="ignore"):
+        tie = diff & (pid != 0) & (want_id != 0) & (np.abs(t - want_t) <= 1e-5 * np.abs(want_t))
+        found_more = diff & (pid != 0) & ((want_id == 0) | (t < want_t))
+    print("%s: fast traversal differs on %d of %d rays (%d ties, %d hits the reference's box test dropped)" % (
+        name, diff.sum(), len(diff), tie.sum(), found_more.sum()))
+    assert not (diff & ~tie & ~found_more).any(), "fast traversal lost hits"
+    assert diff.mean() < 1e-3
+
+
 def test_secondary_rays(case):
     _, _, scene, g = case
     m = g["prim_id"] != 0
@@ -135,7 +162,8 @@ def test_film_wide_filter():
 
 
 RENDER_CASES = [c for c in CASES if c[0] in ("tiny", "metal_shipped_small", "ssenv_shipped_small", "killeroo_direct_small",
-                                             "bunny_direct_small", "bunny_shipped_small", "killeroo_direct_one_small")]
+                                             "bunny_direct_small", "bunny_shipped_small", "killeroo_direct_one_small", "bunny_measured_small",
+                                             "tiny_merl_small")]
 
 
 @pytest.mark.parametrize("rcase", RENDER_CASES, ids=[c[0] for c in RENDER_CASES])
