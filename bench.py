@@ -341,6 +341,8 @@ def main():
     class_rays = [0] * D.K_CLASSES
     elided = 0
     first_vertices = 0
+    first_ms = [0.0] * D.K_CLASSES                   # bounce-0 launch of each class: mean device time and units over the profiled frames
+    first_units = [0.0] * D.K_CLASSES
     serial_ms = 0.0
     prof_steps = max(1, min(args.steps, 5 if not args.workload.startswith("synth_10m") else 1))
     scene.set_lanes(1)
@@ -352,6 +354,8 @@ def main():
         serial_ms += st["render_ms"]
         elided += st["mis_rays_elided"]
         first_vertices += st["first_vertices"]
+        for k in range(D.K_CLASSES):
+            first_ms[k] += st["first_launch_ms"][k] / prof_steps; first_units[k] += st["first_launch_units"][k] / prof_steps
         for k in range(D.K_CLASSES):
             class_ms[k] += st["class_ms"][k]; class_launches[k] += st["class_launches"][k]; class_rays[k] += st["class_rays"][k]
     scene.set_lanes(int(os.environ.get("SPT_LANES", "4")))
@@ -470,13 +474,16 @@ def main():
 
     # ---- rooflines (algorithmic bytes per unit: SURVEY.md 8d for rays, DESIGN.md 3 for the other kernels)
     peak, peak_src = read_peaks()
-    traffic_all = {}
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
+    # ncu evidence of the committed kernels (profiles/r02_ncu_summary_v9.json, written on the GPU box by profiles/tools/ncu_summary.py from
+    # one `ncu --set full --clock-control none` capture of this command's frame): DRAM bytes, issue-slot and pipe utilisation of the
+    # bounce-0 launch of every kernel. bench.py cannot run under ncu itself; the capture it quotes is named in the line.
+    ncu_all = {}
+    ncu_path = os.path.join(ROOT, "profiles", "r02_ncu_summary_v9.json")
+    if os.path.exists(ncu_path) and args.workload in (WORKLOAD, "killeroo_path", "killeroo_path30"):
         try:
-            traffic_all = json.load(open(tp))
+            ncu_all = json.load(open(ncu_path))
         except Exception:
-            traffic_all = {}
+            ncu_all = {}
     closest_bytes = 32.0 * nodes_per_closest + 48.0 * prims_per_closest + 40.0
     any_bytes = 32.0 * nodes_per_any + 48.0 * prims_per_any + 40.0
     v_all, v_first = class_rays[D.K_ACCUMULATE], first_vertices
@@ -496,25 +503,53 @@ def main():
         D.K_FILM: ("camera sample", 136.0 * class_rays[D.K_FILM] + 132.0 * class_rays[D.K_FILM] / max(rp.spp, 1), class_rays[D.K_FILM]),
     }
     total_class = sum(class_ms)
+    # what bounds each kernel, read off the ncu capture (issue slots busy / lanes per instruction / DRAM and L2 throughput)
+    LIMITER = {
+        D.K_GEN: "instruction issue (80 % of the issue slots busy: hashing + camera arithmetic per sample)",
+        D.K_TRACE_PATH: "instruction issue at 12-24 of 32 lanes per instruction; the BVH is served by L1/L2 (DRAM 1-10 % of peak even on the 10 M-triangle "
+                        "scene: profiles/r02_ncu_trace_synth10m.csv), so the HBM fraction below is algorithmic bytes, not DRAM traffic",
+        D.K_SHADE: "instruction latency + fetch (48 % of the issue slots busy at 16 warps/SM, 12.8 k SASS instructions of exact fp32/fp64 arithmetic)",
+        D.K_ACCUMULATE: "HBM streaming (bounce 0 also instruction issue: 77 % of the slots busy)",
+        D.K_ADVANCE: "HBM streaming (73-75 % of the measured copy bandwidth in DRAM traffic)",
+        D.K_FILM: "HBM reads of the radiance rows + film atomics",
+    }
+
     def roof(k):
+        """Two views of a kernel class: over ALL its launches of the profiled frames (share of the step), and its bounce-0 launch alone
+        - one well-defined launch (first vertices / camera rays) whose DRAM traffic the ncu capture gives for comparison."""
         ms = class_ms[k]
         unit, nbytes, units = unit_bytes[k]
+        per_unit = nbytes / max(units, 1)
         ach = nbytes / (ms / 1e3) / 1e9 if ms > 0 else 0.0
-        return {"bound": "hbm", "kernel": D.K_KERNELS[k] + " (" + D.K_NAMES[k] + ")", "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach / peak, "traffic": traffic_all.get(D.K_NAMES[k]), "peak_source": peak_src,
-                "bytes_per_unit": nbytes / max(units, 1), "unit_of_work": unit,
-                "units_per_launch": units / max(class_launches[k], 1),
-                "avg_launch_ms": ms / max(class_launches[k], 1), "share_of_step": ms / total_class if total_class else None}
+        f_ms, f_units = first_ms[k], first_units[k]
+        if k == D.K_ACCUMULATE:
+            f_bytes = (56.0 + 128.0) * f_units
+        elif k == D.K_ADVANCE:
+            f_bytes = (104.0 + 128.0) * f_units
+        elif k == D.K_TRACE_PATH:
+            f_bytes = closest_bytes * f_units
+        else:
+            f_bytes = per_unit * f_units
+        f_ach = f_bytes / (f_ms / 1e3) / 1e9 if f_ms > 0 else 0.0
+        nc = ncu_all.get(D.K_NAMES[k]) or {}
+        return {"bound": "hbm", "limiter": LIMITER.get(k), "kernel": D.K_KERNELS[k] + " (" + D.K_NAMES[k] + "), bounce-0 launch",
+                "achieved": f_ach, "peak": peak, "unit": "GB/s", "frac": f_ach / peak,
+                "traffic": nc.get("dram_bytes"), "peak_source": peak_src,
+                "bytes_per_unit": f_bytes / max(f_units, 1), "unit_of_work": unit, "units_per_launch": f_units, "avg_launch_ms": f_ms,
+                "all_launches": {"achieved": ach, "frac": ach / peak, "bytes_per_unit": per_unit, "units_per_launch": units / max(class_launches[k], 1),
+                                 "avg_launch_ms": ms / max(class_launches[k], 1), "launches_per_step": class_launches[k] / prof_steps},
+                "share_of_step": ms / total_class if total_class else None,
+                "ncu": {q: nc.get(q) for q in ("ms", "dram_gbs", "dram_throughput_pct", "l2_throughput_pct", "l1_hit_pct", "l2_hit_pct", "issue_active_pct",
+                                               "fma_pipe_pct", "alu_pipe_pct", "fp64_pipe_pct", "lanes_per_inst", "warps_active_pct", "registers")} if nc else None}
     dom = max((k for k in unit_bytes if class_launches[k]), key=lambda k: class_ms[k])
     roofline = roof(dom)
     roofline.update({
         "nodes_per_closest_ray": nodes_per_closest, "prim_tests_per_closest_ray": prims_per_closest,
         "nodes_per_shadow_ray": nodes_per_any, "prim_tests_per_shadow_ray": prims_per_any,
-        "note": "config 1: k_shade is FP32/FP64/INT instruction-issue bound (ncu: issue slots 48 % busy at 16 warps/SM, DRAM 9 %), the traversal "
-                "kernels walk a 4 MB BVH that stays in L2/L1 (DRAM traffic = ray I/O): for both the HBM fraction is indicative only; "
-                "k_accumulate is the HBM-streaming kernel. Per-kernel lines in roofline_by_kernel; traffic from profiles/traffic.json "
-                "(ncu --set full, mean of the captured launches)" if args.workload == WORKLOAD else
-                "algorithmic bytes per unit as for config 1 (DESIGN.md 3); traffic figures in profiles/traffic.json were captured on config 1"})
+        "ncu_capture": ncu_all.get("_source"),
+        "note": "achieved = algorithmic bytes of the kernel's bounce-0 launch (bytes_per_unit x units_per_launch, DESIGN.md 3) / its CUDA-event time in "
+                "this run; traffic = DRAM bytes ncu measured for the same launch of the same command (profiles/r02_ncu_summary_v9.json); `limiter` says "
+                "what actually bounds the kernel - only k_advance / k_addlight are HBM-bound; per-kernel lines in roofline_by_kernel"})
     roofline_by_kernel = {D.K_NAMES[k]: roof(k) for k in unit_bytes if class_launches[k]}
     rays_total = class_rays[D.K_TRACE_PATH] + class_rays[D.K_TRACE_MIS] + class_rays[D.K_TRACE_SHADOW]
     kernel_launch_counts = {D.K_NAMES[k]: class_launches[k] / prof_steps for k in range(D.K_CLASSES) if class_launches[k]}
@@ -524,6 +559,7 @@ def main():
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "reference scene file (killeroo-simple) lowered by the host side; no synthetic substitution" if args.workload == WORKLOAD
                 else "reference scene file lowered by the host side (substitutions listed in config.workload)" if not args.workload.startswith("synth")
+                else "synthetic scene built through the reference's own API and BVHAccel (oracle/synth_scene.cpp) and lowered by the host side" if args.workload in SYNTH_API
                 else "synthetic scene written as .pbrt text, parsed, BVH-built and lowered by the reference's own code (oracle/make_golden.py)",
         "config": {"workload": workload_desc, "camera_samples_per_step": n_samples_total,
                    "parallelism": "image tile sets (32x32, round-robin) x%d, scene replicated; every rank's film kernel adds its samples straight into ONE film "

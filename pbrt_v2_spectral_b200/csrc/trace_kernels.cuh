@@ -183,8 +183,6 @@ __device__ __forceinline__ bool slab6_finite(float x0, float x1, float y0, float
 //
 #define PN_LEAF 0x80000000u
 #define W4_EMPTY_CODE 0xffffffffu
-template <typename T> __device__ __forceinline__ T seg_sel(uint32_t k, T a, T b, T c, T d) { return k == 0 ? a : (k == 1 ? b : (k == 2 ? c : d)); }
-
 // Warp organisation: one loop - every iteration a lane pops if it must, takes one pair step if it holds an interior node,
 // then tests the leaf it may have reached; idle lanes wait for the refill. Two alternatives were built and measured on the
 // B200 (profiles/r02_trace_modes.log, whole killeroo frame): while-while (every lane walks to its next leaf, the warp
@@ -195,6 +193,11 @@ template <typename T> __device__ __forceinline__ T seg_sel(uint32_t k, T a, T b,
 template <bool COUNT, bool WIDE>
 __global__ void __launch_bounds__(128) k_trace_multi(DevScene sc, TraceMultiArgs a) {
     uint2 stk[64];                  // the 64-entry todo stack (bvh.cpp:384): {child code, tmin of its slab test at push time}
+    // per-queue pointers, looked up by the lane's queue number when it fetches / finishes a ray (a ray finishes with one or
+    // two lanes active: a chain of selects there costs whole warp instructions per ray)
+    __shared__ TraceSeg s_seg[TRACE_MAX_SEG];
+    for (uint32_t k = threadIdx.x; k < TRACE_MAX_SEG; k += blockDim.x) s_seg[k] = a.seg[k < a.nseg ? k : 0];
+    __syncthreads();
     const uint32_t e0 = *a.seg[0].count;
     const uint32_t e1 = e0 + (a.nseg > 1 ? *a.seg[1].count : 0u);
     const uint32_t e2 = e1 + (a.nseg > 2 ? *a.seg[2].count : 0u);
@@ -310,12 +313,8 @@ __global__ void __launch_bounds__(128) k_trace_multi(DevScene sc, TraceMultiArgs
         return false;
     };
     auto finish = [&]() {
-        uint32_t *out_slot = seg_sel(seg, a.seg[0].out_slot, a.seg[1].out_slot, a.seg[2].out_slot, a.seg[3].out_slot);
-        out_slot[ri] = best;
-        if (!isAny) {
-            float *out_t = seg_sel(seg, a.seg[0].out_t, a.seg[1].out_t, a.seg[2].out_t, a.seg[3].out_t);
-            out_t[ri] = ray.maxt;
-        }
+        s_seg[seg].out_slot[ri] = best;
+        if (!isAny) s_seg[seg].out_t[ri] = ray.maxt;
         active = false;
     };
     for (;;) {
@@ -332,10 +331,9 @@ __global__ void __launch_bounds__(128) k_trace_multi(DevScene sc, TraceMultiArgs
                     if (q < total) {
                         seg = (q >= e0 ? 1u : 0u) + (q >= e1 ? 1u : 0u) + (q >= e2 ? 1u : 0u);
                         const uint32_t ql = q - (seg == 0 ? 0u : (seg == 1 ? e0 : (seg == 2 ? e1 : e2)));
-                        const uint32_t *queue = seg_sel(seg, a.seg[0].queue, a.seg[1].queue, a.seg[2].queue, a.seg[3].queue);
-                        const float4 *ro = seg_sel(seg, a.seg[0].ro, a.seg[1].ro, a.seg[2].ro, a.seg[3].ro);
-                        const float4 *rd = seg_sel(seg, a.seg[0].rd, a.seg[1].rd, a.seg[2].rd, a.seg[3].rd);
-                        isAny = seg_sel(seg, a.seg[0].any, a.seg[1].any, a.seg[2].any, a.seg[3].any) != 0u;
+                        const uint32_t *queue = s_seg[seg].queue;
+                        const float4 *ro = s_seg[seg].ro, *rd = s_seg[seg].rd;
+                        isAny = s_seg[seg].any != 0u;
                         ri = queue ? queue[ql] : ql;
                         const float4 o = ro[ri], d = rd[ri];
                         ray.o = V(o.x, o.y, o.z); ray.d = V(d.x, d.y, d.z); ray.mint = o.w; ray.maxt = d.w;

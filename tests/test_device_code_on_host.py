@@ -241,3 +241,46 @@ def test_generated_samples_match_the_restated_sampler(trace_shim):
                 k = (b - 3) * 10 + (b - 4 if b > 4 else 0)          # RNG draws consumed before bounce b (path.cpp:82,97)
                 assert np.array_equal(u11[:10].view(np.uint32), rng[s, k:k + 10].view(np.uint32))
                 assert u11[10].view(np.uint32) == rng[s, k + 10].view(np.uint32)
+
+
+ASAN_CHILD = r'''
+import sys, ctypes as C
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(tests)r)
+import numpy as np, oracle_lib as O
+lib = C.CDLL(%(so)r)
+p = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+n = 0
+for name, sp, gp in O.golden_cases():
+    scene, g = O.load_case(sp, gp)
+    rays = np.ascontiguousarray(g["rays"], np.float32)
+    m = g["prim_id"] != 0
+    seg = np.ascontiguousarray(g["rays2"][m])
+    for wide in (0, 1):
+        slot = np.empty(len(rays), np.uint32); t = np.empty(len(rays), np.float32)
+        assert lib.hd_trace(C.byref(scene.desc), p(rays), len(rays), 0, p(slot), p(t), wide) == 0
+        s3 = np.empty(len(seg), np.uint32)
+        lib.hd_trace(C.byref(scene.desc), p(seg), len(seg), 1, p(s3), None, wide)
+    n += 1
+print("asan ok", n)
+'''
+
+
+def test_traversal_kernels_under_address_sanitizer(tmp_path):
+    """compute-sanitizer is closed on this GPU pool (profiles/r02_sanitizer_memcheck.log holds the refusal), so the memory
+    safety of the traversal code is checked where it can be: the kernel source (k_trace_multi, exact and wide), the re-layout
+    kernels and the wide-tree builder compiled for the host with -fsanitize=address,undefined and run over every golden set -
+    out-of-bounds node / stack / vertex accesses and undefined shifts would abort the child."""
+    import sys
+    asan = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(asan) or not os.path.exists(asan):
+        pytest.skip("libasan not available")
+    so = str(tmp_path / "libtracehost_asan.so")
+    csrc = os.path.join(ROOT, "pbrt_v2_spectral_b200", "csrc")
+    subprocess.run(["g++", "-O1", "-g", "-m64", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-std=c++17", "-w",
+                    "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer",
+                    "-I" + os.path.join(ROOT, "tests", "host_shim", "fake"), "-I" + os.path.join(ROOT, "include"), "-I" + csrc,
+                    "-o", so, os.path.join(ROOT, "tests", "host_shim", "trace_on_host.cpp"), "-lm"], check=True)
+    code = ASAN_CHILD % {"root": ROOT, "tests": os.path.join(ROOT, "tests"), "so": so}
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900,
+                       env=dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0"))
+    assert r.returncode == 0 and "asan ok" in r.stdout, (r.stdout + r.stderr)[-3000:]
