@@ -1035,6 +1035,7 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
     int want_lanes = s->max_lanes;
     if (want_lanes > 2 && local_pixels * mem_pp <= (1ull << 25)) want_lanes = 2;
     while (want_lanes > 1 && local_samples < ((uint64_t)want_lanes << 19)) --want_lanes;
+    if (const char *e = getenv("SPT_FORCE_LANES")) want_lanes = std::min(std::max(atoi(e), 1), s->max_lanes);      // A/B runs (profiles/tools)
     const uint64_t lane_cap_pixels = std::max<uint64_t>(1, ((1u << 25) / (uint64_t)want_lanes) / mem_pp);
     uint64_t wave_pixels;
     if (rp->wave_pixels > 0) wave_pixels = (uint64_t)rp->wave_pixels;
