@@ -220,6 +220,16 @@ def killeroo_direct(w, h, spp, name, maxdepth=5):
     return set_filename(set_spp(set_res(s, w, h), spp), name)
 
 
+def specular_direct(w, h, spp, name, maxdepth=5):
+    """killeroo-simple.pbrt under its shipped directlighting integrator with one killeroo of glass and one mirror: the
+    SpecularReflect / SpecularTransmit recursion of DirectLightingIntegrator::Li (directlighting.cpp:97-107)."""
+    s = killeroo_direct(w, h, spp, name, maxdepth)
+    s = s.replace('Material "plastic" "color Kd" [.4 .2 .2] "color Ks" [.5 .5 .5]', 'Material "glass" "color Kr" [.9 .9 .9] "color Kt" [.9 .8 .7] "float index" [1.5]')
+    s = s.replace('Material "plastic" "color Ks" [.3 .3 .3] "color Kd" [.4 .5 .4]', 'Material "mirror" "color Kr" [.8 .85 .9]')
+    assert "glass" in s and "mirror" in s and 'SurfaceIntegrator "directlighting"' in s
+    return s
+
+
 def killeroo_direct_one(w, h, spp, name, maxdepth=5):
     """killeroo-simple.pbrt with the directlighting integrator's other strategy ("one": UniformSampleOneLight)."""
     s = killeroo_direct(w, h, spp, name, maxdepth)
@@ -348,6 +358,8 @@ CONFIGS = {
     "bunny_direct_small":    (bunny_direct, 320, 240, 4, 6000, 8, 1024),
     "killeroo_direct":       (killeroo_direct, 700, 700, 64, 0, 0, 0),
     "killeroo_direct_one_small": (killeroo_direct_one, 176, 176, 4, 3000, 8, 0),
+    # directlighting with specular materials: the SpecularReflect / SpecularTransmit recursion
+    "specular_direct_small": (specular_direct, 176, 176, 4, 3000, 8, 1024),
     # the bunny with its shipped measured BRDF: under the path integrator (config 2) and as shipped (directlighting)
     "bunny_measured_small":  (bunny_measured, 320, 240, 4, 6000, 40, 4096),
     "bunny_shipped_small":   (bunny_shipped, 320, 240, 4, 6000, 8, 1024),
@@ -559,7 +571,7 @@ def share_arrays(path, donor, keys=("tex_texels",)):
 
 # scene files that repeat the geometry of a bench workload (other materials / integrator): every array over 256 KB that is
 # byte-identical in the donor becomes a "<array>@" reference - the snapshot shipped to the GPU box is capped at 512 MiB
-SHARE_DONOR = {"bunny_direct_small": "bunny_path", "bunny_measured_small": "bunny_path", "killeroo_direct_one_small": "killeroo_path",
+SHARE_DONOR = {"specular_direct_small": "killeroo_path", "bunny_direct_small": "bunny_path", "bunny_measured_small": "bunny_path", "killeroo_direct_one_small": "killeroo_path",
                "specular_small": "killeroo_path", "bunny_shipped": "bunny_path", "killeroo_direct": "killeroo_path", "killeroo_path30": "killeroo_path"}
 
 

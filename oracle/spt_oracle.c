@@ -1548,10 +1548,15 @@ static int direct_sample_floats(const SptSceneDesc *sc) {
     for (uint32_t i = 0; i < sc->n_lights; ++i) N += sc->lights[i].n_samples;
     return 7 + 6 * N;
 }
-static void li_sample_direct(const SptSceneDesc *sc, const SptCameraDesc *cam, int spp, const float *smp, float *Lout) {
-    Ray ray;
-    RayDiff rd;
-    camera_ray_diff(cam, smp, spp, &ray, &rd);
+/* SamplerRenderer::Li + DirectLightingIntegrator::Li for one ray of the recursion (samplerrenderer.cpp:225-247,
+ * directlighting.cpp:70-107): emitted light + UniformSampleAllLights / UniformSampleOneLight at the hit - every level reads the
+ * SAME Sample arrays - then SpecularReflect / SpecularTransmit (integrator.cpp:169-250) while depth + 1 < maxDepth. The
+ * RNG values BSDFSample(rng) draws there choose among the BxDFs matching (REFLECTION | SPECULAR) resp. (TRANSMISSION |
+ * SPECULAR) - one at most for every lowered material, and a perfectly specular direction ignores u - so they do not enter.
+ * rd: the camera ray's differentials (level 0); the children's differentials only reach image-texture filtering, which the
+ * lowering does not combine with specular materials under this integrator. */
+static void direct_li(const SptSceneDesc *sc, int strategy_all, int maxDepth, int depth, Ray ray, const RayDiff *rd, const float *smp,
+                      float *Lout) {
     float L[NB];
     for (int c = 0; c < NB; ++c) L[c] = 0.f;
     uint32_t slot; Hit isect;
@@ -1565,69 +1570,99 @@ static void li_sample_direct(const SptSceneDesc *sc, const SptCameraDesc *cam, i
         return;
     }
     BSDF bsdf; v3 n;
-    make_bsdf(sc, slot, &isect, &rd, &bsdf, &n);
+    make_bsdf(sc, slot, &isect, rd, &bsdf, &n);
     v3 p = isect.p, wo = vneg(ray.d);
     float le[NB];
     isect_le(sc, slot, &isect, wo, le);
     for (int c = 0; c < NB; ++c) L[c] += le[c];
-    int N = 0;
-    for (uint32_t i = 0; i < sc->n_lights; ++i) N += sc->lights[i].n_samples;
-    const float *oneD = smp + 5, *twoD = smp + 7 + 2 * N;
-    float Lall[NB];
-    for (int c = 0; c < NB; ++c) Lall[c] = 0.f;
-    for (uint32_t i = 0; i < sc->n_lights; ++i) {
-        int nSamples = sc->lights[i].n_samples;
-        float Ld[NB];
-        for (int c = 0; c < NB; ++c) Ld[c] = 0.f;
-        for (int j = 0; j < nSamples; ++j) {
-            float ls[3] = { twoD[2 * j], twoD[2 * j + 1], oneD[j] };
-            float bs[3] = { twoD[2 * nSamples + 2 * j], twoD[2 * nSamples + 2 * j + 1], oneD[nSamples + j] };
-            float e[NB];
-            estimate_direct(sc, sc->lights + i, (int)i, p, n, wo, isect.rayEpsilon, &bsdf, ls, bs, e);
-            for (int c = 0; c < NB; ++c) Ld[c] += e[c];
+    if (strategy_all) {
+        int N = 0;
+        for (uint32_t i = 0; i < sc->n_lights; ++i) N += sc->lights[i].n_samples;
+        const float *oneD = smp + 5, *twoD = smp + 7 + 2 * N;
+        float Lall[NB];
+        for (int c = 0; c < NB; ++c) Lall[c] = 0.f;
+        for (uint32_t i = 0; i < sc->n_lights; ++i) {
+            int nSamples = sc->lights[i].n_samples;
+            float Ld[NB];
+            for (int c = 0; c < NB; ++c) Ld[c] = 0.f;
+            for (int j = 0; j < nSamples; ++j) {
+                float ls[3] = { twoD[2 * j], twoD[2 * j + 1], oneD[j] };
+                float bs[3] = { twoD[2 * nSamples + 2 * j], twoD[2 * nSamples + 2 * j + 1], oneD[nSamples + j] };
+                float e[NB];
+                estimate_direct(sc, sc->lights + i, (int)i, p, n, wo, isect.rayEpsilon, &bsdf, ls, bs, e);
+                for (int c = 0; c < NB; ++c) Ld[c] += e[c];
+            }
+            for (int c = 0; c < NB; ++c) Lall[c] += Ld[c] / nSamples;
+            oneD += 2 * nSamples; twoD += 4 * nSamples;
         }
-        for (int c = 0; c < NB; ++c) Lall[c] += Ld[c] / nSamples;
-        oneD += 2 * nSamples; twoD += 4 * nSamples;
+        for (int c = 0; c < NB; ++c) L[c] += Lall[c];
+    } else {
+        /* strategy "one" (directlighting.cpp:61-68): [5] light component, [6] light number, [7] bsdf component, [8],[9] volume
+         * integrator, [10],[11] light position, [12],[13] bsdf direction */
+        int nLights = (int)sc->n_lights;
+        if (nLights > 0) {
+            int lightNum = (int)floorf(smp[6] * nLights);
+            if (nLights - 1 < lightNum) lightNum = nLights - 1;
+            float ls[3] = { smp[10], smp[11], smp[5] }, bs[3] = { smp[12], smp[13], smp[7] };
+            float Ld[NB];
+            estimate_direct(sc, sc->lights + lightNum, lightNum, p, n, wo, isect.rayEpsilon, &bsdf, ls, bs, Ld);
+            for (int c = 0; c < NB; ++c) L[c] += Ld[c] * (float)nLights;
+        }
     }
-    for (int c = 0; c < NB; ++c) L[c] += Lall[c];
+    if (depth + 1 < maxDepth) {
+        /* SpecularReflect, then SpecularTransmit: BSDF::Sample_f restricted to the one specular BxDF of that kind */
+        for (int pass = 0; pass < 2; ++pass) {
+            int which = -1;
+            for (int i = 0; i < bsdf.nBxDFs; ++i) {
+                int k = bsdf.kind[i];
+                if (pass == 0 ? (k == BX_SPEC_REFL_NOOP || k == BX_SPEC_REFL_DIEL) : (k == BX_SPEC_TRANS)) { which = i; break; }
+            }
+            if (which < 0) continue;
+            v3 wol = w2l(&bsdf, wo), wil;
+            float f[NB], pdf = 0.f;
+            for (int c = 0; c < NB; ++c) f[c] = 0.f;
+            float fr = 1.f;
+            if (bsdf.kind[which] != BX_SPEC_REFL_NOOP) fr = fresnel_dielectric(wol.z, 1.f, bsdf.ior);
+            if (pass == 1) {                                   /* SpecularTransmission::Sample_f, reflection.cpp:139-162 */
+                int entering = wol.z > 0.;
+                float ei = 1.f, et = bsdf.ior;
+                if (!entering) { float t = ei; ei = et; et = t; }
+                float sini2 = sin_theta2(wol);
+                float eta = ei / et;
+                float sint2 = eta * eta * sini2;
+                if (sint2 >= 1.) continue;                     /* total internal reflection */
+                float cost = sqrtf(stdmaxf(0.f, 1.f - sint2));
+                if (entering) cost = -cost;
+                wil = V(eta * -wol.x, eta * -wol.y, cost);
+                pdf = 1.f;
+                for (int c = 0; c < NB; ++c) f[c] = (1.f - fr) * bsdf.R[which][c] / abs_cos_theta(wil);
+            } else {                                           /* SpecularReflection::Sample_f, reflection.cpp:130-136 */
+                wil = V(-wol.x, -wol.y, wol.z);
+                pdf = 1.f;
+                for (int c = 0; c < NB; ++c) f[c] = fr * bsdf.R[which][c] / abs_cos_theta(wil);
+            }
+            v3 wi = l2w(&bsdf, wil);
+            if (!(pdf > 0.f) || is_black(f) || absdot(wi, n) == 0.f) continue;
+            Ray child; child.o = p; child.d = wi; child.mint = isect.rayEpsilon; child.maxt = INFINITY;
+            float Li[NB];
+            direct_li(sc, strategy_all, maxDepth, depth + 1, child, NULL, smp, Li);
+            float ad = absdot(wi, n);
+            for (int c = 0; c < NB; ++c) L[c] += f[c] * Li[c] * ad / pdf;
+        }
+    }
     memcpy(Lout, L, sizeof(L));
 }
-
-/* DirectLightingIntegrator::Li with strategy "one" (directlighting.cpp:70-105, UniformSampleOneLight core/integrator.cpp:72-107).
- * Sample layout (directlighting.cpp:61-68): [5] light component, [6] light number, [7] bsdf component, [8],[9] volume
- * integrator, [10],[11] light position, [12],[13] bsdf direction. */
-static void li_sample_direct_one(const SptSceneDesc *sc, const SptCameraDesc *cam, int spp, const float *smp, float *Lout) {
+static void li_sample_direct(const SptSceneDesc *sc, const SptCameraDesc *cam, int maxDepth, int spp, const float *smp, float *Lout) {
     Ray ray;
     RayDiff rd;
     camera_ray_diff(cam, smp, spp, &ray, &rd);
-    float L[NB];
-    for (int c = 0; c < NB; ++c) L[c] = 0.f;
-    uint32_t slot; Hit isect;
-    if (!bvh_intersect(sc, &ray, 0, &slot, &isect, NULL, NULL)) {
-        for (uint32_t i = 0; i < sc->n_lights; ++i) {
-            float le[NB];
-            light_le(sc, sc->lights + i, ray.d, le);
-            for (int c = 0; c < NB; ++c) L[c] += le[c];
-        }
-        memcpy(Lout, L, sizeof(L));
-        return;
-    }
-    BSDF bsdf; v3 n;
-    make_bsdf(sc, slot, &isect, &rd, &bsdf, &n);
-    v3 p = isect.p, wo = vneg(ray.d);
-    float le[NB];
-    isect_le(sc, slot, &isect, wo, le);
-    for (int c = 0; c < NB; ++c) L[c] += le[c];
-    int nLights = (int)sc->n_lights;
-    if (nLights > 0) {
-        int lightNum = (int)floorf(smp[6] * nLights);
-        if (nLights - 1 < lightNum) lightNum = nLights - 1;
-        float ls[3] = { smp[10], smp[11], smp[5] }, bs[3] = { smp[12], smp[13], smp[7] };
-        float Ld[NB];
-        estimate_direct(sc, sc->lights + lightNum, lightNum, p, n, wo, isect.rayEpsilon, &bsdf, ls, bs, Ld);
-        for (int c = 0; c < NB; ++c) L[c] += Ld[c] * (float)nLights;
-    }
-    memcpy(Lout, L, sizeof(L));
+    direct_li(sc, 1, maxDepth, 0, ray, &rd, smp, Lout);
+}
+static void li_sample_direct_one(const SptSceneDesc *sc, const SptCameraDesc *cam, int maxDepth, int spp, const float *smp, float *Lout) {
+    Ray ray;
+    RayDiff rd;
+    camera_ray_diff(cam, smp, spp, &ray, &rd);
+    direct_li(sc, 0, maxDepth, 0, ray, &rd, smp, Lout);
 }
 
 int orc_sample_floats(const SptSceneDesc *sc, int32_t integrator) {
@@ -1639,8 +1674,8 @@ void orc_shade_samples(const SptSceneDesc *sc, const SptCameraDesc *cam, int32_t
     const int stride = orc_sample_floats(sc, integrator);
 #pragma omp parallel for schedule(dynamic, 64)
     for (int64_t i = 0; i < (int64_t)n; ++i) {
-        if (integrator == SPT_INTEGRATOR_DIRECT_ALL) li_sample_direct(sc, cam, spp, samples + (size_t)stride * i, out_L + (size_t)NB * i);
-        else if (integrator == SPT_INTEGRATOR_DIRECT_ONE) li_sample_direct_one(sc, cam, spp, samples + (size_t)stride * i, out_L + (size_t)NB * i);
+        if (integrator == SPT_INTEGRATOR_DIRECT_ALL) li_sample_direct(sc, cam, max_depth, spp, samples + (size_t)stride * i, out_L + (size_t)NB * i);
+        else if (integrator == SPT_INTEGRATOR_DIRECT_ONE) li_sample_direct_one(sc, cam, max_depth, spp, samples + (size_t)stride * i, out_L + (size_t)NB * i);
         else li_sample(sc, cam, max_depth, spp, samples + 37 * i, rng ? rng + (size_t)n_rng * i : NULL, rng ? n_rng : 0,
                        out_L + (size_t)NB * i);
     }
@@ -1807,7 +1842,7 @@ void orc_render(const SptSceneDesc *sc, const SptCameraDesc *cam, const SptFilmD
             for (int s = 0; s < rp->spp; ++s) {
                 if (direct) {
                     gen_sample_direct(sc, rp->seed, px, py, s, rp->spp, cam->shutter_open, cam->shutter_close, smp + stride * s);
-                    li_sample_direct(sc, cam, rp->spp, smp + stride * s, L + NB * s);
+                    li_sample_direct(sc, cam, rp->max_depth, rp->spp, smp + stride * s, L + NB * s);
                 } else {
                     orc_gen_sample(rp->seed, px, py, s, rp->spp, cam->shutter_open, cam->shutter_close, nrng,
                                    smp + 37 * s, rng + nrng * s);
@@ -1815,7 +1850,7 @@ void orc_render(const SptSceneDesc *sc, const SptCameraDesc *cam, const SptFilmD
                         /* the product draws strategy "one" from the path sampler's first-bounce dimensions */
                         const float *q = smp + 37 * s;
                         float o14[14] = { q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7], 0.f, 0.f, q[19], q[20], q[21], q[22] };
-                        li_sample_direct_one(sc, cam, rp->spp, o14, L + NB * s);
+                        li_sample_direct_one(sc, cam, rp->max_depth, rp->spp, o14, L + NB * s);
                     } else li_sample(sc, cam, rp->max_depth, rp->spp, smp + 37 * s, rng + nrng * s, nrng, L + NB * s);
                 }
             }

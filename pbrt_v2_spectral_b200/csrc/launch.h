@@ -19,10 +19,11 @@ void spt_launch_slot_to_flag(cudaStream_t st, const uint32_t *slot, uint32_t n, 
 
 void spt_launch_compact_hits(int grid, cudaStream_t st, const uint32_t *queue, const uint32_t *count, const uint32_t *hit_slot,
                              uint32_t *hit_queue, uint32_t *hit_count, uint32_t *miss_queue, uint32_t *miss_count, float *black_L);
-void spt_launch_miss_env(int grid, cudaStream_t st, const DevScene &sc, const WaveBuffers &wb, int bounce, const uint32_t *queue, const uint32_t *count);
+void spt_launch_miss_env(int grid, cudaStream_t st, const DevScene &sc, const WaveBuffers &wb, int bounce, int tree, const uint32_t *queue, const uint32_t *count);
+void spt_launch_spawn_T(int grid, cudaStream_t st, const DevScene &sc, const WaveBuffers &wb, int level, const uint32_t *queue, const uint32_t *count);
 void spt_launch_shade(int grid, cudaStream_t st, const DevScene &sc, const RenderCfg &cfg, const SampleSource &src, const WaveBuffers &wb,
                       int bounce, const uint32_t *queue, const uint32_t *count, uint32_t *shadow_count, uint32_t *mis_count,
-                      uint32_t *elided_count, uint32_t *mis_any_count);
+                      uint32_t *elided_count, uint32_t *mis_any_count, uint32_t *next_queue, uint32_t *next_count, uint32_t *node_ctr);
 void spt_launch_advance(int grid, cudaStream_t st, const DevScene &sc, const RenderCfg &cfg, const WaveBuffers &wb, int bounce,
                         const uint32_t *queue, const uint32_t *count, uint32_t *next_queue, uint32_t *next_count);
 void spt_launch_addlight(int grid, cudaStream_t st, const DevScene &sc, const RenderCfg &cfg, const WaveBuffers &wb, int bounce,

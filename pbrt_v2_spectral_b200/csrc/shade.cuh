@@ -926,19 +926,26 @@ __device__ inline void light_sample(const DevScene &sc, int lightIdx, v3 p, floa
         v3 pt = shape_sample_from(sc, chosen, p, u0, u1, &ns);
         v3 ps = pt;
         // ShapeSet::Sample re-intersects every shape of the set with the unclipped ray p -> pt and keeps
-        // the LAST hit (light.cpp:141-149). For a set of one sphere that hit is pt itself with the same
-        // outward normal (Sphere::Sample's and DifferentialGeometry's orientations agree), up to rounding.
-        if (!(l.shape_count == 1 && chosen.kind == SPT_PRIM_SPHERE)) {
-            Ray r; r.o = p; r.d = vsub(pt, p); r.mint = 1e-3f; r.maxt = SPT_INF;
-            float thit = 1.f;
-            bool anyHit = false;
+        // the LAST hit (light.cpp:141-149) - also for a set of one sphere: at the rim of the cone Sphere::Sample
+        // draws from, its float quadratic misses the sphere, Sample returns the point of closest approach, and
+        // this second intersection (another direction length, other rounding) decides the point and its normal.
+        Ray r; r.o = p; r.d = vsub(pt, p); r.mint = 1e-3f; r.maxt = SPT_INF;
+        float thit = 1.f;
+        int hitSphere = -1;                   // the last hit is on this sphere: its normal is worked out below
+        v3 phitObj = V(0, 0, 0);
+        {
             v3 nnHit = ns;
             for (int i = 0; i < l.shape_count; ++i) {
                 const SptLightShape &s = sc.light_shapes[l.shape_first + i];
-                Hit hh;
-                if (shape_intersect(sc, s.kind, s.flags, (uint32_t)s.data, r, &hh)) { anyHit = true; nnHit = hh.nn; thit = hh.t; }
+                if (s.kind == SPT_PRIM_SPHERE) {
+                    float t;
+                    if (sphere_intersect(sc, sc.quadrics[s.data], s.flags, r, &t, nullptr, &phitObj)) { thit = t; hitSphere = i; }
+                } else {
+                    Hit hh;
+                    if (shape_intersect(sc, s.kind, s.flags, (uint32_t)s.data, r, &hh)) { nnHit = hh.nn; thit = hh.t; hitSphere = -1; }
+                }
             }
-            if (anyHit) ns = nnHit;
+            ns = nnHit;
             ps = ray_at(r, thit);
         }
         out->wi = normalize(vsub(ps, p));
@@ -947,6 +954,28 @@ __device__ inline void light_sample(const DevScene &sc, int lightIdx, v3 p, floa
         float dist = sqrtf(len2(vsub(p, ps)));
         out->shadow_d = vdiv(vsub(ps, p), dist);
         out->shadow_maxt = dist * (1.f - 1e-3f);
+        if (hitSphere >= 0) {
+            // Only the SIGN of Dot(dgLight.nn, -wi) is used (DiffuseAreaLight::L, diffuse.h:47-49). dgLight.nn =
+            // Normalize(Cross(dpdu, dpdv)) of the transformed tangents, flipped by ReverseOrientation ^ SwapsHandedness
+            // (sphere.cpp:105-149, diffgeom.cpp:44-46), points along ObjectToWorld(Normal(phit)), reversed iff ReverseOrientation:
+            // Cross(M a, M b) = det(M) M^-T (a x b), a x b is a positive multiple of phit, and the two handedness signs cancel.
+            // That normal costs no atan2f / acosf / sinf; where its cosine is within 1e-3 of zero (rounding differences
+            // between the two are ~1e-6) the DifferentialGeometry is built as the reference builds it.
+            const SptLightShape &s = sc.light_shapes[l.shape_first + hitSphere];
+            const SptQuadric &q = sc.quadrics[s.data];
+            const SptXform &xf = sc.xforms[q.xform];
+            // (the sign of the un-normalised cosine first; its size against |n| only near zero)
+            v3 nq = xf_normal(xf.minv, phitObj);
+            float c = dot(nq, vneg(out->wi));
+            if (s.flags & SPT_PF_REVERSE) c = -c;
+            if (fabsf(c) < 1e-3f * sqrtf(len2(nq))) {
+                Hit hh;
+                sphere_record(sc, q, s.flags, r, thit, &hh);
+                c = dot(hh.nn, vneg(out->wi));
+            }
+            out->black = !(c > 0.f);
+            return;
+        }
         out->black = !(dot(ns, vneg(out->wi)) > 0.f);
         return;
     }

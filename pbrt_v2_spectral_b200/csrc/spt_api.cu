@@ -536,6 +536,13 @@ int spt_get_stats(SptScene *s, SptStats *out) {
 // ---------------------------------------------------------------------------------------------
 #define SPT_ROW 16
 
+// directlighting on a scene with specular materials: slots per camera sample, the sample itself + the nodes of its
+// SpecularReflect / SpecularTransmit tree (most samples spawn none; a glass object a few per sample that meets it)
+#define SPT_TREE_SLOTS 4
+static int tree_slots() {                 // SPT_TREE_SLOTS in the environment: tests force the split-and-retry path of spt_render with 2
+    if (const char *e = getenv("SPT_TREE_SLOTS")) return std::min(std::max(atoi(e), 2), 64);
+    return SPT_TREE_SLOTS;
+}
 static int ensure_wave(SptScene *s, int n_lanes, uint32_t cap, int max_depth, size_t n_waves, uint32_t sub = 1) {
     cap = (cap + 31u) & ~31u;
     const size_t jcap = (size_t)cap * sub;
@@ -554,7 +561,7 @@ static int ensure_wave(SptScene *s, int n_lanes, uint32_t cap, int max_depth, si
         AL(w.g0, float4, jcap); AL(w.g1, float4, jcap); AL(w.g2, float4, jcap); AL(w.g3, float4, cap);
         AL(w.mis_slot, uint32_t, jcap); AL(w.mis_t, float, jcap); AL(w.sh_slot, uint32_t, jcap);
         AL(w.rec0, float4, jcap); AL(w.rec1, float4, jcap); AL(w.rec2, float4, jcap);
-        AL(w.laux, float4, jcap); AL(w.pflags, uint32_t, cap);
+        AL(w.laux, float4, jcap); AL(w.pflags, uint32_t, cap); AL(w.root, uint32_t, s->dev.has_specular ? cap : 1);
         AL(w.rec3, float4, s->dev.has_ext ? jcap : 1); AL(w.rec4, float4, s->dev.has_ext ? jcap : 1);
         AL(w.frow, float, s->dev.has_measured ? jcap * 3 * NBP : 1);
         AL(w.img_xy, float2, cap);
@@ -642,13 +649,16 @@ static void run_wave(SptScene *s, const RenderCfg &cfg, const SampleSource &src,
         }
         if (last) break;
         // camera rays that escape pick up the environment light (samplerrenderer.cpp:239-243)
-        uint32_t *mq = (s->has_env && (b == 0 || sc.has_specular)) ? wb.missQ : nullptr;
+        uint32_t *mq = (s->has_env && (b == 0 || sc.has_specular || cfg.tree)) ? wb.missQ : nullptr;
         spt_launch_compact_hits(gridC, st, q, row + 0, wb.hit_slot, wb.hitQ, row + 3, mq, row + 10, (b == 0 && !s->has_env) ? wb.L : nullptr);
         s->mark(SPT_K_SHADE, li);
-        if (mq) { spt_launch_miss_env(gridT, st, sc, wb, b, mq, row + 10); s->mark(SPT_K_SHADE, li); }
-        spt_launch_shade(gridT, st, sc, cfg, src, wb, b, wb.hitQ, row + 3, row + 1, row + 2, row + 8, row + 9);
+        if (mq) { spt_launch_miss_env(gridT, st, sc, wb, b, cfg.tree, mq, row + 10); s->mark(SPT_K_SHADE, li); }
+        spt_launch_shade(gridT, st, sc, cfg, src, wb, b, wb.hitQ, row + 3, row + 1, row + 2, row + 8, row + 9, qn, next + 0, counts + 11);
         s->mark(SPT_K_SHADE, li);
-        if (b < cfg.max_depth) {
+        if (cfg.tree) {
+            // the nodes K5 spawned (SpecularReflect / SpecularTransmit) are the next level's rays; their throughput rows
+            if (b < cfg.max_depth) { spt_launch_spawn_T(gridT, st, sc, wb, b, qn, next + 0); s->mark(SPT_K_ADVANCE, li); }
+        } else if (b < cfg.max_depth) {
             spt_launch_advance(gridT, st, sc, cfg, wb, b, wb.hitQ, row + 3, qn, next + 0);
             s->mark(SPT_K_ADVANCE, li);
         }
@@ -828,15 +838,21 @@ int spt_shade_samples(SptScene *s, const SptCameraDesc *cam, int32_t integrator,
     if (integrator != SPT_INTEGRATOR_PATH && integrator != SPT_INTEGRATOR_DIRECT_ALL && integrator != SPT_INTEGRATOR_DIRECT_ONE)
         return fail(SPT_ERR_ARG, "unknown integrator");
     const bool direct = integrator == SPT_INTEGRATOR_DIRECT_ALL, directOne = integrator == SPT_INTEGRATOR_DIRECT_ONE;
-    if ((direct || directOne) && s->dev.has_specular) return fail(SPT_ERR_UNSUPP, "directlighting with specular materials is not supported");
+    if (directOne && s->dev.has_specular) return fail(SPT_ERR_UNSUPP, "directlighting strategy \"one\" with specular materials is not supported");
     if (direct && s->dev.n_lights == 0) return fail(SPT_ERR_UNSUPP, "directlighting needs at least one light");
     if (n == 0) return SPT_OK;
     const int sub = direct ? s->direct_slots : 1;
     const int stride = direct ? 7 + 6 * s->direct_slots : (directOne ? 14 : 37);
-    if (direct || directOne) max_depth = 0;     // strategy "one" is the path integrator's first vertex: emitted light + UniformSampleOneLight
-    if (n * (uint64_t)sub > (1u << 26)) return fail(SPT_ERR_ARG, "too many samples for one call");
+    // directlighting: max_depth is DirectLightingIntegrator::maxDepth, the depth of the SpecularReflect / SpecularTransmit recursion
+    // (directlighting.cpp:97-107); without specular materials there is one level. Strategy "one" is the path integrator's first
+    // vertex: emitted light + UniformSampleOneLight.
+    const bool tree = direct && s->dev.has_specular && max_depth > 1;
+    max_depth = tree ? max_depth - 1 : ((direct || directOne) ? 0 : max_depth);
+    // this entry point (tests, diagnostics) sizes the node pool for the full binary tree of up to five levels: no retries here
+    const uint64_t slots = n * (uint64_t)(tree ? std::min(31, (2 << std::min(max_depth, 4)) - 1) : 1);
+    if (slots * (uint64_t)sub > (1u << 26)) return fail(SPT_ERR_ARG, "too many samples for one call");
     DeviceGuard dg(s->device);
-    int rc = ensure_wave(s, 1, (uint32_t)n, max_depth, 1, (uint32_t)sub);
+    int rc = ensure_wave(s, 1, (uint32_t)slots, max_depth, 1, (uint32_t)sub);
     if (rc != SPT_OK) return rc;
     DevMem m;
     float *dsmp = m.upload(samples, n * (size_t)stride);
@@ -846,7 +862,7 @@ int spt_shade_samples(SptScene *s, const SptCameraDesc *cam, int32_t integrator,
     RenderCfg cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.cam = *cam; cfg.spp = 1; cfg.spp_shift = 0; cfg.max_depth = max_depth; cfg.n_samples = (uint32_t)n;
-    cfg.integrator = integrator; cfg.sub = sub;
+    cfg.integrator = integrator; cfg.sub = sub; cfg.tree = tree ? 1 : 0;
     cfg.tile = 1; cfg.tile_shift = 0; cfg.tilesX = 1; cfg.tilesY = 1; cfg.nranks = 1;
     cfg.diff_scale = 1.f / sqrtf((float)spp);
     SampleSource src; src.smp = dsmp; src.stride = stride; src.rng = drng; src.n_rng = drng ? n_rng : 0; src.seed = 0; src.spp = 1;
@@ -861,6 +877,7 @@ int spt_shade_samples(SptScene *s, const SptCameraDesc *cam, int32_t integrator,
     if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
     m.release();
     if (e != cudaSuccess) return fail(SPT_ERR_CUDA, cudaGetErrorString(e));
+    if (tree && hc[12]) return fail(SPT_ERR_UNSUPP, "specular tree: more nodes than the full binary tree of five levels per sample");
     s->class_times_pending = true;
     s->stats.camera_samples += n;
     add_ray_stats(s, hc, max_depth, 1);
@@ -993,14 +1010,17 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
     if (rp->integrator != SPT_INTEGRATOR_PATH && rp->integrator != SPT_INTEGRATOR_DIRECT_ALL && rp->integrator != SPT_INTEGRATOR_DIRECT_ONE)
         return fail(SPT_ERR_ARG, "unknown integrator");
     const bool direct = rp->integrator == SPT_INTEGRATOR_DIRECT_ALL, directOne = rp->integrator == SPT_INTEGRATOR_DIRECT_ONE;
-    if ((direct || directOne) && s->dev.has_specular) return fail(SPT_ERR_UNSUPP, "directlighting with specular materials is not supported");
+    if (directOne && s->dev.has_specular) return fail(SPT_ERR_UNSUPP, "directlighting strategy \"one\" with specular materials is not supported");
+    if (direct && s->dev.has_specular && s->dev.has_ext) return fail(SPT_ERR_UNSUPP, "directlighting with specular AND textured / substrate / measured materials is not supported");
     if (direct && s->dev.n_lights == 0) return fail(SPT_ERR_UNSUPP, "directlighting needs at least one light");
     if (direct && !s->direct_pow2) return fail(SPT_ERR_ARG, "directlighting: every light's n_samples must be a power of two (Sampler::RoundSize)");
     const int sub = direct ? s->direct_slots : 1;                 // jobs per camera hit
     RenderCfg cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.cam = *cam; cfg.spp = rp->spp; cfg.max_depth = (direct || directOne) ? 0 : rp->max_depth;
-    cfg.integrator = rp->integrator; cfg.sub = sub;
+    // directlighting: one level, or - on scenes with specular materials - the levels of its SpecularReflect / SpecularTransmit tree
+    const bool tree = direct && s->dev.has_specular && rp->max_depth > 1;
+    cfg.cam = *cam; cfg.spp = rp->spp; cfg.max_depth = tree ? rp->max_depth - 1 : ((direct || directOne) ? 0 : rp->max_depth);
+    cfg.integrator = rp->integrator; cfg.sub = sub; cfg.tree = tree ? 1 : 0;
     cfg.diff_scale = 1.f / sqrtf((float)rp->spp);
     for (cfg.spp_shift = 0; (1 << cfg.spp_shift) < cfg.spp; ++cfg.spp_shift) {}
     cfg.x0 = rp->x_start; cfg.y0 = rp->y_start; cfg.x1 = rp->x_end; cfg.y1 = rp->y_end;
@@ -1028,7 +1048,7 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
     // Waves: by default the rank's pixels are cut into a multiple of max_lanes waves, each at most
     // 2^25 / max_lanes paths (17 GB of state over all lanes), dealt to the lanes in turn; small jobs
     // (< 2^19 paths per wave) use fewer lanes, down to one wave on one lane.
-    const uint64_t slots_pp = (uint64_t)rp->spp;                       // paths per pixel
+    const uint64_t slots_pp = (uint64_t)rp->spp * (tree ? tree_slots() : 1);     // path slots per pixel (tree: the samples + their nodes)
     const uint64_t mem_pp = slots_pp * (uint64_t)std::max(1, (sub + 3) / 4);   // directlighting: ~140 B per job on top of ~450 B per path
     const int depth = cfg.max_depth;
     const uint64_t local_samples = local_pixels * slots_pp;
@@ -1051,7 +1071,7 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
     int n_lanes, rc;
     for (;;) {
         n_waves = (size_t)((local_pixels + wave_pixels - 1) / wave_pixels);
-        n_lanes = (int)std::min<size_t>((size_t)s->max_lanes, std::max<size_t>(n_waves, 1));
+        n_lanes = tree ? 1 : (int)std::min<size_t>((size_t)s->max_lanes, std::max<size_t>(n_waves, 1));     // tree: every range is checked before it reaches the film
         rc = ensure_wave(s, n_lanes, (uint32_t)(wave_pixels * slots_pp), depth, std::max<size_t>(n_waves, 1), (uint32_t)sub);
         // a part with less free memory than the default sizing assumes: smaller waves instead of an error
         if (rc != SPT_ERR_CUDA || wave_pixels * slots_pp <= (1u << 16)) break;
@@ -1070,11 +1090,41 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
     CU(cudaEventRecord(s->ev0, st));
     for (int k = 1; k < n_lanes; ++k) CU(cudaStreamWaitEvent(s->lane[k].stream, s->ev0, 0));       // fork
     uint64_t samples = 0;
+    std::vector<uint32_t> hc_tree;          // tree mode: the counter blocks of the pixel ranges that fitted, in the order they ran
+    if (tree) {
+        // The node pool of a wave is what its buffers hold beyond the camera samples: (SPT_TREE_SLOTS - 1) per sample on average.
+        // A range whose trees need more (a window full of glass) is NOT added to the film; it is cut in two and each half runs in
+        // the same buffers with twice the pool per sample - down to the full binary tree, which always fits.
+        const WaveBuffers &wb = s->lane[0].wb;
+        std::vector<std::pair<uint64_t, uint64_t>> todo;                     // {first pixel, pixels}, a stack
+        for (size_t w = n_waves; w-- > 0;) todo.push_back({(uint64_t)w * wave_pixels, std::min<uint64_t>(wave_pixels, local_pixels - (uint64_t)w * wave_pixels)});
+        std::vector<uint32_t> blk(per_wave);
+        while (!todo.empty()) {
+            const uint64_t base = todo.back().first, np = todo.back().second;
+            todo.pop_back();
+            CU(cudaMemsetAsync(s->counts, 0, per_wave * 4, st));
+            cfg.pixel_base = base;
+            cfg.n_samples = (uint32_t)(np * (uint64_t)rp->spp);
+            run_wave(s, cfg, src, s->counts, 0);
+            CU(cudaMemcpyAsync(blk.data(), s->counts, per_wave * 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            if (blk[12]) {
+                if (np == 1) return fail(SPT_ERR_UNSUPP, "specular tree: one pixel's samples spawn more nodes than a wave holds");
+                todo.push_back({base + np / 2, np - np / 2});
+                todo.push_back({base, np / 2});
+                continue;
+            }
+            unsigned gw = (unsigned)std::min<uint64_t>((np * 32 + 255) / 256, (uint64_t)num_sms() * 16);
+            spt_launch_film_add((int)gw, st, fv, s->dev.tables, wb.img_xy, wb.L, wb.cap, (uint32_t)(np * rp->spp), rp->spp);
+            s->mark(SPT_K_FILM, 0);
+            hc_tree.insert(hc_tree.end(), blk.begin(), blk.end());
+        }
+    } else
     for (size_t w = 0; w < n_waves; ++w) {
         const int li = (int)(w % (size_t)n_lanes);
         cfg.pixel_base = (uint64_t)w * wave_pixels;
         uint64_t np = std::min<uint64_t>(wave_pixels, local_pixels - cfg.pixel_base);
-        cfg.n_samples = (uint32_t)(np * slots_pp);
+        cfg.n_samples = (uint32_t)(np * (uint64_t)rp->spp);
         run_wave(s, cfg, src, s->counts + w * per_wave, li);
         unsigned gw = (unsigned)std::min<uint64_t>((np * 32 + 255) / 256, (uint64_t)num_sms() * 16);
         const WaveBuffers &wb = s->lane[li].wb;
@@ -1095,6 +1145,7 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
     cudaEventElapsedTime(&ms, s->ev0, s->ev1);
     s->stats.render_ms = ms;
     s->class_times_pending = true;          // ~80 cudaEventElapsedTime calls: only when spt_get_stats asks (not between frames)
+    if (tree) { hc.swap(hc_tree); n_waves = hc.size() / per_wave; }
     // sample slots of tiles that overhang the sample extent carry rays that cannot hit anything: not samples
     uint64_t slots = 0, valid_pixels = 0;
     for (size_t w = 0; w < n_waves; ++w) slots += hc[w * per_wave];

@@ -44,7 +44,8 @@ __global__ void __launch_bounds__(256) k_gen_camera(RenderCfg cfg, SampleSource 
     }
     // bounce 0 walks the wave in sample order: no queue (queue == NULL means identity), one counter write
     // instead of a million same-address atomics
-    if (blockIdx.x == 0 && threadIdx.x == 0) *count_out = cfg.n_samples;
+    // (word 11 of the row: the next free node slot of a specular tree under directlighting, RenderCfg::tree)
+    if (blockIdx.x == 0 && threadIdx.x == 0) { *count_out = cfg.n_samples; count_out[11] = cfg.n_samples; }
 }
 
 __global__ void k_camera_rays(SptCameraDesc cam, const float *samples, uint32_t n, float *out) {

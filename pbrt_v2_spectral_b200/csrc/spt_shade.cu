@@ -80,11 +80,13 @@ __global__ void __launch_bounds__(256) k_compact_hits(const uint32_t *__restrict
 // Camera rays that escape: SamplerRenderer::Li's miss branch (samplerrenderer.cpp:239-243), the sum of
 // Light::Le over all lights - only the infinite light is non-zero. Later bounces: the same sum times the
 // throughput, but only for a ray that left a specular bounce (path.cpp:106-108).
-__global__ void __launch_bounds__(128) k_miss_env(DevScene sc, WaveBuffers wb, int bounce, const uint32_t *queue, const uint32_t *count) {
+// tree (directlighting on scenes with specular materials): an escaped node of any level adds T * Le to its root's row
+// (samplerrenderer.cpp:239-243 runs for every ray of the recursion); siblings may meet there, hence the atomics.
+__global__ void __launch_bounds__(128) k_miss_env(DevScene sc, WaveBuffers wb, int bounce, int tree, const uint32_t *queue, const uint32_t *count) {
     uint32_t n = *count;
     for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
         uint32_t i = queue[q];
-        if (bounce > 0 && !(wb.pflags[i] & 1u)) continue;
+        if (bounce > 0 && !tree && !(wb.pflags[i] & 1u)) continue;
         float4 d4 = wb.ray_d[i];
         float Le[NB];
         for (int c = 0; c < NB; ++c) Le[c] = 0.f;
@@ -96,6 +98,7 @@ __global__ void __launch_bounds__(128) k_miss_env(DevScene sc, WaveBuffers wb, i
                 for (int c = 0; c < NB; ++c) Le[c] += illum_band(*sc.tables, k, c);
             }
         if (bounce == 0) { for (int c = 0; c < NB; ++c) wb.L[band_off(i, c)] = Le[c]; }
+        else if (tree) { const uint32_t r = wb.root[i]; for (int c = 0; c < NB; ++c) atomicAdd(&wb.L[band_off(r, c)], wb.T[0][band_off(i, c)] * Le[c]); }
         else for (int c = 0; c < NB; ++c) wb.L[band_off(i, c)] += wb.T[bounce & 1][band_off(i, c)] * Le[c];
     }
 }
@@ -128,7 +131,8 @@ __device__ __forceinline__ float2 dir_coef(int mtype, bool on, const DirTerms &t
 template <bool SPEC, bool EXT, bool DIRECT = false, bool MEAS = false>
 __global__ void __launch_bounds__(128, SPT_SHADE_MINBLOCKS) k_shade(DevScene sc, RenderCfg cfg, SampleSource src, WaveBuffers wb, int bounce,
                                                const uint32_t *queue, const uint32_t *count,
-                                               uint32_t *shadow_count, uint32_t *mis_count, uint32_t *elided_count, uint32_t *mis_any_count) {
+                                               uint32_t *shadow_count, uint32_t *mis_count, uint32_t *elided_count, uint32_t *mis_any_count,
+                                               uint32_t *next_queue, uint32_t *next_count, uint32_t *node_ctr) {
     uint32_t n = *count;
     // directlighting (EXT kernels only): a vertex carries `sub` JOBS, one per (light, light sample) of UniformSampleAllLights
     // (integrator.cpp:39-71); the vertex is set up once and the per-direction part below runs per job, its records and
@@ -138,7 +142,7 @@ __global__ void __launch_bounds__(128, SPT_SHADE_MINBLOCKS) k_shade(DevScene sc,
     for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < ((n + 31u) & ~31u); q += gridDim.x * blockDim.x) {
         bool active = q < n;
         uint32_t i = active ? queue[q] : 0;
-        uint32_t slot = 0, s_idx = 0, pk = 0;
+        uint32_t slot = 0, s_idx = 0, pk = 0, i0 = 0;
         Bsdf bsdf;
         v3 p = V(0, 0, 0), n_s = p, woW = p, wo = p;
         float eps = 0.f;
@@ -152,7 +156,7 @@ __global__ void __launch_bounds__(128, SPT_SHADE_MINBLOCKS) k_shade(DevScene sc,
             shape_record(sc, sc.prim_kind[slot], sc.prim_flags[slot], sc.prim_data[slot], ray, wb.hit_t[i], &hit);
             // emitted light at the first vertex (path.cpp:55-56, directlighting.cpp:80; Intersection::Le, intersection.cpp:53-56):
             // K6 starts L from the emitter's spectrum instead of from black
-            if (bounce == 0 || (SPEC && (wb.pflags[i] & 1u))) {
+            if (bounce == 0 || (DIRECT && cfg.tree) || (SPEC && !DIRECT && (wb.pflags[i] & 1u))) {     // directlighting.cpp:80: at every level
                 int li = sc.prim_light[slot];
                 if (li >= 0 && dot(hit.nn, vneg(ray.d)) > 0.f) emitter = li;
             }
@@ -165,11 +169,36 @@ __global__ void __launch_bounds__(128, SPT_SHADE_MINBLOCKS) k_shade(DevScene sc,
             p = hit.p; n_s = bsdf.nn; woW = vneg(ray.d);
             wo = w2l(bsdf, woW);
             eps = hit.rayEpsilon;
-            s_idx = src.smp ? 0u : (i & ((uint32_t)cfg.spp - 1u));
+            // the camera sample whose Sample arrays this vertex reads: itself, or the root of its specular tree
+            if (DIRECT && cfg.tree && bounce > 0) i0 = wb.root[i];
+            else i0 = i;
+            s_idx = src.smp ? 0u : (i0 & ((uint32_t)cfg.spp - 1u));
             if (!src.smp) {
                 int px, py;
-                wave_pixel(cfg, cfg.pixel_base + (i >> cfg.spp_shift), &px, &py);
+                wave_pixel(cfg, cfg.pixel_base + (i0 >> cfg.spp_shift), &px, &py);
                 pk = pixel_key(src.seed, pix_key(px, py));
+            }
+            if (SPEC && DIRECT && cfg.tree && bounce < cfg.max_depth && bsdf_is_specular(bsdf)) {
+                // SpecularReflect / SpecularTransmit (integrator.cpp:169-250): a child node per specular component, its ray and
+                // {parent, material row | component << 16, f |cos| / pdf without the spectrum} (k_spawn_T multiplies the rows)
+#pragma unroll 1
+                for (int comp = 0; comp < 2; ++comp) {
+                    if (!((bsdf.compMask >> comp) & 1)) continue;
+                    Bsdf one = bsdf;
+                    one.compMask = 1 << comp;
+                    v3 wl; float cR, cT, pdfS;
+                    if (!specular_sample(one, wo, 0.f, &wl, &cR, &cT, &pdfS)) continue;
+                    const v3 wiW = l2w(bsdf, wl);
+                    const float ad = absdot(wiW, n_s);
+                    const float sc_ = (comp == 0 ? cR : cT) * ad / pdfS;
+                    if (!(pdfS > 0.f) || sc_ == 0.f || ad == 0.f) continue;
+                    const uint32_t child = atomicAdd(node_ctr, 1u);
+                    if (child >= wb.cap) { node_ctr[1] = 1u; continue; }       // node pool exhausted: reported by spt_render
+                    wb.ray_o[child] = make_float4(p.x, p.y, p.z, eps);
+                    wb.ray_d[child] = make_float4(wiW.x, wiW.y, wiW.z, SPT_INF);
+                    wb.g3[child] = make_float4(__uint_as_float(i), __uint_as_float((uint32_t)sc.prim_material[slot] | (uint32_t)comp << 16), sc_, 0.f);
+                    next_queue[atomicAdd(next_count, 1u)] = child;
+                }
             }
         }
         for (uint32_t dj = 0; dj < nj; ++dj) {
@@ -187,7 +216,7 @@ __global__ void __launch_bounds__(128, SPT_SHADE_MINBLOCKS) k_shade(DevScene sc,
                     }
                     for (int k = 0; k < 10; ++k) u[k] = 0.f;
                     rr = 0.f;
-                    direct_dims(src, i, pk, s_idx, directLight, prefix, sc.lights[directLight].n_samples, jj, cfg.sub, u);
+                    direct_dims(src, i0, pk, s_idx, directLight, prefix, sc.lights[directLight].n_samples, jj, cfg.sub, u);
                 } else if (EXT && cfg.integrator == SPT_INTEGRATOR_DIRECT_ONE && src.smp) {
                     // strategy "one" (directlighting.cpp:61-68): {light component, light number, bsdf component}, 2 volume floats,
                     // {light position, bsdf direction}; generated samples take the path sampler's first-bounce dimensions
@@ -697,7 +726,9 @@ __global__ void __launch_bounds__(32 * ACC_WARPS, 8) k_addlight(DevScene sc, Ren
 // radiance arrives). Phase B, lane = band: per hit the material row is read once, its jobs' staged values are shared-memory
 // broadcasts, and the radiance row is written once - no throughput, no continuation.
 #define ACCD_WARPS 4
-__global__ void __launch_bounds__(32 * ACCD_WARPS, 8) k_accumulate_direct(DevScene sc, RenderCfg cfg, WaveBuffers wb,
+// level > 0 (RenderCfg::tree): the hit is a node of a camera sample's SpecularReflect / SpecularTransmit tree - its radiance times
+// the node's throughput row is ADDED to the root's row (integrator.cpp:196,244: L = f * Li * AbsDot(wi, n) / pdf, level by level).
+__global__ void __launch_bounds__(32 * ACCD_WARPS, 8) k_accumulate_direct(DevScene sc, RenderCfg cfg, WaveBuffers wb, int level,
                                                                        const uint32_t *__restrict__ queue, const uint32_t *__restrict__ count) {
     __shared__ float4 stage_all[ACCD_WARPS][32][4];
     const uint32_t n = *count;
@@ -804,11 +835,42 @@ __global__ void __launch_bounds__(32 * ACCD_WARPS, 8) k_accumulate_direct(DevSce
                     } else LcL = LcB = __ldg(sc.lights[bits >> 16].spectrum + lane);
                     L += fL * LcL * sc4.x + fB * LcB * sc4.y;
                 }
-                if (sub <= 32u) wb.L[band_off(i, lane)] = L; else Lacc += L;
+                if (sub <= 32u) {
+                    if (level == 0) wb.L[band_off(i, lane)] = L;
+                    else atomicAdd(&wb.L[band_off(wb.root[i], lane)], wb.T[0][band_off(i, lane)] * L);
+                } else Lacc += L;
             }
             __syncwarp();
         }
-        if (sub > 32u) wb.L[band_off(queue[h0], lane)] = Lacc;
+        if (sub > 32u) {
+            const uint32_t i = queue[h0];
+            if (level == 0) wb.L[band_off(i, lane)] = Lacc;
+            else atomicAdd(&wb.L[band_off(wb.root[i], lane)], wb.T[0][band_off(i, lane)] * Lacc);
+        }
+    }
+}
+
+// ---- specular tree: throughput rows of the nodes K5 spawned ----------------------------------------------------------
+// T[child] = T[parent] * K * (f |cos| / pdf without the spectrum), K = Kr (component 0) or Kt (1) of the parent's material;
+// a warp takes four children per pass, 8 lanes x float4 per row. Level 0 parents are camera samples (T = 1, root = itself).
+__global__ void __launch_bounds__(128) k_spawn_T(DevScene sc, WaveBuffers wb, int level, const uint32_t *__restrict__ queue, const uint32_t *__restrict__ count) {
+    const uint32_t n = *count;
+    const int lane = threadIdx.x & 31, grp = lane >> 3, bg = lane & 7;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t q0 = warp * 4u; q0 < n; q0 += nwarps * 4u) {
+        const uint32_t q = q0 + (uint32_t)grp;
+        if (q >= n) continue;
+        const uint32_t child = queue[q];
+        const float4 rec = wb.g3[child];
+        const uint32_t parent = __float_as_uint(rec.x), mbits = __float_as_uint(rec.y);
+        const SptMaterial &m = sc.materials[mbits & 0xffffu];
+        const F4 K = ld4((mbits >> 16) ? m.spec1 : m.spec0, bg);
+        const F4 Tp = level == 0 ? splat4(1.f) : ld4g(wb.T[0] + (size_t)parent * NBP, bg);
+        F4 Tc;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) Tc.v[c] = Tp.v[c] * (K.v[c] * rec.z);
+        st4(wb.T[0] + (size_t)child * NBP, bg, Tc);
+        if (bg == 0) wb.root[child] = level == 0 ? parent : wb.root[parent];
     }
 }
 
@@ -967,16 +1029,20 @@ void spt_launch_compact_hits(int grid, cudaStream_t st, const uint32_t *queue, c
                              uint32_t *hit_queue, uint32_t *hit_count, uint32_t *miss_queue, uint32_t *miss_count, float *black_L) {
     k_compact_hits<<<grid, 256, 0, st>>>(queue, count, hit_slot, hit_queue, hit_count, miss_queue, miss_count, black_L);
 }
-void spt_launch_miss_env(int grid, cudaStream_t st, const DevScene &sc, const WaveBuffers &wb, int bounce, const uint32_t *queue, const uint32_t *count) {
-    k_miss_env<<<grid, 128, 0, st>>>(sc, wb, bounce, queue, count);
+void spt_launch_miss_env(int grid, cudaStream_t st, const DevScene &sc, const WaveBuffers &wb, int bounce, int tree, const uint32_t *queue, const uint32_t *count) {
+    k_miss_env<<<grid, 128, 0, st>>>(sc, wb, bounce, tree, queue, count);
+}
+void spt_launch_spawn_T(int grid, cudaStream_t st, const DevScene &sc, const WaveBuffers &wb, int level, const uint32_t *queue, const uint32_t *count) {
+    k_spawn_T<<<grid, 128, 0, st>>>(sc, wb, level, queue, count);
 }
 void spt_launch_shade(int grid, cudaStream_t st, const DevScene &sc, const RenderCfg &cfg, const SampleSource &src, const WaveBuffers &wb,
                       int bounce, const uint32_t *queue, const uint32_t *count, uint32_t *shadow_count, uint32_t *mis_count,
-                      uint32_t *elided_count, uint32_t *mis_any_count) {
-#define SPT_SHADE4(S, E, D, M) k_shade<S, E, D, M><<<grid, 128, 0, st>>>(sc, cfg, src, wb, bounce, queue, count, shadow_count, mis_count, elided_count, mis_any_count)
+                      uint32_t *elided_count, uint32_t *mis_any_count, uint32_t *next_queue, uint32_t *next_count, uint32_t *node_ctr) {
+#define SPT_SHADE4(S, E, D, M) k_shade<S, E, D, M><<<grid, 128, 0, st>>>(sc, cfg, src, wb, bounce, queue, count, shadow_count, mis_count, elided_count, mis_any_count, next_queue, next_count, node_ctr)
 #define SPT_SHADE(S, E) SPT_SHADE4(S, E, false, false)
-    if (cfg.integrator == SPT_INTEGRATOR_DIRECT_ALL) {        // never with specular materials (spt_render refuses)
-        if (sc.has_measured) SPT_SHADE4(false, true, true, true); else SPT_SHADE4(false, true, true, false);
+    if (cfg.integrator == SPT_INTEGRATOR_DIRECT_ALL) {
+        if (sc.has_specular) { if (sc.has_measured) SPT_SHADE4(true, true, true, true); else SPT_SHADE4(true, true, true, false); }
+        else if (sc.has_measured) SPT_SHADE4(false, true, true, true); else SPT_SHADE4(false, true, true, false);
     } else if (sc.has_measured) { if (sc.has_specular) SPT_SHADE4(true, true, false, true); else SPT_SHADE4(false, true, false, true); }
     else if (sc.has_ext || cfg.integrator != SPT_INTEGRATOR_PATH) { if (sc.has_specular) SPT_SHADE(true, true); else SPT_SHADE(false, true); }
     else { if (sc.has_specular) SPT_SHADE(true, false); else SPT_SHADE(false, false); }
@@ -990,7 +1056,7 @@ void spt_launch_advance(int grid, cudaStream_t st, const DevScene &sc, const Ren
 }
 void spt_launch_addlight(int grid, cudaStream_t st, const DevScene &sc, const RenderCfg &cfg, const WaveBuffers &wb, int bounce,
                          const uint32_t *queue, const uint32_t *count) {
-    if (cfg.integrator == SPT_INTEGRATOR_DIRECT_ALL) k_accumulate_direct<<<grid, 128, 0, st>>>(sc, cfg, wb, queue, count);
+    if (cfg.integrator == SPT_INTEGRATOR_DIRECT_ALL) k_accumulate_direct<<<grid, 128, 0, st>>>(sc, cfg, wb, cfg.tree ? bounce : 0, queue, count);
     else if (sc.has_ext) k_addlight<true><<<grid, 128, 0, st>>>(sc, cfg, wb, bounce, queue, count);
     else k_addlight<false><<<grid, 128, 0, st>>>(sc, cfg, wb, bounce, queue, count);
 }

@@ -110,9 +110,9 @@ __device__ __forceinline__ bool quadratic(float A, float B, float C, float *t0, 
 }
 
 __device__ inline void sphere_fill(const SptQuadric &q, const SptXform &xf, int flags, v3 phit, float phi, float thit, Hit *hit);
-// Sphere (src/shapes/sphere.cpp:50-149, :152-201). hit == NULL: accept test only.
+// Sphere (src/shapes/sphere.cpp:50-149, :152-201). hit == NULL: accept test only; phit_obj: the object-space hit point.
 __device__ inline bool sphere_intersect(const DevScene &sc, const SptQuadric &q, int flags, const Ray &r,
-                                        float *tout, Hit *hit) {
+                                        float *tout, Hit *hit, v3 *phit_obj = nullptr) {
     const SptXform &xf = sc.xforms[q.xform];
     Ray ray = r;
     ray.o = xf_point(xf.minv, r.o);
@@ -152,6 +152,7 @@ __device__ inline bool sphere_intersect(const DevScene &sc, const SptQuadric &q,
         if ((zmin > -radius && phit.z < zmin) || (zmax < radius && phit.z > zmax) || phi > phiMax) return false;
     }
     *tout = thit;
+    if (phit_obj) *phit_obj = (clipped || hit) ? phit : ray_at(ray, thit);
     if (!hit) return true;
     sphere_fill(q, xf, flags, phit, phi, thit, hit);
     return true;

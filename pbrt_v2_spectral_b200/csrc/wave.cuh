@@ -40,6 +40,8 @@ struct WaveBuffers {
                                       // 128-byte row each (a table look-up has no wavelength-independent factorisation)
     float4 *laux;                     // infinite light only: RGB radiance of the sampled direction
     uint32_t *pflags;                 // scenes with specular materials: bit 0 = the ray of this path left a specular bounce
+    uint32_t *root;                   // directlighting on scenes with specular materials (RenderCfg::tree): the camera sample a node of
+                                      // the SpecularReflect / SpecularTransmit tree belongs to (slots >= n_samples are such nodes)
     float2 *img_xy;
     float *T[2], *L;                  // [cap][NBP]: band_off(). T[b & 1] = the throughput ARRIVING at the vertex of bounce b (k_advance of
                                       // bounce b writes the other buffer; k_addlight of bounce b still reads this one)
@@ -66,6 +68,8 @@ struct RenderCfg {
     int sub;                          // jobs per path vertex: 1, or under directlighting the sum of the lights' n_samples -
                                       // job r = vertex * sub + j is light sample j of UniformSampleAllLights
     float diff_scale;                 // 1/sqrt(samplesPerPixel): RayDifferential::ScaleDifferentials (samplerrenderer.cpp:91)
+    int tree;                         // directlighting with specular materials: every hit may spawn a reflected and a transmitted node
+                                      // (integrator.cpp:169-250) down to max_depth levels; nodes live in slots n_samples .. cap-1
 };
 
 // flags in rec2.z (low 12 bits)

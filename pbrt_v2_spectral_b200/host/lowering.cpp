@@ -666,12 +666,9 @@ struct Lowerer {
             out->params.integrator = SPT_INTEGRATOR_PATH;
             out->params.max_depth = pi->maxDepth;
         } else if (const DirectLightingIntegrator *dl = dynamic_cast<const DirectLightingIntegrator *>(surf)) {
-            // directlighting.cpp:70-105: UniformSampleAllLights (strategy "all", the default) or UniformSampleOneLight at the camera hit; its
-            // SpecularReflect / SpecularTransmit recursion only does anything for specular BxDFs, which are not lowered under it
-
-            for (size_t i = 0; i < out->materials.size(); ++i)
-                if (out->materials[i].type == SPT_MAT_MIRROR || out->materials[i].type == SPT_MAT_GLASS)
-                    return fail("directlighting integrator with specular materials is not supported");
+            // directlighting.cpp:70-105: UniformSampleAllLights (strategy "all", the default) or UniformSampleOneLight at every hit, and the
+            // SpecularReflect / SpecularTransmit recursion (integrator.cpp:169-250) down to maxDepth - which only does anything for
+            // specular BxDFs (mirror, glass, the subsurface material's reflection)
             out->params.integrator = dl->strategy == SAMPLE_ALL_UNIFORM ? SPT_INTEGRATOR_DIRECT_ALL : SPT_INTEGRATOR_DIRECT_ONE;
             out->params.max_depth = dl->maxDepth;
         } else return fail("surface integrator is neither the path nor the directlighting integrator");

@@ -184,27 +184,16 @@ def test_light_sampling_bit_exact(shim, name):
     p = np.ascontiguousarray(r[:, :3] + r[:, 3:6] * t[hit, None], np.float32)
     rng = np.random.default_rng(9)
     u = rng.random((len(hit), 3)).astype(np.float32)
+    # a third of the samples at the rim of the cone Sphere::Sample draws from (u1 -> 0, sphere.cpp:228-252): there the float
+    # quadratic of Sphere::Intersect misses the sphere by rounding, Sample falls back to the point of closest approach, and
+    # what ShapeSet::Sample's re-intersection (light.cpp:141-149) makes of that point decides whether the sample is black
+    u[::3, 0] *= 0.02
     w = _unit(rng, len(hit), upper=False)
     for light in range(scene.desc.n_lights):
         a = np.zeros((len(hit), 9), np.float32); b = np.zeros_like(a)
         shim.hd_light_sample(C.byref(scene.desc), light, _p(p), _p(u), len(hit), _p(a))
         O.lib().orc_light_sample(C.byref(scene.desc), light, _p(p), _p(u), len(hit), _p(b))
-        lrow = np.frombuffer(scene.a["lights"].tobytes(), np.int32).reshape(-1, O.D.SIZEOF_LIGHT // 4)[light]
-        shapes = np.frombuffer(scene.a["light_shapes"].tobytes(), np.int32).reshape(-1, 4)
-        one_sphere = lrow[0] == 0 and lrow[2] == 1 and shapes[lrow[1], 0] == 1
-        if one_sphere:
-            # the one deliberate shortcut of the device code: ShapeSet::Sample re-intersects the sampled point with every
-            # shape of the set (light.cpp:141-149); for a set of ONE sphere that returns the sampled point itself up to
-            # rounding, and the re-intersection is skipped (csrc/shade.cuh light_sample)
-            off = scene.a["prim_light"][slot[hit]] < 0                  # not the points ON the emitter (distance ~ 0)
-            # measured deviation of the shortcut: directions 2e-5, the shadow segment's length 2.4e-4 (grazing samples) -
-            # inside the 1e-3 by which Sample_L shortens that segment (light.h:79-88)
-            assert np.allclose(a[off][:, [0, 1, 2, 4, 5, 6]], b[off][:, [0, 1, 2, 4, 5, 6]], rtol=0, atol=5e-5), "direction, light %d of %s" % (light, name)
-            assert np.allclose(a[off][:, 3], b[off][:, 3], rtol=1e-5), "pdf, light %d of %s" % (light, name)
-            assert np.allclose(a[off][:, 7], b[off][:, 7], rtol=5e-4), "shadow segment, light %d of %s" % (light, name)
-            assert np.array_equal(a[:, 8], b[:, 8])
-        else:
-            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), "Sample_L of light %d of %s" % (light, name)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), "Sample_L of light %d of %s" % (light, name)
         # Light::Pdf towards the sampled directions (non-zero for area / infinite lights) and towards random ones
         for dirs in (np.ascontiguousarray(b[:, :3]), w):
             pa = np.zeros(len(hit), np.float32); pb = np.zeros_like(pa)

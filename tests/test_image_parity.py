@@ -26,7 +26,9 @@ IMAGES = [("killeroo_small", 1024), ("bunny_small", 4096), ("metal_small", 512),
           # the bunny's shipped measured BRDF: under the path integrator (config 2), and bunny.pbrt exactly as shipped
           ("bunny_measured_small", 4096), ("bunny_shipped_small", 1024),
           # the half-angle (MERL-format) measured BRDF
-          ("tiny_merl_small", 32768)]
+          ("tiny_merl_small", 32768),
+          # directlighting with a glass and a mirror killeroo: the SpecularReflect / SpecularTransmit tree (directlighting.cpp:97-107)
+          ("specular_direct_small", 1024)]
 if D.NBANDS == 30:      # the 30-band library (SPT_NBANDS=30): the image the reference built with nSpectralSamples = 30 rendered
     IMAGES = [("killeroo_small30", 1024)]
 

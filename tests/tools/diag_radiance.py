@@ -13,11 +13,11 @@ for name in names:
     lowered, g = O.load_case(os.path.join(O.GOLDEN_BIG, name + ".spt"), os.path.join(O.GOLDEN_BIG, name + ".golden"))
     scene = capi.Scene(lowered)
     out = {}
-    for md in (0, 1, 5):
+    for md in [int(x) for x in os.environ.get("DIAG_MD", "0,1,5").split(",")]:
         out["L_md%d" % md] = scene.shade_samples(g["samples"], g["rng"], max_depth=md)
     scene.close()
     ref = g["L"]
-    L = out["L_md5"]
+    L = out["L_md%d" % lowered.params.max_depth] if ("L_md%d" % lowered.params.max_depth) in out else out["L_md5"]
     err = np.abs(L - ref).max(axis=1) / np.maximum(np.abs(ref).max(axis=1), 1e-6)
     print(name, "bad", int((err > 2e-4).sum()), "of", len(err), "worst", float(err.max()))
     np.savez_compressed(os.path.join(ROOT, "gpurun_out", "diag_%s.npz" % name), **out)
