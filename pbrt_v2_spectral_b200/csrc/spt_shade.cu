@@ -125,11 +125,26 @@ __device__ __forceinline__ float2 dir_coef(int mtype, bool on, const DirTerms &t
 // with a run-time job count the path integrator's kernels kept the vertex set-up live across a loop of one and lost 10 %).
 // MEAS: the scene has a measured BRDF (DevScene::has_measured) - its kd-tree look-up (512 bytes of per-thread stacks and
 // sums) stays out of the kernels of the textured / substrate scenes, which lost 4-6 % to it.
-#ifndef SPT_SHADE_MINBLOCKS
-#define SPT_SHADE_MINBLOCKS 4          // A/B builds: profiles/tools/build_variants.py
+// The kernel is 13 k (plain) to 20 k (EXT) instructions, 205-320 KB, and a vertex runs through ~60 KB of them; the SM's
+// instruction cache holds 32 KB. Warps that drift apart each stream the code from L2 on their own ("no instruction" was
+// 1.7-3.4 of ~8 stall cycles per issue, 5.9 in the EXT kernels). One barrier per vertex at the top of the loop keeps the warps
+// of a block within a few hundred instructions of each other, so a fetched line serves all of them, and a bigger block keeps
+// more warps together (128 registers: 512 threads = one block per SM). Measured (profiles/r02_shade_sync.log, ms per frame):
+//   config 1        128 threads, no barrier 41.7 | 256 + barrier 41.1 | 512 + barrier 40.9, but slower on an 8-GPU run's 1/8 frames
+//   config 3 (EXT)  155.9 | 129.6 | 124.8        bunny.pbrt as shipped (EXT, MEAS)  292.0 | 239.0 | 235.6
+// Barriers between the stages of a vertex as well: no further gain. A/B builds: profiles/tools/build_variants.py.
+#ifndef SPT_SHADE_THREADS_EXT
+#define SPT_SHADE_THREADS_EXT 512
 #endif
+#ifndef SPT_SHADE_THREADS
+#define SPT_SHADE_THREADS 256
+#endif
+#ifndef SPT_SHADE_SYNC
+#define SPT_SHADE_SYNC 1
+#endif
+#define SHADE_THREADS(EXT) ((EXT) ? SPT_SHADE_THREADS_EXT : SPT_SHADE_THREADS)
 template <bool SPEC, bool EXT, bool DIRECT = false, bool MEAS = false>
-__global__ void __launch_bounds__(128, SPT_SHADE_MINBLOCKS) k_shade(DevScene sc, RenderCfg cfg, SampleSource src, WaveBuffers wb, int bounce,
+__global__ void __launch_bounds__(SHADE_THREADS(EXT), 512 / SHADE_THREADS(EXT)) k_shade(DevScene sc, RenderCfg cfg, SampleSource src, WaveBuffers wb, int bounce,
                                                const uint32_t *queue, const uint32_t *count,
                                                uint32_t *shadow_count, uint32_t *mis_count, uint32_t *elided_count, uint32_t *mis_any_count,
                                                uint32_t *next_queue, uint32_t *next_count, uint32_t *node_ctr) {
@@ -139,7 +154,8 @@ __global__ void __launch_bounds__(128, SPT_SHADE_MINBLOCKS) k_shade(DevScene sc,
     // shadow / MIS rays indexed by r = vertex * sub + job. The path integrator has one job per vertex, r = vertex.
     const bool direct = DIRECT;
     const uint32_t nj = DIRECT ? (uint32_t)cfg.sub : 1u;
-    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < ((n + 31u) & ~31u); q += gridDim.x * blockDim.x) {
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < ((n + (SPT_SHADE_SYNC ? SHADE_THREADS(EXT) - 1u : 31u)) & ~(SPT_SHADE_SYNC ? SHADE_THREADS(EXT) - 1u : 31u)); q += gridDim.x * blockDim.x) {
+        if (SPT_SHADE_SYNC) __syncthreads();
         bool active = q < n;
         uint32_t i = active ? queue[q] : 0;
         uint32_t slot = 0, s_idx = 0, pk = 0, i0 = 0;
@@ -1038,7 +1054,7 @@ void spt_launch_spawn_T(int grid, cudaStream_t st, const DevScene &sc, const Wav
 void spt_launch_shade(int grid, cudaStream_t st, const DevScene &sc, const RenderCfg &cfg, const SampleSource &src, const WaveBuffers &wb,
                       int bounce, const uint32_t *queue, const uint32_t *count, uint32_t *shadow_count, uint32_t *mis_count,
                       uint32_t *elided_count, uint32_t *mis_any_count, uint32_t *next_queue, uint32_t *next_count, uint32_t *node_ctr) {
-#define SPT_SHADE4(S, E, D, M) k_shade<S, E, D, M><<<grid, 128, 0, st>>>(sc, cfg, src, wb, bounce, queue, count, shadow_count, mis_count, elided_count, mis_any_count, next_queue, next_count, node_ctr)
+#define SPT_SHADE4(S, E, D, M) k_shade<S, E, D, M><<<(grid * 128 + SHADE_THREADS(E) - 1) / SHADE_THREADS(E), SHADE_THREADS(E), 0, st>>>(sc, cfg, src, wb, bounce, queue, count, shadow_count, mis_count, elided_count, mis_any_count, next_queue, next_count, node_ctr)
 #define SPT_SHADE(S, E) SPT_SHADE4(S, E, false, false)
     if (cfg.integrator == SPT_INTEGRATOR_DIRECT_ALL) {
         if (sc.has_specular) { if (sc.has_measured) SPT_SHADE4(true, true, true, true); else SPT_SHADE4(true, true, true, false); }
