@@ -20,8 +20,10 @@ __device__ inline void concentric_sample_disk(float u1, float u2, float *dx, flo
         else { r = -sy; theta = 6.0f + sx / r; }
     }
     theta *= PI_F / 4.f;
-    *dx = r * cosf(theta);
-    *dy = r * sinf(theta);
+    float st, ct;
+    sin_cos(theta, &st, &ct);
+    *dx = r * ct;
+    *dy = r * st;
 }
 __device__ inline v3 cosine_sample_hemisphere(float u1, float u2) {                        // montecarlo.h:120-125
     v3 ret;
@@ -33,13 +35,17 @@ __device__ inline v3 uniform_sample_sphere(float u1, float u2) {                
     float z = 1.f - 2.f * u1;
     float r = sqrtf(stdmaxf(0.f, 1.f - z * z));
     float phi = 2.f * PI_F * u2;
-    return V(r * cosf(phi), r * sinf(phi), z);
+    float sp, cp;
+    sin_cos(phi, &sp, &cp);
+    return V(r * cp, r * sp, z);
 }
 __device__ inline v3 uniform_sample_cone(float u1, float u2, float costhetamax, v3 x, v3 y, v3 z) {   // :405-412
     float costheta = lerpf(u1, costhetamax, 1.f);
     float sintheta = sqrtf(1.f - costheta * costheta);
     float phi = u2 * 2.f * PI_F;
-    return vadd(vadd(vmul(x, cosf(phi) * sintheta), vmul(y, sinf(phi) * sintheta)), vmul(z, costheta));
+    float sp, cp;
+    sin_cos(phi, &sp, &cp);
+    return vadd(vadd(vmul(x, cp * sintheta), vmul(y, sp * sintheta)), vmul(z, costheta));
 }
 __device__ __forceinline__ float uniform_cone_pdf(float c) { return 1.f / (2.f * PI_F * (1.f - c)); }
 __device__ __forceinline__ float power_heuristic(float fPdf, float gPdf) {                 // montecarlo.h:254-257

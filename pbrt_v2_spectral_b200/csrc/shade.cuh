@@ -374,6 +374,8 @@ __device__ __forceinline__ float fr_cond(float cosi, float eta, float k) {      
 // accurate to 1 ulp, so the error of the exponent argument is e*|log2 x|*6e-8: negligible wherever the
 // result is not vanishing (radiance tests compare at 2e-4 relative).
 __device__ __forceinline__ float pow01(float x, float e) { return exp2f(e * log2f(x)); }
+// x^5 (the Schlick-style terms of FresnelBlend, reflection.cpp:224-236): three products, within 2 ulp of the reference's powf(x, 5)
+__device__ __forceinline__ float pow5(float x) { const float x2 = x * x; return x2 * x2 * x; }
 
 // scalar part of BSDF::f (reflection.cpp:604-618, with Lambertian :165-167, OrenNayar :170-193,
 // Microfacet :203-214, G reflection.h:395-402, Blinn::D reflection.h:419-422) and, from the same
@@ -416,15 +418,15 @@ __device__ inline void bsdf_terms(const Bsdf &b, v3 woW, v3 wiW, v3 wo, v3 wi, D
         const float costhetah = abs_cos_theta(wh);
         const float ds = 1.f - costhetah * costhetah;
         const float e = (b.ex * wh.x * wh.x + b.ey * wh.y * wh.y) / ds;
-        const float pw = powf(costhetah, e);
+        const float pw = pow01(costhetah, e);            // unused when ds == 0 (e = 0/0)
         float anisoPdf = 0.f;                                        // Anisotropic::Pdf, reflection.cpp:420-432
         if (ds > 0.f && dot(wo, wh) > 0.f) anisoPdf = (sqrtf((b.ex + 1.f) * (b.ey + 1.f)) * INV_TWOPI_F * pw) / (4.f * dot(wo, wh));
         *pdfAll = same ? .5f * (abs_cos_theta(wi) * INV_PI_F + anisoPdf) : 0.f;
         if (!t->reflect || whZero) return;
-        t->a0 = (28.f / (23.f * PI_F)) * (1.f - powf(1.f - .5f * abs_cos_theta(wi), 5.f)) * (1.f - powf(1.f - .5f * abs_cos_theta(wo), 5.f));
+        t->a0 = (28.f / (23.f * PI_F)) * (1.f - pow5(1.f - .5f * abs_cos_theta(wi))) * (1.f - pow5(1.f - .5f * abs_cos_theta(wo)));
         const float D = ds == 0.f ? 0.f : sqrtf((b.ex + 2.f) * (b.ey + 2.f)) * INV_TWOPI_F * pw;      // Anisotropic::D, reflection.h:438-444
         t->a1 = D / (4.f * absdot(wi, wh) * stdmaxf(abs_cos_theta(wi), abs_cos_theta(wo)));
-        t->a2 = powf(1 - dot(wi, wh), 5.f);
+        t->a2 = pow5(1 - dot(wi, wh));
         t->mf = true;
         return;
     }
@@ -474,8 +476,9 @@ __device__ __forceinline__ float f_band(const SptMaterial &m, bool orenNayar, co
 __device__ inline void aniso_first_quadrant(const Bsdf &b, float u1, float u2, float *phi, float *costheta) {
     if (b.ex == b.ey) *phi = PI_F * u1 * 0.5f;
     else *phi = atanf(sqrtf((b.ex + 1.f) / (b.ey + 1.f)) * tanf(PI_F * u1 * 0.5f));
-    float cosphi = cosf(*phi), sinphi = sinf(*phi);
-    *costheta = powf(u2, 1.f / (b.ex * cosphi * cosphi + b.ey * sinphi * sinphi + 1));
+    float cosphi, sinphi;
+    sin_cos(*phi, &sinphi, &cosphi);
+    *costheta = pow01(u2, 1.f / (b.ex * cosphi * cosphi + b.ey * sinphi * sinphi + 1));
 }
 // pdfOverride (substrate only): FresnelBlend::Sample_f returns before `*pdf = Pdf(wo, *wi)` when the direction
 // sampled from the microfacet distribution falls in the other hemisphere (reflection.cpp:444-446), leaving the
@@ -492,12 +495,15 @@ __device__ inline bool bsdf_sample_dir(const Bsdf &b, v3 wo, float uComp, float 
         } else {                                                     // Anisotropic::Sample_f, reflection.cpp:369-405
             u1 = 2.f * (u1 - .5f);
             float phi, costheta;
-            if (u1 < .25f) aniso_first_quadrant(b, 4.f * u1, u2, &phi, &costheta);
-            else if (u1 < .5f) { u1 = 4.f * (.5f - u1); aniso_first_quadrant(b, u1, u2, &phi, &costheta); phi = PI_F - phi; }
-            else if (u1 < .75f) { u1 = 4.f * (u1 - .5f); aniso_first_quadrant(b, u1, u2, &phi, &costheta); phi += PI_F; }
-            else { u1 = 4.f * (1.f - u1); aniso_first_quadrant(b, u1, u2, &phi, &costheta); phi = 2.f * PI_F - phi; }
+            // the quadrant's own u1, ONE copy of the first-quadrant code, then the quadrant's reflection of phi
+            const int quad = u1 < .25f ? 0 : (u1 < .5f ? 1 : (u1 < .75f ? 2 : 3));
+            const float uq = quad == 0 ? 4.f * u1 : (quad == 1 ? 4.f * (.5f - u1) : (quad == 2 ? 4.f * (u1 - .5f) : 4.f * (1.f - u1)));
+            aniso_first_quadrant(b, uq, u2, &phi, &costheta);
+            if (quad == 1) phi = PI_F - phi; else if (quad == 2) phi += PI_F; else if (quad == 3) phi = 2.f * PI_F - phi;
             float sintheta = sqrtf(stdmaxf(0.f, 1.f - costheta * costheta));
-            v3 wh = V(sintheta * cosf(phi), sintheta * sinf(phi), costheta);
+            float sph, cph;
+            sin_cos(phi, &sph, &cph);
+            v3 wh = V(sintheta * cph, sintheta * sph, costheta);
             if (!same_hemisphere(wo, wh)) wh = vneg(wh);
             wi = vadd(vneg(wo), vmul(wh, 2.f * dot(wo, wh)));
             if (!same_hemisphere(wo, wi)) {
@@ -505,7 +511,7 @@ __device__ inline bool bsdf_sample_dir(const Bsdf &b, v3 wo, float uComp, float 
                 float pdf = 0.f;
                 if (ds > 0.f && dot(wo, wh) > 0.f) {
                     float e = (b.ex * wh.x * wh.x + b.ey * wh.y * wh.y) / ds;
-                    pdf = (sqrtf((b.ex + 1.f) * (b.ey + 1.f)) * INV_TWOPI_F * powf(costhetah, e)) / (4.f * dot(wo, wh));
+                    pdf = (sqrtf((b.ex + 1.f) * (b.ey + 1.f)) * INV_TWOPI_F * pow01(costhetah, e)) / (4.f * dot(wo, wh));
                 }
                 *pdfOverride = pdf;
             }
@@ -987,8 +993,9 @@ __device__ inline void light_sample(const DevScene &sc, int lightIdx, v3 p, floa
     float mapPdf = pdfs[0] * pdfs[1];
     if (mapPdf == 0.f) return;
     float theta = uv[1] * PI_F, phi = uv[0] * 2.f * PI_F;
-    float costheta = cosf(theta), sintheta = sinf(theta);
-    float sinphi = sinf(phi), cosphi = cosf(phi);
+    float costheta, sintheta, sinphi, cosphi;
+    sin_cos(theta, &sintheta, &costheta);
+    sin_cos(phi, &sinphi, &cosphi);
     const SptXform &xf = sc.xforms[l.xform];
     out->wi = xf_vector(xf.m, V(sintheta * cosphi, sintheta * sinphi, costheta));
     out->pdf = mapPdf / (2.f * PI_F * PI_F * sintheta);

@@ -20,6 +20,15 @@
 #define ONE_MINUS_EPS 0x1.fffffep-1f
 #define SPT_INF __int_as_float(0x7f800000)
 
+// sinf and cosf of one angle: one range reduction on the device (sincosf returns what sinf / cosf return); the host build of the
+// device sources (tests/host_shim) keeps the two calls the oracle makes
+__device__ __forceinline__ void sin_cos(float x, float *s, float *c) {
+#ifdef __CUDA_ARCH__
+    sincosf(x, s, c);
+#else
+    *s = sinf(x); *c = cosf(x);
+#endif
+}
 struct v3 { float x, y, z; };
 __device__ __forceinline__ v3 V(float x, float y, float z) { v3 r; r.x = x; r.y = y; r.z = z; return r; }
 __device__ __forceinline__ v3 vadd(v3 a, v3 b) { return V(a.x + b.x, a.y + b.y, a.z + b.z); }
