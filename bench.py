@@ -474,11 +474,11 @@ def main():
 
     # ---- rooflines (algorithmic bytes per unit: SURVEY.md 8d for rays, DESIGN.md 3 for the other kernels)
     peak, peak_src = read_peaks()
-    # ncu evidence of the committed kernels (profiles/r02_ncu_summary_v9.json, written on the GPU box by profiles/tools/ncu_summary.py from
+    # ncu evidence of the committed kernels (profiles/r02_ncu_summary_v18.json, written on the GPU box by profiles/tools/ncu_summary.py from
     # one `ncu --set full --clock-control none` capture of this command's frame): DRAM bytes, issue-slot and pipe utilisation of the
     # bounce-0 launch of every kernel. bench.py cannot run under ncu itself; the capture it quotes is named in the line.
     ncu_all = {}
-    ncu_path = os.path.join(ROOT, "profiles", "r02_ncu_summary_v9.json")
+    ncu_path = os.path.join(ROOT, "profiles", "r02_ncu_summary_v18.json")
     if os.path.exists(ncu_path) and args.workload in (WORKLOAD, "killeroo_path", "killeroo_path30"):
         try:
             ncu_all = json.load(open(ncu_path))
@@ -508,7 +508,7 @@ def main():
         D.K_GEN: "instruction issue (80 % of the issue slots busy: hashing + camera arithmetic per sample)",
         D.K_TRACE_PATH: "instruction issue at 12-24 of 32 lanes per instruction; the BVH is served by L1/L2 (DRAM 1-10 % of peak even on the 10 M-triangle "
                         "scene: profiles/r02_ncu_trace_synth10m.csv), so the HBM fraction below is algorithmic bytes, not DRAM traffic",
-        D.K_SHADE: "instruction latency + fetch (48 % of the issue slots busy at 16 warps/SM, 12.8 k SASS instructions of exact fp32/fp64 arithmetic)",
+        D.K_SHADE: "instruction latency (51 % of the issue slots busy at 16 warps/SM: 128 registers; 12.2 k SASS instructions of exact fp32/fp64 arithmetic, ~3.8 k executed per vertex)",
         D.K_ACCUMULATE: "HBM streaming (bounce 0 also instruction issue: 77 % of the slots busy)",
         D.K_ADVANCE: "HBM streaming (73-75 % of the measured copy bandwidth in DRAM traffic)",
         D.K_FILM: "HBM reads of the radiance rows + film atomics",
@@ -548,7 +548,7 @@ def main():
         "nodes_per_shadow_ray": nodes_per_any, "prim_tests_per_shadow_ray": prims_per_any,
         "ncu_capture": ncu_all.get("_source"),
         "note": "achieved = algorithmic bytes of the kernel's bounce-0 launch (bytes_per_unit x units_per_launch, DESIGN.md 3) / its CUDA-event time in "
-                "this run; traffic = DRAM bytes ncu measured for the same launch of the same command (profiles/r02_ncu_summary_v9.json); `limiter` says "
+                "this run; traffic = DRAM bytes ncu measured for the same launch of the same command (profiles/r02_ncu_summary_v18.json); `limiter` says "
                 "what actually bounds the kernel - only k_advance / k_addlight are HBM-bound; per-kernel lines in roofline_by_kernel"})
     roofline_by_kernel = {D.K_NAMES[k]: roof(k) for k in unit_bytes if class_launches[k]}
     rays_total = class_rays[D.K_TRACE_PATH] + class_rays[D.K_TRACE_MIS] + class_rays[D.K_TRACE_SHADOW]
