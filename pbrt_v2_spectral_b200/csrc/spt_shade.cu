@@ -891,44 +891,44 @@ __global__ void __launch_bounds__(128) k_spawn_T(DevScene sc, WaveBuffers wb, in
 }
 
 // ---- K7 ----------------------------------------------------------------------------------------
-// Radiance guards (samplerrenderer.cpp:119-133) + SpectralImageFilm::AddSample
-// (spectralImage.cpp:77-152). One warp per sampler pixel, lane = band: each sample's radiance row
-// is one coalesced 128-byte load; y(L) for the guards is a warp sum. Samples whose footprint is
-// exactly the warp's own pixel (all of them under the box filter, up to rounding onto a pixel edge)
-// accumulate in a register per band and are flushed with one atomic per band per pixel; any other
-// footprint (wide filters) goes to global atomics, one coalesced 32-band atomic row per touched pixel.
-// Samples are handled eight at a time: their rows are loaded together; lanes 0-7 each work out one
-// sample's filter footprint; the eight y(L) sums share one butterfly (9 shuffles instead of 40: after
-// exchanging over lane bits 4, 3, 2 each group of four lanes owns one sample, bits 1, 0 finish it).
-#define FILM_GROUP 8
-__device__ __forceinline__ int film_y_lane(int k) { return ((k & 1) << 4) | ((k & 2) << 2) | (k & 4); }   // a lane that ends up holding y of sample k
+// Radiance guards (samplerrenderer.cpp:119-133) + SpectralImageFilm::AddSample (spectralImage.cpp:77-152).
+// One warp per sampler pixel, 32 samples per pass: lane = (sub, bg) = (lane >> 3, lane & 7) reads bands 4 bg .. 4 bg + 3 of samples
+// s0 + 4 k + sub, k = 0..7 - eight LDG.128 per lane in flight, each warp instruction moving four whole rows (round 2's
+// first form, lane = band with one LDG.32 per row, ran at 0.37 of the HBM rate: 1.81 ms per 31.4 M samples; this one 1.01 ms). Lane j works out the filter footprint of sample
+// s0 + j; a sample's y(L) is a sum over the 8 lanes of its group. Samples whose footprint is exactly the warp's own pixel
+// accumulate in four registers per lane; the four groups are summed at the end and flushed with one 32-lane atomic per
+// pixel (lane (sub, bg) writes band 4 bg + sub). Any other footprint (wide filters): the group's 8 lanes add its row to
+// every pixel it touches.
 __global__ void __launch_bounds__(256) k_film_add(FilmView film, const SptSpectralTables *tables, const float2 *img_xy,
-                                                  const float *L, uint32_t cap, uint32_t n_samples, int spp) {
+                                                   const float *L, uint32_t cap, uint32_t n_samples, int spp) {
     const SptSpectralTables &tb = *tables;
     const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, sub = lane >> 3, bg = lane & 7;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t npix = (n_samples + spp - 1) / spp;
     const SptFilmDesc &fd = film.d;
-    const float cieY = tb.cie_y[lane], yint = tb.yint;
+    const float4 cie = *((const float4 *)tb.cie_y + bg);
+    const float yint = tb.yint;
     const int xs = fd.x_pixel_start, ys = fd.y_pixel_start, xe = xs + fd.x_pixel_count - 1, ye = ys + fd.y_pixel_count - 1;
     for (uint32_t pixel = warp; pixel < npix; pixel += nwarps) {
         const uint32_t first = pixel * (uint32_t)spp;
         const uint32_t ns = min((uint32_t)spp, n_samples - first);
-        // the pixel this warp accumulates for: the one the first sample of the group falls in
-        float2 xy0 = img_xy[first];
+        const float2 xy0 = img_xy[first];
         const int mainx = (int)floorf(xy0.x), mainy = (int)floorf(xy0.y);
         const bool mainInside = mainx >= xs && mainx <= xe && mainy >= ys && mainy <= ye;
-        float acc = 0.f, wsum = 0.f;
-        for (uint32_t s0 = 0; s0 < ns; s0 += FILM_GROUP) {
-            float Lv[FILM_GROUP];
+        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f, wsum = 0.f;
+        for (uint32_t s0 = 0; s0 < ns; s0 += 32u) {
+            float4 Lv[8];
 #pragma unroll
-            for (int k = 0; k < FILM_GROUP; ++k) Lv[k] = L[band_off(first + min(s0 + k, ns - 1), lane)];
-            // ---- footprint of sample s0 + lane (lanes 0-7): 0 nothing to add, 1 exactly the warp's pixel, 2 anything else
-            int kind = 0;
-            float wt = 0.f;
-            if (lane < FILM_GROUP && s0 + lane < ns) {
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t idx = min(s0 + 4u * k + (uint32_t)sub, ns - 1u);
+                Lv[k] = *((const float4 *)(L + (size_t)(first + idx) * NBP) + bg);
+            }
+            // ---- footprint of sample s0 + lane: >= 0 the table weight of a sample that falls exactly on the warp's pixel,
+            // -1 nothing to add, -2 any other footprint
+            float wt = -1.f;
+            if (s0 + lane < ns) {
                 const float2 xy = img_xy[first + s0 + lane];
                 if (xy.x > -1e29f) {                                    // else: sample outside this rank's tile set
                     const float dimageX = xy.x - 0.5f, dimageY = xy.y - 0.5f;
@@ -941,55 +941,32 @@ __global__ void __launch_bounds__(256) k_film_add(FilmView film, const SptSpectr
                             float fy = fabsf((y0 - dimageY) * fd.filter_inv_ywidth * 16);
                             int ix = min((int)floorf(fx), 15), iy = min((int)floorf(fy), 15);
                             wt = film.table[iy * 16 + ix];
-                            kind = 1;
-                        } else kind = 2;
+                        } else wt = -2.f;
                     }
                 }
             }
-            const unsigned fastMask = __ballot_sync(FULL, kind == 1), slowMask = __ballot_sync(FULL, kind == 2);
-            // ---- radiance guards (samplerrenderer.cpp:119-133): NaN anywhere, y < -1e-5, y infinite -> black
-            unsigned nanBits = 0;
-            float y[FILM_GROUP];
 #pragma unroll
-            for (int k = 0; k < FILM_GROUP; ++k) {
-                if (__any_sync(FULL, isnan(Lv[k]))) nanBits |= 1u << k;
-                y[k] = cieY * Lv[k];
-            }
-            float z[4], w2[2], yy;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {                               // lane bit 4 picks sample 2j or 2j+1
-                float send = (lane & 16) ? y[2 * j] : y[2 * j + 1];
-                float keep = (lane & 16) ? y[2 * j + 1] : y[2 * j];
-                z[j] = keep + __shfl_xor_sync(FULL, send, 16);
-            }
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {                               // lane bit 3 picks pair 2j or 2j+1
-                float send = (lane & 8) ? z[2 * j] : z[2 * j + 1];
-                float keep = (lane & 8) ? z[2 * j + 1] : z[2 * j];
-                w2[j] = keep + __shfl_xor_sync(FULL, send, 8);
-            }
-            {
-                float send = (lane & 4) ? w2[0] : w2[1];
-                float keep = (lane & 4) ? w2[1] : w2[0];
-                yy = keep + __shfl_xor_sync(FULL, send, 4);
-            }
-            yy += __shfl_xor_sync(FULL, yy, 2);
-            yy += __shfl_xor_sync(FULL, yy, 1);
-            yy = yy / yint;
-            const unsigned yBad = __ballot_sync(FULL, (double)yy < -1e-5 || isinf(yy));
-            // ---- accumulate
-#pragma unroll
-            for (int k = 0; k < FILM_GROUP; ++k) {
-                const bool bad = ((nanBits >> k) & 1u) || ((yBad >> film_y_lane(k)) & 1u);
-                const float v = bad ? 0.f : Lv[k];
-                const float w = __shfl_sync(FULL, wt, k);
-                if ((fastMask >> k) & 1u) { acc += w * v; wsum += w; }
-                else if ((slowMask >> k) & 1u) {
-                    const float2 xy = img_xy[first + s0 + k];
+            for (int k = 0; k < 8; ++k) {
+                const float4 v = Lv[k];
+                // radiance guards (samplerrenderer.cpp:119-133): NaN anywhere, y < -1e-5, y infinite -> black
+                const unsigned nanLanes = __ballot_sync(FULL, isnan(v.x) || isnan(v.y) || isnan(v.z) || isnan(v.w));
+                float y = cie.x * v.x + cie.y * v.y + cie.z * v.z + cie.w * v.w;
+                y += __shfl_xor_sync(FULL, y, 4);
+                y += __shfl_xor_sync(FULL, y, 2);
+                y += __shfl_xor_sync(FULL, y, 1);
+                y = y / yint;
+                const bool bad = ((nanLanes >> (8 * sub)) & 0xffu) != 0u || (double)y < -1e-5 || isinf(y);
+                const float w = __shfl_sync(FULL, wt, 4 * k + sub);          // -1 beyond the pixel's samples
+                if (w >= 0.f) {
+                    if (!bad) { acc0 += w * v.x; acc1 += w * v.y; acc2 += w * v.z; acc3 += w * v.w; }
+                    wsum += w;
+                } else if (w == -2.f) {
+                    const float2 xy = img_xy[first + s0 + 4u * k + (uint32_t)sub];
                     const float dimageX = xy.x - 0.5f, dimageY = xy.y - 0.5f;
                     int x0 = (int)ceilf(dimageX - fd.filter_xwidth), x1 = (int)floorf(dimageX + fd.filter_xwidth);
                     int y0 = (int)ceilf(dimageY - fd.filter_ywidth), y1 = (int)floorf(dimageY + fd.filter_ywidth);
                     x0 = max(x0, xs); x1 = min(x1, xe); y0 = max(y0, ys); y1 = min(y1, ye);
+                    const float vv[4] = { bad ? 0.f : v.x, bad ? 0.f : v.y, bad ? 0.f : v.z, bad ? 0.f : v.w };
                     for (int py = y0; py <= y1; ++py) {
                         float fy = fabsf((py - dimageY) * fd.filter_inv_ywidth * 16);
                         int iy = min((int)floorf(fy), 15);
@@ -998,16 +975,24 @@ __global__ void __launch_bounds__(256) k_film_add(FilmView film, const SptSpectr
                             int ix = min((int)floorf(fx), 15);
                             float wpx = film.table[iy * 16 + ix];
                             float *dst = film.pix + ((size_t)(py - ys) * fd.x_pixel_count + (px - xs)) * (NB + 1);
-                            if (lane < NB) atomicAdd(dst + lane, wpx * v);
-                            if (lane == 0) atomicAdd(dst + NB, wpx);
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) if (4 * bg + c < NB) atomicAdd(dst + 4 * bg + c, wpx * vv[c]);
+                            if (bg == 0) atomicAdd(dst + NB, wpx);
                         }
                     }
                 }
             }
         }
+        // the four groups' sums -> every lane; lane (sub, bg) flushes band 4 bg + sub
+        acc0 += __shfl_xor_sync(FULL, acc0, 8); acc0 += __shfl_xor_sync(FULL, acc0, 16);
+        acc1 += __shfl_xor_sync(FULL, acc1, 8); acc1 += __shfl_xor_sync(FULL, acc1, 16);
+        acc2 += __shfl_xor_sync(FULL, acc2, 8); acc2 += __shfl_xor_sync(FULL, acc2, 16);
+        acc3 += __shfl_xor_sync(FULL, acc3, 8); acc3 += __shfl_xor_sync(FULL, acc3, 16);
+        wsum += __shfl_xor_sync(FULL, wsum, 8); wsum += __shfl_xor_sync(FULL, wsum, 16);
         if (mainInside && wsum != 0.f) {
             float *dst = film.pix + ((size_t)(mainy - ys) * fd.x_pixel_count + (mainx - xs)) * (NB + 1);
-            if (lane < NB) atomicAdd(dst + lane, acc);
+            const float a = sub == 0 ? acc0 : (sub == 1 ? acc1 : (sub == 2 ? acc2 : acc3));
+            if (4 * bg + sub < NB) atomicAdd(dst + 4 * bg + sub, a);
             if (lane == 0) atomicAdd(dst + NB, wsum);
         }
     }
