@@ -83,9 +83,14 @@ struct DevMem {
         ptrs.push_back({p, bytes});
         return (T *)p;
     }
-    template <typename T> T *upload(const T *host, size_t n) {
+    template <typename T> T *upload(const T *host, size_t n, bool settle = true) {
         T *d = alloc<T>(n);
-        if (d && n && host && cudaMemcpy(d, host, n * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+        // cudaMemcpy from pageable memory returns when the data is in the driver's staging buffer - the DMA into `d` may still be
+        // in flight, ordered on the legacy stream only. The render lanes are non-blocking streams, which that stream does not
+        // order: wait here, or a kernel launched next could read the tail of the array before it lands.
+        // (settle = false: the caller uploads a batch and synchronises the legacy stream once)
+        if (d && n && host && (cudaMemcpy(d, host, n * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess ||
+                               (settle && cudaStreamSynchronize(cudaStreamLegacy) != cudaSuccess))) return nullptr;
         return d;
     }
     // callers synchronise the device (or the stream that last touched the blocks) before releasing
@@ -335,7 +340,7 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
     lap("triangle gather + light cdf");
     DevMem &m = s->mem;
     bool ok = true;
-#define UP(dst, src, n) do { dst = m.upload(src, (size_t)(n)); if (!dst) ok = false; } while (0)
+#define UP(dst, src, n) do { dst = m.upload(src, (size_t)(n), false); if (!dst) ok = false; } while (0)
     float4 *nodes4 = nullptr, *tv_dev = nullptr, *pn_dev = nullptr;
     if (host_relayout) {
         UP(nodes4, (const float4 *)nodes.data(), (size_t)d->n_nodes * 2);
@@ -442,6 +447,7 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
     UP(v.env_marg_func, d->env_marg_func, eh); UP(v.env_marg_cdf, d->env_marg_cdf, eh ? eh + 1 : 0);
     v.env_marg_int = d->env_marg_int;
 #undef UP
+    if (cudaStreamSynchronize(cudaStreamLegacy) != cudaSuccess) ok = false;      // every table has landed (see DevMem::upload)
     lap("uploads");
     s->counters = m.alloc<unsigned long long>(4);
     if (!ok || !s->counters || cudaMemset(s->counters, 0, 32) != cudaSuccess ||
