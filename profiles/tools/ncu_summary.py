@@ -11,6 +11,7 @@ KEYS = {"ms": "gpu__time_duration.sum", "dram_read": "dram__bytes_read.sum", "dr
         "warps_active_pct": "sm__warps_active.avg.pct_of_peak_sustained_active", "registers": "launch__registers_per_thread",
         "l2_sectors_read": "lts__t_sectors_op_read.sum", "l2_sectors_write": "lts__t_sectors_op_write.sum", "l2_hit_pct": "lts__t_sector_hit_rate.pct",
         "l1_hit_pct": "l1tex__t_sector_hit_rate.pct", "inst": "smsp__inst_executed.sum",
+        "l2_bytes": "lts__t_bytes.sum", "l1_bytes": "l1tex__t_bytes.sum",
         "stall_no_instruction": "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
         "stall_long_scoreboard": "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
         "stall_wait": "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio"}
@@ -38,6 +39,8 @@ for r in rows[2:]:
             d[k] = v * SCALE.get(units[i], 1.0)
     if "dram_read" in d: d["dram_bytes"] = d["dram_read"] + d["dram_write"]
     if "l2_sectors_read" in d and d.get("ms"): d["l2_gbs"] = 32.0 * (d["l2_sectors_read"] + d["l2_sectors_write"]) / (d["ms"] * 1e-3) / 1e9
+    if d.get("l2_bytes") and d.get("ms"): d["l2_gbs"] = d["l2_bytes"] / (d["ms"] * 1e-3) / 1e9
+    if d.get("l1_bytes") and d.get("ms"): d["l1_gbs"] = d["l1_bytes"] / (d["ms"] * 1e-3) / 1e9
     if d.get("dram_bytes") and d.get("ms"): d["dram_gbs"] = d["dram_bytes"] / (d["ms"] * 1e-3) / 1e9
     order.append((c, d))
 for c, d in order:                      # first launch of each class = bounce 0; later ones kept as <class>_b1 ...
@@ -46,4 +49,4 @@ for c, d in order:                      # first launch of each class = bounce 0;
     res[k] = d
 res["_source"] = sys.argv[1].split("/")[-1] + ": ncu --set full --clock-control none, one steady-state frame on one stream (SPT_LANES=1); <class> = bounce 0, <class>_bN = later launches in order"
 json.dump(res, open(sys.argv[2], "w"), indent=1)
-print(json.dumps({k: {q: (round(v, 3) if isinstance(v, float) else v) for q, v in d.items() if q in ("ms", "dram_gbs", "l2_gbs", "issue_active_pct", "lanes_per_inst", "fma_pipe_pct")} for k, d in res.items() if isinstance(d, dict)}, indent=0))
+print(json.dumps({k: {q: (round(v, 3) if isinstance(v, float) else v) for q, v in d.items() if q in ("ms", "dram_gbs", "l2_gbs", "l1_gbs", "issue_active_pct", "lanes_per_inst", "fma_pipe_pct")} for k, d in res.items() if isinstance(d, dict)}, indent=0))
