@@ -106,6 +106,42 @@ int num_sms() {
 }  // namespace
 
 #define SPT_MAX_LANES 4
+// Streams and events outlive the scene that created them: a host that builds a scene per frame (the reference's renderer does)
+// would otherwise pay 4 stream + ~80 event creations per frame (0.3 ms). Keyed by device; emptied by spt_trim().
+#define SPT_POOL_DEVICES 64
+struct HandlePool {
+    std::mutex mu;
+    std::vector<cudaStream_t> streams[SPT_POOL_DEVICES];
+    std::vector<cudaEvent_t> timing_events[SPT_POOL_DEVICES], plain_events[SPT_POOL_DEVICES];
+    static int slot(int dev) { return dev >= 0 && dev < SPT_POOL_DEVICES ? dev : -1; }
+    cudaStream_t stream(int dev) {
+        { std::lock_guard<std::mutex> g(mu); int k = slot(dev); if (k >= 0 && !streams[k].empty()) { cudaStream_t st = streams[k].back(); streams[k].pop_back(); return st; } }
+        cudaStream_t st = nullptr;
+        return cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess ? st : nullptr;
+    }
+    cudaEvent_t event(int dev, bool timing) {
+        { std::lock_guard<std::mutex> g(mu); int k = slot(dev); auto *v = timing ? timing_events : plain_events;
+          if (k >= 0 && !v[k].empty()) { cudaEvent_t e = v[k].back(); v[k].pop_back(); return e; } }
+        cudaEvent_t e = nullptr;
+        return cudaEventCreateWithFlags(&e, timing ? cudaEventDefault : cudaEventDisableTiming) == cudaSuccess ? e : nullptr;
+    }
+    // the caller has synchronised the device: nothing is pending on what comes back
+    void put(int dev, cudaStream_t st) { if (!st) return; std::lock_guard<std::mutex> g(mu); int k = slot(dev); if (k >= 0 && streams[k].size() < 64) streams[k].push_back(st); else cudaStreamDestroy(st); }
+    void put(int dev, cudaEvent_t e, bool timing) {
+        if (!e) return;
+        std::lock_guard<std::mutex> g(mu); int k = slot(dev); auto *v = timing ? timing_events : plain_events;
+        if (k >= 0 && v[k].size() < 4096) v[k].push_back(e); else cudaEventDestroy(e);
+    }
+    void trim(int dev) {
+        std::lock_guard<std::mutex> g(mu); int k = slot(dev); if (k < 0) return;
+        for (cudaStream_t st : streams[k]) cudaStreamDestroy(st);
+        for (cudaEvent_t e : timing_events[k]) cudaEventDestroy(e);
+        for (cudaEvent_t e : plain_events[k]) cudaEventDestroy(e);
+        streams[k].clear(); timing_events[k].clear(); plain_events[k].clear();
+    }
+};
+static HandlePool g_handles;
+
 struct SptScene {
     int device = 0;                  // the device the scene lives on: every entry point switches to it (DeviceGuard)
     DevMem mem;
@@ -157,7 +193,7 @@ struct SptScene {
     std::vector<Mark> marks;
     size_t ev_used = 0;
     void mark(int cls, int ln = 0) {
-        if (ev_used == marks.size()) { cudaEvent_t e; cudaEventCreate(&e); marks.push_back(Mark{e, 0, 0}); }
+        if (ev_used == marks.size()) marks.push_back(Mark{g_handles.event(device, true), 0, 0});
         marks[ev_used].cls = cls; marks[ev_used].lane = ln;
         cudaEventRecord(marks[ev_used++].e, lane[ln].stream);
         if (cls >= 0) { ++launches; ++stats.class_launches[cls]; }
@@ -166,14 +202,13 @@ struct SptScene {
 
 static void destroy_lanes(SptScene *s) {
     for (int k = 0; k < SPT_MAX_LANES; ++k) {
-        if (s->lane[k].stream) { cudaStreamDestroy(s->lane[k].stream); s->lane[k].stream = nullptr; }
-        if (s->evjoin[k]) { cudaEventDestroy(s->evjoin[k]); s->evjoin[k] = nullptr; }
+        g_handles.put(s->device, s->lane[k].stream); s->lane[k].stream = nullptr;
+        g_handles.put(s->device, s->evjoin[k], false); s->evjoin[k] = nullptr;
     }
 }
 static bool make_lanes(SptScene *s) {
     for (int k = 0; k < SPT_MAX_LANES; ++k)
-        if (cudaStreamCreateWithFlags(&s->lane[k].stream, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaEventCreateWithFlags(&s->evjoin[k], cudaEventDisableTiming) != cudaSuccess) { destroy_lanes(s); return false; }
+        if (!(s->lane[k].stream = g_handles.stream(s->device)) || !(s->evjoin[k] = g_handles.event(s->device, false))) { destroy_lanes(s); return false; }
     return true;
 }
 
@@ -204,6 +239,8 @@ void spt_host_free(void *p) { if (p) cudaFreeHost(p); }
 void spt_trim(void) {
     cudaDeviceSynchronize();
     g_blocks.trim();
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) g_handles.trim(dev);
 }
 
 static double now_ms() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
@@ -452,7 +489,7 @@ SptScene *spt_scene_create(const SptSceneDesc *d) {
     s->counters = m.alloc<unsigned long long>(4);
     if (!ok || !s->counters || cudaMemset(s->counters, 0, 32) != cudaSuccess ||
         !make_lanes(s) ||
-        cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess) {
+        !(s->ev0 = g_handles.event(s->device, true)) || !(s->ev1 = g_handles.event(s->device, true))) {
         g_err = std::string("scene upload failed: ") + cudaGetErrorString(cudaGetLastError());
         destroy_lanes(s);
         if (s->ev0) cudaEventDestroy(s->ev0);
@@ -475,11 +512,11 @@ void spt_scene_destroy(SptScene *s) {
     s->wide_mem.release();
     s->trace_scratch.release();
     s->counts_mem.release();
-    for (auto &ln : s->lane) { ln.mem.release(); if (ln.stream) cudaStreamDestroy(ln.stream); }
-    if (s->ev0) cudaEventDestroy(s->ev0);
-    if (s->ev1) cudaEventDestroy(s->ev1);
-    for (cudaEvent_t e : s->evjoin) if (e) cudaEventDestroy(e);
-    for (auto &m : s->marks) cudaEventDestroy(m.e);
+    for (auto &ln : s->lane) ln.mem.release();
+    destroy_lanes(s);
+    g_handles.put(s->device, s->ev0, true);
+    g_handles.put(s->device, s->ev1, true);
+    for (auto &m : s->marks) g_handles.put(s->device, m.e, true);
     delete s;
 }
 

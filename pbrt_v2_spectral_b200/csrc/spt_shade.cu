@@ -143,6 +143,9 @@ __device__ __forceinline__ float2 dir_coef(int mtype, bool on, const DirTerms &t
 #define SPT_SHADE_SYNC 1
 #endif
 #define SHADE_THREADS(EXT) ((EXT) ? SPT_SHADE_THREADS_EXT : SPT_SHADE_THREADS)
+#ifndef SPT_SHADE_EARLY_DIMS
+#define SPT_SHADE_EARLY_DIMS 1
+#endif
 template <bool SPEC, bool EXT, bool DIRECT = false, bool MEAS = false>
 __global__ void __launch_bounds__(SHADE_THREADS(EXT), 512 / SHADE_THREADS(EXT)) k_shade(DevScene sc, RenderCfg cfg, SampleSource src, WaveBuffers wb, int bounce,
                                                const uint32_t *queue, const uint32_t *count,
@@ -163,6 +166,21 @@ __global__ void __launch_bounds__(SHADE_THREADS(EXT), 512 / SHADE_THREADS(EXT)) 
         v3 p = V(0, 0, 0), n_s = p, woW = p, wo = p;
         float eps = 0.f;
         int emitter = -1;
+#if SPT_SHADE_EARLY_DIMS
+        // the path integrator's sample values depend on the sample's number only: hashed while the hit's loads are in flight
+        float uE[10], rrE = 0.f;
+        for (int k = 0; k < 10; ++k) uE[k] = 0.f;
+        const bool earlyDims = !DIRECT && !(EXT && cfg.integrator == SPT_INTEGRATOR_DIRECT_ONE && src.smp);
+        if (active && earlyDims) {
+            s_idx = src.smp ? 0u : (i & ((uint32_t)cfg.spp - 1u));
+            if (!src.smp) {
+                int px, py;
+                wave_pixel(cfg, cfg.pixel_base + (i >> cfg.spp_shift), &px, &py);
+                pk = pixel_key(src.seed, pix_key(px, py));
+            }
+            bounce_dims(src, i, pk, s_idx, bounce, sc.n_lights > 0, uE, &rrE);
+        }
+#endif
         if (active) {
             slot = wb.hit_slot[i];
             float4 o4 = wb.ray_o[i], d4 = wb.ray_d[i];
@@ -240,7 +258,14 @@ __global__ void __launch_bounds__(SHADE_THREADS(EXT), 512 / SHADE_THREADS(EXT)) 
                     for (int k = 0; k < 10; ++k) u[k] = 0.f;
                     rr = 0.f;
                     u[0] = q[6]; u[1] = q[10]; u[2] = q[11]; u[3] = q[5]; u[4] = q[12]; u[5] = q[13]; u[6] = q[7];
-                } else bounce_dims(src, i, pk, s_idx, bounce, sc.n_lights > 0, u, &rr);
+                } else {
+#if SPT_SHADE_EARLY_DIMS
+                    for (int k = 0; k < 10; ++k) u[k] = uE[k];
+                    rr = rrE;
+#else
+                    bounce_dims(src, i, pk, s_idx, bounce, sc.n_lights > 0, u, &rr);
+#endif
+                }
 
                 float4 g1 = make_float4(0, 0, 0, 0), g2 = g1, g3 = g1, laux = g1;
                 const int mtype = bsdf.mtype;
