@@ -143,6 +143,9 @@ __device__ __forceinline__ float2 dir_coef(int mtype, bool on, const DirTerms &t
 #define SPT_SHADE_SYNC 1
 #endif
 #define SHADE_THREADS(EXT) ((EXT) ? SPT_SHADE_THREADS_EXT : SPT_SHADE_THREADS)
+#ifndef SPT_ADVANCE_BRANCH
+#define SPT_ADVANCE_BRANCH false
+#endif
 #ifndef SPT_SHADE_EARLY_DIMS
 #define SPT_SHADE_EARLY_DIMS 1
 #endif
@@ -452,6 +455,9 @@ struct LightBand { int kind; IllumCoefs k; };
 // the HBM rate); y(T) is a sum over the 8 lanes of a vertex. Phase C (k_advance), lane = vertex: next ray + queue push.
 static_assert(NBP == 32, "k_advance / k_addlight / k_film_add assume 128-byte rows (lane = band, or 8 lanes x float4)");
 #define ACC_WARPS 4
+#ifndef ADV_CHUNK
+#define ADV_CHUNK 4
+#endif
 struct F4 { float v[4]; };
 __device__ __forceinline__ F4 ld4(const float *row, int bg) { float4 q = __ldg((const float4 *)row + bg); F4 r; r.v[0] = q.x; r.v[1] = q.y; r.v[2] = q.z; r.v[3] = q.w; return r; }
 __device__ __forceinline__ F4 ld4g(const float *row, int bg) { float4 q = *((const float4 *)row + bg); F4 r; r.v[0] = q.x; r.v[1] = q.y; r.v[2] = q.z; r.v[3] = q.w; return r; }
@@ -476,11 +482,21 @@ __device__ __forceinline__ F4 illum4(const SptSpectralTables &tb, const float4 &
 // f of one direction, four bands, from its two folded coefficients {a, b} (see WaveBuffers::rec0) and the material rows.
 // kind: 0 matte / plastic (f = spec0 a + spec1 b), 1 metal (f = a FrCond(b, eta, k)), 2 substrate (FresnelBlend with the
 // Schlick weight c3: Kd (1 - Ks) a + (Ks + (1 - Ks) c3) b)
-// The material kind is branched on ONCE, outside the band loop: with the test inside it the compiler if-converted the loop and
-// every vertex paid for all three formulas (47 % of k_addlight's instructions on a scene of matte and plastic only).
-template <bool EXT>
+// BRANCH: the material kind is tested once, outside the band loop. k_addlight wants that: with the test inside the loop every
+// vertex pays for all the formulas (47 % of its instructions on a scene of matte and plastic only; 1.83 -> 1.27 ms at
+// bounce 0). k_advance keeps the test inside (no difference measured either way once its queue claims were chunked).
+template <bool EXT, bool BRANCH>
 __device__ __forceinline__ F4 fold_f(int kind, const F4 &s0, const F4 &s1, float a, float b, float c3) {
     F4 r;
+    if (!BRANCH) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (kind == 1) r.v[c] = a != 0.f ? a * fr_cond_fast(b, b * b, s0.v[c], s1.v[c]) : 0.f;
+            else if (EXT && kind == 2) { const float oms = 1.f - s1.v[c]; r.v[c] = s0.v[c] * oms * a + (s1.v[c] + oms * c3) * b; }
+            else r.v[c] = fmaf(s0.v[c], a, s1.v[c] * b);
+        }
+        return r;
+    }
     if (kind == 1) {
         if (a != 0.f) {
             const float b2 = b * b;
@@ -516,7 +532,14 @@ __global__ void __launch_bounds__(32 * ACC_WARPS, 8) k_advance(DevScene sc, Rend
     const F4 cieY = ld4(tb.cie_y, bg);
     const float yint = tb.yint;
     const uint32_t nwarps = gridDim.x * ACC_WARPS;
-    for (uint32_t base = (blockIdx.x * ACC_WARPS + warp) * 32u; base < n; base += nwarps * 32u) {
+    // A warp takes ADV_CHUNK consecutive passes of 32 vertices and claims their queue slots with ONE atomic: the counter of the
+    // next path queue is a single address, and one claim per 32 vertices (0.9 M same-address atomics at bounce 0 of config 1)
+    // was what the kernel's time followed, not its DRAM traffic. Survivors wait in shared memory until the chunk is claimed.
+    __shared__ uint32_t pend_all[ACC_WARPS][32 * ADV_CHUNK];
+    uint32_t *pend = pend_all[warp];
+    for (uint32_t cbase = (blockIdx.x * ACC_WARPS + warp) * (32u * ADV_CHUNK); cbase < n; cbase += nwarps * (32u * ADV_CHUNK)) {
+      uint32_t npend = 0;
+      for (uint32_t base = cbase; base < min(n, cbase + 32u * ADV_CHUNK); base += 32u) {
         // ---- phase A: lane = vertex
         const uint32_t q = base + lane;
         const bool active = q < n;
@@ -571,7 +594,7 @@ __global__ void __launch_bounds__(32 * ACC_WARPS, 8) k_advance(DevScene sc, Rend
                     F4 s0 = ld4(m.spec0, bg);
                     const F4 s1 = ld4(m.spec1, bg);
                     if (EXT && ((misc >> 4) & 1u)) s0 = refl4(tb, stage[vv][2], misc >> 8, bg);
-                    fP = fold_f<EXT>((int)kind, s0, s1, cP.x, cP.y, m4.w);
+                    fP = fold_f<EXT, SPT_ADVANCE_BRANCH>((int)kind, s0, s1, cP.x, cP.y, m4.w);
                 }
 #pragma unroll
                 for (int c = 0; c < 4; ++c) Tn.v[c] = Tv.v[c] * (fP.v[c] * cP.z);
@@ -599,14 +622,25 @@ __global__ void __launch_bounds__(32 * ACC_WARPS, 8) k_advance(DevScene sc, Rend
         }
         // ---- phase C: lane = vertex
         const bool alive = active && ((aliveMask >> lane) & 1u);
+        const unsigned pushMask = __ballot_sync(FULL, alive);
         if (alive) {
             const float4 g3 = wb.g3[i], g0 = wb.g0[i];
             wb.ray_o[i] = g0;
             wb.ray_d[i] = make_float4(g3.x, g3.y, g3.z, SPT_INF);
             if (sc.has_specular) wb.pflags[i] = specBounce ? 1u : 0u;
+            pend[npend + __popc(pushMask & ((1u << lane) - 1u))] = i;
         }
-        queue_push(next_queue, next_count, alive, i);
+        npend += (uint32_t)__popc(pushMask);
         __syncwarp();
+      }
+      // ---- the chunk's survivors -> the next path queue, in vertex order
+      if (npend) {
+        uint32_t pushBase = 0;
+        if (lane == 0) pushBase = atomicAdd(next_count, npend);
+        pushBase = __shfl_sync(FULL, pushBase, 0);
+        for (uint32_t k = lane; k < npend; k += 32u) next_queue[pushBase + k] = pend[k];
+      }
+      __syncwarp();
     }
 }
 
@@ -743,8 +777,8 @@ __global__ void __launch_bounds__(32 * ACC_WARPS, 8) k_addlight(DevScene sc, Ren
                     const float4 e3 = stage[v][5];
                     c3L = e3.x; c3B = e3.y;
                 }
-                fL = fold_f<EXT>((int)kind, s0, s1, cLB.x, cLB.y, c3L);
-                fB = fold_f<EXT>((int)kind, s0, s1, cLB.z, cLB.w, c3B);
+                fL = fold_f<EXT, true>((int)kind, s0, s1, cLB.x, cLB.y, c3L);
+                fB = fold_f<EXT, true>((int)kind, s0, s1, cLB.z, cLB.w, c3B);
             }
             // radiance arriving along the light / MIS direction: the light's table row, or (infinite light) an RGB
             // illuminant rebuilt from the staged coefficients
