@@ -257,7 +257,7 @@ def main():
     # N = 1: the film is the library's. N > 1: ONE film per frame buffer lives on rank 0 (spt_film_create there, exported with
     # spt_film_ipc_export); the other ranks open it (spt_film_open_ipc) and their film kernel adds their tile sets' samples
     # straight into it over NVLink - the "gather" is fused into K7, what is left of it is a barrier at the end of the frame.
-    n_buf = 2 if world > 1 else 1
+    n_buf = 3 if world > 1 else 1
     if world == 1:
         films = [capi.Film(fd)]
     else:
@@ -321,11 +321,35 @@ def main():
     lanes_used = 1
     barrier()
     e0.record()
-    for k in range(args.steps):
-        f = frame(k)
-        render_ms += scene.render_ms()
+    if dist is None:
+        for k in range(args.steps):
+            frame(k)
+            render_ms += scene.render_ms()
+    else:
+        # N > 1: the frames are pipelined over THREE film buffers, and the next frame is ENQUEUED (spt_render_begin) before the
+        # host waits for the current one (spt_render_end), so a rank's GPU goes from frame to frame without a host bubble.
+        # Frame k's end-of-frame barrier (a one-element all-reduce: once it completes every rank's samples are in buffer k % 3
+        # on rank 0) is enqueued behind the rank's render and waited for only before frame k + 2 is enqueued. Rank 0 clears
+        # buffer (k - 1) % 3 - complete since barrier k - 1 - BEFORE it enters barrier k; frame k + 2, the next to write that
+        # buffer, is enqueued on every rank behind barrier k. Every barrier has completed before the closing time stamp.
+        done = [torch.cuda.Event() for _ in range(args.steps)]
+        scene.render_begin(films[0], rp)
+        for k in range(args.steps):
+            if k + 1 < args.steps:
+                if k >= 1:
+                    done[k - 1].synchronize()
+                scene.render_begin(films[(k + 1) % n_buf], rp)
+            scene.render_end()                            # blocks until frame k has drained on this rank
+            render_ms += scene.render_ms()
+            if rank == 0 and k >= 1:
+                done[k - 1].synchronize()
+                films[(k - 1) % n_buf].clear_idle()
+            dist.all_reduce(sync_t)
+            done[k].record()
+        for k in range(max(args.steps - 2, 0), args.steps):
+            done[k].synchronize()
         if rank == 0:
-            f.clear()                                    # N > 1: frame k + 1 goes to the other buffer; k + 2 starts behind the next barrier
+            films[(args.steps - 1) % n_buf].clear_idle()
     e1.record()
     barrier()
     lanes_used = scene.stats()["lanes_used"]
@@ -565,8 +589,10 @@ def main():
                    "parallelism": "image tile sets (32x32, round-robin) x%d, scene replicated; every rank's film kernel adds its samples straight into ONE film "
                                   "on rank 0 through a peer mapping (NVLink), a NCCL barrier ends the frame" % world,
                    "l2": "per-step wave state (>2 GB) and film are larger than L2; no explicit flush",
-                   "pipelining": "N > 1: two film buffers alternate, rank 0 clears buffer k behind the barrier of frame k while frame k+1 fills the other; "
-                                 "every frame's film is complete on rank 0 inside the timed region"},
+                   "pipelining": "N > 1: three film buffers; a rank enqueues frame k+1 (spt_render_begin) before it waits for frame k (spt_render_end); "
+                                 "frame k's end-of-frame barrier is waited for before frame k+2 is enqueued, rank 0 clears a buffer behind its "
+                                 "frame's barrier and before it enters the next one; every frame's film is complete on rank 0 (every barrier "
+                                 "has completed) inside the timed region"},
         "mrays_per_s": rays_total / prof_steps / (ms_per_step / 1e3) / 1e6 if world == 1 else None,
         "rays_per_sample": rays_total / prof_steps / (n_samples_total / world) if world else None,
         "rays_per_sample_reference": (rays_total + elided) / prof_steps / (n_samples_total / world) if world else None,

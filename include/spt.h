@@ -377,6 +377,9 @@ SptFilm *spt_film_create(const SptFilmDesc *desc);
 SptFilm *spt_film_create_external(const SptFilmDesc *desc, float *pixels_dev);
 void     spt_film_destroy(SptFilm *film);
 int      spt_film_clear(SptFilm *film);
+/* The same zeroing without waiting for the rest of the device: the CALLER guarantees that no render into this film is in flight
+ * (its frame's end-of-frame barrier has completed); frames running into OTHER films go on. Returns when the film is zero. */
+int      spt_film_clear_idle(SptFilm *film);
 /* K7 on caller-supplied samples: SpectralImageFilm::AddSample (src/film/spectralImage.cpp:77-152)
  * preceded by the radiance guards of src/renderers/samplerrenderer.cpp:119-133.
  * image_xy: n x 2 {imageX, imageY}; L: n x SPT_NBANDS. */
@@ -392,6 +395,15 @@ int      spt_film_write_dat(SptFilm *film, const char *path);
 /* The whole job: SamplerRenderer::Render without the final WriteImage
  * (src/renderers/samplerrenderer.cpp:188-222). Accumulates into film. */
 int spt_render(SptScene *scene, const SptCameraDesc *cam, SptFilm *film, const SptRenderParams *params);
+/* The same job in two calls, for a host that renders frame after frame (the reference renders one image per process, so it has
+ * no counterpart there): spt_render_begin enqueues the frame and returns; spt_render_end waits for the OLDEST frame begun and
+ * finishes its statistics. Up to two frames may be in flight on a scene - begin(k + 1) before end(k) - so that the device goes
+ * from one frame to the next without waiting for the host; they run one after the other, in order, in the same wave buffers
+ * (frames into different films, or into one film that is meant to accumulate both). Per-kernel-class times (SptStats::class_ms)
+ * are only collected for a frame begun while no other was in flight. Between begin and end only these two calls, spt_get_stats
+ * and spt_last_render_ms may be used on the scene. */
+int spt_render_begin(SptScene *scene, const SptCameraDesc *cam, SptFilm *film, const SptRenderParams *params);
+int spt_render_end(SptScene *scene);
 
 /* ---- several GPUs: the scene is replicated, the image is cut into square tiles dealt round-robin to the GPUs
  * (SptRenderParams::tile_rank / tile_nranks, all samples of a pixel on one GPU), and K7 of every GPU adds its samples STRAIGHT

@@ -20,9 +20,9 @@ SYMBOLS = [
     "spt_scene_create", "spt_scene_destroy", "spt_scene_set_traversal", "spt_scene_enable_counters", "spt_scene_set_lanes", "spt_get_stats", "spt_last_render_ms",
     "spt_camera_rays", "spt_trace_closest", "spt_trace_any", "spt_trace_closest_dev", "spt_trace_any_dev",
     "spt_shade_samples",
-    "spt_film_create", "spt_film_create_external", "spt_film_destroy", "spt_film_clear",
+    "spt_film_create", "spt_film_create_external", "spt_film_destroy", "spt_film_clear", "spt_film_clear_idle",
     "spt_film_add_samples", "spt_film_download", "spt_film_device_ptr", "spt_film_write_dat",
-    "spt_render",
+    "spt_render", "spt_render_begin", "spt_render_end",
     "spt_film_ipc_export", "spt_film_open_ipc",
     "spt_multi_create", "spt_multi_destroy", "spt_multi_device_count", "spt_multi_render", "spt_multi_film", "spt_multi_get_stats",
     "spt_multi_last_render_ms",
@@ -70,12 +70,15 @@ def lib():
         L.spt_film_create_external.argtypes = [C.POINTER(D.SptFilmDesc), C.c_void_p]
         L.spt_film_destroy.argtypes = [C.c_void_p]
         L.spt_film_clear.argtypes = [C.c_void_p]
+        L.spt_film_clear_idle.argtypes = [C.c_void_p]
         L.spt_film_add_samples.argtypes = [C.c_void_p, C.POINTER(D.SptSpectralTables), C.c_void_p, C.c_void_p, C.c_uint64]
         L.spt_film_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.spt_film_device_ptr.restype = C.c_void_p
         L.spt_film_device_ptr.argtypes = [C.c_void_p]
         L.spt_film_write_dat.argtypes = [C.c_void_p, C.c_char_p]
         L.spt_render.argtypes = [C.c_void_p, C.POINTER(D.SptCameraDesc), C.c_void_p, C.POINTER(D.SptRenderParams)]
+        L.spt_render_begin.argtypes = [C.c_void_p, C.POINTER(D.SptCameraDesc), C.c_void_p, C.POINTER(D.SptRenderParams)]
+        L.spt_render_end.argtypes = [C.c_void_p]
         L.spt_film_ipc_export.argtypes = [C.c_void_p, C.c_void_p]
         L.spt_film_open_ipc.restype = C.c_void_p
         L.spt_film_open_ipc.argtypes = [C.POINTER(D.SptFilmDesc), C.c_void_p]
@@ -221,6 +224,16 @@ class Scene:
         cam = camera if camera is not None else self.lowered.camera
         _check(lib().spt_render(self.h, C.byref(cam), film.h, C.byref(rp)))
 
+    def render_begin(self, film, params=None, camera=None):
+        """Enqueue a frame and return (spt_render_begin); up to two frames may be in flight."""
+        rp = params if params is not None else self.lowered.params
+        cam = camera if camera is not None else self.lowered.camera
+        _check(lib().spt_render_begin(self.h, C.byref(cam), film.h, C.byref(rp)))
+
+    def render_end(self):
+        """Wait for the oldest frame in flight (spt_render_end)."""
+        _check(lib().spt_render_end(self.h))
+
 
 class Film:
     """SpectralImageFilm accumulator on the device (spt_film_create[_external])."""
@@ -266,6 +279,10 @@ class Film:
 
     def clear(self):
         _check(lib().spt_film_clear(self.h))
+
+    def clear_idle(self):
+        """Zero the film without waiting for frames running into other films (spt_film_clear_idle)."""
+        _check(lib().spt_film_clear_idle(self.h))
 
     def add_samples(self, tables, xy, L):
         xy = np.ascontiguousarray(xy, np.float32); L = np.ascontiguousarray(L, np.float32)

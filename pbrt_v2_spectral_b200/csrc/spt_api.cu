@@ -192,12 +192,30 @@ struct SptScene {
     struct Mark { cudaEvent_t e; int cls; int lane; };
     std::vector<Mark> marks;
     size_t ev_used = 0;
+    bool marks_on = true;            // off for a frame enqueued behind another one (the two would record the same events)
     void mark(int cls, int ln = 0) {
-        if (ev_used == marks.size()) marks.push_back(Mark{g_handles.event(device, true), 0, 0});
-        marks[ev_used].cls = cls; marks[ev_used].lane = ln;
-        cudaEventRecord(marks[ev_used++].e, lane[ln].stream);
-        if (cls >= 0) { ++launches; ++stats.class_launches[cls]; }
+        if (marks_on) {
+            if (ev_used == marks.size()) marks.push_back(Mark{g_handles.event(device, true), 0, 0});
+            marks[ev_used].cls = cls; marks[ev_used].lane = ln;
+            cudaEventRecord(marks[ev_used++].e, lane[ln].stream);
+        }
+        if (cls >= 0) { ++launches; if (marks_on) ++stats.class_launches[cls]; }
     }
+    // Frames in flight (spt_render_begin ... spt_render_end): what spt_render_end needs to finish the frame's statistics. Two
+    // records: the next frame is enqueued while the current one runs, so the device goes from one to the other without
+    // waiting for the host.
+    struct FrameRec {
+        bool timed = false, tree = false, empty = false;
+        size_t n_waves = 0, per_wave = 0;
+        int depth = 0, n_lanes = 0, spp = 0, nranks = 1;
+        uint64_t local_tiles = 0;
+        RenderCfg cfg;
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr, evc = nullptr;
+        uint32_t *hc = nullptr;      // page-locked copy of the frame's counter rows
+        size_t hc_cap = 0;
+        std::vector<uint32_t> hc_tree;
+    } frame[2];
+    int f_head = 0, f_count = 0;     // oldest record, records in flight
 };
 
 static void destroy_lanes(SptScene *s) {
@@ -513,6 +531,10 @@ void spt_scene_destroy(SptScene *s) {
     s->trace_scratch.release();
     s->counts_mem.release();
     for (auto &ln : s->lane) ln.mem.release();
+    for (auto &fr : s->frame) {
+        g_handles.put(s->device, fr.ev0, true); g_handles.put(s->device, fr.ev1, true); g_handles.put(s->device, fr.evc, false);
+        if (fr.hc) cudaFreeHost(fr.hc);
+    }
     destroy_lanes(s);
     g_handles.put(s->device, s->ev0, true);
     g_handles.put(s->device, s->ev1, true);
@@ -792,9 +814,11 @@ static int trace_dev(SptScene *s, bool any, const float4 *ro, const float4 *rd, 
     return SPT_OK;
 }
 
+#define SPT_NOT_IN_FLIGHT(s) do { if ((s)->f_count) return fail(SPT_ERR_ARG, "a frame is in flight on this scene: spt_render_end first"); } while (0)
 static int trace_host(SptScene *s, bool any, const float *rays, uint64_t n, uint32_t *out_slot, uint32_t *out_id,
                       float *out_t, uint8_t *out_hit) {
     if (!s || !rays) return fail(SPT_ERR_ARG, "null argument");
+    SPT_NOT_IN_FLIGHT(s);
     if (n == 0) return SPT_OK;
     if (n > 0x7fffffffull) return fail(SPT_ERR_ARG, "too many rays for one call");
     DeviceGuard dg(s->device);
@@ -839,6 +863,7 @@ int spt_trace_any(SptScene *s, const float *rays, uint64_t n, uint8_t *out_hit) 
 static int trace_resident(SptScene *s, bool any, const float *rays_dev, uint64_t n, uint32_t *slot_dev, float *t_dev,
                           uint8_t *hit_dev) {
     if (!s || !rays_dev) return fail(SPT_ERR_ARG, "null argument");
+    SPT_NOT_IN_FLIGHT(s);
     if (n == 0) return SPT_OK;
     if (n > 0x7fffffffull) return fail(SPT_ERR_ARG, "too many rays for one call");
     DeviceGuard dg(s->device);
@@ -877,6 +902,7 @@ int spt_trace_any_dev(SptScene *s, const float *rays_dev, uint64_t n, uint8_t *o
 int spt_shade_samples(SptScene *s, const SptCameraDesc *cam, int32_t integrator, int32_t max_depth, int32_t spp, const float *samples,
                       const float *rng, int32_t n_rng, uint64_t n, float *out_L) {
     if (!s || !cam || !samples || !out_L) return fail(SPT_ERR_ARG, "null argument");
+    SPT_NOT_IN_FLIGHT(s);
     if (spp <= 0) return fail(SPT_ERR_ARG, "spp must be positive");
     if (integrator != SPT_INTEGRATOR_PATH && integrator != SPT_INTEGRATOR_DIRECT_ALL && integrator != SPT_INTEGRATOR_DIRECT_ONE)
         return fail(SPT_ERR_ARG, "unknown integrator");
@@ -975,6 +1001,17 @@ int spt_film_clear(SptFilm *f) {
     CU(cudaDeviceSynchronize());
     return SPT_OK;
 }
+int spt_film_clear_idle(SptFilm *f) {
+    if (!f) return fail(SPT_ERR_ARG, "null film");
+    DeviceGuard dg(f->device);
+    cudaStream_t st = g_handles.stream(f->device);
+    if (!st) return fail(SPT_ERR_CUDA, "stream creation failed");
+    cudaError_t e = cudaMemsetAsync(f->pix, 0, f->npix() * (NB + 1) * sizeof(float), st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    g_handles.put(f->device, st);
+    if (e != cudaSuccess) return fail(SPT_ERR_CUDA, cudaGetErrorString(e));
+    return SPT_OK;
+}
 float *spt_film_device_ptr(SptFilm *f) { return f ? f->pix : nullptr; }
 
 int spt_film_download(SptFilm *f, float *c, float *weight) {
@@ -1042,9 +1079,10 @@ int spt_film_add_samples(SptFilm *f, const SptSpectralTables *tables, const floa
 }
 
 // ---- the whole job -------------------------------------------------------------------------------
-int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRenderParams *rp) {
+int spt_render_begin(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRenderParams *rp) {
     if (!s || !cam || !film || !rp) return fail(SPT_ERR_ARG, "null argument");
     if (film->device != s->device) return fail(SPT_ERR_ARG, "scene and film live on different devices");
+    if (s->f_count >= 2) return fail(SPT_ERR_ARG, "two frames are already in flight: spt_render_end first");
     DeviceGuard dg(s->device);
     if (rp->spp <= 0 || (rp->spp & (rp->spp - 1))) return fail(SPT_ERR_ARG, "spp must be a power of two (LDSampler rounds up)");
     if (rp->max_depth < 0 || rp->max_depth > 64) return fail(SPT_ERR_ARG, "max_depth out of range");
@@ -1083,9 +1121,11 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
     uint64_t ntiles = (uint64_t)cfg.tilesX * cfg.tilesY;
     uint64_t local_tiles = ntiles > (uint64_t)cfg.rank ? (ntiles - cfg.rank + nranks - 1) / nranks : 0;
     uint64_t local_pixels = local_tiles * (uint64_t)cfg.tile * cfg.tile;
+    SptScene::FrameRec &fr = s->frame[(s->f_head + s->f_count) & 1];
+    fr.timed = s->f_count == 0; fr.tree = false; fr.empty = false; fr.hc_tree.clear();
     if (local_pixels == 0) {            // a rank that owns no tile (more ranks than tiles): nothing to render
-        reset_class_stats(s);
-        s->stats.render_ms = 0.; s->stats.lanes_used = 0;
+        fr.empty = true;
+        ++s->f_count;
         return SPT_OK;
     }
     // Waves: by default the rank's pixels are cut into a multiple of max_lanes waves, each at most
@@ -1112,6 +1152,16 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
     if (wave_pixels * slots_pp * (uint64_t)sub > 0xffffffffull) wave_pixels = std::max<uint64_t>(1, 0xffffffffull / (slots_pp * (uint64_t)sub));
     size_t n_waves;
     int n_lanes, rc;
+    // a frame is still running in the wave buffers: they may only be re-allocated (a bigger frame) once it has drained; the
+    // specular tree checks every pixel range on the host, so it starts on an idle device as well
+    if (s->f_count > 0) {
+        const size_t nw0 = (size_t)((local_pixels + wave_pixels - 1) / wave_pixels);
+        const int nl0 = tree ? 1 : (int)std::min<size_t>((size_t)s->max_lanes, std::max<size_t>(nw0, 1));
+        const uint32_t cap0 = ((uint32_t)(wave_pixels * slots_pp) + 31u) & ~31u;
+        bool grow = tree || s->counts_len < nw0 * (size_t)(depth + 3) * SPT_ROW;
+        for (int li = 0; li < nl0; ++li) if (s->lane[li].wb.cap < cap0 || s->lane[li].wb.jcap < (size_t)cap0 * sub) grow = true;
+        if (grow) CU(cudaDeviceSynchronize());
+    }
     for (;;) {
         n_waves = (size_t)((local_pixels + wave_pixels - 1) / wave_pixels);
         n_lanes = tree ? 1 : (int)std::min<size_t>((size_t)s->max_lanes, std::max<size_t>(n_waves, 1));     // tree: every range is checked before it reaches the film
@@ -1129,11 +1179,20 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
     CU(cudaMemsetAsync(s->counts, 0, std::max<size_t>(n_waves, 1) * per_wave * 4, st));
     SampleSource src; src.smp = nullptr; src.stride = 0; src.rng = nullptr; src.n_rng = 0; src.seed = cfg.seed; src.spp = (uint32_t)rp->spp;
     FilmView fv; fv.d = film->desc; fv.pix = film->pix; fv.table = film->table;
-    reset_class_stats(s);
-    CU(cudaEventRecord(s->ev0, st));
-    for (int k = 1; k < n_lanes; ++k) CU(cudaStreamWaitEvent(s->lane[k].stream, s->ev0, 0));       // fork
-    uint64_t samples = 0;
-    std::vector<uint32_t> hc_tree;          // tree mode: the counter blocks of the pixel ranges that fitted, in the order they ran
+    if (!fr.ev0 && (!(fr.ev0 = g_handles.event(s->device, true)) || !(fr.ev1 = g_handles.event(s->device, true)) ||
+                    !(fr.evc = g_handles.event(s->device, false)))) return fail(SPT_ERR_CUDA, "event creation failed");
+    const size_t hc_words = std::max<size_t>(n_waves, 1) * per_wave;
+    if (fr.hc_cap < hc_words) {
+        if (fr.hc) cudaFreeHost(fr.hc);
+        fr.hc = nullptr; fr.hc_cap = 0;
+        if (cudaMallocHost((void **)&fr.hc, hc_words * 4) != cudaSuccess) return fail(SPT_ERR_CUDA, "cudaMallocHost failed");
+        fr.hc_cap = hc_words;
+    }
+    s->marks_on = fr.timed;
+    if (fr.timed) reset_class_stats(s);
+    CU(cudaEventRecord(fr.ev0, st));
+    for (int k = 1; k < n_lanes; ++k) CU(cudaStreamWaitEvent(s->lane[k].stream, fr.ev0, 0));       // fork
+    std::vector<uint32_t> &hc_tree = fr.hc_tree;          // tree mode: the counter blocks of the pixel ranges that fitted, in the order they ran
     if (tree) {
         // The node pool of a wave is what its buffers hold beyond the camera samples: (SPT_TREE_SLOTS - 1) per sample on average.
         // A range whose trees need more (a window full of glass) is NOT added to the film; it is cut in two and each half runs in
@@ -1178,31 +1237,54 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
         CU(cudaEventRecord(s->evjoin[k], s->lane[k].stream));
         CU(cudaStreamWaitEvent(st, s->evjoin[k], 0));
     }
-    CU(cudaEventRecord(s->ev1, st));
-    s->stats.lanes_used = n_lanes;
-    std::vector<uint32_t> hc(std::max<size_t>(n_waves, 1) * per_wave);
-    CU(cudaMemcpyAsync(hc.data(), s->counts, hc.size() * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    CU(cudaEventRecord(fr.ev1, st));
+    CU(cudaMemcpyAsync(fr.hc, s->counts, hc_words * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(fr.evc, st));
+    s->marks_on = true;
+    fr.tree = tree; fr.n_waves = n_waves; fr.per_wave = per_wave; fr.depth = depth; fr.n_lanes = n_lanes; fr.spp = rp->spp;
+    fr.nranks = nranks; fr.local_tiles = local_tiles; fr.cfg = cfg;
+    ++s->f_count;
+    return SPT_OK;
+}
+
+int spt_render_end(SptScene *s) {
+    if (!s) return fail(SPT_ERR_ARG, "null scene");
+    if (s->f_count == 0) return fail(SPT_ERR_ARG, "no frame in flight");
+    DeviceGuard dg(s->device);
+    SptScene::FrameRec &fr = s->frame[s->f_head];
+    s->f_head ^= 1; --s->f_count;
+    if (fr.empty) {
+        if (fr.timed) reset_class_stats(s);
+        s->stats.render_ms = 0.; s->stats.lanes_used = 0;
+        return SPT_OK;
+    }
+    CU(cudaEventSynchronize(fr.evc));
     CU(cudaGetLastError());
     float ms = 0.f;
-    cudaEventElapsedTime(&ms, s->ev0, s->ev1);
+    cudaEventElapsedTime(&ms, fr.ev0, fr.ev1);
     s->stats.render_ms = ms;
-    s->class_times_pending = true;          // ~80 cudaEventElapsedTime calls: only when spt_get_stats asks (not between frames)
-    if (tree) { hc.swap(hc_tree); n_waves = hc.size() / per_wave; }
+    s->stats.lanes_used = fr.n_lanes;
+    s->class_times_pending = fr.timed;      // ~80 cudaEventElapsedTime calls: only when spt_get_stats asks (not between frames)
+    const RenderCfg &cfg = fr.cfg;
+    size_t n_waves = fr.n_waves;
+    const size_t per_wave = fr.per_wave;
+    std::vector<uint32_t> hc;
+    if (fr.tree) { hc.swap(fr.hc_tree); n_waves = hc.size() / per_wave; }
+    else hc.assign(fr.hc, fr.hc + std::max<size_t>(n_waves, 1) * per_wave);
     // sample slots of tiles that overhang the sample extent carry rays that cannot hit anything: not samples
     uint64_t slots = 0, valid_pixels = 0;
     for (size_t w = 0; w < n_waves; ++w) slots += hc[w * per_wave];
-    for (uint64_t k = 0; k < local_tiles; ++k) {
-        uint64_t t = k * (uint64_t)nranks + (uint64_t)cfg.rank;
+    for (uint64_t k = 0; k < fr.local_tiles; ++k) {
+        uint64_t t = k * (uint64_t)fr.nranks + (uint64_t)cfg.rank;
         int tx = (int)(t % cfg.tilesX), ty = (int)(t / cfg.tilesX);
         int w = std::min(cfg.tile, cfg.x1 - (cfg.x0 + tx * cfg.tile)), h = std::min(cfg.tile, cfg.y1 - (cfg.y0 + ty * cfg.tile));
         if (w > 0 && h > 0) valid_pixels += (uint64_t)w * h;
     }
-    samples = valid_pixels * (uint64_t)rp->spp;
+    const uint64_t samples = valid_pixels * (uint64_t)fr.spp;
     s->stats.class_rays[SPT_K_GEN] = samples; s->stats.class_rays[SPT_K_FILM] = samples;
     s->stats.camera_samples += samples;
-    add_ray_stats(s, hc, depth, n_waves);
-    {   // the first wave's bounce 0: what the first launch of each class worked on (sample slots incl. the few that overhang the extent)
+    if (n_waves) add_ray_stats(s, hc, fr.depth, n_waves);
+    if (n_waves) {   // the first wave's bounce 0: what the first launch of each class worked on (sample slots incl. the few that overhang the extent)
         uint64_t *u = s->stats.first_launch_units;
         u[SPT_K_GEN] = hc[0]; u[SPT_K_FILM] = hc[0]; u[SPT_K_TRACE_PATH] = hc[0];
         u[SPT_K_SHADE] = hc[3]; u[SPT_K_ACCUMULATE] = hc[3]; u[SPT_K_ADVANCE] = hc[3];
@@ -1211,6 +1293,12 @@ int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRe
     s->stats.closest_rays -= overhang;
     s->stats.class_rays[SPT_K_TRACE_PATH] -= overhang;
     return SPT_OK;
+}
+
+int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRenderParams *rp) {
+    if (s && s->f_count) return fail(SPT_ERR_ARG, "a frame begun with spt_render_begin is in flight: spt_render_end first");
+    int rc = spt_render_begin(s, cam, film, rp);
+    return rc == SPT_OK ? spt_render_end(s) : rc;
 }
 
 
