@@ -321,31 +321,29 @@ def main():
     lanes_used = 1
     barrier()
     e0.record()
-    if dist is None:
-        for k in range(args.steps):
-            frame(k)
-            render_ms += scene.render_ms()
-    else:
-        # N > 1: the frames are pipelined over THREE film buffers, and the next frame is ENQUEUED (spt_render_begin) before the
-        # host waits for the current one (spt_render_end), so a rank's GPU goes from frame to frame without a host bubble.
-        # Frame k's end-of-frame barrier (a one-element all-reduce: once it completes every rank's samples are in buffer k % 3
-        # on rank 0) is enqueued behind the rank's render and waited for only before frame k + 2 is enqueued. Rank 0 clears
-        # buffer (k - 1) % 3 - complete since barrier k - 1 - BEFORE it enters barrier k; frame k + 2, the next to write that
-        # buffer, is enqueued on every rank behind barrier k. Every barrier has completed before the closing time stamp.
-        done = [torch.cuda.Event() for _ in range(args.steps)]
-        scene.render_begin(films[0], rp)
-        for k in range(args.steps):
-            if k + 1 < args.steps:
-                if k >= 1:
-                    done[k - 1].synchronize()
-                scene.render_begin(films[(k + 1) % n_buf], rp)
-            scene.render_end()                            # blocks until frame k has drained on this rank
-            render_ms += scene.render_ms()
+    # The frames are pipelined: a rank ENQUEUES frame k + 1 (spt_render_begin) before it waits for frame k (spt_render_end), so
+    # its GPU goes from frame to frame without a host bubble and each lane starts the next frame as soon as it is done with
+    # this one. N > 1: three film buffers on rank 0. Frame k's end-of-frame barrier (a one-element all-reduce: once it
+    # completes every rank's samples are in buffer k % 3) is enqueued behind the rank's render and waited for only before
+    # frame k + 2 is enqueued. Rank 0 clears buffer (k - 1) % 3 - complete since barrier k - 1 - BEFORE it enters barrier k;
+    # frame k + 2, the next to write that buffer, is enqueued on every rank behind barrier k. Every barrier has completed
+    # before the closing time stamp. N = 1: one film, the frames add up in it.
+    done = [torch.cuda.Event() for _ in range(args.steps)] if dist is not None else None
+    scene.render_begin(films[0], rp)
+    for k in range(args.steps):
+        if k + 1 < args.steps:
+            if dist is not None and k >= 1:
+                done[k - 1].synchronize()
+            scene.render_begin(films[(k + 1) % n_buf], rp)
+        scene.render_end()                                # blocks until frame k has drained on this rank
+        render_ms += scene.render_ms()
+        if dist is not None:
             if rank == 0 and k >= 1:
                 done[k - 1].synchronize()
                 films[(k - 1) % n_buf].clear_idle()
             dist.all_reduce(sync_t)
             done[k].record()
+    if dist is not None:
         for k in range(max(args.steps - 2, 0), args.steps):
             done[k].synchronize()
         if rank == 0:
@@ -442,8 +440,8 @@ def main():
         launches = int(lt[0])
     else:
         render_only_ms = render_ms / args.steps
-    # N=1: the job is spt_render itself (library events); N>1: render + NCCL reduce (max over ranks)
-    ms_per_step = render_only_ms if world == 1 else step_ms
+    # the K timed steps as one job: wall clock between the two time stamps / K, max over ranks (N > 1: incl. the end-of-frame barriers)
+    ms_per_step = step_ms
     value = n_samples_total / (ms_per_step / 1e3) / 1e6
 
     # ---- e2e through the C ABI with host buffers (rank-local: each rank uploads, renders its tiles, downloads)

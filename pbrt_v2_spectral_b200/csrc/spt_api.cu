@@ -183,6 +183,7 @@ struct SptScene {
     uint32_t *counts = nullptr;      // device queue lengths: per wave, (max_depth+2) rows of SPT_ROW words
     size_t counts_len = 0;
     cudaStream_t stream = nullptr;   // = lane[0].stream
+    cudaStream_t bk = nullptr;       // book-keeping: end-of-frame join of the lanes, frame-end event, counter read-back
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     SptStats stats{};
     bool class_times_pending = false;    // the per-launch event deltas of the last render are folded into stats.class_ms on demand
@@ -219,12 +220,14 @@ struct SptScene {
 };
 
 static void destroy_lanes(SptScene *s) {
+    g_handles.put(s->device, s->bk); s->bk = nullptr;
     for (int k = 0; k < SPT_MAX_LANES; ++k) {
         g_handles.put(s->device, s->lane[k].stream); s->lane[k].stream = nullptr;
         g_handles.put(s->device, s->evjoin[k], false); s->evjoin[k] = nullptr;
     }
 }
 static bool make_lanes(SptScene *s) {
+    if (!(s->bk = g_handles.stream(s->device))) return false;
     for (int k = 0; k < SPT_MAX_LANES; ++k)
         if (!(s->lane[k].stream = g_handles.stream(s->device)) || !(s->evjoin[k] = g_handles.event(s->device, false))) { destroy_lanes(s); return false; }
     return true;
@@ -608,12 +611,12 @@ static int tree_slots() {                 // SPT_TREE_SLOTS in the environment: 
     if (const char *e = getenv("SPT_TREE_SLOTS")) return std::min(std::max(atoi(e), 2), 64);
     return SPT_TREE_SLOTS;
 }
-static int ensure_wave(SptScene *s, int n_lanes, uint32_t cap, int max_depth, size_t n_waves, uint32_t sub = 1) {
+static int ensure_wave(SptScene *s, int n_lanes, uint32_t cap, int max_depth, size_t n_waves, uint32_t sub = 1, int lane_base = 0) {
     cap = (cap + 31u) & ~31u;
     const size_t jcap = (size_t)cap * sub;
     if (jcap > 0xffffffffull) return fail(SPT_ERR_ARG, "wave too large: paths x jobs per path exceeds 2^32 (lower wave_pixels)");
-    size_t need_counts = n_waves * (size_t)(max_depth + 3) * SPT_ROW;
-    for (int li = 0; li < n_lanes; ++li) {
+    size_t need_counts = 2 * n_waves * (size_t)(max_depth + 3) * SPT_ROW;      // two frames in flight: one half each
+    for (int li = lane_base; li < lane_base + n_lanes; ++li) {
         SptScene::Lane &ln = s->lane[li];
         if (ln.wb.cap >= cap && ln.wb.jcap >= jcap) continue;
         ln.mem.release();
@@ -1079,7 +1082,8 @@ int spt_film_add_samples(SptFilm *f, const SptSpectralTables *tables, const floa
 }
 
 // ---- the whole job -------------------------------------------------------------------------------
-int spt_render_begin(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRenderParams *rp) {
+// pipelined: the caller keeps two frames in flight (spt_render_begin); false: one frame, the host waits for it (spt_render)
+static int render_begin(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRenderParams *rp, bool pipelined) {
     if (!s || !cam || !film || !rp) return fail(SPT_ERR_ARG, "null argument");
     if (film->device != s->device) return fail(SPT_ERR_ARG, "scene and film live on different devices");
     if (s->f_count >= 2) return fail(SPT_ERR_ARG, "two frames are already in flight: spt_render_end first");
@@ -1121,7 +1125,8 @@ int spt_render_begin(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const
     uint64_t ntiles = (uint64_t)cfg.tilesX * cfg.tilesY;
     uint64_t local_tiles = ntiles > (uint64_t)cfg.rank ? (ntiles - cfg.rank + nranks - 1) / nranks : 0;
     uint64_t local_pixels = local_tiles * (uint64_t)cfg.tile * cfg.tile;
-    SptScene::FrameRec &fr = s->frame[(s->f_head + s->f_count) & 1];
+    const int slot = (s->f_head + s->f_count) & 1;            // frame records alternate
+    SptScene::FrameRec &fr = s->frame[slot];
     fr.timed = s->f_count == 0; fr.tree = false; fr.empty = false; fr.hc_tree.clear();
     if (local_pixels == 0) {            // a rank that owns no tile (more ranks than tiles): nothing to render
         fr.empty = true;
@@ -1139,6 +1144,16 @@ int spt_render_begin(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const
     if (want_lanes > 2 && local_pixels * mem_pp <= (1ull << 25)) want_lanes = 2;
     while (want_lanes > 1 && local_samples < ((uint64_t)want_lanes << 19)) --want_lanes;
     if (const char *e = getenv("SPT_FORCE_LANES")) want_lanes = std::min(std::max(atoi(e), 1), s->max_lanes);      // A/B runs (profiles/tools)
+    // Frames kept two in flight on a small share of the image (several GPUs): every launch pays a fixed drain tail - the
+    // longest ray of a persistent trace launch is ~50-100 us of dependent L2 round trips whatever the launch's size - so a
+    // frame is ONE wave (half as many launches as two half-size waves) and consecutive frames alternate between two lanes,
+    // which keeps two independent kernel chains on the device as the two waves of one frame did.
+    int lane_base = 0;
+    static const int pipe_mode = [] { const char *e = getenv("SPT_PIPE_MODE"); return e ? atoi(e) : 1; }();
+    if (pipelined && !tree && s->max_lanes >= 2 && rp->wave_pixels <= 0) {
+        if (pipe_mode == 1 && local_pixels * mem_pp <= (1ull << 24)) { want_lanes = 1; lane_base = slot; }
+        else if (pipe_mode == 2 && s->max_lanes >= 4 && want_lanes == 2 && local_pixels * mem_pp <= (1ull << 23)) lane_base = 2 * slot;
+    }
     const uint64_t lane_cap_pixels = std::max<uint64_t>(1, ((1u << 25) / (uint64_t)want_lanes) / mem_pp);
     uint64_t wave_pixels;
     if (rp->wave_pixels > 0) wave_pixels = (uint64_t)rp->wave_pixels;
@@ -1156,16 +1171,17 @@ int spt_render_begin(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const
     // specular tree checks every pixel range on the host, so it starts on an idle device as well
     if (s->f_count > 0) {
         const size_t nw0 = (size_t)((local_pixels + wave_pixels - 1) / wave_pixels);
-        const int nl0 = tree ? 1 : (int)std::min<size_t>((size_t)s->max_lanes, std::max<size_t>(nw0, 1));
+        const int nl0 = tree ? 1 : (int)std::min<size_t>((size_t)(s->max_lanes - lane_base), std::max<size_t>(nw0, 1));
         const uint32_t cap0 = ((uint32_t)(wave_pixels * slots_pp) + 31u) & ~31u;
-        bool grow = tree || s->counts_len < nw0 * (size_t)(depth + 3) * SPT_ROW;
-        for (int li = 0; li < nl0; ++li) if (s->lane[li].wb.cap < cap0 || s->lane[li].wb.jcap < (size_t)cap0 * sub) grow = true;
+        bool grow = tree || s->counts_len < 2 * nw0 * (size_t)(depth + 3) * SPT_ROW;
+        for (int li = lane_base; li < lane_base + nl0; ++li) if (s->lane[li].wb.cap < cap0 || s->lane[li].wb.jcap < (size_t)cap0 * sub) grow = true;
         if (grow) CU(cudaDeviceSynchronize());
     }
     for (;;) {
         n_waves = (size_t)((local_pixels + wave_pixels - 1) / wave_pixels);
-        n_lanes = tree ? 1 : (int)std::min<size_t>((size_t)s->max_lanes, std::max<size_t>(n_waves, 1));     // tree: every range is checked before it reaches the film
-        rc = ensure_wave(s, n_lanes, (uint32_t)(wave_pixels * slots_pp), depth, std::max<size_t>(n_waves, 1), (uint32_t)sub);
+        n_lanes = tree ? 1 : (int)std::min<size_t>((size_t)(s->max_lanes - lane_base), std::max<size_t>(n_waves, 1));     // tree: every range is checked before it reaches the film
+        if (lane_base) n_lanes = std::min(n_lanes, want_lanes);
+        rc = ensure_wave(s, n_lanes, (uint32_t)(wave_pixels * slots_pp), depth, std::max<size_t>(n_waves, 1), (uint32_t)sub, lane_base);
         // a part with less free memory than the default sizing assumes: smaller waves instead of an error
         if (rc != SPT_ERR_CUDA || wave_pixels * slots_pp <= (1u << 16)) break;
         cudaDeviceSynchronize();
@@ -1175,8 +1191,9 @@ int spt_render_begin(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const
     }
     if (rc != SPT_OK) return rc;
     size_t per_wave = (size_t)(depth + 3) * SPT_ROW;
-    cudaStream_t st = s->stream;
-    CU(cudaMemsetAsync(s->counts, 0, std::max<size_t>(n_waves, 1) * per_wave * 4, st));
+    cudaStream_t st = s->lane[lane_base].stream;
+    // the frame's counter rows: this record's half of the array, zeroed wave by wave on the lane that runs the wave
+    uint32_t *counts = s->counts + (size_t)slot * (s->counts_len / 2);
     SampleSource src; src.smp = nullptr; src.stride = 0; src.rng = nullptr; src.n_rng = 0; src.seed = cfg.seed; src.spp = (uint32_t)rp->spp;
     FilmView fv; fv.d = film->desc; fv.pix = film->pix; fv.table = film->table;
     if (!fr.ev0 && (!(fr.ev0 = g_handles.event(s->device, true)) || !(fr.ev1 = g_handles.event(s->device, true)) ||
@@ -1191,7 +1208,10 @@ int spt_render_begin(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const
     s->marks_on = fr.timed;
     if (fr.timed) reset_class_stats(s);
     CU(cudaEventRecord(fr.ev0, st));
-    for (int k = 1; k < n_lanes; ++k) CU(cudaStreamWaitEvent(s->lane[k].stream, fr.ev0, 0));       // fork
+    // fork - only for a frame that starts on an idle scene. A frame enqueued behind another one needs no common start: every lane
+    // goes on with its next wave in stream order (its wave buffers are its own, the counter rows this record's), so one lane's
+    // last kernels of frame k run beside the other lane's first kernels of frame k + 1 instead of beside an idle half machine.
+    if (fr.timed) for (int k = 1; k < n_lanes; ++k) CU(cudaStreamWaitEvent(s->lane[lane_base + k].stream, fr.ev0, 0));
     std::vector<uint32_t> &hc_tree = fr.hc_tree;          // tree mode: the counter blocks of the pixel ranges that fitted, in the order they ran
     if (tree) {
         // The node pool of a wave is what its buffers hold beyond the camera samples: (SPT_TREE_SLOTS - 1) per sample on average.
@@ -1204,11 +1224,11 @@ int spt_render_begin(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const
         while (!todo.empty()) {
             const uint64_t base = todo.back().first, np = todo.back().second;
             todo.pop_back();
-            CU(cudaMemsetAsync(s->counts, 0, per_wave * 4, st));
+            CU(cudaMemsetAsync(counts, 0, per_wave * 4, st));
             cfg.pixel_base = base;
             cfg.n_samples = (uint32_t)(np * (uint64_t)rp->spp);
-            run_wave(s, cfg, src, s->counts, 0);
-            CU(cudaMemcpyAsync(blk.data(), s->counts, per_wave * 4, cudaMemcpyDeviceToHost, st));
+            run_wave(s, cfg, src, counts, 0);
+            CU(cudaMemcpyAsync(blk.data(), counts, per_wave * 4, cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
             if (blk[12]) {
                 if (np == 1) return fail(SPT_ERR_UNSUPP, "specular tree: one pixel's samples spawn more nodes than a wave holds");
@@ -1223,23 +1243,26 @@ int spt_render_begin(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const
         }
     } else
     for (size_t w = 0; w < n_waves; ++w) {
-        const int li = (int)(w % (size_t)n_lanes);
+        const int li = lane_base + (int)(w % (size_t)n_lanes);
         cfg.pixel_base = (uint64_t)w * wave_pixels;
         uint64_t np = std::min<uint64_t>(wave_pixels, local_pixels - cfg.pixel_base);
         cfg.n_samples = (uint32_t)(np * (uint64_t)rp->spp);
-        run_wave(s, cfg, src, s->counts + w * per_wave, li);
+        CU(cudaMemsetAsync(counts + w * per_wave, 0, per_wave * 4, s->lane[li].stream));
+        run_wave(s, cfg, src, counts + w * per_wave, li);
         unsigned gw = (unsigned)std::min<uint64_t>((np * 32 + 255) / 256, (uint64_t)num_sms() * 16);
         const WaveBuffers &wb = s->lane[li].wb;
         spt_launch_film_add((int)gw, s->lane[li].stream, fv, s->dev.tables, wb.img_xy, wb.L, wb.cap, (uint32_t)(np * rp->spp), rp->spp);
         s->mark(SPT_K_FILM, li);
     }
-    for (int k = 1; k < n_lanes; ++k) {                                              // join
+    // join - on the book-keeping stream, not on a lane: no lane waits for another one, so a frame enqueued behind this one
+    // starts on each lane as soon as that lane is done here
+    for (int k = lane_base; k < lane_base + n_lanes; ++k) {
         CU(cudaEventRecord(s->evjoin[k], s->lane[k].stream));
-        CU(cudaStreamWaitEvent(st, s->evjoin[k], 0));
+        CU(cudaStreamWaitEvent(s->bk, s->evjoin[k], 0));
     }
-    CU(cudaEventRecord(fr.ev1, st));
-    CU(cudaMemcpyAsync(fr.hc, s->counts, hc_words * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaEventRecord(fr.evc, st));
+    CU(cudaEventRecord(fr.ev1, s->bk));
+    CU(cudaMemcpyAsync(fr.hc, counts, hc_words * 4, cudaMemcpyDeviceToHost, s->bk));
+    CU(cudaEventRecord(fr.evc, s->bk));
     s->marks_on = true;
     fr.tree = tree; fr.n_waves = n_waves; fr.per_wave = per_wave; fr.depth = depth; fr.n_lanes = n_lanes; fr.spp = rp->spp;
     fr.nranks = nranks; fr.local_tiles = local_tiles; fr.cfg = cfg;
@@ -1297,9 +1320,10 @@ int spt_render_end(SptScene *s) {
 
 int spt_render(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRenderParams *rp) {
     if (s && s->f_count) return fail(SPT_ERR_ARG, "a frame begun with spt_render_begin is in flight: spt_render_end first");
-    int rc = spt_render_begin(s, cam, film, rp);
+    int rc = render_begin(s, cam, film, rp, false);
     return rc == SPT_OK ? spt_render_end(s) : rc;
 }
+int spt_render_begin(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRenderParams *rp) { return render_begin(s, cam, film, rp, true); }
 
 
 // ---- several GPUs ------------------------------------------------------------------------------------
