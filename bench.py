@@ -159,6 +159,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--wave-pixels", type=int, default=0)
+    ap.add_argument("--frames-ahead", type=int, default=0, help="frames enqueued ahead of the one the host waits for (1..3; default 1 on one GPU, 2 on several)")
     ap.add_argument("--bands", type=int, default=32, choices=[32, 30], help="32: SampledSpectrum as the reference ships it (default); 30: the 30-band "
                     "variant BASELINE.json's metric names - libspt30.so against the reference built with nSpectralSamples = 30 (oracle/_ref/bin30)")
     ap.add_argument("--workload", default=None, help="lowered scene under assets/_lowered (default: BASELINE config 1); "
@@ -257,7 +258,8 @@ def main():
     # N = 1: the film is the library's. N > 1: ONE film per frame buffer lives on rank 0 (spt_film_create there, exported with
     # spt_film_ipc_export); the other ranks open it (spt_film_open_ipc) and their film kernel adds their tile sets' samples
     # straight into it over NVLink - the "gather" is fused into K7, what is left of it is a barrier at the end of the frame.
-    n_buf = 3 if world > 1 else 1
+    ahead = min(max(args.frames_ahead, 1), 3) if args.frames_ahead else (2 if world > 1 else 1)           # frames enqueued ahead of the one the host waits for
+    n_buf = ahead + 2 if world > 1 else 1
     if world == 1:
         films = [capi.Film(fd)]
     else:
@@ -281,7 +283,8 @@ def main():
         """One whole frame of the job on N GPUs: every rank renders its tile set into film buffer k % n_buf (rank 0's memory),
         the end-of-frame barrier makes the film complete, and rank 0 clears it for the frame after next."""
         f = films[k % n_buf]
-        scene.render(f, params if params is not None else rp)        # blocks until this rank's streams have drained
+        scene.render_begin(f, params if params is not None else rp)  # the entry points of the timed region (same wave layout)
+        scene.render_end()                                            # blocks until this rank's streams have drained
         if dist is not None:
             dist.all_reduce(sync_t)
             torch.cuda.current_stream().synchronize()
@@ -321,20 +324,22 @@ def main():
     lanes_used = 1
     barrier()
     e0.record()
-    # The frames are pipelined: a rank ENQUEUES frame k + 1 (spt_render_begin) before it waits for frame k (spt_render_end), so
-    # its GPU goes from frame to frame without a host bubble and each lane starts the next frame as soon as it is done with
-    # this one. N > 1: three film buffers on rank 0. Frame k's end-of-frame barrier (a one-element all-reduce: once it
-    # completes every rank's samples are in buffer k % 3) is enqueued behind the rank's render and waited for only before
-    # frame k + 2 is enqueued. Rank 0 clears buffer (k - 1) % 3 - complete since barrier k - 1 - BEFORE it enters barrier k;
-    # frame k + 2, the next to write that buffer, is enqueued on every rank behind barrier k. Every barrier has completed
-    # before the closing time stamp. N = 1: one film, the frames add up in it.
+    # The frames are pipelined: a rank ENQUEUES frames k + 1 .. k + A (spt_render_begin; A = 1 on one GPU, 2 on several) before
+    # it waits for frame k (spt_render_end), so its GPU goes from frame to frame without a host bubble, and on a 1/N share of
+    # the image - where a frame is one wave - consecutive frames run side by side on different lanes. N > 1: A + 2 film
+    # buffers on rank 0. Frame k's end-of-frame barrier (a one-element all-reduce: once it completes every rank's samples are
+    # in buffer k % (A + 2)) is enqueued behind the rank's render. Rank 0 clears buffer (k - 1) % (A + 2) - complete since
+    # barrier k - 1 - BEFORE it enters barrier k; frame k + A + 1, the next to write that buffer, is enqueued on every rank only
+    # once barrier k has completed. Every barrier has completed before the closing time stamp. N = 1: one film, the frames add
+    # up in it.
     done = [torch.cuda.Event() for _ in range(args.steps)] if dist is not None else None
-    scene.render_begin(films[0], rp)
+    for j in range(min(ahead, args.steps)):
+        scene.render_begin(films[j % n_buf], rp)
     for k in range(args.steps):
-        if k + 1 < args.steps:
+        if k + ahead < args.steps:
             if dist is not None and k >= 1:
                 done[k - 1].synchronize()
-            scene.render_begin(films[(k + 1) % n_buf], rp)
+            scene.render_begin(films[(k + ahead) % n_buf], rp)
         scene.render_end()                                # blocks until frame k has drained on this rank
         render_ms += scene.render_ms()
         if dist is not None:
@@ -587,10 +592,10 @@ def main():
                    "parallelism": "image tile sets (32x32, round-robin) x%d, scene replicated; every rank's film kernel adds its samples straight into ONE film "
                                   "on rank 0 through a peer mapping (NVLink), a NCCL barrier ends the frame" % world,
                    "l2": "per-step wave state (>2 GB) and film are larger than L2; no explicit flush",
-                   "pipelining": "N > 1: three film buffers; a rank enqueues frame k+1 (spt_render_begin) before it waits for frame k (spt_render_end); "
-                                 "frame k's end-of-frame barrier is waited for before frame k+2 is enqueued, rank 0 clears a buffer behind its "
-                                 "frame's barrier and before it enters the next one; every frame's film is complete on rank 0 (every barrier "
-                                 "has completed) inside the timed region"},
+                   "pipelining": "a rank enqueues frames k+1..k+A (spt_render_begin; A = 1 at N = 1, 2 at N > 1) before it waits for frame k "
+                                 "(spt_render_end). N > 1: A + 2 film buffers on rank 0; frame k's end-of-frame barrier is waited for before "
+                                 "frame k+A+1 is enqueued, rank 0 clears a buffer behind its frame's barrier and before it enters the next "
+                                 "one; every frame's film is complete on rank 0 (every barrier has completed) inside the timed region"},
         "mrays_per_s": rays_total / prof_steps / (ms_per_step / 1e3) / 1e6 if world == 1 else None,
         "rays_per_sample": rays_total / prof_steps / (n_samples_total / world) if world else None,
         "rays_per_sample_reference": (rays_total + elided) / prof_steps / (n_samples_total / world) if world else None,

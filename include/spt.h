@@ -397,8 +397,8 @@ int      spt_film_write_dat(SptFilm *film, const char *path);
 int spt_render(SptScene *scene, const SptCameraDesc *cam, SptFilm *film, const SptRenderParams *params);
 /* The same job in two calls, for a host that renders frame after frame (the reference renders one image per process, so it has
  * no counterpart there): spt_render_begin enqueues the frame and returns; spt_render_end waits for the OLDEST frame begun and
- * finishes its statistics. Up to two frames may be in flight on a scene - begin(k + 1) before end(k) - so that the device goes
- * from one frame to the next without waiting for the host; they run one after the other, in order, in the same wave buffers
+ * finishes its statistics. Up to four frames may be in flight on a scene - begin(k + 1) before end(k) - so that the device goes
+ * from one frame to the next without waiting for the host; each stream runs its waves in order, in its own wave buffers
  * (frames into different films, or into one film that is meant to accumulate both). Per-kernel-class times (SptStats::class_ms)
  * are only collected for a frame begun while no other was in flight. Between begin and end only these two calls, spt_get_stats
  * and spt_last_render_ms may be used on the scene. */

@@ -225,7 +225,7 @@ class Scene:
         _check(lib().spt_render(self.h, C.byref(cam), film.h, C.byref(rp)))
 
     def render_begin(self, film, params=None, camera=None):
-        """Enqueue a frame and return (spt_render_begin); up to two frames may be in flight."""
+        """Enqueue a frame and return (spt_render_begin); up to four frames may be in flight."""
         rp = params if params is not None else self.lowered.params
         cam = camera if camera is not None else self.lowered.camera
         _check(lib().spt_render_begin(self.h, C.byref(cam), film.h, C.byref(rp)))

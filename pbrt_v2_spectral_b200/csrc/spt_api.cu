@@ -106,6 +106,7 @@ int num_sms() {
 }  // namespace
 
 #define SPT_MAX_LANES 4
+#define SPT_MAX_FRAMES 4            // frames in flight on a scene (spt_render_begin)
 // Streams and events outlive the scene that created them: a host that builds a scene per frame (the reference's renderer does)
 // would otherwise pay 4 stream + ~80 event creations per frame (0.3 ms). Keyed by device; emptied by spt_trim().
 #define SPT_POOL_DEVICES 64
@@ -215,7 +216,7 @@ struct SptScene {
         uint32_t *hc = nullptr;      // page-locked copy of the frame's counter rows
         size_t hc_cap = 0;
         std::vector<uint32_t> hc_tree;
-    } frame[2];
+    } frame[SPT_MAX_FRAMES];
     int f_head = 0, f_count = 0;     // oldest record, records in flight
 };
 
@@ -615,7 +616,7 @@ static int ensure_wave(SptScene *s, int n_lanes, uint32_t cap, int max_depth, si
     cap = (cap + 31u) & ~31u;
     const size_t jcap = (size_t)cap * sub;
     if (jcap > 0xffffffffull) return fail(SPT_ERR_ARG, "wave too large: paths x jobs per path exceeds 2^32 (lower wave_pixels)");
-    size_t need_counts = 2 * n_waves * (size_t)(max_depth + 3) * SPT_ROW;      // two frames in flight: one half each
+    size_t need_counts = SPT_MAX_FRAMES * n_waves * (size_t)(max_depth + 3) * SPT_ROW;      // frames in flight: one part each
     for (int li = lane_base; li < lane_base + n_lanes; ++li) {
         SptScene::Lane &ln = s->lane[li];
         if (ln.wb.cap >= cap && ln.wb.jcap >= jcap) continue;
@@ -1082,11 +1083,11 @@ int spt_film_add_samples(SptFilm *f, const SptSpectralTables *tables, const floa
 }
 
 // ---- the whole job -------------------------------------------------------------------------------
-// pipelined: the caller keeps two frames in flight (spt_render_begin); false: one frame, the host waits for it (spt_render)
+// pipelined: the caller keeps frames in flight (spt_render_begin); false: one frame, the host waits for it (spt_render)
 static int render_begin(SptScene *s, const SptCameraDesc *cam, SptFilm *film, const SptRenderParams *rp, bool pipelined) {
     if (!s || !cam || !film || !rp) return fail(SPT_ERR_ARG, "null argument");
     if (film->device != s->device) return fail(SPT_ERR_ARG, "scene and film live on different devices");
-    if (s->f_count >= 2) return fail(SPT_ERR_ARG, "two frames are already in flight: spt_render_end first");
+    if (s->f_count >= SPT_MAX_FRAMES) return fail(SPT_ERR_ARG, "four frames are already in flight: spt_render_end first");
     DeviceGuard dg(s->device);
     if (rp->spp <= 0 || (rp->spp & (rp->spp - 1))) return fail(SPT_ERR_ARG, "spp must be a power of two (LDSampler rounds up)");
     if (rp->max_depth < 0 || rp->max_depth > 64) return fail(SPT_ERR_ARG, "max_depth out of range");
@@ -1125,7 +1126,7 @@ static int render_begin(SptScene *s, const SptCameraDesc *cam, SptFilm *film, co
     uint64_t ntiles = (uint64_t)cfg.tilesX * cfg.tilesY;
     uint64_t local_tiles = ntiles > (uint64_t)cfg.rank ? (ntiles - cfg.rank + nranks - 1) / nranks : 0;
     uint64_t local_pixels = local_tiles * (uint64_t)cfg.tile * cfg.tile;
-    const int slot = (s->f_head + s->f_count) & 1;            // frame records alternate
+    const int slot = (s->f_head + s->f_count) % SPT_MAX_FRAMES;            // frame records: a ring
     SptScene::FrameRec &fr = s->frame[slot];
     fr.timed = s->f_count == 0; fr.tree = false; fr.empty = false; fr.hc_tree.clear();
     if (local_pixels == 0) {            // a rank that owns no tile (more ranks than tiles): nothing to render
@@ -1144,15 +1145,21 @@ static int render_begin(SptScene *s, const SptCameraDesc *cam, SptFilm *film, co
     if (want_lanes > 2 && local_pixels * mem_pp <= (1ull << 25)) want_lanes = 2;
     while (want_lanes > 1 && local_samples < ((uint64_t)want_lanes << 19)) --want_lanes;
     if (const char *e = getenv("SPT_FORCE_LANES")) want_lanes = std::min(std::max(atoi(e), 1), s->max_lanes);      // A/B runs (profiles/tools)
-    // Frames kept two in flight on a small share of the image (several GPUs): every launch pays a fixed drain tail - the
-    // longest ray of a persistent trace launch is ~50-100 us of dependent L2 round trips whatever the launch's size - so a
-    // frame is ONE wave (half as many launches as two half-size waves) and consecutive frames alternate between two lanes,
-    // which keeps two independent kernel chains on the device as the two waves of one frame did.
-    int lane_base = 0;
+    // Frames kept in flight on a small share of the image (several GPUs): every launch pays a fixed drain tail - the longest
+    // ray of a persistent trace launch is ~50-100 us of dependent L2 round trips whatever the launch's size - so a frame is
+    // ONE wave (half as many launches as two half-size waves) and consecutive frames go to different lanes, which keeps two
+    // or three independent kernel chains on the device as the two waves of one frame did. Rank 0's tile set of 8 GPUs, one
+    // GPU: 5.50 ms per frame as two waves, 5.17 as one wave with two frames in flight, 5.07 with three
+    // (profiles/r02_pipe_modes.log, r02_pipe_depth.log; SPT_PIPE_MODE=0 restores the two-wave frames).
+    int lane_base = 0, rot = 0;             // rot: lanes the one-wave frames rotate over (their wave buffers are sized together)
     static const int pipe_mode = [] { const char *e = getenv("SPT_PIPE_MODE"); return e ? atoi(e) : 1; }();
+    static const int pipe_lanes = [] { const char *e = getenv("SPT_PIPE_LANES"); return e ? std::min(std::max(atoi(e), 1), SPT_MAX_LANES) : 4; }();
     if (pipelined && !tree && s->max_lanes >= 2 && rp->wave_pixels <= 0) {
-        if (pipe_mode == 1 && local_pixels * mem_pp <= (1ull << 24)) { want_lanes = 1; lane_base = slot; }
-        else if (pipe_mode == 2 && s->max_lanes >= 4 && want_lanes == 2 && local_pixels * mem_pp <= (1ull << 23)) lane_base = 2 * slot;
+        if (pipe_mode == 1 && local_pixels * mem_pp <= (1ull << 24)) {
+            want_lanes = 1;
+            rot = std::min(s->max_lanes, local_pixels * mem_pp <= (1ull << 23) ? pipe_lanes : 2);     // wave state: at most 2^25 paths over the lanes
+            lane_base = slot % rot;
+        }
     }
     const uint64_t lane_cap_pixels = std::max<uint64_t>(1, ((1u << 25) / (uint64_t)want_lanes) / mem_pp);
     uint64_t wave_pixels;
@@ -1173,15 +1180,15 @@ static int render_begin(SptScene *s, const SptCameraDesc *cam, SptFilm *film, co
         const size_t nw0 = (size_t)((local_pixels + wave_pixels - 1) / wave_pixels);
         const int nl0 = tree ? 1 : (int)std::min<size_t>((size_t)(s->max_lanes - lane_base), std::max<size_t>(nw0, 1));
         const uint32_t cap0 = ((uint32_t)(wave_pixels * slots_pp) + 31u) & ~31u;
-        bool grow = tree || s->counts_len < 2 * nw0 * (size_t)(depth + 3) * SPT_ROW;
-        for (int li = lane_base; li < lane_base + nl0; ++li) if (s->lane[li].wb.cap < cap0 || s->lane[li].wb.jcap < (size_t)cap0 * sub) grow = true;
+        bool grow = tree || s->counts_len < SPT_MAX_FRAMES * nw0 * (size_t)(depth + 3) * SPT_ROW;
+        for (int li = rot ? 0 : lane_base; li < (rot ? rot : lane_base + nl0); ++li) if (s->lane[li].wb.cap < cap0 || s->lane[li].wb.jcap < (size_t)cap0 * sub) grow = true;
         if (grow) CU(cudaDeviceSynchronize());
     }
     for (;;) {
         n_waves = (size_t)((local_pixels + wave_pixels - 1) / wave_pixels);
         n_lanes = tree ? 1 : (int)std::min<size_t>((size_t)(s->max_lanes - lane_base), std::max<size_t>(n_waves, 1));     // tree: every range is checked before it reaches the film
-        if (lane_base) n_lanes = std::min(n_lanes, want_lanes);
-        rc = ensure_wave(s, n_lanes, (uint32_t)(wave_pixels * slots_pp), depth, std::max<size_t>(n_waves, 1), (uint32_t)sub, lane_base);
+        if (rot) n_lanes = 1;              // a frame's waves (more than one only on a part short of memory) stay on its lane
+        rc = ensure_wave(s, rot ? rot : n_lanes, (uint32_t)(wave_pixels * slots_pp), depth, std::max<size_t>(n_waves, 1), (uint32_t)sub, rot ? 0 : lane_base);
         // a part with less free memory than the default sizing assumes: smaller waves instead of an error
         if (rc != SPT_ERR_CUDA || wave_pixels * slots_pp <= (1u << 16)) break;
         cudaDeviceSynchronize();
@@ -1193,7 +1200,7 @@ static int render_begin(SptScene *s, const SptCameraDesc *cam, SptFilm *film, co
     size_t per_wave = (size_t)(depth + 3) * SPT_ROW;
     cudaStream_t st = s->lane[lane_base].stream;
     // the frame's counter rows: this record's half of the array, zeroed wave by wave on the lane that runs the wave
-    uint32_t *counts = s->counts + (size_t)slot * (s->counts_len / 2);
+    uint32_t *counts = s->counts + (size_t)slot * (s->counts_len / SPT_MAX_FRAMES);
     SampleSource src; src.smp = nullptr; src.stride = 0; src.rng = nullptr; src.n_rng = 0; src.seed = cfg.seed; src.spp = (uint32_t)rp->spp;
     FilmView fv; fv.d = film->desc; fv.pix = film->pix; fv.table = film->table;
     if (!fr.ev0 && (!(fr.ev0 = g_handles.event(s->device, true)) || !(fr.ev1 = g_handles.event(s->device, true)) ||
@@ -1275,7 +1282,7 @@ int spt_render_end(SptScene *s) {
     if (s->f_count == 0) return fail(SPT_ERR_ARG, "no frame in flight");
     DeviceGuard dg(s->device);
     SptScene::FrameRec &fr = s->frame[s->f_head];
-    s->f_head ^= 1; --s->f_count;
+    s->f_head = (s->f_head + 1) % SPT_MAX_FRAMES; --s->f_count;
     if (fr.empty) {
         if (fr.timed) reset_class_stats(s);
         s->stats.render_ms = 0.; s->stats.lanes_used = 0;

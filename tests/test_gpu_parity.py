@@ -223,34 +223,35 @@ def test_specular_tree_ranges_that_overflow_are_split(monkeypatch):
     assert st1["camera_samples"] == st0["camera_samples"]
 
 
-def test_two_frames_in_flight_equal_two_renders():
-    """spt_render_begin / spt_render_end: frame k + 1 is enqueued before the host waits for frame k. Two frames (other seeds,
-    other films) rendered that way equal the same frames rendered one at a time; a third begin is refused, and so is any other
+def test_frames_in_flight_equal_separate_renders():
+    """spt_render_begin / spt_render_end: frame k + 1 is enqueued before the host waits for frame k. Four frames (other seeds,
+    other films) rendered that way equal the same frames rendered one at a time; a fifth begin is refused, and so is any other
     use of the scene while a frame is in flight."""
     lowered, g = O.load_case(*CASES[0][1:])
     scene = capi.Scene(lowered)
     rps = []
-    for seed in (3, 4):
+    for seed in (3, 4, 5, 6):
         rp = D.SptRenderParams.from_buffer_copy(bytes(lowered.params)); rp.seed = seed; rp.spp = 8
         rps.append(rp)
     want = []
     for rp in rps:
         f = capi.Film(lowered.film); scene.render(f, rp); want.append(f.download()); f.close()
-    films = [capi.Film(lowered.film), capi.Film(lowered.film)]
+    films = [capi.Film(lowered.film) for _ in rps]
     before = scene.stats()["camera_samples"]
-    scene.render_begin(films[0], rps[0])
-    scene.render_begin(films[1], rps[1])
+    for f, rp in zip(films, rps):
+        scene.render_begin(f, rp)
     with pytest.raises(capi.SptError, match="in flight"):
         scene.render_begin(films[1], rps[1])
     with pytest.raises(capi.SptError, match="in flight"):
         scene.trace_any(g["rays2"][:64])
     scene.render_end()
     assert scene.stats()["render_ms"] > 0
-    scene.render_end()
+    for _ in rps[1:]:
+        scene.render_end()
     with pytest.raises(capi.SptError, match="no frame"):
         scene.render_end()
     per_frame = (rps[0].x_end - rps[0].x_start) * (rps[0].y_end - rps[0].y_start) * 8
-    assert scene.stats()["camera_samples"] - before == 2 * per_frame
+    assert scene.stats()["camera_samples"] - before == len(rps) * per_frame
     for f, (c, w) in zip(films, want):
         c2, w2 = f.download()
         assert np.array_equal(w2, w)
