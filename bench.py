@@ -501,11 +501,11 @@ def main():
 
     # ---- rooflines (algorithmic bytes per unit: SURVEY.md 8d for rays, DESIGN.md 3 for the other kernels)
     peak, peak_src = read_peaks()
-    # ncu evidence of the committed kernels (profiles/r02_ncu_summary_v22.json, written on the GPU box by profiles/tools/ncu_summary.py from
+    # ncu evidence of the committed kernels (profiles/r02_ncu_summary_v27.json, written on the GPU box by profiles/tools/ncu_summary.py from
     # one `ncu --set full --clock-control none` capture of this command's frame): DRAM bytes, issue-slot and pipe utilisation of the
     # bounce-0 launch of every kernel. bench.py cannot run under ncu itself; the capture it quotes is named in the line.
     ncu_all = {}
-    ncu_path = os.path.join(ROOT, "profiles", "r02_ncu_summary_v22.json")
+    ncu_path = os.path.join(ROOT, "profiles", "r02_ncu_summary_v27.json")
     if os.path.exists(ncu_path) and args.workload in (WORKLOAD, "killeroo_path", "killeroo_path30"):
         try:
             ncu_all = json.load(open(ncu_path))
@@ -575,7 +575,7 @@ def main():
         "nodes_per_shadow_ray": nodes_per_any, "prim_tests_per_shadow_ray": prims_per_any,
         "ncu_capture": ncu_all.get("_source"),
         "note": "achieved = algorithmic bytes of the kernel's bounce-0 launch (bytes_per_unit x units_per_launch, DESIGN.md 3) / its CUDA-event time in "
-                "this run; traffic = DRAM bytes ncu measured for the same launch of the same command (profiles/r02_ncu_summary_v22.json); `limiter` says "
+                "this run; traffic = DRAM bytes ncu measured for the same launch of the same command (profiles/r02_ncu_summary_v27.json); `limiter` says "
                 "what actually bounds the kernel - only k_advance / k_addlight are HBM-bound; per-kernel lines in roofline_by_kernel"})
     roofline_by_kernel = {D.K_NAMES[k]: roof(k) for k in unit_bytes if class_launches[k]}
     rays_total = class_rays[D.K_TRACE_PATH] + class_rays[D.K_TRACE_MIS] + class_rays[D.K_TRACE_SHADOW]
