@@ -399,9 +399,11 @@ int spt_render(SptScene *scene, const SptCameraDesc *cam, SptFilm *film, const S
  * no counterpart there): spt_render_begin enqueues the frame and returns; spt_render_end waits for the OLDEST frame begun and
  * finishes its statistics. Up to four frames may be in flight on a scene - begin(k + 1) before end(k) - so that the device goes
  * from one frame to the next without waiting for the host; each stream runs its waves in order, in its own wave buffers
- * (frames into different films, or into one film that is meant to accumulate both). Per-kernel-class times (SptStats::class_ms)
- * are only collected for a frame begun while no other was in flight. Between begin and end only these two calls, spt_get_stats
- * and spt_last_render_ms may be used on the scene. */
+ * (frames into different films, or into one film that is meant to accumulate both).
+ * A frame of up to 2^23 paths begun this way runs as ONE wave (spt_render cuts it into two half-size waves on two streams) and
+ * consecutive frames go to different streams: whole frames, not half frames, are what overlaps on the device.
+ * Per-kernel-class times (SptStats::class_ms) are only collected for a frame begun while no other was in flight. Between begin
+ * and end only these two calls, spt_get_stats and spt_last_render_ms may be used on the scene. */
 int spt_render_begin(SptScene *scene, const SptCameraDesc *cam, SptFilm *film, const SptRenderParams *params);
 int spt_render_end(SptScene *scene);
 
