@@ -536,10 +536,13 @@ def main():
         D.K_TRACE_PATH: "instruction issue at 12-24 of 32 lanes per instruction; the BVH is served by L1/L2 (DRAM 1-10 % of peak even on the 10 M-triangle "
                         "scene: profiles/r02_ncu_trace_synth10m.csv), so the HBM fraction below is algorithmic bytes, not DRAM traffic",
         D.K_SHADE: "instruction latency (51 % of the issue slots busy at 16 warps/SM: 128 registers; 12.2 k SASS instructions of exact fp32/fp64 arithmetic, ~3.8 k executed per vertex)",
-        D.K_ACCUMULATE: "HBM streaming (bounce 0 also instruction issue: 77 % of the slots busy)",
-        D.K_ADVANCE: "HBM streaming (73-75 % of the measured copy bandwidth in DRAM traffic)",
+        D.K_ACCUMULATE: "HBM streaming (bounce 0: 68 % of the measured copy bandwidth in DRAM traffic with 67 % of the issue slots busy; later bounces 84 %)",
+        D.K_ADVANCE: "HBM streaming (76-79 % of the measured copy bandwidth in DRAM traffic)",
         D.K_FILM: "HBM reads of the radiance rows + film atomics",
     }
+
+    # the same in one word per kernel class: "issue" (instruction issue slots), "latency" (dependent instructions at low occupancy), "hbm"
+    LIMITED_BY = {D.K_GEN: "issue", D.K_TRACE_PATH: "issue", D.K_SHADE: "latency", D.K_ACCUMULATE: "hbm", D.K_ADVANCE: "hbm", D.K_FILM: "hbm"}
 
     def roof(k):
         """Two views of a kernel class: over ALL its launches of the profiled frames (share of the step), and its bounce-0 launch alone
@@ -559,7 +562,7 @@ def main():
             f_bytes = per_unit * f_units
         f_ach = f_bytes / (f_ms / 1e3) / 1e9 if f_ms > 0 else 0.0
         nc = ncu_all.get(D.K_NAMES[k]) or {}
-        return {"bound": "hbm", "limiter": LIMITER.get(k), "kernel": D.K_KERNELS[k] + " (" + D.K_NAMES[k] + "), bounce-0 launch",
+        return {"bound": "hbm", "limited_by": LIMITED_BY.get(k), "limiter": LIMITER.get(k), "kernel": D.K_KERNELS[k] + " (" + D.K_NAMES[k] + "), bounce-0 launch",
                 "achieved": f_ach, "peak": peak, "unit": "GB/s", "frac": f_ach / peak,
                 "traffic": nc.get("dram_bytes"), "peak_source": peak_src,
                 "bytes_per_unit": f_bytes / max(f_units, 1), "unit_of_work": unit, "units_per_launch": f_units, "avg_launch_ms": f_ms,
