@@ -258,7 +258,10 @@ def main():
     # N = 1: the film is the library's. N > 1: ONE film per frame buffer lives on rank 0 (spt_film_create there, exported with
     # spt_film_ipc_export); the other ranks open it (spt_film_open_ipc) and their film kernel adds their tile sets' samples
     # straight into it over NVLink - the "gather" is fused into K7, what is left of it is a barrier at the end of the frame.
-    ahead = min(max(args.frames_ahead, 1), 3) if args.frames_ahead else (2 if world > 1 else 1)           # frames enqueued ahead of the one the host waits for
+    # frames enqueued ahead of the one the host waits for: two where a rank's frame is small enough to run as ONE wave (up to 2^23
+    # paths: the library then rotates consecutive frames over its lanes, and three whole frames overlap), else one
+    one_wave = world > 1 and n_samples_total // world <= (1 << 23)
+    ahead = min(max(args.frames_ahead, 1), 3) if args.frames_ahead else (2 if one_wave else 1)
     n_buf = ahead + 2 if world > 1 else 1
     if world == 1:
         films = [capi.Film(fd)]
@@ -332,27 +335,15 @@ def main():
     # barrier k - 1 - BEFORE it enters barrier k; frame k + A + 1, the next to write that buffer, is enqueued on every rank only
     # once barrier k has completed. Every barrier has completed before the closing time stamp. N = 1: one film, the frames add
     # up in it.
-    done = [torch.cuda.Event() for _ in range(args.steps)] if dist is not None else None
-    for j in range(min(ahead, args.steps)):
-        scene.render_begin(films[j % n_buf], rp)
-    for k in range(args.steps):
-        if k + ahead < args.steps:
-            if dist is not None and k >= 1:
-                done[k - 1].synchronize()
-            scene.render_begin(films[(k + ahead) % n_buf], rp)
+    def _end(k):
+        nonlocal render_ms
         scene.render_end()                                # blocks until frame k has drained on this rank
         render_ms += scene.render_ms()
-        if dist is not None:
-            if rank == 0 and k >= 1:
-                done[k - 1].synchronize()
-                films[(k - 1) % n_buf].clear_idle()
-            dist.all_reduce(sync_t)
-            done[k].record()
-    if dist is not None:
-        for k in range(max(args.steps - 2, 0), args.steps):
-            done[k].synchronize()
-        if rank == 0:
-            films[(args.steps - 1) % n_buf].clear_idle()
+
+    multi.pipelined_frames(args.steps, ahead, n_buf, lambda k, b: scene.render_begin(films[b], rp), _end,
+                           clear=lambda b: films[b].clear_idle(), rank=rank, sync_t=sync_t)
+    if dist is not None and rank == 0:
+        films[(args.steps - 1) % n_buf].clear_idle()
     e1.record()
     barrier()
     lanes_used = scene.stats()["lanes_used"]
@@ -595,10 +586,10 @@ def main():
                    "parallelism": "image tile sets (32x32, round-robin) x%d, scene replicated; every rank's film kernel adds its samples straight into ONE film "
                                   "on rank 0 through a peer mapping (NVLink), a NCCL barrier ends the frame" % world,
                    "l2": "per-step wave state (>2 GB) and film are larger than L2; no explicit flush",
-                   "pipelining": "a rank enqueues frames k+1..k+A (spt_render_begin; A = 1 at N = 1, 2 at N > 1) before it waits for frame k "
+                   "pipelining": "a rank enqueues frames k+1..k+A (spt_render_begin; A = %d here: 2 where a rank's frame runs as one wave, else 1) before it waits for frame k "
                                  "(spt_render_end). N > 1: A + 2 film buffers on rank 0; frame k's end-of-frame barrier is waited for before "
                                  "frame k+A+1 is enqueued, rank 0 clears a buffer behind its frame's barrier and before it enters the next "
-                                 "one; every frame's film is complete on rank 0 (every barrier has completed) inside the timed region"},
+                                 "one; every frame's film is complete on rank 0 (every barrier has completed) inside the timed region" % ahead},
         "mrays_per_s": rays_total / prof_steps / (ms_per_step / 1e3) / 1e6 if world == 1 else None,
         "rays_per_sample": rays_total / prof_steps / (n_samples_total / world) if world else None,
         "rays_per_sample_reference": (rays_total + elided) / prof_steps / (n_samples_total / world) if world else None,

@@ -8,7 +8,12 @@ the same sum handles them.
 
 `render_fn(params)` renders this rank's tile set into the film tensor; on GPUs it is capi.Scene.render
 on a film created over the tensor's own storage (spt_film_create_external), so NCCL reduces the very
-buffer K7 accumulated into."""
+buffer K7 accumulated into.
+
+That is the exchange for ranks WITHOUT peer access to one another's memory. On one NVLink host the
+exchange is fused into the film kernel instead: the film lives on rank 0, the other ranks
+open it (spt_film_ipc_export / spt_film_open_ipc) and `pipelined_frames` below is the frame loop around
+it - frames kept in flight over a ring of film buffers, a one-element all-reduce as end-of-frame barrier."""
 import copy
 
 import torch
@@ -94,3 +99,54 @@ def render_distributed(render_fn, film_t, params, rank, world, tile=TILE, exchan
     if exchange is not None:
         return exchange.run(film_t, rank)
     return reduce_film(film_t)
+
+
+def pipelined_frames(n_frames, ahead, n_buf, begin, end, clear=None, rank=0, sync_t=None):
+    """Frame loop of a host that renders frame after frame, `ahead` frames enqueued beyond the one it waits for
+    (spt_render_begin / spt_render_end), on N ranks into a ring of `n_buf` film buffers that live on rank 0.
+
+        begin(k, b)   enqueue this rank's share of frame k into buffer b = k % n_buf   (spt_render_begin)
+        end(k)        wait until this rank's frame k has drained                          (spt_render_end)
+        clear(b)      rank 0 only: hand frame k's complete film on / zero buffer b        (spt_film_clear_idle)
+
+    N > 1 (torch.distributed initialised, sync_t = a one-element tensor on the ranks' device): frame k's end-of-frame barrier
+    is a one-element all-reduce enqueued after end(k) - once it completes, every rank's samples of frame k are in buffer
+    k % n_buf. Rank 0 calls clear((k - 1) % n_buf) - complete since barrier k - 1 - BEFORE it enters barrier k, and every
+    rank enqueues frame k + ahead + 1, the next frame that writes a buffer cleared in step k (n_buf = ahead + 2), only once
+    barrier k has completed. On return every barrier has completed; the last frame's buffer has NOT been cleared.
+    N = 1: no barriers, clear is never called (one film may simply accumulate the frames).
+    Returns the number of barriers waited for."""
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    ahead = max(int(ahead), 1)
+    if multi and n_buf < ahead + 2:
+        raise ValueError("pipelined_frames: %d frames ahead need %d film buffers" % (ahead, ahead + 2))
+
+    def barrier():
+        """Enqueue the end-of-frame barrier; returns the call that waits for it."""
+        if sync_t.is_cuda:
+            dist.all_reduce(sync_t)
+            ev = torch.cuda.Event()
+            ev.record()
+            return ev.synchronize
+        return dist.all_reduce(sync_t, async_op=True).wait
+
+    waits = [None] * n_frames
+    for j in range(min(ahead, n_frames)):
+        begin(j, j % n_buf)
+    for k in range(n_frames):
+        if k + ahead < n_frames:
+            if multi and k >= 1:
+                waits[k - 1]()
+            begin(k + ahead, (k + ahead) % n_buf)
+        end(k)
+        if multi:
+            if rank == 0 and k >= 1:
+                waits[k - 1]()
+                clear((k - 1) % n_buf)
+            waits[k] = barrier()
+    n_waited = 0
+    if multi:
+        for k in range(max(n_frames - 2, 0), n_frames):
+            waits[k]()
+        n_waited = n_frames
+    return n_waited

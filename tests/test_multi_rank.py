@@ -107,3 +107,73 @@ def test_film_exchange_covers_a_wide_filter():
         mine = set(ex.idx[r][:ex.counts[r]].tolist())
         assert touched <= mine, "rank %d wrote %d pixels outside its exchange list" % (r, len(touched - mine))
     assert sum(ex.counts) < 3 * npix
+
+
+def _pipeline_worker(rank, world, port, path, ahead, n_frames):
+    """Two ranks run multi.pipelined_frames over a ring of stand-in film buffers in shared memory (one cell per buffer and
+    rank). begin(k, b) is the EARLIEST moment the device could write frame k into buffer b: the buffer must have been cleared
+    of the frame that used it before. end(k) is the LATEST: the rank's contribution lands there. clear(b) runs on rank 0
+    behind the frame's barrier: every rank's contribution to exactly that frame must be in the buffer."""
+    import random
+    import time
+    from pbrt_v2_spectral_b200 import multi
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n_buf = ahead + 2
+    buf = np.memmap(path, dtype=np.int64, mode="r+", shape=(n_buf, world))
+    rnd = random.Random(17 * rank + ahead)
+    in_flight, cleared, max_in_flight = [], [], 0
+
+    def begin(k, b):
+        nonlocal max_in_flight
+        assert b == k % n_buf
+        assert buf[b, rank] == 0, "frame %d enqueued into buffer %d before it was cleared of frame %d" % (k, b, buf[b, rank] - 1)
+        in_flight.append(k)
+        max_in_flight = max(max_in_flight, len(in_flight))
+        time.sleep(rnd.random() * 1e-3)
+
+    def end(k):
+        assert in_flight.pop(0) == k                # frames end in the order they were begun
+        time.sleep(rnd.random() * (3e-3 if rank else 1e-3))     # rank 1 is the straggler
+        buf[k % n_buf, rank] = k + 1
+
+    def clear(b):
+        assert rank == 0
+        k = len(cleared)                            # buffers are cleared in frame order
+        assert b == k % n_buf
+        assert np.all(buf[b] == k + 1), "buffer %d handed on with %s, expected every rank's frame %d" % (b, buf[b], k)
+        cleared.append(k)
+        buf[b] = 0
+
+    sync_t = torch.zeros(1)
+    waited = multi.pipelined_frames(n_frames, ahead, n_buf, begin, end, clear=clear, rank=rank, sync_t=sync_t)
+    assert waited == n_frames and not in_flight
+    assert max_in_flight == min(ahead + 1, n_frames)
+    if rank == 0:
+        assert cleared == list(range(n_frames - 1))              # the last frame's film is left for the caller
+        assert np.all(buf[(n_frames - 1) % n_buf] == n_frames)   # ... complete
+    with pytest.raises(ValueError):
+        multi.pipelined_frames(4, ahead, ahead + 1, begin, end, clear=clear, rank=rank, sync_t=sync_t)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("ahead", [1, 2, 3])
+def test_pipelined_frames_never_write_an_uncleared_buffer(tmp_path, ahead):
+    """The frame loop bench.py --gpus N runs (frames in flight over a ring of film buffers on rank 0) on two
+    gloo ranks with random delays: no frame is enqueued into a buffer that still holds an earlier frame, every frame's film is
+    complete when rank 0 hands it on, and `ahead` + 1 frames are in flight."""
+    world, n_frames = 2, 24
+    path = str(tmp_path / "films.bin")
+    np.zeros((ahead + 2, world), dtype=np.int64).tofile(path)
+    port = 29950 + (os.getpid() + ahead) % 40
+    mp.spawn(_pipeline_worker, args=(world, port, path, ahead, n_frames), nprocs=world, join=True)
+
+
+def test_pipelined_frames_single_rank_has_no_barriers():
+    from pbrt_v2_spectral_b200 import multi
+    log = []
+    n = multi.pipelined_frames(5, 2, 1, lambda k, b: log.append(("b", k, b)), lambda k: log.append(("e", k)))
+    assert n == 0
+    assert log == [("b", 0, 0), ("b", 1, 0), ("b", 2, 0), ("e", 0), ("b", 3, 0), ("e", 1), ("b", 4, 0), ("e", 2), ("e", 3), ("e", 4)]
