@@ -1,6 +1,7 @@
-"""N > 1 host logic on CPU: two gloo ranks each render their tile set (with the oracle standing in for
-the device kernels, test infrastructure only), the films are summed with dist.reduce, and rank 0 holds
-the single-rank image. Mirrors what bench.py --gpus N does over NCCL."""
+"""N > 1 host logic on CPU, two gloo ranks. (1) The exchange for ranks without peer access (multi.render_distributed):
+each rank renders its tile set (with the oracle standing in for the device kernels, test infrastructure only), the films
+are summed with dist.reduce or the sparse FilmExchange, and rank 0 holds the single-rank image. (2) The frame loop
+bench.py --gpus N runs over NCCL around the peer-mapped film (multi.pipelined_frames), on stand-in film buffers."""
 import os
 import sys
 
